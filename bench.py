@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds/second of the PCM -> MFCC+delta+delta-delta hot path on B200.
+
+Workload (BASELINE.json configs[1]): 4096 synthetic 2 s utterances per GPU, 16 kHz int16, 25/10 ms
+frames, 512-point FFT, 26 mel bands, 13 cepstra + delta + delta-delta (N=2) -> float32 [F,39].
+One "step" = one pass of the hot path (prep kernel + fused kernel) over the whole batch.
+
+  value      device-resident throughput (inputs and outputs in HBM), CUDA events, max over ranks
+  e2e        same metric through the reference-facing host-buffer call (dspfe_mfcc_delta_host):
+             pinned host PCM -> H2D -> kernels -> D2H features, every step
+  roofline   fused kernel alone: algorithmic bytes (2*S + 156*F per utterance) / kernel time,
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the oracle (NumPy restatement of the reference features functions) on the host cores
+
+`--impl reference` times the reference algorithm's CPU port (oracle/) on all host cores instead.
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 via torch.distributed.run (one rank per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "dsp-speech-recognition_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
+
+SR = 16000
+UTT_PER_GPU = 4096
+UTT_SAMPLES = 2 * SR
+FRAME_LEN, FRAME_STEP, NUMCEP, DELTA_N = 400, 160, 13, 2
+METRIC = "audio-sec/sec of MFCC+delta+delta-delta (fused kernel), 4096 x 2 s utterances per B200"
+UNIT = "audio-s/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle port)
+def _oracle_batch(xs):
+    from oracle import ref_features as O
+    for x in xs:
+        O.mfcc_delta39(x, DELTA_N)
+    return len(xs)
+
+
+def cpu_throughput(n_utt, cores):
+    """Times the oracle's mfcc+delta+delta on n_utt synthetic 2 s utterances with `cores` worker processes.
+    Synthesis happens before the clock starts."""
+    import multiprocessing as mp
+    from dspfe import synth
+    xs = [synth.synth_utterance(7000 + i, UTT_SAMPLES) for i in range(min(n_utt, 64))]
+    xs = [xs[i % len(xs)] for i in range(n_utt)]
+    chunks = [xs[i::cores] for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_oracle_batch, [c[:2] for c in chunks])          # warm-up: imports, caches
+        t0 = time.perf_counter()
+        pool.map(_oracle_batch, chunks)
+        dt = time.perf_counter() - t0
+    return n_utt * UTT_SAMPLES / SR / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    # calibrate a bounded sample: about 2 s of wall time per step on this host
+    v1, _ = cpu_throughput(4 * cores, cores)
+    n = int(max(4 * cores, min(4096, (v1 * 2.0) / (UTT_SAMPLES / SR))))
+    n -= n % cores
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_throughput(n, cores)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    sample = f"{n} of the 4096 synthetic 2 s utterances per step, oracle.mfcc_delta39 in {cores} processes"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 4096 x 2 s @16 kHz, 13 MFCC + delta + delta-delta (N=2), bounded sample",
+                   "sample_utterances": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O   # checker / cpu_baseline leg only
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    U, S = UTT_PER_GPU, UTT_SAMPLES
+    lengths = np.full(U, S, dtype=np.int64)
+    pcm, off = synth.synth_batch_torch(lengths, seed0=1000003 * rank, device=dev)
+    off_d = off.to(dev)
+    plan = dspfe.MfccPlan(frame_len=FRAME_LEN, frame_step=FRAME_STEP, numcep=NUMCEP, delta_n=DELTA_N)
+    plan.reserve(U, pcm.numel())
+    rows = int(dspfe.frame_counts(lengths, FRAME_LEN, FRAME_STEP).sum())
+    out = torch.empty((plan.rows_bound(pcm.numel(), U), 3 * NUMCEP), dtype=torch.float32, device=dev)
+    fo = torch.empty(U + 1, dtype=torch.int64, device=dev)
+    audio_s = float(lengths.sum()) / SR
+    alg_bytes = 2.0 * float(lengths.sum()) + 4.0 * 3 * NUMCEP * rows
+
+    def step():
+        plan.mfcc_delta(pcm, off_d, out=out, frame_off=fo)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # parity on the samples the kernel actually sees (first 4 utterances) -- checker only
+    step()
+    torch.cuda.synchronize()
+    par = 0.0
+    got = out[: 4 * 199].cpu().numpy()
+    for u in range(4):
+        ref = O.mfcc_delta39(pcm[u * S:(u + 1) * S].cpu().numpy(), DELTA_N)
+        par = max(par, float(np.max(np.abs(got[u * 199:(u + 1) * 199] - ref) / (1 + np.abs(ref)))))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+
+    # fused kernel alone (second pass, per-launch events on the launching stream)
+    kms = []
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        kms.append((a, b))
+    torch.cuda.synchronize()
+    step_ms = float(np.median([a.elapsed_time(b) for a, b in kms]))
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the host-buffer call: pinned host PCM in, pinned host features out, every step
+    h_pcm = torch.empty(pcm.numel(), dtype=torch.int16).pin_memory()
+    h_pcm.copy_(pcm)
+    h_out = torch.empty((rows, 3 * NUMCEP), dtype=torch.float32).pin_memory()
+    h_pcm_np, h_out_np, off_np = h_pcm.numpy(), h_out.numpy(), off.numpy()
+    for _ in range(2):
+        plan.mfcc_delta_host(h_pcm_np, off_np, out=h_out_np)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        plan.mfcc_delta_host(h_pcm_np, off_np, out=h_out_np)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_ok = bool(np.array_equal(h_out_np[: 199 * 4], got))
+
+    t = torch.tensor([ms_total, step_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, step_ms, e2e_s = [float(v) for v in t.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / args.steps
+    value = world * audio_s / (ms_per_step * 1e-3)
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    info = plan.info()
+    cores = len(os.sched_getaffinity(0))
+    cpu = None
+    if world == 1:
+        n = 16 * cores
+        v, dt = cpu_throughput(n, cores)
+        if dt < 3.0:
+            n = int(n * 6.0 / max(dt, 1e-3)); n -= n % cores
+            v, dt = cpu_throughput(n, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} synthetic 2 s utterances of the same workload, oracle.mfcc_delta39 (NumPy float64) in {cores} processes, {dt:.1f} s"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 4096 x 2 s utterances per GPU @16 kHz int16, 25/10 ms frames, nfft 512, 26 mel, "
+                               "13 MFCC + delta + delta-delta (N=2) -> float32 [F,39]",
+                   "utterances_per_gpu": U, "samples_per_utterance": S, "frames_per_gpu": rows,
+                   "l2_policy": "working set per step (262 MB in + 127 MB out) exceeds the 126 MB L2",
+                   "kernel": info, "parity_max_err_vs_oracle": par, "tolerance": 1e-4},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "one step = prep kernel (<1% of the step) + fused kernel; algorithmic bytes = 2*S + 156*F per "
+                             "utterance; the kernel is FP32-pipe/shared-memory bound, see DESIGN.md",
+                     "alg_bytes_per_launch": alg_bytes, "launch_ms": step_ms},
+        "e2e": {"value": world * audio_s / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(pcm.numel() * 2 + (U + 1) * 8),
+                "d2h_bytes_per_step": int(rows * 3 * NUMCEP * 4), "ms_per_step": e2e_s * 1e3, "timer": "host wall clock around the blocking host-buffer call, max over ranks",
+                "matches_device_path": e2e_ok},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,310 @@
+// libdspfe.so — C ABI (include/dspfe.h) over the sm_100a kernels.  No CPU fallback anywhere in
+// this file: every compute entry point launches CUDA kernels or fails with DSPFE_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dspfe.h"
+#include "mfcc_kernel.cuh"
+#include "mfcc_tables.h"
+#include "prep_kernel.cuh"
+
+using namespace dspfe;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(DSPFE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+template <bool HAS_WIN>
+__global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __grid_constant__ MfccParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    mfcc_cta<HAS_WIN>(p, smem);
+}
+
+MfccConfig to_config(const dspfe_mfcc_params& q) {
+    MfccConfig c;
+    c.samplerate = q.samplerate; c.frame_len = q.frame_len; c.frame_step = q.frame_step; c.nfft = q.nfft;
+    c.nfilt = q.nfilt; c.numcep = q.numcep; c.ceplifter = q.ceplifter; c.append_energy = q.append_energy;
+    c.delta_n = q.delta_n; c.seg_frames = q.seg_frames > 0 ? q.seg_frames : 256;
+    c.preemph = q.preemph; c.lowfreq = q.lowfreq; c.highfreq = q.highfreq;
+    if (q.window) c.window.assign(q.window, q.window + (q.frame_len > 0 ? q.frame_len : 0));
+    return c;
+}
+
+// Per-stream scratch for one in-flight batch.
+struct Workspace {
+    int64_t cap_utt = 0, cap_tiles = 0;
+    int64_t* seg_start = nullptr; int32_t* seg_len = nullptr; int64_t* frame_off = nullptr;
+    int32_t* tile_off = nullptr; Tile* tiles = nullptr; int32_t* ntiles = nullptr;
+    int ensure(int64_t n_utt, int64_t n_tiles) {
+        if (n_utt > cap_utt) {
+            cudaFree(seg_start); cudaFree(seg_len); cudaFree(frame_off); cudaFree(tile_off);
+            seg_start = nullptr; seg_len = nullptr; frame_off = nullptr; tile_off = nullptr; cap_utt = 0;
+            CUDA_TRY(cudaMalloc(&seg_start, (n_utt + 1) * sizeof(int64_t)));
+            CUDA_TRY(cudaMalloc(&seg_len, (n_utt + 1) * sizeof(int32_t)));
+            CUDA_TRY(cudaMalloc(&frame_off, (n_utt + 1) * sizeof(int64_t)));
+            CUDA_TRY(cudaMalloc(&tile_off, (n_utt + 1) * sizeof(int32_t)));
+            cap_utt = n_utt;
+        }
+        if (n_tiles > cap_tiles) {
+            cudaFree(tiles); tiles = nullptr; cap_tiles = 0;
+            CUDA_TRY(cudaMalloc(&tiles, n_tiles * sizeof(Tile)));
+            cap_tiles = n_tiles;
+        }
+        if (!ntiles) CUDA_TRY(cudaMalloc(&ntiles, sizeof(int32_t)));
+        return DSPFE_OK;
+    }
+    void release() {
+        cudaFree(seg_start); cudaFree(seg_len); cudaFree(frame_off); cudaFree(tile_off); cudaFree(tiles); cudaFree(ntiles);
+        *this = Workspace();
+    }
+};
+
+constexpr int kSlots = 3;
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    Workspace ws;
+    int16_t* d_pcm = nullptr; int64_t cap_samples = 0;
+    int64_t* d_off = nullptr; int64_t* h_off = nullptr; int64_t cap_utt = 0;  // h_off pinned
+    float* d_out = nullptr; int64_t cap_rows = 0;
+    int64_t* d_frame_off = nullptr;
+};
+
+}  // namespace
+
+struct dspfe_plan {
+    MfccConfig cfg;
+    MfccParams layout;          // scalars + offsets filled by build_mfcc_tables; pointers filled per call
+    float* d_tables = nullptr;
+    bool has_win = false;
+    Workspace ws;
+    HostSlot slots[kSlots];
+    int width = 0;              // 3 * numcep
+};
+
+namespace {
+
+int launch_mfcc(dspfe_plan* pl, Workspace& ws, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets,
+                const int32_t* d_trim, int32_t n_utt, float* d_out, int64_t* d_frame_off, cudaStream_t st) {
+    const int64_t max_tiles = mfcc_max_tiles(total_samples, n_utt, pl->cfg.frame_step, pl->cfg.seg_frames);
+    if (max_tiles > 0x7fffffff) return fail(DSPFE_ERR_INVALID_ARG, "batch too large for one launch");
+    int rc = ws.ensure(n_utt, max_tiles);
+    if (rc) return rc;
+    PrepParams pp;
+    pp.offsets = d_offsets; pp.trim = d_trim; pp.n_utt = n_utt;
+    pp.frame_len = pl->cfg.frame_len; pp.frame_step = pl->cfg.frame_step; pp.seg_frames = pl->cfg.seg_frames;
+    pp.seg_start = ws.seg_start; pp.seg_len = ws.seg_len; pp.frame_off = d_frame_off ? d_frame_off : ws.frame_off;
+    pp.tile_off = ws.tile_off; pp.tiles = ws.tiles; pp.ntiles = ws.ntiles; pp.max_tiles = (int)max_tiles;
+    prep_kernel<<<1, kPrepThreads, 0, st>>>(pp);
+    CUDA_TRY(cudaGetLastError());
+
+    MfccParams mp = pl->layout;
+    mp.pcm = d_pcm; mp.total_samples = total_samples; mp.seg_start = ws.seg_start; mp.seg_len = ws.seg_len;
+    mp.frame_off = pp.frame_off; mp.tiles = ws.tiles; mp.ntiles = ws.ntiles; mp.tables = pl->d_tables; mp.out = d_out;
+    if (pl->has_win) mfcc_delta_kernel<true><<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
+    else mfcc_delta_kernel<false><<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
+    CUDA_TRY(cudaGetLastError());
+    return DSPFE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dspfe_version(void) { return "dspfe 0.1 (sm_100a)"; }
+const char* dspfe_last_error(void) { return g_err.c_str(); }
+
+void dspfe_mfcc_params_default(dspfe_mfcc_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->samplerate = 16000; p->frame_len = 400; p->frame_step = 160; p->nfft = 512; p->nfilt = 26; p->numcep = 13;
+    p->ceplifter = 22; p->append_energy = 1; p->delta_n = 2; p->seg_frames = 0; p->preemph = 0.97;
+    p->lowfreq = 0.0; p->highfreq = 0.0; p->window = nullptr;
+}
+
+int64_t dspfe_num_frames(int64_t n_samples, int32_t frame_len, int32_t frame_step) {
+    if (frame_len < 1 || frame_step < 1) return -1;
+    return num_frames(n_samples, frame_len, frame_step);
+}
+
+int dspfe_mfcc_tables_host(const dspfe_mfcc_params* p, float* blob, int32_t cap, int32_t* n, double* mel_edges) {
+    if (!p || !n) return fail(DSPFE_ERR_INVALID_ARG, "null argument");
+    MfccConfig c = to_config(*p);
+    MfccParams lay{};
+    std::string err;
+    std::vector<float> b = build_mfcc_tables(c, lay, err);
+    if (!err.empty()) return fail(DSPFE_ERR_UNSUPPORTED, err);
+    *n = (int32_t)b.size();
+    if (blob) {
+        if (cap < *n) return fail(DSPFE_ERR_INVALID_ARG, "blob capacity too small");
+        std::memcpy(blob, b.data(), b.size() * sizeof(float));
+    }
+    if (mel_edges) {
+        std::vector<double> e = mel_bin_edges(c);
+        std::memcpy(mel_edges, e.data(), e.size() * sizeof(double));
+    }
+    return DSPFE_OK;
+}
+
+int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
+    if (!p || !plan) return fail(DSPFE_ERR_INVALID_ARG, "null argument");
+    *plan = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DSPFE_ERR_CUDA, "no CUDA device: libdspfe has no CPU fallback");
+    dspfe_plan* pl = new (std::nothrow) dspfe_plan();
+    if (!pl) return fail(DSPFE_ERR_NOMEM, "out of host memory");
+    pl->cfg = to_config(*p);
+    std::memset(&pl->layout, 0, sizeof(pl->layout));
+    std::string err;
+    std::vector<float> blob = build_mfcc_tables(pl->cfg, pl->layout, err);
+    if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
+    pl->has_win = !pl->cfg.window.empty();
+    pl->width = 3 * pl->cfg.numcep;
+    cudaError_t e = cudaMalloc(&pl->d_tables, blob.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_delta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout.sm_total);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_delta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout.sm_total);
+    if (e != cudaSuccess) { cudaFree(pl->d_tables); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
+    *plan = pl;
+    return DSPFE_OK;
+}
+
+int dspfe_plan_reserve(dspfe_plan* pl, int64_t max_utt, int64_t max_total_samples) {
+    if (!pl || max_utt < 0 || max_total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    return pl->ws.ensure(max_utt, mfcc_max_tiles(max_total_samples, max_utt, pl->cfg.frame_step, pl->cfg.seg_frames));
+}
+
+void dspfe_plan_destroy(dspfe_plan* pl) {
+    if (!pl) return;
+    pl->ws.release();
+    for (auto& s : pl->slots) {
+        s.ws.release();
+        cudaFree(s.d_pcm); cudaFree(s.d_off); cudaFree(s.d_out); cudaFree(s.d_frame_off);
+        if (s.h_off) cudaFreeHost(s.h_off);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(pl->d_tables);
+    delete pl;
+}
+
+int dspfe_plan_info(const dspfe_plan* pl, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* regs_per_thread) {
+    if (!pl) return fail(DSPFE_ERR_INVALID_ARG, "null plan");
+    cudaFuncAttributes fa;
+    int nb = 0;
+    if (pl->has_win) {
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_delta_kernel<true>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_delta_kernel<true>, kMfccThreads, pl->layout.sm_total));
+    } else {
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_delta_kernel<false>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_delta_kernel<false>, kMfccThreads, pl->layout.sm_total));
+    }
+    if (smem_bytes) *smem_bytes = pl->layout.sm_total;
+    if (ctas_per_sm) *ctas_per_sm = nb;
+    if (regs_per_thread) *regs_per_thread = fa.numRegs;
+    return DSPFE_OK;
+}
+
+int64_t dspfe_rows_bound(const dspfe_plan* pl, int64_t total_samples, int64_t n_utt) {
+    if (!pl) return -1;
+    return total_samples / pl->cfg.frame_step + n_utt;
+}
+
+int dspfe_mfcc_delta(dspfe_plan* pl, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets,
+                     const int32_t* d_trim, int32_t n_utt, float* d_out, int64_t max_rows, int64_t* d_frame_off,
+                     void* stream) {
+    if (!pl || !d_offsets || !d_out || n_utt < 0 || total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    if (!d_pcm && total_samples > 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm is null");
+    if (((uintptr_t)d_pcm & 15) != 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm must be 16-byte aligned");
+    if (max_rows < dspfe_rows_bound(pl, total_samples, n_utt))
+        return fail(DSPFE_ERR_INVALID_ARG, "d_out capacity (max_rows) is below dspfe_rows_bound()");
+    return launch_mfcc(pl, pl->ws, d_pcm, total_samples, d_offsets, d_trim, n_utt, d_out, d_frame_off, (cudaStream_t)stream);
+}
+
+int dspfe_mfcc_delta_host(dspfe_plan* pl, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt, float* h_out,
+                          int64_t* h_frame_off) {
+    if (!pl || !h_offsets || !h_out || n_utt < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    const int flen = pl->cfg.frame_len, fstep = pl->cfg.frame_step, width = pl->width;
+    // slabs of consecutive utterances: <= kSlabSamples samples each (one oversized utterance = its own slab)
+    const int64_t kSlabSamples = 8ll << 20;
+    int64_t row = 0;
+    int slab = 0;
+    int32_t u = 0;
+    while (u < n_utt) {
+        int32_t u_end = u; int64_t samples = 0, rows = 0;
+        while (u_end < n_utt) {
+            const int64_t len = h_offsets[u_end + 1] - h_offsets[u_end];
+            if (len < 0) return fail(DSPFE_ERR_INVALID_ARG, "offsets must be non-decreasing");
+            if (u_end > u && samples + len > kSlabSamples) break;
+            samples += len; rows += num_frames(len, flen, fstep);
+            if (h_frame_off) h_frame_off[u_end] = row + rows - num_frames(len, flen, fstep);
+            ++u_end;
+        }
+        const int32_t nu = u_end - u;
+        HostSlot& s = pl->slots[slab % kSlots];
+        if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));  // the slot's previous slab has fully drained
+        if (samples + 8 > s.cap_samples) {
+            cudaFree(s.d_pcm); s.d_pcm = nullptr; s.cap_samples = 0;
+            const int64_t cap = std::max<int64_t>(samples + 8, kSlabSamples + 8);
+            CUDA_TRY(cudaMalloc(&s.d_pcm, cap * sizeof(int16_t)));
+            s.cap_samples = cap;
+        }
+        if (nu + 1 > s.cap_utt) {
+            cudaFree(s.d_off); cudaFree(s.d_frame_off); if (s.h_off) cudaFreeHost(s.h_off);
+            s.d_off = nullptr; s.d_frame_off = nullptr; s.h_off = nullptr; s.cap_utt = 0;
+            const int64_t cap = std::max<int64_t>(nu + 1, 4096);
+            CUDA_TRY(cudaMalloc(&s.d_off, cap * sizeof(int64_t)));
+            CUDA_TRY(cudaMalloc(&s.d_frame_off, cap * sizeof(int64_t)));
+            CUDA_TRY(cudaHostAlloc(&s.h_off, cap * sizeof(int64_t), cudaHostAllocDefault));
+            s.cap_utt = cap;
+        }
+        const int64_t rows_bound = samples / fstep + nu;
+        if (rows_bound > s.cap_rows) {
+            cudaFree(s.d_out); s.d_out = nullptr; s.cap_rows = 0;
+            const int64_t cap = std::max<int64_t>(rows_bound, kSlabSamples / fstep + 4096);
+            CUDA_TRY(cudaMalloc(&s.d_out, cap * width * sizeof(float)));
+            s.cap_rows = cap;
+        }
+        const int64_t base = h_offsets[u];
+        for (int32_t i = 0; i <= nu; ++i) s.h_off[i] = h_offsets[u + i] - base;
+        if (samples > 0)
+            CUDA_TRY(cudaMemcpyAsync(s.d_pcm, h_pcm + base, samples * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.d_off, s.h_off, (nu + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        int rc = launch_mfcc(pl, s.ws, s.d_pcm, samples, s.d_off, nullptr, nu, s.d_out, s.d_frame_off, s.stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_out + row * width, s.d_out, rows * width * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        row += rows;
+        u = u_end;
+        ++slab;
+    }
+    if (h_frame_off) h_frame_off[n_utt] = row;
+    for (auto& s : pl->slots)
+        if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return DSPFE_OK;
+}
+
+int dspfe_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault));
+    return DSPFE_OK;
+}
+
+int dspfe_host_free(void* p) {
+    CUDA_TRY(cudaFreeHost(p));
+    return DSPFE_OK;
+}
+
+}  // extern "C"

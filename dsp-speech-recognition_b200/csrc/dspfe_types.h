@@ -1,0 +1,62 @@
+// Plain-data parameter blocks shared by host code, the CUDA kernels and the test emulator.
+#pragma once
+#include <stdint.h>
+
+namespace dspfe {
+
+constexpr int kNfft = 512;            // real FFT length of the MFCC kernel (reference default, base.py:9)
+constexpr int kBins = kNfft / 2 + 1;  // 257
+constexpr int kGroupLanes = 16;       // lanes that cooperate on one frame pair
+constexpr int kMaxNfilt = 40;
+constexpr int kMaxNumcep = 16;
+constexpr int kMaxDeltaN = 4;
+constexpr int kMaxRanges = kMaxNfilt + 3;
+constexpr int kMaxTasks = 6;          // mel ranges per lane
+constexpr int kScratchUnits = 272;    // 8-byte units per group: 16x17 transpose tile, >= 257 power bins
+constexpr int kMfccThreads = 128;     // 8 groups -> 16 frames per pass of the chunk loop
+constexpr int kMfccGroups = kMfccThreads / kGroupLanes;
+constexpr int kFramesPerPass = 2 * kMfccGroups;
+
+struct Tile { int utt, f0, nf, pad; };  // output frames [f0, f0+nf) of utterance utt
+
+struct MfccParams {
+    // inputs (device pointers)
+    const int16_t* pcm;         // packed ragged PCM, base 16-byte aligned
+    int64_t total_samples;      // samples in pcm
+    const int64_t* seg_start;   // [U] first sample of each (trimmed) utterance inside pcm
+    const int32_t* seg_len;     // [U] samples
+    const int64_t* frame_off;   // [U+1] output row of each utterance's frame 0
+    const Tile* tiles;          // tile table written by the prep kernel
+    const int32_t* ntiles;      // number of valid tiles (device scalar)
+    const float* tables;        // constant tables blob (see MfccTables)
+    float* out;                 // [F_total, 3*numcep]
+    // dims
+    int frame_len, frame_step, nfilt, numcep, delta_n, seg_frames, nrange, append_energy;
+    float preemph, delta_scale, pow_scale;
+    // table blob offsets, in floats
+    int o_twa, o_twp, o_melw, o_rng, o_task, o_dct, o_win, dct_stride, tbl_floats;
+    // shared-memory carve-up, in bytes
+    int sm_mbar, sm_scratch, sm_mfcc, sm_fbuf, sm_raw, sm_total;
+    int fbuf_floats;            // (kFramesPerPass-1)*step + frame_len
+};
+
+struct PrepParams {
+    const int64_t* offsets;     // [U+1] packed utterance boundaries (samples)
+    const int32_t* trim;        // optional [U,2] (left,right) sample indices from the endpoint kernel, or null
+    int n_utt;
+    int frame_len, frame_step, seg_frames;
+    int64_t* seg_start; int32_t* seg_len; int64_t* frame_off; int32_t* tile_off;
+    Tile* tiles; int32_t* ntiles; int max_tiles;
+};
+
+// frame count rule of framesig (reference sigproc.py:79-82)
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+int64_t num_frames(int64_t slen, int frame_len, int frame_step) {
+    if (slen <= frame_len) return 1;
+    return 1 + (slen - frame_len + frame_step - 1) / frame_step;
+}
+
+}  // namespace dspfe

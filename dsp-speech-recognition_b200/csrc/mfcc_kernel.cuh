@@ -1,0 +1,368 @@
+// K1: fused MFCC + delta + delta-delta over a ragged batch (sm_100a).
+//
+// Replaces, in one pass over packed int16 PCM, the reference chain
+//   preemphasis (sigproc.py:178) -> framesig (sigproc.py:66) -> powspec (sigproc.py:151) ->
+//   get_filterbanks/dot (base.py:28-29) -> log -> dct(ortho) (base.py:12-13) -> lifter (base.py:60)
+//   -> energy substitution (base.py:15) -> delta, delta (base.py:70; model.py:76-77).
+//
+// Work decomposition
+//   * one CTA (128 threads) per tile = up to seg_frames consecutive output frames of one utterance,
+//     plus 2N halo frames either side (only when an utterance is split into several tiles);
+//   * the CTA streams the tile's PCM in chunks of 16 frames: a 1-D bulk async copy (TMA engine,
+//     cp.async.bulk + mbarrier) lands raw int16 in shared memory while the previous chunk computes;
+//   * a conversion pass turns the chunk into pre-emphasised fp32 once (frames overlap 2.5x);
+//   * each 16-lane group owns a PAIR of frames carried in the two halves of packed-FP32 registers
+//     (FADD2/FMUL2/FFMA2): 512-point real FFT as a 256-point complex FFT (radix-16 x radix-16, one
+//     shared-memory transpose) + split post-pass done pairwise (k, 256-k) with 16-lane shuffles,
+//     power spectrum -> shared, mel as range sums (each bin read once), log, DCT*lifter;
+//   * MFCC rows stay in shared memory for the whole tile; the epilogue computes delta (edge clamp on
+//     the utterance), delta-delta (edge clamp on the delta array, Appendix A-5) and writes [F,3*numcep]
+//     rows with coalesced stores.
+#pragma once
+#include "dspfe_types.h"
+#include "simt.h"
+
+namespace dspfe {
+
+struct cpx2 { float2 re, im; };  // one complex value for each of the two frames of a pair
+
+DEVFN cpx2 cadd(cpx2 a, cpx2 b) { cpx2 r; r.re = f2add(a.re, b.re); r.im = f2add(a.im, b.im); return r; }
+DEVFN cpx2 csub(cpx2 a, cpx2 b) { cpx2 r; r.re = f2sub(a.re, b.re); r.im = f2sub(a.im, b.im); return r; }
+// a * (wr + i*wi), scalar twiddle shared by both frames
+DEVFN cpx2 cmuls(cpx2 a, float wr, float wi) {
+    cpx2 r;
+    r.re = f2fmas(a.re, wr, f2muls(a.im, -wi));
+    r.im = f2fmas(a.re, wi, f2muls(a.im, wr));
+    return r;
+}
+DEVFN cpx2 cmul_negi(cpx2 a) { cpx2 r; r.re = a.im; r.im = f2neg(a.re); return r; }  // a * (-i)
+
+// forward 4-point DFT (W4 = -i)
+DEVFN void dft4(cpx2& a, cpx2& b, cpx2& c, cpx2& d) {
+    cpx2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = cmul_negi(csub(b, d));
+    a = cadd(t0, t2); c = csub(t0, t2); b = cadd(t1, t3); d = csub(t1, t3);
+}
+
+// forward 16-point DFT in registers, natural order in and out: X[k] = sum_n x[n] W16^{nk}
+DEVFN void dft16(cpx2 (&x)[16]) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+    // layer 1: for each n_b, DFT4 over n_a of x[4*n_a + n_b]; result k_a left at x[4*k_a + n_b]
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) dft4(x[nb], x[4 + nb], x[8 + nb], x[12 + nb]);
+    // twiddle W16^{n_b * k_a}
+    x[5] = cmuls(x[5], c1, -s1);                                   // W^1
+    { cpx2 t = x[6]; x[6].re = f2muls(f2add(t.re, t.im), r2); x[6].im = f2muls(f2sub(t.im, t.re), r2); }   // W^2
+    x[7] = cmuls(x[7], s1, -c1);                                   // W^3
+    { cpx2 t = x[9]; x[9].re = f2muls(f2add(t.re, t.im), r2); x[9].im = f2muls(f2sub(t.im, t.re), r2); }   // W^2
+    x[10] = cmul_negi(x[10]);                                      // W^4
+    { cpx2 t = x[11]; x[11].re = f2muls(f2sub(t.im, t.re), r2); x[11].im = f2muls(f2add(t.re, t.im), -r2); }  // W^6
+    x[13] = cmuls(x[13], s1, -c1);                                 // W^3
+    { cpx2 t = x[14]; x[14].re = f2muls(f2sub(t.im, t.re), r2); x[14].im = f2muls(f2add(t.re, t.im), -r2); }  // W^6
+    x[15] = cmuls(x[15], -c1, s1);                                 // W^9
+    // layer 2: for each k_a, DFT4 over n_b of x[4*k_a + n_b]; output k_b is X[k_a + 4*k_b]
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) dft4(x[4 * ka], x[4 * ka + 1], x[4 * ka + 2], x[4 * ka + 3]);
+    // x[4*k_a + k_b] now holds X[k_a + 4*k_b]: transpose the 4x4 register tile (pure renaming)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) { cpx2 t = x[4 * a + b]; x[4 * a + b] = x[4 * b + a]; x[4 * b + a] = t; }
+}
+
+struct MfccSmem {
+    float* tables;
+    simt::mbar_t* mbar;
+    float2* scratch;   // per group: kScratchUnits float2
+    float* mfcc;       // [(seg_frames + 4N)][numcep]
+    float* fbuf;       // pre-emphasised fp32 samples of the current chunk
+    int16_t* raw;      // raw PCM chunk (bulk-copy destination)
+};
+
+struct ChunkGeom {
+    int64_t a0s;        // packed-buffer sample index that lands at raw[0] (multiple of 8)
+    int64_t bulk_src;   // == a0s
+    int bulk_bytes;     // multiple of 16, may be 0
+    int64_t tail_lo, tail_hi;  // packed sample range loaded with plain loads
+    int64_t s0;         // utterance sample index of fbuf[0]
+};
+
+DEVFN ChunkGeom chunk_geom(const MfccParams& p, int64_t start, int S, int frame0) {
+    ChunkGeom g;
+    g.s0 = (int64_t)frame0 * p.frame_step;
+    int64_t s_first = g.s0 > 0 ? g.s0 - 1 : 0;
+    int64_t s_last = g.s0 + p.fbuf_floats;
+    if (s_last > S) s_last = S;
+    if (s_last < s_first) s_last = s_first;
+    int64_t p_first = start + s_first, p_last = start + s_last;
+    g.a0s = p_first & ~(int64_t)7;
+    int64_t a1s = (p_last + 7) & ~(int64_t)7;
+    int64_t lim = p.total_samples & ~(int64_t)7;
+    if (a1s > lim) a1s = lim;
+    if (a1s < g.a0s) a1s = g.a0s;
+    g.bulk_src = g.a0s;
+    g.bulk_bytes = (int)(a1s - g.a0s) * 2;
+    g.tail_lo = a1s > p_first ? a1s : p_first;
+    g.tail_hi = p_last;
+    return g;
+}
+
+template <bool HAS_WIN>
+DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
+    const int tid = simt::tid();
+    const int lane = tid & 15;
+    const int grp = tid >> 4;
+    const int tile_id = simt::bid();
+    if (tile_id >= *p.ntiles) return;
+
+    MfccSmem sm;
+    sm.tables = reinterpret_cast<float*>(smem_raw);
+    sm.mbar = reinterpret_cast<simt::mbar_t*>(smem_raw + p.sm_mbar);
+    sm.scratch = reinterpret_cast<float2*>(smem_raw + p.sm_scratch);
+    sm.mfcc = reinterpret_cast<float*>(smem_raw + p.sm_mfcc);
+    sm.fbuf = reinterpret_cast<float*>(smem_raw + p.sm_fbuf);
+    sm.raw = reinterpret_cast<int16_t*>(smem_raw + p.sm_raw);
+
+    const Tile tile = p.tiles[tile_id];
+    const int u = tile.utt;
+    const int64_t start = p.seg_start[u];
+    const int S = p.seg_len[u];
+    const int64_t row0 = p.frame_off[u];
+    const int F = (int)(p.frame_off[u + 1] - row0);
+    const int N = p.delta_n;
+    const int numcep = p.numcep;
+    const int v_lo = tile.f0 - 2 * N > 0 ? tile.f0 - 2 * N : 0;
+    const int v_hi = tile.f0 + tile.nf - 1 + 2 * N < F - 1 ? tile.f0 + tile.nf - 1 + 2 * N : F - 1;
+    const int nchunks = (v_hi - v_lo + kFramesPerPass) / kFramesPerPass;
+
+    // ---- constant tables -> shared, mbarrier init, first chunk in flight
+    for (int i = tid; i < p.tbl_floats; i += kMfccThreads) sm.tables[i] = p.tables[i];
+    if (tid == 0) { simt::mbar_init(sm.mbar, 1); simt::fence_mbar_init(); }
+    simt::cta_sync();
+
+    const float2* twa = reinterpret_cast<const float2*>(sm.tables + p.o_twa);
+    const float2* twp = reinterpret_cast<const float2*>(sm.tables + p.o_twp);
+    const float2* melw = reinterpret_cast<const float2*>(sm.tables + p.o_melw);
+    const int* rng = reinterpret_cast<const int*>(sm.tables + p.o_rng);
+    const int* task = reinterpret_cast<const int*>(sm.tables + p.o_task);
+    const float* dct = sm.tables + p.o_dct;
+    const float* win = sm.tables + p.o_win;
+    float2* scr = sm.scratch + grp * kScratchUnits;
+
+    auto issue_chunk = [&](int c) {
+        ChunkGeom g = chunk_geom(p, start, S, v_lo + c * kFramesPerPass);
+        if (tid == 0 && g.bulk_bytes > 0) {
+            simt::fence_proxy_async();
+            simt::mbar_expect_tx(sm.mbar, (uint32_t)g.bulk_bytes);
+            simt::bulk_g2s(sm.raw, p.pcm + g.bulk_src, (uint32_t)g.bulk_bytes, sm.mbar);
+        }
+        for (int64_t i = g.tail_lo + tid; i < g.tail_hi; i += kMfccThreads) sm.raw[i - g.a0s] = p.pcm[i];
+    };
+    issue_chunk(0);
+
+    uint32_t parity = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int frame0 = v_lo + c * kFramesPerPass;
+        const ChunkGeom g = chunk_geom(p, start, S, frame0);
+        if (g.bulk_bytes > 0) { simt::mbar_wait(sm.mbar, parity); parity ^= 1; }
+        if (c == 0) simt::cta_sync();  // chunk-0 tail stores -> visible (later chunks: the loop-end barrier)
+
+        // ---- raw int16 -> pre-emphasised fp32 (reference sigproc.py:185; zero padding after it, :84-87)
+        {
+            const int64_t base = start - g.a0s + g.s0;  // raw index of fbuf[0]
+            for (int i = tid; i < p.fbuf_floats; i += kMfccThreads) {
+                const int64_t s = g.s0 + i;
+                float y = 0.f;
+                if (s < S) {
+                    const float x = (float)sm.raw[base + i];
+                    const float xp = s > 0 ? (float)sm.raw[base + i - 1] : 0.f;
+                    y = dsp_fmaf(-p.preemph, xp, x);
+                }
+                sm.fbuf[i] = y;
+            }
+        }
+        simt::cta_sync();
+        if (c + 1 < nchunks) issue_chunk(c + 1);  // raw is free again: overlap the next load with the FFTs
+
+        // ---- one frame pair per 16-lane group
+        const int vA = frame0 + 2 * grp;
+        if (vA <= v_hi) {
+            cpx2 x[16];
+            {
+                const float* fa = sm.fbuf + (2 * grp) * p.frame_step;
+                const float* fb = fa + p.frame_step;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const int i0 = 2 * (16 * n1 + lane);
+                    float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+                    if (i0 < p.frame_len) { ar = fa[i0]; br = fb[i0]; }
+                    if (i0 + 1 < p.frame_len) { ai = fa[i0 + 1]; bi = fb[i0 + 1]; }
+                    if (HAS_WIN) {
+                        const float w0 = i0 < p.frame_len ? win[i0] : 0.f;
+                        const float w1 = i0 + 1 < p.frame_len ? win[i0 + 1] : 0.f;
+                        ar *= w0; br *= w0; ai *= w1; bi *= w1;
+                    }
+                    x[n1].re = make_float2(ar, br);
+                    x[n1].im = make_float2(ai, bi);
+                }
+            }
+            // stage 1: DFT over n1 (registers); lane = n2
+            dft16(x);
+            // twiddle W256^{n2*k1}
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) { const float2 w = twa[k1 * 16 + lane]; x[k1] = cmuls(x[k1], w.x, w.y); }
+            // transpose through shared: (k1, n2) -> lane k1, register n2; real parts then imaginary parts
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) scr[k1 * 17 + lane] = x[k1].re;
+            simt::group_sync();
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) x[n2].re = scr[lane * 17 + n2];
+            simt::group_sync();
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) scr[k1 * 17 + lane] = x[k1].im;
+            simt::group_sync();
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) x[n2].im = scr[lane * 17 + n2];
+            simt::group_sync();
+            // stage 2: DFT over n2; lane = k1, register k2 holds Z[k1 + 16*k2]
+            dft16(x);
+
+            // ---- real-FFT split, pairwise: bins k = lane + 16 r (r < 8) and 256 - k share one butterfly.
+            // partner Z[(256-k) mod 256] lives in lane (16-lane)&15, register 15-r (lane 0: register (16-r)&15).
+            const int src = (16 - lane) & 15;
+            const float sc = p.pow_scale;  // 1 / (4 * NFFT)
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                if (r == 8 && lane != 0) break;  // lane 0 also owns the self-paired bin 128
+                cpx2 a = x[r], b;
+                if (r < 8) {
+                    b.re.x = simt::shfl16(x[15 - r].re.x, src); b.re.y = simt::shfl16(x[15 - r].re.y, src);
+                    b.im.x = simt::shfl16(x[15 - r].im.x, src); b.im.y = simt::shfl16(x[15 - r].im.y, src);
+                    if (lane == 0) b = x[(16 - r) & 15];
+                } else {
+                    b = x[8];
+                }
+                // s = a + conj(b), d = a - conj(b); X[k] = (s + W^k * (-i d)) / 2, X[256-k] = conj(s - W^k * (-i d)) / 2
+                const float2 sre = f2add(a.re, b.re), sim = f2sub(a.im, b.im);
+                const float2 dre = f2sub(a.re, b.re), dim = f2add(a.im, b.im);
+                const float2 w = twp[r * 16 + lane];  // W512^k
+                // t = W^k * (d.im, -d.re)
+                const float2 tre = f2fmas(dim, w.x, f2muls(dre, w.y));
+                const float2 tim = f2fmas(dim, w.y, f2muls(dre, -w.x));
+                // square X[k] = s + t and X[256-k] = conj(s - t) separately: forming |s|^2+|t|^2 +- 2Re(s conj t)
+                // would cancel catastrophically for the weaker bin of the pair
+                const float2 are = f2add(sre, tre), aim = f2add(sim, tim);
+                const float2 bre = f2sub(sre, tre), bim = f2sub(sim, tim);
+                const float2 pa = f2muls(f2fma(aim, aim, f2mul(are, are)), sc);
+                const float2 pb = f2muls(f2fma(bim, bim, f2mul(bre, bre)), sc);
+                const int k = lane + 16 * r;
+                // the stage-2 reads of scr are complete (group_sync above); P aliases the transpose tile
+                if (r < 8) {
+                    scr[k] = pa;                     // lane 0, r 0: Z[0] pairs with itself -> X[0] and X[256]
+                    scr[256 - k] = pb;
+                } else {
+                    scr[128] = pa;
+                }
+            }
+            simt::group_sync();
+
+            // ---- mel filterbank as range sums: filter j = up(range j+1) + down(range j+2)
+            float2 upv[kMaxTasks], dnv[kMaxTasks];
+            float2 esum = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < kMaxTasks; ++t) {
+                const int ri = task[lane * kMaxTasks + t];
+                float2 up = make_float2(0.f, 0.f), dn = up;
+                if (ri >= 0) {
+                    const int lo = rng[2 * ri], hi = rng[2 * ri + 1];
+                    for (int k = lo; k < hi; ++k) {
+                        const float2 pw = scr[k];
+                        const float2 w = melw[k];
+                        up = f2fmas(pw, w.x, up);
+                        dn = f2fmas(pw, w.y, dn);
+                        esum = f2add(esum, pw);
+                    }
+                }
+                upv[t] = up; dnv[t] = dn;
+            }
+            // total frame energy (reference base.py:25): reduce over the group
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) {
+                esum.x += simt::shfl16(esum.x, lane ^ m);
+                esum.y += simt::shfl16(esum.y, lane ^ m);
+            }
+            simt::group_sync();  // all lanes are done reading P before the staging area overwrites it
+            float2* segu = scr;                  // [nrange]
+            float2* segd = scr + kMaxRanges;     // [nrange]
+            float2* lmel = scr + 2 * kMaxRanges + 2;  // [nfilt]
+#pragma unroll
+            for (int t = 0; t < kMaxTasks; ++t) {
+                const int ri = task[lane * kMaxTasks + t];
+                if (ri >= 0) { segu[ri] = upv[t]; segd[ri] = dnv[t]; }
+            }
+            simt::group_sync();
+            const float eps64 = 2.220446049250313e-16f;  // numpy.finfo(float64).eps, reference base.py:26,30
+            for (int j = lane; j < p.nfilt; j += 16) {
+                float2 f = f2add(segu[j + 1], segd[j + 2]);
+                if (f.x == 0.f) f.x = eps64;
+                if (f.y == 0.f) f.y = eps64;
+                lmel[j] = make_float2(dsp_logf(f.x), dsp_logf(f.y));
+            }
+            simt::group_sync();
+            // ---- DCT-II (ortho) * lifter, c0 := log(energy)
+            if (lane < numcep) {
+                float2 acc = make_float2(0.f, 0.f);
+                const float* drow = dct + lane * p.dct_stride;
+                for (int m = 0; m < p.nfilt; ++m) acc = f2fmas(lmel[m], drow[m], acc);
+                if (lane == 0 && p.append_energy) {
+                    if (esum.x == 0.f) esum.x = eps64;
+                    if (esum.y == 0.f) esum.y = eps64;
+                    acc = make_float2(dsp_logf(esum.x), dsp_logf(esum.y));
+                }
+                sm.mfcc[(vA - v_lo) * numcep + lane] = acc.x;
+                if (vA + 1 <= v_hi) sm.mfcc[(vA + 1 - v_lo) * numcep + lane] = acc.y;
+            }
+        }
+        simt::cta_sync();  // fbuf may be overwritten by the next conversion pass
+    }
+
+    // ---- epilogue: delta (clamped on the utterance), delta-delta (clamped on the delta array), stores
+    float* dbuf = sm.fbuf;  // aliases fbuf+raw: no copy is in flight any more
+    const int u_lo = tile.f0 - N > 0 ? tile.f0 - N : 0;
+    const int u_hi = tile.f0 + tile.nf - 1 + N < F - 1 ? tile.f0 + tile.nf - 1 + N : F - 1;
+    const int nd = (u_hi - u_lo + 1) * numcep;
+    for (int i = tid; i < nd; i += kMfccThreads) {
+        const int uu = u_lo + i / numcep, cc = i % numcep;
+        float acc = 0.f;
+        for (int n = 1; n <= N; ++n) {
+            int hi = uu + n; if (hi > F - 1) hi = F - 1;
+            int lo = uu - n; if (lo < 0) lo = 0;
+            acc = dsp_fmaf((float)n, sm.mfcc[(hi - v_lo) * numcep + cc] - sm.mfcc[(lo - v_lo) * numcep + cc], acc);
+        }
+        dbuf[i] = acc * p.delta_scale;
+    }
+    simt::cta_sync();
+    const int width = 3 * numcep;
+    const int nout = tile.nf * width;
+    float* outp = p.out + (row0 + tile.f0) * width;
+    for (int i = tid; i < nout; i += kMfccThreads) {
+        const int tt = tile.f0 + i / width, col = i % width;
+        float v;
+        if (col < numcep) {
+            v = sm.mfcc[(tt - v_lo) * numcep + col];
+        } else if (col < 2 * numcep) {
+            v = dbuf[(tt - u_lo) * numcep + col - numcep];
+        } else {
+            const int cc = col - 2 * numcep;
+            float acc = 0.f;
+            for (int n = 1; n <= N; ++n) {
+                int hi = tt + n; if (hi > F - 1) hi = F - 1;
+                int lo = tt - n; if (lo < 0) lo = 0;
+                acc = dsp_fmaf((float)n, dbuf[(hi - u_lo) * numcep + cc] - dbuf[(lo - u_lo) * numcep + cc], acc);
+            }
+            v = acc * p.delta_scale;
+        }
+        outp[i] = v;
+    }
+}
+
+}  // namespace dspfe

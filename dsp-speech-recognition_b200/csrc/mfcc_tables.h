@@ -1,0 +1,175 @@
+// Host-side (double precision) construction of the MFCC kernel's constant tables and of its
+// shared-memory / table-blob layout.  Pure C++ (no CUDA calls): used by libdspfe.so at plan creation
+// and by the CPU-only tests.  Formulas follow reference base.py:34-58 (mel filterbank),
+// base.py:12-13 (DCT-II ortho), base.py:60-68 (lifter), base.py:74 (delta denominator).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dspfe_types.h"
+
+namespace dspfe {
+
+struct MfccConfig {
+    int samplerate = 16000;
+    int frame_len = 400;     // samples (caller applies round_half_up(winlen*samplerate), sigproc.py:77)
+    int frame_step = 160;
+    int nfft = 512;
+    int nfilt = 26;
+    int numcep = 13;
+    int ceplifter = 22;
+    int append_energy = 1;
+    int delta_n = 2;
+    int seg_frames = 256;    // tile length in output frames
+    double preemph = 0.97;
+    double lowfreq = 0.0;
+    double highfreq = 0.0;   // <= 0 means samplerate/2
+    std::vector<double> window;  // empty = rectangular (reference default winfunc)
+};
+
+inline double hz2mel(double hz) { return 2595.0 * std::log10(1.0 + hz / 700.0); }
+inline double mel2hz(double mel) { return 700.0 * (std::pow(10.0, mel / 2595.0) - 1.0); }
+
+// FFT-bin edges of the triangular filters: floor((nfft+1)*mel2hz(linspace)/samplerate), base.py:44-49
+inline std::vector<double> mel_bin_edges(const MfccConfig& c) {
+    const double high = c.highfreq > 0 ? c.highfreq : c.samplerate / 2.0;
+    const double lowmel = hz2mel(c.lowfreq), highmel = hz2mel(high);
+    const int n = c.nfilt + 2;
+    std::vector<double> b(n);
+    const double step = (highmel - lowmel) / (n - 1);  // numpy.linspace: arange(num)*step + start, last := stop
+    for (int i = 0; i < n; ++i) {
+        const double mel = (i == n - 1) ? highmel : i * step + lowmel;
+        b[i] = std::floor((c.nfft + 1) * mel2hz(mel) / c.samplerate);
+    }
+    return b;
+}
+
+inline std::string mfcc_config_check(const MfccConfig& c) {
+    if (c.nfft != kNfft) return "nfft must be 512 in this build (other sizes: SURVEY f-2)";
+    if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
+    if (c.frame_step < 2 || (c.frame_step & 1)) return "frame_step must be even and >= 2";
+    if (c.nfilt < 1 || c.nfilt > kMaxNfilt) return "nfilt must be in [1, 40]";
+    if (c.numcep < 1 || c.numcep > kMaxNumcep || c.numcep > c.nfilt) return "numcep must be in [1, min(16, nfilt)]";
+    if (c.delta_n < 1 || c.delta_n > kMaxDeltaN) return "delta N must be in [1, 4]";
+    if (c.seg_frames < 16 || c.seg_frames > 1024) return "seg_frames must be in [16, 1024]";
+    const double high = c.highfreq > 0 ? c.highfreq : c.samplerate / 2.0;
+    if (high > c.samplerate / 2.0) return "highfreq is greater than samplerate/2";
+    if (c.lowfreq < 0 || c.lowfreq >= high) return "lowfreq must be in [0, highfreq)";
+    if (!c.window.empty() && (int)c.window.size() != c.frame_len) return "window length must equal frame_len";
+    return "";
+}
+
+// Fills the layout fields of `p` (table offsets, shared-memory carve-up, scalars) and returns the
+// table blob.  Pointer fields of `p` are left untouched.
+inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, std::string& err) {
+    err = mfcc_config_check(c);
+    std::vector<float> blob;
+    if (!err.empty()) return blob;
+    const double kPi = 3.14159265358979323846;
+    p.frame_len = c.frame_len; p.frame_step = c.frame_step; p.nfilt = c.nfilt; p.numcep = c.numcep;
+    p.delta_n = c.delta_n; p.seg_frames = c.seg_frames; p.append_energy = c.append_energy;
+    p.preemph = (float)c.preemph;
+    int den = 0; for (int i = 1; i <= c.delta_n; ++i) den += i * i;
+    p.delta_scale = (float)(1.0 / (2.0 * den));
+    p.pow_scale = (float)(1.0 / (4.0 * c.nfft));
+    p.nrange = c.nfilt + 3;
+
+    auto align4 = [&]() { while (blob.size() & 3) blob.push_back(0.f); };
+    // W256^{n2*k1} at [k1*16 + n2]
+    p.o_twa = (int)blob.size();
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const double a = -2.0 * kPi * (double)(n2 * k1) / 256.0;
+            blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
+        }
+    // W512^k for the split post-pass, k < 144
+    p.o_twp = (int)blob.size();
+    for (int k = 0; k < 144; ++k) {
+        const double a = -2.0 * kPi * (double)k / 512.0;
+        blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
+    }
+    // per-bin (rising, falling) mel weights
+    const std::vector<double> bins = mel_bin_edges(c);
+    std::vector<int> edge(p.nrange + 1);
+    edge[0] = 0;
+    for (int i = 0; i < c.nfilt + 2; ++i) edge[i + 1] = std::min(std::max((int)bins[i], 0), kBins);
+    edge[p.nrange] = kBins;
+    for (int i = 1; i <= p.nrange; ++i) edge[i] = std::max(edge[i], edge[i - 1]);
+    p.o_melw = (int)blob.size();
+    {
+        std::vector<float> w(2 * (kBins + 1), 0.f);
+        for (int j = 0; j <= c.nfilt; ++j) {  // range j+1 = bins [bin[j], bin[j+1])
+            const double lo = bins[j], hi = bins[j + 1];
+            for (int k = edge[j + 1]; k < edge[j + 2]; ++k) {
+                w[2 * k] = (j < c.nfilt) ? (float)((k - lo) / (hi - lo)) : 0.f;   // rising edge of filter j
+                w[2 * k + 1] = (j > 0) ? (float)((hi - k) / (hi - lo)) : 0.f;     // falling edge of filter j-1
+            }
+        }
+        blob.insert(blob.end(), w.begin(), w.end());
+    }
+    // ranges and their longest-first assignment to the 16 lanes of a group
+    p.o_rng = (int)blob.size();
+    {
+        std::vector<int> r(2 * kMaxRanges, 0);
+        for (int i = 0; i < p.nrange; ++i) { r[2 * i] = edge[i]; r[2 * i + 1] = edge[i + 1]; }
+        for (int v : r) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
+    }
+    p.o_task = (int)blob.size();
+    {
+        std::vector<int> order;
+        for (int i = 0; i < p.nrange; ++i) if (edge[i + 1] > edge[i]) order.push_back(i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return edge[a + 1] - edge[a] > edge[b + 1] - edge[b]; });
+        std::vector<int> t(kGroupLanes * kMaxTasks, -1), load(kGroupLanes, 0), cnt(kGroupLanes, 0);
+        for (int ri : order) {
+            int best = -1;
+            for (int l = 0; l < kGroupLanes; ++l)
+                if (cnt[l] < kMaxTasks && (best < 0 || load[l] < load[best])) best = l;
+            if (best < 0) { err = "mel range assignment overflow"; return {}; }
+            t[best * kMaxTasks + cnt[best]++] = ri;
+            load[best] += edge[ri + 1] - edge[ri];
+        }
+        for (int v : t) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
+    }
+    // DCT-II (ortho) rows premultiplied by the lifter
+    p.o_dct = (int)blob.size();
+    p.dct_stride = c.nfilt | 1;
+    for (int k = 0; k < c.numcep; ++k) {
+        const double s = std::sqrt((k == 0 ? 1.0 : 2.0) / c.nfilt);
+        const double lift = c.ceplifter > 0 ? 1.0 + (c.ceplifter / 2.0) * std::sin(kPi * k / c.ceplifter) : 1.0;
+        for (int m = 0; m < p.dct_stride; ++m)
+            blob.push_back(m < c.nfilt ? (float)(lift * s * std::cos(kPi * k * (2 * m + 1) / (2.0 * c.nfilt))) : 0.f);
+    }
+    align4();
+    p.o_win = (int)blob.size();
+    for (double w : c.window) blob.push_back((float)w);
+    align4();
+    p.tbl_floats = (int)blob.size();
+
+    // shared-memory carve-up
+    auto up16 = [](int v) { return (v + 15) & ~15; };
+    int off = up16(p.tbl_floats * 4);
+    p.sm_mbar = off; off += 16;
+    p.sm_scratch = off; off += kMfccGroups * kScratchUnits * 8;
+    p.sm_mfcc = off; off += up16((c.seg_frames + 4 * c.delta_n) * c.numcep * 4);
+    p.fbuf_floats = (kFramesPerPass - 1) * c.frame_step + c.frame_len;
+    const int fbuf_bytes = up16(p.fbuf_floats * 4);
+    const int raw_bytes = up16((p.fbuf_floats + 1) * 2) + 32;  // history sample + 16-byte alignment slack either side
+    const int dbuf_bytes = up16((c.seg_frames + 2 * c.delta_n) * c.numcep * 4);
+    p.sm_fbuf = off;
+    p.sm_raw = off + fbuf_bytes;
+    off += std::max(fbuf_bytes + raw_bytes, dbuf_bytes);
+    p.sm_total = off;
+    if (p.sm_total > 227 * 1024) err = "configuration needs more than 227 KB of shared memory per CTA";
+    return blob;
+}
+
+// Upper bound on the number of tiles for a packed batch (grid size of the MFCC kernel).
+inline int64_t mfcc_max_tiles(int64_t total_samples, int64_t n_utt, int frame_step, int seg_frames) {
+    const int64_t max_frames = total_samples / frame_step + n_utt;
+    return n_utt + max_frames / seg_frames + 1;
+}
+
+}  // namespace dspfe

@@ -1,0 +1,98 @@
+// SIMT portability shim for the dspfe kernels.
+//
+// The kernel bodies (mfcc_kernel.cuh, endpoint_kernel.cuh, pitch_kernel.cuh) are written once
+// against this small vocabulary.  Under nvcc (the product build, sm_100a only) every item maps to
+// a CUDA intrinsic or inline PTX.  Under -DDSPFE_EMU (tests/emu only, plain g++) the same bodies
+// run on a fibre-based SIMT emulator so that index arithmetic, halo handling and barrier placement
+// can be checked in the GPU-less container.  The emulator is test infrastructure: it is never
+// linked into libdspfe.so and no product path can reach it.
+#pragma once
+#include <stdint.h>
+
+#ifdef DSPFE_EMU
+// ---------------------------------------------------------------- emulator (tests/emu only)
+#include <cmath>
+#include <cstring>
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#define DEVFN static inline
+#define DSPFE_RESTRICT
+namespace simt {
+int tid();                         // threadIdx.x
+int bid();                         // blockIdx.x
+int nthreads();                    // blockDim.x
+void cta_sync();                   // __syncthreads
+void group_sync();                 // barrier over the caller's 16-lane group
+float shfl16(float v, int src);    // __shfl_sync(halfmask, v, src, 16)
+float shfl32_xor(float v, int m);  // full-warp xor shuffle
+int shfl32_i(int v, int src);
+struct mbar_t { uint64_t v; };
+static inline void mbar_init(mbar_t*, int) {}
+static inline void fence_mbar_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_expect_tx(mbar_t*, uint32_t) {}
+static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, mbar_t*) { std::memcpy(dst, src, bytes); }
+static inline void mbar_wait(mbar_t*, uint32_t) {}
+}  // namespace simt
+DEVFN float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DEVFN float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+DEVFN float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+DEVFN float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
+DEVFN float dsp_logf(float x) { return std::log(x); }
+DEVFN float dsp_fmaf(float a, float b, float c) { return std::fmaf(a, b, c); }
+#else
+// ---------------------------------------------------------------- sm_100a device build
+#include <cuda_runtime.h>
+#define DEVFN __device__ __forceinline__
+#define DSPFE_RESTRICT __restrict__
+namespace simt {
+DEVFN int tid() { return threadIdx.x; }
+DEVFN int bid() { return blockIdx.x; }
+DEVFN int nthreads() { return blockDim.x; }
+DEVFN void cta_sync() { __syncthreads(); }
+DEVFN unsigned group_mask() { return (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu; }
+DEVFN void group_sync() { __syncwarp(group_mask()); }
+DEVFN float shfl16(float v, int src) { return __shfl_sync(group_mask(), v, src, 16); }
+DEVFN float shfl32_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+DEVFN int shfl32_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP): global -> shared::cta.
+struct mbar_t { uint64_t v; };
+DEVFN uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVFN void mbar_init(mbar_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+DEVFN void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DEVFN void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DEVFN void mbar_expect_tx(mbar_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+DEVFN void bulk_g2s(void* dst, const void* src, uint32_t bytes, mbar_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+DEVFN void mbar_wait(mbar_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+}  // namespace simt
+// Packed FP32 (FADD2/FMUL2/FFMA2 on sm_100a): .x and .y carry two independent frames.
+DEVFN float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+DEVFN float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+DEVFN float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+DEVFN float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+DEVFN float dsp_logf(float x) { return logf(x); }
+DEVFN float dsp_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+// scalar-broadcast forms (the scalar folds into the packed instruction's .F32 operand)
+DEVFN float2 f2muls(float2 a, float s) { return f2mul(a, make_float2(s, s)); }
+DEVFN float2 f2fmas(float2 a, float s, float2 c) { return f2fma(a, make_float2(s, s), c); }
+DEVFN float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }

@@ -1,0 +1,8 @@
+"""dspfe — Python host layer over libdspfe.so (hand-written sm_100a CUDA kernels).
+
+PyTorch supplies device memory and streams only; every feature value is computed by the
+kernels in csrc/.  There is no CPU fallback: if libdspfe.so is missing or no CUDA device is
+present, the compute entry points raise.
+"""
+from .binding import (DspfeError, MfccPlan, lib, lib_path, mfcc_params, num_frames, frame_counts,  # noqa: F401
+                      mfcc_tables_host)

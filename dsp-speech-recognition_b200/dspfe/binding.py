@@ -1,0 +1,170 @@
+"""ctypes binding of include/dspfe.h."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdspfe.so")
+_lib = None
+
+
+class DspfeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dspfe error {code}: {msg}")
+        self.code = code
+
+
+class _MfccParams(ctypes.Structure):
+    _fields_ = [("samplerate", ctypes.c_int32), ("frame_len", ctypes.c_int32), ("frame_step", ctypes.c_int32),
+                ("nfft", ctypes.c_int32), ("nfilt", ctypes.c_int32), ("numcep", ctypes.c_int32),
+                ("ceplifter", ctypes.c_int32), ("append_energy", ctypes.c_int32), ("delta_n", ctypes.c_int32),
+                ("seg_frames", ctypes.c_int32), ("preemph", ctypes.c_double), ("lowfreq", ctypes.c_double),
+                ("highfreq", ctypes.c_double), ("window", ctypes.POINTER(ctypes.c_double))]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Loads libdspfe.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} is missing: build it with `python dsp-speech-recognition_b200/build.py` "
+                              "(there is no CPU fallback)")
+        L = ctypes.CDLL(_LIB_PATH)
+        L.dspfe_version.restype = ctypes.c_char_p
+        L.dspfe_last_error.restype = ctypes.c_char_p
+        L.dspfe_num_frames.restype = ctypes.c_int64
+        L.dspfe_num_frames.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]
+        L.dspfe_rows_bound.restype = ctypes.c_int64
+        L.dspfe_rows_bound.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+        L.dspfe_plan_create.argtypes = [ctypes.POINTER(_MfccParams), ctypes.POINTER(ctypes.c_void_p)]
+        L.dspfe_plan_reserve.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+        L.dspfe_plan_destroy.argtypes = [ctypes.c_void_p]
+        L.dspfe_plan_destroy.restype = None
+        L.dspfe_plan_info.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 3
+        L.dspfe_mfcc_delta.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+        L.dspfe_mfcc_delta_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                            ctypes.c_void_p, ctypes.c_void_p]
+        L.dspfe_mfcc_tables_host.argtypes = [ctypes.POINTER(_MfccParams), ctypes.c_void_p, ctypes.c_int32,
+                                             ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p]
+        L.dspfe_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64]
+        L.dspfe_host_free.argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise DspfeError(rc, lib().dspfe_last_error().decode())
+
+
+def mfcc_params(samplerate=16000, frame_len=400, frame_step=160, nfft=512, nfilt=26, numcep=13, ceplifter=22,
+                append_energy=True, delta_n=2, seg_frames=0, preemph=0.97, lowfreq=0.0, highfreq=None, window=None):
+    """Returns (ctypes struct, keep-alive) for dspfe_mfcc_params; `window` is winfunc(frame_len) or None."""
+    p = _MfccParams(int(samplerate), int(frame_len), int(frame_step), int(nfft), int(nfilt), int(numcep),
+                    int(ceplifter), int(bool(append_energy)), int(delta_n), int(seg_frames), float(preemph),
+                    float(lowfreq or 0.0), float(highfreq or 0.0), None)
+    keep = None
+    if window is not None:
+        keep = np.ascontiguousarray(window, dtype=np.float64)
+        if keep.shape != (int(frame_len),):
+            raise ValueError("window must have frame_len entries")
+        p.window = keep.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    return p, keep
+
+
+def num_frames(n_samples, frame_len, frame_step):
+    return int(lib().dspfe_num_frames(int(n_samples), int(frame_len), int(frame_step)))
+
+
+def frame_counts(lengths, frame_len, frame_step):
+    """framesig's frame count (reference sigproc.py:79-82), vectorised on the host."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    return np.where(lengths <= frame_len, 1, 1 + (lengths - frame_len + frame_step - 1) // frame_step).astype(np.int64)
+
+
+def mfcc_tables_host(**kw):
+    """Host-only table construction (no CUDA): returns (blob float32[n], mel_edges float64[nfilt+2])."""
+    p, keep = mfcc_params(**kw)
+    n = ctypes.c_int32(0)
+    _check(lib().dspfe_mfcc_tables_host(ctypes.byref(p), None, 0, ctypes.byref(n), None))
+    blob = np.zeros(n.value, dtype=np.float32)
+    edges = np.zeros(p.nfilt + 2, dtype=np.float64)
+    _check(lib().dspfe_mfcc_tables_host(ctypes.byref(p), blob.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n),
+                                        edges.ctypes.data_as(ctypes.c_void_p)))
+    return blob, edges
+
+
+class MfccPlan:
+    """dspfe_plan: parameters + device tables + workspaces for the fused MFCC+delta+delta-delta kernel."""
+
+    def __init__(self, **kw):
+        self._p, self._keep = mfcc_params(**kw)
+        self.frame_len, self.frame_step = self._p.frame_len, self._p.frame_step
+        self.width = 3 * self._p.numcep
+        h = ctypes.c_void_p()
+        _check(lib().dspfe_plan_create(ctypes.byref(self._p), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dspfe_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def info(self):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _check(lib().dspfe_plan_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return dict(smem_bytes=a.value, ctas_per_sm=b.value, regs_per_thread=c.value)
+
+    def rows_bound(self, total_samples, n_utt):
+        return int(lib().dspfe_rows_bound(self._h, int(total_samples), int(n_utt)))
+
+    def reserve(self, max_utt, max_total_samples):
+        _check(lib().dspfe_plan_reserve(self._h, int(max_utt), int(max_total_samples)))
+
+    def mfcc_delta(self, pcm, offsets, trim=None, out=None, frame_off=None, stream=None):
+        """Device path.  pcm int16 CUDA tensor [total], offsets int64 CUDA tensor [U+1], optional trim int32
+        CUDA tensor [U,2].  Asynchronous on `stream` (default: torch's current stream).  Returns
+        (out float32 [rows_bound, 3*numcep], frame_off int64 [U+1]); rows beyond frame_off[-1] are untouched."""
+        import torch
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+        assert offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()
+        n_utt = offsets.numel() - 1
+        total = pcm.numel()
+        rows = self.rows_bound(total, n_utt)
+        if out is None:
+            out = torch.empty((rows, self.width), dtype=torch.float32, device=pcm.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] >= rows
+        if frame_off is None:
+            frame_off = torch.empty(n_utt + 1, dtype=torch.int64, device=pcm.device)
+        tp = None
+        if trim is not None:
+            assert trim.is_cuda and trim.dtype == torch.int32 and trim.is_contiguous() and trim.shape == (n_utt, 2)
+            tp = trim.data_ptr()
+        st = stream if stream is not None else torch.cuda.current_stream(pcm.device).cuda_stream
+        _check(lib().dspfe_mfcc_delta(self._h, pcm.data_ptr(), total, offsets.data_ptr(), tp, n_utt, out.data_ptr(),
+                                      out.shape[0], frame_off.data_ptr(), ctypes.c_void_p(st)))
+        return out, frame_off
+
+    def mfcc_delta_host(self, pcm, offsets, out=None):
+        """Host path (the reference-facing call): NumPy (or pinned torch CPU) int16 pcm + int64 offsets in, NumPy
+        float32 [rows, 3*numcep] out; H2D, kernels and D2H are pipelined inside libdspfe."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_utt = len(offsets) - 1
+        rows = int(frame_counts(np.diff(offsets), self.frame_len, self.frame_step).sum())
+        if out is None:
+            out = np.empty((rows, self.width), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape[0] >= rows
+        fo = np.empty(n_utt + 1, dtype=np.int64)
+        _check(lib().dspfe_mfcc_delta_host(self._h, pcm.ctypes.data_as(ctypes.c_void_p),
+                                           offsets.ctypes.data_as(ctypes.c_void_p), n_utt,
+                                           out.ctypes.data_as(ctypes.c_void_p), fo.ctypes.data_as(ctypes.c_void_p)))
+        return out[:rows], fo

@@ -1,0 +1,112 @@
+/* dspfe.h — C ABI of libdspfe.so, the B200 (sm_100a) speech front-end.
+ *
+ * Drop-in boundary for the PCM -> classifier-features path of AuCson/DSP-Speech-Recognition.
+ * The reference has no FFI: its boundary is the Python package `features`
+ * (features/__init__.py:1-6).  Each entry point below names the reference function(s) it
+ * replaces; the Python package `dsp-speech-recognition_b200/features` binds these with ctypes
+ * and re-exposes the reference's own names and signatures.
+ *
+ * Conventions
+ *   - every function returns 0 (DSPFE_OK) or a negative dspfe_status; dspfe_last_error() gives
+ *     the message of the calling thread's last failure;
+ *   - `d_` pointers are device memory, `h_` pointers host memory; the caller owns all of them;
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, and keep their workspaces inside the plan (grown only when a larger batch
+ *     than ever before arrives; dspfe_plan_reserve() pre-sizes them);
+ *   - a packed ragged batch is int16 PCM `pcm[total_samples]` plus `offsets[n_utt+1]` (int64,
+ *     samples); utterance u is pcm[offsets[u] .. offsets[u+1]).  No padding between utterances
+ *     is required; `d_pcm` itself must be 16-byte aligned.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     DSPFE_ERR_CUDA.
+ */
+#ifndef DSPFE_H_
+#define DSPFE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DSPFE_OK = 0,
+    DSPFE_ERR_INVALID_ARG = -1,   /* null pointer, bad size, misaligned buffer */
+    DSPFE_ERR_UNSUPPORTED = -2,   /* parameter combination outside the supported set (no CPU fallback) */
+    DSPFE_ERR_CUDA = -3,          /* CUDA runtime error (message has the cudaError string) */
+    DSPFE_ERR_NOMEM = -4
+} dspfe_status;
+
+typedef struct dspfe_plan dspfe_plan;
+
+/* Parameters of the MFCC (+delta) path.  Field meanings follow reference base.py:8-10 `mfcc(...)`.
+ * frame_len / frame_step are in samples: the caller applies round_half_up(winlen*samplerate)
+ * (reference sigproc.py:77-78). */
+typedef struct {
+    int32_t samplerate;      /* 16000 */
+    int32_t frame_len;       /* 400  (25 ms) */
+    int32_t frame_step;      /* 160  (10 ms) */
+    int32_t nfft;            /* 512 */
+    int32_t nfilt;           /* 26 */
+    int32_t numcep;          /* 13 */
+    int32_t ceplifter;       /* 22 (<= 0 disables, base.py:66-68) */
+    int32_t append_energy;   /* 1: c0 := log(frame energy), base.py:15 */
+    int32_t delta_n;         /* N of delta(feat, N), base.py:70 */
+    int32_t seg_frames;      /* tile length in frames (tuning knob; 0 = default) */
+    double preemph;          /* 0.97 */
+    double lowfreq;          /* 0 */
+    double highfreq;         /* <= 0: samplerate / 2 */
+    const double* window;    /* host array [frame_len] = winfunc(frame_len), or NULL for rectangular */
+} dspfe_mfcc_params;
+
+const char* dspfe_version(void);
+const char* dspfe_last_error(void);
+
+/* Reference defaults (base.py:8-10) with delta_n = 2. */
+void dspfe_mfcc_params_default(dspfe_mfcc_params* p);
+
+/* framesig's frame count, reference sigproc.py:79-82. */
+int64_t dspfe_num_frames(int64_t n_samples, int32_t frame_len, int32_t frame_step);
+
+/* Host-only: build the kernel's constant tables (no CUDA call).  Writes up to `cap` floats to
+ * `blob`, the float count to *n, and the 28 mel bin edges (nfilt+2 doubles) to `mel_edges` if
+ * non-null.  Lets CPU-only tests check the tables against the oracle. */
+int dspfe_mfcc_tables_host(const dspfe_mfcc_params* p, float* blob, int32_t cap, int32_t* n, double* mel_edges);
+
+/* Plan = parameters + device tables + workspaces on the current CUDA device. */
+int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan);
+int dspfe_plan_reserve(dspfe_plan* plan, int64_t max_utt, int64_t max_total_samples);
+void dspfe_plan_destroy(dspfe_plan* plan);
+/* shared-memory bytes per CTA and CTAs per SM of the fused kernel (for reports) */
+int dspfe_plan_info(const dspfe_plan* plan, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* regs_per_thread);
+
+/* Fused MFCC + delta + delta-delta over a packed ragged batch, everything device-resident.
+ * Replaces features.mfcc (base.py:8) followed by features.delta twice (base.py:70; as called in
+ * model.py:74-77) for every utterance of the batch.
+ *   d_offsets   [n_utt+1] int64 utterance boundaries in samples
+ *   d_trim      optional [n_utt,2] int32 (left,right) sample indices inside each utterance, as
+ *               produced by dspfe_endpoint(); the utterance is replaced by sig[left:right]
+ *               (Python slice semantics, model.py:62); NULL = whole utterances
+ *   d_out       [rows, 3*numcep] float32, rows >= total frame count
+ *   d_frame_off [n_utt+1] int64, written: first output row of each utterance (last = total rows)
+ *   max_rows    capacity of d_out in rows; must be >= dspfe_rows_bound(...)  */
+int dspfe_mfcc_delta(dspfe_plan* plan, const int16_t* d_pcm, int64_t total_samples,
+                     const int64_t* d_offsets, const int32_t* d_trim, int32_t n_utt,
+                     float* d_out, int64_t max_rows, int64_t* d_frame_off, void* stream);
+
+/* Upper bound on output rows for any batch with these totals. */
+int64_t dspfe_rows_bound(const dspfe_plan* plan, int64_t total_samples, int64_t n_utt);
+
+/* Same computation through host buffers: H2D copy of pcm/offsets, kernels, D2H copy of the
+ * features, pipelined over utterance slabs on internal streams; returns after the result is in
+ * h_out.  h_out must hold sum_u num_frames(len_u) rows; h_frame_off [n_utt+1] is written.
+ * Pinned host memory (dspfe_host_alloc) makes the copies truly asynchronous. */
+int dspfe_mfcc_delta_host(dspfe_plan* plan, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt,
+                          float* h_out, int64_t* h_frame_off);
+
+int dspfe_host_alloc(void** p, int64_t bytes);   /* cudaHostAlloc */
+int dspfe_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPFE_H_ */

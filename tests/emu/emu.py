@@ -1,0 +1,71 @@
+"""ctypes binding of the CPU SIMT emulator (tests only; see tests/emu/emu_simt.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libdspfe_emu.so")
+
+
+class MfccParams(ctypes.Structure):
+    _fields_ = [("samplerate", ctypes.c_int32), ("frame_len", ctypes.c_int32), ("frame_step", ctypes.c_int32),
+                ("nfft", ctypes.c_int32), ("nfilt", ctypes.c_int32), ("numcep", ctypes.c_int32),
+                ("ceplifter", ctypes.c_int32), ("append_energy", ctypes.c_int32), ("delta_n", ctypes.c_int32),
+                ("seg_frames", ctypes.c_int32), ("preemph", ctypes.c_double), ("lowfreq", ctypes.c_double),
+                ("highfreq", ctypes.c_double), ("window", ctypes.POINTER(ctypes.c_double))]
+
+
+def build():
+    srcs = [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith(".cpp")]
+    csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "dsp-speech-recognition_b200", "csrc")
+    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DDSPFE_EMU", "-shared", "-fPIC", "-o", LIB] + srcs)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.emu_mfcc_delta.restype = ctypes.c_longlong
+    return _lib
+
+
+def make_params(frame_len=400, frame_step=160, nfilt=26, numcep=13, ceplifter=22, append_energy=True, delta_n=2,
+                seg_frames=0, preemph=0.97, lowfreq=0.0, highfreq=0.0, window=None, samplerate=16000, nfft=512):
+    p = MfccParams(samplerate, frame_len, frame_step, nfft, nfilt, numcep, ceplifter, int(append_energy), delta_n,
+                   seg_frames, preemph, lowfreq, highfreq, None)
+    keep = None
+    if window is not None:
+        keep = np.ascontiguousarray(window, dtype=np.float64)
+        p.window = keep.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    return p, keep
+
+
+def mfcc_delta(pcm, offsets, trim=None, **kw):
+    p, keep = make_params(**kw)
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    rows = int(len(pcm) // p.frame_step + n)
+    out = np.full((rows, 3 * p.numcep), np.nan, dtype=np.float32)
+    fo = np.zeros(n + 1, dtype=np.int64)
+    err = ctypes.create_string_buffer(256)
+    tp = None
+    if trim is not None:
+        trim = np.ascontiguousarray(trim, dtype=np.int32)
+        tp = trim.ctypes.data_as(ctypes.c_void_p)
+    r = lib().emu_mfcc_delta(ctypes.byref(p), pcm.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(len(pcm)),
+                             offsets.ctypes.data_as(ctypes.c_void_p), tp, n, out.ctypes.data_as(ctypes.c_void_p),
+                             ctypes.c_longlong(rows), fo.ctypes.data_as(ctypes.c_void_p), err, 256)
+    if r < 0:
+        raise RuntimeError(f"emulator: {err.value.decode()} ({r})")
+    return out[:r], fo

@@ -1,0 +1,70 @@
+// Emulator entry point for K1 (fused MFCC + delta + delta-delta).  TEST INFRASTRUCTURE ONLY.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../dsp-speech-recognition_b200/csrc/mfcc_kernel.cuh"
+#include "../../dsp-speech-recognition_b200/csrc/mfcc_tables.h"
+#include "../../include/dspfe.h"
+
+namespace emu { bool run_cta(int bid, int nthreads, void (*body)(void*), void* arg); }
+using namespace dspfe;
+
+namespace {
+struct Args { MfccParams p; bool has_win; std::vector<unsigned char>* smem; };
+void body(void* a) {
+    Args* A = (Args*)a;
+    if (A->has_win) mfcc_cta<true>(A->p, A->smem->data());
+    else mfcc_cta<false>(A->p, A->smem->data());
+}
+}  // namespace
+
+// Same contract as dspfe_mfcc_delta but host pointers and synchronous.  Returns rows written, <0 on error.
+extern "C" long long emu_mfcc_delta(const dspfe_mfcc_params* q, const int16_t* pcm, long long total_samples,
+                                    const long long* offsets, const int* trim, int n_utt, float* out, long long max_rows,
+                                    long long* frame_off_out, char* errbuf, int errcap) {
+    MfccConfig c;
+    c.samplerate = q->samplerate; c.frame_len = q->frame_len; c.frame_step = q->frame_step; c.nfft = q->nfft;
+    c.nfilt = q->nfilt; c.numcep = q->numcep; c.ceplifter = q->ceplifter; c.append_energy = q->append_energy;
+    c.delta_n = q->delta_n; c.seg_frames = q->seg_frames > 0 ? q->seg_frames : 256;
+    c.preemph = q->preemph; c.lowfreq = q->lowfreq; c.highfreq = q->highfreq;
+    if (q->window) c.window.assign(q->window, q->window + q->frame_len);
+    MfccParams p; std::memset(&p, 0, sizeof(p));
+    std::string err;
+    std::vector<float> blob = build_mfcc_tables(c, p, err);
+    if (!err.empty()) { std::snprintf(errbuf, errcap, "%s", err.c_str()); return -2; }
+    // host mirror of prep_kernel
+    std::vector<int64_t> seg_start(n_utt + 1), frame_off(n_utt + 1);
+    std::vector<int32_t> seg_len(n_utt + 1);
+    std::vector<Tile> tiles;
+    int64_t fo = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        int64_t a = offsets[u], len = offsets[u + 1] - offsets[u];
+        if (trim) {
+            int64_t l = trim[2 * u], r = trim[2 * u + 1];
+            if (l < 0) l = 0; if (r < 0) r = 0;
+            if (l > len) l = len; if (r > len) r = len;
+            a += l; len = r > l ? r - l : 0;
+        }
+        seg_start[u] = a; seg_len[u] = (int32_t)len;
+        const int F = (int)num_frames(len, c.frame_len, c.frame_step);
+        const int T = (F + c.seg_frames - 1) / c.seg_frames, per = (F + T - 1) / T;
+        frame_off[u] = fo;
+        for (int t = 0; t < T; ++t) { Tile tl; tl.utt = u; tl.f0 = t * per; tl.nf = std::min(per, F - tl.f0); tl.pad = 0; tiles.push_back(tl); }
+        fo += F;
+    }
+    frame_off[n_utt] = fo;
+    if (fo > max_rows) { std::snprintf(errbuf, errcap, "out too small"); return -1; }
+    if (frame_off_out) std::memcpy(frame_off_out, frame_off.data(), (n_utt + 1) * sizeof(int64_t));
+    int32_t ntiles = (int32_t)tiles.size();
+    p.pcm = pcm; p.total_samples = total_samples; p.seg_start = seg_start.data(); p.seg_len = seg_len.data();
+    p.frame_off = frame_off.data(); p.tiles = tiles.data(); p.ntiles = &ntiles; p.tables = blob.data(); p.out = out;
+    std::vector<unsigned char> smem(p.sm_total + 64);
+    Args A{p, !c.window.empty(), &smem};
+    for (int b = 0; b < ntiles + 1; ++b) {   // +1: exercises the early-exit path of surplus CTAs
+        std::memset(smem.data(), 0xCD, smem.size());   // poison: uninitialised shared memory shows up as garbage
+        if (!emu::run_cta(b, kMfccThreads, body, &A)) { std::snprintf(errbuf, errcap, "deadlock in CTA %d", b); return -3; }
+    }
+    return fo;
+}

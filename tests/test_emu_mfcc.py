@@ -1,0 +1,72 @@
+"""K1 kernel body (csrc/mfcc_kernel.cuh) executed on the CPU SIMT emulator (tests/emu) against the
+golden vectors of the live reference and against the oracle.  Checks the kernel's index arithmetic,
+halo/clamp handling and barrier placement without a GPU; the GPU parity tests proper are
+tests/test_mfcc_gpu.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu  # noqa: E402
+from dspfe import synth  # noqa: E402
+from oracle import ref_features as O  # noqa: E402
+from tol import assert_mfcc_close  # noqa: E402
+
+
+def test_golden_single_utterances(golden):
+    g = golden("mfcc")
+    for name in sorted({k.split("/")[0] for k in g.files if k.endswith("/x")}):
+        x = g[f"{name}/x"]
+        for N in (2, 3):
+            out, fo = emu.mfcc_delta(x, [0, len(x)], delta_n=N)
+            assert fo[-1] == len(g[f"{name}/d39_n{N}"])
+            assert_mfcc_close(out, g[f"{name}/d39_n{N}"], what=f"{name} N={N}")
+
+
+def test_golden_variants(golden):
+    g = golden("mfcc")
+    x = g["r_1p37s/x"]
+    out, _ = emu.mfcc_delta(x, [0, len(x)], window=np.hamming(400))
+    assert_mfcc_close(out, g["hamming/d39_n2"], what="hamming")
+    out, _ = emu.mfcc_delta(x, [0, len(x)], preemph=0.0)
+    assert_mfcc_close(out[:, :13], g["nopre/mfcc"], what="preemph=0 (2-D quirk equivalent)")
+    out, _ = emu.mfcc_delta(x, [0, len(x)], nfilt=40, numcep=16, ceplifter=0, append_energy=False)
+    assert_mfcc_close(out[:, :16], g["nfilt40_cep20/mfcc"], what="nfilt40")
+    out, _ = emu.mfcc_delta(x, [0, len(x)], lowfreq=300, highfreq=3400)
+    assert_mfcc_close(out[:, :13], g["band/mfcc"], what="band")
+    out, _ = emu.mfcc_delta(x, [0, len(x)], frame_len=320, frame_step=128)
+    assert_mfcc_close(out[:, :13], g["win20_step8/mfcc"], what="20ms/8ms")
+
+
+@pytest.mark.parametrize("seg", [16, 48, 256])
+def test_ragged_batch_multi_tile(seg):
+    """Packed ragged batch with odd (2-byte aligned) utterance starts; small tiles force the 2N halo path."""
+    lengths = [8001, 399, 16003, 1, 5555, 12345, 400, 0, 777]
+    pcm, off = synth.synth_batch(lengths, seed0=900)
+    out, fo = emu.mfcc_delta(pcm, off, delta_n=3, seg_frames=seg)
+    for u, n in enumerate(lengths):
+        ref = O.mfcc_delta39(pcm[off[u]:off[u + 1]], 3) if n > 0 else None
+        rows = out[fo[u]:fo[u + 1]]
+        if n == 0:   # the reference cannot frame an empty signal; the kernel emits the one zero-padded frame
+            assert rows.shape == (1, 39)
+            continue
+        assert_mfcc_close(rows, ref, what=f"utt {u} len {n} seg {seg}")
+
+
+def test_trim_matches_python_slice():
+    pcm, off = synth.synth_batch([9000, 12000], seed0=910)
+    trim = np.array([[1000, 7777], [3, 99999]], dtype=np.int32)   # right beyond the end clamps like sig[l:r]
+    out, fo = emu.mfcc_delta(pcm, off, trim=trim)
+    for u in range(2):
+        x = pcm[off[u]:off[u + 1]][trim[u, 0]:trim[u, 1]]
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], O.mfcc_delta39(x, 2), what=f"trim {u}")
+
+
+def test_unsupported_configs_are_rejected():
+    x = np.zeros(1000, dtype=np.int16)
+    for kw in (dict(nfft=1536), dict(frame_len=600), dict(frame_step=161), dict(nfilt=41), dict(numcep=17),
+               dict(delta_n=0), dict(highfreq=9000.0)):
+        with pytest.raises(RuntimeError):
+            emu.mfcc_delta(x, [0, 1000], **kw)

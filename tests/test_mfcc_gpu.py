@@ -1,0 +1,141 @@
+"""GPU parity tests of K1 (fused MFCC + delta + delta-delta) through the C ABI (libdspfe.so)."""
+import numpy as np
+import pytest
+
+from tol import assert_mfcc_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_dev():
+    import torch
+    return torch, torch.device("cuda:0")
+
+
+def run_device(plan, pcm, off, torch_dev, trim=None):
+    torch, dev = torch_dev
+    t = None if trim is None else torch.from_numpy(np.ascontiguousarray(trim, dtype=np.int32)).to(dev)
+    out, fo = plan.mfcc_delta(torch.from_numpy(np.ascontiguousarray(pcm)).to(dev),
+                              torch.from_numpy(np.ascontiguousarray(off, dtype=np.int64)).to(dev), trim=t)
+    torch.cuda.synchronize()
+    fo = fo.cpu().numpy()
+    return out.cpu().numpy()[:fo[-1]], fo
+
+
+def test_golden_single_utterances(golden, torch_dev):
+    import dspfe
+    g = golden("mfcc")
+    for N in (2, 3):
+        plan = dspfe.MfccPlan(delta_n=N)
+        for name in sorted({k.split("/")[0] for k in g.files if k.endswith("/x")}):
+            x = g[f"{name}/x"]
+            out, fo = run_device(plan, x, [0, len(x)], torch_dev)
+            assert_mfcc_close(out, g[f"{name}/d39_n{N}"], what=f"{name} N={N}")
+            host, _ = plan.mfcc_delta_host(x, np.array([0, len(x)]))
+            np.testing.assert_array_equal(host, out)
+
+
+def test_golden_variants(golden, torch_dev):
+    import dspfe
+    g = golden("mfcc")
+    x = g["r_1p37s/x"]
+    off = [0, len(x)]
+    out, _ = run_device(dspfe.MfccPlan(window=np.hamming(400)), x, off, torch_dev)
+    assert_mfcc_close(out, g["hamming/d39_n2"], what="hamming")
+    out, _ = run_device(dspfe.MfccPlan(preemph=0.0), x, off, torch_dev)
+    assert_mfcc_close(out[:, :13], g["nopre/mfcc"], what="preemph=0")
+    out, _ = run_device(dspfe.MfccPlan(nfilt=40, numcep=16, ceplifter=0, append_energy=False), x, off, torch_dev)
+    assert_mfcc_close(out[:, :16], g["nfilt40_cep20/mfcc"], what="nfilt40")
+    out, _ = run_device(dspfe.MfccPlan(lowfreq=300, highfreq=3400), x, off, torch_dev)
+    assert_mfcc_close(out[:, :13], g["band/mfcc"], what="band")
+    out, _ = run_device(dspfe.MfccPlan(frame_len=320, frame_step=128), x, off, torch_dev)
+    assert_mfcc_close(out[:, :13], g["win20_step8/mfcc"], what="20ms/8ms")
+
+
+@pytest.mark.parametrize("seg", [16, 48, 256])
+def test_ragged_batch_vs_oracle(seg, torch_dev):
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    lengths = [8001, 399, 16003, 1, 5555, 80000, 12345, 400, 0, 777, 47777]
+    pcm, off = synth.synth_batch(lengths, seed0=900)
+    plan = dspfe.MfccPlan(delta_n=3, seg_frames=seg)
+    out, fo = run_device(plan, pcm, off, torch_dev)
+    for u, n in enumerate(lengths):
+        rows = out[fo[u]:fo[u + 1]]
+        if n == 0:
+            assert rows.shape == (1, 39) and np.all(np.isfinite(rows))
+            continue
+        assert_mfcc_close(rows, O.mfcc_delta39(pcm[off[u]:off[u + 1]], 3), what=f"utt {u} len {n} seg {seg}")
+    host, fo_h = plan.mfcc_delta_host(pcm, off)
+    np.testing.assert_array_equal(fo_h, fo)
+    np.testing.assert_array_equal(host, out)
+
+
+def test_trim_matches_python_slice(torch_dev):
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    pcm, off = synth.synth_batch([9000, 12000, 30000], seed0=910)
+    trim = np.array([[1000, 7777], [3, 99999], [12000, 25000]], dtype=np.int32)
+    out, fo = run_device(dspfe.MfccPlan(), pcm, off, torch_dev, trim=trim)
+    for u in range(3):
+        x = pcm[off[u]:off[u + 1]][trim[u, 0]:trim[u, 1]]
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], O.mfcc_delta39(x, 2), what=f"trim {u}")
+
+
+def test_config2_full_size_properties(torch_dev):
+    """BASELINE config 2 (4096 x 2 s): sampled oracle parity + size-independent properties."""
+    torch, dev = torch_dev
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    U, S = 4096, 32000
+    pcm, off = synth.synth_batch_torch(np.full(U, S), seed0=1234, device=dev)
+    off_d = off.to(dev)
+    plan = dspfe.MfccPlan()
+    out, fo = plan.mfcc_delta(pcm, off_d)
+    torch.cuda.synchronize()
+    assert int(fo[-1]) == U * 199
+    out = out[: U * 199]
+    assert bool(torch.isfinite(out).all())
+    # (1) sampled parity against the oracle on the exact samples the kernel saw
+    for u in (0, 1, 777, 2048, 4095):
+        x = pcm[u * S:(u + 1) * S].cpu().numpy()
+        assert_mfcc_close(out[u * 199:(u + 1) * 199].cpu().numpy(), O.mfcc_delta39(x, 2), what=f"C2 utt {u}")
+    # (2) packing independence: any utterance alone gives bit-identical rows
+    for u in (5, 4000):
+        solo, _ = plan.mfcc_delta(pcm[u * S:(u + 1) * S].clone(), torch.tensor([0, S], device=dev))
+        torch.cuda.synchronize()
+        assert torch.equal(solo[:199], out[u * 199:(u + 1) * 199])
+    # (3) determinism: a second launch is bit-identical
+    out2, _ = plan.mfcc_delta(pcm, off_d)
+    torch.cuda.synchronize()
+    assert torch.equal(out2[: U * 199], out)
+    # (4) delta columns equal the reference regression applied to the kernel's own static columns
+    m = out[:199, :13].double().cpu().numpy()
+    d1 = O.delta(m, 2)
+    np.testing.assert_allclose(out[:199, 13:26].cpu().numpy(), d1, atol=2e-5)
+    np.testing.assert_allclose(out[:199, 26:].cpu().numpy(), O.delta(d1, 2), atol=2e-5)
+    # (5) gain property: halving the PCM shifts c0 by log(1/4) and leaves c1..c12 alone (up to int16 rounding)
+    half = (pcm[: 8 * S] // 2 * 2)
+    a, _ = plan.mfcc_delta(half.contiguous(), off_d[:9].contiguous())
+    b, _ = plan.mfcc_delta((half // 2).contiguous(), off_d[:9].contiguous())
+    torch.cuda.synchronize()
+    a, b = a[: 8 * 199], b[: 8 * 199]
+    assert float((a[:, 0] - b[:, 0] - np.log(4.0)).abs().max()) < 1e-4
+    assert float((a[:, 1:13] - b[:, 1:13]).abs().max()) < 2e-4
+
+
+def test_errors(torch_dev):
+    torch, dev = torch_dev
+    import dspfe
+    with pytest.raises(dspfe.DspfeError):
+        dspfe.MfccPlan(nfft=1536)
+    with pytest.raises(dspfe.DspfeError):
+        dspfe.MfccPlan(highfreq=9000.0)
+    plan = dspfe.MfccPlan()
+    pcm = torch.zeros(1001, dtype=torch.int16, device=dev)
+    with pytest.raises(dspfe.DspfeError):          # misaligned base pointer
+        plan.mfcc_delta(pcm[1:], torch.tensor([0, 1000], device=dev))
