@@ -10,7 +10,8 @@
 //     plus 2N halo frames either side (only when an utterance is split into several tiles);
 //   * the CTA streams the tile's PCM in chunks of 16 frames: a 1-D bulk async copy (TMA engine,
 //     cp.async.bulk + mbarrier) lands raw int16 in shared memory while the previous chunk computes;
-//   * a conversion pass turns the chunk into pre-emphasised fp32 once (frames overlap 2.5x);
+//   * a vectorised conversion pass (8 samples per thread, int16->fp32 by mantissa splicing instead of
+//     the slow I2F) turns the chunk into pre-emphasised fp32 once (frames overlap 2.5x);
 //   * each 16-lane group owns a PAIR of frames carried in the two halves of packed-FP32 registers
 //     (FADD2/FMUL2/FFMA2): 512-point real FFT as a 256-point complex FFT (radix-16 x radix-16, one
 //     shared-memory transpose) + split post-pass done pairwise (k, 256-k) with 16-lane shuffles,
@@ -141,8 +142,8 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
 
     const float2* twa = reinterpret_cast<const float2*>(sm.tables + p.o_twa);
     const float2* twp = reinterpret_cast<const float2*>(sm.tables + p.o_twp);
-    const float2* melw = reinterpret_cast<const float2*>(sm.tables + p.o_melw);
-    const int* rng = reinterpret_cast<const int*>(sm.tables + p.o_rng);
+    const int* rng = reinterpret_cast<const int*>(sm.tables + p.o_rng);   // per range: lo, hi, 1/(hi-lo) (0 outside the filters)
+    const float* rngf = sm.tables + p.o_rng;
     const int* task = reinterpret_cast<const int*>(sm.tables + p.o_task);
     const float* dct = sm.tables + p.o_dct;
     const float* win = sm.tables + p.o_win;
@@ -159,6 +160,8 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     };
     issue_chunk(0);
 
+    const int nfull = p.frame_len >> 5;        // FFT input rows (32 samples each) that lie fully inside the frame
+    const bool odd_start = (start & 1) != 0;   // frame starts are 8-byte aligned in fbuf unless the utterance starts on an odd sample
     uint32_t parity = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int frame0 = v_lo + c * kFramesPerPass;
@@ -166,37 +169,70 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
         if (g.bulk_bytes > 0) { simt::mbar_wait(sm.mbar, parity); parity ^= 1; }
         if (c == 0) simt::cta_sync();  // chunk-0 tail stores -> visible (later chunks: the loop-end barrier)
 
-        // ---- raw int16 -> pre-emphasised fp32 (reference sigproc.py:185; zero padding after it, :84-87)
+        // ---- raw int16 -> pre-emphasised fp32, 8 samples per thread.  fbuf[q] pairs with raw[q] (packed sample
+        // a0s + q).  Reference: y[0] = x[0], y[n] = x[n] - c*x[n-1] (sigproc.py:185), zeros past the end (:84-87).
         {
-            const int64_t base = start - g.a0s + g.s0;  // raw index of fbuf[0]
-            for (int i = tid; i < p.fbuf_floats; i += kMfccThreads) {
-                const int64_t s = g.s0 + i;
-                float y = 0.f;
-                if (s < S) {
-                    const float x = (float)sm.raw[base + i];
-                    const float xp = s > 0 ? (float)sm.raw[base + i - 1] : 0.f;
-                    y = dsp_fmaf(-p.preemph, xp, x);
+            const int rel = (int)(g.a0s - start);  // utterance sample index of raw[0] (may be negative)
+            const float cpre = p.preemph;
+            for (int j0 = 0; j0 < p.fbuf_vecs; j0 += kMfccThreads) {
+                const int j = j0 + tid;
+                const bool act = j < p.fbuf_vecs;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (act) v = reinterpret_cast<const uint4*>(sm.raw)[j];
+                uint32_t pw = (uint32_t)simt::shfl32_i((int)v.w, (tid & 31) - 1);   // previous thread's last pair
+                if ((tid & 31) == 0) pw = (act && j > 0) ? ((uint32_t)(uint16_t)sm.raw[8 * j - 1]) << 16 : 0u;
+                if (act) {
+                    float e[9];
+                    e[0] = cvt_hi16(pw);
+                    e[1] = cvt_lo16(v.x); e[2] = cvt_hi16(v.x); e[3] = cvt_lo16(v.y); e[4] = cvt_hi16(v.y);
+                    e[5] = cvt_lo16(v.z); e[6] = cvt_hi16(v.z); e[7] = cvt_lo16(v.w); e[8] = cvt_hi16(v.w);
+                    float y[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) y[m] = dsp_fmaf(-cpre, e[m], e[m + 1]);
+                    const int s_first = rel + 8 * j;
+                    if (s_first < 1 || s_first + 7 >= S) {   // utterance head / tail: patch element-wise
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const int s = s_first + m;
+                            if (s < 0 || s >= S) y[m] = 0.f;
+                            else if (s == 0) y[m] = e[m + 1];
+                        }
+                    }
+                    float4* dst = reinterpret_cast<float4*>(sm.fbuf) + 2 * j;
+                    dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+                    dst[1] = make_float4(y[4], y[5], y[6], y[7]);
                 }
-                sm.fbuf[i] = y;
             }
         }
         simt::cta_sync();
         if (c + 1 < nchunks) issue_chunk(c + 1);  // raw is free again: overlap the next load with the FFTs
 
-        // ---- one frame pair per 16-lane group
+        // ---- one frame pair per 16-lane group; a warp (two groups) is active or idle as a whole
         const int vA = frame0 + 2 * grp;
-        if (vA <= v_hi) {
+        if (frame0 + 4 * (tid >> 5) <= v_hi) {
             cpx2 x[16];
             {
-                const float* fa = sm.fbuf + (2 * grp) * p.frame_step;
+                const int fb0 = (int)(start - g.a0s + g.s0) + (2 * grp) * p.frame_step + 2 * lane;
+                const float* fa = sm.fbuf + fb0;
                 const float* fb = fa + p.frame_step;
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) {
-                    const int i0 = 2 * (16 * n1 + lane);
                     float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
-                    if (i0 < p.frame_len) { ar = fa[i0]; br = fb[i0]; }
-                    if (i0 + 1 < p.frame_len) { ai = fa[i0 + 1]; bi = fb[i0 + 1]; }
+                    if (n1 < nfull) {
+                        if (!odd_start) {
+                            const float2 a2 = *reinterpret_cast<const float2*>(fa + 32 * n1);
+                            const float2 b2 = *reinterpret_cast<const float2*>(fb + 32 * n1);
+                            ar = a2.x; ai = a2.y; br = b2.x; bi = b2.y;
+                        } else {
+                            ar = fa[32 * n1]; ai = fa[32 * n1 + 1]; br = fb[32 * n1]; bi = fb[32 * n1 + 1];
+                        }
+                    } else if (n1 == nfull) {
+                        const int i0 = 32 * n1 + 2 * lane;
+                        if (i0 < p.frame_len) { ar = fa[32 * n1]; br = fb[32 * n1]; }
+                        if (i0 + 1 < p.frame_len) { ai = fa[32 * n1 + 1]; bi = fb[32 * n1 + 1]; }
+                    }
                     if (HAS_WIN) {
+                        const int i0 = 32 * n1 + 2 * lane;
                         const float w0 = i0 < p.frame_len ? win[i0] : 0.f;
                         const float w1 = i0 + 1 < p.frame_len ? win[i0 + 1] : 0.f;
                         ar *= w0; br *= w0; ai *= w1; bi *= w1;
@@ -265,7 +301,10 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             }
             simt::group_sync();
 
-            // ---- mel filterbank as range sums: filter j = up(range j+1) + down(range j+2)
+            // ---- mel filterbank as range sums over the triangle edges.  For the range [lo, hi) between two
+            // filter centres: rising part of filter j   = sum P[k] * (k-lo)/(hi-lo),
+            //                 falling part of filter j-1 = sum P[k] * (hi-k)/(hi-lo)   (reference base.py:52-57);
+            // the weights are generated arithmetically, each power bin is read once.
             float2 upv[kMaxTasks], dnv[kMaxTasks];
             float2 esum = make_float2(0.f, 0.f);
 #pragma unroll
@@ -273,14 +312,20 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 const int ri = task[lane * kMaxTasks + t];
                 float2 up = make_float2(0.f, 0.f), dn = up;
                 if (ri >= 0) {
-                    const int lo = rng[2 * ri], hi = rng[2 * ri + 1];
-                    for (int k = lo; k < hi; ++k) {
-                        const float2 pw = scr[k];
-                        const float2 w = melw[k];
-                        up = f2fmas(pw, w.x, up);
-                        dn = f2fmas(pw, w.y, dn);
+                    const int lo = rng[3 * ri], hi = rng[3 * ri + 1];
+                    const float inv = rngf[3 * ri + 2];
+                    float fi = 0.f, gi = (float)(hi - lo);
+                    const float2* pp = scr + lo;
+                    const int len = hi - lo;
+#pragma unroll 2
+                    for (int k = 0; k < len; ++k) {
+                        const float2 pw = pp[k];
+                        up = f2fmas(pw, fi, up);
+                        dn = f2fmas(pw, gi, dn);
                         esum = f2add(esum, pw);
+                        fi += 1.f; gi -= 1.f;
                     }
+                    up = f2muls(up, inv); dn = f2muls(dn, inv);
                 }
                 upv[t] = up; dnv[t] = dn;
             }
@@ -293,7 +338,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             simt::group_sync();  // all lanes are done reading P before the staging area overwrites it
             float2* segu = scr;                  // [nrange]
             float2* segd = scr + kMaxRanges;     // [nrange]
-            float2* lmel = scr + 2 * kMaxRanges + 2;  // [nfilt]
+            float2* lmel = scr + 2 * kMaxRanges + 2;  // [nfilt + 1]; the last entry is log(energy)
 #pragma unroll
             for (int t = 0; t < kMaxTasks; ++t) {
                 const int ri = task[lane * kMaxTasks + t];
@@ -301,8 +346,9 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             }
             simt::group_sync();
             const float eps64 = 2.220446049250313e-16f;  // numpy.finfo(float64).eps, reference base.py:26,30
-            for (int j = lane; j < p.nfilt; j += 16) {
-                float2 f = f2add(segu[j + 1], segd[j + 2]);
+            for (int j = lane; j <= p.nfilt; j += 16) {
+                float2 f = esum;
+                if (j < p.nfilt) f = f2add(segu[j + 1], segd[j + 2]);
                 if (f.x == 0.f) f.x = eps64;
                 if (f.y == 0.f) f.y = eps64;
                 lmel[j] = make_float2(dsp_logf(f.x), dsp_logf(f.y));
@@ -312,56 +358,70 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             if (lane < numcep) {
                 float2 acc = make_float2(0.f, 0.f);
                 const float* drow = dct + lane * p.dct_stride;
+#pragma unroll 2
                 for (int m = 0; m < p.nfilt; ++m) acc = f2fmas(lmel[m], drow[m], acc);
-                if (lane == 0 && p.append_energy) {
-                    if (esum.x == 0.f) esum.x = eps64;
-                    if (esum.y == 0.f) esum.y = eps64;
-                    acc = make_float2(dsp_logf(esum.x), dsp_logf(esum.y));
-                }
-                sm.mfcc[(vA - v_lo) * numcep + lane] = acc.x;
+                if (lane == 0 && p.append_energy) acc = lmel[p.nfilt];
+                if (vA <= v_hi) sm.mfcc[(vA - v_lo) * numcep + lane] = acc.x;
                 if (vA + 1 <= v_hi) sm.mfcc[(vA + 1 - v_lo) * numcep + lane] = acc.y;
             }
         }
         simt::cta_sync();  // fbuf may be overwritten by the next conversion pass
     }
 
-    // ---- epilogue: delta (clamped on the utterance), delta-delta (clamped on the delta array), stores
+    // ---- epilogue: delta (clamped on the utterance), delta-delta (clamped on the delta array), stores.
+    // Flat indices advance by the CTA size without any division: (row, col) += (128 / w, 128 % w).
     float* dbuf = sm.fbuf;  // aliases fbuf+raw: no copy is in flight any more
     const int u_lo = tile.f0 - N > 0 ? tile.f0 - N : 0;
     const int u_hi = tile.f0 + tile.nf - 1 + N < F - 1 ? tile.f0 + tile.nf - 1 + N : F - 1;
-    const int nd = (u_hi - u_lo + 1) * numcep;
-    for (int i = tid; i < nd; i += kMfccThreads) {
-        const int uu = u_lo + i / numcep, cc = i % numcep;
-        float acc = 0.f;
-        for (int n = 1; n <= N; ++n) {
-            int hi = uu + n; if (hi > F - 1) hi = F - 1;
-            int lo = uu - n; if (lo < 0) lo = 0;
-            acc = dsp_fmaf((float)n, sm.mfcc[(hi - v_lo) * numcep + cc] - sm.mfcc[(lo - v_lo) * numcep + cc], acc);
+    {
+        const int nd = (u_hi - u_lo + 1) * numcep;
+        const int qstep = kMfccThreads / numcep, rstep = kMfccThreads % numcep;
+        int uu = u_lo + tid / numcep, cc = tid % numcep;
+        for (int i = tid; i < nd; i += kMfccThreads) {
+            float acc = 0.f;
+#pragma unroll
+            for (int n = 1; n <= kMaxDeltaN; ++n) {
+                if (n <= N) {
+                    int hi = uu + n; if (hi > F - 1) hi = F - 1;
+                    int lo = uu - n; if (lo < 0) lo = 0;
+                    acc = dsp_fmaf((float)n, sm.mfcc[(hi - v_lo) * numcep + cc] - sm.mfcc[(lo - v_lo) * numcep + cc], acc);
+                }
+            }
+            dbuf[i] = acc * p.delta_scale;
+            uu += qstep; cc += rstep;
+            if (cc >= numcep) { cc -= numcep; ++uu; }
         }
-        dbuf[i] = acc * p.delta_scale;
     }
     simt::cta_sync();
-    const int width = 3 * numcep;
-    const int nout = tile.nf * width;
-    float* outp = p.out + (row0 + tile.f0) * width;
-    for (int i = tid; i < nout; i += kMfccThreads) {
-        const int tt = tile.f0 + i / width, col = i % width;
-        float v;
-        if (col < numcep) {
-            v = sm.mfcc[(tt - v_lo) * numcep + col];
-        } else if (col < 2 * numcep) {
-            v = dbuf[(tt - u_lo) * numcep + col - numcep];
-        } else {
-            const int cc = col - 2 * numcep;
-            float acc = 0.f;
-            for (int n = 1; n <= N; ++n) {
-                int hi = tt + n; if (hi > F - 1) hi = F - 1;
-                int lo = tt - n; if (lo < 0) lo = 0;
-                acc = dsp_fmaf((float)n, dbuf[(hi - u_lo) * numcep + cc] - dbuf[(lo - u_lo) * numcep + cc], acc);
+    {
+        const int width = 3 * numcep;
+        const int nout = tile.nf * width;
+        float* outp = p.out + (row0 + tile.f0) * width;
+        const int qstep = kMfccThreads / width, rstep = kMfccThreads % width;
+        int tt = tile.f0 + tid / width, col = tid % width;
+        for (int i = tid; i < nout; i += kMfccThreads) {
+            float v;
+            if (col < numcep) {
+                v = sm.mfcc[(tt - v_lo) * numcep + col];
+            } else if (col < 2 * numcep) {
+                v = dbuf[(tt - u_lo) * numcep + col - numcep];
+            } else {
+                const int cc = col - 2 * numcep;
+                float acc = 0.f;
+#pragma unroll
+                for (int n = 1; n <= kMaxDeltaN; ++n) {
+                    if (n <= N) {
+                        int hi = tt + n; if (hi > F - 1) hi = F - 1;
+                        int lo = tt - n; if (lo < 0) lo = 0;
+                        acc = dsp_fmaf((float)n, dbuf[(hi - u_lo) * numcep + cc] - dbuf[(lo - u_lo) * numcep + cc], acc);
+                    }
+                }
+                v = acc * p.delta_scale;
             }
-            v = acc * p.delta_scale;
+            outp[i] = v;
+            tt += qstep; col += rstep;
+            if (col >= width) { col -= width; ++tt; }
         }
-        outp[i] = v;
     }
 }
 

@@ -91,31 +91,30 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
         const double a = -2.0 * kPi * (double)k / 512.0;
         blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
     }
-    // per-bin (rising, falling) mel weights
     const std::vector<double> bins = mel_bin_edges(c);
     std::vector<int> edge(p.nrange + 1);
     edge[0] = 0;
     for (int i = 0; i < c.nfilt + 2; ++i) edge[i + 1] = std::min(std::max((int)bins[i], 0), kBins);
     edge[p.nrange] = kBins;
     for (int i = 1; i <= p.nrange; ++i) edge[i] = std::max(edge[i], edge[i - 1]);
-    p.o_melw = (int)blob.size();
-    {
-        std::vector<float> w(2 * (kBins + 1), 0.f);
-        for (int j = 0; j <= c.nfilt; ++j) {  // range j+1 = bins [bin[j], bin[j+1])
-            const double lo = bins[j], hi = bins[j + 1];
-            for (int k = edge[j + 1]; k < edge[j + 2]; ++k) {
-                w[2 * k] = (j < c.nfilt) ? (float)((k - lo) / (hi - lo)) : 0.f;   // rising edge of filter j
-                w[2 * k + 1] = (j > 0) ? (float)((hi - k) / (hi - lo)) : 0.f;     // falling edge of filter j-1
-            }
-        }
-        blob.insert(blob.end(), w.begin(), w.end());
-    }
     // ranges and their longest-first assignment to the 16 lanes of a group
     p.o_rng = (int)blob.size();
     {
-        std::vector<int> r(2 * kMaxRanges, 0);
-        for (int i = 0; i < p.nrange; ++i) { r[2 * i] = edge[i]; r[2 * i + 1] = edge[i + 1]; }
-        for (int v : r) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
+        // per range: lo, hi (ints) and 1/(hi-lo) (float); the two outer ranges carry no filter -> 0
+        for (int i = 0; i < kMaxRanges; ++i) {
+            int lo = 0, hi = 0; float inv = 0.f;
+            if (i < p.nrange) {
+                lo = edge[i]; hi = edge[i + 1];
+                // weights use the un-clamped float edges of the reference: (k - bin[j]) / (bin[j+1] - bin[j])
+                if (i >= 1 && i <= c.nfilt + 1 && hi > lo) {
+                    if (bins[i - 1] != (double)lo || bins[i] != (double)hi) { err = "mel bin edges fall outside [0, nfft/2]"; return {}; }
+                    inv = (float)(1.0 / (bins[i] - bins[i - 1]));
+                }
+            }
+            float f; std::memcpy(&f, &lo, 4); blob.push_back(f);
+            std::memcpy(&f, &hi, 4); blob.push_back(f);
+            blob.push_back(inv);
+        }
     }
     p.o_task = (int)blob.size();
     {
@@ -155,8 +154,11 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     p.sm_scratch = off; off += kMfccGroups * kScratchUnits * 8;
     p.sm_mfcc = off; off += up16((c.seg_frames + 4 * c.delta_n) * c.numcep * 4);
     p.fbuf_floats = (kFramesPerPass - 1) * c.frame_step + c.frame_len;
-    const int fbuf_bytes = up16(p.fbuf_floats * 4);
-    const int raw_bytes = up16((p.fbuf_floats + 1) * 2) + 32;  // history sample + 16-byte alignment slack either side
+    // raw staging: the chunk's samples + one history sample + up to 7 samples of 16-byte alignment slack either side;
+    // fbuf mirrors raw index for index
+    p.fbuf_vecs = (p.fbuf_floats + 1 + 14 + 7) / 8;
+    const int fbuf_bytes = p.fbuf_vecs * 8 * 4;
+    const int raw_bytes = p.fbuf_vecs * 8 * 2;
     const int dbuf_bytes = up16((c.seg_frames + 2 * c.delta_n) * c.numcep * 4);
     p.sm_fbuf = off;
     p.sm_raw = off + fbuf_bytes;

@@ -28,6 +28,7 @@ void group_sync();                 // barrier over the caller's 16-lane group
 float shfl16(float v, int src);    // __shfl_sync(halfmask, v, src, 16)
 float shfl32_xor(float v, int m);  // full-warp xor shuffle
 int shfl32_i(int v, int src);
+void warp_sync();                  // __syncwarp()
 struct mbar_t { uint64_t v; };
 static inline void mbar_init(mbar_t*, int) {}
 static inline void fence_mbar_init() {}
@@ -42,6 +43,11 @@ DEVFN float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y
 DEVFN float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
 DEVFN float dsp_logf(float x) { return std::log(x); }
 DEVFN float dsp_fmaf(float a, float b, float c) { return std::fmaf(a, b, c); }
+// int16 halves of a 32-bit word -> float
+DEVFN float cvt_lo16(uint32_t w) { return (float)(int16_t)(w & 0xffffu); }
+DEVFN float cvt_hi16(uint32_t w) { return (float)(int16_t)(w >> 16); }
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #else
 // ---------------------------------------------------------------- sm_100a device build
 #include <cuda_runtime.h>
@@ -52,11 +58,12 @@ DEVFN int tid() { return threadIdx.x; }
 DEVFN int bid() { return blockIdx.x; }
 DEVFN int nthreads() { return blockDim.x; }
 DEVFN void cta_sync() { __syncthreads(); }
-DEVFN unsigned group_mask() { return (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu; }
-DEVFN void group_sync() { __syncwarp(group_mask()); }
-DEVFN float shfl16(float v, int src) { return __shfl_sync(group_mask(), v, src, 16); }
+// the two 16-lane groups of a warp always run the same code path, so full-warp primitives are safe
+DEVFN void group_sync() { __syncwarp(); }
+DEVFN float shfl16(float v, int src) { return __shfl_sync(0xffffffffu, v, src, 16); }
 DEVFN float shfl32_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEVFN int shfl32_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+DEVFN void warp_sync() { __syncwarp(); }
 
 // mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP): global -> shared::cta.
 struct mbar_t { uint64_t v; };
@@ -90,6 +97,10 @@ DEVFN float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 DEVFN float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 DEVFN float dsp_logf(float x) { return logf(x); }
 DEVFN float dsp_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
+// int16 halves of a 32-bit word -> float without the (slow, XU-pipe) I2F: splice the biased 16-bit
+// value into the mantissa of 2^23 and subtract 2^23 + 2^15 (exact).
+DEVFN float cvt_lo16(uint32_t w) { return __uint_as_float(__byte_perm(w ^ 0x80008000u, 0x4B000000u, 0x7610)) - 8421376.0f; }
+DEVFN float cvt_hi16(uint32_t w) { return __uint_as_float(__byte_perm(w ^ 0x80008000u, 0x4B000000u, 0x7632)) - 8421376.0f; }
 #endif
 
 // scalar-broadcast forms (the scalar folds into the packed instruction's .F32 operand)

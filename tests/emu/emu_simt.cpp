@@ -81,7 +81,7 @@ float shfl16(float v, int src) {
     group_sync();
     return r;
 }
-static void warp_sync() { int w = emu::g_cur / 32; emu::barrier(emu::g_warp_count[w], emu::g_warp_gen[w], 32); }
+void warp_sync() { int w = emu::g_cur / 32; emu::barrier(emu::g_warp_count[w], emu::g_warp_gen[w], 32); }
 float shfl32_xor(float v, int m) {
     const int me = emu::g_cur;
     emu::g_slot[me] = v;
