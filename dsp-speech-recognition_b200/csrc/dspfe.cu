@@ -25,10 +25,24 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return fail(DSPFE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
     } while (0)
 
-template <bool HAS_WIN>
+template <bool HAS_WIN, int NFULL>
 __global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __grid_constant__ MfccParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    mfcc_cta<HAS_WIN>(p, smem);
+    mfcc_cta<HAS_WIN, NFULL>(p, smem);
+}
+
+typedef void (*mfcc_kernel_t)(const MfccParams);
+// specialisations: rectangular / windowed x frame_len/32 in {12 (25 ms @16 kHz), 15 (30 ms @16 kHz), generic}
+mfcc_kernel_t pick_kernel(bool has_win, int frame_len) {
+    const int nfull = frame_len >> 5;
+    if (has_win) {
+        if (nfull == 12) return mfcc_delta_kernel<true, 12>;
+        if (nfull == 15) return mfcc_delta_kernel<true, 15>;
+        return mfcc_delta_kernel<true, -1>;
+    }
+    if (nfull == 12) return mfcc_delta_kernel<false, 12>;
+    if (nfull == 15) return mfcc_delta_kernel<false, 15>;
+    return mfcc_delta_kernel<false, -1>;
 }
 
 MfccConfig to_config(const dspfe_mfcc_params& q) {
@@ -87,6 +101,7 @@ struct dspfe_plan {
     MfccParams layout;          // scalars + offsets filled by build_mfcc_tables; pointers filled per call
     float* d_tables = nullptr;
     bool has_win = false;
+    mfcc_kernel_t kernel = nullptr;
     Workspace ws;
     HostSlot slots[kSlots];
     int width = 0;              // 3 * numcep
@@ -111,8 +126,7 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const int16_t* d_pcm, int64_t tot
     MfccParams mp = pl->layout;
     mp.pcm = d_pcm; mp.total_samples = total_samples; mp.seg_start = ws.seg_start; mp.seg_len = ws.seg_len;
     mp.frame_off = pp.frame_off; mp.tiles = ws.tiles; mp.ntiles = ws.ntiles; mp.tables = pl->d_tables; mp.out = d_out;
-    if (pl->has_win) mfcc_delta_kernel<true><<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
-    else mfcc_delta_kernel<false><<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
+    pl->kernel<<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
     CUDA_TRY(cudaGetLastError());
     return DSPFE_OK;
 }
@@ -173,8 +187,8 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     pl->width = 3 * pl->cfg.numcep;
     cudaError_t e = cudaMalloc(&pl->d_tables, blob.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_delta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout.sm_total);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_delta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout.sm_total);
+    pl->kernel = pick_kernel(pl->has_win, pl->cfg.frame_len);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout.sm_total);
     if (e != cudaSuccess) { cudaFree(pl->d_tables); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
     *plan = pl;
     return DSPFE_OK;
@@ -202,13 +216,8 @@ int dspfe_plan_info(const dspfe_plan* pl, int32_t* smem_bytes, int32_t* ctas_per
     if (!pl) return fail(DSPFE_ERR_INVALID_ARG, "null plan");
     cudaFuncAttributes fa;
     int nb = 0;
-    if (pl->has_win) {
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_delta_kernel<true>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_delta_kernel<true>, kMfccThreads, pl->layout.sm_total));
-    } else {
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_delta_kernel<false>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_delta_kernel<false>, kMfccThreads, pl->layout.sm_total));
-    }
+    CUDA_TRY(cudaFuncGetAttributes(&fa, pl->kernel));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pl->kernel, kMfccThreads, pl->layout.sm_total));
     if (smem_bytes) *smem_bytes = pl->layout.sm_total;
     if (ctas_per_sm) *ctas_per_sm = nb;
     if (regs_per_thread) *regs_per_thread = fa.numRegs;

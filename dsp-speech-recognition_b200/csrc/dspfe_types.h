@@ -11,7 +11,8 @@ constexpr int kMaxNfilt = 40;
 constexpr int kMaxNumcep = 16;
 constexpr int kMaxDeltaN = 4;
 constexpr int kMaxRanges = kMaxNfilt + 3;
-constexpr int kMaxTasks = 4;          // mel ranges per lane
+constexpr int kMaxTasks = 4;          // mel sub-ranges per lane
+constexpr int kMaxSubs = 64;          // mel sub-ranges (ranges longer than 16 bins are split)
 constexpr int kScratchUnits = 272;    // 8-byte units per group: 16x17 transpose tile, >= 257 power bins
 constexpr int kMfccThreads = 128;     // 8 groups -> 16 frames per pass of the chunk loop
 constexpr int kMfccGroups = kMfccThreads / kGroupLanes;
@@ -34,7 +35,7 @@ struct MfccParams {
     int frame_len, frame_step, nfilt, numcep, delta_n, seg_frames, nrange, append_energy;
     float preemph, delta_scale, pow_scale;
     // table blob offsets, in floats
-    int o_twa, o_twp, o_rng, o_task, o_dct, o_win, dct_stride, tbl_floats;
+    int o_twa, o_twp, o_sub, o_rsub, o_task, o_dct, o_win, dct_stride, tbl_floats;
     // shared-memory carve-up, in bytes
     int sm_mbar, sm_scratch, sm_mfcc, sm_fbuf, sm_raw, sm_total;
     int fbuf_floats;            // (kFramesPerPass-1)*step + frame_len: samples one chunk needs

@@ -107,7 +107,8 @@ DEVFN ChunkGeom chunk_geom(const MfccParams& p, int64_t start, int S, int frame0
     return g;
 }
 
-template <bool HAS_WIN>
+// NFULL = frame_len / 32 (FFT input rows that lie fully inside the frame) when known at compile time, else -1.
+template <bool HAS_WIN, int NFULL>
 DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     const int tid = simt::tid();
     const int lane = tid & 15;
@@ -142,8 +143,9 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
 
     const float2* twa = reinterpret_cast<const float2*>(sm.tables + p.o_twa);
     const float2* twp = reinterpret_cast<const float2*>(sm.tables + p.o_twp);
-    const int* rng = reinterpret_cast<const int*>(sm.tables + p.o_rng);   // per range: lo, hi, 1/(hi-lo) (0 outside the filters)
-    const float* rngf = sm.tables + p.o_rng;
+    const int* subi = reinterpret_cast<const int*>(sm.tables + p.o_sub);   // per sub-range: lo, len | fi0, gi0, inv
+    const float* subf = sm.tables + p.o_sub;
+    const int* rsub = reinterpret_cast<const int*>(sm.tables + p.o_rsub);  // per range: first sub-range, count
     const int* task = reinterpret_cast<const int*>(sm.tables + p.o_task);
     const float* dct = sm.tables + p.o_dct;
     const float* win = sm.tables + p.o_win;
@@ -160,8 +162,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     };
     issue_chunk(0);
 
-    const int nfull = p.frame_len >> 5;        // FFT input rows (32 samples each) that lie fully inside the frame
-    const bool odd_start = (start & 1) != 0;   // frame starts are 8-byte aligned in fbuf unless the utterance starts on an odd sample
+    const int nfull = NFULL >= 0 ? NFULL : (p.frame_len >> 5);
     uint32_t parity = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int frame0 = v_lo + c * kFramesPerPass;
@@ -169,8 +170,8 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
         if (g.bulk_bytes > 0) { simt::mbar_wait(sm.mbar, parity); parity ^= 1; }
         if (c == 0) simt::cta_sync();  // chunk-0 tail stores -> visible (later chunks: the loop-end barrier)
 
-        // ---- raw int16 -> pre-emphasised fp32, 8 samples per thread.  fbuf[q] pairs with raw[q] (packed sample
-        // a0s + q).  Reference: y[0] = x[0], y[n] = x[n] - c*x[n-1] (sigproc.py:185), zeros past the end (:84-87).
+        // ---- raw int16 -> pre-emphasised fp32, 8 samples per thread.  Sample q of the staging area (packed sample
+        // a0s + q) lands in plane q&1 at index q>>1.  Reference: y[0] = x[0], y[n] = x[n] - c*x[n-1] (sigproc.py:185), zeros past the end (:84-87).
         {
             const int rel = (int)(g.a0s - start);  // utterance sample index of raw[0] (may be negative)
             const float cpre = p.preemph;
@@ -198,43 +199,44 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                             else if (s == 0) y[m] = e[m + 1];
                         }
                     }
-                    float4* dst = reinterpret_cast<float4*>(sm.fbuf) + 2 * j;
-                    dst[0] = make_float4(y[0], y[1], y[2], y[3]);
-                    dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+                    // even-index samples and odd-index samples go to separate planes: the FFT loads (re from one
+                    // plane, im from the other, consecutive lanes -> consecutive words) are then conflict-free
+                    reinterpret_cast<float4*>(sm.fbuf)[j] = make_float4(y[0], y[2], y[4], y[6]);
+                    reinterpret_cast<float4*>(sm.fbuf + 4 * p.fbuf_vecs)[j] = make_float4(y[1], y[3], y[5], y[7]);
                 }
             }
         }
         simt::cta_sync();
         if (c + 1 < nchunks) issue_chunk(c + 1);  // raw is free again: overlap the next load with the FFTs
 
-        // ---- one frame pair per 16-lane group; a warp (two groups) is active or idle as a whole
-        const int vA = frame0 + 2 * grp;
+        // ---- one frame pair per 16-lane group; a warp (two groups) is active or idle as a whole.  Within a warp
+        // group 0 packs frames (f, f+2) and group 1 packs (f+1, f+3): the two groups' loads then fall into
+        // disjoint halves of the 32 banks (frame step/2 = 80 words = 16 mod 32 for the 10 ms step).
+        const int fl = 4 * (tid >> 5) + (grp & 1);   // chunk-local index of the frame in the .x halves; .y = fl + 2
+        const int vA = frame0 + fl;
         if (frame0 + 4 * (tid >> 5) <= v_hi) {
             cpx2 x[16];
             {
-                const int fb0 = (int)(start - g.a0s + g.s0) + (2 * grp) * p.frame_step + 2 * lane;
-                const float* fa = sm.fbuf + fb0;
-                const float* fb = fa + p.frame_step;
+                const int fb0 = (int)(start - g.a0s + g.s0) + fl * p.frame_step;   // staging index of the frame's sample 0
+                const float* plane_e = sm.fbuf;
+                const float* plane_o = sm.fbuf + 4 * p.fbuf_vecs;
+                const bool odd = (fb0 & 1) != 0;                                   // uniform over the CTA (even frame step)
+                const float* fre = (odd ? plane_o : plane_e) + (fb0 >> 1) + lane;      // sample 2n   of the frame
+                const float* fim = (odd ? plane_e + 1 : plane_o) + (fb0 >> 1) + lane;  // sample 2n+1 of the frame
+                const int dB = p.frame_step;                                       // two frames ahead = step words in a plane
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) {
+                    // four scalar loads land directly in the (frame A, frame B) register pairs
                     float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
                     if (n1 < nfull) {
-                        if (!odd_start) {
-                            const float2 a2 = *reinterpret_cast<const float2*>(fa + 32 * n1);
-                            const float2 b2 = *reinterpret_cast<const float2*>(fb + 32 * n1);
-                            ar = a2.x; ai = a2.y; br = b2.x; bi = b2.y;
-                        } else {
-                            ar = fa[32 * n1]; ai = fa[32 * n1 + 1]; br = fb[32 * n1]; bi = fb[32 * n1 + 1];
-                        }
+                        ar = fre[16 * n1]; ai = fim[16 * n1]; br = fre[16 * n1 + dB]; bi = fim[16 * n1 + dB];
                     } else if (n1 == nfull) {
                         const int i0 = 32 * n1 + 2 * lane;
-                        if (i0 < p.frame_len) { ar = fa[32 * n1]; br = fb[32 * n1]; }
-                        if (i0 + 1 < p.frame_len) { ai = fa[32 * n1 + 1]; bi = fb[32 * n1 + 1]; }
+                        if (i0 < p.frame_len) { ar = fre[16 * n1]; br = fre[16 * n1 + dB]; }
+                        if (i0 + 1 < p.frame_len) { ai = fim[16 * n1]; bi = fim[16 * n1 + dB]; }
                     }
-                    if (HAS_WIN) {
-                        const int i0 = 32 * n1 + 2 * lane;
-                        const float w0 = i0 < p.frame_len ? win[i0] : 0.f;
-                        const float w1 = i0 + 1 < p.frame_len ? win[i0 + 1] : 0.f;
+                    if (HAS_WIN) {   // window planes are zero-padded to 256 entries each
+                        const float w0 = win[16 * n1 + lane], w1 = win[256 + 16 * n1 + lane];
                         ar *= w0; br *= w0; ai *= w1; bi *= w1;
                     }
                     x[n1].re = make_float2(ar, br);
@@ -301,31 +303,28 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             }
             simt::group_sync();
 
-            // ---- mel filterbank as range sums over the triangle edges.  For the range [lo, hi) between two
-            // filter centres: rising part of filter j   = sum P[k] * (k-lo)/(hi-lo),
-            //                 falling part of filter j-1 = sum P[k] * (hi-k)/(hi-lo)   (reference base.py:52-57);
-            // the weights are generated arithmetically, each power bin is read once.
+            // ---- mel filterbank as sums over sub-ranges of the triangle edges (see mfcc_tables.h): the weights
+            // are generated arithmetically, each power bin is read exactly once.
             float2 upv[kMaxTasks], dnv[kMaxTasks];
             float2 esum = make_float2(0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < kMaxTasks; ++t) {
-                const int ri = task[lane * kMaxTasks + t];
+                const int si = task[lane * kMaxTasks + t];
                 float2 up = make_float2(0.f, 0.f), dn = up;
-                if (ri >= 0) {
-                    const int lo = rng[3 * ri], hi = rng[3 * ri + 1];
-                    const float inv = rngf[3 * ri + 2];
-                    float fi = 0.f, gi = (float)(hi - lo);
-                    const float2* pp = scr + lo;
-                    const int len = hi - lo;
-#pragma unroll 2
+                if (si >= 0) {
+                    const int len = subi[5 * si + 1];
+                    const float2* pp = scr + subi[5 * si];
+                    float fi = subf[5 * si + 2], gi = subf[5 * si + 3];
+                    const float inv = subf[5 * si + 4];
+#pragma unroll 4
                     for (int k = 0; k < len; ++k) {
                         const float2 pw = pp[k];
                         up = f2fmas(pw, fi, up);
                         dn = f2fmas(pw, gi, dn);
-                        esum = f2add(esum, pw);
                         fi += 1.f; gi -= 1.f;
                     }
                     up = f2muls(up, inv); dn = f2muls(dn, inv);
+                    esum = f2add(esum, f2add(up, dn));   // rising + falling weights sum to 1: this is sum(P) of the sub-range
                 }
                 upv[t] = up; dnv[t] = dn;
             }
@@ -336,19 +335,25 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 esum.y += simt::shfl16(esum.y, lane ^ m);
             }
             simt::group_sync();  // all lanes are done reading P before the staging area overwrites it
-            float2* segu = scr;                  // [nrange]
-            float2* segd = scr + kMaxRanges;     // [nrange]
-            float2* lmel = scr + 2 * kMaxRanges + 2;  // [nfilt + 1]; the last entry is log(energy)
+            float2* segu = scr;                   // [kMaxSubs]
+            float2* segd = scr + kMaxSubs;        // [kMaxSubs]
+            float2* lmel = scr + 2 * kMaxSubs;    // [nfilt + 1]; the last entry is log(energy)
 #pragma unroll
             for (int t = 0; t < kMaxTasks; ++t) {
-                const int ri = task[lane * kMaxTasks + t];
-                if (ri >= 0) { segu[ri] = upv[t]; segd[ri] = dnv[t]; }
+                const int si = task[lane * kMaxTasks + t];
+                if (si >= 0) { segu[si] = upv[t]; segd[si] = dnv[t]; }
             }
             simt::group_sync();
             const float eps64 = 2.220446049250313e-16f;  // numpy.finfo(float64).eps, reference base.py:26,30
             for (int j = lane; j <= p.nfilt; j += 16) {
                 float2 f = esum;
-                if (j < p.nfilt) f = f2add(segu[j + 1], segd[j + 2]);
+                if (j < p.nfilt) {   // filter j = rising part over range j+1 + falling part over range j+2
+                    f = make_float2(0.f, 0.f);
+                    const int a0 = rsub[2 * (j + 1)], an = rsub[2 * (j + 1) + 1];
+                    for (int q = 0; q < an; ++q) f = f2add(f, segu[a0 + q]);
+                    const int b0 = rsub[2 * (j + 2)], bn = rsub[2 * (j + 2) + 1];
+                    for (int q = 0; q < bn; ++q) f = f2add(f, segd[b0 + q]);
+                }
                 if (f.x == 0.f) f.x = eps64;
                 if (f.y == 0.f) f.y = eps64;
                 lmel[j] = make_float2(dsp_logf(f.x), dsp_logf(f.y));
@@ -357,35 +362,41 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             // ---- DCT-II (ortho) * lifter, c0 := log(energy)
             if (lane < numcep) {
                 float2 acc = make_float2(0.f, 0.f);
-                const float* drow = dct + lane * p.dct_stride;
-#pragma unroll 2
-                for (int m = 0; m < p.nfilt; ++m) acc = f2fmas(lmel[m], drow[m], acc);
+                const float2* drow = reinterpret_cast<const float2*>(dct + lane * p.dct_stride);
+                const float4* lm4 = reinterpret_cast<const float4*>(lmel);
+                const int half = (p.nfilt + 1) >> 1;   // odd nfilt: the pad coefficient is 0 and multiplies log(energy)
+#pragma unroll 4
+                for (int m = 0; m < half; ++m) {
+                    const float4 l = lm4[m];
+                    const float2 w = drow[m];
+                    acc = f2fmas(make_float2(l.x, l.y), w.x, acc);
+                    acc = f2fmas(make_float2(l.z, l.w), w.y, acc);
+                }
                 if (lane == 0 && p.append_energy) acc = lmel[p.nfilt];
                 if (vA <= v_hi) sm.mfcc[(vA - v_lo) * numcep + lane] = acc.x;
-                if (vA + 1 <= v_hi) sm.mfcc[(vA + 1 - v_lo) * numcep + lane] = acc.y;
+                if (vA + 2 <= v_hi) sm.mfcc[(vA + 2 - v_lo) * numcep + lane] = acc.y;
             }
         }
         simt::cta_sync();  // fbuf may be overwritten by the next conversion pass
     }
 
     // ---- epilogue: delta (clamped on the utterance), delta-delta (clamped on the delta array), stores.
-    // Flat indices advance by the CTA size without any division: (row, col) += (128 / w, 128 % w).
-    float* dbuf = sm.fbuf;  // aliases fbuf+raw: no copy is in flight any more
+    // Three uniform passes (no divergent per-column work); flat indices advance by the CTA size without any
+    // division: (row, col) += (128 / w, 128 % w).
+    float* dbuf = sm.fbuf;                                   // aliases fbuf+raw: no copy is in flight any more
+    float* ddbuf = reinterpret_cast<float*>(sm.scratch);     // aliases the FFT scratch
     const int u_lo = tile.f0 - N > 0 ? tile.f0 - N : 0;
     const int u_hi = tile.f0 + tile.nf - 1 + N < F - 1 ? tile.f0 + tile.nf - 1 + N : F - 1;
+    const int qstep = kMfccThreads / numcep, rstep = kMfccThreads % numcep;
     {
         const int nd = (u_hi - u_lo + 1) * numcep;
-        const int qstep = kMfccThreads / numcep, rstep = kMfccThreads % numcep;
         int uu = u_lo + tid / numcep, cc = tid % numcep;
         for (int i = tid; i < nd; i += kMfccThreads) {
             float acc = 0.f;
-#pragma unroll
-            for (int n = 1; n <= kMaxDeltaN; ++n) {
-                if (n <= N) {
-                    int hi = uu + n; if (hi > F - 1) hi = F - 1;
-                    int lo = uu - n; if (lo < 0) lo = 0;
-                    acc = dsp_fmaf((float)n, sm.mfcc[(hi - v_lo) * numcep + cc] - sm.mfcc[(lo - v_lo) * numcep + cc], acc);
-                }
+            for (int n = 1; n <= N; ++n) {
+                int hi = uu + n; if (hi > F - 1) hi = F - 1;
+                int lo = uu - n; if (lo < 0) lo = 0;
+                acc = dsp_fmaf((float)n, sm.mfcc[(hi - v_lo) * numcep + cc] - sm.mfcc[(lo - v_lo) * numcep + cc], acc);
             }
             dbuf[i] = acc * p.delta_scale;
             uu += qstep; cc += rstep;
@@ -394,33 +405,36 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     }
     simt::cta_sync();
     {
+        const int ndd = tile.nf * numcep;
+        int tt = tile.f0 + tid / numcep, cc = tid % numcep;
+        for (int i = tid; i < ndd; i += kMfccThreads) {
+            float acc = 0.f;
+            for (int n = 1; n <= N; ++n) {
+                int hi = tt + n; if (hi > F - 1) hi = F - 1;
+                int lo = tt - n; if (lo < 0) lo = 0;
+                acc = dsp_fmaf((float)n, dbuf[(hi - u_lo) * numcep + cc] - dbuf[(lo - u_lo) * numcep + cc], acc);
+            }
+            ddbuf[i] = acc * p.delta_scale;
+            tt += qstep; cc += rstep;
+            if (cc >= numcep) { cc -= numcep; ++tt; }
+        }
+    }
+    simt::cta_sync();
+    {
         const int width = 3 * numcep;
         const int nout = tile.nf * width;
         float* outp = p.out + (row0 + tile.f0) * width;
-        const int qstep = kMfccThreads / width, rstep = kMfccThreads % width;
-        int tt = tile.f0 + tid / width, col = tid % width;
+        const float* src0 = sm.mfcc + (tile.f0 - v_lo) * numcep;
+        const float* src1 = dbuf + (tile.f0 - u_lo) * numcep;
+        const int qs = kMfccThreads / width, rs = kMfccThreads % width;
+        int row = tid / width, col = tid % width;
         for (int i = tid; i < nout; i += kMfccThreads) {
-            float v;
-            if (col < numcep) {
-                v = sm.mfcc[(tt - v_lo) * numcep + col];
-            } else if (col < 2 * numcep) {
-                v = dbuf[(tt - u_lo) * numcep + col - numcep];
-            } else {
-                const int cc = col - 2 * numcep;
-                float acc = 0.f;
-#pragma unroll
-                for (int n = 1; n <= kMaxDeltaN; ++n) {
-                    if (n <= N) {
-                        int hi = tt + n; if (hi > F - 1) hi = F - 1;
-                        int lo = tt - n; if (lo < 0) lo = 0;
-                        acc = dsp_fmaf((float)n, dbuf[(hi - u_lo) * numcep + cc] - dbuf[(lo - u_lo) * numcep + cc], acc);
-                    }
-                }
-                v = acc * p.delta_scale;
-            }
-            outp[i] = v;
-            tt += qstep; col += rstep;
-            if (col >= width) { col -= width; ++tt; }
+            const float* s = src0; int cc = col;
+            if (col >= numcep) { s = src1; cc = col - numcep; }
+            if (col >= 2 * numcep) { s = ddbuf; cc = col - 2 * numcep; }
+            outp[i] = s[row * numcep + cc];
+            row += qs; col += rs;
+            if (col >= width) { col -= width; ++row; }
         }
     }
 }

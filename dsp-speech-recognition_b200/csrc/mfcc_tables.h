@@ -97,44 +97,59 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     for (int i = 0; i < c.nfilt + 2; ++i) edge[i + 1] = std::min(std::max((int)bins[i], 0), kBins);
     edge[p.nrange] = kBins;
     for (int i = 1; i <= p.nrange; ++i) edge[i] = std::max(edge[i], edge[i - 1]);
-    // ranges and their longest-first assignment to the 16 lanes of a group
-    p.o_rng = (int)blob.size();
-    {
-        // per range: lo, hi (ints) and 1/(hi-lo) (float); the two outer ranges carry no filter -> 0
-        for (int i = 0; i < kMaxRanges; ++i) {
-            int lo = 0, hi = 0; float inv = 0.f;
-            if (i < p.nrange) {
-                lo = edge[i]; hi = edge[i + 1];
-                // weights use the un-clamped float edges of the reference: (k - bin[j]) / (bin[j+1] - bin[j])
-                if (i >= 1 && i <= c.nfilt + 1 && hi > lo) {
-                    if (bins[i - 1] != (double)lo || bins[i] != (double)hi) { err = "mel bin edges fall outside [0, nfft/2]"; return {}; }
-                    inv = (float)(1.0 / (bins[i] - bins[i - 1]));
-                }
+    // Mel ranges = the intervals between consecutive filter centres (plus the two unfiltered ends).  Inside
+    // range [lo, hi): rising weight of filter j = (k-lo)/(hi-lo), falling weight of filter j-1 = (hi-k)/(hi-lo)
+    // (reference base.py:52-57).  Ranges longer than 16 bins are split into sub-ranges so that the 16 lanes of
+    // a group get balanced work; each sub-range starts its weight counters at (sub_lo - lo, hi - sub_lo).
+    struct Sub { int lo, len; float fi0, gi0, inv; int range; };
+    std::vector<Sub> subs;
+    std::vector<int> rsub(2 * kMaxRanges, 0);
+    for (int i = 0; i < p.nrange; ++i) {
+        const int lo = edge[i], hi = edge[i + 1];
+        rsub[2 * i] = (int)subs.size();
+        if (hi > lo) {
+            if (i >= 1 && i <= c.nfilt + 1 && (bins[i - 1] != (double)lo || bins[i] != (double)hi)) {
+                err = "mel bin edges fall outside [0, nfft/2]"; return {};
             }
-            float f; std::memcpy(&f, &lo, 4); blob.push_back(f);
-            std::memcpy(&f, &hi, 4); blob.push_back(f);
-            blob.push_back(inv);
+            const int parts = (hi - lo + 15) / 16;
+            for (int q = 0; q < parts; ++q) {
+                const int a = lo + (int)((int64_t)(hi - lo) * q / parts), b = lo + (int)((int64_t)(hi - lo) * (q + 1) / parts);
+                subs.push_back({a, b - a, (float)(a - lo), (float)(hi - a), (float)(1.0 / (hi - lo)), i});
+            }
         }
+        rsub[2 * i + 1] = (int)subs.size() - rsub[2 * i];
     }
+    if ((int)subs.size() > kMaxSubs) { err = "too many mel sub-ranges"; return {}; }
+    p.o_sub = (int)blob.size();
+    for (int i = 0; i < kMaxSubs; ++i) {
+        Sub s = i < (int)subs.size() ? subs[i] : Sub{0, 0, 0.f, 0.f, 0.f, 0};
+        float f; std::memcpy(&f, &s.lo, 4); blob.push_back(f);
+        std::memcpy(&f, &s.len, 4); blob.push_back(f);
+        blob.push_back(s.fi0); blob.push_back(s.gi0); blob.push_back(s.inv);
+    }
+    p.o_rsub = (int)blob.size();
+    for (int v : rsub) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
+    // longest-first assignment of the sub-ranges to the 16 lanes of a group
     p.o_task = (int)blob.size();
     {
         std::vector<int> order;
-        for (int i = 0; i < p.nrange; ++i) if (edge[i + 1] > edge[i]) order.push_back(i);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return edge[a + 1] - edge[a] > edge[b + 1] - edge[b]; });
+        for (int i = 0; i < (int)subs.size(); ++i) order.push_back(i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subs[a].len > subs[b].len; });
         std::vector<int> t(kGroupLanes * kMaxTasks, -1), load(kGroupLanes, 0), cnt(kGroupLanes, 0);
-        for (int ri : order) {
+        for (int si : order) {
             int best = -1;
             for (int l = 0; l < kGroupLanes; ++l)
                 if (cnt[l] < kMaxTasks && (best < 0 || load[l] < load[best])) best = l;
-            if (best < 0) { err = "mel range assignment overflow"; return {}; }
-            t[best * kMaxTasks + cnt[best]++] = ri;
-            load[best] += edge[ri + 1] - edge[ri];
+            if (best < 0) { err = "mel sub-range assignment overflow"; return {}; }
+            t[best * kMaxTasks + cnt[best]++] = si;
+            load[best] += subs[si].len;
         }
         for (int v : t) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
     }
+    align4();
     // DCT-II (ortho) rows premultiplied by the lifter
     p.o_dct = (int)blob.size();
-    p.dct_stride = c.nfilt | 1;
+    p.dct_stride = c.nfilt; while ((p.dct_stride & 3) != 2) ++p.dct_stride;   // float2 rows, conflict-free over lanes
     for (int k = 0; k < c.numcep; ++k) {
         const double s = std::sqrt((k == 0 ? 1.0 : 2.0) / c.nfilt);
         const double lift = c.ceplifter > 0 ? 1.0 + (c.ceplifter / 2.0) * std::sin(kPi * k / c.ceplifter) : 1.0;
@@ -143,7 +158,10 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     }
     align4();
     p.o_win = (int)blob.size();
-    for (double w : c.window) blob.push_back((float)w);
+    if (!c.window.empty()) {   // two zero-padded planes: even-index and odd-index window samples
+        for (int q = 0; q < 2; ++q)
+            for (int n = 0; n < 256; ++n) { const int i = 2 * n + q; blob.push_back(i < c.frame_len ? (float)c.window[i] : 0.f); }
+    }
     align4();
     p.tbl_floats = (int)blob.size();
 
@@ -151,7 +169,8 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     auto up16 = [](int v) { return (v + 15) & ~15; };
     int off = up16(p.tbl_floats * 4);
     p.sm_mbar = off; off += 16;
-    p.sm_scratch = off; off += kMfccGroups * kScratchUnits * 8;
+    // FFT scratch; the epilogue reuses it for the delta-delta rows of the tile
+    p.sm_scratch = off; off += std::max(kMfccGroups * kScratchUnits * 8, up16(c.seg_frames * c.numcep * 4));
     p.sm_mfcc = off; off += up16((c.seg_frames + 4 * c.delta_n) * c.numcep * 4);
     p.fbuf_floats = (kFramesPerPass - 1) * c.frame_step + c.frame_len;
     // raw staging: the chunk's samples + one history sample + up to 7 samples of 16-byte alignment slack either side;

@@ -15,8 +15,9 @@ namespace {
 struct Args { MfccParams p; bool has_win; std::vector<unsigned char>* smem; };
 void body(void* a) {
     Args* A = (Args*)a;
-    if (A->has_win) mfcc_cta<true>(A->p, A->smem->data());
-    else mfcc_cta<false>(A->p, A->smem->data());
+    const int nfull = A->p.frame_len >> 5;
+    if (A->has_win) { if (nfull == 12) mfcc_cta<true, 12>(A->p, A->smem->data()); else mfcc_cta<true, -1>(A->p, A->smem->data()); }
+    else { if (nfull == 12) mfcc_cta<false, 12>(A->p, A->smem->data()); else mfcc_cta<false, -1>(A->p, A->smem->data()); }
 }
 }  // namespace
 
