@@ -7,7 +7,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/dspfe.h"
+#include "abi_common.h"
 #include "mfcc_kernel.cuh"
 #include "mfcc_tables.h"
 #include "prep_kernel.cuh"
@@ -15,15 +15,6 @@
 using namespace dspfe;
 
 namespace {
-
-thread_local std::string g_err;
-int fail(int code, const std::string& msg) { g_err = msg; return code; }
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t e_ = (expr);                                                               \
-        if (e_ != cudaSuccess)                                                                 \
-            return fail(DSPFE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
-    } while (0)
 
 template <bool HAS_WIN, int NFULL>
 __global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __grid_constant__ MfccParams p) {
@@ -121,13 +112,13 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const int16_t* d_pcm, int64_t tot
     pp.seg_start = ws.seg_start; pp.seg_len = ws.seg_len; pp.frame_off = d_frame_off ? d_frame_off : ws.frame_off;
     pp.tile_off = ws.tile_off; pp.tiles = ws.tiles; pp.ntiles = ws.ntiles; pp.max_tiles = (int)max_tiles;
     prep_kernel<<<1, kPrepThreads, 0, st>>>(pp);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH_CHECK("prep_kernel", st);
 
     MfccParams mp = pl->layout;
     mp.pcm = d_pcm; mp.total_samples = total_samples; mp.seg_start = ws.seg_start; mp.seg_len = ws.seg_len;
     mp.frame_off = pp.frame_off; mp.tiles = ws.tiles; mp.ntiles = ws.ntiles; mp.tables = pl->d_tables; mp.out = d_out;
     pl->kernel<<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH_CHECK("mfcc_delta_kernel", st);
     return DSPFE_OK;
 }
 

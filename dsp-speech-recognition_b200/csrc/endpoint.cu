@@ -1,0 +1,179 @@
+// C ABI of the endpoint-detection path (include/dspfe.h, "endpoint" section).  Kernels: endpoint_kernel.cuh.
+#include <cstring>
+#include <vector>
+
+#include "abi_common.h"
+#include "dspfe_types.h"
+#include "endpoint_kernel.cuh"
+
+using namespace dspfe;
+
+struct dspfe_endpoint_plan {
+    dspfe_endpoint_params prm;
+    EpRule rule;
+    int frame_len, frame_step, q, rem;
+    // workspaces
+    int64_t cap_utt = 0, cap_blocks = 0, cap_frames = 0;
+    int64_t *frame_off = nullptr, *block_off = nullptr;
+    int32_t *blk = nullptr, *asum = nullptr, *zcr = nullptr;
+    // host-path staging
+    cudaStream_t stream = nullptr;
+    int16_t* d_pcm = nullptr; int64_t cap_samples = 0;
+    int64_t* d_off = nullptr; int32_t* d_lr = nullptr; int64_t cap_hutt = 0;
+};
+
+namespace {
+
+int fill_rule(const dspfe_endpoint_params& q, EpRule& r, int& frame_len, int& frame_step) {
+    if (q.samplerate <= 0 || !(q.cfg_frame > 0) || !(q.cfg_step > 0)) return fail(DSPFE_ERR_INVALID_ARG, "bad endpoint parameters");
+    r.cfg_frame = q.cfg_frame; r.cfg_step = q.cfg_step; r.mh1 = q.mh1; r.mh2 = q.mh2; r.th = q.th;
+    r.l_sil = q.l_sil; r.r_sil = q.r_sil; r.sigma = q.sigma; r.zcr_max_shift = q.zcr_max_shift; r.zcr_r_sil = q.zcr_r_sil;
+    r.min_span = q.min_span; r.rate = q.samplerate;
+    frame_len = (int)((double)q.samplerate * q.cfg_frame);   // to_frames: int(rate * t)   (sigproc.py:19)
+    frame_step = (int)(q.cfg_step * (double)q.samplerate);   //            int(step * rate)
+    if (frame_len < 1 || frame_step < 1) return fail(DSPFE_ERR_UNSUPPORTED, "endpoint frame length/step below one sample");
+    if ((int)(q.l_sil / q.cfg_step) + (int)(q.r_sil / q.cfg_step) > 64 || (int)(q.zcr_r_sil / q.cfg_step) > 64)
+        return fail(DSPFE_ERR_UNSUPPORTED, "silence windows longer than 64 frames are not supported");
+    return DSPFE_OK;
+}
+
+int ensure(dspfe_endpoint_plan* pl, int64_t n_utt, int64_t blocks, int64_t frames) {
+    if (n_utt + 1 > pl->cap_utt) {
+        cudaFree(pl->frame_off); cudaFree(pl->block_off); pl->frame_off = pl->block_off = nullptr; pl->cap_utt = 0;
+        CUDA_TRY(cudaMalloc(&pl->frame_off, (n_utt + 1) * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&pl->block_off, (n_utt + 1) * sizeof(int64_t)));
+        pl->cap_utt = n_utt + 1;
+    }
+    if (blocks > pl->cap_blocks) {
+        cudaFree(pl->blk); pl->blk = nullptr; pl->cap_blocks = 0;
+        CUDA_TRY(cudaMalloc(&pl->blk, blocks * 6 * sizeof(int32_t)));
+        pl->cap_blocks = blocks;
+    }
+    if (frames > pl->cap_frames) {
+        cudaFree(pl->asum); cudaFree(pl->zcr); pl->asum = pl->zcr = nullptr; pl->cap_frames = 0;
+        CUDA_TRY(cudaMalloc(&pl->asum, frames * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&pl->zcr, frames * sizeof(int32_t)));
+        pl->cap_frames = frames;
+    }
+    return DSPFE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void dspfe_endpoint_params_default(dspfe_endpoint_params* p, int32_t samplerate) {
+    if (!p) return;
+    p->samplerate = samplerate; p->min_span = 50;
+    p->cfg_frame = 0.03; p->cfg_step = 0.01; p->mh1 = 0.25; p->mh2 = 0.125; p->th = 0.100; p->l_sil = 0.100; p->r_sil = 0.100;
+    p->sigma = 3.0; p->zcr_max_shift = 0.400; p->zcr_r_sil = 0.100;
+}
+
+int dspfe_endpoint_decide_host(const dspfe_endpoint_params* p, const int32_t* asum, const int32_t* zcr, int32_t n_frames, int32_t* lr) {
+    if (!p || !asum || !zcr || !lr || n_frames < 1) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    EpRule r; int fl, fs;
+    int rc = fill_rule(*p, r, fl, fs);
+    if (rc) return rc;
+    endpoint_decide(asum, zcr, n_frames, fl, r, lr);
+    return DSPFE_OK;
+}
+
+int dspfe_endpoint_create(const dspfe_endpoint_params* p, dspfe_endpoint_plan** plan) {
+    if (!p || !plan) return fail(DSPFE_ERR_INVALID_ARG, "null argument");
+    *plan = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(DSPFE_ERR_CUDA, "no CUDA device: libdspfe has no CPU fallback");
+    dspfe_endpoint_plan* pl = new (std::nothrow) dspfe_endpoint_plan();
+    if (!pl) return fail(DSPFE_ERR_NOMEM, "out of host memory");
+    pl->prm = *p;
+    int rc = fill_rule(*p, pl->rule, pl->frame_len, pl->frame_step);
+    if (rc) { delete pl; return rc; }
+    pl->q = pl->frame_len / pl->frame_step; pl->rem = pl->frame_len % pl->frame_step;
+    *plan = pl;
+    return DSPFE_OK;
+}
+
+void dspfe_endpoint_destroy(dspfe_endpoint_plan* pl) {
+    if (!pl) return;
+    cudaFree(pl->frame_off); cudaFree(pl->block_off); cudaFree(pl->blk); cudaFree(pl->asum); cudaFree(pl->zcr);
+    cudaFree(pl->d_pcm); cudaFree(pl->d_off); cudaFree(pl->d_lr);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+int32_t dspfe_endpoint_frame_len(const dspfe_endpoint_plan* pl) { return pl ? pl->frame_len : -1; }
+int32_t dspfe_endpoint_frame_step(const dspfe_endpoint_plan* pl) { return pl ? pl->frame_step : -1; }
+
+int64_t dspfe_endpoint_frames_bound(const dspfe_endpoint_plan* pl, int64_t total_samples, int64_t n_utt) {
+    if (!pl) return -1;
+    return total_samples / pl->frame_step + n_utt;
+}
+
+int dspfe_endpoint(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets, int32_t n_utt,
+                   int32_t* d_lr, int32_t* d_asum, int32_t* d_zcr, int64_t* d_frame_off, int64_t max_frames, void* stream) {
+    if (!pl || !d_offsets || !d_lr || n_utt < 0 || total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    if (!d_pcm && total_samples > 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm is null");
+    const int64_t frames_bound = dspfe_endpoint_frames_bound(pl, total_samples, n_utt);
+    if ((d_asum || d_zcr) && max_frames < frames_bound) return fail(DSPFE_ERR_INVALID_ARG, "max_frames is below dspfe_endpoint_frames_bound()");
+    const int64_t blocks_bound = frames_bound + (int64_t)n_utt * (pl->q + 1);
+    int rc = ensure(pl, n_utt, blocks_bound, frames_bound);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    EpParams p;
+    p.pcm = d_pcm; p.offsets = d_offsets; p.n_utt = n_utt; p.frame_len = pl->frame_len; p.frame_step = pl->frame_step;
+    p.q = pl->q; p.rem = pl->rem; p.frame_off = d_frame_off ? d_frame_off : pl->frame_off; p.block_off = pl->block_off;
+    p.blk = pl->blk; p.asum = d_asum ? d_asum : pl->asum; p.zcr = d_zcr ? d_zcr : pl->zcr; p.lr = d_lr;
+    p.max_blocks = blocks_bound; p.max_frames = frames_bound; p.rule = pl->rule;
+    ep_prep_kernel<<<1, kEpPrepThreads, 0, st>>>(p);
+    LAUNCH_CHECK("ep_prep_kernel", st);
+    ep_block_kernel<<<(unsigned)((blocks_bound + 7) / 8), 256, 0, st>>>(p);
+    LAUNCH_CHECK("ep_block_kernel", st);
+    ep_frame_kernel<<<(unsigned)((frames_bound + 255) / 256), 256, 0, st>>>(p);
+    LAUNCH_CHECK("ep_frame_kernel", st);
+    ep_decide_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, st>>>(p);
+    LAUNCH_CHECK("ep_decide_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_endpoint_host(dspfe_endpoint_plan* pl, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt, int32_t* h_lr,
+                        int32_t* h_asum, int32_t* h_zcr, int64_t* h_frame_off) {
+    if (!pl || !h_offsets || !h_lr || n_utt < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    const int64_t base = h_offsets[0], total = h_offsets[n_utt] - base;
+    if (total < 0) return fail(DSPFE_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    if (!pl->stream) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    if (total + 8 > pl->cap_samples) {
+        cudaFree(pl->d_pcm); pl->d_pcm = nullptr; pl->cap_samples = 0;
+        CUDA_TRY(cudaMalloc(&pl->d_pcm, (total + 8) * sizeof(int16_t)));
+        pl->cap_samples = total + 8;
+    }
+    if (n_utt + 1 > pl->cap_hutt) {
+        cudaFree(pl->d_off); cudaFree(pl->d_lr); pl->d_off = nullptr; pl->d_lr = nullptr; pl->cap_hutt = 0;
+        CUDA_TRY(cudaMalloc(&pl->d_off, (n_utt + 1) * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&pl->d_lr, (int64_t)n_utt * 2 * sizeof(int32_t)));
+        pl->cap_hutt = n_utt + 1;
+    }
+    std::vector<int64_t> rel(n_utt + 1);
+    int64_t frames = 0;
+    for (int32_t u = 0; u <= n_utt; ++u) {
+        rel[u] = h_offsets[u] - base;
+        if (u < n_utt) {
+            if (h_frame_off) h_frame_off[u] = frames;
+            frames += num_frames(h_offsets[u + 1] - h_offsets[u], pl->frame_len, pl->frame_step);
+        }
+    }
+    if (h_frame_off) h_frame_off[n_utt] = frames;
+    cudaStream_t st = pl->stream;
+    if (total > 0) CUDA_TRY(cudaMemcpyAsync(pl->d_pcm, h_pcm + base, total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pl->d_off, rel.data(), (n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    int rc = dspfe_endpoint(pl, pl->d_pcm, total, pl->d_off, n_utt, pl->d_lr, nullptr, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_lr, pl->d_lr, (int64_t)n_utt * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (h_asum) CUDA_TRY(cudaMemcpyAsync(h_asum, pl->asum, frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (h_zcr) CUDA_TRY(cudaMemcpyAsync(h_zcr, pl->zcr, frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DSPFE_OK;
+}
+
+}  // extern "C"

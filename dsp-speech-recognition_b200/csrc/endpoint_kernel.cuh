@@ -1,0 +1,268 @@
+// K2/K3: energy + zero-crossing endpoint detection over a ragged batch (sm_100a).
+//
+// Replaces reference features/endpoint.py: get_amplitude (:109), get_zcr (:182), amplitude_rule (:133),
+// zcr_rule (:201) and their driver basic_endpoint_detection (:34), on raw int16 PCM.
+//   K2a  one warp per hop block (frame_step samples): exact int32 sum |x|, sign changes inside the block,
+//        sign change across the boundary to the next block, and the same for the first (frame_len % step)
+//        samples (frames that are not a whole number of hops);
+//   K2b  one thread per frame: combines the block partials into sum|x| and the zero-crossing count of the
+//        frame (zero padding past the end of the utterance is implicit: sigproc.py:84-87);
+//   K3   one thread per utterance: the reference's double-threshold state machine, replayed in float64 with
+//        NumPy's pairwise summation order so that thresholds, and therefore (left, right), are bit-exact.
+// All statistics are integers, so amp = sum/frame_len (one float64 divide on the host) equals the
+// reference's np.mean exactly.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define DSP_HD __host__ __device__ inline
+#else
+#define DSP_HD inline
+#endif
+
+namespace dspfe {
+
+struct EpRule {           // reference call-site constants (endpoint.py:42-45,56,60-64,133,201)
+    double cfg_frame;     // 0.03  (config.py:31)
+    double cfg_step;      // 0.01  (config.py:32)
+    double mh1, mh2;      // 0.25, then 0.125 when the span is shorter than min_span
+    double th;            // 0.1 s above the high threshold
+    double l_sil, r_sil;  // 0.1 s of assumed silence either side
+    double sigma;         // 3
+    double zcr_max_shift; // 0.4 s
+    double zcr_r_sil;     // 0.1 s
+    int min_span;         // 50 frames
+    int rate;
+};
+
+// numpy's pairwise summation (DOUBLE_pairwise_sum).  Callers pass n <= 64, so only numpy's n < 8 and
+// n <= 128 branches are needed (no recursion: device stack stays within the default 1 KB).
+DSP_HD double np_pairwise_sum(const double* a, int n) {
+    if (n < 8) {
+        double res = 0.;
+        for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    if (n <= 128) {
+        double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+            r0 += a[i]; r1 += a[i + 1]; r2 += a[i + 2]; r3 += a[i + 3];
+            r4 += a[i + 4]; r5 += a[i + 5]; r6 += a[i + 6]; r7 += a[i + 7];
+        }
+        double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    return NAN;   // unreachable for n <= 128
+}
+
+// np.mean / np.std (population) of up to 64 values, numpy operation order.  n == 0 gives NaN like numpy.
+DSP_HD void np_mean_std(const double* a, int n, double* mean, double* std) {
+    if (n <= 0) { *mean = NAN; *std = NAN; return; }
+    const double m = np_pairwise_sum(a, n) / (double)n;
+    double sq[64];
+    for (int i = 0; i < n; ++i) { const double d = a[i] - m; sq[i] = d * d; }
+    *mean = m;
+    *std = sqrt(np_pairwise_sum(sq, n) / (double)n);
+}
+
+// amplitude_rule (endpoint.py:133-179) reduced to what basic_endpoint_detection uses: (first segment start,
+// last segment end), or (0, F) when no segment qualifies.  asum[f] = sum |x| of frame f.
+DSP_HD void amplitude_rule(const int32_t* asum, int F, int frame_len, const EpRule& r, double mh, int* left, int* right) {
+    const double inv = (double)frame_len;
+    const int nl = (int)(r.l_sil / r.cfg_step), nr = (int)(r.r_sil / r.cfg_step);
+    double sil[64];
+    int n = 0;
+    // amp[:nl] + amp[-nr:] with Python slice clamping
+    for (int i = 0; i < nl && i < F && n < 64; ++i) sil[n++] = (double)asum[i] / inv;
+    if (nr > 0) for (int i = (F - nr > 0 ? F - nr : 0); i < F && n < 64; ++i) sil[n++] = (double)asum[i] / inv;
+    else for (int i = 0; i < F && n < 64; ++i) sil[n++] = (double)asum[i] / inv;   // amp[-0:] is the whole list
+    // sorted(sil)[:-2]
+    for (int i = 1; i < n; ++i) { double v = sil[i]; int j = i - 1; while (j >= 0 && sil[j] > v) { sil[j + 1] = sil[j]; --j; } sil[j + 1] = v; }
+    n = n - 2 > 0 ? n - 2 : 0;
+    double s_mean, s_sigma;
+    np_mean_std(sil, n, &s_mean, &s_sigma);
+    const double T_H = r.th / r.cfg_frame;
+    const double M_L = s_mean + r.sigma * s_sigma;
+    int32_t amax = 0;
+    for (int i = 0; i < F; ++i) amax = asum[i] > amax ? asum[i] : amax;
+    const double a_hi = ((double)amax / inv) * mh;
+    const double M_H = (M_L > a_hi) ? M_L : a_hi;   // Python max(a_hi, M_L): NaN M_L keeps a_hi
+    int first = -1, last = -1;
+    int i = 0;
+    while (i < F) {
+        if ((double)asum[i] / inv >= M_H) {
+            int j = i, k = i;
+            while (k < F && (double)asum[k] / inv > M_H) ++k;
+            if ((double)(k - j) < T_H) {
+                i = k;
+            } else {
+                while (j > 0 && (double)asum[j] / inv > M_L) --j;
+                while (k < F && (double)asum[k] / inv > M_L) ++k;
+                if (first < 0) first = j;
+                last = k;
+                i = k;
+            }
+        }
+        ++i;
+    }
+    if (first < 0) { *left = 0; *right = F; } else { *left = first; *right = last; }
+}
+
+// zcr_rule (endpoint.py:201-220)
+DSP_HD void zcr_rule(const int32_t* zcr, int F, const EpRule& r, int left, int right, int* l2, int* r2) {
+    const double max_shift = r.zcr_max_shift / r.cfg_frame;
+    const int nr = (int)(r.zcr_r_sil / r.cfg_step);
+    double sil[64];
+    int n = 0;
+    if (nr > 0) for (int i = (F - nr > 0 ? F - nr : 0); i < F && n < 64; ++i) sil[n++] = (double)zcr[i];
+    else for (int i = 0; i < F && n < 64; ++i) sil[n++] = (double)zcr[i];
+    double mu, sg;
+    np_mean_std(sil, n, &mu, &sg);
+    const double thres = mu + 3 * sg;
+    int j = left;
+    while (j > 0 && (double)(left - j) <= max_shift && (double)zcr[j] > thres) --j;
+    int k = right;
+    while (k < F && (double)(k - right) <= max_shift && (double)zcr[k] > thres) ++k;
+    *l2 = j; *r2 = k;
+}
+
+// basic_endpoint_detection (endpoint.py:34-66): frame-level decision + conversion to sample indices.
+DSP_HD void endpoint_decide(const int32_t* asum, const int32_t* zcr, int F, int frame_len, const EpRule& r, int32_t* out_lr) {
+    int left, right;
+    amplitude_rule(asum, F, frame_len, r, r.mh1, &left, &right);
+    if (right - left < r.min_span) amplitude_rule(asum, F, frame_len, r, r.mh2, &left, &right);
+    int l2, r2;
+    zcr_rule(zcr, F, r, left, right, &l2, &r2);
+    if (r2 - l2 < r.min_span) { l2 = 0; r2 = F; }
+    // int(left2 * cfg.step * rate): float64 product evaluated left to right, truncated (Appendix A-9)
+    out_lr[0] = (int32_t)((double)l2 * r.cfg_step * (double)r.rate);
+    out_lr[1] = (int32_t)((double)r2 * r.cfg_step * (double)r.rate);
+}
+
+struct EpParams {
+    const int16_t* pcm;
+    const int64_t* offsets;    // [U+1]
+    int n_utt;
+    int frame_len, frame_step; // int(rate*cfg.frame), int(cfg.step*rate)  (sigproc.py:19)
+    int q, rem;                // frame_len = q*frame_step + rem
+    // workspaces / outputs
+    int64_t* frame_off;        // [U+1] endpoint-frame prefix sums
+    int64_t* block_off;        // [U+1] hop-block prefix sums
+    int32_t* blk;              // [total_blocks, 6]: A, Z, C, A', Z', pad
+    int32_t* asum;             // [F_total]
+    int32_t* zcr;              // [F_total]
+    int32_t* lr;               // [U, 2]
+    int64_t max_blocks, max_frames;
+    EpRule rule;
+};
+
+#ifdef __CUDACC__
+constexpr int kEpPrepThreads = 1024;
+
+// hop blocks an utterance with F frames touches
+__device__ inline int64_t ep_blocks(int64_t F, int q, int rem) { return F - 1 + q + (rem > 0 ? 1 : 0); }
+
+__global__ void __launch_bounds__(kEpPrepThreads) ep_prep_kernel(EpParams p) {
+    __shared__ long long s_f[kEpPrepThreads], s_b[kEpPrepThreads];
+    const int tid = threadIdx.x;
+    const int per = (p.n_utt + kEpPrepThreads - 1) / kEpPrepThreads;
+    const int u0 = min(tid * per, p.n_utt), u1 = min(u0 + per, p.n_utt);
+    long long f = 0, b = 0;
+    for (int u = u0; u < u1; ++u) {
+        const long long F = num_frames(p.offsets[u + 1] - p.offsets[u], p.frame_len, p.frame_step);
+        f += F; b += ep_blocks(F, p.q, p.rem);
+    }
+    s_f[tid] = f; s_b[tid] = b;
+    __syncthreads();
+    for (int d = 1; d < kEpPrepThreads; d <<= 1) {
+        long long x = tid >= d ? s_f[tid - d] : 0, y = tid >= d ? s_b[tid - d] : 0;
+        __syncthreads();
+        s_f[tid] += x; s_b[tid] += y;
+        __syncthreads();
+    }
+    long long fo = s_f[tid] - f, bo = s_b[tid] - b;
+    for (int u = u0; u < u1; ++u) {
+        const long long F = num_frames(p.offsets[u + 1] - p.offsets[u], p.frame_len, p.frame_step);
+        p.frame_off[u] = fo; p.block_off[u] = bo;
+        fo += F; bo += ep_blocks(F, p.q, p.rem);
+    }
+    if (tid == kEpPrepThreads - 1) { p.frame_off[p.n_utt] = s_f[tid]; p.block_off[p.n_utt] = s_b[tid]; }
+}
+
+// largest u with off[u] <= g
+__device__ inline int find_owner(const int64_t* off, int n, int64_t g) {
+    int lo = 0, hi = n;   // off[lo] <= g < off[hi]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// K2a: one warp per hop block
+__global__ void __launch_bounds__(256) ep_block_kernel(EpParams p) {
+    const int64_t g = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= p.block_off[p.n_utt] || g >= p.max_blocks) return;
+    const int u = find_owner(p.block_off, p.n_utt, g);
+    const int64_t b = g - p.block_off[u];
+    const int64_t base = p.offsets[u];
+    const int64_t S = p.offsets[u + 1] - base;
+    const int64_t s0 = b * p.frame_step;
+    const int16_t* x = p.pcm + base;
+    int A = 0, Z = 0, A2 = 0, Z2 = 0;
+    for (int i = lane; i < p.frame_step; i += 32) {
+        const int64_t s = s0 + i;
+        const int v = s < S ? (int)x[s] : 0;
+        const int w = (s + 1 < S) ? (int)x[s + 1] : 0;
+        const int a = v < 0 ? -v : v;
+        const int zc = (v * w < 0) ? 1 : 0;
+        A += a;
+        if (i + 1 < p.frame_step) Z += zc;            // pair inside the block
+        if (i < p.rem) A2 += a;
+        if (i + 1 < p.rem) Z2 += zc;
+    }
+    int C = 0;
+    if (lane == 0) {   // pair across the boundary to the next block
+        const int64_t s = s0 + p.frame_step - 1;
+        const int v = s < S ? (int)x[s] : 0, w = (s + 1 < S) ? (int)x[s + 1] : 0;
+        C = (v * w < 0) ? 1 : 0;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        A += __shfl_xor_sync(0xffffffffu, A, m); Z += __shfl_xor_sync(0xffffffffu, Z, m);
+        A2 += __shfl_xor_sync(0xffffffffu, A2, m); Z2 += __shfl_xor_sync(0xffffffffu, Z2, m);
+    }
+    if (lane == 0) {
+        int32_t* o = p.blk + g * 6;
+        o[0] = A; o[1] = Z; o[2] = C; o[3] = A2; o[4] = Z2; o[5] = 0;
+    }
+}
+
+// K2b: one thread per frame
+__global__ void __launch_bounds__(256) ep_frame_kernel(EpParams p) {
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= p.frame_off[p.n_utt] || g >= p.max_frames) return;
+    const int u = find_owner(p.frame_off, p.n_utt, g);
+    const int64_t f = g - p.frame_off[u];
+    const int32_t* b = p.blk + (p.block_off[u] + f) * 6;
+    int A = 0, Z = 0;
+    for (int j = 0; j < p.q; ++j) { A += b[6 * j]; Z += b[6 * j + 1]; if (j + 1 < p.q) Z += b[6 * j + 2]; }
+    if (p.rem > 0) {
+        if (p.q > 0) Z += b[6 * (p.q - 1) + 2];
+        A += b[6 * p.q + 3]; Z += b[6 * p.q + 4];
+    }
+    p.asum[g] = A; p.zcr[g] = Z;
+}
+
+// K3: one thread per utterance
+__global__ void __launch_bounds__(128) ep_decide_kernel(EpParams p) {
+    const int u = blockIdx.x * 128 + threadIdx.x;
+    if (u >= p.n_utt) return;
+    const int64_t f0 = p.frame_off[u];
+    const int F = (int)(p.frame_off[u + 1] - f0);
+    endpoint_decide(p.asum + f0, p.zcr + f0, F, p.frame_len, p.rule, p.lr + 2 * u);
+}
+#endif  // __CUDACC__
+
+}  // namespace dspfe

@@ -4,5 +4,5 @@ PyTorch supplies device memory and streams only; every feature value is computed
 kernels in csrc/.  There is no CPU fallback: if libdspfe.so is missing or no CUDA device is
 present, the compute entry points raise.
 """
-from .binding import (DspfeError, MfccPlan, lib, lib_path, mfcc_params, num_frames, frame_counts,  # noqa: F401
-                      mfcc_tables_host)
+from .binding import (DspfeError, EndpointPlan, MfccPlan, endpoint_decide_host, endpoint_params, frame_counts,  # noqa: F401
+                      lib, lib_path, mfcc_params, mfcc_tables_host, num_frames)

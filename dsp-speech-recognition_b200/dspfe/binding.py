@@ -168,3 +168,116 @@ class MfccPlan:
                                            offsets.ctypes.data_as(ctypes.c_void_p), n_utt,
                                            out.ctypes.data_as(ctypes.c_void_p), fo.ctypes.data_as(ctypes.c_void_p)))
         return out[:rows], fo
+
+
+# ------------------------------------------------------------------------------------------------ endpoint
+class _EndpointParams(ctypes.Structure):
+    _fields_ = [("samplerate", ctypes.c_int32), ("min_span", ctypes.c_int32), ("cfg_frame", ctypes.c_double),
+                ("cfg_step", ctypes.c_double), ("mh1", ctypes.c_double), ("mh2", ctypes.c_double), ("th", ctypes.c_double),
+                ("l_sil", ctypes.c_double), ("r_sil", ctypes.c_double), ("sigma", ctypes.c_double),
+                ("zcr_max_shift", ctypes.c_double), ("zcr_r_sil", ctypes.c_double)]
+
+
+def _bind_endpoint(L):
+    if getattr(L, "_ep_bound", False):
+        return
+    L.dspfe_endpoint_params_default.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.c_int32]
+    L.dspfe_endpoint_params_default.restype = None
+    L.dspfe_endpoint_create.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.POINTER(ctypes.c_void_p)]
+    L.dspfe_endpoint_destroy.argtypes = [ctypes.c_void_p]
+    L.dspfe_endpoint_destroy.restype = None
+    L.dspfe_endpoint_frame_len.argtypes = [ctypes.c_void_p]
+    L.dspfe_endpoint_frame_step.argtypes = [ctypes.c_void_p]
+    L.dspfe_endpoint_frames_bound.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+    L.dspfe_endpoint_frames_bound.restype = ctypes.c_int64
+    L.dspfe_endpoint.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                 ctypes.c_void_p]
+    L.dspfe_endpoint_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.dspfe_endpoint_decide_host.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int32, ctypes.c_void_p]
+    L._ep_bound = True
+
+
+def endpoint_params(samplerate=16000, cfg_frame=0.03, cfg_step=0.01, **kw):
+    L = lib()
+    _bind_endpoint(L)
+    p = _EndpointParams()
+    L.dspfe_endpoint_params_default(ctypes.byref(p), int(samplerate))
+    p.cfg_frame, p.cfg_step = float(cfg_frame), float(cfg_step)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def endpoint_decide_host(asum, zcr, **kw):
+    """Host-only replay of the decision rule (no CUDA) on per-frame sum|x| and zero-crossing counts."""
+    p = endpoint_params(**kw)
+    asum = np.ascontiguousarray(asum, dtype=np.int32)
+    zcr = np.ascontiguousarray(zcr, dtype=np.int32)
+    lr = np.zeros(2, dtype=np.int32)
+    _check(lib().dspfe_endpoint_decide_host(ctypes.byref(p), asum.ctypes.data_as(ctypes.c_void_p),
+                                            zcr.ctypes.data_as(ctypes.c_void_p), len(asum), lr.ctypes.data_as(ctypes.c_void_p)))
+    return int(lr[0]), int(lr[1])
+
+
+class EndpointPlan:
+    """dspfe_endpoint_plan: batched basic_endpoint_detection (reference endpoint.py:34)."""
+
+    def __init__(self, **kw):
+        self._p = endpoint_params(**kw)
+        h = ctypes.c_void_p()
+        _check(lib().dspfe_endpoint_create(ctypes.byref(self._p), ctypes.byref(h)))
+        self._h = h
+        self.frame_len = int(lib().dspfe_endpoint_frame_len(h))
+        self.frame_step = int(lib().dspfe_endpoint_frame_step(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dspfe_endpoint_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def frames_bound(self, total_samples, n_utt):
+        return int(lib().dspfe_endpoint_frames_bound(self._h, int(total_samples), int(n_utt)))
+
+    def detect(self, pcm, offsets, want_features=False, stream=None):
+        """Device path: pcm int16 CUDA tensor, offsets int64 CUDA tensor [U+1].  Returns lr int32 [U,2]
+        (and asum, zcr int32 [frames_bound], frame_off int64 [U+1] when want_features)."""
+        import torch
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and offsets.is_cuda and offsets.dtype == torch.int64
+        n_utt = offsets.numel() - 1
+        lr = torch.empty((n_utt, 2), dtype=torch.int32, device=pcm.device)
+        st = stream if stream is not None else torch.cuda.current_stream(pcm.device).cuda_stream
+        if want_features:
+            fb = self.frames_bound(pcm.numel(), n_utt)
+            asum = torch.empty(fb, dtype=torch.int32, device=pcm.device)
+            zcr = torch.empty(fb, dtype=torch.int32, device=pcm.device)
+            fo = torch.empty(n_utt + 1, dtype=torch.int64, device=pcm.device)
+            _check(lib().dspfe_endpoint(self._h, pcm.data_ptr(), pcm.numel(), offsets.data_ptr(), n_utt, lr.data_ptr(),
+                                        asum.data_ptr(), zcr.data_ptr(), fo.data_ptr(), fb, ctypes.c_void_p(st)))
+            return lr, asum, zcr, fo
+        _check(lib().dspfe_endpoint(self._h, pcm.data_ptr(), pcm.numel(), offsets.data_ptr(), n_utt, lr.data_ptr(),
+                                    None, None, None, 0, ctypes.c_void_p(st)))
+        return lr
+
+    def detect_host(self, pcm, offsets, want_features=False):
+        """Host path: NumPy int16 pcm + int64 offsets -> lr int32 [U,2] (+ asum, zcr, frame_off)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_utt = len(offsets) - 1
+        lr = np.zeros((n_utt, 2), dtype=np.int32)
+        if not want_features:
+            _check(lib().dspfe_endpoint_host(self._h, pcm.ctypes.data_as(ctypes.c_void_p), offsets.ctypes.data_as(ctypes.c_void_p),
+                                             n_utt, lr.ctypes.data_as(ctypes.c_void_p), None, None, None))
+            return lr
+        nf = int(frame_counts(np.diff(offsets), self.frame_len, self.frame_step).sum())
+        asum = np.zeros(nf, dtype=np.int32)
+        zcr = np.zeros(nf, dtype=np.int32)
+        fo = np.zeros(n_utt + 1, dtype=np.int64)
+        _check(lib().dspfe_endpoint_host(self._h, pcm.ctypes.data_as(ctypes.c_void_p), offsets.ctypes.data_as(ctypes.c_void_p),
+                                         n_utt, lr.ctypes.data_as(ctypes.c_void_p), asum.ctypes.data_as(ctypes.c_void_p),
+                                         zcr.ctypes.data_as(ctypes.c_void_p), fo.ctypes.data_as(ctypes.c_void_p)))
+        return lr, asum, zcr, fo

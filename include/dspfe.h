@@ -106,6 +106,53 @@ int dspfe_mfcc_delta_host(dspfe_plan* plan, const int16_t* h_pcm, const int64_t*
 int dspfe_host_alloc(void** p, int64_t bytes);   /* cudaHostAlloc */
 int dspfe_host_free(void* p);
 
+/* ------------------------------------------------------------------------------------------------
+ * Endpoint detection: short-time amplitude + zero-crossing rate, double-threshold rule.
+ * Replaces features.basic_endpoint_detection (endpoint.py:34-66) with its helpers get_amplitude
+ * (:109), get_zcr (:182), amplitude_rule (:133) and zcr_rule (:201) for every utterance of a batch.
+ * Frame length / step are int(rate*cfg_frame) / int(cfg_step*rate) (sigproc.py:19; config.py:31-32).
+ * All outputs are integers and bit-exact against the reference for int16 input.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dspfe_endpoint_plan dspfe_endpoint_plan;
+
+typedef struct {
+    int32_t samplerate;      /* 16000 */
+    int32_t min_span;        /* 50 frames: shorter spans retry with mh2, then fall back to the whole signal */
+    double cfg_frame;        /* 0.03  (config.py:31) */
+    double cfg_step;         /* 0.01  (config.py:32) */
+    double mh1, mh2;         /* 0.25, 0.125  (endpoint.py:42,45) */
+    double th;               /* 0.1 s */
+    double l_sil, r_sil;     /* 0.1 s, 0.1 s */
+    double sigma;            /* 3 */
+    double zcr_max_shift;    /* 0.4 s */
+    double zcr_r_sil;        /* 0.1 s (zcr_rule's l_sil is 0) */
+} dspfe_endpoint_params;
+
+void dspfe_endpoint_params_default(dspfe_endpoint_params* p, int32_t samplerate);
+int dspfe_endpoint_create(const dspfe_endpoint_params* p, dspfe_endpoint_plan** plan);
+void dspfe_endpoint_destroy(dspfe_endpoint_plan* plan);
+int32_t dspfe_endpoint_frame_len(const dspfe_endpoint_plan* plan);
+int32_t dspfe_endpoint_frame_step(const dspfe_endpoint_plan* plan);
+int64_t dspfe_endpoint_frames_bound(const dspfe_endpoint_plan* plan, int64_t total_samples, int64_t n_utt);
+
+/* Device path.  d_lr [n_utt,2] int32 receives (left,right) sample indices exactly as the reference
+ * returns them (right may exceed the utterance length, endpoint.py:64).  Optional outputs (may be
+ * NULL): d_asum [frames] int32 = sum |x| per frame (amp = d_asum / frame_len in float64 is the
+ * reference's get_amplitude), d_zcr [frames] int32 = get_zcr, d_frame_off [n_utt+1] int64.
+ * max_frames = capacity of d_asum / d_zcr, >= dspfe_endpoint_frames_bound(). */
+int dspfe_endpoint(dspfe_endpoint_plan* plan, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets,
+                   int32_t n_utt, int32_t* d_lr, int32_t* d_asum, int32_t* d_zcr, int64_t* d_frame_off,
+                   int64_t max_frames, void* stream);
+
+/* Host-buffer path: H2D, kernels, D2H; returns when the results are in the host arrays. */
+int dspfe_endpoint_host(dspfe_endpoint_plan* plan, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt,
+                        int32_t* h_lr, int32_t* h_asum, int32_t* h_zcr, int64_t* h_frame_off);
+
+/* Host-only (no CUDA): the decision rule on precomputed frame statistics; lets CPU-only tests check the
+ * float64 rule replay (NumPy summation order included) against the oracle. */
+int dspfe_endpoint_decide_host(const dspfe_endpoint_params* p, const int32_t* asum, const int32_t* zcr, int32_t n_frames,
+                               int32_t* lr);
+
 #ifdef __cplusplus
 }
 #endif

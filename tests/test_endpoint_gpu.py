@@ -1,0 +1,99 @@
+"""GPU parity tests of the endpoint kernels (K2a/K2b/K3) through the C ABI: bit-exact integers."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def pack(xs):
+    off = np.zeros(len(xs) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in xs], out=off[1:])
+    return np.concatenate(xs).astype(np.int16), off
+
+
+def test_golden_batch_bit_exact(golden):
+    import torch
+    import dspfe
+    g = golden("endpoint")
+    names = [str(n) for n in g["names"]]
+    pcm, off = pack([g[f"{n}/x"] for n in names])
+    plan = dspfe.EndpointPlan()
+    assert (plan.frame_len, plan.frame_step) == (480, 160)
+    lr, asum, zcr, fo = plan.detect_host(pcm, off, want_features=True)
+    np.testing.assert_array_equal(lr, g["lr"])
+    for i, n in enumerate(names):
+        np.testing.assert_array_equal(asum[fo[i]:fo[i + 1]] / 480.0, g[f"{n}/amp"])     # float64 divide == np.mean
+        np.testing.assert_array_equal(zcr[fo[i]:fo[i + 1]], g[f"{n}/zcr"])
+    dev = torch.device("cuda:0")
+    lr_d, asum_d, zcr_d, fo_d = plan.detect(torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev), want_features=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(lr_d.cpu().numpy(), lr)
+    np.testing.assert_array_equal(asum_d.cpu().numpy()[: fo[-1]], asum)
+    np.testing.assert_array_equal(zcr_d.cpu().numpy()[: fo[-1]], zcr)
+    np.testing.assert_array_equal(fo_d.cpu().numpy(), fo)
+
+
+def test_random_ragged_vs_oracle():
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    lengths = synth.ragged_lengths(192, seed=3)
+    lengths[:6] = [1, 479, 480, 481, 640, 8000]
+    pcm, off = synth.synth_batch(lengths, seed0=5000)
+    lr, asum, zcr, fo = dspfe.EndpointPlan().detect_host(pcm, off, want_features=True)
+    mism = 0
+    for u in range(len(lengths)):
+        x = pcm[off[u]:off[u + 1]]
+        l, r, amp, z = O.basic_endpoint_detection(x, 16000, return_feature=True)
+        np.testing.assert_array_equal(asum[fo[u]:fo[u + 1]] / 480.0, np.array(amp))
+        np.testing.assert_array_equal(zcr[fo[u]:fo[u + 1]], np.array(z))
+        mism += (int(lr[u, 0]), int(lr[u, 1])) != (l, r)
+    assert mism == 0, f"{mism} of {len(lengths)} endpoint pairs differ"
+
+
+@pytest.mark.parametrize("rate,cfg_frame,cfg_step", [(8000, 0.03, 0.01), (16000, 0.025, 0.01), (44100, 0.03, 0.01), (16000, 0.005, 0.01)])
+def test_other_rates_and_partial_hops(rate, cfg_frame, cfg_step):
+    """frame_len not a multiple of the hop (and shorter than the hop) exercises the partial-block path."""
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    lengths = [int(rate * t) for t in (0.4, 1.0, 2.3, 0.05)]
+    pcm, off = synth.synth_batch(lengths, seed0=6000, sr=rate)
+    plan = dspfe.EndpointPlan(samplerate=rate, cfg_frame=cfg_frame, cfg_step=cfg_step)
+    lr, asum, zcr, fo = plan.detect_host(pcm, off, want_features=True)
+    for u in range(len(lengths)):
+        x = pcm[off[u]:off[u + 1]]
+        l, r, amp, z = O.basic_endpoint_detection(x, rate, return_feature=True, cfg_frame=cfg_frame, cfg_step=cfg_step)
+        np.testing.assert_array_equal(asum[fo[u]:fo[u + 1]] / float(plan.frame_len), np.array(amp))
+        np.testing.assert_array_equal(zcr[fo[u]:fo[u + 1]], np.array(z))
+        assert (int(lr[u, 0]), int(lr[u, 1])) == (l, r)
+
+
+def test_config4_ragged_endpoint_then_mfcc():
+    """BASELINE config 4: endpoint detection + MFCC on a ragged batch, chained on the device through d_trim."""
+    import torch
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    from tol import assert_mfcc_close
+    dev = torch.device("cuda:0")
+    U = 4096
+    lengths = synth.ragged_lengths(U, seed=11)
+    pcm, off = synth.synth_batch_torch(lengths, seed0=777, device=dev)
+    off_d = off.to(dev)
+    ep, mf = dspfe.EndpointPlan(), dspfe.MfccPlan(delta_n=3)
+    lr = ep.detect(pcm, off_d)
+    out, fo = mf.mfcc_delta(pcm, off_d, trim=lr)
+    torch.cuda.synchronize()
+    lr_h, fo_h, off_h = lr.cpu().numpy(), fo.cpu().numpy(), off.numpy()
+    # size-independent properties over the whole batch
+    assert np.all(lr_h[:, 0] >= 0) and np.all(lr_h[:, 1] > lr_h[:, 0])
+    seg = np.minimum(lr_h[:, 1], lengths) - np.minimum(lr_h[:, 0], lengths)
+    np.testing.assert_array_equal(np.diff(fo_h), dspfe.frame_counts(seg, 400, 160))
+    assert bool(torch.isfinite(out[: fo_h[-1]]).all())
+    # sampled oracle parity: endpoints bit-exact, trimmed MFCC within tolerance
+    for u in (0, 1, 2, 1000, 2047, 4095):
+        x = pcm[off_h[u]:off_h[u + 1]].cpu().numpy()
+        l, r = O.basic_endpoint_detection(x, 16000)
+        assert (int(lr_h[u, 0]), int(lr_h[u, 1])) == (l, r)
+        assert_mfcc_close(out[fo_h[u]:fo_h[u + 1]].cpu().numpy(), O.mfcc_delta39(x[l:r], 3), what=f"C4 utt {u}")
