@@ -16,24 +16,27 @@ using namespace dspfe;
 
 namespace {
 
-template <bool HAS_WIN, int NFULL>
+template <bool HAS_WIN, int NFULL, bool F32IN, int MODE = 0>
 __global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __grid_constant__ MfccParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    mfcc_cta<HAS_WIN, NFULL>(p, smem);
+    mfcc_cta<HAS_WIN, NFULL, F32IN, MODE>(p, smem);
 }
 
 typedef void (*mfcc_kernel_t)(const MfccParams);
 // specialisations: rectangular / windowed x frame_len/32 in {12 (25 ms @16 kHz), 15 (30 ms @16 kHz), generic}
-mfcc_kernel_t pick_kernel(bool has_win, int frame_len) {
+mfcc_kernel_t pick_kernel(bool has_win, int frame_len, bool f32, int mode = 0) {
     const int nfull = frame_len >> 5;
+    if (mode == 1) return has_win ? mfcc_delta_kernel<true, -1, true, 1> : mfcc_delta_kernel<false, -1, true, 1>;   // taps: float32 input only
+    if (mode == 2) return has_win ? mfcc_delta_kernel<true, -1, true, 2> : mfcc_delta_kernel<false, -1, true, 2>;
+    if (f32) return has_win ? mfcc_delta_kernel<true, -1, true> : mfcc_delta_kernel<false, -1, true>;
     if (has_win) {
-        if (nfull == 12) return mfcc_delta_kernel<true, 12>;
-        if (nfull == 15) return mfcc_delta_kernel<true, 15>;
-        return mfcc_delta_kernel<true, -1>;
+        if (nfull == 12) return mfcc_delta_kernel<true, 12, false>;
+        if (nfull == 15) return mfcc_delta_kernel<true, 15, false>;
+        return mfcc_delta_kernel<true, -1, false>;
     }
-    if (nfull == 12) return mfcc_delta_kernel<false, 12>;
-    if (nfull == 15) return mfcc_delta_kernel<false, 15>;
-    return mfcc_delta_kernel<false, -1>;
+    if (nfull == 12) return mfcc_delta_kernel<false, 12, false>;
+    if (nfull == 15) return mfcc_delta_kernel<false, 15, false>;
+    return mfcc_delta_kernel<false, -1, false>;
 }
 
 MfccConfig to_config(const dspfe_mfcc_params& q) {
@@ -90,9 +93,10 @@ struct HostSlot {
 struct dspfe_plan {
     MfccConfig cfg;
     MfccParams layout;          // scalars + offsets filled by build_mfcc_tables; pointers filled per call
+    MfccParams layout_f32;      // same for float32 input samples (larger raw staging area)
     float* d_tables = nullptr;
     bool has_win = false;
-    mfcc_kernel_t kernel = nullptr;
+    mfcc_kernel_t kernel = nullptr, kernel_f32 = nullptr, kernel_fbank = nullptr, kernel_spec = nullptr;
     Workspace ws;
     HostSlot slots[kSlots];
     int width = 0;              // 3 * numcep
@@ -100,8 +104,8 @@ struct dspfe_plan {
 
 namespace {
 
-int launch_mfcc(dspfe_plan* pl, Workspace& ws, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets,
-                const int32_t* d_trim, int32_t n_utt, float* d_out, int64_t* d_frame_off, cudaStream_t st) {
+int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int64_t total_samples, const int64_t* d_offsets,
+                const int32_t* d_trim, int32_t n_utt, float* d_out, int64_t* d_frame_off, cudaStream_t st, int mode = 0, int spec_kind = 0) {
     const int64_t max_tiles = mfcc_max_tiles(total_samples, n_utt, pl->cfg.frame_step, pl->cfg.seg_frames);
     if (max_tiles > 0x7fffffff) return fail(DSPFE_ERR_INVALID_ARG, "batch too large for one launch");
     int rc = ws.ensure(n_utt, max_tiles);
@@ -114,10 +118,12 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const int16_t* d_pcm, int64_t tot
     prep_kernel<<<1, kPrepThreads, 0, st>>>(pp);
     LAUNCH_CHECK("prep_kernel", st);
 
-    MfccParams mp = pl->layout;
+    MfccParams mp = f32 ? pl->layout_f32 : pl->layout;
     mp.pcm = d_pcm; mp.total_samples = total_samples; mp.seg_start = ws.seg_start; mp.seg_len = ws.seg_len;
     mp.frame_off = pp.frame_off; mp.tiles = ws.tiles; mp.ntiles = ws.ntiles; mp.tables = pl->d_tables; mp.out = d_out;
-    pl->kernel<<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
+    mp.spec_kind = spec_kind;
+    mfcc_kernel_t kern = mode == 1 ? pl->kernel_fbank : mode == 2 ? pl->kernel_spec : (f32 ? pl->kernel_f32 : pl->kernel);
+    kern<<<(unsigned)max_tiles, kMfccThreads, mp.sm_total, st>>>(mp);
     LAUNCH_CHECK("mfcc_delta_kernel", st);
     return DSPFE_OK;
 }
@@ -173,13 +179,20 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     std::memset(&pl->layout, 0, sizeof(pl->layout));
     std::string err;
     std::vector<float> blob = build_mfcc_tables(pl->cfg, pl->layout, err);
+    if (err.empty()) { std::memset(&pl->layout_f32, 0, sizeof(pl->layout_f32)); build_mfcc_tables(pl->cfg, pl->layout_f32, err, true); }
     if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
     pl->has_win = !pl->cfg.window.empty();
     pl->width = 3 * pl->cfg.numcep;
     cudaError_t e = cudaMalloc(&pl->d_tables, blob.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice);
-    pl->kernel = pick_kernel(pl->has_win, pl->cfg.frame_len);
+    pl->kernel = pick_kernel(pl->has_win, pl->cfg.frame_len, false);
+    pl->kernel_f32 = pick_kernel(pl->has_win, pl->cfg.frame_len, true);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout.sm_total);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
+    pl->kernel_fbank = pick_kernel(pl->has_win, pl->cfg.frame_len, true, 1);
+    pl->kernel_spec = pick_kernel(pl->has_win, pl->cfg.frame_len, true, 2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_fbank, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
     if (e != cudaSuccess) { cudaFree(pl->d_tables); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
     *plan = pl;
     return DSPFE_OK;
@@ -229,7 +242,37 @@ int dspfe_mfcc_delta(dspfe_plan* pl, const int16_t* d_pcm, int64_t total_samples
     if (((uintptr_t)d_pcm & 15) != 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm must be 16-byte aligned");
     if (max_rows < dspfe_rows_bound(pl, total_samples, n_utt))
         return fail(DSPFE_ERR_INVALID_ARG, "d_out capacity (max_rows) is below dspfe_rows_bound()");
-    return launch_mfcc(pl, pl->ws, d_pcm, total_samples, d_offsets, d_trim, n_utt, d_out, d_frame_off, (cudaStream_t)stream);
+    return launch_mfcc(pl, pl->ws, d_pcm, false, total_samples, d_offsets, d_trim, n_utt, d_out, d_frame_off, (cudaStream_t)stream);
+}
+
+int dspfe_mfcc_delta_f32(dspfe_plan* pl, const float* d_pcm, int64_t total_samples, const int64_t* d_offsets,
+                         const int32_t* d_trim, int32_t n_utt, float* d_out, int64_t max_rows, int64_t* d_frame_off,
+                         void* stream) {
+    if (!pl || !d_offsets || !d_out || n_utt < 0 || total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    if (!d_pcm && total_samples > 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm is null");
+    if (((uintptr_t)d_pcm & 15) != 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm must be 16-byte aligned");
+    if (max_rows < dspfe_rows_bound(pl, total_samples, n_utt))
+        return fail(DSPFE_ERR_INVALID_ARG, "d_out capacity (max_rows) is below dspfe_rows_bound()");
+    return launch_mfcc(pl, pl->ws, d_pcm, true, total_samples, d_offsets, d_trim, n_utt, d_out, d_frame_off, (cudaStream_t)stream);
+}
+
+int dspfe_fbank_f32(dspfe_plan* pl, const float* d_pcm, int64_t total_samples, const int64_t* d_offsets, int32_t n_utt,
+                    float* d_out, int64_t max_rows, int64_t* d_frame_off, void* stream) {
+    if (!pl || !d_offsets || !d_out || n_utt < 0 || total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    if (((uintptr_t)d_pcm & 15) != 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm must be 16-byte aligned");
+    if (max_rows < dspfe_rows_bound(pl, total_samples, n_utt)) return fail(DSPFE_ERR_INVALID_ARG, "d_out capacity (max_rows) is below dspfe_rows_bound()");
+    return launch_mfcc(pl, pl->ws, d_pcm, true, total_samples, d_offsets, nullptr, n_utt, d_out, d_frame_off, (cudaStream_t)stream, 1, 0);
+}
+
+int dspfe_spectrum_f32(dspfe_plan* pl, const float* d_pcm, int64_t total_samples, const int64_t* d_offsets, int32_t n_utt,
+                       int32_t kind, float* d_out, int64_t max_rows, int64_t* d_frame_off, void* stream) {
+    if (!pl || !d_offsets || !d_out || n_utt < 0 || total_samples < 0 || kind < 0 || kind > 2) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    if (((uintptr_t)d_pcm & 15) != 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm must be 16-byte aligned");
+    if (max_rows < dspfe_rows_bound(pl, total_samples, n_utt)) return fail(DSPFE_ERR_INVALID_ARG, "d_out capacity (max_rows) is below dspfe_rows_bound()");
+    return launch_mfcc(pl, pl->ws, d_pcm, true, total_samples, d_offsets, nullptr, n_utt, d_out, d_frame_off, (cudaStream_t)stream, 2, kind);
 }
 
 int dspfe_mfcc_delta_host(dspfe_plan* pl, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt, float* h_out,
@@ -283,7 +326,7 @@ int dspfe_mfcc_delta_host(dspfe_plan* pl, const int16_t* h_pcm, const int64_t* h
         if (samples > 0)
             CUDA_TRY(cudaMemcpyAsync(s.d_pcm, h_pcm + base, samples * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
         CUDA_TRY(cudaMemcpyAsync(s.d_off, s.h_off, (nu + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
-        int rc = launch_mfcc(pl, s.ws, s.d_pcm, samples, s.d_off, nullptr, nu, s.d_out, s.d_frame_off, s.stream);
+        int rc = launch_mfcc(pl, s.ws, s.d_pcm, false, samples, s.d_off, nullptr, nu, s.d_out, s.d_frame_off, s.stream);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(h_out + row * width, s.d_out, rows * width * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         row += rows;

@@ -22,7 +22,7 @@ struct Tile { int utt, f0, nf, pad; };  // output frames [f0, f0+nf) of utteranc
 
 struct MfccParams {
     // inputs (device pointers)
-    const int16_t* pcm;         // packed ragged PCM, base 16-byte aligned
+    const void* pcm;            // packed ragged PCM (int16 or float32 samples), base 16-byte aligned
     int64_t total_samples;      // samples in pcm
     const int64_t* seg_start;   // [U] first sample of each (trimmed) utterance inside pcm
     const int32_t* seg_len;     // [U] samples
@@ -33,6 +33,7 @@ struct MfccParams {
     float* out;                 // [F_total, 3*numcep]
     // dims
     int frame_len, frame_step, nfilt, numcep, delta_n, seg_frames, nrange, append_energy;
+    int spec_kind;              // MODE 2 only: 0 power, 1 magnitude, 2 10*log10(power)
     float preemph, delta_scale, pow_scale;
     // table blob offsets, in floats
     int o_twa, o_twp, o_sub, o_rsub, o_task, o_dct, o_win, dct_stride, tbl_floats;

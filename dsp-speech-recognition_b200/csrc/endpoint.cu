@@ -78,6 +78,31 @@ int dspfe_endpoint_decide_host(const dspfe_endpoint_params* p, const int32_t* as
     return DSPFE_OK;
 }
 
+int dspfe_amplitude_rule_host(const dspfe_endpoint_params* p, const double* amp, int32_t n_frames, double mh,
+                              int32_t* segs, int32_t seg_cap, int32_t* n_segs) {
+    if (!p || !amp || !n_segs || n_frames < 1 || seg_cap < 1 || !segs) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    EpRule r; int fl, fs;
+    int rc = fill_rule(*p, r, fl, fs);
+    if (rc) return rc;
+    int left, right;
+    const int n = amplitude_rule(AmpFromF64{amp}, n_frames, r, mh, &left, &right, segs, seg_cap);
+    if (n == 0) { segs[0] = 0; segs[1] = n_frames; *n_segs = 1; } else { *n_segs = n; }   // reference: [(0, len(amp))]
+    return DSPFE_OK;
+}
+
+int dspfe_zcr_rule_host(const dspfe_endpoint_params* p, const double* zcr, int32_t n_frames, double l_sil, int32_t left,
+                        int32_t right, int32_t* out_jk) {
+    if (!p || !zcr || !out_jk || n_frames < 1 || left < 0 || left >= n_frames || right < 0 || right > n_frames)
+        return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    EpRule r; int fl, fs;
+    int rc = fill_rule(*p, r, fl, fs);
+    if (rc) return rc;
+    int j, k;
+    zcr_rule(AmpFromF64{zcr}, n_frames, r, l_sil, left, right, &j, &k);
+    out_jk[0] = j; out_jk[1] = k;
+    return DSPFE_OK;
+}
+
 int dspfe_endpoint_create(const dspfe_endpoint_params* p, dspfe_endpoint_plan** plan) {
     if (!p || !plan) return fail(DSPFE_ERR_INVALID_ARG, "null argument");
     *plan = nullptr;

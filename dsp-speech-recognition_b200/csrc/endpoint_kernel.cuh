@@ -68,17 +68,22 @@ DSP_HD void np_mean_std(const double* a, int n, double* mean, double* std) {
     *std = sqrt(np_pairwise_sum(sq, n) / (double)n);
 }
 
-// amplitude_rule (endpoint.py:133-179) reduced to what basic_endpoint_detection uses: (first segment start,
-// last segment end), or (0, F) when no segment qualifies.  asum[f] = sum |x| of frame f.
-DSP_HD void amplitude_rule(const int32_t* asum, int F, int frame_len, const EpRule& r, double mh, int* left, int* right) {
-    const double inv = (double)frame_len;
+// Frame statistics come either as exact integer sums (device path: amp = sum|x| / frame_len) or as float64
+// values (host entry points that mirror the reference's list-based API).
+struct AmpFromSum { const int32_t* s; double len; DSP_HD double operator()(int i) const { return (double)s[i] / len; } };
+struct AmpFromF64 { const double* a; DSP_HD double operator()(int i) const { return a[i]; } };
+struct ZcrFromI32 { const int32_t* z; DSP_HD double operator()(int i) const { return (double)z[i]; } };
+
+// amplitude_rule (endpoint.py:133-179).  Writes up to seg_cap (j,k) pairs to segs (may be null) and returns the
+// number of segments found; *left/*right = first segment start / last segment end, or (0, F) when none qualifies.
+template <class Amp>
+DSP_HD int amplitude_rule(Amp amp, int F, const EpRule& r, double mh, int* left, int* right, int32_t* segs = nullptr, int seg_cap = 0) {
     const int nl = (int)(r.l_sil / r.cfg_step), nr = (int)(r.r_sil / r.cfg_step);
     double sil[64];
     int n = 0;
-    // amp[:nl] + amp[-nr:] with Python slice clamping
-    for (int i = 0; i < nl && i < F && n < 64; ++i) sil[n++] = (double)asum[i] / inv;
-    if (nr > 0) for (int i = (F - nr > 0 ? F - nr : 0); i < F && n < 64; ++i) sil[n++] = (double)asum[i] / inv;
-    else for (int i = 0; i < F && n < 64; ++i) sil[n++] = (double)asum[i] / inv;   // amp[-0:] is the whole list
+    // amp[:nl] + amp[-nr:] with Python slice clamping (amp[-0:] is the whole list)
+    for (int i = 0; i < nl && i < F && n < 64; ++i) sil[n++] = amp(i);
+    for (int i = (nr > 0 && F - nr > 0 ? F - nr : 0); i < F && n < 64; ++i) sil[n++] = amp(i);
     // sorted(sil)[:-2]
     for (int i = 1; i < n; ++i) { double v = sil[i]; int j = i - 1; while (j >= 0 && sil[j] > v) { sil[j + 1] = sil[j]; --j; } sil[j + 1] = v; }
     n = n - 2 > 0 ? n - 2 : 0;
@@ -86,56 +91,61 @@ DSP_HD void amplitude_rule(const int32_t* asum, int F, int frame_len, const EpRu
     np_mean_std(sil, n, &s_mean, &s_sigma);
     const double T_H = r.th / r.cfg_frame;
     const double M_L = s_mean + r.sigma * s_sigma;
-    int32_t amax = 0;
-    for (int i = 0; i < F; ++i) amax = asum[i] > amax ? asum[i] : amax;
-    const double a_hi = ((double)amax / inv) * mh;
-    const double M_H = (M_L > a_hi) ? M_L : a_hi;   // Python max(a_hi, M_L): NaN M_L keeps a_hi
-    int first = -1, last = -1;
+    double amax = amp(0);
+    for (int i = 1; i < F; ++i) { const double v = amp(i); amax = v > amax ? v : amax; }
+    const double a_hi = amax * mh;
+    const double M_H = (M_L > a_hi) ? M_L : a_hi;   // Python max(a_hi, M_L): a NaN M_L keeps a_hi
+    int first = -1, last = -1, nseg = 0;
     int i = 0;
     while (i < F) {
-        if ((double)asum[i] / inv >= M_H) {
+        if (amp(i) >= M_H) {
             int j = i, k = i;
-            while (k < F && (double)asum[k] / inv > M_H) ++k;
+            while (k < F && amp(k) > M_H) ++k;
             if ((double)(k - j) < T_H) {
                 i = k;
             } else {
-                while (j > 0 && (double)asum[j] / inv > M_L) --j;
-                while (k < F && (double)asum[k] / inv > M_L) ++k;
+                while (j > 0 && amp(j) > M_L) --j;
+                while (k < F && amp(k) > M_L) ++k;
                 if (first < 0) first = j;
                 last = k;
+                if (segs && nseg < seg_cap) { segs[2 * nseg] = j; segs[2 * nseg + 1] = k; }
+                ++nseg;
                 i = k;
             }
         }
         ++i;
     }
     if (first < 0) { *left = 0; *right = F; } else { *left = first; *right = last; }
+    return nseg;
 }
 
-// zcr_rule (endpoint.py:201-220)
-DSP_HD void zcr_rule(const int32_t* zcr, int F, const EpRule& r, int left, int right, int* l2, int* r2) {
+// zcr_rule (endpoint.py:201-220); l_sil is a parameter of the reference function but its only caller uses 0
+template <class Zcr>
+DSP_HD void zcr_rule(Zcr zcr, int F, const EpRule& r, double l_sil, int left, int right, int* l2, int* r2) {
     const double max_shift = r.zcr_max_shift / r.cfg_frame;
-    const int nr = (int)(r.zcr_r_sil / r.cfg_step);
+    const int nl = (int)(l_sil / r.cfg_step), nr = (int)(r.zcr_r_sil / r.cfg_step);
     double sil[64];
     int n = 0;
-    if (nr > 0) for (int i = (F - nr > 0 ? F - nr : 0); i < F && n < 64; ++i) sil[n++] = (double)zcr[i];
-    else for (int i = 0; i < F && n < 64; ++i) sil[n++] = (double)zcr[i];
+    for (int i = 0; i < nl && i < F && n < 64; ++i) sil[n++] = zcr(i);
+    for (int i = (nr > 0 && F - nr > 0 ? F - nr : 0); i < F && n < 64; ++i) sil[n++] = zcr(i);
     double mu, sg;
     np_mean_std(sil, n, &mu, &sg);
     const double thres = mu + 3 * sg;
     int j = left;
-    while (j > 0 && (double)(left - j) <= max_shift && (double)zcr[j] > thres) --j;
+    while (j > 0 && (double)(left - j) <= max_shift && zcr(j) > thres) --j;
     int k = right;
-    while (k < F && (double)(k - right) <= max_shift && (double)zcr[k] > thres) ++k;
+    while (k < F && (double)(k - right) <= max_shift && zcr(k) > thres) ++k;
     *l2 = j; *r2 = k;
 }
 
 // basic_endpoint_detection (endpoint.py:34-66): frame-level decision + conversion to sample indices.
 DSP_HD void endpoint_decide(const int32_t* asum, const int32_t* zcr, int F, int frame_len, const EpRule& r, int32_t* out_lr) {
     int left, right;
-    amplitude_rule(asum, F, frame_len, r, r.mh1, &left, &right);
-    if (right - left < r.min_span) amplitude_rule(asum, F, frame_len, r, r.mh2, &left, &right);
+    const AmpFromSum amp{asum, (double)frame_len};
+    amplitude_rule(amp, F, r, r.mh1, &left, &right);
+    if (right - left < r.min_span) amplitude_rule(amp, F, r, r.mh2, &left, &right);
     int l2, r2;
-    zcr_rule(zcr, F, r, left, right, &l2, &r2);
+    zcr_rule(ZcrFromI32{zcr}, F, r, 0.0, left, right, &l2, &r2);
     if (r2 - l2 < r.min_span) { l2 = 0; r2 = F; }
     // int(left2 * cfg.step * rate): float64 product evaluated left to right, truncated (Appendix A-9)
     out_lr[0] = (int32_t)((double)l2 * r.cfg_step * (double)r.rate);

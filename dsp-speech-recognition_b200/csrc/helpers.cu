@@ -1,0 +1,148 @@
+// Small single-purpose kernels behind the reference's helper functions (include/dspfe.h, "helpers").
+// They exist so that every arithmetic entry point of the drop-in `features` package runs on the GPU; none
+// of them is on the throughput path (the fused kernels never materialise frames).  float64 where the
+// reference result is float64 and cheap to reproduce exactly (framing, pre-emphasis, row statistics).
+#include "abi_common.h"
+#include "dspfe_types.h"
+
+using namespace dspfe;
+
+namespace {
+
+// framesig (sigproc.py:66-98): zero-padded overlapping frames times the window
+__global__ void frames_kernel(const double* sig, int64_t n, int frame_len, int frame_step, const double* win, int64_t nframes, double* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nframes * frame_len) return;
+    const int64_t f = i / frame_len;
+    const int k = (int)(i - f * frame_len);
+    const int64_t s = f * frame_step + k;
+    const double v = s < n ? sig[s] : 0.0;
+    out[i] = win ? v * win[k] : v;
+}
+
+// preemphasis (sigproc.py:178-185)
+__global__ void preemph_kernel(const double* x, int64_t n, double coeff, double* y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = i == 0 ? x[0] : x[i] - coeff * x[i - 1];
+}
+
+// numpy's pairwise sum for any n, evaluated without recursion (explicit stack of pending right halves)
+__device__ double pairwise_block(const double* a, int n, bool absval, bool sq) {
+    auto f = [&](double v) { return sq ? v * v : (absval ? fabs(v) : v); };
+    if (n < 8) { double r = 0.; for (int i = 0; i < n; ++i) r += f(a[i]); return r; }
+    double r0 = f(a[0]), r1 = f(a[1]), r2 = f(a[2]), r3 = f(a[3]), r4 = f(a[4]), r5 = f(a[5]), r6 = f(a[6]), r7 = f(a[7]);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+        r0 += f(a[i]); r1 += f(a[i + 1]); r2 += f(a[i + 2]); r3 += f(a[i + 3]);
+        r4 += f(a[i + 4]); r5 += f(a[i + 5]); r6 += f(a[i + 6]); r7 += f(a[i + 7]);
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += f(a[i]);
+    return res;
+}
+__device__ double np_sum_any(const double* a, int n, bool absval, bool sq) {
+    // numpy: n > 128 -> n2 = n/2 rounded down to a multiple of 8; sum(left) + sum(right).  Post-order walk.
+    struct Item { const double* p; int n; int state; double left; };
+    Item st[24];
+    int sp = 0;
+    st[0] = {a, n, 0, 0.};
+    double ret = 0.;
+    while (sp >= 0) {
+        Item& t = st[sp];
+        if (t.n <= 128) { ret = pairwise_block(t.p, t.n, absval, sq); --sp; continue; }
+        int n2 = t.n / 2; n2 -= n2 % 8;
+        if (t.state == 0) { t.state = 1; st[++sp] = {t.p, n2, 0, 0.}; }
+        else if (t.state == 1) { t.left = ret; t.state = 2; st[++sp] = {t.p + n2, t.n - n2, 0, 0.}; }
+        else { ret = t.left + ret; --sp; }
+    }
+    return ret;
+}
+
+// get_amplitude (endpoint.py:109-126, window='square'): mean |x| (or x^2) per frame, numpy summation order
+__global__ void row_amp_kernel(const double* frames, int64_t nrows, int len, int use_sq, double* out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    out[r] = np_sum_any(frames + r * len, len, true, use_sq != 0) / (double)len;
+}
+
+// get_zcr (endpoint.py:182-198)
+__global__ void row_zcr_kernel(const double* frames, int64_t nrows, int len, int64_t* out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const double* x = frames + r * len;
+    int64_t c = 0;
+    for (int i = 0; i + 1 < len; ++i) c += (x[i] * x[i + 1] < 0.0) ? 1 : 0;
+    out[r] = c;
+}
+
+// delta (base.py:70-79) on an arbitrary [F, C] float32 matrix
+__global__ void delta_kernel(const float* in, int64_t F, int C, int N, float scale, float* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * C) return;
+    const int64_t t = i / C;
+    const int c = (int)(i - t * C);
+    float acc = 0.f;
+    for (int n = 1; n <= N; ++n) {
+        const int64_t hi = t + n > F - 1 ? F - 1 : t + n, lo = t - n < 0 ? 0 : t - n;
+        acc = fmaf((float)n, in[hi * C + c] - in[lo * C + c], acc);
+    }
+    out[i] = acc * scale;
+}
+
+unsigned grid_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+extern "C" {
+
+int dspfe_frames_f64(const double* d_sig, int64_t n, int32_t frame_len, int32_t frame_step, const double* d_win,
+                     double* d_out, int64_t n_frames, void* stream) {
+    if (!d_out || frame_len < 1 || frame_step < 1 || n < 0 || (!d_sig && n > 0)) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_frames != num_frames(n, frame_len, frame_step)) return fail(DSPFE_ERR_INVALID_ARG, "n_frames must equal dspfe_num_frames()");
+    cudaStream_t st = (cudaStream_t)stream;
+    frames_kernel<<<grid_for(n_frames * frame_len, 256), 256, 0, st>>>(d_sig, n, frame_len, frame_step, d_win, n_frames, d_out);
+    LAUNCH_CHECK("frames_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_preemphasis_f64(const double* d_x, int64_t n, double coeff, double* d_y, void* stream) {
+    if (n < 0 || (n > 0 && (!d_x || !d_y))) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return DSPFE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    preemph_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_x, n, coeff, d_y);
+    LAUNCH_CHECK("preemph_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_row_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t use_sq, double* d_out, void* stream) {
+    if (n_rows < 0 || len < 1 || (n_rows > 0 && (!d_frames || !d_out))) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_rows == 0) return DSPFE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    row_amp_kernel<<<grid_for(n_rows, 128), 128, 0, st>>>(d_frames, n_rows, len, use_sq, d_out);
+    LAUNCH_CHECK("row_amp_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_row_zcr_f64(const double* d_frames, int64_t n_rows, int32_t len, int64_t* d_out, void* stream) {
+    if (n_rows < 0 || len < 1 || (n_rows > 0 && (!d_frames || !d_out))) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_rows == 0) return DSPFE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    row_zcr_kernel<<<grid_for(n_rows, 128), 128, 0, st>>>(d_frames, n_rows, len, d_out);
+    LAUNCH_CHECK("row_zcr_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_delta_f32(const float* d_in, int64_t n_frames, int32_t n_cols, int32_t N, float* d_out, void* stream) {
+    if (N < 1) return fail(DSPFE_ERR_INVALID_ARG, "N must be an integer >= 1");
+    if (n_frames < 0 || n_cols < 1 || (n_frames > 0 && (!d_in || !d_out))) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_frames == 0) return DSPFE_OK;
+    int den = 0;
+    for (int i = 1; i <= N; ++i) den += i * i;
+    cudaStream_t st = (cudaStream_t)stream;
+    delta_kernel<<<grid_for(n_frames * n_cols, 256), 256, 0, st>>>(d_in, n_frames, n_cols, N, (float)(1.0 / (2.0 * den)), d_out);
+    LAUNCH_CHECK("delta_kernel", st);
+    return DSPFE_OK;
+}
+
+}  // extern "C"

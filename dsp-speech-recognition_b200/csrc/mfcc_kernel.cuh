@@ -76,18 +76,20 @@ struct MfccSmem {
     float2* scratch;   // per group: kScratchUnits float2
     float* mfcc;       // [(seg_frames + 4N)][numcep]
     float* fbuf;       // pre-emphasised fp32 samples of the current chunk
-    int16_t* raw;      // raw PCM chunk (bulk-copy destination)
+    unsigned char* raw;  // raw PCM chunk (bulk-copy destination): int16 or float32 samples
 };
 
 struct ChunkGeom {
-    int64_t a0s;        // packed-buffer sample index that lands at raw[0] (multiple of 8)
+    int64_t a0s;        // packed-buffer sample index that lands at raw[0] (16-byte aligned)
     int64_t bulk_src;   // == a0s
     int bulk_bytes;     // multiple of 16, may be 0
     int64_t tail_lo, tail_hi;  // packed sample range loaded with plain loads
     int64_t s0;         // utterance sample index of fbuf[0]
 };
 
+template <bool F32>
 DEVFN ChunkGeom chunk_geom(const MfccParams& p, int64_t start, int S, int frame0) {
+    const int64_t AL = F32 ? 3 : 7;   // samples per 16 bytes, minus one
     ChunkGeom g;
     g.s0 = (int64_t)frame0 * p.frame_step;
     int64_t s_first = g.s0 > 0 ? g.s0 - 1 : 0;
@@ -95,20 +97,23 @@ DEVFN ChunkGeom chunk_geom(const MfccParams& p, int64_t start, int S, int frame0
     if (s_last > S) s_last = S;
     if (s_last < s_first) s_last = s_first;
     int64_t p_first = start + s_first, p_last = start + s_last;
-    g.a0s = p_first & ~(int64_t)7;
-    int64_t a1s = (p_last + 7) & ~(int64_t)7;
-    int64_t lim = p.total_samples & ~(int64_t)7;
+    g.a0s = p_first & ~AL;
+    int64_t a1s = (p_last + AL) & ~AL;
+    int64_t lim = p.total_samples & ~AL;
     if (a1s > lim) a1s = lim;
     if (a1s < g.a0s) a1s = g.a0s;
     g.bulk_src = g.a0s;
-    g.bulk_bytes = (int)(a1s - g.a0s) * 2;
+    g.bulk_bytes = (int)(a1s - g.a0s) * (F32 ? 4 : 2);
     g.tail_lo = a1s > p_first ? a1s : p_first;
     g.tail_hi = p_last;
     return g;
 }
 
 // NFULL = frame_len / 32 (FFT input rows that lie fully inside the frame) when known at compile time, else -1.
-template <bool HAS_WIN, int NFULL>
+// F32IN: the packed batch holds float32 samples instead of int16 (e.g. a signal the caller already scaled).
+// MODE: 0 = MFCC + delta + delta-delta rows [F, 3*numcep]; 1 = filterbank energies + frame energy [F, nfilt+1]
+// (reference fbank, base.py:18); 2 = spectrum [F, 257]: power (sigproc.py:151), magnitude (:136) or 10*log10 power (:161).
+template <bool HAS_WIN, int NFULL, bool F32IN, int MODE>
 DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     const int tid = simt::tid();
     const int lane = tid & 15;
@@ -122,7 +127,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     sm.scratch = reinterpret_cast<float2*>(smem_raw + p.sm_scratch);
     sm.mfcc = reinterpret_cast<float*>(smem_raw + p.sm_mfcc);
     sm.fbuf = reinterpret_cast<float*>(smem_raw + p.sm_fbuf);
-    sm.raw = reinterpret_cast<int16_t*>(smem_raw + p.sm_raw);
+    sm.raw = smem_raw + p.sm_raw;
 
     const Tile tile = p.tiles[tile_id];
     const int u = tile.utt;
@@ -130,7 +135,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     const int S = p.seg_len[u];
     const int64_t row0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - row0);
-    const int N = p.delta_n;
+    const int N = MODE == 0 ? p.delta_n : 0;   // the tap modes need no delta halo
     const int numcep = p.numcep;
     const int v_lo = tile.f0 - 2 * N > 0 ? tile.f0 - 2 * N : 0;
     const int v_hi = tile.f0 + tile.nf - 1 + 2 * N < F - 1 ? tile.f0 + tile.nf - 1 + 2 * N : F - 1;
@@ -152,13 +157,18 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     float2* scr = sm.scratch + grp * kScratchUnits;
 
     auto issue_chunk = [&](int c) {
-        ChunkGeom g = chunk_geom(p, start, S, v_lo + c * kFramesPerPass);
+        ChunkGeom g = chunk_geom<F32IN>(p, start, S, v_lo + c * kFramesPerPass);
+        const int esz = F32IN ? 4 : 2;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.pcm);
         if (tid == 0 && g.bulk_bytes > 0) {
             simt::fence_proxy_async();
             simt::mbar_expect_tx(sm.mbar, (uint32_t)g.bulk_bytes);
-            simt::bulk_g2s(sm.raw, p.pcm + g.bulk_src, (uint32_t)g.bulk_bytes, sm.mbar);
+            simt::bulk_g2s(sm.raw, src + g.bulk_src * esz, (uint32_t)g.bulk_bytes, sm.mbar);
         }
-        for (int64_t i = g.tail_lo + tid; i < g.tail_hi; i += kMfccThreads) sm.raw[i - g.a0s] = p.pcm[i];
+        for (int64_t i = g.tail_lo + tid; i < g.tail_hi; i += kMfccThreads) {
+            if (F32IN) reinterpret_cast<float*>(sm.raw)[i - g.a0s] = reinterpret_cast<const float*>(src)[i];
+            else reinterpret_cast<int16_t*>(sm.raw)[i - g.a0s] = reinterpret_cast<const int16_t*>(src)[i];
+        }
     };
     issue_chunk(0);
 
@@ -166,7 +176,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     uint32_t parity = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int frame0 = v_lo + c * kFramesPerPass;
-        const ChunkGeom g = chunk_geom(p, start, S, frame0);
+        const ChunkGeom g = chunk_geom<F32IN>(p, start, S, frame0);
         if (g.bulk_bytes > 0) { simt::mbar_wait(sm.mbar, parity); parity ^= 1; }
         if (c == 0) simt::cta_sync();  // chunk-0 tail stores -> visible (later chunks: the loop-end barrier)
 
@@ -178,15 +188,23 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             for (int j0 = 0; j0 < p.fbuf_vecs; j0 += kMfccThreads) {
                 const int j = j0 + tid;
                 const bool act = j < p.fbuf_vecs;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (act) v = reinterpret_cast<const uint4*>(sm.raw)[j];
-                uint32_t pw = (uint32_t)simt::shfl32_i((int)v.w, (tid & 31) - 1);   // previous thread's last pair
-                if ((tid & 31) == 0) pw = (act && j > 0) ? ((uint32_t)(uint16_t)sm.raw[8 * j - 1]) << 16 : 0u;
-                if (act) {
-                    float e[9];
+                float e[9];
+                if (F32IN) {
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (act) { v0 = reinterpret_cast<const float4*>(sm.raw)[2 * j]; v1 = reinterpret_cast<const float4*>(sm.raw)[2 * j + 1]; }
+                    float pv = __int_as_float_compat(simt::shfl32_i(__float_as_int_compat(v1.w), (tid & 31) - 1));
+                    if ((tid & 31) == 0) pv = (act && j > 0) ? reinterpret_cast<const float*>(sm.raw)[8 * j - 1] : 0.f;
+                    e[0] = pv; e[1] = v0.x; e[2] = v0.y; e[3] = v0.z; e[4] = v0.w; e[5] = v1.x; e[6] = v1.y; e[7] = v1.z; e[8] = v1.w;
+                } else {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (act) v = reinterpret_cast<const uint4*>(sm.raw)[j];
+                    uint32_t pw = (uint32_t)simt::shfl32_i((int)v.w, (tid & 31) - 1);   // previous thread's last pair
+                    if ((tid & 31) == 0) pw = (act && j > 0) ? ((uint32_t)reinterpret_cast<const uint16_t*>(sm.raw)[8 * j - 1]) << 16 : 0u;
                     e[0] = cvt_hi16(pw);
                     e[1] = cvt_lo16(v.x); e[2] = cvt_hi16(v.x); e[3] = cvt_lo16(v.y); e[4] = cvt_hi16(v.y);
                     e[5] = cvt_lo16(v.z); e[6] = cvt_hi16(v.z); e[7] = cvt_lo16(v.w); e[8] = cvt_hi16(v.w);
+                }
+                if (act) {
                     float y[8];
 #pragma unroll
                     for (int m = 0; m < 8; ++m) y[m] = dsp_fmaf(-cpre, e[m], e[m + 1]);
@@ -302,6 +320,16 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 }
             }
             simt::group_sync();
+            if (MODE == 2) {   // spectrum tap: rows straight to global memory
+                const float nfft = (float)kNfft;
+                for (int k = lane; k < kBins; k += 16) {
+                    float2 v = scr[k];
+                    if (p.spec_kind == 1) { v.x = sqrtf(v.x * nfft); v.y = sqrtf(v.y * nfft); }
+                    else if (p.spec_kind == 2) { v.x = 10.f * log10f(fmaxf(v.x, 1e-30f)); v.y = 10.f * log10f(fmaxf(v.y, 1e-30f)); }
+                    if (vA <= v_hi) p.out[(row0 + vA) * kBins + k] = v.x;
+                    if (vA + 2 <= v_hi) p.out[(row0 + vA + 2) * kBins + k] = v.y;
+                }
+            } else {
 
             // ---- mel filterbank as sums over sub-ranges of the triangle edges (see mfcc_tables.h): the weights
             // are generated arithmetically, each power bin is read exactly once.
@@ -356,11 +384,16 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 }
                 if (f.x == 0.f) f.x = eps64;
                 if (f.y == 0.f) f.y = eps64;
-                lmel[j] = make_float2(dsp_logf(f.x), dsp_logf(f.y));
+                if (MODE == 1) {   // filterbank tap (column nfilt = frame energy)
+                    if (vA <= v_hi) p.out[(row0 + vA) * (p.nfilt + 1) + j] = f.x;
+                    if (vA + 2 <= v_hi) p.out[(row0 + vA + 2) * (p.nfilt + 1) + j] = f.y;
+                } else {
+                    lmel[j] = make_float2(dsp_logf(f.x), dsp_logf(f.y));
+                }
             }
             simt::group_sync();
             // ---- DCT-II (ortho) * lifter, c0 := log(energy)
-            if (lane < numcep) {
+            if (MODE == 0 && lane < numcep) {
                 float2 acc = make_float2(0.f, 0.f);
                 const float2* drow = reinterpret_cast<const float2*>(dct + lane * p.dct_stride);
                 const float4* lm4 = reinterpret_cast<const float4*>(lmel);
@@ -376,10 +409,12 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 if (vA <= v_hi) sm.mfcc[(vA - v_lo) * numcep + lane] = acc.x;
                 if (vA + 2 <= v_hi) sm.mfcc[(vA + 2 - v_lo) * numcep + lane] = acc.y;
             }
+            }   // MODE != 2
         }
         simt::cta_sync();  // fbuf may be overwritten by the next conversion pass
     }
 
+    if (MODE != 0) return;
     // ---- epilogue: delta (clamped on the utterance), delta-delta (clamped on the delta array), stores.
     // Three uniform passes (no divergent per-column work); flat indices advance by the CTA size without any
     // division: (row, col) += (128 / w, 128 % w).

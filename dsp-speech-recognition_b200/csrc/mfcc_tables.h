@@ -64,7 +64,8 @@ inline std::string mfcc_config_check(const MfccConfig& c) {
 
 // Fills the layout fields of `p` (table offsets, shared-memory carve-up, scalars) and returns the
 // table blob.  Pointer fields of `p` are left untouched.
-inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, std::string& err) {
+// `in_f32` selects the shared-memory layout for float32 input samples (a 4-byte raw staging area).
+inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, std::string& err, bool in_f32 = false) {
     err = mfcc_config_check(c);
     std::vector<float> blob;
     if (!err.empty()) return blob;
@@ -177,7 +178,7 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     // fbuf mirrors raw index for index
     p.fbuf_vecs = (p.fbuf_floats + 1 + 14 + 7) / 8;
     const int fbuf_bytes = p.fbuf_vecs * 8 * 4;
-    const int raw_bytes = p.fbuf_vecs * 8 * 2;
+    const int raw_bytes = p.fbuf_vecs * 8 * (in_f32 ? 4 : 2);
     const int dbuf_bytes = up16((c.seg_frames + 2 * c.delta_n) * c.numcep * 4);
     p.sm_fbuf = off;
     p.sm_raw = off + fbuf_bytes;

@@ -42,6 +42,7 @@ DEVFN float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y
 DEVFN float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 DEVFN float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
 DEVFN float dsp_logf(float x) { return std::log(x); }
+static inline float sqrtf_(float x) { return std::sqrt(x); }
 DEVFN float dsp_fmaf(float a, float b, float c) { return std::fmaf(a, b, c); }
 // int16 halves of a 32-bit word -> float
 DEVFN float cvt_lo16(uint32_t w) { return (float)(int16_t)(w & 0xffffu); }
@@ -101,6 +102,14 @@ DEVFN float dsp_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
 // value into the mantissa of 2^23 and subtract 2^23 + 2^15 (exact).
 DEVFN float cvt_lo16(uint32_t w) { return __uint_as_float(__byte_perm(w ^ 0x80008000u, 0x4B000000u, 0x7610)) - 8421376.0f; }
 DEVFN float cvt_hi16(uint32_t w) { return __uint_as_float(__byte_perm(w ^ 0x80008000u, 0x4B000000u, 0x7632)) - 8421376.0f; }
+#endif
+
+#ifdef DSPFE_EMU
+DEVFN int __float_as_int_compat(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+DEVFN float __int_as_float_compat(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+#else
+DEVFN int __float_as_int_compat(float f) { return __float_as_int(f); }
+DEVFN float __int_as_float_compat(int i) { return __int_as_float(i); }
 #endif
 
 // scalar-broadcast forms (the scalar folds into the packed instruction's .F32 operand)

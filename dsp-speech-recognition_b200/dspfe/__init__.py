@@ -5,4 +5,5 @@ kernels in csrc/.  There is no CPU fallback: if libdspfe.so is missing or no CUD
 present, the compute entry points raise.
 """
 from .binding import (DspfeError, EndpointPlan, MfccPlan, endpoint_decide_host, endpoint_params, frame_counts,  # noqa: F401
-                      lib, lib_path, mfcc_params, mfcc_tables_host, num_frames)
+                      lib, lib_path, mfcc_params, mfcc_tables_host, num_frames, frames_f64, preemphasis_f64,
+                      row_amplitude_f64, row_zcr_f64, delta_f32, amplitude_rule_host, zcr_rule_host)

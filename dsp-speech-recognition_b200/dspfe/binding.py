@@ -197,6 +197,10 @@ def _bind_endpoint(L):
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.dspfe_endpoint_decide_host.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_int32, ctypes.c_void_p]
+    L.dspfe_amplitude_rule_host.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.c_void_p, ctypes.c_int32, ctypes.c_double,
+                                            ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    L.dspfe_zcr_rule_host.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.c_void_p, ctypes.c_int32, ctypes.c_double,
+                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     L._ep_bound = True
 
 
@@ -220,6 +224,26 @@ def endpoint_decide_host(asum, zcr, **kw):
     _check(lib().dspfe_endpoint_decide_host(ctypes.byref(p), asum.ctypes.data_as(ctypes.c_void_p),
                                             zcr.ctypes.data_as(ctypes.c_void_p), len(asum), lr.ctypes.data_as(ctypes.c_void_p)))
     return int(lr[0]), int(lr[1])
+
+
+def amplitude_rule_host(amp, mh=0.25, **kw):
+    """amplitude_rule on a float64 list: returns the reference's list of (j, k) segments."""
+    p = endpoint_params(**kw)
+    amp = np.ascontiguousarray(amp, dtype=np.float64)
+    segs = np.zeros((max(len(amp), 1), 2), dtype=np.int32)
+    n = ctypes.c_int32(0)
+    _check(lib().dspfe_amplitude_rule_host(ctypes.byref(p), amp.ctypes.data_as(ctypes.c_void_p), len(amp), float(mh),
+                                           segs.ctypes.data_as(ctypes.c_void_p), len(segs), ctypes.byref(n)))
+    return [(int(j), int(k)) for j, k in segs[: n.value]]
+
+
+def zcr_rule_host(zcr, left, right, l_sil=0.0, **kw):
+    p = endpoint_params(**kw)
+    zcr = np.ascontiguousarray(zcr, dtype=np.float64)
+    jk = np.zeros(2, dtype=np.int32)
+    _check(lib().dspfe_zcr_rule_host(ctypes.byref(p), zcr.ctypes.data_as(ctypes.c_void_p), len(zcr), float(l_sil), int(left),
+                                     int(right), jk.ctypes.data_as(ctypes.c_void_p)))
+    return int(jk[0]), int(jk[1])
 
 
 class EndpointPlan:
@@ -281,3 +305,127 @@ class EndpointPlan:
                                          n_utt, lr.ctypes.data_as(ctypes.c_void_p), asum.ctypes.data_as(ctypes.c_void_p),
                                          zcr.ctypes.data_as(ctypes.c_void_p), fo.ctypes.data_as(ctypes.c_void_p)))
         return lr, asum, zcr, fo
+
+
+# ------------------------------------------------------------------------------------------------ taps + helpers
+def _bind_helpers(L):
+    if getattr(L, "_h_bound", False):
+        return
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.dspfe_mfcc_delta_f32.argtypes = [vp, vp, i64, vp, vp, i32, vp, i64, vp, vp]
+    L.dspfe_fbank_f32.argtypes = [vp, vp, i64, vp, i32, vp, i64, vp, vp]
+    L.dspfe_spectrum_f32.argtypes = [vp, vp, i64, vp, i32, i32, vp, i64, vp, vp]
+    L.dspfe_frames_f64.argtypes = [vp, i64, i32, i32, vp, vp, i64, vp]
+    L.dspfe_preemphasis_f64.argtypes = [vp, i64, ctypes.c_double, vp, vp]
+    L.dspfe_row_amplitude_f64.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.dspfe_row_zcr_f64.argtypes = [vp, i64, i32, vp, vp]
+    L.dspfe_delta_f32.argtypes = [vp, i64, i32, i32, vp, vp]
+    L._h_bound = True
+
+
+def _cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise DspfeError(-3, "no CUDA device: libdspfe has no CPU fallback")
+    return torch, torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream(torch, dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _mfcc_f32(self, pcm, offsets, trim=None):
+    """float32-sample variant of MfccPlan.mfcc_delta (device tensors)."""
+    import torch
+    L = lib(); _bind_helpers(L)
+    assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+    n_utt = offsets.numel() - 1
+    rows = self.rows_bound(pcm.numel(), n_utt)
+    out = torch.empty((rows, self.width), dtype=torch.float32, device=pcm.device)
+    fo = torch.empty(n_utt + 1, dtype=torch.int64, device=pcm.device)
+    tp = None if trim is None else trim.data_ptr()
+    _check(L.dspfe_mfcc_delta_f32(self._h, pcm.data_ptr(), pcm.numel(), offsets.data_ptr(), tp, n_utt, out.data_ptr(), rows,
+                                  fo.data_ptr(), _stream(torch, pcm.device)))
+    return out, fo
+
+
+def _fbank_f32(self, pcm, offsets):
+    """[rows, nfilt+1] float32: filterbank energies and the frame energy (reference base.fbank)."""
+    import torch
+    L = lib(); _bind_helpers(L)
+    assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+    n_utt = offsets.numel() - 1
+    rows = self.rows_bound(pcm.numel(), n_utt)
+    out = torch.empty((rows, self._p.nfilt + 1), dtype=torch.float32, device=pcm.device)
+    fo = torch.empty(n_utt + 1, dtype=torch.int64, device=pcm.device)
+    _check(L.dspfe_fbank_f32(self._h, pcm.data_ptr(), pcm.numel(), offsets.data_ptr(), n_utt, out.data_ptr(), rows, fo.data_ptr(),
+                             _stream(torch, pcm.device)))
+    return out, fo
+
+
+def _spectrum_f32(self, pcm, offsets, kind=0):
+    """[rows, 257] float32: kind 0 power, 1 magnitude, 2 10*log10(power) (reference sigproc.powspec/magspec/logpowspec)."""
+    import torch
+    L = lib(); _bind_helpers(L)
+    assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+    n_utt = offsets.numel() - 1
+    rows = self.rows_bound(pcm.numel(), n_utt)
+    out = torch.empty((rows, self._p.nfft // 2 + 1), dtype=torch.float32, device=pcm.device)
+    fo = torch.empty(n_utt + 1, dtype=torch.int64, device=pcm.device)
+    _check(L.dspfe_spectrum_f32(self._h, pcm.data_ptr(), pcm.numel(), offsets.data_ptr(), n_utt, int(kind), out.data_ptr(), rows,
+                                fo.data_ptr(), _stream(torch, pcm.device)))
+    return out, fo
+
+
+MfccPlan.mfcc_delta_f32 = _mfcc_f32
+MfccPlan.fbank_f32 = _fbank_f32
+MfccPlan.spectrum_f32 = _spectrum_f32
+
+
+def frames_f64(sig, frame_len, frame_step, win=None):
+    """framesig on the device: NumPy 1-D signal -> float64 [n_frames, frame_len]."""
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    x = torch.from_numpy(np.ascontiguousarray(sig, dtype=np.float64)).to(dev)
+    nf = num_frames(x.numel(), frame_len, frame_step)
+    w = None if win is None else torch.from_numpy(np.ascontiguousarray(win, dtype=np.float64)).to(dev)
+    out = torch.empty((nf, frame_len), dtype=torch.float64, device=dev)
+    _check(L.dspfe_frames_f64(x.data_ptr(), x.numel(), int(frame_len), int(frame_step), None if w is None else w.data_ptr(),
+                              out.data_ptr(), nf, _stream(torch, dev)))
+    return out.cpu().numpy()
+
+
+def preemphasis_f64(x, coeff):
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    y = torch.empty_like(xd)
+    _check(L.dspfe_preemphasis_f64(xd.data_ptr(), xd.numel(), float(coeff), y.data_ptr(), _stream(torch, dev)))
+    return y.cpu().numpy()
+
+
+def row_amplitude_f64(frames, use_sq=False):
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    f = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64)).to(dev)
+    out = torch.empty(f.shape[0], dtype=torch.float64, device=dev)
+    _check(L.dspfe_row_amplitude_f64(f.data_ptr(), f.shape[0], f.shape[1], int(bool(use_sq)), out.data_ptr(), _stream(torch, dev)))
+    return out.cpu().numpy()
+
+
+def row_zcr_f64(frames):
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    f = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64)).to(dev)
+    out = torch.empty(f.shape[0], dtype=torch.int64, device=dev)
+    _check(L.dspfe_row_zcr_f64(f.data_ptr(), f.shape[0], f.shape[1], out.data_ptr(), _stream(torch, dev)))
+    return out.cpu().numpy()
+
+
+def delta_f32(feat, N):
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    f = torch.from_numpy(np.ascontiguousarray(feat, dtype=np.float32)).to(dev)
+    out = torch.empty_like(f)
+    _check(L.dspfe_delta_f32(f.data_ptr(), f.shape[0], f.shape[1], int(N), out.data_ptr(), _stream(torch, dev)))
+    return out.cpu().numpy()

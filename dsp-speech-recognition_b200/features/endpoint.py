@@ -1,0 +1,110 @@
+"""Drop-in for reference features/endpoint.py: energy + zero-crossing endpoint detection."""
+import numpy as np
+
+import dspfe
+from . import _gpu
+from .sigproc import *  # noqa: F401,F403  (the reference module star-imports sigproc, endpoint.py:8)
+from .preprocess import preemphasis  # noqa: F401
+
+try:  # names the reference module re-exports from the host project (endpoint.py:9-13); optional here
+    from plotter import plot_frame, show  # noqa: F401
+except Exception:
+    def plot_frame(*a, **k):
+        return None
+
+    def show(*a, **k):
+        return None
+try:
+    from reader import Reader  # noqa: F401
+except Exception:
+    Reader = None
+try:
+    from config import cfg, meta  # noqa: F401
+except Exception:
+    cfg = meta = None
+
+noise_rec = []
+
+
+def max_pitch(l, rate, bias=20):
+    """reference endpoint.py:15-18."""
+    idx = bias + np.argmax(l)
+    return 1 / (1.0 / rate * idx)
+
+
+def center_clip(frame, binary=True):
+    """reference endpoint.py:20-30 (shadowed by pitch.center_clip in the flat namespace)."""
+    from .pitch import center_clip as _cc
+    return _cc(frame, binary)
+
+
+def basic_endpoint_detection(sig, rate, return_feature=False):
+    """reference endpoint.py:34-66 on the device (K2a/K2b/K3).  Returns Python ints (left, right) in samples, plus
+    the amplitude list (np.float64) and zero-crossing list (np.int64) when return_feature."""
+    cfg_frame, cfg_step = _gpu.cfg_frame_step()
+    x, f32 = _gpu.pack_one(sig)
+    if f32:
+        raise NotImplementedError("endpoint detection is built for int16-valued PCM (what reader.py delivers)")
+    plan = _gpu.endpoint_plan(int(rate), cfg_frame, cfg_step)
+    off = np.array([0, len(x)], dtype=np.int64)
+    if not return_feature:
+        lr = plan.detect_host(x, off)
+        return int(lr[0, 0]), int(lr[0, 1])
+    lr, asum, zcr, _ = plan.detect_host(x, off, want_features=True)
+    amp = [np.float64(v) / np.float64(plan.frame_len) for v in asum]
+    return int(lr[0, 0]), int(lr[0, 1]), amp, [np.int64(v) for v in zcr]
+
+
+def robust_endpoint_detection(sig, rate):
+    """reference endpoint.py:68-92 (autocorrelation-gated expansion): listed as "next" (SURVEY f-3)."""
+    raise NotImplementedError("robust_endpoint_detection (acr-gated rule) is not built yet; see DESIGN.md, row f-3")
+
+
+def get_noise(amp, sep_point):
+    """reference endpoint.py:94-107."""
+    if sep_point[0] == (0, len(amp)):
+        return 1e30
+    left, noise, l = 0, 0, 0
+    for item in sep_point:
+        noise += np.sum(amp[left:item[0]])
+        l += item[0] - left
+        left = item[1]
+    noise += np.sum(amp[left:])
+    l += len(amp) - left
+    return noise / l
+
+
+def get_amplitude(frames, window='square', use_sq=False):
+    """reference endpoint.py:109-126 on the device (dspfe_row_amplitude_f64).  Returns a list of np.float64."""
+    if not (isinstance(window, str) and window == 'square'):
+        raise NotImplementedError("only the default window='square' is built (SURVEY f-3)")
+    frames = np.asarray(frames, dtype=np.float64)
+    return [np.float64(v) for v in dspfe.row_amplitude_f64(frames, use_sq)]
+
+
+def amplitude_feature(sig, rate, winlen, step):
+    """reference endpoint.py:128-131."""
+    return get_amplitude(to_frames(sig, rate, winlen, step))  # noqa: F405
+
+
+def amplitude_rule(amp, mh=0.25, th=0.100, l_sil=0.100, r_sil=0.100, sigma=3, use_acr=False, frames=None, rate=None):
+    """reference endpoint.py:133-179: list of (j, k) frame segments, or [(0, len(amp))].  Runs the C++ rule that
+    the device kernel K3 runs (csrc/endpoint_kernel.cuh), through dspfe_amplitude_rule_host."""
+    if use_acr:
+        raise NotImplementedError("the autocorrelation gate is not built yet (SURVEY f-3)")
+    cfg_frame, cfg_step = _gpu.cfg_frame_step()
+    return dspfe.amplitude_rule_host([float(a) for a in amp], mh, cfg_frame=cfg_frame, cfg_step=cfg_step, th=float(th),
+                                     l_sil=float(l_sil), r_sil=float(r_sil), sigma=float(sigma))
+
+
+def get_zcr(frames):
+    """reference endpoint.py:182-198 on the device (dspfe_row_zcr_f64).  Returns a list of np.int64."""
+    frames = np.asarray(frames, dtype=np.float64)
+    return [np.int64(v) for v in dspfe.row_zcr_f64(frames)]
+
+
+def zcr_rule(zcr, left, right, max_shift=0.400, l_sil=0, r_sil=0.100):
+    """reference endpoint.py:201-220 (same C++ rule as K3, through dspfe_zcr_rule_host)."""
+    cfg_frame, cfg_step = _gpu.cfg_frame_step()
+    return dspfe.zcr_rule_host([float(z) for z in zcr], int(left), int(right), l_sil=float(l_sil), cfg_frame=cfg_frame,
+                               cfg_step=cfg_step, zcr_max_shift=float(max_shift), zcr_r_sil=float(r_sil))

@@ -93,6 +93,21 @@ int dspfe_mfcc_delta(dspfe_plan* plan, const int16_t* d_pcm, int64_t total_sampl
                      const int64_t* d_offsets, const int32_t* d_trim, int32_t n_utt,
                      float* d_out, int64_t max_rows, int64_t* d_frame_off, void* stream);
 
+/* Same kernel fed with float32 samples (a signal the caller has already scaled, e.g. model.py:62-63 passes
+ * sklearn-scaled audio to features.mfcc).  Offsets and trims are in samples as above. */
+int dspfe_mfcc_delta_f32(dspfe_plan* plan, const float* d_pcm, int64_t total_samples,
+                         const int64_t* d_offsets, const int32_t* d_trim, int32_t n_utt,
+                         float* d_out, int64_t max_rows, int64_t* d_frame_off, void* stream);
+
+/* Taps of the same kernel (float32 samples in).  dspfe_fbank_f32 replaces features.fbank (base.py:18-32):
+ * d_out [rows, nfilt+1] = filterbank energies, then the total frame energy, both floored at float64 eps.
+ * dspfe_spectrum_f32 replaces sigproc.powspec (:151, kind 0), magspec (:136, kind 1) and the un-normalised
+ * logpowspec (:161, kind 2): d_out [rows, nfft/2+1].  The plan's preemph / window apply as for the MFCC. */
+int dspfe_fbank_f32(dspfe_plan* plan, const float* d_pcm, int64_t total_samples, const int64_t* d_offsets, int32_t n_utt,
+                    float* d_out, int64_t max_rows, int64_t* d_frame_off, void* stream);
+int dspfe_spectrum_f32(dspfe_plan* plan, const float* d_pcm, int64_t total_samples, const int64_t* d_offsets, int32_t n_utt,
+                       int32_t kind, float* d_out, int64_t max_rows, int64_t* d_frame_off, void* stream);
+
 /* Upper bound on output rows for any batch with these totals. */
 int64_t dspfe_rows_bound(const dspfe_plan* plan, int64_t total_samples, int64_t n_utt);
 
@@ -152,6 +167,29 @@ int dspfe_endpoint_host(dspfe_endpoint_plan* plan, const int16_t* h_pcm, const i
  * float64 rule replay (NumPy summation order included) against the oracle. */
 int dspfe_endpoint_decide_host(const dspfe_endpoint_params* p, const int32_t* asum, const int32_t* zcr, int32_t n_frames,
                                int32_t* lr);
+/* Host-only list forms of the two rules, for the reference's list-based API: amplitude_rule (endpoint.py:133; the
+ * l_sil/r_sil/th/sigma of `p` apply, `mh` is the call's high-threshold factor) writes up to seg_cap (j,k) pairs and
+ * their count; zcr_rule (endpoint.py:201) writes (j,k).  Same C++ code as the device kernel K3. */
+int dspfe_amplitude_rule_host(const dspfe_endpoint_params* p, const double* amp, int32_t n_frames, double mh,
+                              int32_t* segs, int32_t seg_cap, int32_t* n_segs);
+int dspfe_zcr_rule_host(const dspfe_endpoint_params* p, const double* zcr, int32_t n_frames, double l_sil, int32_t left,
+                        int32_t right, int32_t* out_jk);
+
+/* ------------------------------------------------------------------------------------------------
+ * Helpers: the reference's small array functions as device kernels (not on the throughput path; the
+ * fused kernels never materialise frames).  All pointers are device memory.
+ * ---------------------------------------------------------------------------------------------- */
+/* framesig (sigproc.py:66-98) / to_frames (:11): [n_frames, frame_len] float64, zero padded, times d_win if given */
+int dspfe_frames_f64(const double* d_sig, int64_t n, int32_t frame_len, int32_t frame_step, const double* d_win,
+                     double* d_out, int64_t n_frames, void* stream);
+/* preemphasis (sigproc.py:178 == preprocess.py:11) */
+int dspfe_preemphasis_f64(const double* d_x, int64_t n, double coeff, double* d_y, void* stream);
+/* get_amplitude(frames, 'square', use_sq) (endpoint.py:109): per-row mean |x| or x^2 in NumPy's summation order */
+int dspfe_row_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t use_sq, double* d_out, void* stream);
+/* get_zcr(frames) (endpoint.py:182) */
+int dspfe_row_zcr_f64(const double* d_frames, int64_t n_rows, int32_t len, int64_t* d_out, void* stream);
+/* delta(feat, N) (base.py:70) on an arbitrary [n_frames, n_cols] float32 matrix */
+int dspfe_delta_f32(const float* d_in, int64_t n_frames, int32_t n_cols, int32_t N, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,8 @@ def make_params(frame_len=400, frame_step=160, nfilt=26, numcep=13, ceplifter=22
 
 def mfcc_delta(pcm, offsets, trim=None, **kw):
     p, keep = make_params(**kw)
-    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    f32 = np.asarray(pcm).dtype.kind == "f"
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32 if f32 else np.int16)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = len(offsets) - 1
     rows = int(len(pcm) // p.frame_step + n)
@@ -63,7 +64,7 @@ def mfcc_delta(pcm, offsets, trim=None, **kw):
     if trim is not None:
         trim = np.ascontiguousarray(trim, dtype=np.int32)
         tp = trim.ctypes.data_as(ctypes.c_void_p)
-    r = lib().emu_mfcc_delta(ctypes.byref(p), pcm.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(len(pcm)),
+    r = lib().emu_mfcc_delta(ctypes.byref(p), pcm.ctypes.data_as(ctypes.c_void_p), int(f32), ctypes.c_longlong(len(pcm)),
                              offsets.ctypes.data_as(ctypes.c_void_p), tp, n, out.ctypes.data_as(ctypes.c_void_p),
                              ctypes.c_longlong(rows), fo.ctypes.data_as(ctypes.c_void_p), err, 256)
     if r < 0:

@@ -12,17 +12,18 @@ namespace emu { bool run_cta(int bid, int nthreads, void (*body)(void*), void* a
 using namespace dspfe;
 
 namespace {
-struct Args { MfccParams p; bool has_win; std::vector<unsigned char>* smem; };
+struct Args { MfccParams p; bool has_win; bool f32; std::vector<unsigned char>* smem; };
 void body(void* a) {
     Args* A = (Args*)a;
     const int nfull = A->p.frame_len >> 5;
-    if (A->has_win) { if (nfull == 12) mfcc_cta<true, 12>(A->p, A->smem->data()); else mfcc_cta<true, -1>(A->p, A->smem->data()); }
-    else { if (nfull == 12) mfcc_cta<false, 12>(A->p, A->smem->data()); else mfcc_cta<false, -1>(A->p, A->smem->data()); }
+    if (A->f32) { if (A->has_win) mfcc_cta<true, -1, true, 0>(A->p, A->smem->data()); else mfcc_cta<false, -1, true, 0>(A->p, A->smem->data()); return; }
+    if (A->has_win) { if (nfull == 12) mfcc_cta<true, 12, false, 0>(A->p, A->smem->data()); else mfcc_cta<true, -1, false, 0>(A->p, A->smem->data()); }
+    else { if (nfull == 12) mfcc_cta<false, 12, false, 0>(A->p, A->smem->data()); else mfcc_cta<false, -1, false, 0>(A->p, A->smem->data()); }
 }
 }  // namespace
 
 // Same contract as dspfe_mfcc_delta but host pointers and synchronous.  Returns rows written, <0 on error.
-extern "C" long long emu_mfcc_delta(const dspfe_mfcc_params* q, const int16_t* pcm, long long total_samples,
+extern "C" long long emu_mfcc_delta(const dspfe_mfcc_params* q, const void* pcm, int in_f32, long long total_samples,
                                     const long long* offsets, const int* trim, int n_utt, float* out, long long max_rows,
                                     long long* frame_off_out, char* errbuf, int errcap) {
     MfccConfig c;
@@ -33,7 +34,7 @@ extern "C" long long emu_mfcc_delta(const dspfe_mfcc_params* q, const int16_t* p
     if (q->window) c.window.assign(q->window, q->window + q->frame_len);
     MfccParams p; std::memset(&p, 0, sizeof(p));
     std::string err;
-    std::vector<float> blob = build_mfcc_tables(c, p, err);
+    std::vector<float> blob = build_mfcc_tables(c, p, err, in_f32 != 0);
     if (!err.empty()) { std::snprintf(errbuf, errcap, "%s", err.c_str()); return -2; }
     // host mirror of prep_kernel
     std::vector<int64_t> seg_start(n_utt + 1), frame_off(n_utt + 1);
@@ -62,7 +63,7 @@ extern "C" long long emu_mfcc_delta(const dspfe_mfcc_params* q, const int16_t* p
     p.pcm = pcm; p.total_samples = total_samples; p.seg_start = seg_start.data(); p.seg_len = seg_len.data();
     p.frame_off = frame_off.data(); p.tiles = tiles.data(); p.ntiles = &ntiles; p.tables = blob.data(); p.out = out;
     std::vector<unsigned char> smem(p.sm_total + 64);
-    Args A{p, !c.window.empty(), &smem};
+    Args A{p, !c.window.empty(), in_f32 != 0, &smem};
     for (int b = 0; b < ntiles + 1; ++b) {   // +1: exercises the early-exit path of surplus CTAs
         std::memset(smem.data(), 0xCD, smem.size());   // poison: uninitialised shared memory shows up as garbage
         if (!emu::run_cta(b, kMfccThreads, body, &A)) { std::snprintf(errbuf, errcap, "deadlock in CTA %d", b); return -3; }

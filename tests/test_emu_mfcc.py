@@ -64,6 +64,17 @@ def test_trim_matches_python_slice():
         assert_mfcc_close(out[fo[u]:fo[u + 1]], O.mfcc_delta39(x, 2), what=f"trim {u}")
 
 
+def test_float32_input_path():
+    """float32 samples (a caller-scaled signal, model.py:62-63) through the same kernel body."""
+    lengths = [8001, 399, 3, 12345]
+    pcm, off = synth.synth_batch(lengths, seed0=920)
+    x = pcm.astype(np.float32) / np.float32(517.25)
+    out, fo = emu.mfcc_delta(x, off, delta_n=2, seg_frames=32)
+    for u, n in enumerate(lengths):
+        ref = O.mfcc_delta39(x[off[u]:off[u + 1]].astype(np.float64), 2)
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], ref, what=f"f32 utt {u}")
+
+
 def test_unsupported_configs_are_rejected():
     x = np.zeros(1000, dtype=np.int16)
     for kw in (dict(nfft=1536), dict(frame_len=600), dict(frame_step=161), dict(nfilt=41), dict(numcep=17),
