@@ -63,7 +63,8 @@ __device__ double np_sum_any(const double* a, int n, bool absval, bool sq) {
 __global__ void row_amp_kernel(const double* frames, int64_t nrows, int len, int use_sq, double* out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
-    out[r] = np_sum_any(frames + r * len, len, true, use_sq != 0) / (double)len;
+    const double s = np_sum_any(frames + r * len, len, true, use_sq == 1);
+    out[r] = use_sq == 2 ? s : s / (double)len;
 }
 
 // get_zcr (endpoint.py:182-198)

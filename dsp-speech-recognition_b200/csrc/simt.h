@@ -112,6 +112,18 @@ DEVFN int __float_as_int_compat(float f) { return __float_as_int(f); }
 DEVFN float __int_as_float_compat(int i) { return __int_as_float(i); }
 #endif
 
+// float64 xor-shuffle over the full warp (two 32-bit shuffles)
+DEVFN double shfl32_xor_f64(double v, int m) {
+    const int src = (simt::tid() & 31) ^ m;
+#ifdef DSPFE_EMU
+    int w[2]; std::memcpy(w, &v, 8);
+    w[0] = simt::shfl32_i(w[0], src); w[1] = simt::shfl32_i(w[1], src);
+    double r; std::memcpy(&r, w, 8); return r;
+#else
+    return __hiloint2double(simt::shfl32_i(__double2hiint(v), src), simt::shfl32_i(__double2loint(v), src));
+#endif
+}
+
 // scalar-broadcast forms (the scalar folds into the packed instruction's .F32 operand)
 DEVFN float2 f2muls(float2 a, float s) { return f2mul(a, make_float2(s, s)); }
 DEVFN float2 f2fmas(float2 a, float s, float2 c) { return f2fma(a, make_float2(s, s), c); }

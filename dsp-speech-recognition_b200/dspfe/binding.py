@@ -404,12 +404,12 @@ def preemphasis_f64(x, coeff):
     return y.cpu().numpy()
 
 
-def row_amplitude_f64(frames, use_sq=False):
+def row_amplitude_f64(frames, use_sq=False):   # use_sq: False mean|x|, True mean x^2, 2 plain sum|x|
     torch, dev = _cuda()
     L = lib(); _bind_helpers(L)
     f = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64)).to(dev)
     out = torch.empty(f.shape[0], dtype=torch.float64, device=dev)
-    _check(L.dspfe_row_amplitude_f64(f.data_ptr(), f.shape[0], f.shape[1], int(bool(use_sq)), out.data_ptr(), _stream(torch, dev)))
+    _check(L.dspfe_row_amplitude_f64(f.data_ptr(), f.shape[0], f.shape[1], (2 if use_sq == 2 else int(bool(use_sq))), out.data_ptr(), _stream(torch, dev)))
     return out.cpu().numpy()
 
 
@@ -429,3 +429,205 @@ def delta_f32(feat, N):
     out = torch.empty_like(f)
     _check(L.dspfe_delta_f32(f.data_ptr(), f.shape[0], f.shape[1], int(N), out.data_ptr(), _stream(torch, dev)))
     return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ pitch
+class _PitchParams(ctypes.Structure):
+    _fields_ = [("samplerate", ctypes.c_int32), ("dst_rate", ctypes.c_int32), ("frame_len", ctypes.c_int32),
+                ("frame_step", ctypes.c_int32), ("method", ctypes.c_int32), ("center_clip", ctypes.c_int32),
+                ("row_len", ctypes.c_int32), ("reserved", ctypes.c_int32), ("band_lo", ctypes.c_double),
+                ("band_hi", ctypes.c_double), ("preemph", ctypes.c_double)]
+
+
+def _bind_pitch(L):
+    if getattr(L, "_p_bound", False):
+        return
+    vp, i64, i32, f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+    L.dspfe_pitch_params_default.argtypes = [ctypes.POINTER(_PitchParams), i32]
+    L.dspfe_pitch_params_default.restype = None
+    L.dspfe_pitch_create.argtypes = [ctypes.POINTER(_PitchParams), ctypes.POINTER(vp)]
+    L.dspfe_pitch_destroy.argtypes = [vp]
+    L.dspfe_pitch_destroy.restype = None
+    L.dspfe_pitch_row_len.argtypes = [vp]
+    L.dspfe_pitch_num_frames.argtypes = [vp, i64]
+    L.dspfe_pitch_num_frames.restype = i64
+    L.dspfe_pitch_frames_bound.argtypes = [vp, i64, i64]
+    L.dspfe_pitch_frames_bound.restype = i64
+    L.dspfe_pitch.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, vp, vp, vp, vp, i64, vp]
+    L.dspfe_pitch_host.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.dspfe_center_clip_f32.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.dspfe_track_rows_f32.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp]
+    L.dspfe_robust_max_pitch_host.argtypes = [vp, i32, i32, vp]
+    L.dspfe_smooth_subsequence_host.argtypes = [vp, i32, i32, f64, vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.dspfe_sub_endpoint_host.argtypes = [vp, i32, ctypes.POINTER(i32)]
+    L.dspfe_pitch_feature_tail_host.argtypes = [vp, vp, i32, vp]
+    L.dspfe_poly_lead_host.argtypes = [vp, i32, i32, ctypes.POINTER(f64)]
+    L._p_bound = True
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class PitchPlan:
+    """dspfe_pitch_plan: batched pitch_detect (method 0) / pitch_detect_sr (method 1) / pitch_feature
+    (reference pitch.py:83, :96, :26)."""
+
+    def __init__(self, method=0, samplerate=16000, dst_rate=10000, frame_len=512, frame_step=100, center_clip=True,
+                 row_len=0, band_lo=50.0, band_hi=None, preemph=0.0):
+        L = lib(); _bind_pitch(L)
+        p = _PitchParams()
+        L.dspfe_pitch_params_default(ctypes.byref(p), int(method))
+        p.samplerate, p.dst_rate, p.frame_len, p.frame_step = int(samplerate), int(dst_rate), int(frame_len), int(frame_step)
+        p.center_clip, p.row_len, p.band_lo, p.preemph = int(bool(center_clip)), int(row_len), float(band_lo), float(preemph)
+        if band_hi is not None:
+            p.band_hi = float(band_hi)
+        self._p = p
+        h = ctypes.c_void_p()
+        _check(L.dspfe_pitch_create(ctypes.byref(p), ctypes.byref(h)))
+        self._h = h
+        self.method = int(method)
+        self.row_len = int(L.dspfe_pitch_row_len(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dspfe_pitch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def frames_bound(self, total_samples, n_utt):
+        return int(lib().dspfe_pitch_frames_bound(self._h, int(total_samples), int(n_utt)))
+
+    def num_frames(self, n_samples):
+        return int(lib().dspfe_pitch_num_frames(self._h, int(n_samples)))
+
+    def detect(self, pcm, offsets, trim=None, want_feat=False, want_rows=False, want_track=True, out=None, stream=None):
+        """Device path: pcm int16 or float32 CUDA tensor, offsets int64 CUDA tensor [U+1], optional trim int32 [U,2].
+        Returns a dict of CUDA tensors: pitch float64 [bound], lag int32 [bound], frame_off int64 [U+1]
+        (+ feat float64 [U,5], rows float32 [bound,row_len]); entries beyond frame_off[-1] are untouched.
+        `out` may carry preallocated tensors under the same keys."""
+        import torch
+        assert pcm.is_cuda and pcm.dtype in (torch.int16, torch.float32) and pcm.is_contiguous()
+        assert offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()
+        n_utt = offsets.numel() - 1
+        fb = self.frames_bound(pcm.numel(), n_utt)
+        dev = pcm.device
+        o = dict(out or {})
+        if want_track and o.get("pitch") is None:
+            o["pitch"] = torch.empty(fb, dtype=torch.float64, device=dev)
+        if want_track and o.get("lag") is None:
+            o["lag"] = torch.empty(fb, dtype=torch.int32, device=dev)
+        if o.get("frame_off") is None:
+            o["frame_off"] = torch.empty(n_utt + 1, dtype=torch.int64, device=dev)
+        if want_feat and o.get("feat") is None:
+            o["feat"] = torch.empty((n_utt, 5), dtype=torch.float64, device=dev)
+        if want_rows and o.get("rows") is None:
+            o["rows"] = torch.empty((fb, self.row_len), dtype=torch.float32, device=dev)
+        tp = None
+        if trim is not None:
+            assert trim.is_cuda and trim.dtype == torch.int32 and trim.is_contiguous() and trim.shape == (n_utt, 2)
+            tp = trim.data_ptr()
+        ptr = lambda k: o[k].data_ptr() if o.get(k) is not None else None
+        st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        _check(lib().dspfe_pitch(self._h, pcm.data_ptr(), int(pcm.dtype == torch.float32), pcm.numel(), offsets.data_ptr(), tp, n_utt,
+                                 ptr("pitch"), ptr("lag"), ptr("feat") if want_feat else None, ptr("rows") if want_rows else None,
+                                 ptr("frame_off"), fb, ctypes.c_void_p(st)))
+        return o
+
+    def detect_host(self, pcm, offsets, trim=None, want_feat=False):
+        """Host path: NumPy int16 / float32 pcm + int64 offsets (+ int32 trim [U,2]) ->
+        (pitch float64 [F], lag int32 [F], frame_off int64 [U+1][, feat float64 [U,5]])."""
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.dtype != np.int16:
+            pcm = pcm.astype(np.float32, copy=False)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_utt = len(offsets) - 1
+        lens = np.diff(offsets)
+        if trim is not None:
+            trim = np.ascontiguousarray(trim, dtype=np.int32).reshape(n_utt, 2)
+            l = np.clip(trim[:, 0].astype(np.int64), 0, lens); r = np.clip(trim[:, 1].astype(np.int64), 0, lens)
+            lens = np.maximum(r - l, 0)
+        nf = int(sum(self.num_frames(int(n)) for n in lens))
+        pitch = np.zeros(nf, dtype=np.float64)
+        lag = np.zeros(nf, dtype=np.int32)
+        fo = np.zeros(n_utt + 1, dtype=np.int64)
+        feat = np.zeros((n_utt, 5), dtype=np.float64) if want_feat else None
+        _check(lib().dspfe_pitch_host(self._h, _np_ptr(pcm), int(pcm.dtype == np.float32), _np_ptr(offsets), _np_ptr(trim), n_utt,
+                                      _np_ptr(pitch), _np_ptr(lag), _np_ptr(feat), _np_ptr(fo)))
+        return (pitch, lag, fo, feat) if want_feat else (pitch, lag, fo)
+
+
+def center_clip_f32(rows, binary=True):
+    """center_clip (reference pitch.py:145) on [n_rows, len<=512] (or one 1-D frame), on the device."""
+    torch, dev = _cuda()
+    L = lib(); _bind_pitch(L)
+    a = np.ascontiguousarray(rows, dtype=np.float32)
+    one = a.ndim == 1
+    a2 = a.reshape(1, -1) if one else a
+    x = torch.from_numpy(a2).to(dev)
+    out = torch.empty_like(x)
+    _check(L.dspfe_center_clip_f32(x.data_ptr(), x.shape[0], x.shape[1], int(bool(binary)), out.data_ptr(), _stream(torch, dev)))
+    r = out.cpu().numpy()
+    return r[0] if one else r
+
+
+def smooth_rows_f32(rows, mode=0, want_score=False, want_lag=False, do_smooth=True):
+    """smooth(g, 2) (reference pitch.py:157) on [n_rows, row_len<=512] float32 on the device; optionally the
+    peak_score rows [n_rows, 80] (mode 0) and lag = 20 + first argmax.  Returns (smoothed, score|None, lag|None).
+    do_smooth=False scores the rows as given (peak_score alone)."""
+    torch, dev = _cuda()
+    L = lib(); _bind_pitch(L)
+    x = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(dev)
+    assert x.dim() == 2
+    sm = torch.empty_like(x)
+    sc = torch.empty((x.shape[0], 80), dtype=torch.int32, device=dev) if want_score else None
+    lg = torch.empty(x.shape[0], dtype=torch.int32, device=dev) if want_lag else None
+    _check(L.dspfe_track_rows_f32(x.data_ptr(), x.shape[0], x.shape[1], int(mode), int(bool(do_smooth)), sm.data_ptr(),
+                                   None if sc is None else sc.data_ptr(), None if lg is None else lg.data_ptr(), _stream(torch, dev)))
+    return sm.cpu().numpy(), None if sc is None else sc.cpu().numpy(), None if lg is None else lg.cpu().numpy()
+
+
+def robust_max_pitch_host(lags, repair=True):
+    """max_pitch / robust_max_pitch (reference pitch.py:166, :191) on integer lags (bias already added)."""
+    L = lib(); _bind_pitch(L)
+    lags = np.ascontiguousarray(lags, dtype=np.int32)
+    out = np.zeros(len(lags), dtype=np.float64)
+    _check(L.dspfe_robust_max_pitch_host(_np_ptr(lags), len(lags), int(bool(repair)), _np_ptr(out)))
+    return out
+
+
+def smooth_subsequence_host(pitch, tor=3, thres=30.0):
+    """find_smooth_subsequence (reference pitch.py:245): returns (values list, (i0, j0))."""
+    L = lib(); _bind_pitch(L)
+    pitch = np.ascontiguousarray(pitch, dtype=np.float64)
+    seg = np.zeros(len(pitch), dtype=np.float64)
+    n, i0, j0 = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+    _check(L.dspfe_smooth_subsequence_host(_np_ptr(pitch), len(pitch), int(tor), float(thres), _np_ptr(seg), ctypes.byref(n),
+                                           ctypes.byref(i0), ctypes.byref(j0)))
+    return seg[: n.value], (i0.value, j0.value)
+
+
+def sub_endpoint_host(amp):
+    L = lib(); _bind_pitch(L)
+    amp = np.ascontiguousarray(amp, dtype=np.float64)
+    p = ctypes.c_int32(0)
+    _check(L.dspfe_sub_endpoint_host(_np_ptr(amp), len(amp), ctypes.byref(p)))
+    return p.value
+
+
+def pitch_feature_tail_host(pitch, amp):
+    L = lib(); _bind_pitch(L)
+    pitch = np.ascontiguousarray(pitch, dtype=np.float64)
+    amp = np.ascontiguousarray(amp, dtype=np.float64)
+    out = np.zeros(5, dtype=np.float64)
+    _check(L.dspfe_pitch_feature_tail_host(_np_ptr(pitch), _np_ptr(amp), len(pitch), _np_ptr(out)))
+    return out
+
+
+def poly_lead_host(seq, deg):
+    L = lib(); _bind_pitch(L)
+    seq = np.ascontiguousarray(seq, dtype=np.float64)
+    c = ctypes.c_double(0.0)
+    _check(L.dspfe_poly_lead_host(_np_ptr(seq), len(seq), int(deg), ctypes.byref(c)))
+    return c.value

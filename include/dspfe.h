@@ -176,6 +176,72 @@ int dspfe_zcr_rule_host(const dspfe_endpoint_params* p, const double* zcr, int32
                         int32_t right, int32_t* out_jk);
 
 /* ------------------------------------------------------------------------------------------------
+ * Pitch: cepstrum pitch (features.pitch_detect, pitch.py:83-94), autocorrelation pitch (pitch_detect_sr,
+ * pitch.py:96-110) and the five SVM inputs of pitch_model.py (pitch_feature, pitch.py:26-47) for every utterance
+ * of a packed ragged batch.  Per utterance the kernels replay: downsampling (preprocess.py:21, sample picking) ->
+ * to_frames (sigproc.py:11) -> center_clip (pitch.py:145) -> window band-pass (sigproc.py:22) -> cepstrum
+ * (pitch.py:135) or autocorrelation scores (pitch.py:112, sigproc.py:48) -> smooth (pitch.py:157) -> peak_score
+ * (pitch.py:227) -> robust_max_pitch (pitch.py:191) [-> sub_endpoint_detect (:64), find_smooth_subsequence (:245),
+ * slope/quad_params/peakshift (:49-62)].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dspfe_pitch_plan dspfe_pitch_plan;
+
+typedef struct {
+    int32_t samplerate;      /* rate of the packed samples, 16000 */
+    int32_t dst_rate;        /* 10000: rate the pitch functions decimate to (pitch.py:84,100) */
+    int32_t frame_len;       /* int(dst_rate*winlen): 512 (pitch_detect), or 300 for pitch_detect_sr as model.py:92 calls it */
+    int32_t frame_step;      /* int(step*dst_rate): 100 */
+    int32_t method;          /* 0 cepstrum (pitch_detect), 1 autocorrelation (pitch_detect_sr) */
+    int32_t center_clip;     /* 1: center_clip(frame, False) before the band-pass (pitch.py:88); 0 for the per-frame taps */
+    int32_t row_len;         /* cepstrum columns kept per frame; 0 = 200 (all peak_score can reach), 512 for the full-row tap */
+    int32_t reserved;
+    double band_lo, band_hi; /* band-pass edges in Hz: 50..1000 (pitch.py:137) / 50..900 (pitch.py:124) */
+    double preemph;          /* pre-emphasis over the whole utterance before trimming (pitch_model.py:39-41); 0 = none */
+} dspfe_pitch_params;
+
+void dspfe_pitch_params_default(dspfe_pitch_params* p, int32_t method);
+int dspfe_pitch_create(const dspfe_pitch_params* p, dspfe_pitch_plan** plan);
+void dspfe_pitch_destroy(dspfe_pitch_plan* plan);
+int32_t dspfe_pitch_row_len(const dspfe_pitch_plan* plan);
+/* pitch frames of one utterance of n_samples (after decimation and framing) / upper bound for a whole batch */
+int64_t dspfe_pitch_num_frames(const dspfe_pitch_plan* plan, int64_t n_samples);
+int64_t dspfe_pitch_frames_bound(const dspfe_pitch_plan* plan, int64_t total_samples, int64_t n_utt);
+
+/* Device path, asynchronous on `stream`.  sample_dtype: 0 = int16, 1 = float32 samples.  d_trim as for
+ * dspfe_mfcc_delta (pitch runs on sig[left:right], pitch_model.py:41).  Outputs (each may be NULL):
+ *   d_pitch [frames] float64 Hz (robust_max_pitch), d_lag [frames] int32 = 20 + argmax (before the octave repair),
+ *   d_feat [n_utt,5] float64 = pitch_feature (cepstrum method only; NaN x5 where a half has < 3 usable frames),
+ *   d_rows [frames,row_len] float32 = the per-frame cepstrum / autocorrelation rows before smoothing,
+ *   d_frame_off [n_utt+1] int64.  max_frames = capacity in frames, >= dspfe_pitch_frames_bound(). */
+int dspfe_pitch(dspfe_pitch_plan* plan, const void* d_pcm, int32_t sample_dtype, int64_t total_samples, const int64_t* d_offsets,
+                const int32_t* d_trim, int32_t n_utt, double* d_pitch, int32_t* d_lag, double* d_feat, float* d_rows,
+                int64_t* d_frame_off, int64_t max_frames, void* stream);
+
+/* Host-buffer path: H2D, kernels, D2H; returns when the results are in the host arrays (h_trim optional). */
+int dspfe_pitch_host(dspfe_pitch_plan* plan, const void* h_pcm, int32_t sample_dtype, const int64_t* h_offsets, const int32_t* h_trim,
+                     int32_t n_utt, double* h_pitch, int32_t* h_lag, double* h_feat, int64_t* h_frame_off);
+
+/* Taps on caller-supplied device arrays.
+ * center_clip (pitch.py:145 == endpoint.py:20): rows of len <= 512 float32; binary != 0 gives -1/0/1. */
+int dspfe_center_clip_f32(const float* d_in, int64_t n_rows, int32_t len, int32_t binary, float* d_out, void* stream);
+/* K4b/K5b on caller rows [n_rows,row_len] (row_len <= 512): smooth(g, 2) (pitch.py:157) when do_smooth, then per row either
+ * peak_score (pitch.py:227; mode 0, d_score [n_rows,80]) and its first argmax, or the plain first argmax (mode 1);
+ * d_lag = 20 + argmax.  d_smoothed receives the rows that were scored.  Outputs may be NULL. */
+int dspfe_track_rows_f32(const float* d_rows, int64_t n_rows, int32_t row_len, int32_t mode, int32_t do_smooth, float* d_smoothed,
+                         int32_t* d_score, int32_t* d_lag, void* stream);
+
+/* Host-only list helpers, the reference's small sequential functions (same C++ as the device kernels K4b/K6):
+ * max_pitch / robust_max_pitch on lags (pitch.py:166,191; repair = 0/1), find_smooth_subsequence (pitch.py:245),
+ * sub_endpoint_detect on per-frame sum|x| (pitch.py:64), the pitch_feature tail (pitch.py:33-46) and the leading
+ * polyfit coefficient of slope / quad_params (pitch.py:49-57; deg 1 or 2). */
+int dspfe_robust_max_pitch_host(const int32_t* lag, int32_t n, int32_t repair, double* pitch);
+int dspfe_smooth_subsequence_host(const double* pitch, int32_t n, int32_t tor, double thres, double* seg, int32_t* seg_len,
+                                  int32_t* i0, int32_t* j0);
+int dspfe_sub_endpoint_host(const double* amp, int32_t n_frames, int32_t* p);
+int dspfe_pitch_feature_tail_host(const double* pitch, const double* amp, int32_t n_frames, double* out5);
+int dspfe_poly_lead_host(const double* seq, int32_t n, int32_t deg, double* coef);
+
+/* ------------------------------------------------------------------------------------------------
  * Helpers: the reference's small array functions as device kernels (not on the throughput path; the
  * fused kernels never materialise frames).  All pointers are device memory.
  * ---------------------------------------------------------------------------------------------- */
@@ -184,7 +250,8 @@ int dspfe_frames_f64(const double* d_sig, int64_t n, int32_t frame_len, int32_t 
                      double* d_out, int64_t n_frames, void* stream);
 /* preemphasis (sigproc.py:178 == preprocess.py:11) */
 int dspfe_preemphasis_f64(const double* d_x, int64_t n, double coeff, double* d_y, void* stream);
-/* get_amplitude(frames, 'square', use_sq) (endpoint.py:109): per-row mean |x| or x^2 in NumPy's summation order */
+/* get_amplitude(frames, 'square', use_sq) (endpoint.py:109): per-row mean |x| (use_sq 0) or x^2 (1) in NumPy's summation
+ * order; use_sq 2 = plain sum |x| per row (sub_endpoint_detect, pitch.py:65) */
 int dspfe_row_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t use_sq, double* d_out, void* stream);
 /* get_zcr(frames) (endpoint.py:182) */
 int dspfe_row_zcr_f64(const double* d_frames, int64_t n_rows, int32_t len, int64_t* d_out, void* stream);

@@ -36,6 +36,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(build())
         _lib.emu_mfcc_delta.restype = ctypes.c_longlong
+        _lib.emu_pitch.restype = ctypes.c_longlong
     return _lib
 
 
@@ -70,3 +71,43 @@ def mfcc_delta(pcm, offsets, trim=None, **kw):
     if r < 0:
         raise RuntimeError(f"emulator: {err.value.decode()} ({r})")
     return out[:r], fo
+
+
+class PitchParams(ctypes.Structure):
+    _fields_ = [("samplerate", ctypes.c_int32), ("dst_rate", ctypes.c_int32), ("frame_len", ctypes.c_int32),
+                ("frame_step", ctypes.c_int32), ("method", ctypes.c_int32), ("center_clip", ctypes.c_int32),
+                ("row_len", ctypes.c_int32), ("reserved", ctypes.c_int32), ("band_lo", ctypes.c_double),
+                ("band_hi", ctypes.c_double), ("preemph", ctypes.c_double)]
+
+
+def pitch(pcm, offsets, trim=None, method=0, samplerate=16000, dst_rate=10000, frame_len=512, frame_step=100, center_clip=1,
+          row_len=0, band_lo=50.0, band_hi=None, preemph=0.0, want_feat=False, want_rows=False):
+    """K4/K5/K6 bodies on the emulator.  Returns dict(pitch, lag, frame_off[, feat, rows, smoothed, score])."""
+    q = PitchParams(samplerate, dst_rate, frame_len, frame_step, method, center_clip, row_len, 0, band_lo,
+                    band_hi if band_hi is not None else (1000.0 if method == 0 else 900.0), preemph)
+    f32 = np.asarray(pcm).dtype.kind == "f"
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32 if f32 else np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    cap = int(len(pcm) // frame_step + 3 * n + 8)
+    rl = (row_len or 200) if method == 0 else 180
+    out = dict(pitch=np.full(cap, np.nan), lag=np.zeros(cap, dtype=np.int32), frame_off=np.zeros(n + 1, dtype=np.int64))
+    vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    feat = np.full((n, 5), np.nan) if want_feat else None
+    rows = np.full((cap, rl), np.nan, dtype=np.float32) if want_rows else None
+    sm = np.full((cap, rl), np.nan, dtype=np.float32) if want_rows else None
+    sc = np.zeros((cap, 80), dtype=np.int32) if (want_rows and method == 0) else None
+    tp = None if trim is None else np.ascontiguousarray(trim, dtype=np.int32)
+    err = ctypes.create_string_buffer(256)
+    r = lib().emu_pitch(ctypes.byref(q), vp(pcm), int(f32), vp(offsets), vp(tp), n, vp(out["pitch"]), vp(out["lag"]), vp(feat),
+                        vp(rows), vp(sm), vp(sc), vp(out["frame_off"]), ctypes.c_longlong(cap), err, 256)
+    if r < 0:
+        raise RuntimeError(f"emulator: {err.value.decode()} ({r})")
+    out["pitch"], out["lag"] = out["pitch"][:r], out["lag"][:r]
+    if want_feat:
+        out["feat"] = feat
+    if want_rows:
+        out["rows"], out["smoothed"] = rows[:r], sm[:r]
+        if sc is not None:
+            out["score"] = sc[:r]
+    return out

@@ -1,0 +1,81 @@
+// Emulator entry point for K4/K5/K6 (pitch).  TEST INFRASTRUCTURE ONLY.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../dsp-speech-recognition_b200/csrc/dspfe_types.h"
+#include "../../dsp-speech-recognition_b200/csrc/pitch_kernel.cuh"
+#include "../../dsp-speech-recognition_b200/csrc/pitch_tables.h"
+#include "../../include/dspfe.h"
+
+namespace emu { bool run_cta(int bid, int nthreads, void (*body)(void*), void* arg); }
+using namespace dspfe;
+
+namespace {
+struct Args { PitchParams p; std::vector<unsigned char>* smem; int64_t total_frames; };
+void frame_body(void* a) {
+    Args* A = (Args*)a;
+    const int w = simt::tid() >> 5;
+    const int64_t g = (int64_t)simt::bid() * kPitchWarps + w;
+    if (g >= A->total_frames) return;
+    float2* bufa = reinterpret_cast<float2*>(A->smem->data()) + w * 2 * kPitchFft;
+    pitch_frame_warp(A->p, g, bufa, bufa + kPitchFft);
+}
+void track_body(void* a) {
+    Args* A = (Args*)a;
+    float* chunk = reinterpret_cast<float*>(A->smem->data());
+    int* sc = reinterpret_cast<int*>(chunk + kTrackChunk * A->p.row_len);
+    pitch_track_cta(A->p, chunk, sc);
+}
+}  // namespace
+
+// Same contract as dspfe_pitch but host pointers and synchronous.  Returns total frames, <0 on error.
+extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int in_f32, const long long* offsets, const int* trim,
+                               int n_utt, double* pitch, int* lag, double* feat, float* rows, float* rows_smoothed, int* score,
+                               long long* frame_off_out, long long max_frames, char* errbuf, int errcap) {
+    PitchParams p;
+    std::vector<float2> tw, H;
+    std::string err;
+    if (build_pitch_tables(*q, p, tw, H, err)) { std::snprintf(errbuf, errcap, "%s", err.c_str()); return -2; }
+    std::vector<int64_t> seg_start(n_utt + 1), frame_off(n_utt + 1);
+    std::vector<int32_t> seg_len(n_utt + 1), ds_len(n_utt + 1);
+    int64_t fo = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        int64_t a = offsets[u], len = offsets[u + 1] - offsets[u];
+        if (trim) {
+            int64_t l = trim[2 * u], r = trim[2 * u + 1];
+            if (l < 0) l = 0; if (r < 0) r = 0;
+            if (l > len) l = len; if (r > len) r = len;
+            a += l; len = r > l ? r - l : 0;
+        }
+        seg_start[u] = a; seg_len[u] = (int32_t)len;
+        ds_len[u] = (int32_t)ds_length(len, p.ds_idx, p.ds_in, p.ds_out);
+        frame_off[u] = fo;
+        fo += num_frames(ds_len[u], p.frame_len, p.frame_step);
+    }
+    frame_off[n_utt] = fo;
+    if (fo > max_frames) { std::snprintf(errbuf, errcap, "outputs too small"); return -1; }
+    if (frame_off_out) std::memcpy(frame_off_out, frame_off.data(), (n_utt + 1) * sizeof(int64_t));
+    std::vector<float> rows_own; std::vector<double> amp(fo), pitch_own(fo), scratch(3 * fo); std::vector<int32_t> lag_own(fo);
+    if (!rows) { rows_own.resize((size_t)fo * p.row_len); rows = rows_own.data(); }
+    p.pcm = pcm; p.in_f32 = in_f32; p.offsets = (const int64_t*)offsets; p.trim = trim; p.n_utt = n_utt;
+    p.tw = tw.data(); p.H = H.data(); p.frame_off = frame_off.data(); p.seg_start = seg_start.data(); p.seg_len = seg_len.data();
+    p.ds_len = ds_len.data(); p.rows = rows; p.rows_out = rows_smoothed; p.score = score; p.frame_amp = amp.data();
+    p.pitch = pitch ? pitch : pitch_own.data(); p.lag = lag ? lag : lag_own.data(); p.feat = feat; p.scratch = scratch.data();
+    p.max_frames = fo;
+    std::vector<unsigned char> smem(kPitchWarps * 2 * kPitchFft * sizeof(float2) + 64);
+    Args A{p, &smem, fo};
+    for (int64_t b = 0; b * kPitchWarps < fo + kPitchWarps; ++b) {
+        std::memset(smem.data(), 0xCD, smem.size());
+        if (!emu::run_cta((int)b, 32 * kPitchWarps, frame_body, &A)) { std::snprintf(errbuf, errcap, "deadlock in frame CTA %lld", (long long)b); return -3; }
+    }
+    std::vector<unsigned char> smem2(kTrackChunk * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + 64);
+    Args B{p, &smem2, fo};
+    for (int u = 0; u < n_utt; ++u) {
+        std::memset(smem2.data(), 0xCD, smem2.size());
+        if (!emu::run_cta(u, kTrackThreads, track_body, &B)) { std::snprintf(errbuf, errcap, "deadlock in track CTA %d", u); return -3; }
+    }
+    if (feat) for (int u = 0; u < n_utt; ++u) pitch_feature_thread(p, u);
+    return fo;
+}

@@ -120,3 +120,37 @@ def test_sample_index_truncation_quirk():
     l2, r2 = O.zcr_rule([np.int64(0)] * F, sep[0][0], sep[-1][1])
     assert (l, r) == (int(l2 * 0.01 * 16000), int(r2 * 0.01 * 16000))
     assert any(int(k * 0.01 * 16000) != 160 * k for k in range(F))
+
+
+def test_pitch_list_helpers_against_oracle():
+    rng = np.random.default_rng(11)
+    for t in range(200):
+        F = int(rng.integers(1, 300))
+        lags = rng.integers(20, 100, size=F)
+        if t % 2:   # realistic tracks: a slowly moving lag with octave errors
+            base = np.clip(60 + np.cumsum(rng.integers(-2, 3, size=F)), 25, 95)
+            lags = np.where(rng.random(F) < 0.15, np.minimum(base * 2, 99), base)
+        scores = np.zeros((F, 80), dtype=int)
+        scores[np.arange(F), lags - 20] = 5
+        want = O.robust_max_pitch(scores)
+        got = dspfe.robust_max_pitch_host(lags, repair=True)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(dspfe.robust_max_pitch_host(lags, repair=False), O.max_pitch(scores))
+        seg, idx = O.find_smooth_subsequence(want, bias=0)
+        gseg, gidx = dspfe.smooth_subsequence_host(want)
+        np.testing.assert_array_equal(gseg, seg)
+        assert gidx == idx
+        amp = rng.random(F) * 1000
+        if t % 3 == 0:
+            amp = np.round(amp / 100) * 100   # ties
+        assert dspfe.sub_endpoint_host(amp) == O.sub_endpoint_detect([[a] for a in amp])
+        if len(seg) >= 3:
+            np.testing.assert_allclose(dspfe.poly_lead_host(seg, 1), O.slope(seg), rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(dspfe.poly_lead_host(seg, 2), O.quad_params(seg), rtol=1e-8, atol=1e-12)
+
+
+def test_pitch_frame_counts():
+    """decimated length ((S-1)*5-1)//8+2 and the 512/100 framing (SURVEY §8 C3) without a device: the plan
+    constructor needs CUDA, so the same formulas are checked through the oracle's index list."""
+    for S in (1, 2, 3, 8, 9, 100, 8000, 32000, 80000):
+        assert len(O.downsample_indices(S, 16000, 10000)) == ((S - 1) * 5 - 1) // 8 + 2 if S > 1 else 1

@@ -1,0 +1,192 @@
+"""GPU parity tests of the pitch kernels (K4a/K4b/K5/K6) through the C ABI.
+
+Contract (BASELINE.json north_star): pitch-peak lags are exact except where a float32 near-tie moves
+an integer peak score; such frames are counted and bounded.  pitch_feature floats: 1e-6 relative on utterances whose
+lags are all exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LAG_MISMATCH_BUDGET = 0.01   # fraction of frames whose Hz value may differ from the float64 reference
+
+
+def pack(xs):
+    off = np.zeros(len(xs) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in xs], out=off[1:])
+    return np.concatenate(xs).astype(np.int16), off
+
+
+def test_golden_pitch_tracks_exact(golden):
+    import dspfe
+    g = golden("pitch")
+    names = ["u0", "u1", "u2", "u3"]
+    pcm, off = pack([g[f"{n}/x"] for n in names])
+    for method, key, kw in ((0, "pitch_cep", {}), (1, "pitch_sr", {}), (1, "pitch_sr300", dict(frame_len=300))):
+        pitch, lag, fo = dspfe.PitchPlan(method=method, **kw).detect_host(pcm, off)
+        for i, n in enumerate(names):
+            np.testing.assert_array_equal(pitch[fo[i]:fo[i + 1]], g[f"{n}/{key}"], err_msg=f"{n} {key}")
+
+
+def test_golden_pitch_feature_chain(golden):
+    """pitch_model.py:38-41 on the device: endpoints -> pre-emphasis over the whole signal -> slice -> pitch_feature."""
+    import torch
+    import dspfe
+    g = golden("pitch")
+    names = ["u0", "u1", "u2", "u3"]
+    pcm, off = pack([g[f"{n}/x"] for n in names])
+    dev = torch.device("cuda:0")
+    pcm_d, off_d = torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev)
+    lr = dspfe.EndpointPlan().detect(pcm_d, off_d)
+    np.testing.assert_array_equal(lr.cpu().numpy(), np.stack([g[f"{n}/lr"] for n in names]))
+    o = dspfe.PitchPlan(method=0, preemph=0.97).detect(pcm_d, off_d, trim=lr, want_feat=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(o["feat"].cpu().numpy(), g["pitch_feature"], rtol=1e-6, atol=1e-9)
+    # host-buffer path gives the same bits
+    _, _, _, feat = dspfe.PitchPlan(method=0, preemph=0.97).detect_host(pcm, off, trim=lr.cpu().numpy(), want_feat=True)
+    np.testing.assert_array_equal(feat, o["feat"].cpu().numpy())
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_ragged_batch_vs_oracle(method):
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    lengths = synth.ragged_lengths(24, seed=21, lo=8000, hi=40000)
+    lengths[:5] = [1, 700, 1000, 819, 8001]
+    pcm, off = synth.synth_batch(lengths, seed0=4200)
+    pitch, lag, fo = dspfe.PitchPlan(method=method).detect_host(pcm, off)
+    ref_fn = O.pitch_detect if method == 0 else O.pitch_detect_sr
+    bad = tot = 0
+    for u in range(len(lengths)):
+        want, _ = ref_fn(pcm[off[u]:off[u + 1]], 16000)
+        got = pitch[fo[u]:fo[u + 1]]
+        assert len(got) == len(want), u
+        bad += int(np.sum(got != np.asarray(want))); tot += len(want)
+    print(f"method {method}: {bad} of {tot} frames differ")
+    assert bad <= LAG_MISMATCH_BUDGET * tot
+
+
+def test_rows_tap_matches_reference_cepstrum_and_acr():
+    import torch
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    x = synth.synth_utterance(99, 24000)
+    dev = torch.device("cuda:0")
+    xd = torch.from_numpy(x).to(dev)
+    od = torch.tensor([0, len(x)], dtype=torch.int64, device=dev)
+    fr = O.to_frames(O.downsampling(x, 16000, 10000), 10000, 0.0512, 0.01)
+    cl = O.center_clip(fr, False)
+    o = dspfe.PitchPlan(method=0, row_len=512).detect(xd, od, want_rows=True)
+    torch.cuda.synchronize()
+    F = int(o["frame_off"][-1])
+    ce = O.pitch_detect_frame(cl, 10000)
+    assert F == len(ce)
+    assert np.max(np.abs(o["rows"][:F].cpu().numpy() - ce)) <= 1e-5 * np.max(np.abs(ce))
+    o = dspfe.PitchPlan(method=1).detect(xd, od, want_rows=True)
+    torch.cuda.synchronize()
+    sr = O.pitch_detect_frame_sr(cl, 10000)
+    assert np.max(np.abs(o["rows"][:F].cpu().numpy() - sr)) <= 2e-5 * np.max(np.abs(sr))
+
+
+def test_dropin_pitch_module():
+    """The reference-facing functions of features.pitch (same names, signatures and return types)."""
+    import features
+    from dspfe import synth
+    from oracle import ref_features as O
+    x = synth.synth_utterance(31, 20000)
+    l, r = features.basic_endpoint_detection(x, 16000)
+    sig = features.preemphasis(x, coeff=0.97)
+    feat = features.pitch_feature(sig[l:r], 16000)
+    want = O.pitch_feature(O.preemphasis(x, 0.97)[l:r], 16000)
+    assert isinstance(feat, tuple) and len(feat) == 5
+    np.testing.assert_allclose(feat, want, rtol=1e-6, atol=1e-9)
+    p, frames = features.pitch_detect(x, 16000)
+    wp, wf = O.pitch_detect(x, 16000)
+    assert isinstance(p, list) and p == wp
+    np.testing.assert_array_equal(frames, wf)
+    p, _ = features.pitch_detect_sr(x, 16000, winlen=0.03, step=0.01)     # as model.py:92 calls it
+    assert p == O.pitch_detect_sr(x, 16000, winlen=0.03, step=0.01)[0]
+    fr = wf[40]
+    np.testing.assert_array_equal(features.center_clip(fr), O.center_clip(fr))
+    cc = features.center_clip(fr, False)
+    np.testing.assert_allclose(cc, O.center_clip(fr, False), rtol=1e-6, atol=1e-3)
+    ce = features.pitch_detect_frame(cc, 10000, 'male')
+    wce = O.pitch_detect_frame(O.center_clip(fr, False), 10000)
+    assert ce.shape == (512,) and np.max(np.abs(ce - wce)) <= 1e-5 * np.max(np.abs(wce))
+    sr = features.pitch_detect_frame_sr(cc[:300], 10000)
+    wsr = O.pitch_detect_frame_sr(O.center_clip(fr, False)[:300], 10000)
+    assert isinstance(sr, list) and len(sr) == 180
+    assert np.max(np.abs(np.array(sr) - np.array(wsr))) <= 2e-5 * np.max(np.abs(wsr))
+    rows = O.pitch_detect_frame(O.center_clip(wf[30:50], False), 10000)
+    sm = features.smooth(rows.tolist())
+    wsm = np.asarray(O.smooth(rows))
+    assert isinstance(sm, list) and np.max(np.abs(np.asarray(sm) - wsm)) <= 1e-5 * np.max(np.abs(wsm))
+    assert features.peak_score(wsm[5]) == O.peak_score(wsm[5].astype(np.float32))
+    sc = [O.peak_score(c) for c in wsm]
+    assert features.robust_max_pitch(sc) == O.robust_max_pitch(sc)
+    assert features.max_pitch(sc) == O.max_pitch(sc)
+    assert features.greedy_max_pitch(sc) == O.greedy_max_pitch(sc)
+    seg, idx = features.find_smooth_subsequence(wp, bias=3)
+    wseg, widx = O.find_smooth_subsequence(wp, bias=3)
+    assert list(seg) == list(wseg) and idx == widx
+    np.testing.assert_allclose(features.slope(wseg), O.slope(wseg), rtol=1e-9)
+    np.testing.assert_allclose(features.quad_params(wseg), O.quad_params(wseg), rtol=1e-8)
+    assert features.peakshift(wseg, wp) == O.peakshift(wseg, wp)
+    assert features.sub_endpoint_detect(wf) == O.sub_endpoint_detect(wf)
+    import pickle
+    assert features.pitch.pickle is pickle    # pitch_model.py star-imports it from here (SURVEY A-12)
+
+
+def test_config3_full_size_properties():
+    """BASELINE config 3: cepstrum + autocorrelation pitch features on 4096 ragged utterances.  Size-independent
+    properties over the whole batch plus sampled oracle parity."""
+    import torch
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    dev = torch.device("cuda:0")
+    U = 4096
+    lengths = synth.ragged_lengths(U, seed=33)
+    pcm, off = synth.synth_batch_torch(lengths, seed0=31337, device=dev)
+    off_d = off.to(dev)
+    lr = dspfe.EndpointPlan().detect(pcm, off_d)
+    cep = dspfe.PitchPlan(method=0, preemph=0.97)
+    o = cep.detect(pcm, off_d, trim=lr, want_feat=True)
+    acr = dspfe.PitchPlan(method=1).detect(pcm, off_d)
+    torch.cuda.synchronize()
+    fo = o["frame_off"].cpu().numpy()
+    lr_h, off_h = lr.cpu().numpy(), off.numpy()
+    seg = np.minimum(lr_h[:, 1], lengths) - np.minimum(lr_h[:, 0], lengths)
+    np.testing.assert_array_equal(np.diff(fo), [cep.num_frames(int(n)) for n in seg])
+    lag = o["lag"][: fo[-1]].cpu().numpy()
+    pitch = o["pitch"][: fo[-1]].cpu().numpy()
+    assert lag.min() >= 20 and lag.max() <= 99
+    base = 1.0 / (0.0001 * lag)
+    assert np.all((pitch == base) | (pitch == 2 * base))       # robust_max_pitch only ever doubles
+    fo2 = acr["frame_off"].cpu().numpy()
+    lag2 = acr["lag"][: fo2[-1]].cpu().numpy()
+    assert lag2.min() >= 20 and lag2.max() <= 199
+    # idempotence / determinism: a second run gives the same bits; a sub-batch equals its slice of the whole
+    o2 = cep.detect(pcm, off_d, trim=lr, want_feat=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o2["pitch"][: fo[-1]], o["pitch"][: fo[-1]])
+    assert torch.equal(torch.nan_to_num(o2["feat"]), torch.nan_to_num(o["feat"]))
+    a, b = 1000, 1100
+    sub = cep.detect(pcm[off_h[a]:off_h[b]].clone(), (off_d[a:b + 1] - off_d[a]).contiguous(), trim=lr[a:b].contiguous(), want_feat=True)
+    torch.cuda.synchronize()
+    assert torch.equal(sub["pitch"][: fo[b] - fo[a]], o["pitch"][fo[a]:fo[b]])
+    # sampled oracle parity
+    feat = o["feat"].cpu().numpy()
+    bad = tot = 0
+    for u in (0, 1, 777, 2048, 4095):
+        x = pcm[off_h[u]:off_h[u + 1]].cpu().numpy()
+        l, r = int(lr_h[u, 0]), int(lr_h[u, 1])
+        sig = O.preemphasis(x, 0.97)[l:r]
+        want, _ = O.pitch_detect(sig, 16000)
+        got = pitch[fo[u]:fo[u + 1]]
+        bad += int(np.sum(got != np.asarray(want))); tot += len(want)
+        if np.array_equal(got, want) and len(want) > 40:
+            np.testing.assert_allclose(feat[u], O.pitch_feature(sig, 16000), rtol=1e-6, atol=1e-9)
+    assert bad <= LAG_MISMATCH_BUDGET * tot, f"{bad} of {tot}"
