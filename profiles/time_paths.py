@@ -1,0 +1,47 @@
+"""Per-path device timings (CUDA events) of the front-end on one GPU: endpoint, MFCC, cepstrum pitch (+feature),
+autocorrelation pitch on a ragged batch (BASELINE configs 3/4).  usage: python profiles/time_paths.py [U] [iters]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dsp-speech-recognition_b200"))
+import numpy as np
+import torch
+import dspfe
+from dspfe import synth
+
+U = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = torch.device("cuda:0")
+lengths = synth.ragged_lengths(U, seed=33)
+pcm, off = synth.synth_batch_torch(lengths, seed0=31337, device=dev)
+off_d = off.to(dev)
+audio_s = float(lengths.sum()) / 16000
+ep, mf = dspfe.EndpointPlan(), dspfe.MfccPlan(delta_n=2)
+cep, acr = dspfe.PitchPlan(method=0, preemph=0.97), dspfe.PitchPlan(method=1)
+lr = ep.detect(pcm, off_d)
+bufs = {}
+
+
+def timed(name, fn):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    print(json.dumps({"path": name, "ms": ms, "audio_s_per_s": audio_s / (ms * 1e-3), "utterances": U, "audio_s": audio_s}))
+
+
+out = torch.empty((mf.rows_bound(pcm.numel(), U), 39), dtype=torch.float32, device=dev)
+fo = torch.empty(U + 1, dtype=torch.int64, device=dev)
+timed("endpoint", lambda: ep.detect(pcm, off_d))
+timed("mfcc_delta (trimmed)", lambda: mf.mfcc_delta(pcm, off_d, trim=lr, out=out, frame_off=fo))
+o1 = cep.detect(pcm, off_d, trim=lr, want_feat=True)
+timed("pitch_cepstrum + pitch_feature", lambda: cep.detect(pcm, off_d, trim=lr, want_feat=True, out=o1))
+o2 = acr.detect(pcm, off_d)
+timed("pitch_autocorrelation", lambda: acr.detect(pcm, off_d, out=o2))
