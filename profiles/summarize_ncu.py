@@ -1,0 +1,53 @@
+"""Markdown summary of an `ncu --set full` report: per captured launch, the metrics DESIGN.md / bench.py quote.
+usage: python profiles/summarize_ncu.py gpurun_out/X.ncu-rep > profiles/rN_name.md"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs/thread"),
+    ("launch__shared_mem_per_block_dynamic", "dyn smem/CTA"), ("launch__occupancy_limit_shared_mem", "occ limit smem (CTAs)"),
+    ("launch__occupancy_limit_registers", "occ limit regs (CTAs)"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/shared throughput %"),
+    ("sm__inst_executed.avg.per_cycle_active", "IPC (warp inst/clk/SM)"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe active %"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA inst % of peak"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU inst % of peak"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU inst % of peak"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU inst % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared wavefronts"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared bank conflicts"),
+    ("smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio", "stall short scoreboard"),
+    ("smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "stall long scoreboard"),
+    ("smsp__average_warp_latency_issue_stalled_barrier.ratio", "stall barrier"),
+    ("smsp__average_warp_latency_issue_stalled_mio_throttle.ratio", "stall mio throttle"),
+    ("smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "stall math pipe throttle"),
+    ("smsp__average_warp_latency_issue_stalled_not_selected.ratio", "stall not selected"),
+    ("smsp__average_warp_latency_issue_stalled_wait.ratio", "stall wait"),
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu summary of `{rep.split('/')[-1]}` (`ncu --set full --clock-control none`; cold-cache, serialised launches)\n")
+    for r in rows[2:]:
+        print(f"## {r[col['Kernel Name']][:110]}\n")
+        print("| metric | value |\n|---|---|")
+        for k, name in KEYS:
+            if k in col and r[col[k]] != "":
+                print(f"| {name} (`{k}`) | {r[col[k]]} {units[col[k]]} |")
+        print()
+
+
+if __name__ == "__main__":
+    main()
