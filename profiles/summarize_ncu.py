@@ -40,7 +40,12 @@ def main():
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     print(f"# ncu summary of `{rep.split('/')[-1]}` (`ncu --set full --clock-control none`; cold-cache, serialised launches)\n")
+    seen = {}
     for r in rows[2:]:
+        name = r[col['Kernel Name']]
+        seen[name] = seen.get(name, 0) + 1
+        if seen[name] > 1 and "--all" not in sys.argv:
+            continue   # one launch per kernel name (the others repeat it)
         print(f"## {r[col['Kernel Name']][:110]}\n")
         print("| metric | value |\n|---|---|")
         for k, name in KEYS:
