@@ -1,0 +1,54 @@
+// Register-resident FFT building blocks on packed frame pairs (shared by K1 and the pitch kernels).
+// A cpx2 is one complex value for each of two frames: the .x halves belong to frame A, the .y halves to frame B,
+// so every butterfly is one FADD2 / FMUL2 / FFMA2 on sm_100a.
+#pragma once
+#include "simt.h"
+
+namespace dspfe {
+
+struct cpx2 { float2 re, im; };  // one complex value for each of the two frames of a pair
+
+DEVFN cpx2 cadd(cpx2 a, cpx2 b) { cpx2 r; r.re = f2add(a.re, b.re); r.im = f2add(a.im, b.im); return r; }
+DEVFN cpx2 csub(cpx2 a, cpx2 b) { cpx2 r; r.re = f2sub(a.re, b.re); r.im = f2sub(a.im, b.im); return r; }
+// a * (wr + i*wi), scalar twiddle shared by both frames
+DEVFN cpx2 cmuls(cpx2 a, float wr, float wi) {
+    cpx2 r;
+    r.re = f2fmas(a.re, wr, f2muls(a.im, -wi));
+    r.im = f2fmas(a.re, wi, f2muls(a.im, wr));
+    return r;
+}
+DEVFN cpx2 cmul_negi(cpx2 a) { cpx2 r; r.re = a.im; r.im = f2neg(a.re); return r; }  // a * (-i)
+
+// forward 4-point DFT (W4 = -i)
+DEVFN void dft4(cpx2& a, cpx2& b, cpx2& c, cpx2& d) {
+    cpx2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = cmul_negi(csub(b, d));
+    a = cadd(t0, t2); c = csub(t0, t2); b = cadd(t1, t3); d = csub(t1, t3);
+}
+
+// forward 16-point DFT in registers, natural order in and out: X[k] = sum_n x[n] W16^{nk}
+DEVFN void dft16(cpx2 (&x)[16]) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+    // layer 1: for each n_b, DFT4 over n_a of x[4*n_a + n_b]; result k_a left at x[4*k_a + n_b]
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) dft4(x[nb], x[4 + nb], x[8 + nb], x[12 + nb]);
+    // twiddle W16^{n_b * k_a}
+    x[5] = cmuls(x[5], c1, -s1);                                   // W^1
+    { cpx2 t = x[6]; x[6].re = f2muls(f2add(t.re, t.im), r2); x[6].im = f2muls(f2sub(t.im, t.re), r2); }   // W^2
+    x[7] = cmuls(x[7], s1, -c1);                                   // W^3
+    { cpx2 t = x[9]; x[9].re = f2muls(f2add(t.re, t.im), r2); x[9].im = f2muls(f2sub(t.im, t.re), r2); }   // W^2
+    x[10] = cmul_negi(x[10]);                                      // W^4
+    { cpx2 t = x[11]; x[11].re = f2muls(f2sub(t.im, t.re), r2); x[11].im = f2muls(f2add(t.re, t.im), -r2); }  // W^6
+    x[13] = cmuls(x[13], s1, -c1);                                 // W^3
+    { cpx2 t = x[14]; x[14].re = f2muls(f2sub(t.im, t.re), r2); x[14].im = f2muls(f2add(t.re, t.im), -r2); }  // W^6
+    x[15] = cmuls(x[15], -c1, s1);                                 // W^9
+    // layer 2: for each k_a, DFT4 over n_b of x[4*k_a + n_b]; output k_b is X[k_a + 4*k_b]
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) dft4(x[4 * ka], x[4 * ka + 1], x[4 * ka + 2], x[4 * ka + 3]);
+    // x[4*k_a + k_b] now holds X[k_a + 4*k_b]: transpose the 4x4 register tile (pure renaming)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) { cpx2 t = x[4 * a + b]; x[4 * a + b] = x[4 * b + a]; x[4 * b + a] = t; }
+}
+
+}  // namespace dspfe

@@ -52,13 +52,18 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
     if (tid == kPitchPrepThreads - 1) p.frame_off[p.n_utt] = s_fr[tid];
 }
 
-__global__ void __launch_bounds__(32 * kPitchWarps) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
+__global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
+    float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
+    int32_t* ds_idx = reinterpret_cast<int32_t*>(smem + kTabMod * 8);
+    for (int i = threadIdx.x; i < kTabMod; i += blockDim.x) tws[i] = p.tab[i];
+    for (int i = threadIdx.x; i < p.ds_out; i += blockDim.x) ds_idx[i] = p.ds_idx[i];
+    __syncthreads();
     const int w = threadIdx.x >> 5;
-    const int64_t g = (int64_t)blockIdx.x * kPitchWarps + w;
-    if (g >= p.frame_off[p.n_utt] || g >= p.max_frames) return;   // whole warp leaves; only warp-level syncs below
-    float2* bufa = reinterpret_cast<float2*>(smem) + w * 2 * kPitchFft;
-    pitch_frame_warp(p, g, bufa, bufa + kPitchFft);
+    const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
+    const int64_t g0 = 2 * ((int64_t)blockIdx.x * kPitchWarps + w);
+    if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
+    pitch_frame_pair(p, g0, total, smem + kTabMod * 8 + kMaxDsOut * 4 + w * kWarpSmemBytes, tws, tws + kTabW32, ds_idx);
 }
 
 __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid_constant__ PitchParams p) {
@@ -103,7 +108,7 @@ __global__ void center_clip_kernel(const float* in, int64_t n_rows, int len, int
 struct dspfe_pitch_plan {
     dspfe_pitch_params prm;
     PitchParams base;          // scalars + table pointers; per-call pointers filled in launch
-    float2* d_tw = nullptr; float2* d_H = nullptr;
+    float2* d_tab = nullptr;
     // workspaces
     int64_t cap_utt = 0, cap_frames = 0;
     int64_t* seg_start = nullptr; int32_t* seg_len = nullptr; int32_t* ds_len = nullptr; int64_t* frame_off = nullptr;
@@ -161,25 +166,23 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
     if (!pl) return fail(DSPFE_ERR_NOMEM, "out of host memory");
     pl->prm = *q;
     PitchParams& b = pl->base;
-    std::vector<float2> tw, H;
+    std::vector<float2> tab;
     std::string err;
-    const int trc = build_pitch_tables(*q, b, tw, H, err);
+    const int trc = build_pitch_tables(*q, b, tab, err);
     if (trc) { delete pl; return fail(trc, err); }
-    cudaError_t e = cudaMalloc(&pl->d_tw, kPitchFft * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_H, kPitchFft * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMemcpy(pl->d_tw, tw.data(), kPitchFft * sizeof(float2), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pl->d_H, H.data(), kPitchFft * sizeof(float2), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPitchWarps * 2 * kPitchFft * (int)sizeof(float2));
+    cudaError_t e = cudaMalloc(&pl->d_tab, kTabTotal * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_tab, tab.data(), kTabTotal * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, track_smem(kCepLen));
-    if (e != cudaSuccess) { cudaFree(pl->d_tw); cudaFree(pl->d_H); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
-    b.tw = pl->d_tw; b.H = pl->d_H;
+    if (e != cudaSuccess) { cudaFree(pl->d_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
+    b.tab = pl->d_tab;
     *plan = pl;
     return DSPFE_OK;
 }
 
 void dspfe_pitch_destroy(dspfe_pitch_plan* pl) {
     if (!pl) return;
-    cudaFree(pl->d_tw); cudaFree(pl->d_H);
+    cudaFree(pl->d_tab);
     cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off);
     cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
     cudaFree(pl->d_pcm); cudaFree(pl->d_off); cudaFree(pl->d_trim); cudaFree(pl->d_feat);
@@ -221,7 +224,7 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     p.max_frames = bound;
     pitch_prep_kernel<<<1, kPitchPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("pitch_prep_kernel", st);
-    pitch_frame_kernel<<<(unsigned)((bound + kPitchWarps - 1) / kPitchWarps), 32 * kPitchWarps, kPitchWarps * 2 * kPitchFft * sizeof(float2), st>>>(p);
+    pitch_frame_kernel<<<(unsigned)((bound + 2 * kPitchWarps - 1) / (2 * kPitchWarps)), 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_frame_kernel", st);
     if (d_pitch || d_lag || d_feat) {
         pitch_track_kernel<<<(unsigned)n_utt, kTrackThreads, track_smem(p.row_len), st>>>(p);

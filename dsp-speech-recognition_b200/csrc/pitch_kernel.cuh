@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "simt.h"
+#include "fft_regs.h"
 
 #ifndef DSP_HD
 #ifdef __CUDACC__
@@ -37,10 +38,17 @@ constexpr int kCepCols = 200;       // columns peak_score can reach: lags 20..99
 constexpr int kAcrLags = 180;       // lags 20..199 (pitch.py:125-129)
 constexpr int kMinLag = 20;
 constexpr int kPeakLags = 80;       // peak_score evaluates lags 20..99 (pitch.py:232)
-constexpr int kPitchWarps = 4;      // frames per CTA in K4a/K5a
+constexpr int kMaxDsOut = 256;      // decimator pattern length limit
+constexpr int kPitchWarps = 4;      // warps per CTA in K4a/K5a, each carrying a pair of frames
+constexpr int kTwStride = 34;       // row stride (float2) of the twiddle table and the transpose tile: conflict-free both ways
+constexpr int kWarpScr = 16 * kTwStride;
+constexpr int kWarpSmemBytes = kWarpScr * 8 + 512 * 8 + 512 * 16;   // transpose tile | clipped frame pair | parked spectrum
+// table blob offsets, in float2
+constexpr int kTabTw = 0, kTabW32 = kTabTw + kWarpScr, kTabMod = kTabW32 + 32, kTabHe = kTabMod + 512, kTabHo = kTabHe + 512,
+              kTabTotal = kTabHo + 512;
+constexpr int kFrameCtaSmem = (kTabMod * 8) + kMaxDsOut * 4 + kPitchWarps * kWarpSmemBytes;   // shared tables | ds_idx | per-warp areas
 constexpr int kTrackThreads = 512;
 constexpr int kTrackChunk = 16;     // frames smoothed per pass of K4b/K5b
-constexpr int kMaxDsOut = 256;      // decimator pattern length limit
 
 struct PitchParams {
     const void* pcm; int in_f32;         // packed samples: int16 or float32
@@ -53,8 +61,9 @@ struct PitchParams {
     int frame_len, frame_step;           // at the decimated rate: 512/100 (or 300/100 for the autocorrelation variant)
     int do_clip;                         // center_clip(frame, False) before the band-pass (pitch.py:88,103)
     int no_smooth;                       // taps only: K4b/K5b score the rows as given (peak_score on its own)
-    const float2* tw;                    // W1024^k, k < 1024
-    const float2* H;                     // FFT1024 of the FIR taps
+    const float2* tab;                   // table blob (kTab* offsets): W512 twiddles, W32, W1024^n, He, Ho
+    float pre_hi, pre_lo;                // preemph split into float32 head + tail
+    int ds_q32, ds_r32;                  // 32 / ds_out, 32 % ds_out
     int mode;                            // 0 cepstrum, 1 autocorrelation
     int row_len;                         // columns per row: cepstrum 200 (fused) or 512 (tap); autocorrelation 180
     int64_t* frame_off;                  // [U+1] prefix sums of pitch frames
@@ -174,106 +183,130 @@ DSP_HD bool pitch_feature_tail(const double* pitch, const double* amp, int F, do
 // ---------------------------------------------------------------------------------------------------------
 // warp-cooperative pieces (device + emulator)
 // ---------------------------------------------------------------------------------------------------------
-DEVFN float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-
-// Radix-4 Stockham FFT over shared memory, one warp per transform, natural order in and out.
-// a: input (destroyed), b: scratch; returns the buffer holding the result.  tw = W1024^k.  No normalisation.
-template <int N, bool INV>
-DEVFN float2* warp_fft(float2* a, float2* b, const float2* tw, int lane) {
-    constexpr int TS = kPitchFft / N;   // table stride
-    int Ns = 1;
-#pragma unroll 1
-    for (; Ns * 4 <= N; Ns *= 4) {
-        const int tstep = TS * (N / (Ns * 4));
-        for (int j = lane; j < N / 4; j += 32) {
-            const int k = j & (Ns - 1);
-            float2 v0 = a[j], v1 = a[j + N / 4], v2 = a[j + N / 2], v3 = a[j + 3 * N / 4];
-            if (Ns > 1) {
-                float2 w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
-                if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-                v1 = cmulf(v1, w1); v2 = cmulf(v2, w2); v3 = cmulf(v3, w3);
-            }
-            const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-            const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-            float2 t3 = make_float2(v1.y - v3.y, v3.x - v1.x);   // -i (v1 - v3)
-            if (INV) { t3.x = -t3.x; t3.y = -t3.y; }             // +i (v1 - v3)
-            const int j0 = ((j - k) << 2) + k;
-            b[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-            b[j0 + Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
-            b[j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
-            b[j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
-        }
-        simt::warp_sync();
-        float2* t = a; a = b; b = t;
-    }
-    if (Ns < N) {   // one radix-2 pass left (N = 512)
-        const int tstep = TS * (N / (Ns * 2));
-        for (int j = lane; j < N / 2; j += 32) {
-            const int k = j & (Ns - 1);
-            float2 v0 = a[j], v1 = a[j + N / 2];
-            float2 w = tw[k * tstep];
-            if (INV) w.y = -w.y;
-            v1 = cmulf(v1, w);
-            const int j0 = ((j - k) << 1) + k;
-            b[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
-            b[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
-        }
-        simt::warp_sync();
-        float2* t = a; a = b; b = t;
-    }
-    return a;
+// 512-point complex FFT of a packed frame pair, one warp, 16 complex values per lane, 512 = 16 x 16 x 2:
+// radix-16 in registers, twiddle, transpose through shared memory, radix-16 in registers, radix-2 across lane pairs.
+//   layout A (time side):      element n = 32*n1 + n2        -> lane n2, register n1
+//   layout B (frequency side): element k = k1 + 16*r + 256*s -> lane 2*k1 + s, register r
+// fft512_AB is decimation in frequency (A -> B), fft512_BA decimation in time (B -> A); both compute the FORWARD
+// DFT sum x[j] W512^{jk}.  The inverse is the same routine on (im, re)-swapped data (swap, forward, swap), so the
+// chain FFT -> pointwise -> IFFT -> pointwise -> FFT ... never needs a reordering pass.
+DEVFN cpx2 shfl_xor_c(cpx2 a, int m) {
+    cpx2 r;
+    r.re.x = simt::shfl32_xor(a.re.x, m); r.re.y = simt::shfl32_xor(a.re.y, m);
+    r.im.x = simt::shfl32_xor(a.im.x, m); r.im.y = simt::shfl32_xor(a.im.y, m);
+    return r;
 }
-
-DEVFN int warp_sum_i(int v) {
+DEVFN void swap_ri(cpx2 (&x)[16]) {
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) v += simt::shfl32_i(v, (simt::tid() & 31) ^ m);
-    return v;
-}
-DEVFN unsigned warp_min_u(unsigned v) {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) { const unsigned o = (unsigned)simt::shfl32_i((int)v, (simt::tid() & 31) ^ m); v = o < v ? o : v; }
-    return v;
+    for (int i = 0; i < 16; ++i) { const float2 t = x[i].re; x[i].re = x[i].im; x[i].im = t; }
 }
 
-// k-th smallest (0-based) of the warp's 16x32 unsigned keys, exact, by bitwise selection (31 value bits)
-DEVFN unsigned warp_select(const unsigned (&key)[16], int k) {
-    unsigned K = 0;
-    for (int b = 30; b >= 0; --b) {
-        const unsigned trial = K | ((1u << b) - 1u);
-        int c = 0;
+// tws: W512^{k1*n2} at [k1*kTwStride + n2]; w32s: [2r] = 1, [2r+1] = W32^r; scr: kWarpScr float2 owned by the warp
+DEVFN void fft512_AB(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
+    dft16(x);                                                   // over n1 -> k1 (lane = n2)
 #pragma unroll
-        for (int t = 0; t < 16; ++t) c += key[t] <= trial ? 1 : 0;
-        c = warp_sum_i(c);
-        if (c < k + 1) K |= 1u << b;
+    for (int k1 = 1; k1 < 16; ++k1) { const float2 w = tws[k1 * kTwStride + lane]; x[k1] = cmuls(x[k1], w.x, w.y); }
+    const int rb = (lane >> 1) * kTwStride + (lane & 1);      // lane (k1, p) reads a[k1][2m + p]
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * kTwStride + lane] = x[k1].re;
+    simt::warp_sync();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m].re = scr[rb + 2 * m];
+    simt::warp_sync();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * kTwStride + lane] = x[k1].im;
+    simt::warp_sync();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m].im = scr[rb + 2 * m];
+    simt::warp_sync();
+    dft16(x);                                                   // over m -> r
+    const int p = lane & 1;
+    const float sg = p ? -1.f : 1.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {                              // X[k1+16r] = B0 + W32^r B1, X[k1+16r+256] = B0 - W32^r B1
+        const float2 w = w32s[2 * r + p];
+        const cpx2 u = cmuls(x[r], w.x, w.y);
+        const cpx2 v = shfl_xor_c(u, 1);
+        x[r].re = f2fmas(u.re, sg, v.re); x[r].im = f2fmas(u.im, sg, v.im);
     }
-    return K;
 }
 
-// median of the non-negative entries among the warp's 16x32 values (np.median(frame[frame >= 0]), pitch.py:146):
-// NaN when there is none.  `valid` masks the entries that belong to the frame.
-DEVFN float warp_median_nonneg(const float (&x)[16], int L, int lane) {
-    unsigned key[16];
-    int m_cnt = 0;
+DEVFN void fft512_BA(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
+    const int s = lane & 1;
+    const float sg = s ? -1.f : 1.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {                              // lane s=0: v0 + v1; lane s=1: (v0 - v1) W32^r
+        const cpx2 v = shfl_xor_c(x[r], 1);
+        cpx2 d; d.re = f2fmas(x[r].re, sg, v.re); d.im = f2fmas(x[r].im, sg, v.im);
+        const float2 w = w32s[2 * r + s];
+        x[r] = cmuls(d, w.x, w.y);
+    }
+    dft16(x);                                                   // over r -> m; lane (k1, p) now holds D[k1][n2 = 2m + p]
+    const int rb = (lane >> 1) * kTwStride + s;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) { const float2 w = tws[rb + 2 * m]; x[m] = cmuls(x[m], w.x, w.y); }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) scr[rb + 2 * m] = x[m].re;
+    simt::warp_sync();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) x[k1].re = scr[k1 * kTwStride + lane];
+    simt::warp_sync();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) scr[rb + 2 * m] = x[m].im;
+    simt::warp_sync();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) x[k1].im = scr[k1 * kTwStride + lane];
+    simt::warp_sync();
+    dft16(x);                                                   // over k1 -> n1 (lane = n2)
+}
+DEVFN void ifft512_BA(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
+    swap_ri(x); fft512_BA(x, scr, tws, w32s, lane); swap_ri(x);   // unnormalised inverse
+}
+
+// medians of the non-negative entries of two frames at once (np.median(frame[frame >= 0]), pitch.py:146): exact k-th
+// order statistics by bitwise selection on the float bit patterns; NaN when a frame has no non-negative sample.
+DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], int L, int lane) {
+    unsigned ka[16], kb[16];
+    int cnt = 0;
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-        const bool nn = (lane + 32 * t) < L && x[t] >= 0.f;
-        key[t] = nn ? ((unsigned)__float_as_int_compat(x[t]) & 0x7fffffffu) : 0xffffffffu;   // -0.0 counts as 0
-        m_cnt += nn ? 1 : 0;
+        const bool in = (lane + 32 * t) < L;
+        const bool na = in && xa[t] >= 0.f, nb = in && xb[t] >= 0.f;
+        ka[t] = na ? ((unsigned)__float_as_int_compat(xa[t]) & 0x7fffffffu) : 0xffffffffu;   // -0.0 counts as 0
+        kb[t] = nb ? ((unsigned)__float_as_int_compat(xb[t]) & 0x7fffffffu) : 0xffffffffu;
+        cnt += (na ? 1 : 0) + (nb ? 0x10000 : 0);
     }
-    m_cnt = warp_sum_i(m_cnt);
-    if (m_cnt == 0) return NAN;
-    const unsigned k1 = warp_select(key, (m_cnt - 1) >> 1);
-    unsigned k2 = k1;
-    if ((m_cnt & 1) == 0) {   // even count: average with the next order statistic
-        int c = 0; unsigned nxt = 0xffffffffu;
+    cnt = warp_redux_add(cnt);
+    const int ma = cnt & 0xffff, mb = cnt >> 16;
+    const int ra = (ma - 1) >> 1, rb = (mb - 1) >> 1;          // rank of the lower middle element
+    unsigned Ka = 0, Kb = 0;
+    for (int b = 30; b >= 0; --b) {
+        const unsigned ta = Ka | ((1u << b) - 1u), tb = Kb | ((1u << b) - 1u);
+        int c = 0;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) { c += key[t] <= k1 ? 1 : 0; if (key[t] > k1 && key[t] < nxt) nxt = key[t]; }
-        c = warp_sum_i(c); nxt = warp_min_u(nxt);
-        k2 = (c >= (m_cnt >> 1) + 1) ? k1 : nxt;
+        for (int t = 0; t < 16; ++t) c += (ka[t] <= ta ? 1 : 0) + (kb[t] <= tb ? 0x10000 : 0);
+        c = warp_redux_add(c);
+        if ((c & 0xffff) < ra + 1) Ka |= 1u << b;
+        if ((c >> 16) < rb + 1) Kb |= 1u << b;
     }
-    // np.median of an even count is mean([a, b]) = (a + b) / 2
-    return (__int_as_float_compat((int)k1) + __int_as_float_compat((int)k2)) * 0.5f;
+    // even count: the upper middle element is the same key when enough keys are <= K, else the next larger key
+    int c = 0; unsigned na = 0xffffffffu, nb = 0xffffffffu;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        c += (ka[t] <= Ka ? 1 : 0) + (kb[t] <= Kb ? 0x10000 : 0);
+        if (ka[t] > Ka && ka[t] < na) na = ka[t];
+        if (kb[t] > Kb && kb[t] < nb) nb = kb[t];
+    }
+    c = warp_redux_add(c); na = warp_redux_min(na); nb = warp_redux_min(nb);
+    const unsigned Ka2 = ((ma & 1) || (c & 0xffff) >= (ma >> 1) + 1) ? Ka : na;
+    const unsigned Kb2 = ((mb & 1) || (c >> 16) >= (mb >> 1) + 1) ? Kb : nb;
+    float2 med;   // np.median of an even count is (a + b) / 2
+    med.x = ma ? (__int_as_float_compat((int)Ka) + __int_as_float_compat((int)Ka2)) * 0.5f : NAN;
+    med.y = mb ? (__int_as_float_compat((int)Kb) + __int_as_float_compat((int)Kb2)) * 0.5f : NAN;
+    return med;
 }
+// single-frame form (center_clip tap)
+DEVFN float warp_median_nonneg(const float (&x)[16], int L, int lane) { return warp_median_nonneg2(x, x, L, lane).x; }
 
 // center_clip(frame, False) (pitch.py:145-155) on one value
 DEVFN float clip_value(float v, float med) {
@@ -289,90 +322,187 @@ DEVFN int find_utt(const int64_t* frame_off, int n_utt, int64_t g) {
     return lo;
 }
 
-// One frame: gather + clip + FIR + (cepstrum | autocorrelation) -> p.rows[g, :], p.frame_amp[g].
-// smem: two float2[1024] buffers owned by the warp.
-DEVFN void pitch_frame_warp(const PitchParams& p, int64_t g, float2* bufa, float2* bufb) {
-    const int lane = simt::tid() & 31;
+// Gather one frame through the sample-picking decimator (preprocess.py:21-28), pre-emphasised over the whole
+// utterance (preprocess.py:11-19), zero padded past the decimated length (sigproc.py:84-87): x[t] = sample lane + 32 t.
+// Returns the lane's partial sum of |x| (sub_endpoint_detect, pitch.py:65).
+DEVFN float gather_frame(const PitchParams& p, int64_t g, const int32_t* ds_idx, float (&x)[16], int lane) {
     const int u = find_utt(p.frame_off, p.n_utt, g);
     const int64_t f = g - p.frame_off[u];
     const int64_t start = p.seg_start[u];
     const int64_t ubase = p.offsets[u];
     const int Ld = p.ds_len[u];
     const int L = p.frame_len;
-    // ---- gather the frame (zero padded past the decimated length), 16 samples per lane: n = lane + 32 t
-    float x[16];
-    double asum = 0.0;
+    const int64_t k0 = f * p.frame_step + lane;
+    // k - 1 = a * ds_out + b, advanced by 32 per step without a division; k0 = 0 starts from -1 = (-1, ds_out - 1)
+    int64_t a = k0 >= 1 ? (k0 - 1) / p.ds_out : -1;
+    int b = k0 >= 1 ? (int)((k0 - 1) - a * p.ds_out) : p.ds_out - 1;
+    float asum = 0.f;
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
         const int n = lane + 32 * t;
-        const int64_t k = f * p.frame_step + n;
-        double v = 0.0;
+        const int64_t k = k0 + 32 * t;
+        float v = 0.f;
         if (n < L && k < Ld) {
-            const int64_t s = start + ds_index(k, p.ds_idx, p.ds_in, p.ds_out);   // packed-buffer sample index
-            double cur, prev = 0.0;
+            const int64_t s = start + (k == 0 ? 0 : a * p.ds_in + ds_idx[b]);   // packed-buffer sample index
+            float cur, prev = 0.f;
             if (p.in_f32) { cur = reinterpret_cast<const float*>(p.pcm)[s]; if (s > ubase) prev = reinterpret_cast<const float*>(p.pcm)[s - 1]; }
-            else { cur = reinterpret_cast<const int16_t*>(p.pcm)[s]; if (s > ubase) prev = reinterpret_cast<const int16_t*>(p.pcm)[s - 1]; }
-            // preprocess.preemphasis (:11-19) in float64 like the reference: x[n] - c*x[n-1], x[0] kept
-            v = (p.preemph != 0.0 && s > ubase) ? cur - p.preemph * prev : cur;
+            else { cur = cvt_i16(reinterpret_cast<const int16_t*>(p.pcm)[s]); if (s > ubase) prev = cvt_i16(reinterpret_cast<const int16_t*>(p.pcm)[s - 1]); }
+            // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one
+            v = p.pre_hi != 0.f ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
         }
-        x[t] = (float)v;
-        asum += fabs(v);
+        x[t] = v;
+        asum += fabsf(v);
+        a += p.ds_q32; b += p.ds_r32;
+        if (b >= p.ds_out) { b -= p.ds_out; ++a; }
     }
-    // sum |x| of the raw frame in float64 (pitch.py:65)
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) asum += shfl32_xor_f64(asum, m);
-    if (lane == 0 && p.frame_amp) p.frame_amp[g] = asum;
+    return asum;
+}
 
+// Two consecutive frames (g0, g0 + 1) per warp: gather + clip + FIR band-pass + (cepstrum | autocorrelation)
+// -> p.rows[g, :], p.frame_amp[g].  The causal complex FIR y = conv(x, h)[:512] (sigproc.py:22-46) is evaluated through
+// the even / odd bins of its 1024-point spectrum, which only takes 512-point transforms:
+//     Xe = FFT512(x), Xo = FFT512(x W1024^n);  y[n] = (IFFT512(Xe He)[n] + W1024^-n IFFT512(Xo Ho)[n]) / 2
+// and for the cepstrum (pitch.py:135-143) the first inverse transform folds away:
+//     FFT512(y) = (Xe He + FFT512(W1024^-n IFFT512(Xo Ho))) / 2.
+// wsm: per-warp shared memory = scr[kWarpScr] float2 | xs[512] float2 | park[512] float4.
+DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws,
+                            const float2* w32s, const int32_t* ds_idx) {
+    const int lane = simt::tid() & 31;
+    float2* scr = reinterpret_cast<float2*>(wsm);
+    float2* xs = scr + kWarpScr;
+    float4* park = reinterpret_cast<float4*>(xs + 512);
+    const float2* modA = p.tab + kTabMod;   // W1024^n, n = 32 t + lane
+    const float2* HeB = p.tab + kTabHe;     // H1024[2k], layout B order [r*32 + lane]
+    const float2* HoB = p.tab + kTabHo;     // H1024[2k+1]
+    const bool hasB = g0 + 1 < total;
+    const int L = p.frame_len;
+    // ---- gather both frames; sum |x| of the raw frames in float64 across the warp
+    float xa[16], xb[16];
+    double sa = (double)gather_frame(p, g0, ds_idx, xa, lane), sb = 0.0;
+    if (hasB) sb = (double)gather_frame(p, g0 + 1, ds_idx, xb, lane);
+    else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) xb[t] = 0.f;
+    }
+    if (p.frame_amp) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
+        if (lane == 0) { p.frame_amp[g0] = sa; if (hasB) p.frame_amp[g0 + 1] = sb; }
+    }
     // ---- centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
-    float med = 0.f;
-    if (p.do_clip) med = warp_median_nonneg(x, L, lane);
+    float2 med = make_float2(0.f, 0.f);
+    if (p.do_clip) med = warp_median_nonneg2(xa, xb, L, lane);
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-        const int n = lane + 32 * t;
-        const float c = p.do_clip ? clip_value(x[t], med) : x[t];
-        bufa[n] = make_float2(n < L ? c : 0.f, 0.f);
-        bufa[n + 512] = make_float2(0.f, 0.f);
+        const bool in = lane + 32 * t < L;
+        const float ca = p.do_clip ? clip_value(xa[t], med.x) : xa[t];
+        const float cb = p.do_clip ? clip_value(xb[t], med.y) : xb[t];
+        xs[32 * t + lane] = make_float2(in ? ca : 0.f, in ? cb : 0.f);
     }
-    simt::warp_sync();
-    // ---- FIR band-pass: y = conv(x, h)[:L] through the 1024-point spectrum (sigproc.py:22-46)
-    float2* A = warp_fft<1024, false>(bufa, bufb, p.tw, lane);
-    float2* B = (A == bufa) ? bufb : bufa;
-    for (int j = lane; j < 1024; j += 32) A[j] = cmulf(A[j], p.H[j]);
-    simt::warp_sync();
-    float2* Y = warp_fft<1024, true>(A, B, p.tw, lane);
-    float2* Z = (Y == bufa) ? bufb : bufa;
+    // (every lane only ever touches its own xs / park entries: no barrier needed around them)
+    cpx2 x[16];
+    const float2 zero2 = make_float2(0.f, 0.f);
+    // ---- Xe = FFT512(x)
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { x[t].re = xs[32 * t + lane]; x[t].im = zero2; }
+    fft512_AB(x, scr, tws, w32s, lane);
+    if (p.mode == 0) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {   // park Xe He / 2
+            const float2 h = ldg(HeB + r * 32 + lane);
+            const cpx2 v = cmuls(x[r], 0.5f * h.x, 0.5f * h.y);
+            park[r * 32 + lane] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { const float2 h = ldg(HeB + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
+        ifft512_BA(x, scr, tws, w32s, lane);   // 512 * circular part of the convolution
+#pragma unroll
+        for (int t = 0; t < 16; ++t) park[32 * t + lane] = make_float4(x[t].re.x, x[t].re.y, x[t].im.x, x[t].im.y);
+    }
+    // ---- Xo = FFT512(x W1024^n), then d = IFFT512(Xo Ho)
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const float2 xv = xs[32 * t + lane], m = ldg(modA + 32 * t + lane);
+        x[t].re = f2muls(xv, m.x); x[t].im = f2muls(xv, m.y);
+    }
+    fft512_AB(x, scr, tws, w32s, lane);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { const float2 h = ldg(HoB + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
+    ifft512_BA(x, scr, tws, w32s, lane);
     const float inv1024 = 1.0f / 1024.0f;
     if (p.mode == 0) {
-        // ---- cepstrum: |ifft(log|fft(y)|)| (pitch.py:135-143); L == 512 here
-        for (int j = lane; j < 512; j += 32) { float2 v = Y[j]; Y[j] = make_float2(v.x * inv1024, v.y * inv1024); }
-        simt::warp_sync();
-        float2* X = warp_fft<512, false>(Y, Z, p.tw, lane);
-        float2* X2 = (X == bufa) ? bufb : bufa;
-        for (int j = lane; j < 512; j += 32) { const float2 v = X[j]; X[j] = make_float2(dsp_logf(sqrtf(v.x * v.x + v.y * v.y)), 0.f); }
-        simt::warp_sync();
-        float2* C = warp_fft<512, true>(X, X2, p.tw, lane);
-        const float inv512 = 1.0f / 512.0f;
-        float* row = p.rows + g * p.row_len;
-        for (int j = lane; j < p.row_len; j += 32) { const float2 v = C[j]; row[j] = sqrtf(v.x * v.x + v.y * v.y) * inv512; }
-    } else {
-        // ---- autocorrelation of |y| (pitch.py:112-132, sigproc.py:48-53) through |FFT|^2
-        for (int j = lane; j < 1024; j += 32) {
-            const float2 v = Y[j];
-            Y[j] = make_float2(j < L ? sqrtf(v.x * v.x + v.y * v.y) * inv1024 : 0.f, 0.f);
+        // ---- cepstrum: FFT512(y) = park + FFT512(W1024^-n d / 1024); log|.|; IFFT512; |.| / 512
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { const float2 m = ldg(modA + 32 * t + lane); x[t] = cmuls(x[t], m.x * inv1024, -m.y * inv1024); }
+        fft512_AB(x, scr, tws, w32s, lane);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float4 pk = park[r * 32 + lane];
+            const float2 yr = f2add(x[r].re, make_float2(pk.x, pk.y)), yi = f2add(x[r].im, make_float2(pk.z, pk.w));
+            const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
+            x[r].re = make_float2(0.5f * dsp_fast_logf(s2.x), 0.5f * dsp_fast_logf(s2.y));
+            x[r].im = zero2;
         }
-        simt::warp_sync();
-        float2* V = warp_fft<1024, false>(Y, Z, p.tw, lane);
-        float2* V2 = (V == bufa) ? bufb : bufa;
-        for (int j = lane; j < 1024; j += 32) { const float2 v = V[j]; V[j] = make_float2(v.x * v.x + v.y * v.y, 0.f); }
-        simt::warp_sync();
-        float2* R = warp_fft<1024, true>(V, V2, p.tw, lane);
-        float* row = p.rows + g * p.row_len;
-        for (int j = lane; j < p.row_len; j += 32) {
-            const int n = kMinLag + j;
-            row[j] = (n < L) ? R[n].x * inv1024 / (float)(L - n) : NAN;
+        ifft512_BA(x, scr, tws, w32s, lane);
+        const float inv512 = 1.0f / 512.0f;
+        float* rowa = p.rows + g0 * p.row_len;
+        float* rowb = rowa + p.row_len;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int n = 32 * t + lane;
+            if (n < p.row_len) {
+                const float2 s2 = f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re));
+                rowa[n] = dsp_fast_sqrtf(s2.x) * inv512;
+                if (hasB) rowb[n] = dsp_fast_sqrtf(s2.y) * inv512;
+            }
+        }
+    } else {
+        // ---- autocorrelation of v = |y| (pitch.py:112-132, sigproc.py:48-53): r = IFFT1024(|FFT1024(v)|^2), again
+        // through the even / odd bins: r[n] = (IFFT512(|Ve|^2)[n] + W1024^-n IFFT512(|Vo|^2)[n]) / 1024
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const float2 m = ldg(modA + 32 * t + lane);
+            const float4 pk = park[32 * t + lane];
+            const cpx2 d = cmuls(x[t], m.x, -m.y);
+            const float2 yr = f2add(d.re, make_float2(pk.x, pk.y)), yi = f2add(d.im, make_float2(pk.z, pk.w));
+            const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
+            const bool in = 32 * t + lane < L;
+            xs[32 * t + lane] = make_float2(in ? dsp_fast_sqrtf(s2.x) * inv1024 : 0.f, in ? dsp_fast_sqrtf(s2.y) * inv1024 : 0.f);
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { x[t].re = xs[32 * t + lane]; x[t].im = zero2; }
+        fft512_AB(x, scr, tws, w32s, lane);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { x[r].re = f2fma(x[r].im, x[r].im, f2mul(x[r].re, x[r].re)); x[r].im = zero2; }
+        ifft512_BA(x, scr, tws, w32s, lane);
+        float2* ge = reinterpret_cast<float2*>(park);   // real parts of the even-bin half, lags < 224
+#pragma unroll
+        for (int t = 0; t < 7; ++t) ge[32 * t + lane] = x[t].re;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const float2 xv = xs[32 * t + lane], m = ldg(modA + 32 * t + lane);
+            x[t].re = f2muls(xv, m.x); x[t].im = f2muls(xv, m.y);
+        }
+        fft512_AB(x, scr, tws, w32s, lane);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { x[r].re = f2fma(x[r].im, x[r].im, f2mul(x[r].re, x[r].re)); x[r].im = zero2; }
+        ifft512_BA(x, scr, tws, w32s, lane);
+        float* rowa = p.rows + g0 * p.row_len;
+        float* rowb = rowa + p.row_len;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const int n = 32 * t + lane, j = n - kMinLag;
+            if (j >= 0 && j < p.row_len) {
+                const float2 m = ldg(modA + n);
+                // Re(conj(W1024^n) go[n]) = m.x go.re + m.y go.im
+                const float2 r = f2muls(f2add(ge[n], f2fmas(x[t].re, m.x, f2muls(x[t].im, m.y))), inv1024);
+                const float inv = (n < L) ? 1.0f / (float)(L - n) : NAN;
+                rowa[j] = r.x * inv;
+                if (hasB) rowb[j] = r.y * inv;
+            }
         }
     }
-    simt::warp_sync();
 }
 
 // K4b / K5b: one CTA (512 threads) per utterance, frames in order, kTrackChunk at a time.

@@ -44,6 +44,10 @@ DEVFN float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(
 DEVFN float dsp_logf(float x) { return std::log(x); }
 static inline float sqrtf_(float x) { return std::sqrt(x); }
 DEVFN float dsp_fmaf(float a, float b, float c) { return std::fmaf(a, b, c); }
+DEVFN float dsp_fast_logf(float x) { return std::log(x); }
+DEVFN float dsp_fast_sqrtf(float x) { return std::sqrt(x); }
+DEVFN float cvt_i16(int v) { return (float)v; }
+template <class T> DEVFN T ldg(const T* p) { return *p; }
 // int16 halves of a 32-bit word -> float
 DEVFN float cvt_lo16(uint32_t w) { return (float)(int16_t)(w & 0xffffu); }
 DEVFN float cvt_hi16(uint32_t w) { return (float)(int16_t)(w >> 16); }
@@ -98,6 +102,12 @@ DEVFN float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 DEVFN float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 DEVFN float dsp_logf(float x) { return logf(x); }
 DEVFN float dsp_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
+// MUFU-based log / sqrt (about 2 ulp): the pitch kernels take 512 logs and up to 512 square roots per frame
+DEVFN float dsp_fast_logf(float x) { return __logf(x); }
+DEVFN float dsp_fast_sqrtf(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// one int16 value -> float by mantissa splicing (exact; I2F runs at 16/clk/SM)
+DEVFN float cvt_i16(int v) { return __uint_as_float(0x4B000000u | (((unsigned)v & 0xffffu) ^ 0x8000u)) - 8421376.0f; }
+template <class T> DEVFN T ldg(const T* p) { return __ldg(p); }
 // int16 halves of a 32-bit word -> float without the (slow, XU-pipe) I2F: splice the biased 16-bit
 // value into the mantissa of 2^23 and subtract 2^23 + 2^15 (exact).
 DEVFN float cvt_lo16(uint32_t w) { return __uint_as_float(__byte_perm(w ^ 0x80008000u, 0x4B000000u, 0x7610)) - 8421376.0f; }
@@ -111,6 +121,24 @@ DEVFN float __int_as_float_compat(int i) { float f; std::memcpy(&f, &i, 4); retu
 DEVFN int __float_as_int_compat(float f) { return __float_as_int(f); }
 DEVFN float __int_as_float_compat(int i) { return __int_as_float(i); }
 #endif
+
+// warp-wide integer sum (REDUX on sm_100a)
+DEVFN int warp_redux_add(int v) {
+#ifdef DSPFE_EMU
+    for (int m = 16; m >= 1; m >>= 1) v += simt::shfl32_i(v, (simt::tid() & 31) ^ m);
+    return v;
+#else
+    return __reduce_add_sync(0xffffffffu, v);
+#endif
+}
+DEVFN unsigned warp_redux_min(unsigned v) {
+#ifdef DSPFE_EMU
+    for (int m = 16; m >= 1; m >>= 1) { const unsigned o = (unsigned)simt::shfl32_i((int)v, (simt::tid() & 31) ^ m); v = o < v ? o : v; }
+    return v;
+#else
+    return __reduce_min_sync(0xffffffffu, v);
+#endif
+}
 
 // float64 xor-shuffle over the full warp (two 32-bit shuffles)
 DEVFN double shfl32_xor_f64(double v, int m) {

@@ -17,10 +17,10 @@ struct Args { PitchParams p; std::vector<unsigned char>* smem; int64_t total_fra
 void frame_body(void* a) {
     Args* A = (Args*)a;
     const int w = simt::tid() >> 5;
-    const int64_t g = (int64_t)simt::bid() * kPitchWarps + w;
-    if (g >= A->total_frames) return;
-    float2* bufa = reinterpret_cast<float2*>(A->smem->data()) + w * 2 * kPitchFft;
-    pitch_frame_warp(A->p, g, bufa, bufa + kPitchFft);
+    const int64_t g0 = 2 * ((int64_t)simt::bid() * kPitchWarps + w);
+    if (g0 >= A->total_frames) return;
+    // the device kernel stages the twiddles and the decimator pattern in shared memory; the emulator reads them in place
+    pitch_frame_pair(A->p, g0, A->total_frames, A->smem->data() + w * kWarpSmemBytes, A->p.tab, A->p.tab + kTabW32, A->p.ds_idx);
 }
 void track_body(void* a) {
     Args* A = (Args*)a;
@@ -35,9 +35,9 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
                                int n_utt, double* pitch, int* lag, double* feat, float* rows, float* rows_smoothed, int* score,
                                long long* frame_off_out, long long max_frames, char* errbuf, int errcap) {
     PitchParams p;
-    std::vector<float2> tw, H;
+    std::vector<float2> tab;
     std::string err;
-    if (build_pitch_tables(*q, p, tw, H, err)) { std::snprintf(errbuf, errcap, "%s", err.c_str()); return -2; }
+    if (build_pitch_tables(*q, p, tab, err)) { std::snprintf(errbuf, errcap, "%s", err.c_str()); return -2; }
     std::vector<int64_t> seg_start(n_utt + 1), frame_off(n_utt + 1);
     std::vector<int32_t> seg_len(n_utt + 1), ds_len(n_utt + 1);
     int64_t fo = 0;
@@ -60,13 +60,13 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
     std::vector<float> rows_own; std::vector<double> amp(fo), pitch_own(fo), scratch(3 * fo); std::vector<int32_t> lag_own(fo);
     if (!rows) { rows_own.resize((size_t)fo * p.row_len); rows = rows_own.data(); }
     p.pcm = pcm; p.in_f32 = in_f32; p.offsets = (const int64_t*)offsets; p.trim = trim; p.n_utt = n_utt;
-    p.tw = tw.data(); p.H = H.data(); p.frame_off = frame_off.data(); p.seg_start = seg_start.data(); p.seg_len = seg_len.data();
+    p.tab = tab.data(); p.frame_off = frame_off.data(); p.seg_start = seg_start.data(); p.seg_len = seg_len.data();
     p.ds_len = ds_len.data(); p.rows = rows; p.rows_out = rows_smoothed; p.score = score; p.frame_amp = amp.data();
     p.pitch = pitch ? pitch : pitch_own.data(); p.lag = lag ? lag : lag_own.data(); p.feat = feat; p.scratch = scratch.data();
     p.max_frames = fo;
-    std::vector<unsigned char> smem(kPitchWarps * 2 * kPitchFft * sizeof(float2) + 64);
+    std::vector<unsigned char> smem(kPitchWarps * kWarpSmemBytes + 64);
     Args A{p, &smem, fo};
-    for (int64_t b = 0; b * kPitchWarps < fo + kPitchWarps; ++b) {
+    for (int64_t b = 0; b * 2 * kPitchWarps < fo + 2 * kPitchWarps; ++b) {
         std::memset(smem.data(), 0xCD, smem.size());
         if (!emu::run_cta((int)b, 32 * kPitchWarps, frame_body, &A)) { std::snprintf(errbuf, errcap, "deadlock in frame CTA %lld", (long long)b); return -3; }
     }
