@@ -156,7 +156,7 @@ int dspfe_endpoint(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_
     LAUNCH_CHECK("ep_block_kernel", st);
     ep_frame_kernel<<<(unsigned)((frames_bound + 255) / 256), 256, 0, st>>>(p);
     LAUNCH_CHECK("ep_frame_kernel", st);
-    ep_decide_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, st>>>(p);
+    ep_decide_kernel<<<(unsigned)((n_utt + kEpDecideWarps - 1) / kEpDecideWarps), 32 * kEpDecideWarps, 0, st>>>(p);
     LAUNCH_CHECK("ep_decide_kernel", st);
     return DSPFE_OK;
 }

@@ -265,13 +265,26 @@ __global__ void __launch_bounds__(256) ep_frame_kernel(EpParams p) {
     p.asum[g] = A; p.zcr[g] = Z;
 }
 
-// K3: one thread per utterance
-__global__ void __launch_bounds__(128) ep_decide_kernel(EpParams p) {
-    const int u = blockIdx.x * 128 + threadIdx.x;
+// K3: one warp per utterance.  The rule is a sequential state machine over the utterance's frame statistics; the
+// warp first stages them in shared memory with coalesced loads (a thread walking global memory on its own pays a full
+// DRAM latency per frame), then lane 0 replays the rule.  Utterances longer than kEpStageFrames run from global memory.
+constexpr int kEpStageFrames = 1024;
+constexpr int kEpDecideWarps = 4;
+__global__ void __launch_bounds__(32 * kEpDecideWarps) ep_decide_kernel(EpParams p) {
+    __shared__ int32_t s_stat[kEpDecideWarps][2][kEpStageFrames];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = blockIdx.x * kEpDecideWarps + w;
     if (u >= p.n_utt) return;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
-    endpoint_decide(p.asum + f0, p.zcr + f0, F, p.frame_len, p.rule, p.lr + 2 * u);
+    const int32_t* asum = p.asum + f0;
+    const int32_t* zcr = p.zcr + f0;
+    if (F <= kEpStageFrames) {
+        for (int i = lane; i < F; i += 32) { s_stat[w][0][i] = asum[i]; s_stat[w][1][i] = zcr[i]; }
+        __syncwarp();
+        asum = s_stat[w][0]; zcr = s_stat[w][1];
+    }
+    if (lane == 0) endpoint_decide(asum, zcr, F, p.frame_len, p.rule, p.lr + 2 * u);
 }
 #endif  // __CUDACC__
 

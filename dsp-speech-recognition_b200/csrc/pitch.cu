@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
     if (tid == kPitchPrepThreads - 1) p.frame_off[p.n_utt] = s_fr[tid];
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
@@ -63,19 +64,19 @@ __global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const 
     const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
     const int64_t g0 = 2 * ((int64_t)blockIdx.x * kPitchWarps + w);
     if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
-    pitch_frame_pair(p, g0, total, smem + kTabMod * 8 + kMaxDsOut * 4 + w * kWarpSmemBytes, tws, tws + kTabW32, ds_idx);
+    pitch_frame_pair<MODE>(p, g0, total, smem + kTabMod * 8 + kMaxDsOut * 4 + w * kWarpSmemBytes, tws, tws + kTabW32, ds_idx);
 }
 
 __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* chunk = reinterpret_cast<float*>(smem);
-    int* sc = reinterpret_cast<int*>(chunk + kTrackChunk * p.row_len);
+    int* sc = reinterpret_cast<int*>(chunk + (kTrackChunk + 1) * p.row_len);
     pitch_track_cta(p, chunk, sc);
 }
 
-__global__ void pitch_feature_kernel(const __grid_constant__ PitchParams p) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < p.n_utt) pitch_feature_thread(p, u);
+__global__ void __launch_bounds__(32) pitch_feature_kernel(const __grid_constant__ PitchParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    pitch_feature_warp(p, blockIdx.x, reinterpret_cast<double*>(smem));
 }
 
 // smooth + peak_score on caller-supplied rows (taps of pitch.py:157 / :227): one "utterance" of n_rows frames
@@ -144,7 +145,7 @@ int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
     return DSPFE_OK;
 }
 
-int track_smem(int row_len) { return kTrackChunk * row_len * (int)sizeof(float) + kTrackChunk * kPeakLags * (int)sizeof(int); }
+int track_smem(int row_len) { return (kTrackChunk + 1) * row_len * (int)sizeof(float) + kTrackChunk * kPeakLags * (int)sizeof(int); }
 
 }  // namespace
 
@@ -172,7 +173,8 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
     if (trc) { delete pl; return fail(trc, err); }
     cudaError_t e = cudaMalloc(&pl->d_tab, kTabTotal * sizeof(float2));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_tab, tab.data(), kTabTotal * sizeof(float2), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, track_smem(kCepLen));
     if (e != cudaSuccess) { cudaFree(pl->d_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
     b.tab = pl->d_tab;
@@ -224,14 +226,16 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     p.max_frames = bound;
     pitch_prep_kernel<<<1, kPitchPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("pitch_prep_kernel", st);
-    pitch_frame_kernel<<<(unsigned)((bound + 2 * kPitchWarps - 1) / (2 * kPitchWarps)), 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
+    const unsigned fgrid = (unsigned)((bound + 2 * kPitchWarps - 1) / (2 * kPitchWarps));
+    if (p.mode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
+    else pitch_frame_kernel<1><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_frame_kernel", st);
     if (d_pitch || d_lag || d_feat) {
         pitch_track_kernel<<<(unsigned)n_utt, kTrackThreads, track_smem(p.row_len), st>>>(p);
         LAUNCH_CHECK("pitch_track_kernel", st);
     }
     if (d_feat) {
-        pitch_feature_kernel<<<(unsigned)((n_utt + 63) / 64), 64, 0, st>>>(p);
+        pitch_feature_kernel<<<(unsigned)n_utt, 32, 5 * kFeatMaxFrames * sizeof(double), st>>>(p);
         LAUNCH_CHECK("pitch_feature_kernel", st);
     }
     return DSPFE_OK;

@@ -47,7 +47,7 @@ constexpr int kWarpSmemBytes = kWarpScr * 8 + 512 * 8 + 512 * 16;   // transpose
 constexpr int kTabTw = 0, kTabW32 = kTabTw + kWarpScr, kTabMod = kTabW32 + 32, kTabHe = kTabMod + 512, kTabHo = kTabHe + 512,
               kTabTotal = kTabHo + 512;
 constexpr int kFrameCtaSmem = (kTabMod * 8) + kMaxDsOut * 4 + kPitchWarps * kWarpSmemBytes;   // shared tables | ds_idx | per-warp areas
-constexpr int kTrackThreads = 512;
+constexpr int kTrackThreads = 256;
 constexpr int kTrackChunk = 16;     // frames smoothed per pass of K4b/K5b
 
 struct PitchParams {
@@ -315,38 +315,47 @@ DEVFN float clip_value(float v, float med) {
     return 0.f;
 }
 
-// frame g -> utterance index: last u with frame_off[u] <= g
-DEVFN int find_utt(const int64_t* frame_off, int n_utt, int64_t g) {
+// frame g -> utterance index: last u with frame_off[u] <= g.  Warp-cooperative 32-ary search: three dependent loads
+// for up to 32768 utterances instead of log2(U) of them.
+DEVFN int find_utt(const int64_t* frame_off, int n_utt, int64_t g, int lane) {
     int lo = 0, hi = n_utt;   // invariant: frame_off[lo] <= g < frame_off[hi]
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frame_off[mid] <= g) lo = mid; else hi = mid; }
+    while (hi - lo > 1) {
+        const int stride = (hi - lo + 31) >> 5;
+        const int i = lo + lane * stride;                       // probes lo, lo + stride, ...
+        const bool le = i < hi && frame_off[i] <= g;            // true on a prefix of the lanes (lane 0 always)
+        const int c = warp_redux_add(le ? 1 : 0);
+        lo += (c - 1) * stride;
+        hi = lo + stride < hi ? lo + stride : hi;
+    }
     return lo;
 }
 
 // Gather one frame through the sample-picking decimator (preprocess.py:21-28), pre-emphasised over the whole
 // utterance (preprocess.py:11-19), zero padded past the decimated length (sigproc.py:84-87): x[t] = sample lane + 32 t.
 // Returns the lane's partial sum of |x| (sub_endpoint_detect, pitch.py:65).
-DEVFN float gather_frame(const PitchParams& p, int64_t g, const int32_t* ds_idx, float (&x)[16], int lane) {
-    const int u = find_utt(p.frame_off, p.n_utt, g);
-    const int64_t f = g - p.frame_off[u];
+DEVFN float gather_frame(const PitchParams& p, int64_t g, int u, const int32_t* ds_idx, float (&x)[16], int lane) {
+    const int f = (int)(g - p.frame_off[u]);
     const int64_t start = p.seg_start[u];
-    const int64_t ubase = p.offsets[u];
+    const int lim = (int)(p.offsets[u] - start);   // relative index of the utterance's first sample (<= 0)
     const int Ld = p.ds_len[u];
     const int L = p.frame_len;
-    const int64_t k0 = f * p.frame_step + lane;
+    const int k0 = f * p.frame_step + lane;
     // k - 1 = a * ds_out + b, advanced by 32 per step without a division; k0 = 0 starts from -1 = (-1, ds_out - 1)
-    int64_t a = k0 >= 1 ? (k0 - 1) / p.ds_out : -1;
-    int b = k0 >= 1 ? (int)((k0 - 1) - a * p.ds_out) : p.ds_out - 1;
+    int a = k0 >= 1 ? (k0 - 1) / p.ds_out : -1;
+    int b = k0 >= 1 ? (k0 - 1) - a * p.ds_out : p.ds_out - 1;
+    const int16_t* s16 = reinterpret_cast<const int16_t*>(p.pcm) + start;
+    const float* s32 = reinterpret_cast<const float*>(p.pcm) + start;
     float asum = 0.f;
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
         const int n = lane + 32 * t;
-        const int64_t k = k0 + 32 * t;
+        const int k = k0 + 32 * t;
         float v = 0.f;
         if (n < L && k < Ld) {
-            const int64_t s = start + (k == 0 ? 0 : a * p.ds_in + ds_idx[b]);   // packed-buffer sample index
+            const int s = k == 0 ? 0 : a * p.ds_in + ds_idx[b];   // sample index inside the (trimmed) utterance
             float cur, prev = 0.f;
-            if (p.in_f32) { cur = reinterpret_cast<const float*>(p.pcm)[s]; if (s > ubase) prev = reinterpret_cast<const float*>(p.pcm)[s - 1]; }
-            else { cur = cvt_i16(reinterpret_cast<const int16_t*>(p.pcm)[s]); if (s > ubase) prev = cvt_i16(reinterpret_cast<const int16_t*>(p.pcm)[s - 1]); }
+            if (p.in_f32) { cur = s32[s]; if (s > lim) prev = s32[s - 1]; }
+            else { cur = cvt_i16(s16[s]); if (s > lim) prev = cvt_i16(s16[s - 1]); }
             // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one
             v = p.pre_hi != 0.f ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
         }
@@ -364,7 +373,10 @@ DEVFN float gather_frame(const PitchParams& p, int64_t g, const int32_t* ds_idx,
 //     Xe = FFT512(x), Xo = FFT512(x W1024^n);  y[n] = (IFFT512(Xe He)[n] + W1024^-n IFFT512(Xo Ho)[n]) / 2
 // and for the cepstrum (pitch.py:135-143) the first inverse transform folds away:
 //     FFT512(y) = (Xe He + FFT512(W1024^-n IFFT512(Xo Ho))) / 2.
+// The transforms run as a rolled loop over stages (one copy of each routine in the instruction stream: the fully
+// inlined chain thrashed the instruction cache).  MODE 0 = cepstrum (5 transforms), 1 = autocorrelation (8).
 // wsm: per-warp shared memory = scr[kWarpScr] float2 | xs[512] float2 | park[512] float4.
+template <int MODE>
 DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws,
                             const float2* w32s, const int32_t* ds_idx) {
     const int lane = simt::tid() & 31;
@@ -376,168 +388,187 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
     const float2* HoB = p.tab + kTabHo;     // H1024[2k+1]
     const bool hasB = g0 + 1 < total;
     const int L = p.frame_len;
-    // ---- gather both frames; sum |x| of the raw frames in float64 across the warp
-    float xa[16], xb[16];
-    double sa = (double)gather_frame(p, g0, ds_idx, xa, lane), sb = 0.0;
-    if (hasB) sb = (double)gather_frame(p, g0 + 1, ds_idx, xb, lane);
-    else {
+    {
+        // ---- gather both frames; sum |x| of the raw frames in float64 across the warp
+        float xa[16], xb[16];
+        const int ua = find_utt(p.frame_off, p.n_utt, g0, lane);
+        double sa = (double)gather_frame(p, g0, ua, ds_idx, xa, lane), sb = 0.0;
+        if (hasB) sb = (double)gather_frame(p, g0 + 1, (g0 + 1 < p.frame_off[ua + 1]) ? ua : ua + 1, ds_idx, xb, lane);
+        else {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) xb[t] = 0.f;
-    }
-    if (p.frame_amp) {
+            for (int t = 0; t < 16; ++t) xb[t] = 0.f;
+        }
+        if (p.frame_amp) {
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
-        if (lane == 0) { p.frame_amp[g0] = sa; if (hasB) p.frame_amp[g0 + 1] = sb; }
-    }
-    // ---- centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
-    float2 med = make_float2(0.f, 0.f);
-    if (p.do_clip) med = warp_median_nonneg2(xa, xb, L, lane);
+            for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
+            if (lane == 0) { p.frame_amp[g0] = sa; if (hasB) p.frame_amp[g0 + 1] = sb; }
+        }
+        // ---- centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
+        float2 med = make_float2(0.f, 0.f);
+        if (p.do_clip) med = warp_median_nonneg2(xa, xb, L, lane);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const bool in = lane + 32 * t < L;
-        const float ca = p.do_clip ? clip_value(xa[t], med.x) : xa[t];
-        const float cb = p.do_clip ? clip_value(xb[t], med.y) : xb[t];
-        xs[32 * t + lane] = make_float2(in ? ca : 0.f, in ? cb : 0.f);
+        for (int t = 0; t < 16; ++t) {
+            const bool in = lane + 32 * t < L;
+            const float ca = p.do_clip ? clip_value(xa[t], med.x) : xa[t];
+            const float cb = p.do_clip ? clip_value(xb[t], med.y) : xb[t];
+            xs[32 * t + lane] = make_float2(in ? ca : 0.f, in ? cb : 0.f);
+        }
     }
     // (every lane only ever touches its own xs / park entries: no barrier needed around them)
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);
-    // ---- Xe = FFT512(x)
-#pragma unroll
-    for (int t = 0; t < 16; ++t) { x[t].re = xs[32 * t + lane]; x[t].im = zero2; }
-    fft512_AB(x, scr, tws, w32s, lane);
-    if (p.mode == 0) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {   // park Xe He / 2
-            const float2 h = ldg(HeB + r * 32 + lane);
-            const cpx2 v = cmuls(x[r], 0.5f * h.x, 0.5f * h.y);
-            park[r * 32 + lane] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) { const float2 h = ldg(HeB + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
-        ifft512_BA(x, scr, tws, w32s, lane);   // 512 * circular part of the convolution
-#pragma unroll
-        for (int t = 0; t < 16; ++t) park[32 * t + lane] = make_float4(x[t].re.x, x[t].re.y, x[t].im.x, x[t].im.y);
-    }
-    // ---- Xo = FFT512(x W1024^n), then d = IFFT512(Xo Ho)
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const float2 xv = xs[32 * t + lane], m = ldg(modA + 32 * t + lane);
-        x[t].re = f2muls(xv, m.x); x[t].im = f2muls(xv, m.y);
-    }
-    fft512_AB(x, scr, tws, w32s, lane);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) { const float2 h = ldg(HoB + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
-    ifft512_BA(x, scr, tws, w32s, lane);
     const float inv1024 = 1.0f / 1024.0f;
-    if (p.mode == 0) {
-        // ---- cepstrum: FFT512(y) = park + FFT512(W1024^-n d / 1024); log|.|; IFFT512; |.| / 512
+    constexpr int kStages = MODE == 0 ? 5 : 8;
+    // stage kinds: cepstrum  AB AB BA AB BA ; autocorrelation  AB BA AB BA AB BA AB BA
+#pragma unroll 1
+    for (int st = 0; st < kStages; ++st) {
+        const bool is_ba = MODE == 0 ? (st == 2 || st == 4) : (st & 1);
+        // ---- stage input
+        if (st == 0 || (MODE == 1 && st == 4)) {            // a real sequence from xs
 #pragma unroll
-        for (int t = 0; t < 16; ++t) { const float2 m = ldg(modA + 32 * t + lane); x[t] = cmuls(x[t], m.x * inv1024, -m.y * inv1024); }
-        fft512_AB(x, scr, tws, w32s, lane);
+            for (int t = 0; t < 16; ++t) { x[t].re = xs[32 * t + lane]; x[t].im = zero2; }
+        } else if ((MODE == 0 && st == 1) || (MODE == 1 && (st == 2 || st == 6))) {   // the same sequence times W1024^n
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const float4 pk = park[r * 32 + lane];
-            const float2 yr = f2add(x[r].re, make_float2(pk.x, pk.y)), yi = f2add(x[r].im, make_float2(pk.z, pk.w));
-            const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
-            x[r].re = make_float2(0.5f * dsp_fast_logf(s2.x), 0.5f * dsp_fast_logf(s2.y));
-            x[r].im = zero2;
-        }
-        ifft512_BA(x, scr, tws, w32s, lane);
-        const float inv512 = 1.0f / 512.0f;
-        float* rowa = p.rows + g0 * p.row_len;
-        float* rowb = rowa + p.row_len;
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int n = 32 * t + lane;
-            if (n < p.row_len) {
-                const float2 s2 = f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re));
-                rowa[n] = dsp_fast_sqrtf(s2.x) * inv512;
-                if (hasB) rowb[n] = dsp_fast_sqrtf(s2.y) * inv512;
+            for (int t = 0; t < 16; ++t) {
+                const float2 xv = xs[32 * t + lane], m = ldg(modA + 32 * t + lane);
+                x[t].re = f2muls(xv, m.x); x[t].im = f2muls(xv, m.y);
             }
         }
-    } else {
-        // ---- autocorrelation of v = |y| (pitch.py:112-132, sigproc.py:48-53): r = IFFT1024(|FFT1024(v)|^2), again
-        // through the even / odd bins: r[n] = (IFFT512(|Ve|^2)[n] + W1024^-n IFFT512(|Vo|^2)[n]) / 1024
+        if (is_ba) { swap_ri(x); fft512_BA(x, scr, tws, w32s, lane); swap_ri(x); }   // unnormalised inverse
+        else fft512_AB(x, scr, tws, w32s, lane);
+        // ---- stage output
+        if (MODE == 0) {
+            if (st == 0) {                                   // park Xe He / 2
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const float2 m = ldg(modA + 32 * t + lane);
-            const float4 pk = park[32 * t + lane];
-            const cpx2 d = cmuls(x[t], m.x, -m.y);
-            const float2 yr = f2add(d.re, make_float2(pk.x, pk.y)), yi = f2add(d.im, make_float2(pk.z, pk.w));
-            const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
-            const bool in = 32 * t + lane < L;
-            xs[32 * t + lane] = make_float2(in ? dsp_fast_sqrtf(s2.x) * inv1024 : 0.f, in ? dsp_fast_sqrtf(s2.y) * inv1024 : 0.f);
-        }
+                for (int r = 0; r < 16; ++r) {
+                    const float2 h = ldg(HeB + r * 32 + lane);
+                    const cpx2 v = cmuls(x[r], 0.5f * h.x, 0.5f * h.y);
+                    park[r * 32 + lane] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
+                }
+            } else if (st == 1) {                            // Xo Ho
 #pragma unroll
-        for (int t = 0; t < 16; ++t) { x[t].re = xs[32 * t + lane]; x[t].im = zero2; }
-        fft512_AB(x, scr, tws, w32s, lane);
+                for (int r = 0; r < 16; ++r) { const float2 h = ldg(HoB + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
+            } else if (st == 2) {                            // W1024^-n d / 1024
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { x[r].re = f2fma(x[r].im, x[r].im, f2mul(x[r].re, x[r].re)); x[r].im = zero2; }
-        ifft512_BA(x, scr, tws, w32s, lane);
-        float2* ge = reinterpret_cast<float2*>(park);   // real parts of the even-bin half, lags < 224
+                for (int t = 0; t < 16; ++t) { const float2 m = ldg(modA + 32 * t + lane); x[t] = cmuls(x[t], m.x * inv1024, -m.y * inv1024); }
+            } else if (st == 3) {                            // FFT512(y) = park + .; log|.|
 #pragma unroll
-        for (int t = 0; t < 7; ++t) ge[32 * t + lane] = x[t].re;
+                for (int r = 0; r < 16; ++r) {
+                    const float4 pk = park[r * 32 + lane];
+                    const float2 yr = f2add(x[r].re, make_float2(pk.x, pk.y)), yi = f2add(x[r].im, make_float2(pk.z, pk.w));
+                    const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
+                    x[r].re = make_float2(0.5f * dsp_fast_logf(s2.x), 0.5f * dsp_fast_logf(s2.y));
+                    x[r].im = zero2;
+                }
+            } else {                                         // |IFFT512| / 512 -> rows
+                const float inv512 = 1.0f / 512.0f;
+                float* rowa = p.rows + g0 * p.row_len;
+                float* rowb = rowa + p.row_len;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const float2 xv = xs[32 * t + lane], m = ldg(modA + 32 * t + lane);
-            x[t].re = f2muls(xv, m.x); x[t].im = f2muls(xv, m.y);
-        }
-        fft512_AB(x, scr, tws, w32s, lane);
+                for (int t = 0; t < 16; ++t) {
+                    const int n = 32 * t + lane;
+                    if (n < p.row_len) {
+                        const float2 s2 = f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re));
+                        rowa[n] = dsp_fast_sqrtf(s2.x) * inv512;
+                        if (hasB) rowb[n] = dsp_fast_sqrtf(s2.y) * inv512;
+                    }
+                }
+            }
+        } else {
+            // autocorrelation of v = |y| (pitch.py:112-132, sigproc.py:48-53): r = IFFT1024(|FFT1024(v)|^2), again through
+            // the even / odd bins: r[n] = (IFFT512(|Ve|^2)[n] + W1024^-n IFFT512(|Vo|^2)[n]) / 1024
+            if (st == 0 || st == 2) {                        // X He | Xo Ho
+                const float2* H = st == 0 ? HeB : HoB;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { x[r].re = f2fma(x[r].im, x[r].im, f2mul(x[r].re, x[r].re)); x[r].im = zero2; }
-        ifft512_BA(x, scr, tws, w32s, lane);
-        float* rowa = p.rows + g0 * p.row_len;
-        float* rowb = rowa + p.row_len;
+                for (int r = 0; r < 16; ++r) { const float2 h = ldg(H + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
+            } else if (st == 1) {                            // park the circular part
 #pragma unroll
-        for (int t = 0; t < 7; ++t) {
-            const int n = 32 * t + lane, j = n - kMinLag;
-            if (j >= 0 && j < p.row_len) {
-                const float2 m = ldg(modA + n);
-                // Re(conj(W1024^n) go[n]) = m.x go.re + m.y go.im
-                const float2 r = f2muls(f2add(ge[n], f2fmas(x[t].re, m.x, f2muls(x[t].im, m.y))), inv1024);
-                const float inv = (n < L) ? 1.0f / (float)(L - n) : NAN;
-                rowa[j] = r.x * inv;
-                if (hasB) rowb[j] = r.y * inv;
+                for (int t = 0; t < 16; ++t) park[32 * t + lane] = make_float4(x[t].re.x, x[t].re.y, x[t].im.x, x[t].im.y);
+            } else if (st == 3) {                            // v = |park + W1024^-n d| / 1024 -> xs
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const float2 m = ldg(modA + 32 * t + lane);
+                    const float4 pk = park[32 * t + lane];
+                    const cpx2 d = cmuls(x[t], m.x, -m.y);
+                    const float2 yr = f2add(d.re, make_float2(pk.x, pk.y)), yi = f2add(d.im, make_float2(pk.z, pk.w));
+                    const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
+                    const bool in = 32 * t + lane < L;
+                    xs[32 * t + lane] = make_float2(in ? dsp_fast_sqrtf(s2.x) * inv1024 : 0.f, in ? dsp_fast_sqrtf(s2.y) * inv1024 : 0.f);
+                }
+            } else if (st == 4 || st == 6) {                 // power spectrum
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { x[r].re = f2fma(x[r].im, x[r].im, f2mul(x[r].re, x[r].re)); x[r].im = zero2; }
+            } else if (st == 5) {                            // real parts of the even-bin half, lags < 224
+                float2* ge = reinterpret_cast<float2*>(park);
+#pragma unroll
+                for (int t = 0; t < 7; ++t) ge[32 * t + lane] = x[t].re;
+            } else {                                         // st == 7: combine, unbiased normalisation, rows
+                const float2* ge = reinterpret_cast<const float2*>(park);
+                float* rowa = p.rows + g0 * p.row_len;
+                float* rowb = rowa + p.row_len;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    const int n = 32 * t + lane, j = n - kMinLag;
+                    if (j >= 0 && j < p.row_len) {
+                        const float2 m = ldg(modA + n);
+                        // Re(conj(W1024^n) go[n]) = m.x go.re + m.y go.im
+                        const float2 r = f2muls(f2add(ge[n], f2fmas(x[t].re, m.x, f2muls(x[t].im, m.y))), inv1024);
+                        const float inv = (n < L) ? 1.0f / (float)(L - n) : NAN;
+                        rowa[j] = r.x * inv;
+                        if (hasB) rowb[j] = r.y * inv;
+                    }
+                }
             }
         }
     }
 }
 
-// K4b / K5b: one CTA (512 threads) per utterance, frames in order, kTrackChunk at a time.
-// smem: float chunk[kTrackChunk][row_len] + int sc[kTrackChunk][80].
-DEVFN void pitch_track_cta(const PitchParams& p, float* chunk, int* sc) {
+// K4b / K5b: one CTA (256 threads) per utterance, frames in order, kTrackChunk at a time.  Each pass first stages the
+// raw rows of the chunk (plus one row of look-ahead) in shared memory with coalesced vector loads, then runs the
+// reference's in-place running mean on them (one column per thread; rows < i are already smoothed, exactly the
+// reference's recurrence), scores the rows in parallel and takes the arg-max with one warp per row.
+// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80].
+DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc) {
     const int u = simt::bid();
     const int tid = simt::tid();
+    const int lane = tid & 31, warp = tid >> 5;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
     const int RL = p.row_len;
-    const bool col = tid < RL;
-    const float* base = p.rows + f0 * RL + tid;
-    float s1 = 0.f, s2 = 0.f;                 // smoothed rows i-1 and i-2 of this thread's column
-    float r0 = (col && F > 0) ? base[0] : 0.f;                 // raw rows i and i+1
-    float r1 = (col && F > 1) ? base[RL] : 0.f;
+    const float* rows = p.rows + f0 * RL;
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};    // smoothed rows i-1 and i-2 of this thread's (up to two) columns
     for (int c0 = 0; c0 < F; c0 += kTrackChunk) {
         const int nrows = F - c0 < kTrackChunk ? F - c0 : kTrackChunk;
-        if (col) {
-            for (int k = 0; k < nrows; ++k) {
-                const int i = c0 + k;
-                const float r2 = (i + 2 < F) ? base[(int64_t)(i + 2) * RL] : 0.f;   // prefetch
-                // smooth (pitch.py:157-164): g[i] = mean(g[left:right]) in place => rows < i are already smoothed.
-                // np.mean over axis 0 adds the rows in order, then divides by the count.
-                const int right = (i + 2 < F) ? i + 2 : F - 1;
-                const int left = i - 2 > 0 ? i - 2 : 0;
-                float acc = 0.f; bool any = false;
-                if (i - 2 >= 0 && i - 2 < right) { acc = s2; any = true; }
-                if (i - 1 >= 0 && i - 1 < right) { acc = any ? acc + s1 : s1; any = true; }
-                if (i < right) { acc = any ? acc + r0 : r0; any = true; }
-                if (i + 1 < right) { acc = any ? acc + r1 : r1; any = true; }
-                float gsm = any ? acc / (float)(right - left) : NAN;   // empty window: np.mean([]) = NaN
-                if (p.no_smooth) gsm = r0;
-                chunk[k * RL + tid] = gsm;
-                if (p.rows_out) p.rows_out[(f0 + i) * RL + tid] = gsm;
-                s2 = s1; s1 = gsm; r0 = r1; r1 = r2;
+        const int nload = (c0 + nrows < F ? nrows + 1 : nrows) * RL;          // floats to stage (rows are contiguous)
+        const float* src = rows + (int64_t)c0 * RL;
+        if ((RL & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            for (int i = tid; i < (nload >> 2); i += kTrackThreads) reinterpret_cast<float4*>(buf)[i] = reinterpret_cast<const float4*>(src)[i];
+        } else {
+            for (int i = tid; i < nload; i += kTrackThreads) buf[i] = src[i];
+        }
+        simt::cta_sync();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int col = tid + cc * kTrackThreads;
+            if (col < RL) {
+                for (int k = 0; k < nrows; ++k) {
+                    const int i = c0 + k;
+                    const float r0 = buf[k * RL + col];
+                    // smooth (pitch.py:157-164): g[i] = mean(g[left:right]) in place; np.mean over axis 0 adds the rows
+                    // in order, then divides by the count
+                    const int right = (i + 2 < F) ? i + 2 : F - 1;
+                    const int left = i - 2 > 0 ? i - 2 : 0;
+                    float acc = 0.f; bool any = false;
+                    if (i - 2 >= 0 && i - 2 < right) { acc = s2[cc]; any = true; }
+                    if (i - 1 >= 0 && i - 1 < right) { acc = any ? acc + s1[cc] : s1[cc]; any = true; }
+                    if (i < right) { acc = any ? acc + r0 : r0; any = true; }
+                    if (i + 1 < right) { const float r1 = buf[(k + 1) * RL + col]; acc = any ? acc + r1 : r1; any = true; }
+                    float gsm = any ? acc / (float)(right - left) : NAN;   // empty window: np.mean([]) = NaN
+                    if (p.no_smooth) gsm = r0;
+                    buf[k * RL + col] = gsm;
+                    if (p.rows_out) p.rows_out[(f0 + i) * RL + col] = gsm;
+                    s2[cc] = s1[cc]; s1[cc] = gsm;
+                }
             }
         }
         simt::cta_sync();
@@ -545,28 +576,32 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* chunk, int* sc) {
             // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk
             for (int t = tid; t < nrows * kPeakLags; t += kTrackThreads) {
                 const int k = t / kPeakLags, c = kMinLag + t % kPeakLags;
-                const float* row = chunk + k * RL;
+                const float* row = buf + k * RL;
                 const float v = row[c];
                 int pp = c; while (pp > 0 && row[pp] <= v) --pp;
                 // the right-hand scan matters only while it is shorter than the left-hand distance
                 int qmax = c + (c - pp); if (qmax > RL) qmax = RL;
                 int q = c; while (q < qmax && row[q] <= v) ++q;
-                const int s = (c - pp) < (q - c) ? (c - pp) : (q - c);
-                sc[t] = s;
-                if (p.score) p.score[(f0 + c0 + k) * kPeakLags + (c - kMinLag)] = s;
+                const int sv = (c - pp) < (q - c) ? (c - pp) : (q - c);
+                sc[t] = sv;
+                if (p.score) p.score[(f0 + c0 + k) * kPeakLags + (c - kMinLag)] = sv;
             }
             simt::cta_sync();
-            if (tid < nrows) {   // first argmax (pitch.py:169)
-                const int* s = sc + tid * kPeakLags;
-                int best = 0;
-                for (int t = 1; t < kPeakLags; ++t) if (s[t] > s[best]) best = t;
-                p.lag[f0 + c0 + tid] = kMinLag + best;
+            for (int k = warp; k < nrows; k += kTrackThreads / 32) {   // first argmax (pitch.py:169), one warp per row
+                const int* srow = sc + k * kPeakLags;
+                int bv = -1, bi = 0;
+                for (int t = lane; t < kPeakLags; t += 32) if (srow[t] > bv) { bv = srow[t]; bi = t; }
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    const int ov = simt::shfl32_i(bv, lane ^ m), oi = simt::shfl32_i(bi, lane ^ m);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) p.lag[f0 + c0 + k] = kMinLag + bi;
             }
         } else {
             // np.argmax over the smoothed scores, one warp per row: first maximum, a NaN counts as the maximum
-            const int k = tid >> 5, lane = tid & 31;
-            if (k < nrows) {
-                const float* row = chunk + k * RL;
+            for (int k = warp; k < nrows; k += kTrackThreads / 32) {
+                const float* row = buf + k * RL;
                 float bv = 0.f; int bi = -1;
                 for (int j = lane; j < RL; j += 32) {
                     const float v = row[j];
@@ -593,11 +628,73 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* chunk, int* sc) {
     if (tid == 0 && F > 0 && p.pitch) robust_pitch(p.lag + f0, F, p.pitch + f0);
 }
 
-// K6: pitch_feature tail, one thread per utterance
-DEVFN void pitch_feature_thread(const PitchParams& p, int u) {
+// K6: pitch_feature tail, one warp per utterance.  The utterance's pitch track and frame amplitudes are staged in
+// shared memory; the valley search and the two medians run across the lanes, the sequential list logic on lane 0.
+// smem: 5 * kFeatMaxFrames doubles.  Longer utterances fall back to lane 0 walking global memory.
+constexpr int kFeatMaxFrames = 640;
+DEVFN double warp_kth(const double* v, int n, int k, int lane) {   // k-th smallest (0-based) by rank counting; n >= 1
+    double out = 0.0; int found = 0;
+    for (int e = lane; e < n; e += 32) {
+        const double x = v[e];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (v[j] < x || (v[j] == x && j < e)) ? 1 : 0;
+        if (rank == k) { out = x; found = 1; }
+    }
+    // exactly one lane found it
+    const int src = __builtin_ffs((int)simt::ballot32(found != 0)) - 1;
+    return shfl32_f64(out, src);
+}
+DEVFN void pitch_feature_warp(const PitchParams& p, int u, double* sm) {
+    const int lane = simt::tid() & 31;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
-    pitch_feature_tail(p.pitch + f0, p.frame_amp + f0, F, p.scratch + 3 * f0, p.feat + 5 * (int64_t)u);
+    double* out5 = p.feat + 5 * (int64_t)u;
+    if (F > kFeatMaxFrames) {
+        if (lane == 0) pitch_feature_tail(p.pitch + f0, p.frame_amp + f0, F, p.scratch + 3 * f0, out5);
+        return;
+    }
+    double* pitch = sm; double* amp = sm + kFeatMaxFrames; double* s1 = amp + kFeatMaxFrames; double* s2 = s1 + kFeatMaxFrames;
+    double* tmp = s2 + kFeatMaxFrames;
+    for (int i = lane; i < F; i += 32) { pitch[i] = p.pitch[f0 + i]; amp[i] = p.frame_amp[f0 + i]; }
+    simt::warp_sync();
+    // sub_endpoint_detect (pitch.py:64-81): the first index attaining the largest valley score (> -1000), else F/2
+    double bs = -1000.0; int bi = 0;
+    for (int i = 10 + lane; i < F - 10; i += 32) {
+        bool lower = false;
+        for (int j = i - 2; j <= i + 2; ++j) lower = lower || (amp[j] < amp[i]);
+        if (lower) continue;
+        double sc = 0;
+        for (int j = i - 10; j <= i + 10; ++j) sc += amp[j] - amp[i];
+        if (sc > bs) { bs = sc; bi = i; }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const double os = shfl32_xor_f64(bs, m);
+        const int oi = simt::shfl32_i(bi, lane ^ m);
+        if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    const int pv = bi == 0 ? F / 2 : bi;
+    const int p_bias = pv > 15 ? 5 : 0;
+    // find_smooth_subsequence on both halves (sequential), lanes 0 and 1 take one half each
+    int n1 = 0, n2 = 0;
+    {
+        int a, b, n = 0;
+        if (lane == 0) n = smooth_run(pitch + p_bias, pv - p_bias, 3, 30.0, s1, tmp, &a, &b);
+        if (lane == 1) n = smooth_run(pitch + pv, F - pv, 3, 30.0, s2, tmp + pv, &a, &b);   // lane 0 uses at most pv entries of tmp
+        n1 = simt::shfl32_i(n, 0); n2 = simt::shfl32_i(n, 1);
+    }
+    simt::warp_sync();
+    if (n1 < 3 || n2 < 3) { if (lane < 5) out5[lane] = NAN; return; }
+    double r = 0.0;
+    if (lane == 0) r = ls_slope(s1, n1);
+    if (lane == 1) r = ls_slope(s2, n2);
+    if (lane == 2) r = ls_quad(s1, n1);
+    if (lane == 3) r = ls_quad(s2, n2);
+    if (lane < 4) out5[lane] = r;
+    // np.median of both runs by rank counting across the lanes
+    const double m1 = 0.5 * (warp_kth(s1, n1, (n1 - 1) >> 1, lane) + warp_kth(s1, n1, n1 >> 1, lane));
+    const double m2 = 0.5 * (warp_kth(s2, n2, (n2 - 1) >> 1, lane) + warp_kth(s2, n2, n2 >> 1, lane));
+    if (lane == 0) out5[4] = m2 - m1;   // peakshift(seq1, seq2) = median(seq2) - median(seq1)
 }
 
 }  // namespace dspfe

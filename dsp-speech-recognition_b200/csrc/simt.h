@@ -28,6 +28,7 @@ void group_sync();                 // barrier over the caller's 16-lane group
 float shfl16(float v, int src);    // __shfl_sync(halfmask, v, src, 16)
 float shfl32_xor(float v, int m);  // full-warp xor shuffle
 int shfl32_i(int v, int src);
+unsigned ballot32(bool pred);      // __ballot_sync(full mask, pred)
 void warp_sync();                  // __syncwarp()
 struct mbar_t { uint64_t v; };
 static inline void mbar_init(mbar_t*, int) {}
@@ -68,6 +69,7 @@ DEVFN void group_sync() { __syncwarp(); }
 DEVFN float shfl16(float v, int src) { return __shfl_sync(0xffffffffu, v, src, 16); }
 DEVFN float shfl32_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEVFN int shfl32_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+DEVFN unsigned ballot32(bool pred) { return __ballot_sync(0xffffffffu, pred); }
 DEVFN void warp_sync() { __syncwarp(); }
 
 // mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP): global -> shared::cta.
@@ -143,6 +145,17 @@ DEVFN unsigned warp_redux_min(unsigned v) {
 // float64 xor-shuffle over the full warp (two 32-bit shuffles)
 DEVFN double shfl32_xor_f64(double v, int m) {
     const int src = (simt::tid() & 31) ^ m;
+#ifdef DSPFE_EMU
+    int w[2]; std::memcpy(w, &v, 8);
+    w[0] = simt::shfl32_i(w[0], src); w[1] = simt::shfl32_i(w[1], src);
+    double r; std::memcpy(&r, w, 8); return r;
+#else
+    return __hiloint2double(simt::shfl32_i(__double2hiint(v), src), simt::shfl32_i(__double2loint(v), src));
+#endif
+}
+
+// float64 from a given lane
+DEVFN double shfl32_f64(double v, int src) {
 #ifdef DSPFE_EMU
     int w[2]; std::memcpy(w, &v, 8);
     w[0] = simt::shfl32_i(w[0], src); w[1] = simt::shfl32_i(w[1], src);

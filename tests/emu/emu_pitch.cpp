@@ -20,13 +20,19 @@ void frame_body(void* a) {
     const int64_t g0 = 2 * ((int64_t)simt::bid() * kPitchWarps + w);
     if (g0 >= A->total_frames) return;
     // the device kernel stages the twiddles and the decimator pattern in shared memory; the emulator reads them in place
-    pitch_frame_pair(A->p, g0, A->total_frames, A->smem->data() + w * kWarpSmemBytes, A->p.tab, A->p.tab + kTabW32, A->p.ds_idx);
+    unsigned char* wsm = A->smem->data() + w * kWarpSmemBytes;
+    if (A->p.mode == 0) pitch_frame_pair<0>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32, A->p.ds_idx);
+    else pitch_frame_pair<1>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32, A->p.ds_idx);
 }
 void track_body(void* a) {
     Args* A = (Args*)a;
     float* chunk = reinterpret_cast<float*>(A->smem->data());
-    int* sc = reinterpret_cast<int*>(chunk + kTrackChunk * A->p.row_len);
+    int* sc = reinterpret_cast<int*>(chunk + (kTrackChunk + 1) * A->p.row_len);
     pitch_track_cta(A->p, chunk, sc);
+}
+void feature_body(void* a) {
+    Args* A = (Args*)a;
+    pitch_feature_warp(A->p, simt::bid(), reinterpret_cast<double*>(A->smem->data()));
 }
 }  // namespace
 
@@ -70,12 +76,19 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
         std::memset(smem.data(), 0xCD, smem.size());
         if (!emu::run_cta((int)b, 32 * kPitchWarps, frame_body, &A)) { std::snprintf(errbuf, errcap, "deadlock in frame CTA %lld", (long long)b); return -3; }
     }
-    std::vector<unsigned char> smem2(kTrackChunk * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + 64);
+    std::vector<unsigned char> smem2((kTrackChunk + 1) * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + 64);
     Args B{p, &smem2, fo};
     for (int u = 0; u < n_utt; ++u) {
         std::memset(smem2.data(), 0xCD, smem2.size());
         if (!emu::run_cta(u, kTrackThreads, track_body, &B)) { std::snprintf(errbuf, errcap, "deadlock in track CTA %d", u); return -3; }
     }
-    if (feat) for (int u = 0; u < n_utt; ++u) pitch_feature_thread(p, u);
+    if (feat) {
+        std::vector<unsigned char> smem3(5 * kFeatMaxFrames * sizeof(double) + 64);
+        Args C{p, &smem3, fo};
+        for (int u = 0; u < n_utt; ++u) {
+            std::memset(smem3.data(), 0xCD, smem3.size());
+            if (!emu::run_cta(u, 32, feature_body, &C)) { std::snprintf(errbuf, errcap, "deadlock in feature CTA %d", u); return -3; }
+        }
+    }
     return fo;
 }

@@ -100,4 +100,9 @@ int shfl32_i(int v, int src) {
     int o; std::memcpy(&o, &r, 4);
     return o;
 }
+unsigned ballot32(bool pred) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (unsigned)(shfl32_i(pred ? 1 : 0, l) != 0) << l;
+    return m;
+}
 }  // namespace simt

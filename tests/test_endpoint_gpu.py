@@ -38,7 +38,7 @@ def test_random_ragged_vs_oracle():
     from dspfe import synth
     from oracle import ref_features as O
     lengths = synth.ragged_lengths(192, seed=3)
-    lengths[:6] = [1, 479, 480, 481, 640, 8000]
+    lengths[:7] = [1, 479, 480, 481, 640, 8000, 180000]   # the last one has more frames than the decision kernel stages
     pcm, off = synth.synth_batch(lengths, seed0=5000)
     lr, asum, zcr, fo = dspfe.EndpointPlan().detect_host(pcm, off, want_features=True)
     mism = 0

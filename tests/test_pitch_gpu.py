@@ -53,7 +53,7 @@ def test_ragged_batch_vs_oracle(method):
     from dspfe import synth
     from oracle import ref_features as O
     lengths = synth.ragged_lengths(24, seed=21, lo=8000, hi=40000)
-    lengths[:5] = [1, 700, 1000, 819, 8001]
+    lengths[:6] = [1, 700, 1000, 819, 8001, 110000]   # the last one exceeds the feature kernel's staged frame count
     pcm, off = synth.synth_batch(lengths, seed0=4200)
     pitch, lag, fo = dspfe.PitchPlan(method=method).detect_host(pcm, off)
     ref_fn = O.pitch_detect if method == 0 else O.pitch_detect_sr
