@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid
     extern __shared__ __align__(16) unsigned char smem[];
     float* chunk = reinterpret_cast<float*>(smem);
     int* sc = reinterpret_cast<int*>(chunk + (kTrackChunk + 1) * p.row_len);
-    pitch_track_cta(p, chunk, sc);
+    pitch_track_cta(p, chunk, sc, reinterpret_cast<double*>(sc + kTrackChunk * kPeakLags));
 }
 
 __global__ void __launch_bounds__(32) pitch_feature_kernel(const __grid_constant__ PitchParams p) {
@@ -145,7 +145,7 @@ int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
     return DSPFE_OK;
 }
 
-int track_smem(int row_len) { return (kTrackChunk + 1) * row_len * (int)sizeof(float) + kTrackChunk * kPeakLags * (int)sizeof(int); }
+int track_smem(int row_len) { return (kTrackChunk + 1) * row_len * (int)sizeof(float) + kTrackChunk * kPeakLags * (int)sizeof(int) + kTrackMaxFrames * 12; }
 
 }  // namespace
 
@@ -310,7 +310,7 @@ int dspfe_center_clip_f32(const float* d_in, int64_t n_rows, int32_t len, int32_
 int dspfe_track_rows_f32(const float* d_rows, int64_t n_rows, int32_t row_len, int32_t mode, int32_t do_smooth, float* d_smoothed,
                          int32_t* d_score, int32_t* d_lag, void* stream) {
     if (!d_rows || n_rows < 1 || row_len < 1 || (mode != 0 && mode != 1)) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
-    if (row_len > kTrackThreads) return fail(DSPFE_ERR_UNSUPPORTED, "rows longer than 512 columns are not built");
+    if (row_len > 2 * kTrackThreads) return fail(DSPFE_ERR_UNSUPPORTED, "rows longer than 512 columns are not built");
     if (mode == 0 && (d_score || d_lag) && row_len < kMinLag + kPeakLags) return fail(DSPFE_ERR_INVALID_ARG, "peak_score needs rows of at least 100 columns");
     cudaStream_t st = (cudaStream_t)stream;
     int64_t* d_fo = nullptr; int32_t* d_lag_tmp = nullptr;

@@ -48,6 +48,7 @@ constexpr int kTabTw = 0, kTabW32 = kTabTw + kWarpScr, kTabMod = kTabW32 + 32, k
               kTabTotal = kTabHo + 512;
 constexpr int kFrameCtaSmem = (kTabMod * 8) + kMaxDsOut * 4 + kPitchWarps * kWarpSmemBytes;   // shared tables | ds_idx | per-warp areas
 constexpr int kTrackThreads = 256;
+constexpr int kTrackMaxFrames = 1024;   // utterances up to this many frames keep their lag / Hz track in shared memory
 constexpr int kTrackChunk = 16;     // frames smoothed per pass of K4b/K5b
 
 struct PitchParams {
@@ -527,8 +528,8 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
 // raw rows of the chunk (plus one row of look-ahead) in shared memory with coalesced vector loads, then runs the
 // reference's in-place running mean on them (one column per thread; rows < i are already smoothed, exactly the
 // reference's recurrence), scores the rows in parallel and takes the arg-max with one warp per row.
-// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80].
-DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc) {
+// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80] + double spitch[kTrackMaxFrames] + int slag[kTrackMaxFrames].
+DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* spitch) {
     const int u = simt::bid();
     const int tid = simt::tid();
     const int lane = tid & 31, warp = tid >> 5;
@@ -536,6 +537,11 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc) {
     const int F = (int)(p.frame_off[u + 1] - f0);
     const int RL = p.row_len;
     const float* rows = p.rows + f0 * RL;
+    // the lag track stays in shared memory for the octave-repair sweeps (a thread walking global memory on its own
+    // pays a DRAM latency per frame); longer utterances use the global arrays directly
+    int32_t* slag = reinterpret_cast<int32_t*>(spitch + kTrackMaxFrames);
+    const bool staged = F <= kTrackMaxFrames;
+    int32_t* lagv = staged ? slag : p.lag + f0;
     float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};    // smoothed rows i-1 and i-2 of this thread's (up to two) columns
     for (int c0 = 0; c0 < F; c0 += kTrackChunk) {
         const int nrows = F - c0 < kTrackChunk ? F - c0 : kTrackChunk;
@@ -596,7 +602,7 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc) {
                     const int ov = simt::shfl32_i(bv, lane ^ m), oi = simt::shfl32_i(bi, lane ^ m);
                     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
-                if (lane == 0) p.lag[f0 + c0 + k] = kMinLag + bi;
+                if (lane == 0) lagv[c0 + k] = kMinLag + bi;
             }
         } else {
             // np.argmax over the smoothed scores, one warp per row: first maximum, a NaN counts as the maximum
@@ -620,12 +626,21 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc) {
                     else take = ov > bv || (ov == bv && oi < bi);
                     if (take) { bv = ov; bi = oi; }
                 }
-                if (lane == 0) p.lag[f0 + c0 + k] = kMinLag + (bi < 0 ? 0 : bi);
+                if (lane == 0) lagv[c0 + k] = kMinLag + (bi < 0 ? 0 : bi);
             }
         }
         simt::cta_sync();
     }
-    if (tid == 0 && F > 0 && p.pitch) robust_pitch(p.lag + f0, F, p.pitch + f0);
+    if (!staged) {
+        if (tid == 0 && F > 0 && p.pitch) robust_pitch(p.lag + f0, F, p.pitch + f0);
+        return;
+    }
+    if (tid == 0 && p.pitch) robust_pitch(slag, F, spitch);
+    simt::cta_sync();
+    for (int i = tid; i < F; i += kTrackThreads) {
+        p.lag[f0 + i] = slag[i];
+        if (p.pitch) p.pitch[f0 + i] = spitch[i];
+    }
 }
 
 // K6: pitch_feature tail, one warp per utterance.  The utterance's pitch track and frame amplitudes are staged in
