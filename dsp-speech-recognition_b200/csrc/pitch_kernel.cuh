@@ -40,11 +40,10 @@ constexpr int kMinLag = 20;
 constexpr int kPeakLags = 80;       // peak_score evaluates lags 20..99 (pitch.py:232)
 constexpr int kMaxDsOut = 256;      // decimator pattern length limit
 constexpr int kPitchWarps = 4;      // warps per CTA in K4a/K5a, each carrying a pair of frames
-constexpr int kTwStride = 34;       // row stride (float2) of the twiddle table and the transpose tile: conflict-free both ways
-constexpr int kWarpScr = 16 * kTwStride;
+constexpr int kWarpScr = 2 * 16 * 17;   // two padded 16x16 transpose tiles (float2), one per half-warp
 constexpr int kWarpSmemBytes = kWarpScr * 8 + 512 * 8 + 512 * 16;   // transpose tile | clipped frame pair | parked spectrum
 // table blob offsets, in float2
-constexpr int kTabTw = 0, kTabW32 = kTabTw + kWarpScr, kTabMod = kTabW32 + 32, kTabHe = kTabMod + 512, kTabHo = kTabHe + 512,
+constexpr int kTabTw = 0, kTabW32 = kTabTw + 512, kTabMod = kTabW32 + 32, kTabHe = kTabMod + 512, kTabHo = kTabHe + 512,
               kTabTotal = kTabHo + 512;
 constexpr int kFrameCtaSmem = (kTabMod * 8) + kMaxDsOut * 4 + kPitchWarps * kWarpSmemBytes;   // shared tables | ds_idx | per-warp areas
 constexpr int kTrackThreads = 256;
@@ -184,84 +183,48 @@ DSP_HD bool pitch_feature_tail(const double* pitch, const double* amp, int F, do
 // ---------------------------------------------------------------------------------------------------------
 // warp-cooperative pieces (device + emulator)
 // ---------------------------------------------------------------------------------------------------------
-// 512-point complex FFT of a packed frame pair, one warp, 16 complex values per lane, 512 = 16 x 16 x 2:
-// radix-16 in registers, twiddle, transpose through shared memory, radix-16 in registers, radix-2 across lane pairs.
-//   layout A (time side):      element n = 32*n1 + n2        -> lane n2, register n1
-//   layout B (frequency side): element k = k1 + 16*r + 256*s -> lane 2*k1 + s, register r
-// fft512_AB is decimation in frequency (A -> B), fft512_BA decimation in time (B -> A); both compute the FORWARD
-// DFT sum x[j] W512^{jk}.  The inverse is the same routine on (im, re)-swapped data (swap, forward, swap), so the
-// chain FFT -> pointwise -> IFFT -> pointwise -> FFT ... never needs a reordering pass.
+// 512-point complex FFT of a packed frame pair, one warp, 16 complex values per lane, 512 = 16 x 2 x 16:
+//   element n = 32*n1 + 16*q + n2'  ->  lane 16*q + n2', register n1   (natural order: n = 32*register + lane)
+// radix-16 in registers over n1, radix-2 across the two half-warps (one shuffle), twiddle, a 16x16 transpose inside each
+// half-warp through shared memory, radix-16 in registers over n2'.  With the radix-2 stage in the middle the output
+// lands in the SAME layout (k = k1 + 16*kq + 32*k2' -> lane 16*kq + k1, register k2'), so one routine serves every
+// transform of the chain and all pointwise tables are in natural order.  Forward DFT sum x[n] W512^{nk}; the
+// unnormalised inverse is the same routine between two conjugations.
 DEVFN cpx2 shfl_xor_c(cpx2 a, int m) {
     cpx2 r;
     r.re.x = simt::shfl32_xor(a.re.x, m); r.re.y = simt::shfl32_xor(a.re.y, m);
     r.im.x = simt::shfl32_xor(a.im.x, m); r.im.y = simt::shfl32_xor(a.im.y, m);
     return r;
 }
-DEVFN void swap_ri(cpx2 (&x)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { const float2 t = x[i].re; x[i].re = x[i].im; x[i].im = t; }
-}
 
-// tws: W512^{k1*n2} at [k1*kTwStride + n2]; w32s: [2r] = 1, [2r+1] = W32^r; scr: kWarpScr float2 owned by the warp
-DEVFN void fft512_AB(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
-    dft16(x);                                                   // over n1 -> k1 (lane = n2)
+// tws: W512^{n2' (k1 + 16 kq)} at [k1*32 + lane]; w32s: [2*k1 + q] = W32^{q k1}; scr: kWarpScr float2 owned by the warp
+DEVFN void fft512(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
+    dft16(x);                                                   // over n1 -> k1
+    const int q = lane >> 4, ll = lane & 15;
+    const float sg = q ? -1.f : 1.f;
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) { const float2 w = tws[k1 * kTwStride + lane]; x[k1] = cmuls(x[k1], w.x, w.y); }
-    const int rb = (lane >> 1) * kTwStride + (lane & 1);      // lane (k1, p) reads a[k1][2m + p]
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * kTwStride + lane] = x[k1].re;
-    simt::warp_sync();
-#pragma unroll
-    for (int m = 0; m < 16; ++m) x[m].re = scr[rb + 2 * m];
-    simt::warp_sync();
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * kTwStride + lane] = x[k1].im;
-    simt::warp_sync();
-#pragma unroll
-    for (int m = 0; m < 16; ++m) x[m].im = scr[rb + 2 * m];
-    simt::warp_sync();
-    dft16(x);                                                   // over m -> r
-    const int p = lane & 1;
-    const float sg = p ? -1.f : 1.f;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {                              // X[k1+16r] = B0 + W32^r B1, X[k1+16r+256] = B0 - W32^r B1
-        const float2 w = w32s[2 * r + p];
-        const cpx2 u = cmuls(x[r], w.x, w.y);
-        const cpx2 v = shfl_xor_c(u, 1);
-        x[r].re = f2fmas(u.re, sg, v.re); x[r].im = f2fmas(u.im, sg, v.im);
+    for (int k1 = 0; k1 < 16; ++k1) {                           // b[kq] = a[q=0] + (-1)^kq W32^k1 a[q=1]
+        const float2 w = w32s[2 * k1 + q];
+        const cpx2 u = cmuls(x[k1], w.x, w.y);
+        const cpx2 v = shfl_xor_c(u, 16);
+        cpx2 d; d.re = f2fmas(u.re, sg, v.re); d.im = f2fmas(u.im, sg, v.im);
+        const float2 t = tws[k1 * 32 + lane];
+        x[k1] = cmuls(d, t.x, t.y);
     }
-}
-
-DEVFN void fft512_BA(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
-    const int s = lane & 1;
-    const float sg = s ? -1.f : 1.f;
+    float2* tile = scr + q * (16 * 17);                         // (k1, n2') -> (n2', k1) inside the half-warp
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {                              // lane s=0: v0 + v1; lane s=1: (v0 - v1) W32^r
-        const cpx2 v = shfl_xor_c(x[r], 1);
-        cpx2 d; d.re = f2fmas(x[r].re, sg, v.re); d.im = f2fmas(x[r].im, sg, v.im);
-        const float2 w = w32s[2 * r + s];
-        x[r] = cmuls(d, w.x, w.y);
-    }
-    dft16(x);                                                   // over r -> m; lane (k1, p) now holds D[k1][n2 = 2m + p]
-    const int rb = (lane >> 1) * kTwStride + s;
-#pragma unroll
-    for (int m = 0; m < 16; ++m) { const float2 w = tws[rb + 2 * m]; x[m] = cmuls(x[m], w.x, w.y); }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) scr[rb + 2 * m] = x[m].re;
+    for (int k1 = 0; k1 < 16; ++k1) tile[k1 * 17 + ll] = x[k1].re;
     simt::warp_sync();
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) x[k1].re = scr[k1 * kTwStride + lane];
+    for (int n2 = 0; n2 < 16; ++n2) x[n2].re = tile[ll * 17 + n2];
     simt::warp_sync();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) scr[rb + 2 * m] = x[m].im;
+    for (int k1 = 0; k1 < 16; ++k1) tile[k1 * 17 + ll] = x[k1].im;
     simt::warp_sync();
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) x[k1].im = scr[k1 * kTwStride + lane];
+    for (int n2 = 0; n2 < 16; ++n2) x[n2].im = tile[ll * 17 + n2];
     simt::warp_sync();
-    dft16(x);                                                   // over k1 -> n1 (lane = n2)
-}
-DEVFN void ifft512_BA(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
-    swap_ri(x); fft512_BA(x, scr, tws, w32s, lane); swap_ri(x);   // unnormalised inverse
+    dft16(x);                                                   // over n2' -> k2'
 }
 
 // medians of the non-negative entries of two frames at once (np.median(frame[frame >= 0]), pitch.py:146): exact k-th
@@ -385,7 +348,7 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
     float2* xs = scr + kWarpScr;
     float4* park = reinterpret_cast<float4*>(xs + 512);
     const float2* modA = p.tab + kTabMod;   // W1024^n, n = 32 t + lane
-    const float2* HeB = p.tab + kTabHe;     // H1024[2k], layout B order [r*32 + lane]
+    const float2* HeB = p.tab + kTabHe;     // H1024[2k], k = 32 t + lane
     const float2* HoB = p.tab + kTabHo;     // H1024[2k+1]
     const bool hasB = g0 + 1 < total;
     const int L = p.frame_len;
@@ -420,48 +383,56 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
     const float2 zero2 = make_float2(0.f, 0.f);
     const float inv1024 = 1.0f / 1024.0f;
     constexpr int kStages = MODE == 0 ? 5 : 8;
-    // stage kinds: cepstrum  AB AB BA AB BA ; autocorrelation  AB BA AB BA AB BA AB BA
+    // cepstrum:         0 F(x)        -> park Xe He / 2        autocorrelation: 0 F(x)       -> Xe He
+    //                   1 F(x W^n)    -> Xo Ho                                  1 inverse    -> park
+    //                   2 inverse     -> W^-n d / 1024                          2 F(x W^n)   -> Xo Ho
+    //                   3 forward     -> + park, log|.|                         3 inverse    -> v = |park + W^-n d| / 1024 -> xs
+    //                   4 inverse     -> |.| / 512 -> rows                      4 F(v)       -> |Ve|^2      5 inverse -> keep Re
+    //                                                                           6 F(v W^n)   -> |Vo|^2      7 inverse -> rows
 #pragma unroll 1
     for (int st = 0; st < kStages; ++st) {
-        const bool is_ba = MODE == 0 ? (st == 2 || st == 4) : (st & 1);
-        // ---- stage input
-        if (st == 0 || (MODE == 1 && st == 4)) {            // a real sequence from xs
-#pragma unroll
-            for (int t = 0; t < 16; ++t) { x[t].re = xs[32 * t + lane]; x[t].im = zero2; }
-        } else if ((MODE == 0 && st == 1) || (MODE == 1 && (st == 2 || st == 6))) {   // the same sequence times W1024^n
+        const bool inv = MODE == 0 ? (st == 2 || st == 4) : (st & 1);
+        const bool load = MODE == 0 ? st <= 1 : !(st & 1);
+        const bool loadmod = MODE == 0 ? st == 1 : (st == 2 || st == 6);
+        if (load) {                                          // a real sequence from xs, optionally times W1024^n
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
-                const float2 xv = xs[32 * t + lane], m = ldg(modA + 32 * t + lane);
+                const float2 xv = xs[32 * t + lane];
+                float2 m = make_float2(1.f, 0.f);
+                if (loadmod) m = ldg(modA + 32 * t + lane);
                 x[t].re = f2muls(xv, m.x); x[t].im = f2muls(xv, m.y);
             }
         }
-        if (is_ba) { swap_ri(x); fft512_BA(x, scr, tws, w32s, lane); swap_ri(x); }   // unnormalised inverse
-        else fft512_AB(x, scr, tws, w32s, lane);
-        // ---- stage output
+        const float cj = inv ? -1.f : 1.f;                   // inverse = conj . forward . conj
+#pragma unroll
+        for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
+        fft512(x, scr, tws, w32s, lane);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
+        // ---- pointwise table products: He / Ho after a forward transform, conj(W1024^n) after the FIR's inverse
+        const bool mulH = MODE == 0 ? st <= 1 : (st == 0 || st == 2);
+        const bool mulM = MODE == 0 ? st == 2 : st == 3;
+        if (mulH || mulM) {
+            const float2* T = mulM ? modA : ((MODE == 0 ? st == 0 : st == 0) ? HeB : HoB);
+            const float sr = mulM ? (MODE == 0 ? inv1024 : 1.f) : ((MODE == 0 && st == 0) ? 0.5f : 1.f);
+            const float si = mulM ? -sr : sr;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) { const float2 h = ldg(T + 32 * t + lane); x[t] = cmuls(x[t], h.x * sr, h.y * si); }
+        }
         if (MODE == 0) {
             if (st == 0) {                                   // park Xe He / 2
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const float2 h = ldg(HeB + r * 32 + lane);
-                    const cpx2 v = cmuls(x[r], 0.5f * h.x, 0.5f * h.y);
-                    park[r * 32 + lane] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
-                }
-            } else if (st == 1) {                            // Xo Ho
-#pragma unroll
-                for (int r = 0; r < 16; ++r) { const float2 h = ldg(HoB + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
-            } else if (st == 2) {                            // W1024^-n d / 1024
-#pragma unroll
-                for (int t = 0; t < 16; ++t) { const float2 m = ldg(modA + 32 * t + lane); x[t] = cmuls(x[t], m.x * inv1024, -m.y * inv1024); }
+                for (int t = 0; t < 16; ++t) park[32 * t + lane] = make_float4(x[t].re.x, x[t].re.y, x[t].im.x, x[t].im.y);
             } else if (st == 3) {                            // FFT512(y) = park + .; log|.|
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const float4 pk = park[r * 32 + lane];
-                    const float2 yr = f2add(x[r].re, make_float2(pk.x, pk.y)), yi = f2add(x[r].im, make_float2(pk.z, pk.w));
+                for (int t = 0; t < 16; ++t) {
+                    const float4 pk = park[32 * t + lane];
+                    const float2 yr = f2add(x[t].re, make_float2(pk.x, pk.y)), yi = f2add(x[t].im, make_float2(pk.z, pk.w));
                     const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
-                    x[r].re = make_float2(0.5f * dsp_fast_logf(s2.x), 0.5f * dsp_fast_logf(s2.y));
-                    x[r].im = zero2;
+                    x[t].re = make_float2(0.5f * dsp_fast_logf(s2.x), 0.5f * dsp_fast_logf(s2.y));
+                    x[t].im = zero2;
                 }
-            } else {                                         // |IFFT512| / 512 -> rows
+            } else if (st == 4) {                            // |IFFT512| / 512 -> rows
                 const float inv512 = 1.0f / 512.0f;
                 float* rowa = p.rows + g0 * p.row_len;
                 float* rowb = rowa + p.row_len;
@@ -478,32 +449,26 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
         } else {
             // autocorrelation of v = |y| (pitch.py:112-132, sigproc.py:48-53): r = IFFT1024(|FFT1024(v)|^2), again through
             // the even / odd bins: r[n] = (IFFT512(|Ve|^2)[n] + W1024^-n IFFT512(|Vo|^2)[n]) / 1024
-            if (st == 0 || st == 2) {                        // X He | Xo Ho
-                const float2* H = st == 0 ? HeB : HoB;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) { const float2 h = ldg(H + r * 32 + lane); x[r] = cmuls(x[r], h.x, h.y); }
-            } else if (st == 1) {                            // park the circular part
+            if (st == 1) {                                   // park the circular part of the convolution
 #pragma unroll
                 for (int t = 0; t < 16; ++t) park[32 * t + lane] = make_float4(x[t].re.x, x[t].re.y, x[t].im.x, x[t].im.y);
             } else if (st == 3) {                            // v = |park + W1024^-n d| / 1024 -> xs
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const float2 m = ldg(modA + 32 * t + lane);
                     const float4 pk = park[32 * t + lane];
-                    const cpx2 d = cmuls(x[t], m.x, -m.y);
-                    const float2 yr = f2add(d.re, make_float2(pk.x, pk.y)), yi = f2add(d.im, make_float2(pk.z, pk.w));
+                    const float2 yr = f2add(x[t].re, make_float2(pk.x, pk.y)), yi = f2add(x[t].im, make_float2(pk.z, pk.w));
                     const float2 s2 = f2fma(yi, yi, f2mul(yr, yr));
                     const bool in = 32 * t + lane < L;
                     xs[32 * t + lane] = make_float2(in ? dsp_fast_sqrtf(s2.x) * inv1024 : 0.f, in ? dsp_fast_sqrtf(s2.y) * inv1024 : 0.f);
                 }
             } else if (st == 4 || st == 6) {                 // power spectrum
 #pragma unroll
-                for (int r = 0; r < 16; ++r) { x[r].re = f2fma(x[r].im, x[r].im, f2mul(x[r].re, x[r].re)); x[r].im = zero2; }
+                for (int t = 0; t < 16; ++t) { x[t].re = f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re)); x[t].im = zero2; }
             } else if (st == 5) {                            // real parts of the even-bin half, lags < 224
                 float2* ge = reinterpret_cast<float2*>(park);
 #pragma unroll
                 for (int t = 0; t < 7; ++t) ge[32 * t + lane] = x[t].re;
-            } else {                                         // st == 7: combine, unbiased normalisation, rows
+            } else if (st == 7) {                            // combine, unbiased normalisation, rows
                 const float2* ge = reinterpret_cast<const float2*>(park);
                 float* rowa = p.rows + g0 * p.row_len;
                 float* rowb = rowa + p.row_len;
@@ -514,9 +479,9 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
                         const float2 m = ldg(modA + n);
                         // Re(conj(W1024^n) go[n]) = m.x go.re + m.y go.im
                         const float2 r = f2muls(f2add(ge[n], f2fmas(x[t].re, m.x, f2muls(x[t].im, m.y))), inv1024);
-                        const float inv = (n < L) ? 1.0f / (float)(L - n) : NAN;
-                        rowa[j] = r.x * inv;
-                        if (hasB) rowb[j] = r.y * inv;
+                        const float inv_n = (n < L) ? 1.0f / (float)(L - n) : NAN;
+                        rowa[j] = r.x * inv_n;
+                        if (hasB) rowb[j] = r.y * inv_n;
                     }
                 }
             }

@@ -48,34 +48,31 @@ inline int build_pitch_tables(const dspfe_pitch_params& q, PitchParams& b, std::
     if (q.method == 0 && (b.row_len < kPeakLags + kMinLag || b.row_len > kCepLen)) { err = "row_len must be in 100..512"; return DSPFE_ERR_INVALID_ARG; }
     b.ds_q32 = 32 / b.ds_out; b.ds_r32 = 32 % b.ds_out;
     b.pre_hi = (float)q.preemph; b.pre_lo = (float)(q.preemph - (double)b.pre_hi);
-    // tables, float64 on the host, rounded once: W512^{k1 n2} (row stride kTwStride), W32^r, W1024^n, and the even /
-    // odd bins of the 1024-point spectrum of the FIR taps in the kernels' frequency-side register layout
+    // tables, float64 on the host, rounded once: the FFT twiddles, W1024^n and the even / odd bins of the 1024-point
+    // spectrum of the FIR taps, all in natural order
     const double kPi = 3.14159265358979323846;
     tab.assign(kTabTotal, make_float2(0.f, 0.f));
-    for (int k1 = 0; k1 < 16; ++k1)
-        for (int n2 = 0; n2 < 32; ++n2) {
-            const double a = -2 * kPi * (double)(k1 * n2) / 512.0;
-            tab[kTabTw + k1 * kTwStride + n2] = make_float2((float)cos(a), (float)sin(a));
+    for (int k1 = 0; k1 < 16; ++k1) {
+        for (int lane = 0; lane < 32; ++lane) {                   // W512^{n2' (k1 + 16 kq)}, lane = 16 kq + n2'
+            const int kq = lane >> 4, n2 = lane & 15;
+            const double a = -2 * kPi * (double)(n2 * (k1 + 16 * kq)) / 512.0;
+            tab[kTabTw + k1 * 32 + lane] = make_float2((float)cos(a), (float)sin(a));
         }
-    for (int r = 0; r < 16; ++r) {
-        tab[kTabW32 + 2 * r] = make_float2(1.f, 0.f);
-        tab[kTabW32 + 2 * r + 1] = make_float2((float)cos(-2 * kPi * r / 32.0), (float)sin(-2 * kPi * r / 32.0));
+        tab[kTabW32 + 2 * k1] = make_float2(1.f, 0.f);            // W32^{q k1}
+        tab[kTabW32 + 2 * k1 + 1] = make_float2((float)cos(-2 * kPi * k1 / 32.0), (float)sin(-2 * kPi * k1 / 32.0));
     }
     for (int n = 0; n < 512; ++n) tab[kTabMod + n] = make_float2((float)cos(-2 * kPi * n / 1024.0), (float)sin(-2 * kPi * n / 1024.0));
     std::vector<double> hr, hi;
     fir_taps(q.frame_len, (double)q.dst_rate, q.band_lo, q.band_hi, true, hr, hi);
-    for (int r = 0; r < 16; ++r)
-        for (int lane = 0; lane < 32; ++lane) {
-            const int k = (lane >> 1) + 16 * r + 256 * (lane & 1);   // layout B
-            for (int odd = 0; odd < 2; ++odd) {
-                const int k1024 = 2 * k + odd;
-                double sr = 0, si = 0;
-                for (int n = 0; n < q.frame_len; ++n) {
-                    const double a = -2 * kPi * (double)((long long)k1024 * n % kPitchFft) / kPitchFft, c = cos(a), s = sin(a);
-                    sr += hr[n] * c - hi[n] * s; si += hr[n] * s + hi[n] * c;
-                }
-                tab[(odd ? kTabHo : kTabHe) + r * 32 + lane] = make_float2((float)sr, (float)si);
+    for (int k = 0; k < 512; ++k)
+        for (int odd = 0; odd < 2; ++odd) {                       // even / odd bins of the 1024-point spectrum of the taps
+            const int k1024 = 2 * k + odd;
+            double sr = 0, si = 0;
+            for (int n = 0; n < q.frame_len; ++n) {
+                const double a = -2 * kPi * (double)((long long)k1024 * n % kPitchFft) / kPitchFft, c = cos(a), s_ = sin(a);
+                sr += hr[n] * c - hi[n] * s_; si += hr[n] * s_ + hi[n] * c;
             }
+            tab[(odd ? kTabHo : kTabHe) + k] = make_float2((float)sr, (float)si);
         }
     return 0;
 }
