@@ -246,10 +246,15 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], i
     unsigned Ka = 0, Kb = 0;
     for (int b = 30; b >= 0; --b) {
         const unsigned ta = Ka | ((1u << b) - 1u), tb = Kb | ((1u << b) - 1u);
-        int c = 0;
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;                   // independent partial counts: no 32-deep add chain
 #pragma unroll
-        for (int t = 0; t < 16; ++t) c += (ka[t] <= ta ? 1 : 0) + (kb[t] <= tb ? 0x10000 : 0);
-        c = warp_redux_add(c);
+        for (int t = 0; t < 16; t += 4) {
+            c0 += (ka[t] <= ta ? 1 : 0) + (kb[t] <= tb ? 0x10000 : 0);
+            c1 += (ka[t + 1] <= ta ? 1 : 0) + (kb[t + 1] <= tb ? 0x10000 : 0);
+            c2 += (ka[t + 2] <= ta ? 1 : 0) + (kb[t + 2] <= tb ? 0x10000 : 0);
+            c3 += (ka[t + 3] <= ta ? 1 : 0) + (kb[t + 3] <= tb ? 0x10000 : 0);
+        }
+        const int c = warp_redux_add((c0 + c1) + (c2 + c3));
         if ((c & 0xffff) < ra + 1) Ka |= 1u << b;
         if ((c >> 16) < rb + 1) Kb |= 1u << b;
     }
@@ -294,41 +299,41 @@ DEVFN int find_utt(const int64_t* frame_off, int n_utt, int64_t g, int lane) {
     return lo;
 }
 
-// Gather one frame through the sample-picking decimator (preprocess.py:21-28), pre-emphasised over the whole
-// utterance (preprocess.py:11-19), zero padded past the decimated length (sigproc.py:84-87): x[t] = sample lane + 32 t.
-// Returns the lane's partial sum of |x| (sub_endpoint_detect, pitch.py:65).
-DEVFN float gather_frame(const PitchParams& p, int64_t g, int u, const int32_t* ds_idx, float (&x)[16], int lane) {
-    const int f = (int)(g - p.frame_off[u]);
+// Source cursor of one frame for the gather through the sample-picking decimator (preprocess.py:21-28): the lane's
+// sample t sits at decimated index k = f*step + lane + 32 t, and k - 1 = a * ds_out + b is advanced by 32 per step
+// without a division (k = 0 starts from -1 = (-1, ds_out - 1)).
+struct FrameCursor {
+    const int16_t* s16; const float* s32;
+    int lim;      // relative index of the utterance's first sample (<= 0): pre-emphasis reaches back to it
+    int Ld, k, a, b;
+};
+DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane, bool valid) {
+    FrameCursor c;
     const int64_t start = p.seg_start[u];
-    const int lim = (int)(p.offsets[u] - start);   // relative index of the utterance's first sample (<= 0)
-    const int Ld = p.ds_len[u];
-    const int L = p.frame_len;
-    const int k0 = f * p.frame_step + lane;
-    // k - 1 = a * ds_out + b, advanced by 32 per step without a division; k0 = 0 starts from -1 = (-1, ds_out - 1)
-    int a = k0 >= 1 ? (k0 - 1) / p.ds_out : -1;
-    int b = k0 >= 1 ? (k0 - 1) - a * p.ds_out : p.ds_out - 1;
-    const int16_t* s16 = reinterpret_cast<const int16_t*>(p.pcm) + start;
-    const float* s32 = reinterpret_cast<const float*>(p.pcm) + start;
-    float asum = 0.f;
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const int n = lane + 32 * t;
-        const int k = k0 + 32 * t;
-        float v = 0.f;
-        if (n < L && k < Ld) {
-            const int s = k == 0 ? 0 : a * p.ds_in + ds_idx[b];   // sample index inside the (trimmed) utterance
-            float cur, prev = 0.f;
-            if (p.in_f32) { cur = s32[s]; if (s > lim) prev = s32[s - 1]; }
-            else { cur = cvt_i16(s16[s]); if (s > lim) prev = cvt_i16(s16[s - 1]); }
-            // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one
-            v = p.pre_hi != 0.f ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
-        }
-        x[t] = v;
-        asum += fabsf(v);
-        a += p.ds_q32; b += p.ds_r32;
-        if (b >= p.ds_out) { b -= p.ds_out; ++a; }
+    c.s16 = reinterpret_cast<const int16_t*>(p.pcm) + start;
+    c.s32 = reinterpret_cast<const float*>(p.pcm) + start;
+    c.lim = (int)(p.offsets[u] - start);
+    c.Ld = valid ? p.ds_len[u] : 0;
+    c.k = (int)(g - p.frame_off[u]) * p.frame_step + lane;
+    c.a = c.k >= 1 ? (c.k - 1) / p.ds_out : -1;
+    c.b = c.k >= 1 ? (c.k - 1) - c.a * p.ds_out : p.ds_out - 1;
+    return c;
+}
+// one sample: pre-emphasised over the whole utterance (preprocess.py:11-19), zero past the decimated length
+// (sigproc.py:84-87); then the cursor moves on by 32 decimated samples
+DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds_idx, int n) {
+    float v = 0.f;
+    if (n < p.frame_len && c.k < c.Ld) {
+        const int s = c.k == 0 ? 0 : c.a * p.ds_in + ds_idx[c.b];   // sample index inside the (trimmed) utterance
+        float cur, prev = 0.f;
+        if (p.in_f32) { cur = c.s32[s]; if (s > c.lim) prev = c.s32[s - 1]; }
+        else { cur = cvt_i16(c.s16[s]); if (s > c.lim) prev = cvt_i16(c.s16[s - 1]); }
+        // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one
+        v = p.pre_hi != 0.f ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
     }
-    return asum;
+    c.k += 32; c.a += p.ds_q32; c.b += p.ds_r32;
+    if (c.b >= p.ds_out) { c.b -= p.ds_out; ++c.a; }
+    return v;
 }
 
 // Two consecutive frames (g0, g0 + 1) per warp: gather + clip + FIR band-pass + (cepstrum | autocorrelation)
@@ -353,15 +358,27 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
     const bool hasB = g0 + 1 < total;
     const int L = p.frame_len;
     {
-        // ---- gather both frames; sum |x| of the raw frames in float64 across the warp
-        float xa[16], xb[16];
+        // ---- gather both frames into xs (a rolled loop, four samples per frame in flight: the fully unrolled form
+        // streamed 50 KB of straight-line code through the instruction cache per pair); sum |x| of the raw frames
+        // (sub_endpoint_detect, pitch.py:65) in float64 across the warp
         const int ua = find_utt(p.frame_off, p.n_utt, g0, lane);
-        double sa = (double)gather_frame(p, g0, ua, ds_idx, xa, lane), sb = 0.0;
-        if (hasB) sb = (double)gather_frame(p, g0 + 1, (g0 + 1 < p.frame_off[ua + 1]) ? ua : ua + 1, ds_idx, xb, lane);
-        else {
+        const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
+        FrameCursor ca = frame_cursor(p, g0, ua, lane, true), cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB);
+        float fa = 0.f, fb = 0.f;
+#pragma unroll 1
+        for (int t0 = 0; t0 < 16; t0 += 4) {
 #pragma unroll
-            for (int t = 0; t < 16; ++t) xb[t] = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const int n = 32 * (t0 + j) + lane;
+                const float va = frame_sample(p, ca, ds_idx, n), vb = frame_sample(p, cb, ds_idx, n);
+                xs[n] = make_float2(va, vb);
+                fa += fabsf(va); fb += fabsf(vb);
+            }
         }
+        float xa[16], xb[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { const float2 v = xs[32 * t + lane]; xa[t] = v.x; xb[t] = v.y; }
+        double sa = (double)fa, sb = (double)fb;
         if (p.frame_amp) {
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
@@ -493,8 +510,10 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
 // raw rows of the chunk (plus one row of look-ahead) in shared memory with coalesced vector loads, then runs the
 // reference's in-place running mean on them (one column per thread; rows < i are already smoothed, exactly the
 // reference's recurrence), scores the rows in parallel and takes the arg-max with one warp per row.
-// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80] + double spitch[kTrackMaxFrames] + int slag[kTrackMaxFrames].
+// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80] + double spitch[kTrackMaxFrames] + int slag[kTrackMaxFrames]
+//       + float bmax[kTrackChunk * 64].
 DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* spitch) {
+    float* bmax = reinterpret_cast<float*>(reinterpret_cast<int32_t*>(spitch + kTrackMaxFrames) + kTrackMaxFrames);   // [kTrackChunk * 64]
     const int u = simt::bid();
     const int tid = simt::tid();
     const int lane = tid & 31, warp = tid >> 5;
@@ -544,16 +563,44 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
         }
         simt::cta_sync();
         if (p.mode == 0) {
-            // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk
+            // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk: distance to the nearest sample
+            // that is not <= the lag's value, on either side.  Maxima over blocks of 8 columns (a NaN makes its block a
+            // stopper, as it stops the reference's scan) let the scans skip whole blocks.
+            const int nblk = (RL + 7) >> 3;
+            for (int t = tid; t < nrows * nblk; t += kTrackThreads) {
+                const int k = t / nblk, b = t - k * nblk;
+                const float* row = buf + k * RL + 8 * b;
+                const int n = RL - 8 * b < 8 ? RL - 8 * b : 8;
+                float m = -INFINITY; bool nan = false;
+                for (int j = 0; j < n; ++j) { const float v = row[j]; nan = nan || v != v; m = v > m ? v : m; }
+                bmax[t] = nan ? INFINITY : m;
+            }
+            simt::cta_sync();
             for (int t = tid; t < nrows * kPeakLags; t += kTrackThreads) {
                 const int k = t / kPeakLags, c = kMinLag + t % kPeakLags;
                 const float* row = buf + k * RL;
+                const float* bm = bmax + k * nblk;
                 const float v = row[c];
-                int pp = c; while (pp > 0 && row[pp] <= v) --pp;
-                // the right-hand scan matters only while it is shorter than the left-hand distance
-                int qmax = c + (c - pp); if (qmax > RL) qmax = RL;
-                int q = c; while (q < qmax && row[q] <= v) ++q;
-                const int sv = (c - pp) < (q - c) ? (c - pp) : (q - c);
+                int sv = 0;                                   // a NaN value stops both scans at once
+                if (v == v) {
+                    int pp = c - 1;
+                    while (pp > 0) {
+                        if ((pp & 7) == 7 && bm[pp >> 3] <= v) { pp -= 8; continue; }
+                        if (!(row[pp] <= v)) break;
+                        --pp;
+                    }
+                    if (pp < 0) pp = 0;
+                    // the right-hand scan matters only while it is shorter than the left-hand distance
+                    int qmax = c + (c - pp); if (qmax > RL) qmax = RL;
+                    int q = c + 1;
+                    while (q < qmax) {
+                        if ((q & 7) == 0 && bm[q >> 3] <= v) { q += 8; continue; }
+                        if (!(row[q] <= v)) break;
+                        ++q;
+                    }
+                    if (q > qmax) q = qmax;
+                    sv = (c - pp) < (q - c) ? (c - pp) : (q - c);
+                }
                 sc[t] = sv;
                 if (p.score) p.score[(f0 + c0 + k) * kPeakLags + (c - kMinLag)] = sv;
             }
