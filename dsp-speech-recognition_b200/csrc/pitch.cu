@@ -145,7 +145,7 @@ int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
     return DSPFE_OK;
 }
 
-int track_smem(int row_len) { return (kTrackChunk + 1) * row_len * (int)sizeof(float) + kTrackChunk * kPeakLags * (int)sizeof(int) + kTrackMaxFrames * 12 + kTrackChunk * 64 * 4; }
+int track_smem(int row_len) { return (kTrackChunk + 1) * row_len * (int)sizeof(float) + kTrackChunk * kPeakLags * (int)sizeof(int) + kTrackMaxFrames * 12; }
 
 }  // namespace
 

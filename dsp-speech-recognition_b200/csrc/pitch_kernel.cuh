@@ -510,10 +510,8 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
 // raw rows of the chunk (plus one row of look-ahead) in shared memory with coalesced vector loads, then runs the
 // reference's in-place running mean on them (one column per thread; rows < i are already smoothed, exactly the
 // reference's recurrence), scores the rows in parallel and takes the arg-max with one warp per row.
-// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80] + double spitch[kTrackMaxFrames] + int slag[kTrackMaxFrames]
-//       + float bmax[kTrackChunk * 64].
+// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80] + double spitch[kTrackMaxFrames] + int slag[kTrackMaxFrames].
 DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* spitch) {
-    float* bmax = reinterpret_cast<float*>(reinterpret_cast<int32_t*>(spitch + kTrackMaxFrames) + kTrackMaxFrames);   // [kTrackChunk * 64]
     const int u = simt::bid();
     const int tid = simt::tid();
     const int lane = tid & 31, warp = tid >> 5;
@@ -563,43 +561,20 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
         }
         simt::cta_sync();
         if (p.mode == 0) {
-            // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk: distance to the nearest sample
-            // that is not <= the lag's value, on either side.  Maxima over blocks of 8 columns (a NaN makes its block a
-            // stopper, as it stops the reference's scan) let the scans skip whole blocks.
-            const int nblk = (RL + 7) >> 3;
-            for (int t = tid; t < nrows * nblk; t += kTrackThreads) {
-                const int k = t / nblk, b = t - k * nblk;
-                const float* row = buf + k * RL + 8 * b;
-                const int n = RL - 8 * b < 8 ? RL - 8 * b : 8;
-                float m = -INFINITY; bool nan = false;
-                for (int j = 0; j < n; ++j) { const float v = row[j]; nan = nan || v != v; m = v > m ? v : m; }
-                bmax[t] = nan ? INFINITY : m;
-            }
-            simt::cta_sync();
+            // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk: min over both sides of the
+            // distance to the nearest sample that is not <= the lag's value (the left scan ends at index 0, the right
+            // one at the row end).  Only the smaller distance matters, so both sides expand together and the search
+            // ends at the first stopper on either side.
             for (int t = tid; t < nrows * kPeakLags; t += kTrackThreads) {
                 const int k = t / kPeakLags, c = kMinLag + t % kPeakLags;
                 const float* row = buf + k * RL;
-                const float* bm = bmax + k * nblk;
                 const float v = row[c];
                 int sv = 0;                                   // a NaN value stops both scans at once
                 if (v == v) {
-                    int pp = c - 1;
-                    while (pp > 0) {
-                        if ((pp & 7) == 7 && bm[pp >> 3] <= v) { pp -= 8; continue; }
-                        if (!(row[pp] <= v)) break;
-                        --pp;
-                    }
-                    if (pp < 0) pp = 0;
-                    // the right-hand scan matters only while it is shorter than the left-hand distance
-                    int qmax = c + (c - pp); if (qmax > RL) qmax = RL;
-                    int q = c + 1;
-                    while (q < qmax) {
-                        if ((q & 7) == 0 && bm[q >> 3] <= v) { q += 8; continue; }
-                        if (!(row[q] <= v)) break;
-                        ++q;
-                    }
-                    if (q > qmax) q = qmax;
-                    sv = (c - pp) < (q - c) ? (c - pp) : (q - c);
+                    const int rmax = c < RL - c ? c : RL - c; // index 0 / the row end stop the scans
+                    int r = 1;
+                    while (r < rmax && row[c - r] <= v && row[c + r] <= v) ++r;
+                    sv = r;
                 }
                 sc[t] = sv;
                 if (p.score) p.score[(f0 + c0 + k) * kPeakLags + (c - kMinLag)] = sv;

@@ -76,7 +76,7 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
         std::memset(smem.data(), 0xCD, smem.size());
         if (!emu::run_cta((int)b, 32 * kPitchWarps, frame_body, &A)) { std::snprintf(errbuf, errcap, "deadlock in frame CTA %lld", (long long)b); return -3; }
     }
-    std::vector<unsigned char> smem2((kTrackChunk + 1) * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + kTrackMaxFrames * 12 + kTrackChunk * 64 * 4 + 64);
+    std::vector<unsigned char> smem2((kTrackChunk + 1) * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + kTrackMaxFrames * 12 + 64);
     Args B{p, &smem2, fo};
     for (int u = 0; u < n_utt; ++u) {
         std::memset(smem2.data(), 0xCD, smem2.size());
