@@ -212,6 +212,7 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
         return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
     if (n_utt == 0) return DSPFE_OK;
     if (!d_pcm && total_samples > 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm is null");
+    if (((uintptr_t)d_pcm & 15) != 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm must be 16-byte aligned");
     const int64_t bound = dspfe_pitch_frames_bound(pl, total_samples, n_utt);
     if ((d_pitch || d_lag || d_rows) && max_frames < bound) return fail(DSPFE_ERR_INVALID_ARG, "max_frames is below dspfe_pitch_frames_bound()");
     if (d_feat && pl->base.mode != 0) return fail(DSPFE_ERR_UNSUPPORTED, "pitch_feature is defined on the cepstrum pitch (pitch.py:33)");
@@ -219,7 +220,7 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     PitchParams p = pl->base;
-    p.pcm = d_pcm; p.in_f32 = sample_dtype; p.offsets = d_offsets; p.trim = d_trim; p.n_utt = n_utt;
+    p.pcm = d_pcm; p.in_f32 = sample_dtype; p.total_samples = total_samples; p.offsets = d_offsets; p.trim = d_trim; p.n_utt = n_utt;
     p.frame_off = d_frame_off ? d_frame_off : pl->frame_off; p.seg_start = pl->seg_start; p.seg_len = pl->seg_len; p.ds_len = pl->ds_len;
     p.rows = d_rows ? d_rows : pl->rows; p.rows_out = nullptr; p.score = nullptr; p.frame_amp = pl->frame_amp;
     p.pitch = d_pitch ? d_pitch : pl->pitch; p.lag = d_lag ? d_lag : pl->lag; p.feat = d_feat; p.scratch = pl->scratch;

@@ -21,6 +21,9 @@
 
 #include "simt.h"
 #include "fft_regs.h"
+#ifndef DSPFE_EMU
+#include <cuda_fp16.h>
+#endif
 
 #ifndef DSP_HD
 #ifdef __CUDACC__
@@ -51,7 +54,8 @@ constexpr int kTrackMaxFrames = 1024;   // utterances up to this many frames kee
 constexpr int kTrackChunk = 16;     // frames smoothed per pass of K4b/K5b
 
 struct PitchParams {
-    const void* pcm; int in_f32;         // packed samples: int16 or float32
+    const void* pcm; int in_f32;         // packed samples: int16 or float32 (16-byte aligned base)
+    int64_t total_samples;
     const int64_t* offsets;              // [U+1]
     const int32_t* trim;                 // optional [U,2] (left,right): pitch runs on sig[left:right]
     int n_utt;
@@ -244,7 +248,72 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], i
     const int ma = cnt & 0xffff, mb = cnt >> 16;
     const int ra = (ma - 1) >> 1, rb = (mb - 1) >> 1;          // rank of the lower middle element
     unsigned Ka = 0, Kb = 0;
-    for (int b = 30; b >= 0; --b) {
+    bool done = false;
+#ifndef DSPFE_EMU
+    {
+        // Fast path: the high 16 bits of a non-negative float are the bit pattern of a non-negative half with the same
+        // ordering, so HSET2 compares two keys per instruction and HADD2 counts them (excluded keys 0xFFFF.. are NaNs
+        // and never count).  Valid while every real key is below the half inf/NaN patterns (|x| < 2^121).
+        int mx = -1;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { mx = max(mx, (int)ka[t]); mx = max(mx, (int)kb[t]); }   // excluded keys are -1 as signed
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (mx < 0x7C000000) {
+            __half2 pa[8], pb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned wa = __byte_perm(ka[2 * j], ka[2 * j + 1], 0x7632), wb = __byte_perm(kb[2 * j], kb[2 * j + 1], 0x7632);
+                pa[j] = *reinterpret_cast<const __half2*>(&wa); pb[j] = *reinterpret_cast<const __half2*>(&wb);
+            }
+            auto count_le = [&](unsigned ta, unsigned tb) {    // #(hi16 <= t) per frame, packed (A | B << 16)
+                const unsigned wa = ta * 0x10001u, wb = tb * 0x10001u;
+                const __half2 ha = *reinterpret_cast<const __half2*>(&wa), hb = *reinterpret_cast<const __half2*>(&wb);
+                __half2 a0 = __hle2(pa[0], ha), a1 = __hle2(pa[1], ha), b0 = __hle2(pb[0], hb), b1 = __hle2(pb[1], hb);
+#pragma unroll
+                for (int j = 2; j < 8; j += 2) {
+                    a0 = __hadd2(a0, __hle2(pa[j], ha)); a1 = __hadd2(a1, __hle2(pa[j + 1], ha));
+                    b0 = __hadd2(b0, __hle2(pb[j], hb)); b1 = __hadd2(b1, __hle2(pb[j + 1], hb));
+                }
+                a0 = __hadd2(a0, a1); b0 = __hadd2(b0, b1);
+                const int ca = __half2int_rn(__hadd(__low2half(a0), __high2half(a0)));
+                const int cb = __half2int_rn(__hadd(__low2half(b0), __high2half(b0)));
+                return __reduce_add_sync(0xffffffffu, ca + (cb << 16));
+            };
+            unsigned Ha = 0, Hb = 0;
+            for (int b = 14; b >= 0; --b) {
+                const int c = count_le(Ha | ((1u << b) - 1u), Hb | ((1u << b) - 1u));
+                if ((c & 0xffff) < ra + 1) Ha |= 1u << b;
+                if ((c >> 16) < rb + 1) Hb |= 1u << b;
+            }
+            // rank inside the bucket of keys that share the high half
+            const int below = count_le(Ha ? Ha - 1 : 0, Hb ? Hb - 1 : 0);
+            int qa = ra - (Ha ? (below & 0xffff) : 0), qb = rb - (Hb ? (below >> 16) : 0);
+            // the bucket rarely holds more than a few distinct values: peel them off in increasing order
+            unsigned ma_[16], mb_[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) { ma_[t] = (ka[t] >> 16) == Ha ? ka[t] : 0xffffffffu; mb_[t] = (kb[t] >> 16) == Hb ? kb[t] : 0xffffffffu; }
+            bool fa = ma == 0, fb = mb == 0;                    // nothing to find in an empty frame
+            long long pva = -1, pvb = -1;
+            while (!(fa && fb)) {
+                unsigned ca_ = 0xffffffffu, cb_ = 0xffffffffu;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    if ((long long)ma_[t] > pva && ma_[t] < ca_) ca_ = ma_[t];
+                    if ((long long)mb_[t] > pvb && mb_[t] < cb_) cb_ = mb_[t];
+                }
+                ca_ = __reduce_min_sync(0xffffffffu, ca_); cb_ = __reduce_min_sync(0xffffffffu, cb_);
+                int n = 0;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) n += (ma_[t] == ca_ ? 1 : 0) + (mb_[t] == cb_ ? 0x10000 : 0);
+                n = __reduce_add_sync(0xffffffffu, n);
+                if (!fa) { if (qa < (n & 0xffff) || ca_ == 0xffffffffu) { Ka = ca_; fa = true; } else { qa -= n & 0xffff; pva = ca_; } }
+                if (!fb) { if (qb < (n >> 16) || cb_ == 0xffffffffu) { Kb = cb_; fb = true; } else { qb -= n >> 16; pvb = cb_; } }
+            }
+            done = true;
+        }
+    }
+#endif
+    for (int b = done ? -1 : 30; b >= 0; --b) {
         const unsigned ta = Ka | ((1u << b) - 1u), tb = Kb | ((1u << b) - 1u);
         int c0 = 0, c1 = 0, c2 = 0, c3 = 0;                   // independent partial counts: no 32-deep add chain
 #pragma unroll
@@ -303,20 +372,42 @@ DEVFN int find_utt(const int64_t* frame_off, int n_utt, int64_t g, int lane) {
 // sample t sits at decimated index k = f*step + lane + 32 t, and k - 1 = a * ds_out + b is advanced by 32 per step
 // without a division (k = 0 starts from -1 = (-1, ds_out - 1)).
 struct FrameCursor {
-    const int16_t* s16; const float* s32;
+    const unsigned char* src;   // sample s of the (trimmed) utterance lives at src + s * esz (global memory or the staged copy)
     int lim;      // relative index of the utterance's first sample (<= 0): pre-emphasis reaches back to it
     int Ld, k, a, b;
 };
-DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane, bool valid) {
+constexpr int kStageBytes = 4096;   // per frame; the span of a 512-sample frame at 16 kHz -> 10 kHz is 1.7 KB of int16
+// Stages the source span of one frame in shared memory with 16-byte loads (one DRAM latency for the whole frame
+// instead of one per group of samples) and returns the cursor; spans that do not fit are read in place.
+DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane, bool valid, unsigned char* stage) {
     FrameCursor c;
+    const int esz = p.in_f32 ? 4 : 2;
     const int64_t start = p.seg_start[u];
-    c.s16 = reinterpret_cast<const int16_t*>(p.pcm) + start;
-    c.s32 = reinterpret_cast<const float*>(p.pcm) + start;
+    const unsigned char* pcm = reinterpret_cast<const unsigned char*>(p.pcm);
+    c.src = pcm + start * esz;
     c.lim = (int)(p.offsets[u] - start);
     c.Ld = valid ? p.ds_len[u] : 0;
-    c.k = (int)(g - p.frame_off[u]) * p.frame_step + lane;
+    const int kf = (int)(g - p.frame_off[u]) * p.frame_step;
+    c.k = kf + lane;
     c.a = c.k >= 1 ? (c.k - 1) / p.ds_out : -1;
     c.b = c.k >= 1 ? (c.k - 1) - c.a * p.ds_out : p.ds_out - 1;
+    const int kl = kf + p.frame_len - 1 < c.Ld - 1 ? kf + p.frame_len - 1 : c.Ld - 1;
+    if (kf <= kl) {
+        int s_lo = (int)ds_index(kf, p.ds_idx, p.ds_in, p.ds_out) - 1;
+        if (s_lo < c.lim) s_lo = c.lim;
+        const int s_hi = (int)ds_index(kl, p.ds_idx, p.ds_in, p.ds_out);
+        const int64_t b_lo = (start + s_lo) * esz, b_hi = (start + s_hi + 1) * esz, a0 = b_lo & ~(int64_t)15;
+        const int nbytes = (int)(b_hi - a0);
+        if (nbytes <= kStageBytes) {
+            const int64_t total_bytes = p.total_samples * esz;
+            for (int off = lane * 16; off < nbytes; off += 512) {
+                if (a0 + off + 16 <= total_bytes) *reinterpret_cast<uint4*>(stage + off) = ldg(reinterpret_cast<const uint4*>(pcm + a0 + off));
+                else for (int e = 0; e < 16 && a0 + off + e < total_bytes; ++e) stage[off + e] = pcm[a0 + off + e];
+            }
+            c.src = stage + (start * esz - a0);
+        }
+    }
+    simt::warp_sync();
     return c;
 }
 // one sample: pre-emphasised over the whole utterance (preprocess.py:11-19), zero past the decimated length
@@ -326,8 +417,13 @@ DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds
     if (n < p.frame_len && c.k < c.Ld) {
         const int s = c.k == 0 ? 0 : c.a * p.ds_in + ds_idx[c.b];   // sample index inside the (trimmed) utterance
         float cur, prev = 0.f;
-        if (p.in_f32) { cur = c.s32[s]; if (s > c.lim) prev = c.s32[s - 1]; }
-        else { cur = cvt_i16(c.s16[s]); if (s > c.lim) prev = cvt_i16(c.s16[s - 1]); }
+        if (p.in_f32) {
+            const float* q = reinterpret_cast<const float*>(c.src) + s;
+            cur = q[0]; if (s > c.lim) prev = q[-1];
+        } else {
+            const int16_t* q = reinterpret_cast<const int16_t*>(c.src) + s;
+            cur = cvt_i16(q[0]); if (s > c.lim) prev = cvt_i16(q[-1]);
+        }
         // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one
         v = p.pre_hi != 0.f ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
     }
@@ -358,12 +454,14 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
     const bool hasB = g0 + 1 < total;
     const int L = p.frame_len;
     {
-        // ---- gather both frames into xs (a rolled loop, four samples per frame in flight: the fully unrolled form
+        // ---- gather both frames into xs from their staged source spans (a rolled loop: the fully unrolled form
         // streamed 50 KB of straight-line code through the instruction cache per pair); sum |x| of the raw frames
         // (sub_endpoint_detect, pitch.py:65) in float64 across the warp
         const int ua = find_utt(p.frame_off, p.n_utt, g0, lane);
         const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
-        FrameCursor ca = frame_cursor(p, g0, ua, lane, true), cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB);
+        unsigned char* stage = reinterpret_cast<unsigned char*>(park);     // park is free until the first transform is done
+        FrameCursor ca = frame_cursor(p, g0, ua, lane, true, stage);
+        FrameCursor cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB, stage + kStageBytes);
         float fa = 0.f, fb = 0.f;
 #pragma unroll 1
         for (int t0 = 0; t0 < 16; t0 += 4) {

@@ -65,7 +65,7 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
     if (frame_off_out) std::memcpy(frame_off_out, frame_off.data(), (n_utt + 1) * sizeof(int64_t));
     std::vector<float> rows_own; std::vector<double> amp(fo), pitch_own(fo), scratch(3 * fo); std::vector<int32_t> lag_own(fo);
     if (!rows) { rows_own.resize((size_t)fo * p.row_len); rows = rows_own.data(); }
-    p.pcm = pcm; p.in_f32 = in_f32; p.offsets = (const int64_t*)offsets; p.trim = trim; p.n_utt = n_utt;
+    p.pcm = pcm; p.in_f32 = in_f32; p.total_samples = offsets[n_utt]; p.offsets = (const int64_t*)offsets; p.trim = trim; p.n_utt = n_utt;
     p.tab = tab.data(); p.frame_off = frame_off.data(); p.seg_start = seg_start.data(); p.seg_len = seg_len.data();
     p.ds_len = ds_len.data(); p.rows = rows; p.rows_out = rows_smoothed; p.score = score; p.frame_amp = amp.data();
     p.pitch = pitch ? pitch : pitch_own.data(); p.lag = lag ? lag : lag_own.data(); p.feat = feat; p.scratch = scratch.data();
