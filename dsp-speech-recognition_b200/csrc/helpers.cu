@@ -2,8 +2,11 @@
 // They exist so that every arithmetic entry point of the drop-in `features` package runs on the GPU; none
 // of them is on the throughput path (the fused kernels never materialise frames).  float64 where the
 // reference result is float64 and cheap to reproduce exactly (framing, pre-emphasis, row statistics).
+#include <vector>
+
 #include "abi_common.h"
 #include "dspfe_types.h"
+#include "pitch_tables.h"
 
 using namespace dspfe;
 
@@ -91,6 +94,24 @@ __global__ void delta_kernel(const float* in, int64_t F, int C, int N, float sca
     out[i] = acc * scale;
 }
 
+// window (sigproc.py:22-46): y[n] = sum_{m<=n} x[m] h[n-m], complex float64 taps, output truncated to len(x)
+__global__ void fir_window_kernel(const double* x, int n, const double* hr, const double* hi, double* y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sr = 0.0, si = 0.0;
+    for (int m = 0; m <= i; ++m) { const double v = x[m]; sr += v * hr[i - m]; si += v * hi[i - m]; }
+    y[2 * i] = sr; y[2 * i + 1] = si;
+}
+
+// acr (sigproc.py:48-53): lagged products, then numpy's pairwise sum and the unbiased normalisation
+__global__ void lag_products_kernel(const double* x, int len, int n, double* prod) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len - n) prod[i] = x[i] * x[i + n];
+}
+__global__ void acr_finish_kernel(const double* prod, int count, int len, int n, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = np_sum_any(prod, count, false, false) / (double)(len - n);
+}
+
 unsigned grid_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -143,6 +164,37 @@ int dspfe_delta_f32(const float* d_in, int64_t n_frames, int32_t n_cols, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     delta_kernel<<<grid_for(n_frames * n_cols, 256), 256, 0, st>>>(d_in, n_frames, n_cols, N, (float)(1.0 / (2.0 * den)), d_out);
     LAUNCH_CHECK("delta_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_fir_window_f64(const double* d_x, int32_t n, double rate, double low_freq, double high_freq, int32_t hamming,
+                         double* d_y, void* stream) {
+    if (n < 1 || !d_x || !d_y || !(rate > 0)) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n > 8192) return fail(DSPFE_ERR_UNSUPPORTED, "window() signals longer than 8192 samples are not built");
+    std::vector<double> hr, hi;
+    fir_taps(n, rate, low_freq, high_freq, hamming != 0, hr, hi);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_h = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_h, 2 * (size_t)n * sizeof(double), st));
+    CUDA_TRY(cudaMemcpyAsync(d_h, hr.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_h + n, hi.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    fir_window_kernel<<<grid_for(n, 128), 128, 0, st>>>(d_x, n, d_h, d_h + n, d_y);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_h, st);
+    if (e != cudaSuccess) return fail(DSPFE_ERR_CUDA, std::string("fir_window_kernel: ") + cudaGetErrorString(e));
+    return DSPFE_OK;
+}
+
+int dspfe_acr_f64(const double* d_frame, int32_t len, int32_t n, double* d_out, void* stream) {
+    if (!d_frame || !d_out || len < 1 || n < 0 || n >= len) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_prod = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_prod, (size_t)(len - n) * sizeof(double), st));
+    lag_products_kernel<<<grid_for(len - n, 256), 256, 0, st>>>(d_frame, len, n, d_prod);
+    acr_finish_kernel<<<1, 32, 0, st>>>(d_prod, len - n, len, n, d_out);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_prod, st);
+    if (e != cudaSuccess) return fail(DSPFE_ERR_CUDA, std::string("acr kernels: ") + cudaGetErrorString(e));
     return DSPFE_OK;
 }
 

@@ -362,6 +362,28 @@ int dspfe_pitch_feature_tail_host(const double* pitch, const double* amp, int32_
     return DSPFE_OK;
 }
 
+int dspfe_dp_max_pitch_host(const double* g, int32_t n_rows, int32_t n_cols, double* path) {
+    // dp_max_pitch (pitch.py:208-225): Viterbi over lags with a 5-per-step jump penalty.  As in the reference, the
+    // back-trace starts from the predecessor chosen for the LAST column of the last row (not from the best end state).
+    if (!g || !path || n_rows < 2 || n_cols < 1) return fail(DSPFE_ERR_INVALID_ARG, "dp_max_pitch needs at least two rows");
+    std::vector<double> dp((size_t)n_cols, 0.0), nx((size_t)n_cols);
+    std::vector<int32_t> prev((size_t)n_rows * n_cols, 0);
+    int step = 0;
+    for (int i = 1; i < n_rows; ++i) {
+        for (int j = 0; j < n_cols; ++j) {
+            double best = 0; int arg = -1;
+            for (int k = 0; k < n_cols; ++k) {
+                const double r = dp[k] - 5.0 * (double)(k > j ? k - j : j - k) + g[(size_t)i * n_cols + j];
+                if (arg < 0 || r > best) { best = r; arg = k; }
+            }
+            nx[j] = best; prev[(size_t)i * n_cols + j] = arg; step = arg;
+        }
+        dp.swap(nx);
+    }
+    for (int i = n_rows - 1; i >= 0; --i) { path[i] = 10000.0 / (double)step; step = prev[(size_t)i * n_cols + step]; }
+    return DSPFE_OK;
+}
+
 int dspfe_poly_lead_host(const double* seq, int32_t n, int32_t deg, double* coef) {
     if (!seq || !coef || n < 1 || (deg != 1 && deg != 2)) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
     if (n <= deg) return fail(DSPFE_ERR_UNSUPPORTED, "fewer points than coefficients");

@@ -320,6 +320,8 @@ def _bind_helpers(L):
     L.dspfe_row_amplitude_f64.argtypes = [vp, i64, i32, i32, vp, vp]
     L.dspfe_row_zcr_f64.argtypes = [vp, i64, i32, vp, vp]
     L.dspfe_delta_f32.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.dspfe_fir_window_f64.argtypes = [vp, i32, ctypes.c_double, ctypes.c_double, ctypes.c_double, i32, vp, vp]
+    L.dspfe_acr_f64.argtypes = [vp, i32, i32, vp, vp]
     L._h_bound = True
 
 
@@ -462,6 +464,7 @@ def _bind_pitch(L):
     L.dspfe_sub_endpoint_host.argtypes = [vp, i32, ctypes.POINTER(i32)]
     L.dspfe_pitch_feature_tail_host.argtypes = [vp, vp, i32, vp]
     L.dspfe_poly_lead_host.argtypes = [vp, i32, i32, ctypes.POINTER(f64)]
+    L.dspfe_dp_max_pitch_host.argtypes = [vp, i32, i32, vp]
     L._p_bound = True
 
 
@@ -631,3 +634,34 @@ def poly_lead_host(seq, deg):
     c = ctypes.c_double(0.0)
     _check(L.dspfe_poly_lead_host(_np_ptr(seq), len(seq), int(deg), ctypes.byref(c)))
     return c.value
+
+
+def dp_max_pitch_host(g):
+    """dp_max_pitch (reference pitch.py:208-225) on a [n_rows, n_cols] score array."""
+    L = lib(); _bind_pitch(L)
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    out = np.zeros(g.shape[0], dtype=np.float64)
+    _check(L.dspfe_dp_max_pitch_host(_np_ptr(g), g.shape[0], g.shape[1], _np_ptr(out)))
+    return out
+
+
+def fir_window_f64(sig, rate, low_freq, high_freq, hamming):
+    """window (reference sigproc.py:22-46) on the device: complex128 [n]."""
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    x = torch.from_numpy(np.ascontiguousarray(sig, dtype=np.float64)).to(dev)
+    y = torch.empty((x.numel(), 2), dtype=torch.float64, device=dev)
+    _check(L.dspfe_fir_window_f64(x.data_ptr(), x.numel(), float(rate), float(low_freq), float(high_freq), int(bool(hamming)),
+                                  y.data_ptr(), _stream(torch, dev)))
+    r = y.cpu().numpy()
+    return r[:, 0] + 1j * r[:, 1]
+
+
+def acr_f64(frame, n):
+    """acr (reference sigproc.py:48-53) on the device."""
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    x = torch.from_numpy(np.ascontiguousarray(frame, dtype=np.float64)).to(dev)
+    out = torch.empty(1, dtype=torch.float64, device=dev)
+    _check(L.dspfe_acr_f64(x.data_ptr(), x.numel(), int(n), out.data_ptr(), _stream(torch, dev)))
+    return np.float64(out.cpu().numpy()[0])

@@ -188,8 +188,11 @@ def robust_max_pitch(g, bias=20):
 
 
 def dp_max_pitch(g):
-    """reference pitch.py:208-225 (Viterbi over lags): never called on the path."""
-    raise NotImplementedError("dp_max_pitch is not built (SURVEY.md row f-3)")
+    """reference pitch.py:208-225: Viterbi over lags with a jump penalty (same back-trace start as the reference)."""
+    a = np.asarray(g, dtype=np.float64)
+    if a.ndim != 2 or a.shape[0] < 2:
+        raise NotImplementedError("dp_max_pitch needs a 2-D score array with at least two rows")
+    return dspfe.dp_max_pitch_host(a).tolist()
 
 
 def peak_score(sig, gender='male'):

@@ -15,27 +15,18 @@ def to_frames(sig, rate, t=0.020, step=0.010):
     return framesig(sig, int(rate * t), int(step * rate))
 
 
-def _fir_taps(N, rate, low_freq, high_freq, wintype):
-    Hd = np.zeros(N)
-    Hd[int(N * low_freq / rate):int(N * high_freq / rate)] = 1
-    w = np.hamming(N) if wintype == 'hamming' else np.ones(N)
-    return 2 * np.pi * w * np.fft.ifft(Hd, N)
-
-
 def window(sig, rate, low_freq=0, high_freq=500, wintype='square'):
-    """reference sigproc.py:22-46: causal complex FIR band-pass, output truncated to len(sig).
-    Host helper (never called by the reference's callers directly; the pitch kernels apply the same filter
-    on the device through its 1024-point spectrum)."""
+    """reference sigproc.py:22-46: causal complex FIR band-pass (one-sided ideal band => complex taps), output truncated
+    to len(sig); float64 on the device.  The fused pitch kernels apply the same filter through its 1024-point spectrum."""
     sig = np.asarray(sig)
-    N = len(sig)
-    return np.convolve(sig, _fir_taps(N, rate, low_freq, high_freq, wintype))[:N]
+    if sig.ndim != 1:
+        raise NotImplementedError("expected a 1-D signal")
+    return dspfe.fir_window_f64(sig, rate, low_freq, high_freq, wintype == 'hamming')
 
 
 def acr(frame, n):
-    """reference sigproc.py:48-53."""
-    if n == 0:
-        return np.sum(frame * frame) / len(frame)
-    return np.sum(frame[:-n] * frame[n:]) / (len(frame) - n)
+    """reference sigproc.py:48-53: unbiased autocorrelation at lag n (n = 0: mean square)."""
+    return dspfe.acr_f64(np.asarray(frame, dtype=np.float64), n)
 
 
 def round_half_up(number):

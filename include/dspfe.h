@@ -240,6 +240,8 @@ int dspfe_smooth_subsequence_host(const double* pitch, int32_t n, int32_t tor, d
 int dspfe_sub_endpoint_host(const double* amp, int32_t n_frames, int32_t* p);
 int dspfe_pitch_feature_tail_host(const double* pitch, const double* amp, int32_t n_frames, double* out5);
 int dspfe_poly_lead_host(const double* seq, int32_t n, int32_t deg, double* coef);
+/* dp_max_pitch (pitch.py:208-225): Viterbi over the columns of g [n_rows,n_cols]; path [n_rows] = 10000 / lag index */
+int dspfe_dp_max_pitch_host(const double* g, int32_t n_rows, int32_t n_cols, double* path);
 
 /* ------------------------------------------------------------------------------------------------
  * Helpers: the reference's small array functions as device kernels (not on the throughput path; the
@@ -255,6 +257,11 @@ int dspfe_preemphasis_f64(const double* d_x, int64_t n, double coeff, double* d_
 int dspfe_row_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t use_sq, double* d_out, void* stream);
 /* get_zcr(frames) (endpoint.py:182) */
 int dspfe_row_zcr_f64(const double* d_frames, int64_t n_rows, int32_t len, int64_t* d_out, void* stream);
+/* window (sigproc.py:22-46): causal complex FIR band-pass of a real signal, d_y [n,2] = (re, im) float64 */
+int dspfe_fir_window_f64(const double* d_x, int32_t n, double rate, double low_freq, double high_freq, int32_t hamming,
+                         double* d_y, void* stream);
+/* acr (sigproc.py:48-53): unbiased autocorrelation of one frame at lag n -> d_out[0] */
+int dspfe_acr_f64(const double* d_frame, int32_t len, int32_t n, double* d_out, void* stream);
 /* delta(feat, N) (base.py:70) on an arbitrary [n_frames, n_cols] float32 matrix */
 int dspfe_delta_f32(const float* d_in, int64_t n_frames, int32_t n_cols, int32_t N, float* d_out, void* stream);
 

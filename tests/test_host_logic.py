@@ -149,6 +149,13 @@ def test_pitch_list_helpers_against_oracle():
             np.testing.assert_allclose(dspfe.poly_lead_host(seg, 2), O.quad_params(seg), rtol=1e-8, atol=1e-12)
 
 
+def test_dp_max_pitch_matches_oracle():
+    rng = np.random.default_rng(3)
+    for t in range(20):
+        g = rng.integers(0, 40, size=(int(rng.integers(2, 60)), 80))
+        np.testing.assert_array_equal(dspfe.dp_max_pitch_host(g), O.dp_max_pitch(g))
+
+
 def test_pitch_frame_counts():
     """decimated length ((S-1)*5-1)//8+2 and the 512/100 framing (SURVEY §8 C3) without a device: the plan
     constructor needs CUDA, so the same formulas are checked through the oracle's index list."""

@@ -135,6 +135,15 @@ def test_dropin_pitch_module():
     np.testing.assert_allclose(features.quad_params(wseg), O.quad_params(wseg), rtol=1e-8)
     assert features.peakshift(wseg, wp) == O.peakshift(wseg, wp)
     assert features.sub_endpoint_detect(wf) == O.sub_endpoint_detect(wf)
+    assert features.dp_max_pitch(sc) == O.dp_max_pitch(sc)
+    # sigproc.window / acr on the device (float64)
+    y = features.window(fr, 10000, 50, 1000, 'hamming')
+    wy = O.window(fr, 10000, 50, 1000, 'hamming')
+    assert y.dtype == np.complex128 and np.max(np.abs(y - wy)) <= 1e-9 * np.max(np.abs(wy))
+    y = features.window(fr[:300], 10000, 0, 500)
+    assert np.max(np.abs(y - O.window(fr[:300], 10000, 0, 500))) <= 1e-9 * np.max(np.abs(wy))
+    for n in (0, 1, 37, 199):
+        np.testing.assert_allclose(features.acr(fr, n), O.acr(fr, n), rtol=1e-13)
     import pickle
     assert features.pitch.pickle is pickle    # pitch_model.py star-imports it from here (SURVEY A-12)
 
