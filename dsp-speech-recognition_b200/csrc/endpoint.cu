@@ -90,6 +90,27 @@ int dspfe_amplitude_rule_host(const dspfe_endpoint_params* p, const double* amp,
     return DSPFE_OK;
 }
 
+int dspfe_amplitude_rule_gated_host(const dspfe_endpoint_params* p, const double* amp, const int32_t* gate, int32_t n_frames, double mh,
+                                    int32_t* segs, int32_t seg_cap, int32_t* n_segs) {
+    if (!p || !amp || !gate || !n_segs || n_frames < 1 || seg_cap < 1 || !segs) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    EpRule r; int fl, fs;
+    int rc = fill_rule(*p, r, fl, fs);
+    if (rc) return rc;
+    int left, right;
+    const int n = amplitude_rule(AmpFromF64{amp}, n_frames, r, mh, &left, &right, segs, seg_cap, GateFromFlags{gate});
+    if (n == 0) { segs[0] = 0; segs[1] = n_frames; *n_segs = 1; } else { *n_segs = n; }
+    return DSPFE_OK;
+}
+
+int dspfe_acr_gate_rows_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t samplerate, int32_t* d_gate, void* stream) {
+    if (n_rows < 0 || len < 1 || samplerate < 1 || (n_rows > 0 && (!d_frames || !d_gate))) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_rows == 0) return DSPFE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    acr_gate_rows_kernel<<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(d_frames, n_rows, len, samplerate / 500, samplerate / 50, d_gate);
+    LAUNCH_CHECK("acr_gate_rows_kernel", st);
+    return DSPFE_OK;
+}
+
 int dspfe_zcr_rule_host(const dspfe_endpoint_params* p, const double* zcr, int32_t n_frames, double l_sil, int32_t left,
                         int32_t right, int32_t* out_jk) {
     if (!p || !zcr || !out_jk || n_frames < 1 || left < 0 || left >= n_frames || right < 0 || right > n_frames)
@@ -158,6 +179,40 @@ int dspfe_endpoint(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_
     LAUNCH_CHECK("ep_frame_kernel", st);
     ep_decide_kernel<<<(unsigned)((n_utt + kEpDecideWarps - 1) / kEpDecideWarps), 32 * kEpDecideWarps, 0, st>>>(p);
     LAUNCH_CHECK("ep_decide_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_endpoint_robust(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets, int32_t n_utt,
+                          int32_t* d_lr, void* stream) {
+    if (!pl || !d_offsets || !d_lr || n_utt < 0 || total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    if (!d_pcm && total_samples > 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm is null");
+    if (pl->frame_len > kEpGateMaxLen) return fail(DSPFE_ERR_UNSUPPORTED, "robust endpoint frames longer than 1536 samples are not built");
+    // frame statistics exactly as the basic path (its own decision is discarded), then the gated rule
+    int rc = dspfe_endpoint(pl, d_pcm, total_samples, d_offsets, n_utt, d_lr, nullptr, nullptr, nullptr, 0, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t frames_bound = dspfe_endpoint_frames_bound(pl, total_samples, n_utt);
+    EpParams p;
+    p.pcm = d_pcm; p.offsets = d_offsets; p.n_utt = n_utt; p.frame_len = pl->frame_len; p.frame_step = pl->frame_step;
+    p.q = pl->q; p.rem = pl->rem; p.frame_off = pl->frame_off; p.block_off = pl->block_off; p.blk = pl->blk; p.asum = pl->asum; p.zcr = pl->zcr;
+    p.lr = d_lr; p.max_blocks = 0; p.max_frames = frames_bound; p.rule = pl->rule;
+    ep_decide_robust_kernel<<<(unsigned)((n_utt + kEpRobustWarps - 1) / kEpRobustWarps), 32 * kEpRobustWarps, 0, st>>>(p);
+    LAUNCH_CHECK("ep_decide_robust_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_endpoint_robust_host(dspfe_endpoint_plan* pl, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt, int32_t* h_lr) {
+    if (!pl || !h_offsets || !h_lr || n_utt < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_utt == 0) return DSPFE_OK;
+    // stage through the basic host path's buffers (it leaves pcm / offsets on the device), then re-decide with the gate
+    int rc = dspfe_endpoint_host(pl, h_pcm, h_offsets, n_utt, h_lr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    const int64_t total = h_offsets[n_utt] - h_offsets[0];
+    rc = dspfe_endpoint_robust(pl, pl->d_pcm, total, pl->d_off, n_utt, pl->d_lr, pl->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_lr, pl->d_lr, (int64_t)n_utt * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
     return DSPFE_OK;
 }
 

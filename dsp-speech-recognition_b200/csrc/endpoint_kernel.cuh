@@ -76,8 +76,14 @@ struct ZcrFromI32 { const int32_t* z; DSP_HD double operator()(int i) const { re
 
 // amplitude_rule (endpoint.py:133-179).  Writes up to seg_cap (j,k) pairs to segs (may be null) and returns the
 // number of segments found; *left/*right = first segment start / last segment end, or (0, F) when none qualifies.
-template <class Amp>
-DSP_HD int amplitude_rule(Amp amp, int F, const EpRule& r, double mh, int* left, int* right, int32_t* segs = nullptr, int seg_cap = 0) {
+// Gate of the expansion loops: always open for the basic rule; robust_endpoint_detection closes it on frames whose
+// normalised autocorrelation peak is below 0.55 (acr_rule, endpoint.py:142-144).
+struct GateOpen { DSP_HD bool operator()(int) const { return true; } };
+struct GateFromFlags { const int32_t* g; DSP_HD bool operator()(int i) const { return g[i] != 0; } };
+
+template <class Amp, class Gate = GateOpen>
+DSP_HD int amplitude_rule(Amp amp, int F, const EpRule& r, double mh, int* left, int* right, int32_t* segs = nullptr, int seg_cap = 0,
+                          Gate gate = Gate()) {
     const int nl = (int)(r.l_sil / r.cfg_step), nr = (int)(r.r_sil / r.cfg_step);
     double sil[64];
     int n = 0;
@@ -104,8 +110,8 @@ DSP_HD int amplitude_rule(Amp amp, int F, const EpRule& r, double mh, int* left,
             if ((double)(k - j) < T_H) {
                 i = k;
             } else {
-                while (j > 0 && amp(j) > M_L) --j;
-                while (k < F && amp(k) > M_L) ++k;
+                while (j > 0 && amp(j) > M_L && gate(j)) --j;
+                while (k < F && amp(k) > M_L && gate(k)) ++k;
                 if (first < 0) first = j;
                 last = k;
                 if (segs && nseg < seg_cap) { segs[2 * nseg] = j; segs[2 * nseg + 1] = k; }
@@ -148,6 +154,40 @@ DSP_HD void endpoint_decide(const int32_t* asum, const int32_t* zcr, int F, int 
     zcr_rule(ZcrFromI32{zcr}, F, r, 0.0, left, right, &l2, &r2);
     if (r2 - l2 < r.min_span) { l2 = 0; r2 = F; }
     // int(left2 * cfg.step * rate): float64 product evaluated left to right, truncated (Appendix A-9)
+    out_lr[0] = (int32_t)((double)l2 * r.cfg_step * (double)r.rate);
+    out_lr[1] = (int32_t)((double)r2 * r.cfg_step * (double)r.rate);
+}
+
+// acr_rule (endpoint.py:142-144) from exact integer lag sums: acr(frame, n) = sum_i x[i] x[i+n] / (len - n)
+// (sigproc.py:48-53; the products of int16 samples and their sums are exact in the reference's float64 too), gate =
+// max_n acr(n) / acr(0) > 0.55 over n in [rate // 500, rate // 50).  best = max_n S_n / (len - n) as computed by the caller.
+DSP_HD bool acr_gate_decide(double best, long long s0, int len) {
+    const double a0 = (double)s0 / (double)len;
+    return best / a0 > 0.55;          // 0 / 0 = NaN compares false, as in the reference
+}
+// plain sequential form (host entry points, utterances too long for the staged kernel)
+DSP_HD bool acr_gate_frame(const int16_t* x, long long avail, int len, int n0, int n1) {
+    // x[i] for i < avail, zero beyond (sigproc.py:84-87)
+    long long s0 = 0;
+    for (int i = 0; i < len && i < avail; ++i) s0 += (long long)x[i] * x[i];
+    double best = 0.0; bool any = false;
+    for (int n = n0; n < n1 && n < len; ++n) {
+        long long sn = 0;
+        for (int i = 0; i + n < len && i + n < avail; ++i) sn += (long long)x[i] * x[i + n];
+        const double a = (double)sn / (double)(len - n);
+        if (!any || a > best) { best = a; any = true; }
+    }
+    return any && acr_gate_decide(best, s0, len);
+}
+
+// robust_endpoint_detection (endpoint.py:68-92): amplitude_rule(mh = 0.5) with the gate, zcr_rule, whole-signal fallback
+template <class Gate>
+DSP_HD void endpoint_decide_robust(const int32_t* asum, const int32_t* zcr, int F, int frame_len, const EpRule& r, Gate gate, int32_t* out_lr) {
+    int left, right;
+    amplitude_rule(AmpFromSum{asum, (double)frame_len}, F, r, 0.5, &left, &right, nullptr, 0, gate);
+    int l2, r2;
+    zcr_rule(ZcrFromI32{zcr}, F, r, 0.0, left, right, &l2, &r2);
+    if (r2 - l2 < r.min_span) { l2 = 0; r2 = F; }
     out_lr[0] = (int32_t)((double)l2 * r.cfg_step * (double)r.rate);
     out_lr[1] = (int32_t)((double)r2 * r.cfg_step * (double)r.rate);
 }
@@ -285,6 +325,82 @@ __global__ void __launch_bounds__(32 * kEpDecideWarps) ep_decide_kernel(EpParams
         asum = s_stat[w][0]; zcr = s_stat[w][1];
     }
     if (lane == 0) endpoint_decide(asum, zcr, F, p.frame_len, p.rule, p.lr + 2 * u);
+}
+// Warp-cooperative gate: the frame is staged as int32 in shared memory, every lane takes the lags n0 + lane + 32 m.
+// All lanes of the warp execute the rule in lock step on identical data, so the gate is called convergently.
+constexpr int kEpGateMaxLen = 1536;
+struct GateWarp {
+    const int16_t* x; long long S; int step, len, n0, n1; int* sx;   // utterance samples, its length, framing, lag range, staging
+    __device__ bool operator()(int j) const {
+        const int lane = threadIdx.x & 31;
+        const long long b = (long long)j * step;
+        __syncwarp();
+        for (int i = lane; i < len; i += 32) sx[i] = (b + i < S) ? (int)x[b + i] : 0;
+        __syncwarp();
+        long long s0 = 0;
+        for (int i = lane; i < len; i += 32) s0 += (long long)sx[i] * sx[i];
+        double best = -1.0e300; 
+        for (int n = n0 + lane; n < n1 && n < len; n += 32) {
+            long long sn = 0;
+            for (int i = 0; i + n < len; ++i) sn += (long long)sx[i] * sx[i + n];
+            const double a = (double)sn / (double)(len - n);
+            best = a > best ? a : best;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+            const double o = __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(best), m), __shfl_xor_sync(0xffffffffu, __double2loint(best), m));
+            best = o > best ? o : best;
+        }
+        if (n0 >= n1 || n0 >= len) return false;
+        return acr_gate_decide(best, s0, len);
+    }
+};
+
+constexpr int kEpRobustWarps = 2;
+__global__ void __launch_bounds__(32 * kEpRobustWarps) ep_decide_robust_kernel(EpParams p) {
+    __shared__ int32_t s_stat[kEpRobustWarps][2][kEpStageFrames];
+    __shared__ int s_x[kEpRobustWarps][kEpGateMaxLen];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = blockIdx.x * kEpRobustWarps + w;
+    if (u >= p.n_utt) return;
+    const int64_t f0 = p.frame_off[u];
+    const int F = (int)(p.frame_off[u + 1] - f0);
+    const int32_t* asum = p.asum + f0;
+    const int32_t* zcr = p.zcr + f0;
+    if (F <= kEpStageFrames) {
+        for (int i = lane; i < F; i += 32) { s_stat[w][0][i] = asum[i]; s_stat[w][1][i] = zcr[i]; }
+        __syncwarp();
+        asum = s_stat[w][0]; zcr = s_stat[w][1];
+    }
+    const GateWarp gate{p.pcm + p.offsets[u], (long long)(p.offsets[u + 1] - p.offsets[u]), p.frame_step, p.frame_len,
+                        p.rule.rate / 500, p.rule.rate / 50, s_x[w]};
+    int32_t lr[2];
+    endpoint_decide_robust(asum, zcr, F, p.frame_len, p.rule, gate, lr);   // every lane, identical data
+    if (lane == 0) { p.lr[2 * u] = lr[0]; p.lr[2 * u + 1] = lr[1]; }
+}
+
+// the gate of every row of a float64 frame matrix (the list-typed amplitude_rule(use_acr=True, frames=...) API): one warp per row
+__global__ void acr_gate_rows_kernel(const double* frames, int64_t n_rows, int len, int n0, int n1, int32_t* gate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const double* x = frames + r * len;
+    double s0 = 0.0, best = -1.0e300;
+    for (int i = lane; i < len; i += 32) s0 += x[i] * x[i];
+    for (int n = n0 + lane; n < n1 && n < len; n += 32) {
+        double sn = 0.0;
+        for (int i = 0; i + n < len; ++i) sn += x[i] * x[i + n];
+        const double a = sn / (double)(len - n);
+        best = a > best ? a : best;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        s0 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(s0), m), __shfl_xor_sync(0xffffffffu, __double2loint(s0), m));
+        const double o = __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(best), m), __shfl_xor_sync(0xffffffffu, __double2loint(best), m));
+        best = o > best ? o : best;
+    }
+    if (lane == 0) gate[r] = (n0 < n1 && n0 < len && best / (s0 / (double)len) > 0.55) ? 1 : 0;
 }
 #endif  // __CUDACC__
 

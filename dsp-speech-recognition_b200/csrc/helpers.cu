@@ -112,6 +112,49 @@ __global__ void acr_finish_kernel(const double* prod, int count, int len, int n,
     if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = np_sum_any(prod, count, false, false) / (double)(len - n);
 }
 
+// Caller-side batching epilogue of model.py (:75-88 CMVN of the static block, :35-50 pad / truncate to T frames,
+// :131-135 [T, B, 3C] layout): one CTA per utterance.  Column statistics over ALL frames of the utterance in float64;
+// sklearn.preprocessing.scale semantics (population std, a constant column is only centred).
+constexpr int kBatchThreads = 128;
+__global__ void __launch_bounds__(kBatchThreads) cmvn_pad_kernel(const float* feat, const int64_t* frame_off, int n_utt, int C, int T,
+                                                                float* out, int32_t* len0) {
+    __shared__ double s_sum[kBatchThreads], s_sq[kBatchThreads];
+    __shared__ float s_mean[kMaxNumcep], s_inv[kMaxNumcep];
+    const int u = blockIdx.x, tid = threadIdx.x;
+    const int64_t r0 = frame_off[u];
+    const int F = (int)(frame_off[u + 1] - r0);
+    const int W = 3 * C;
+    const int per = kBatchThreads / C;               // row lanes per column
+    const int c = tid % C, rl = tid / C;
+    double sm = 0.0, sq = 0.0;
+    if (rl < per)
+        for (int t = rl; t < F; t += per) { const double v = feat[(r0 + t) * W + c]; sm += v; sq += v * v; }
+    s_sum[tid] = sm; s_sq[tid] = sq;
+    __syncthreads();
+    if (tid < C) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < per; ++k) { a += s_sum[tid + k * C]; b += s_sq[tid + k * C]; }
+        const double mean = F > 0 ? a / F : 0.0;
+        double var = F > 0 ? b / F - mean * mean : 0.0;
+        if (var < 0.0) var = 0.0;
+        double sd = sqrt(var);
+        if (sd < 10.0 * 2.220446049250313e-16 * fmax(1.0, fabs(mean))) sd = 1.0;   // constant column: centre only
+        s_mean[tid] = (float)mean; s_inv[tid] = (float)(1.0 / sd);
+    }
+    __syncthreads();
+    const int n = (F < T ? F : T) * W;
+    for (int i = tid; i < T * W; i += kBatchThreads) {
+        const int t = i / W, col = i - t * W;
+        float v = 0.f;
+        if (i < n) {
+            v = feat[(r0 + t) * W + col];
+            if (col < C) v = (v - s_mean[col]) * s_inv[col];
+        }
+        out[((int64_t)t * n_utt + u) * W + col] = v;
+    }
+    if (tid == 0 && len0) len0[u] = F < T ? F : T;
+}
+
 unsigned grid_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -164,6 +207,17 @@ int dspfe_delta_f32(const float* d_in, int64_t n_frames, int32_t n_cols, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     delta_kernel<<<grid_for(n_frames * n_cols, 256), 256, 0, st>>>(d_in, n_frames, n_cols, N, (float)(1.0 / (2.0 * den)), d_out);
     LAUNCH_CHECK("delta_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_cmvn_pad_batch(const float* d_feat, const int64_t* d_frame_off, int32_t n_utt, int32_t numcep, int32_t T, float* d_out,
+                         int32_t* d_len0, void* stream) {
+    if (!d_feat || !d_frame_off || !d_out || n_utt < 0 || T < 1) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (numcep < 1 || numcep > kMaxNumcep) return fail(DSPFE_ERR_UNSUPPORTED, "numcep outside 1..16");
+    if (n_utt == 0) return DSPFE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cmvn_pad_kernel<<<(unsigned)n_utt, kBatchThreads, 0, st>>>(d_feat, d_frame_off, n_utt, numcep, T, d_out, d_len0);
+    LAUNCH_CHECK("cmvn_pad_kernel", st);
     return DSPFE_OK;
 }
 

@@ -201,6 +201,12 @@ def _bind_endpoint(L):
                                             ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     L.dspfe_zcr_rule_host.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.c_void_p, ctypes.c_int32, ctypes.c_double,
                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    L.dspfe_endpoint_robust.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
+                                        ctypes.c_void_p, ctypes.c_void_p]
+    L.dspfe_endpoint_robust_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+    L.dspfe_amplitude_rule_gated_host.argtypes = [ctypes.POINTER(_EndpointParams), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                                  ctypes.c_double, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    L.dspfe_acr_gate_rows_f64.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     L._ep_bound = True
 
 
@@ -287,6 +293,24 @@ class EndpointPlan:
                                     None, None, None, 0, ctypes.c_void_p(st)))
         return lr
 
+    def detect_robust(self, pcm, offsets, stream=None):
+        """robust_endpoint_detection (reference endpoint.py:68) on device tensors: lr int32 [U,2]."""
+        import torch
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and offsets.is_cuda and offsets.dtype == torch.int64
+        n_utt = offsets.numel() - 1
+        lr = torch.empty((n_utt, 2), dtype=torch.int32, device=pcm.device)
+        st = stream if stream is not None else torch.cuda.current_stream(pcm.device).cuda_stream
+        _check(lib().dspfe_endpoint_robust(self._h, pcm.data_ptr(), pcm.numel(), offsets.data_ptr(), n_utt, lr.data_ptr(), ctypes.c_void_p(st)))
+        return lr
+
+    def detect_robust_host(self, pcm, offsets):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lr = np.zeros((len(offsets) - 1, 2), dtype=np.int32)
+        _check(lib().dspfe_endpoint_robust_host(self._h, pcm.ctypes.data_as(ctypes.c_void_p), offsets.ctypes.data_as(ctypes.c_void_p),
+                                                len(offsets) - 1, lr.ctypes.data_as(ctypes.c_void_p)))
+        return lr
+
     def detect_host(self, pcm, offsets, want_features=False):
         """Host path: NumPy int16 pcm + int64 offsets -> lr int32 [U,2] (+ asum, zcr, frame_off)."""
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
@@ -320,6 +344,7 @@ def _bind_helpers(L):
     L.dspfe_row_amplitude_f64.argtypes = [vp, i64, i32, i32, vp, vp]
     L.dspfe_row_zcr_f64.argtypes = [vp, i64, i32, vp, vp]
     L.dspfe_delta_f32.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.dspfe_cmvn_pad_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     L.dspfe_fir_window_f64.argtypes = [vp, i32, ctypes.c_double, ctypes.c_double, ctypes.c_double, i32, vp, vp]
     L.dspfe_acr_f64.argtypes = [vp, i32, i32, vp, vp]
     L._h_bound = True
@@ -665,3 +690,41 @@ def acr_f64(frame, n):
     out = torch.empty(1, dtype=torch.float64, device=dev)
     _check(L.dspfe_acr_f64(x.data_ptr(), x.numel(), int(n), out.data_ptr(), _stream(torch, dev)))
     return np.float64(out.cpu().numpy()[0])
+
+
+def cmvn_pad_batch(feat, frame_off, numcep=13, T=200, out=None):
+    """The reference trainer's batching epilogue (model.py:75-88, :35-50, :131-135) on device tensors: feat float32
+    [rows, 3*numcep] and frame_off int64 [U+1] as written by MfccPlan.mfcc_delta.  Returns (inp float32 [T, U, 3*numcep],
+    len0 int32 [U])."""
+    import torch
+    L = lib(); _bind_helpers(L)
+    assert feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous() and feat.shape[1] == 3 * numcep
+    n_utt = frame_off.numel() - 1
+    if out is None:
+        out = torch.empty((T, n_utt, 3 * numcep), dtype=torch.float32, device=feat.device)
+    len0 = torch.empty(n_utt, dtype=torch.int32, device=feat.device)
+    _check(L.dspfe_cmvn_pad_batch(feat.data_ptr(), frame_off.data_ptr(), n_utt, int(numcep), int(T), out.data_ptr(), len0.data_ptr(),
+                                  _stream(torch, feat.device)))
+    return out, len0
+
+
+def amplitude_rule_gated_host(amp, gate, mh=0.25, **kw):
+    """amplitude_rule(use_acr=True) on a float64 list and the per-frame acr_rule flags."""
+    p = endpoint_params(**kw)
+    amp = np.ascontiguousarray(amp, dtype=np.float64)
+    gate = np.ascontiguousarray(gate, dtype=np.int32)
+    segs = np.zeros((max(len(amp), 1), 2), dtype=np.int32)
+    n = ctypes.c_int32(0)
+    _check(lib().dspfe_amplitude_rule_gated_host(ctypes.byref(p), _np_ptr(amp), _np_ptr(gate), len(amp), float(mh), _np_ptr(segs),
+                                                 len(segs), ctypes.byref(n)))
+    return [(int(j), int(k)) for j, k in segs[: n.value]]
+
+
+def acr_gate_rows_f64(frames, rate):
+    """acr_rule (reference endpoint.py:142-144) of every row of a float64 frame matrix, on the device: int32 flags."""
+    torch, dev = _cuda()
+    L = lib(); _bind_endpoint(L)
+    f = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64)).to(dev)
+    g = torch.empty(f.shape[0], dtype=torch.int32, device=dev)
+    _check(L.dspfe_acr_gate_rows_f64(f.data_ptr(), f.shape[0], f.shape[1], int(rate), g.data_ptr(), _stream(torch, dev)))
+    return g.cpu().numpy()

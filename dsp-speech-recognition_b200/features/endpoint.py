@@ -56,8 +56,15 @@ def basic_endpoint_detection(sig, rate, return_feature=False):
 
 
 def robust_endpoint_detection(sig, rate):
-    """reference endpoint.py:68-92 (autocorrelation-gated expansion): listed as "next" (SURVEY f-3)."""
-    raise NotImplementedError("robust_endpoint_detection (acr-gated rule) is not built yet; see DESIGN.md, row f-3")
+    """reference endpoint.py:68-92 on the device: amplitude_rule(mh=0.5) gated by the autocorrelation peak of each frame
+    (exact integer lag sums), zcr_rule, whole-signal fallback.  Returns Python ints (left, right) in samples."""
+    cfg_frame, cfg_step = _gpu.cfg_frame_step()
+    x, f32 = _gpu.pack_one(sig)
+    if f32:
+        raise NotImplementedError("endpoint detection is built for int16-valued PCM (what reader.py delivers)")
+    plan = _gpu.endpoint_plan(int(rate), cfg_frame, cfg_step)
+    lr = plan.detect_robust_host(x, np.array([0, len(x)], dtype=np.int64))
+    return int(lr[0, 0]), int(lr[0, 1])
 
 
 def get_noise(amp, sep_point):
@@ -90,9 +97,11 @@ def amplitude_feature(sig, rate, winlen, step):
 def amplitude_rule(amp, mh=0.25, th=0.100, l_sil=0.100, r_sil=0.100, sigma=3, use_acr=False, frames=None, rate=None):
     """reference endpoint.py:133-179: list of (j, k) frame segments, or [(0, len(amp))].  Runs the C++ rule that
     the device kernel K3 runs (csrc/endpoint_kernel.cuh), through dspfe_amplitude_rule_host."""
-    if use_acr:
-        raise NotImplementedError("the autocorrelation gate is not built yet (SURVEY f-3)")
     cfg_frame, cfg_step = _gpu.cfg_frame_step()
+    if use_acr:   # acr_rule of every frame on the device, then the same C++ rule with the gate
+        gate = dspfe.acr_gate_rows_f64(np.asarray(frames, dtype=np.float64), int(rate))
+        return dspfe.amplitude_rule_gated_host([float(a) for a in amp], gate, mh, cfg_frame=cfg_frame, cfg_step=cfg_step, th=float(th),
+                                               l_sil=float(l_sil), r_sil=float(r_sil), sigma=float(sigma))
     return dspfe.amplitude_rule_host([float(a) for a in amp], mh, cfg_frame=cfg_frame, cfg_step=cfg_step, th=float(th),
                                      l_sil=float(l_sil), r_sil=float(r_sil), sigma=float(sigma))
 

@@ -163,6 +163,18 @@ int dspfe_endpoint(dspfe_endpoint_plan* plan, const int16_t* d_pcm, int64_t tota
 int dspfe_endpoint_host(dspfe_endpoint_plan* plan, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt,
                         int32_t* h_lr, int32_t* h_asum, int32_t* h_zcr, int64_t* h_frame_off);
 
+/* robust_endpoint_detection (endpoint.py:68-92): the same frame statistics, amplitude_rule(mh = 0.5) whose expansion is
+ * gated by acr_rule (endpoint.py:142-144: max over lags rate//500 .. rate//50 of acr(frame, n) / acr(frame, 0) > 0.55,
+ * evaluated from exact integer lag sums), zcr_rule and the whole-signal fallback.  d_lr / h_lr [n_utt,2] int32. */
+int dspfe_endpoint_robust(dspfe_endpoint_plan* plan, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets,
+                          int32_t n_utt, int32_t* d_lr, void* stream);
+int dspfe_endpoint_robust_host(dspfe_endpoint_plan* plan, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt, int32_t* h_lr);
+/* List form of amplitude_rule(use_acr=True) (endpoint.py:133): gate[n_frames] (0/1) is acr_rule of every frame, which
+ * dspfe_acr_gate_rows_f64 computes on the device for a float64 frame matrix [n_rows, len]. */
+int dspfe_amplitude_rule_gated_host(const dspfe_endpoint_params* p, const double* amp, const int32_t* gate, int32_t n_frames, double mh,
+                                    int32_t* segs, int32_t seg_cap, int32_t* n_segs);
+int dspfe_acr_gate_rows_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t samplerate, int32_t* d_gate, void* stream);
+
 /* Host-only (no CUDA): the decision rule on precomputed frame statistics; lets CPU-only tests check the
  * float64 rule replay (NumPy summation order included) against the oracle. */
 int dspfe_endpoint_decide_host(const dspfe_endpoint_params* p, const int32_t* asum, const int32_t* zcr, int32_t n_frames,
@@ -257,6 +269,12 @@ int dspfe_preemphasis_f64(const double* d_x, int64_t n, double coeff, double* d_
 int dspfe_row_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t use_sq, double* d_out, void* stream);
 /* get_zcr(frames) (endpoint.py:182) */
 int dspfe_row_zcr_f64(const double* d_frames, int64_t n_rows, int32_t len, int64_t* d_out, void* stream);
+/* Caller-side batching epilogue of the reference trainer (model.py:75-88, :35-50, :131-135) on K1's rows
+ * [F_total, 3*numcep]: the static block is standardised per utterance and column (sklearn scale: population std over
+ * all frames, constant columns only centred), delta / delta-delta are passed through, every utterance is truncated or
+ * zero padded to T frames, and the batch is written time-major: d_out [T, n_utt, 3*numcep]; d_len0 [n_utt] = min(F, T). */
+int dspfe_cmvn_pad_batch(const float* d_feat, const int64_t* d_frame_off, int32_t n_utt, int32_t numcep, int32_t T, float* d_out,
+                         int32_t* d_len0, void* stream);
 /* window (sigproc.py:22-46): causal complex FIR band-pass of a real signal, d_y [n,2] = (re, im) float64 */
 int dspfe_fir_window_f64(const double* d_x, int32_t n, double rate, double low_freq, double high_freq, int32_t hamming,
                          double* d_y, void* stream);

@@ -627,3 +627,36 @@ def pitch_feature(sig, rate, gender="male"):
     s1, _ = find_smooth_subsequence(pitch[p_bias:p], bias=p_bias)
     s2, _ = find_smooth_subsequence(pitch[p:], bias=p)
     return slope(s1), slope(s2), quad_params(s1), quad_params(s2), peakshift(s1, s2)
+
+
+# --------------------------------------------------------------------------
+# model.py glue around the features (the "next" row f-1 of SURVEY.md section 8)
+# --------------------------------------------------------------------------
+def sk_scale(x, with_mean=True):
+    """sklearn.preprocessing.scale(x) on a 2-D array, axis 0: population std, constant columns are not divided."""
+    x = np.asarray(x, dtype=np.float64)
+    mean = x.mean(axis=0) if with_mean else np.zeros(x.shape[1])
+    sd = x.std(axis=0)
+    sd = np.where(sd < 10 * np.finfo(np.float64).eps, 1.0, sd)
+    return (x - mean) / sd
+
+
+def model_batch(utterances, rate=16000, T=200, N=3, scale_signal=True, **mfcc_kw):
+    """model.py:52-64 (endpoint_detect without augmentation), :66-88 (feature_extract_mfcc), :35-50 (pad), :114-135
+    (get_batch_full): returns (inp float64 [T, B, 39], len0 int array)."""
+    feats, len0 = [], []
+    for sig in utterances:
+        l, r = basic_endpoint_detection(sig, rate)
+        sound = np.asarray(sig[l:r], dtype=np.float64).reshape(-1, 1)
+        if scale_signal:
+            sound = sk_scale(sound, with_mean=False)              # model.py:62-63
+        m0 = mfcc(sound.reshape(-1), rate, **mfcc_kw)
+        m0 = m0 - np.mean(m0)                                     # model.py:75
+        d1 = delta(m0, N)
+        d2 = delta(d1, N)
+        m0 = sk_scale(m0)                                         # model.py:78
+        f = np.concatenate([m0, d1, d2], axis=1)
+        f = np.pad(f, ((0, T - len(f)), (0, 0))) if len(f) < T else f[:T]   # model.py:35-39
+        feats.append(f)
+        len0.append(min(len(m0), T))
+    return np.stack(feats).transpose(1, 0, 2), np.array(len0)

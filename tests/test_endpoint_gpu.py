@@ -97,3 +97,35 @@ def test_config4_ragged_endpoint_then_mfcc():
         l, r = O.basic_endpoint_detection(x, 16000)
         assert (int(lr_h[u, 0]), int(lr_h[u, 1])) == (l, r)
         assert_mfcc_close(out[fo_h[u]:fo_h[u + 1]].cpu().numpy(), O.mfcc_delta39(x[l:r], 3), what=f"C4 utt {u}")
+
+
+def test_robust_endpoint_detection_vs_oracle():
+    """the autocorrelation-gated rule, bit-exact (integer lag sums)."""
+    import torch
+    import dspfe
+    import features
+    from dspfe import synth
+    from oracle import ref_features as O
+    lengths = synth.ragged_lengths(48, seed=8, lo=8000, hi=48000)
+    lengths[:4] = [300, 480, 9000, 170000]
+    pcm, off = synth.synth_batch(lengths, seed0=8100)
+    plan = dspfe.EndpointPlan()
+    lr = plan.detect_robust_host(pcm, off)
+    dev = torch.device("cuda:0")
+    lr_d = plan.detect_robust(torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(lr_d.cpu().numpy(), lr)
+    differs_from_basic = 0
+    for u in range(len(lengths)):
+        x = pcm[off[u]:off[u + 1]]
+        want = O.robust_endpoint_detection(x, 16000)
+        assert (int(lr[u, 0]), int(lr[u, 1])) == want, u
+        differs_from_basic += want != O.basic_endpoint_detection(x, 16000)
+    assert differs_from_basic > 0          # the gate must actually bite on this set
+    x = pcm[off[5]:off[6]]
+    assert features.robust_endpoint_detection(x, 16000) == O.robust_endpoint_detection(x, 16000)
+    # list-typed API: amplitude_rule(use_acr=True, frames=..., rate=...)
+    frames = O.to_frames(x, 16000, 0.03, 0.01)
+    amp = O.get_amplitude(frames)
+    assert features.amplitude_rule(amp, 0.5, frames=frames, use_acr=True, rate=16000) == \
+        O.amplitude_rule(amp, 0.5, frames=frames, use_acr=True, rate=16000)

@@ -139,3 +139,28 @@ def test_errors(torch_dev):
     pcm = torch.zeros(1001, dtype=torch.int16, device=dev)
     with pytest.raises(dspfe.DspfeError):          # misaligned base pointer
         plan.mfcc_delta(pcm[1:], torch.tensor([0, 1000], device=dev))
+
+
+def test_model_batch_epilogue_cmvn_pad():
+    """endpoint -> MFCC+delta+delta-delta on sig[l:r] -> per-utterance CMVN of the static block -> pad /
+    truncate to 200 frames -> [T, B, 39], all on the device, against the restated model.py glue (which also scales the
+    signal by its std first: that only shifts c0 by a constant the CMVN removes)."""
+    import torch
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    dev = torch.device("cuda:0")
+    lengths = [16000, 52000, 9000, 33333, 70000]
+    pcm, off = synth.synth_batch(lengths, seed0=640)
+    pcm_d, off_d = torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev)
+    lr = dspfe.EndpointPlan().detect(pcm_d, off_d)
+    feat, fo = dspfe.MfccPlan(delta_n=3).mfcc_delta(pcm_d, off_d, trim=lr)
+    inp, len0 = dspfe.cmvn_pad_batch(feat, fo)
+    torch.cuda.synchronize()
+    want, wl = O.model_batch([pcm[off[u]:off[u + 1]] for u in range(len(lengths))])
+    assert inp.shape == (200, len(lengths), 39)
+    np.testing.assert_array_equal(len0.cpu().numpy(), wl)
+    got = inp.cpu().numpy()
+    assert np.max(np.abs(got - want) / (1 + np.abs(want))) <= 2e-4      # standardisation divides by a column std < 1 for some columns
+    for u, n in enumerate(wl):
+        assert not got[n:, u].any()                                      # zero padding beyond the utterance
