@@ -303,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
 def run_frontend(args, rank, world, local_rank):
     """--workload frontend: ragged 0.5-5 s utterances (U per GPU, LPT-sharded from one global list), every path of the
     front-end per step: endpoints -> MFCC+delta+delta-delta on sig[l:r] -> cepstrum pitch + pitch_feature on
-    preemphasis(sig)[l:r] -> autocorrelation pitch.  Device-resident; audio-s/s over all ranks."""
+    preemphasis(sig)[l:r] -> autocorrelation pitch on sig[l:r] (300-sample frames, as model.py:92 calls it).  Device-resident; audio-s/s over all ranks."""
     import torch
     import torch.distributed as dist
     import dspfe
@@ -322,7 +322,8 @@ def run_frontend(args, rank, world, local_rank):
     off_d = off.to(dev)
     n_utt = len(lengths)
     ep, mf = dspfe.EndpointPlan(), dspfe.MfccPlan(delta_n=DELTA_N)
-    cep, acr = dspfe.PitchPlan(method=0, preemph=0.97), dspfe.PitchPlan(method=1)
+    cep = dspfe.PitchPlan(method=0, preemph=0.97)          # pitch_model.py:38-41
+    acr = dspfe.PitchPlan(method=1, frame_len=300)          # model.py:92: pitch_detect_sr(sound, winlen=cfg.frame) on the trimmed signal
     out = torch.empty((mf.rows_bound(pcm.numel(), n_utt), 3 * NUMCEP), dtype=torch.float32, device=dev)
     fo = torch.empty(n_utt + 1, dtype=torch.int64, device=dev)
     bufs = {}
@@ -331,7 +332,7 @@ def run_frontend(args, rank, world, local_rank):
         lr = ep.detect(pcm, off_d)
         mf.mfcc_delta(pcm, off_d, trim=lr, out=out, frame_off=fo)
         bufs["cep"] = cep.detect(pcm, off_d, trim=lr, want_feat=True, out=bufs.get("cep"))
-        bufs["acr"] = acr.detect(pcm, off_d, out=bufs.get("acr"))
+        bufs["acr"] = acr.detect(pcm, off_d, trim=lr, out=bufs.get("acr"))
 
     def barrier():
         if world > 1:

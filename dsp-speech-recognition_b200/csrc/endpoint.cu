@@ -160,6 +160,7 @@ int dspfe_endpoint(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_
     if (!pl || !d_offsets || !d_lr || n_utt < 0 || total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
     if (n_utt == 0) return DSPFE_OK;
     if (!d_pcm && total_samples > 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm is null");
+    if (((uintptr_t)d_pcm & 15) != 0) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm must be 16-byte aligned");
     const int64_t frames_bound = dspfe_endpoint_frames_bound(pl, total_samples, n_utt);
     if ((d_asum || d_zcr) && max_frames < frames_bound) return fail(DSPFE_ERR_INVALID_ARG, "max_frames is below dspfe_endpoint_frames_bound()");
     const int64_t blocks_bound = frames_bound + (int64_t)n_utt * (pl->q + 1);
@@ -173,7 +174,7 @@ int dspfe_endpoint(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_
     p.max_blocks = blocks_bound; p.max_frames = frames_bound; p.rule = pl->rule;
     ep_prep_kernel<<<1, kEpPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("ep_prep_kernel", st);
-    ep_block_kernel<<<(unsigned)((blocks_bound + 7) / 8), 256, 0, st>>>(p);
+    ep_block_kernel<<<(unsigned)((blocks_bound + 127) / 128), 128, 0, st>>>(p);
     LAUNCH_CHECK("ep_block_kernel", st);
     ep_frame_kernel<<<(unsigned)((frames_bound + 255) / 256), 256, 0, st>>>(p);
     LAUNCH_CHECK("ep_frame_kernel", st);

@@ -249,44 +249,67 @@ __device__ inline int find_owner(const int64_t* off, int n, int64_t g) {
     return lo;
 }
 
-// K2a: one warp per hop block
-__global__ void __launch_bounds__(256) ep_block_kernel(EpParams p) {
-    const int64_t g = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+// K2a: one THREAD per hop block (frame_step samples): the lane streams its own hop with 16-byte loads and keeps the
+// four running integers in registers, so there is no cross-lane reduction and a warp retires 32 hops per pass
+// (the first version spent one warp and a five-step shuffle reduction on every hop).  Utterance starts are only
+// 2-byte aligned: the aligned middle of the hop goes through uint4 loads, the few samples either side through
+// scalar loads.  Samples past the end of the utterance are zeros (sigproc.py:84-87).
+struct HopAcc {
+    int A, Z, A2, Z2;   // sum |x|, sign changes between neighbours inside the hop; the same over the first `rem` samples
+    int prev; int i;    // previous sample, index of the next sample inside the hop
+};
+__device__ __forceinline__ void hop_push(HopAcc& h, int v, int rem) {
+    const int a = v < 0 ? -v : v;
+    const int zc = (h.prev * v) < 0 ? 1 : 0;        // |x| <= 32768: the product fits
+    h.A += a;
+    if (h.i > 0) h.Z += zc;                           // pair (i-1, i)
+    if (h.i < rem) { h.A2 += a; if (h.i > 0) h.Z2 += zc; }
+    h.prev = v; ++h.i;
+}
+// eight samples of an aligned vector, none masked, rem == 0: the fast path
+__device__ __forceinline__ void hop_push8(HopAcc& h, uint4 w) {
+    int v[8];
+    v[0] = (int)(short)(w.x & 0xffffu); v[1] = (int)w.x >> 16; v[2] = (int)(short)(w.y & 0xffffu); v[3] = (int)w.y >> 16;
+    v[4] = (int)(short)(w.z & 0xffffu); v[5] = (int)w.z >> 16; v[6] = (int)(short)(w.w & 0xffffu); v[7] = (int)w.w >> 16;
+    int a = 0, z = ((h.prev * v[0]) >> 31) & (h.i > 0 ? 1 : 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += v[k] < 0 ? -v[k] : v[k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) z += (unsigned)(v[k] * v[k + 1]) >> 31;
+    h.A += a; h.Z += z; h.prev = v[7]; h.i += 8;
+}
+__global__ void __launch_bounds__(128) ep_block_kernel(EpParams p) {
+    const int64_t g = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (g >= p.block_off[p.n_utt] || g >= p.max_blocks) return;
     const int u = find_owner(p.block_off, p.n_utt, g);
     const int64_t b = g - p.block_off[u];
     const int64_t base = p.offsets[u];
     const int64_t S = p.offsets[u + 1] - base;
-    const int64_t s0 = b * p.frame_step;
+    const int64_t s0 = b * p.frame_step;                 // first sample of the hop inside the utterance
     const int16_t* x = p.pcm + base;
-    int A = 0, Z = 0, A2 = 0, Z2 = 0;
-    for (int i = lane; i < p.frame_step; i += 32) {
-        const int64_t s = s0 + i;
-        const int v = s < S ? (int)x[s] : 0;
-        const int w = (s + 1 < S) ? (int)x[s + 1] : 0;
-        const int a = v < 0 ? -v : v;
-        const int zc = (v * w < 0) ? 1 : 0;
-        A += a;
-        if (i + 1 < p.frame_step) Z += zc;            // pair inside the block
-        if (i < p.rem) A2 += a;
-        if (i + 1 < p.rem) Z2 += zc;
-    }
+    const int step = p.frame_step, rem = p.rem;
+    HopAcc h{0, 0, 0, 0, 0, 0};
     int C = 0;
-    if (lane == 0) {   // pair across the boundary to the next block
-        const int64_t s = s0 + p.frame_step - 1;
-        const int v = s < S ? (int)x[s] : 0, w = (s + 1 < S) ? (int)x[s + 1] : 0;
-        C = (v * w < 0) ? 1 : 0;
+    if (s0 < S) {
+        const int64_t n_in = S - s0 < step ? S - s0 : step;          // samples of the hop that exist
+        // head: up to the next 16-byte boundary of the packed buffer
+        const int64_t addr0 = base + s0;                              // sample index in the packed buffer
+        int head = (int)((8 - (addr0 & 7)) & 7);
+        if (head > n_in) head = (int)n_in;
+        int i = 0;
+        for (; i < head; ++i) hop_push(h, (int)x[s0 + i], rem);
+        if (rem == 0) {
+            const uint4* xv = reinterpret_cast<const uint4*>(p.pcm + addr0 + head);
+            const int nvec = (int)((n_in - head) >> 3);
+            for (int k = 0; k < nvec; ++k) hop_push8(h, __ldg(xv + k));
+            i += 8 * nvec;
+        }
+        for (; i < n_in; ++i) hop_push(h, (int)x[s0 + i], rem);
+        // pair across the boundary to the next hop (the next sample may be past the end: zero)
+        if (n_in == step) { const int w = (s0 + step < S) ? (int)x[s0 + step] : 0; C = (h.prev * w) < 0 ? 1 : 0; }
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        A += __shfl_xor_sync(0xffffffffu, A, m); Z += __shfl_xor_sync(0xffffffffu, Z, m);
-        A2 += __shfl_xor_sync(0xffffffffu, A2, m); Z2 += __shfl_xor_sync(0xffffffffu, Z2, m);
-    }
-    if (lane == 0) {
-        int32_t* o = p.blk + g * 6;
-        o[0] = A; o[1] = Z; o[2] = C; o[3] = A2; o[4] = Z2; o[5] = 0;
-    }
+    int32_t* o = p.blk + g * 6;
+    o[0] = h.A; o[1] = h.Z; o[2] = C; o[3] = h.A2; o[4] = h.Z2; o[5] = 0;
 }
 
 // K2b: one thread per frame

@@ -374,7 +374,8 @@ DEVFN int find_utt(const int64_t* frame_off, int n_utt, int64_t g, int lane) {
 struct FrameCursor {
     const unsigned char* src;   // sample s of the (trimmed) utterance lives at src + s * esz (global memory or the staged copy)
     int lim;      // relative index of the utterance's first sample (<= 0): pre-emphasis reaches back to it
-    int Ld, k, a, b;
+    int nvalid;   // the lane's samples t < nvalid lie inside both the frame and the decimated signal
+    int a, b;     // k - 1 = a * ds_out + b for the lane's current decimated index k
 };
 constexpr int kStageBytes = 4096;   // per frame; the span of a 512-sample frame at 16 kHz -> 10 kHz is 1.7 KB of int16
 // Stages the source span of one frame in shared memory with 16-byte loads (one DRAM latency for the whole frame
@@ -386,12 +387,14 @@ DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane,
     const unsigned char* pcm = reinterpret_cast<const unsigned char*>(p.pcm);
     c.src = pcm + start * esz;
     c.lim = (int)(p.offsets[u] - start);
-    c.Ld = valid ? p.ds_len[u] : 0;
+    const int Ld = valid ? p.ds_len[u] : 0;
     const int kf = (int)(g - p.frame_off[u]) * p.frame_step;
-    c.k = kf + lane;
-    c.a = c.k >= 1 ? (c.k - 1) / p.ds_out : -1;
-    c.b = c.k >= 1 ? (c.k - 1) - c.a * p.ds_out : p.ds_out - 1;
-    const int kl = kf + p.frame_len - 1 < c.Ld - 1 ? kf + p.frame_len - 1 : c.Ld - 1;
+    const int k = kf + lane;
+    c.a = k >= 1 ? (k - 1) / p.ds_out : -1;                    // k = 0 starts from -1 = (-1, ds_out - 1): its index
+    c.b = k >= 1 ? (k - 1) - c.a * p.ds_out : p.ds_out - 1;    // a*ds_in + ds_idx[b] is negative and clamps to sample 0
+    const int kl = kf + p.frame_len - 1 < Ld - 1 ? kf + p.frame_len - 1 : Ld - 1;
+    const int nlim = (p.frame_len < Ld - kf ? p.frame_len : Ld - kf) - lane;   // samples n = lane + 32 t with n < min(L, Ld - kf)
+    c.nvalid = nlim > 0 ? (nlim + 31) >> 5 : 0;
     if (kf <= kl) {
         int s_lo = (int)ds_index(kf, p.ds_idx, p.ds_in, p.ds_out) - 1;
         if (s_lo < c.lim) s_lo = c.lim;
@@ -412,24 +415,39 @@ DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane,
 }
 // one sample: pre-emphasised over the whole utterance (preprocess.py:11-19), zero past the decimated length
 // (sigproc.py:84-87); then the cursor moves on by 32 decimated samples
-DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds_idx, int n) {
+template <bool F32>
+DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds_idx, int t) {
     float v = 0.f;
-    if (n < p.frame_len && c.k < c.Ld) {
-        const int s = c.k == 0 ? 0 : c.a * p.ds_in + ds_idx[c.b];   // sample index inside the (trimmed) utterance
+    if (t < c.nvalid) {
+        int s = c.a * p.ds_in + ds_idx[c.b];   // sample index inside the (trimmed) utterance
+        s = s > 0 ? s : 0;
         float cur, prev = 0.f;
-        if (p.in_f32) {
+        if (F32) {
             const float* q = reinterpret_cast<const float*>(c.src) + s;
             cur = q[0]; if (s > c.lim) prev = q[-1];
         } else {
             const int16_t* q = reinterpret_cast<const int16_t*>(c.src) + s;
             cur = cvt_i16(q[0]); if (s > c.lim) prev = cvt_i16(q[-1]);
         }
-        // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one
-        v = p.pre_hi != 0.f ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
+        // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one;
+        // pre_hi = pre_lo = 0 leaves the sample as it is
+        v = dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur));
     }
-    c.k += 32; c.a += p.ds_q32; c.b += p.ds_r32;
+    c.a += p.ds_q32; c.b += p.ds_r32;
     if (c.b >= p.ds_out) { c.b -= p.ds_out; ++c.a; }
     return v;
+}
+template <bool F32>
+DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb) {
+#pragma unroll 1
+    for (int t0 = 0; t0 < 16; t0 += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float va = frame_sample<F32>(p, ca, ds_idx, t0 + j), vb = frame_sample<F32>(p, cb, ds_idx, t0 + j);
+            xs[32 * (t0 + j) + lane] = make_float2(va, vb);
+            fa += fabsf(va); fb += fabsf(vb);
+        }
+    }
 }
 
 // Two consecutive frames (g0, g0 + 1) per warp: gather + clip + FIR band-pass + (cepstrum | autocorrelation)
@@ -463,16 +481,8 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
         FrameCursor ca = frame_cursor(p, g0, ua, lane, true, stage);
         FrameCursor cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB, stage + kStageBytes);
         float fa = 0.f, fb = 0.f;
-#pragma unroll 1
-        for (int t0 = 0; t0 < 16; t0 += 4) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 32 * (t0 + j) + lane;
-                const float va = frame_sample(p, ca, ds_idx, n), vb = frame_sample(p, cb, ds_idx, n);
-                xs[n] = make_float2(va, vb);
-                fa += fabsf(va); fb += fabsf(vb);
-            }
-        }
+        if (p.in_f32) gather_pair<true>(p, ca, cb, ds_idx, xs, lane, fa, fb);
+        else gather_pair<false>(p, ca, cb, ds_idx, xs, lane, fa, fb);
         float xa[16], xb[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) { const float2 v = xs[32 * t + lane]; xa[t] = v.x; xb[t] = v.y; }

@@ -19,7 +19,7 @@ pcm, off = synth.synth_batch_torch(lengths, seed0=31337, device=dev)
 off_d = off.to(dev)
 audio_s = float(lengths.sum()) / 16000
 ep, mf = dspfe.EndpointPlan(), dspfe.MfccPlan(delta_n=2)
-cep, acr = dspfe.PitchPlan(method=0, preemph=0.97), dspfe.PitchPlan(method=1)
+cep, acr = dspfe.PitchPlan(method=0, preemph=0.97), dspfe.PitchPlan(method=1, frame_len=300)
 lr = ep.detect(pcm, off_d)
 bufs = {}
 
@@ -43,5 +43,5 @@ timed("endpoint", lambda: ep.detect(pcm, off_d))
 timed("mfcc_delta (trimmed)", lambda: mf.mfcc_delta(pcm, off_d, trim=lr, out=out, frame_off=fo))
 o1 = cep.detect(pcm, off_d, trim=lr, want_feat=True)
 timed("pitch_cepstrum + pitch_feature", lambda: cep.detect(pcm, off_d, trim=lr, want_feat=True, out=o1))
-o2 = acr.detect(pcm, off_d)
-timed("pitch_autocorrelation", lambda: acr.detect(pcm, off_d, out=o2))
+o2 = acr.detect(pcm, off_d, trim=lr)
+timed("pitch_autocorrelation (trimmed, 300-sample frames)", lambda: acr.detect(pcm, off_d, trim=lr, out=o2))
