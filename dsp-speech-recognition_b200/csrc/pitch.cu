@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const 
 __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* chunk = reinterpret_cast<float*>(smem);
-    int* sc = reinterpret_cast<int*>(chunk + (kTrackChunk + 1) * p.row_len);
-    pitch_track_cta(p, chunk, sc, reinterpret_cast<double*>(sc + kTrackChunk * kPeakLags));
+    int* sc = reinterpret_cast<int*>(chunk + (track_chunk(p.row_len) + 1) * p.row_len);
+    pitch_track_cta(p, chunk, sc, reinterpret_cast<double*>(sc + track_chunk(p.row_len) * kPeakLags));
 }
 
 __global__ void __launch_bounds__(32) pitch_feature_kernel(const __grid_constant__ PitchParams p) {
@@ -145,7 +145,7 @@ int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
     return DSPFE_OK;
 }
 
-int track_smem(int row_len) { return (kTrackChunk + 1) * row_len * (int)sizeof(float) + kTrackChunk * kPeakLags * (int)sizeof(int) + kTrackMaxFrames * 12; }
+int track_smem(int row_len) { return (track_chunk(row_len) + 1) * row_len * (int)sizeof(float) + track_chunk(row_len) * kPeakLags * (int)sizeof(int) + kTrackMaxFrames * 12; }
 
 }  // namespace
 

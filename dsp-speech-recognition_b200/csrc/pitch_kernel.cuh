@@ -51,7 +51,8 @@ constexpr int kTabTw = 0, kTabW32 = kTabTw + 512, kTabMod = kTabW32 + 32, kTabHe
 constexpr int kFrameCtaSmem = (kTabMod * 8) + kMaxDsOut * 4 + kPitchWarps * kWarpSmemBytes;   // shared tables | ds_idx | per-warp areas
 constexpr int kTrackThreads = 256;
 constexpr int kTrackMaxFrames = 1024;   // utterances up to this many frames keep their lag / Hz track in shared memory
-constexpr int kTrackChunk = 16;     // frames smoothed per pass of K4b/K5b
+constexpr int kTrackChunk = 32;     // frames smoothed per pass of K4b/K5b (16 for rows wider than 256 columns)
+DSP_HD int track_chunk(int row_len) { return row_len <= 256 ? kTrackChunk : kTrackChunk / 2; }
 
 struct PitchParams {
     const void* pcm; int in_f32;         // packed samples: int16 or float32 (16-byte aligned base)
@@ -618,7 +619,8 @@ DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, uns
 // raw rows of the chunk (plus one row of look-ahead) in shared memory with coalesced vector loads, then runs the
 // reference's in-place running mean on them (one column per thread; rows < i are already smoothed, exactly the
 // reference's recurrence), scores the rows in parallel and takes the arg-max with one warp per row.
-// smem: float buf[(kTrackChunk + 1) * row_len] + int sc[kTrackChunk * 80] + double spitch[kTrackMaxFrames] + int slag[kTrackMaxFrames].
+// smem (CH = track_chunk(row_len)): float buf[(CH + 1) * row_len] + int sc[CH * 80] + double spitch[kTrackMaxFrames]
+//       + int slag[kTrackMaxFrames].
 DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* spitch) {
     const int u = simt::bid();
     const int tid = simt::tid();
@@ -626,6 +628,7 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
     const int RL = p.row_len;
+    const int CH = track_chunk(RL);
     const float* rows = p.rows + f0 * RL;
     // the lag track stays in shared memory for the octave-repair sweeps (a thread walking global memory on its own
     // pays a DRAM latency per frame); longer utterances use the global arrays directly
@@ -633,8 +636,8 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
     const bool staged = F <= kTrackMaxFrames;
     int32_t* lagv = staged ? slag : p.lag + f0;
     float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};    // smoothed rows i-1 and i-2 of this thread's (up to two) columns
-    for (int c0 = 0; c0 < F; c0 += kTrackChunk) {
-        const int nrows = F - c0 < kTrackChunk ? F - c0 : kTrackChunk;
+    for (int c0 = 0; c0 < F; c0 += CH) {
+        const int nrows = F - c0 < CH ? F - c0 : CH;
         const int nload = (c0 + nrows < F ? nrows + 1 : nrows) * RL;          // floats to stage (rows are contiguous)
         const float* src = rows + (int64_t)c0 * RL;
         if ((RL & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
@@ -730,7 +733,16 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
         if (tid == 0 && F > 0 && p.pitch) robust_pitch(p.lag + f0, F, p.pitch + f0);
         return;
     }
-    if (tid == 0 && p.pitch) robust_pitch(slag, F, spitch);
+    // max_pitch (pitch.py:166-172) for every frame in parallel, then the two sequential octave-repair sweeps
+    // (robust_max_pitch, pitch.py:191-206) on one thread: compares and doublings only
+    for (int i = tid; i < F; i += kTrackThreads) spitch[i] = 1.0 / (0.0001 * (double)slag[i]);
+    simt::cta_sync();
+    if (tid == 0 && p.pitch) {
+        for (int i = 1; i < F; ++i)
+            if (fabs(2 * spitch[i] - spitch[i - 1]) < 50 && spitch[i] < 170) spitch[i] = 2 * spitch[i];
+        for (int i = F - 2; i > 0; --i)
+            if (fabs(2 * spitch[i] - spitch[i + 1]) < 50 && spitch[i] < 170) spitch[i] = 2 * spitch[i];
+    }
     simt::cta_sync();
     for (int i = tid; i < F; i += kTrackThreads) {
         p.lag[f0 + i] = slag[i];

@@ -27,8 +27,8 @@ void frame_body(void* a) {
 void track_body(void* a) {
     Args* A = (Args*)a;
     float* chunk = reinterpret_cast<float*>(A->smem->data());
-    int* sc = reinterpret_cast<int*>(chunk + (kTrackChunk + 1) * A->p.row_len);
-    pitch_track_cta(A->p, chunk, sc, reinterpret_cast<double*>(sc + kTrackChunk * kPeakLags));
+    int* sc = reinterpret_cast<int*>(chunk + (track_chunk(A->p.row_len) + 1) * A->p.row_len);
+    pitch_track_cta(A->p, chunk, sc, reinterpret_cast<double*>(sc + track_chunk(A->p.row_len) * kPeakLags));
 }
 void feature_body(void* a) {
     Args* A = (Args*)a;
@@ -76,7 +76,7 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
         std::memset(smem.data(), 0xCD, smem.size());
         if (!emu::run_cta((int)b, 32 * kPitchWarps, frame_body, &A)) { std::snprintf(errbuf, errcap, "deadlock in frame CTA %lld", (long long)b); return -3; }
     }
-    std::vector<unsigned char> smem2((kTrackChunk + 1) * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + kTrackMaxFrames * 12 + 64);
+    std::vector<unsigned char> smem2((track_chunk(p.row_len) + 1) * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + kTrackMaxFrames * 12 + 64);
     Args B{p, &smem2, fo};
     for (int u = 0; u < n_utt; ++u) {
         std::memset(smem2.data(), 0xCD, smem2.size());
