@@ -674,21 +674,45 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
         if (p.mode == 0) {
             // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk: min over both sides of the
             // distance to the nearest sample that is not <= the lag's value (the left scan ends at index 0, the right
-            // one at the row end).  Only the smaller distance matters, so both sides expand together and the search
-            // ends at the first stopper on either side.
-            for (int t = tid; t < nrows * kPeakLags; t += kTrackThreads) {
-                const int k = t / kPeakLags, c = kMinLag + t % kPeakLags;
+            // one at the row end).  Only the smaller distance matters, so both sides expand together.  Most lags stop
+            // within a few samples; the few real peaks would keep a whole warp spinning, so after four steps the
+            // unfinished lags are finished one at a time with the 32 lanes spread over the distances.
+            const int ntask = nrows * kPeakLags;
+            for (int t0 = warp * 32; t0 < ntask; t0 += kTrackThreads) {
+                const int t = t0 + lane;
+                const bool live = t < ntask;
+                const int k = live ? t / kPeakLags : 0, c = kMinLag + (live ? t % kPeakLags : 0);
                 const float* row = buf + k * RL;
                 const float v = row[c];
-                int sv = 0;                                   // a NaN value stops both scans at once
-                if (v == v) {
-                    const int rmax = c < RL - c ? c : RL - c; // index 0 / the row end stop the scans
+                const int rmax = c < RL - c ? c : RL - c;         // index 0 / the row end stop the scans
+                int sv = 0;                                       // a NaN value stops both scans at once
+                bool open = false;
+                if (live && v == v) {
                     int r = 1;
-                    while (r < rmax && row[c - r] <= v && row[c + r] <= v) ++r;
+                    while (r < rmax && r <= 4 && row[c - r] <= v && row[c + r] <= v) ++r;
                     sv = r;
+                    open = r > 4 && r < rmax;                      // all of r = 1..4 passed: keep going from r = 5
                 }
-                sc[t] = sv;
-                if (p.score) p.score[(f0 + c0 + k) * kPeakLags + (c - kMinLag)] = sv;
+                unsigned todo = simt::ballot32(open);
+                while (todo) {
+                    const int src = __builtin_ffs((int)todo) - 1;
+                    todo &= todo - 1;
+                    const int ck = simt::shfl32_i(k, src), cc = simt::shfl32_i(c, src), cm = simt::shfl32_i(rmax, src);
+                    const float cv = __int_as_float_compat(simt::shfl32_i(__float_as_int_compat(v), src));
+                    const float* crow = buf + ck * RL;
+                    int found = cm;
+                    for (int r0 = 5; r0 < cm; r0 += 32) {
+                        const int r = r0 + lane;
+                        const bool stop = r < cm && !(crow[cc - r] <= cv && crow[cc + r] <= cv);
+                        const unsigned m = simt::ballot32(stop);
+                        if (m) { found = r0 + __builtin_ffs((int)m) - 1; break; }
+                    }
+                    if (lane == src) sv = found;
+                }
+                if (live) {
+                    sc[t] = sv;
+                    if (p.score) p.score[(f0 + c0 + k) * kPeakLags + (c - kMinLag)] = sv;
+                }
             }
             simt::cta_sync();
             for (int k = warp; k < nrows; k += kTrackThreads / 32) {   // first argmax (pitch.py:169), one warp per row
