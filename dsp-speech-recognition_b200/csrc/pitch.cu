@@ -57,6 +57,10 @@ __global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const 
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
     int32_t* ds_idx = reinterpret_cast<int32_t*>(smem + kTabMod * 8);
+    {   // the grid is sized for the untrimmed batch: surplus CTAs leave before touching the tables
+        const int64_t tot = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
+        if (2 * (int64_t)blockIdx.x * kPitchWarps >= tot) return;
+    }
     for (int i = threadIdx.x; i < kTabMod; i += blockDim.x) tws[i] = p.tab[i];
     for (int i = threadIdx.x; i < p.ds_out; i += blockDim.x) ds_idx[i] = p.ds_idx[i];
     __syncthreads();
