@@ -728,3 +728,34 @@ def acr_gate_rows_f64(frames, rate):
     g = torch.empty(f.shape[0], dtype=torch.int32, device=dev)
     _check(L.dspfe_acr_gate_rows_f64(f.data_ptr(), f.shape[0], f.shape[1], int(rate), g.data_ptr(), _stream(torch, dev)))
     return g.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ ingest
+def wav_info(data):
+    """Header of one WAV file image (bytes): dict(rate, channels, bits, n_frames, data_offset).  Host only."""
+    L = lib()
+    L.dspfe_wav_info.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int32)] * 3 + [ctypes.POINTER(ctypes.c_int64)] * 2
+    buf = np.frombuffer(data, dtype=np.uint8)
+    r, c, b = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    n, o = ctypes.c_int64(), ctypes.c_int64()
+    _check(L.dspfe_wav_info(_np_ptr(buf), len(buf), ctypes.byref(r), ctypes.byref(c), ctypes.byref(b), ctypes.byref(n), ctypes.byref(o)))
+    return dict(rate=r.value, channels=c.value, bits=b.value, n_frames=n.value, data_offset=o.value)
+
+
+def ingest_wavs(paths):
+    """reader.py:67-85 for a list of files: (pcm int16 CUDA tensor [total], offsets int64 NumPy [n+1], rates int32 [n]).
+    Channel 0 of every 16-bit PCM WAV file, packed back to back on the current device."""
+    torch, dev = _cuda()
+    L = lib()
+    L.dspfe_ingest_wavs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p]
+    images = [np.fromfile(p, dtype=np.uint8) for p in paths]
+    n = len(images)
+    total = sum(wav_info(im)["n_frames"] for im in images)
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[im.ctypes.data for im in images])
+    sizes = np.array([len(im) for im in images], dtype=np.int64)
+    pcm = torch.empty(max(total, 1), dtype=torch.int16, device=dev)
+    off = np.zeros(n + 1, dtype=np.int64)
+    rates = np.zeros(max(n, 1), dtype=np.int32)
+    _check(L.dspfe_ingest_wavs(ptrs, _np_ptr(sizes), n, pcm.data_ptr(), pcm.numel(), _np_ptr(off), _np_ptr(rates), _stream(torch, dev)))
+    return pcm[:total], off, rates[:n]

@@ -283,6 +283,16 @@ int dspfe_acr_f64(const double* d_frame, int32_t len, int32_t n, double* d_out, 
 /* delta(feat, N) (base.py:70) on an arbitrary [n_frames, n_cols] float32 matrix */
 int dspfe_delta_f32(const float* d_in, int64_t n_frames, int32_t n_cols, int32_t N, float* d_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Ingest (reader.py:67-85: scipy.io.wavfile.read + sig[:,0]): 16-bit PCM RIFF/WAVE files, channel 0, into the packed
+ * ragged batch.  dspfe_wav_info parses one file image on the host.  dspfe_ingest_wavs takes the images of n files,
+ * writes h_offsets [n_files+1] (samples) and h_rates [n_files], streams the sample bytes through pinned staging buffers
+ * and de-interleaves channel 0 on the device into d_pcm (capacity in samples); returns when the batch is resident.
+ * ---------------------------------------------------------------------------------------------- */
+int dspfe_wav_info(const void* bytes, int64_t size, int32_t* rate, int32_t* channels, int32_t* bits, int64_t* n_frames, int64_t* data_offset);
+int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32_t n_files, int16_t* d_pcm, int64_t capacity,
+                      int64_t* h_offsets, int32_t* h_rates, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

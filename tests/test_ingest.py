@@ -1,0 +1,62 @@
+"""WAV ingest (reference reader.py:67-85): header parsing on the CPU, the device path on the GPU."""
+import io
+import os
+import struct
+
+import numpy as np
+import pytest
+from scipy.io import wavfile
+
+import dspfe
+
+
+def _wav_bytes(rate, data):
+    b = io.BytesIO()
+    wavfile.write(b, rate, data)
+    return b.getvalue()
+
+
+def test_wav_header_parser_against_scipy():
+    rng = np.random.default_rng(0)
+    for rate, ch, n in ((16000, 2, 1234), (44100, 1, 77), (48000, 2, 0), (8000, 6, 19)):
+        data = rng.integers(-32768, 32767, size=(n, ch) if ch > 1 else (n,), dtype=np.int16)
+        img = _wav_bytes(rate, data)
+        info = dspfe.wav_info(img)
+        assert (info["rate"], info["channels"], info["bits"], info["n_frames"]) == (rate, ch, 16, n)
+        got = np.frombuffer(img, dtype=np.int16, offset=info["data_offset"], count=n * ch)
+        np.testing.assert_array_equal(got, data.reshape(-1))
+    # an extra chunk before 'data' (LIST), odd-sized with its pad byte
+    data = rng.integers(-100, 100, size=(50, 2), dtype=np.int16)
+    img = _wav_bytes(16000, data)
+    extra = b"LIST" + struct.pack("<I", 5) + b"abcde" + bytes(1)
+    img2 = img[:36] + extra + img[36:]
+    img2 = img2[:4] + struct.pack("<I", len(img2) - 8) + img2[8:]
+    info = dspfe.wav_info(img2)
+    assert info["n_frames"] == 50 and info["data_offset"] == 44 + len(extra)
+    with pytest.raises(dspfe.DspfeError):
+        dspfe.wav_info(b"RIFFxxxxWAVEjunk")
+    with pytest.raises(dspfe.DspfeError) as e:
+        dspfe.wav_info(_wav_bytes(16000, rng.random(10).astype(np.float32)))
+    assert e.value.code == -2
+
+
+@pytest.mark.gpu
+def test_ingest_matches_reader_semantics(tmp_path):
+    rng = np.random.default_rng(1)
+    paths, want = [], []
+    for i, (rate, ch, n) in enumerate(((16000, 2, 20000), (16000, 1, 333), (44100, 2, 1), (16000, 2, 0), (48000, 3, 4097))):
+        data = rng.integers(-32768, 32767, size=(n, ch) if ch > 1 else (n,), dtype=np.int16)
+        p = os.path.join(tmp_path, f"p{i:03d}-{i:02d}-01.wav")
+        wavfile.write(p, rate, data)
+        paths.append(p)
+        r, sig = wavfile.read(p)                            # reader.py:76
+        want.append((r, sig[:, 0] if sig.ndim == 2 else sig))   # reader.py:80 (the reference indexes [:,0]; mono files are taken as they are)
+    pcm, off, rates = dspfe.ingest_wavs(paths)
+    pcm = pcm.cpu().numpy()
+    assert list(rates) == [w[0] for w in want]
+    for i, (_, sig) in enumerate(want):
+        np.testing.assert_array_equal(pcm[off[i]:off[i + 1]], sig)
+    # the packed batch feeds the kernels directly
+    import torch
+    lr = dspfe.EndpointPlan().detect(torch.from_numpy(pcm).cuda(), torch.from_numpy(off).cuda())
+    assert lr.shape == (5, 2)
