@@ -45,3 +45,22 @@ o1 = cep.detect(pcm, off_d, trim=lr, want_feat=True)
 timed("pitch_cepstrum + pitch_feature", lambda: cep.detect(pcm, off_d, trim=lr, want_feat=True, out=o1))
 o2 = acr.detect(pcm, off_d, trim=lr)
 timed("pitch_autocorrelation (trimmed, 300-sample frames)", lambda: acr.detect(pcm, off_d, trim=lr, out=o2))
+
+# ---- rows SURVEY section 8 marks "next": the trainer's batching epilogue (f-1), the gated endpoint rule (f-3), WAV ingest (f-4)
+feat, ffo = mf.mfcc_delta(pcm, off_d, trim=lr, out=out, frame_off=fo)
+inp = torch.empty((200, U, 39), dtype=torch.float32, device=dev)
+timed("cmvn_pad_batch (f-1: CMVN + pad to [200,U,39])", lambda: dspfe.cmvn_pad_batch(feat, ffo, out=inp))
+timed("robust_endpoint_detection (f-3: autocorrelation-gated rule)", lambda: ep.detect_robust(pcm, off_d))
+if "--ingest" in sys.argv:
+    import tempfile, time
+    from scipy.io import wavfile
+    d = tempfile.mkdtemp()
+    paths = []
+    rng = np.random.default_rng(0)
+    for i in range(256):
+        x = rng.integers(-3000, 3000, size=(int(lengths[i]), 2), dtype=np.int16)
+        paths.append(os.path.join(d, f"u{i}.wav")); wavfile.write(paths[-1], 16000, x)
+    dspfe.ingest_wavs(paths[:8])
+    t0 = time.perf_counter(); p2, o2_, _ = dspfe.ingest_wavs(paths); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(json.dumps({"path": "ingest_wavs (f-4: 256 stereo files from the page cache)", "ms": dt * 1e3,
+                      "audio_s_per_s": float(o2_[-1]) / 16000 / dt, "file_MB_per_s": sum(os.path.getsize(p) for p in paths) / 1e6 / dt}))
