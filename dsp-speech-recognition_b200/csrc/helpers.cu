@@ -70,6 +70,21 @@ __global__ void row_amp_kernel(const double* frames, int64_t nrows, int len, int
     out[r] = use_sq == 2 ? s : s / (double)len;
 }
 
+// get_amplitude with a window (endpoint.py:118-125): mean over n of np.convolve(|x| or x^2, w, 'same')[n] equals
+// (1/len) * sum_m v[m] * c[m], where c[m] is the sum of the window taps that the 'same' crop lets sample m meet
+__global__ void row_weighted_amp_kernel(const double* frames, int64_t nrows, int len, const double* c, int use_sq, double* out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    const double* x = frames + r * len;
+    double acc = 0.0;
+    for (int m = lane; m < len; m += 32) { const double v = use_sq ? x[m] * x[m] : fabs(x[m]); acc += v * c[m]; }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1)
+        acc += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(acc), k), __shfl_xor_sync(0xffffffffu, __double2loint(acc), k));
+    if (lane == 0) out[r] = acc / (double)len;
+}
+
 // get_zcr (endpoint.py:182-198)
 __global__ void row_zcr_kernel(const double* frames, int64_t nrows, int len, int64_t* out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,6 +201,32 @@ int dspfe_row_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len,
     cudaStream_t st = (cudaStream_t)stream;
     row_amp_kernel<<<grid_for(n_rows, 128), 128, 0, st>>>(d_frames, n_rows, len, use_sq, d_out);
     LAUNCH_CHECK("row_amp_kernel", st);
+    return DSPFE_OK;
+}
+
+int dspfe_row_windowed_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, const double* h_window, int32_t win_len,
+                                     int32_t use_sq, double* d_out, void* stream) {
+    if (n_rows < 0 || len < 1 || win_len < 1 || !h_window || (n_rows > 0 && (!d_frames || !d_out))) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    if (n_rows == 0) return DSPFE_OK;
+    // np.convolve(v, w, 'same') with len(v) = N, len(w) = M: out[n] = full[n + off], off = (min(N,M) - 1) / 2, full[k] = sum_m v[m] w[k-m]
+    const int N = len, M = win_len, off = ((N < M ? N : M) - 1) / 2;
+    std::vector<double> pre((size_t)M + 1, 0.0), c((size_t)N);
+    for (int k = 0; k < M; ++k) pre[k + 1] = pre[k] + h_window[k];
+    for (int m = 0; m < N; ++m) {           // taps j = n + off - m with n in [0, max(N,M)) cropped to N outputs... 'same' returns max(N,M) samples
+        const int L = N > M ? N : M;
+        int lo = off - m, hi = L - 1 + off - m;      // j range over n = 0..L-1
+        if (lo < 0) lo = 0;
+        if (hi > M - 1) hi = M - 1;
+        c[m] = hi >= lo ? pre[hi + 1] - pre[lo] : 0.0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_c = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_c, (size_t)N * sizeof(double), st));
+    CUDA_TRY(cudaMemcpyAsync(d_c, c.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
+    row_weighted_amp_kernel<<<grid_for(n_rows, 4), 128, 0, st>>>(d_frames, n_rows, len, d_c, use_sq, d_out);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_c, st);
+    if (e != cudaSuccess) return fail(DSPFE_ERR_CUDA, std::string("row_weighted_amp_kernel: ") + cudaGetErrorString(e));
     return DSPFE_OK;
 }
 

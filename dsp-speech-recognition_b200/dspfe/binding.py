@@ -343,6 +343,7 @@ def _bind_helpers(L):
     L.dspfe_preemphasis_f64.argtypes = [vp, i64, ctypes.c_double, vp, vp]
     L.dspfe_row_amplitude_f64.argtypes = [vp, i64, i32, i32, vp, vp]
     L.dspfe_row_zcr_f64.argtypes = [vp, i64, i32, vp, vp]
+    L.dspfe_row_windowed_amplitude_f64.argtypes = [vp, i64, i32, vp, i32, i32, vp, vp]
     L.dspfe_delta_f32.argtypes = [vp, i64, i32, i32, vp, vp]
     L.dspfe_cmvn_pad_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     L.dspfe_fir_window_f64.argtypes = [vp, i32, ctypes.c_double, ctypes.c_double, ctypes.c_double, i32, vp, vp]
@@ -437,6 +438,18 @@ def row_amplitude_f64(frames, use_sq=False):   # use_sq: False mean|x|, True mea
     f = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64)).to(dev)
     out = torch.empty(f.shape[0], dtype=torch.float64, device=dev)
     _check(L.dspfe_row_amplitude_f64(f.data_ptr(), f.shape[0], f.shape[1], (2 if use_sq == 2 else int(bool(use_sq))), out.data_ptr(), _stream(torch, dev)))
+    return out.cpu().numpy()
+
+
+def row_windowed_amplitude_f64(frames, window, use_sq=False):
+    """get_amplitude(frames, window=<taps>, use_sq) on the device (mean of the 'same' convolution per row)."""
+    torch, dev = _cuda()
+    L = lib(); _bind_helpers(L)
+    f = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64)).to(dev)
+    w = np.ascontiguousarray(window, dtype=np.float64)
+    out = torch.empty(f.shape[0], dtype=torch.float64, device=dev)
+    _check(L.dspfe_row_windowed_amplitude_f64(f.data_ptr(), f.shape[0], f.shape[1], _np_ptr(w), len(w), int(bool(use_sq)), out.data_ptr(),
+                                              _stream(torch, dev)))
     return out.cpu().numpy()
 
 

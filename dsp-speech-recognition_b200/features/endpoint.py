@@ -68,25 +68,30 @@ def robust_endpoint_detection(sig, rate):
 
 
 def get_noise(amp, sep_point):
-    """reference endpoint.py:94-107."""
-    if sep_point[0] == (0, len(amp)):
+    """reference endpoint.py:94-107: mean amplitude of the frames outside every detected (j, k) segment; 1e30 when the
+    rule fell back to the whole signal."""
+    amp = np.asarray(amp, dtype=np.float64)
+    n = len(amp)
+    if tuple(sep_point[0]) == (0, n):
         return 1e30
-    left, noise, l = 0, 0, 0
-    for item in sep_point:
-        noise += np.sum(amp[left:item[0]])
-        l += item[0] - left
-        left = item[1]
-    noise += np.sum(amp[left:])
-    l += len(amp) - left
-    return noise / l
+    # the reference walks the gaps between consecutive segments; accumulate them in the same order
+    total, count, start = 0, 0, 0
+    for j, k in sep_point:
+        total = total + np.sum(amp[start:j])
+        count += j - start
+        start = k
+    return (total + np.sum(amp[start:])) / (count + n - start)
 
 
 def get_amplitude(frames, window='square', use_sq=False):
-    """reference endpoint.py:109-126 on the device (dspfe_row_amplitude_f64).  Returns a list of np.float64."""
-    if not (isinstance(window, str) and window == 'square'):
-        raise NotImplementedError("only the default window='square' is built (SURVEY f-3)")
+    """reference endpoint.py:109-126 on the device: per frame the mean of |x| (or x^2), optionally convolved ('same')
+    with a Hamming window first.  Returns a list of np.float64."""
     frames = np.asarray(frames, dtype=np.float64)
-    return [np.float64(v) for v in dspfe.row_amplitude_f64(frames, use_sq)]
+    if isinstance(window, str) and window == 'square':
+        return [np.float64(v) for v in dspfe.row_amplitude_f64(frames, use_sq)]
+    if isinstance(window, str) and window == 'hamming':
+        return [np.float64(v) for v in dspfe.row_windowed_amplitude_f64(frames, np.hamming(frames.shape[-1]), use_sq)]
+    raise NotImplementedError("window must be 'square' or 'hamming'")
 
 
 def amplitude_feature(sig, rate, winlen, step):

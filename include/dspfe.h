@@ -267,6 +267,10 @@ int dspfe_preemphasis_f64(const double* d_x, int64_t n, double coeff, double* d_
 /* get_amplitude(frames, 'square', use_sq) (endpoint.py:109): per-row mean |x| (use_sq 0) or x^2 (1) in NumPy's summation
  * order; use_sq 2 = plain sum |x| per row (sub_endpoint_detect, pitch.py:65) */
 int dspfe_row_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, int32_t use_sq, double* d_out, void* stream);
+/* get_amplitude(frames, window=<taps>, use_sq) (endpoint.py:118-125): per-row mean of np.convolve(|x| or x^2, window, 'same');
+ * h_window is a host array of win_len taps (np.hamming(len) for window='hamming') */
+int dspfe_row_windowed_amplitude_f64(const double* d_frames, int64_t n_rows, int32_t len, const double* h_window, int32_t win_len,
+                                     int32_t use_sq, double* d_out, void* stream);
 /* get_zcr(frames) (endpoint.py:182) */
 int dspfe_row_zcr_f64(const double* d_frames, int64_t n_rows, int32_t len, int64_t* d_out, void* stream);
 /* Caller-side batching epilogue of the reference trainer (model.py:75-88, :35-50, :131-135) on K1's rows

@@ -385,17 +385,21 @@ def robust_endpoint_detection(sig, rate, cfg_frame=CFG_FRAME, cfg_step=CFG_STEP)
 
 
 def get_noise(amp, sep_point):
-    """endpoint.py:94-107."""
-    if sep_point[0] == (0, len(amp)):
+    """endpoint.py:94-107: mean amplitude outside the detected segments (1e30 for the whole-signal fallback)."""
+    n = len(amp)
+    if sep_point[0] == (0, n):
         return 1e30
-    left, noise, l = 0, 0, 0
-    for item in sep_point:
-        noise += np.sum(amp[left:item[0]])
-        l += item[0] - left
-        left = item[1]
-    noise += np.sum(amp[left:])
-    l += len(amp) - left
-    return noise / l
+    gaps = []                                   # (start, stop) of every stretch between / around the segments
+    cursor = 0
+    for seg_start, seg_stop in sep_point:
+        gaps.append((cursor, seg_start))
+        cursor = seg_stop
+    gaps.append((cursor, n))
+    acc, frames = 0, 0
+    for g0, g1 in gaps:                         # same accumulation order as the reference's running sum
+        acc += np.sum(amp[g0:g1])
+        frames += g1 - g0
+    return acc / frames
 
 
 def endpoint_max_pitch(l, rate, bias=20):

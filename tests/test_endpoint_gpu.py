@@ -129,3 +129,21 @@ def test_robust_endpoint_detection_vs_oracle():
     amp = O.get_amplitude(frames)
     assert features.amplitude_rule(amp, 0.5, frames=frames, use_acr=True, rate=16000) == \
         O.amplitude_rule(amp, 0.5, frames=frames, use_acr=True, rate=16000)
+
+
+def test_get_amplitude_variants_and_noise():
+    import features
+    from dspfe import synth
+    from oracle import ref_features as O
+    x = synth.synth_utterance(77, 9000)
+    frames = O.to_frames(x, 16000, 0.03, 0.01)
+    for window in ('square', 'hamming'):
+        for use_sq in (False, True):
+            got = features.get_amplitude(frames, window, use_sq)
+            want = O.get_amplitude(frames, window, use_sq)
+            assert isinstance(got, list)
+            np.testing.assert_allclose(got, want, rtol=1e-12)
+    amp = O.get_amplitude(frames)
+    sep = O.amplitude_rule(amp)
+    assert features.get_noise(amp, sep) == O.get_noise(amp, sep)
+    assert features.get_noise(amp, [(0, len(amp))]) == 1e30
