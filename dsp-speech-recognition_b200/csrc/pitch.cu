@@ -52,23 +52,33 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
     if (tid == kPitchPrepThreads - 1) p.frame_off[p.n_utt] = s_fr[tid];
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
+// K4a-1: gather + exact median + centre clip, a frame pair per warp
+__global__ void __launch_bounds__(32 * kPitchWarps, 4) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
-    int32_t* ds_idx = reinterpret_cast<int32_t*>(smem + kTabMod * 8);
-    {   // the grid is sized for the untrimmed batch: surplus CTAs leave before touching the tables
-        const int64_t tot = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
-        if (2 * (int64_t)blockIdx.x * kPitchWarps >= tot) return;
-    }
-    for (int i = threadIdx.x; i < kTabMod; i += blockDim.x) tws[i] = p.tab[i];
+    int32_t* ds_idx = reinterpret_cast<int32_t*>(smem);
+    const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
+    if (2 * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // the grid is sized for the untrimmed batch
     for (int i = threadIdx.x; i < p.ds_out; i += blockDim.x) ds_idx[i] = p.ds_idx[i];
     __syncthreads();
     const int w = threadIdx.x >> 5;
-    const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
     const int64_t g0 = 2 * ((int64_t)blockIdx.x * kPitchWarps + w);
     if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
-    pitch_frame_pair<MODE>(p, g0, total, smem + kTabMod * 8 + kMaxDsOut * 4 + w * kWarpSmemBytes, tws, tws + kTabW32, ds_idx);
+    pitch_clip_pair(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
+}
+
+// K4a-2 / K5a-2: the transforms, a frame pair per warp
+template <int MODE>
+__global__ void __launch_bounds__(32 * kPitchWarps, 4) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
+    const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
+    if (2 * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // surplus CTAs leave before touching the tables
+    for (int i = threadIdx.x; i < kTabMod; i += blockDim.x) tws[i] = p.tab[i];
+    __syncthreads();
+    const int w = threadIdx.x >> 5;
+    const int64_t g0 = 2 * ((int64_t)blockIdx.x * kPitchWarps + w);
+    if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
+    pitch_fft_pair<MODE>(p, g0, total, smem + kTabMod * 8 + w * kWarpSmemBytes, tws, tws + kTabW32);
 }
 
 __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid_constant__ PitchParams p) {
@@ -117,7 +127,7 @@ struct dspfe_pitch_plan {
     // workspaces
     int64_t cap_utt = 0, cap_frames = 0;
     int64_t* seg_start = nullptr; int32_t* seg_len = nullptr; int32_t* ds_len = nullptr; int64_t* frame_off = nullptr;
-    float* rows = nullptr; double* frame_amp = nullptr; double* pitch = nullptr; int32_t* lag = nullptr; double* scratch = nullptr;
+    float2* clip = nullptr; float* rows = nullptr; double* frame_amp = nullptr; double* pitch = nullptr; int32_t* lag = nullptr; double* scratch = nullptr;
     // host-path staging
     cudaStream_t stream = nullptr;
     void* d_pcm = nullptr; int64_t cap_bytes = 0;
@@ -137,8 +147,9 @@ int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
         pl->cap_utt = n_utt + 1;
     }
     if (frames > pl->cap_frames) {
-        cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
-        pl->rows = nullptr; pl->frame_amp = nullptr; pl->pitch = nullptr; pl->lag = nullptr; pl->scratch = nullptr; pl->cap_frames = 0;
+        cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch); cudaFree(pl->clip);
+        pl->clip = nullptr; pl->rows = nullptr; pl->frame_amp = nullptr; pl->pitch = nullptr; pl->lag = nullptr; pl->scratch = nullptr; pl->cap_frames = 0;
+        CUDA_TRY(cudaMalloc(&pl->clip, ((frames + 1) / 2) * 512 * sizeof(float2)));
         CUDA_TRY(cudaMalloc(&pl->rows, frames * pl->base.row_len * sizeof(float)));
         CUDA_TRY(cudaMalloc(&pl->frame_amp, frames * sizeof(double)));
         CUDA_TRY(cudaMalloc(&pl->pitch, frames * sizeof(double)));
@@ -177,6 +188,7 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
     if (trc) { delete pl; return fail(trc, err); }
     cudaError_t e = cudaMalloc(&pl->d_tab, kTabTotal * sizeof(float2));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_tab, tab.data(), kTabTotal * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, track_smem(kCepLen));
@@ -190,7 +202,7 @@ void dspfe_pitch_destroy(dspfe_pitch_plan* pl) {
     if (!pl) return;
     cudaFree(pl->d_tab);
     cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off);
-    cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
+    cudaFree(pl->clip); cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
     cudaFree(pl->d_pcm); cudaFree(pl->d_off); cudaFree(pl->d_trim); cudaFree(pl->d_feat);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     delete pl;
@@ -226,12 +238,14 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     PitchParams p = pl->base;
     p.pcm = d_pcm; p.in_f32 = sample_dtype; p.total_samples = total_samples; p.offsets = d_offsets; p.trim = d_trim; p.n_utt = n_utt;
     p.frame_off = d_frame_off ? d_frame_off : pl->frame_off; p.seg_start = pl->seg_start; p.seg_len = pl->seg_len; p.ds_len = pl->ds_len;
-    p.rows = d_rows ? d_rows : pl->rows; p.rows_out = nullptr; p.score = nullptr; p.frame_amp = pl->frame_amp;
+    p.clip = pl->clip; p.rows = d_rows ? d_rows : pl->rows; p.rows_out = nullptr; p.score = nullptr; p.frame_amp = pl->frame_amp;
     p.pitch = d_pitch ? d_pitch : pl->pitch; p.lag = d_lag ? d_lag : pl->lag; p.feat = d_feat; p.scratch = pl->scratch;
     p.max_frames = bound;
     pitch_prep_kernel<<<1, kPitchPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("pitch_prep_kernel", st);
     const unsigned fgrid = (unsigned)((bound + 2 * kPitchWarps - 1) / (2 * kPitchWarps));
+    pitch_clip_kernel<<<fgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
+    LAUNCH_CHECK("pitch_clip_kernel", st);
     if (p.mode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     else pitch_frame_kernel<1><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_frame_kernel", st);

@@ -44,11 +44,14 @@ constexpr int kPeakLags = 80;       // peak_score evaluates lags 20..99 (pitch.p
 constexpr int kMaxDsOut = 256;      // decimator pattern length limit
 constexpr int kPitchWarps = 4;      // warps per CTA in K4a/K5a, each carrying a pair of frames
 constexpr int kWarpScr = 2 * 16 * 17;   // two padded 16x16 transpose tiles (float2), one per half-warp
-constexpr int kWarpSmemBytes = kWarpScr * 8 + 512 * 8 + 512 * 16;   // transpose tile | clipped frame pair | parked spectrum
+constexpr int kWarpSmemBytes = kWarpScr * 8 + 512 * 16;              // transform kernel: transpose tile | parked spectrum
 // table blob offsets, in float2
 constexpr int kTabTw = 0, kTabW32 = kTabTw + 512, kTabMod = kTabW32 + 32, kTabHe = kTabMod + 512, kTabHo = kTabHe + 512,
               kTabTotal = kTabHo + 512;
-constexpr int kFrameCtaSmem = (kTabMod * 8) + kMaxDsOut * 4 + kPitchWarps * kWarpSmemBytes;   // shared tables | ds_idx | per-warp areas
+constexpr int kFrameCtaSmem = (kTabMod * 8) + kPitchWarps * kWarpSmemBytes;                      // shared tables | per-warp areas
+constexpr int kStageBytes = 2048;   // per frame; the span of a 512-sample frame at 16 kHz -> 10 kHz is 1.7 KB of int16
+constexpr int kClipWarpSmemBytes = 2 * kStageBytes + 512 * 8;       // clip kernel: two staged source spans | gathered frame pair
+constexpr int kClipCtaSmem = kMaxDsOut * 4 + kPitchWarps * kClipWarpSmemBytes;
 constexpr int kTrackThreads = 256;
 constexpr int kTrackMaxFrames = 1024;   // utterances up to this many frames keep their lag / Hz track in shared memory
 constexpr int kTrackChunk = 32;     // frames smoothed per pass of K4b/K5b (16 for rows wider than 256 columns)
@@ -73,6 +76,7 @@ struct PitchParams {
     int row_len;                         // columns per row: cepstrum 200 (fused) or 512 (tap); autocorrelation 180
     int64_t* frame_off;                  // [U+1] prefix sums of pitch frames
     int64_t* seg_start; int32_t* seg_len; int32_t* ds_len;   // per utterance: trimmed range and decimated length
+    float2* clip;                        // [ceil(F_total/2), 512] clipped frame pairs (K4a-1 -> K4a-2)
     float* rows;                         // [F_total, row_len] raw rows (K4a/K5a output)
     float* rows_out;                     // optional: smoothed rows (tap of smooth, pitch.py:157)
     int32_t* score;                      // optional [F_total, 80]: peak_score of every smoothed row (tap)
@@ -378,7 +382,6 @@ struct FrameCursor {
     int nvalid;   // the lane's samples t < nvalid lie inside both the frame and the decimated signal
     int a, b;     // k - 1 = a * ds_out + b for the lane's current decimated index k
 };
-constexpr int kStageBytes = 4096;   // per frame; the span of a 512-sample frame at 16 kHz -> 10 kHz is 1.7 KB of int16
 // Stages the source span of one frame in shared memory with 16-byte loads (one DRAM latency for the whole frame
 // instead of one per group of samples) and returns the cursor; spans that do not fit are read in place.
 DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane, bool valid, unsigned char* stage) {
@@ -451,59 +454,67 @@ DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, c
     }
 }
 
-// Two consecutive frames (g0, g0 + 1) per warp: gather + clip + FIR band-pass + (cepstrum | autocorrelation)
-// -> p.rows[g, :], p.frame_amp[g].  The causal complex FIR y = conv(x, h)[:512] (sigproc.py:22-46) is evaluated through
+// K4a-1: gather + median + centre clip of a frame pair -> p.clip[pair] (512 float2, frame A in .x, frame B in .y) and
+// p.frame_amp.  Its own kernel: it needs few registers and little shared memory, so three times as many warps as the
+// transform kernel can hide its load and bisection latencies.
+// wsm: per-warp shared memory = stage[2][kStageBytes] | xs[512] float2.
+DEVFN void pitch_clip_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const int32_t* ds_idx) {
+    const int lane = simt::tid() & 31;
+    unsigned char* stage = wsm;
+    float2* xs = reinterpret_cast<float2*>(wsm + 2 * kStageBytes);
+    const bool hasB = g0 + 1 < total;
+    const int L = p.frame_len;
+    // ---- gather both frames into xs from their staged source spans; sum |x| of the raw frames (sub_endpoint_detect,
+    // pitch.py:65) in float64 across the warp
+    const int ua = find_utt(p.frame_off, p.n_utt, g0, lane);
+    const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
+    FrameCursor ca = frame_cursor(p, g0, ua, lane, true, stage);
+    FrameCursor cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB, stage + kStageBytes);
+    float fa = 0.f, fb = 0.f;
+    if (p.in_f32) gather_pair<true>(p, ca, cb, ds_idx, xs, lane, fa, fb);
+    else gather_pair<false>(p, ca, cb, ds_idx, xs, lane, fa, fb);
+    float xa[16], xb[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { const float2 v = xs[32 * t + lane]; xa[t] = v.x; xb[t] = v.y; }
+    double sa = (double)fa, sb = (double)fb;
+    if (p.frame_amp) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
+        if (lane == 0) { p.frame_amp[g0] = sa; if (hasB) p.frame_amp[g0 + 1] = sb; }
+    }
+    // ---- centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
+    float2 med = make_float2(0.f, 0.f);
+    if (p.do_clip) med = warp_median_nonneg2(xa, xb, L, lane);
+    float2* dst = p.clip + (g0 >> 1) * 512;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const bool in = lane + 32 * t < L;
+        const float va = p.do_clip ? clip_value(xa[t], med.x) : xa[t];
+        const float vb = p.do_clip ? clip_value(xb[t], med.y) : xb[t];
+        dst[32 * t + lane] = make_float2(in ? va : 0.f, in ? vb : 0.f);
+    }
+}
+
+// K4a-2 / K5a-2: two consecutive frames (g0, g0 + 1) per warp: FIR band-pass + (cepstrum | autocorrelation) of the clipped
+// pair -> p.rows[g, :].  The causal complex FIR y = conv(x, h)[:512] (sigproc.py:22-46) is evaluated through
 // the even / odd bins of its 1024-point spectrum, which only takes 512-point transforms:
 //     Xe = FFT512(x), Xo = FFT512(x W1024^n);  y[n] = (IFFT512(Xe He)[n] + W1024^-n IFFT512(Xo Ho)[n]) / 2
 // and for the cepstrum (pitch.py:135-143) the first inverse transform folds away:
 //     FFT512(y) = (Xe He + FFT512(W1024^-n IFFT512(Xo Ho))) / 2.
-// The transforms run as a rolled loop over stages (one copy of each routine in the instruction stream: the fully
+// The transforms run as a rolled loop over stages (one copy of the routine in the instruction stream: the fully
 // inlined chain thrashed the instruction cache).  MODE 0 = cepstrum (5 transforms), 1 = autocorrelation (8).
-// wsm: per-warp shared memory = scr[kWarpScr] float2 | xs[512] float2 | park[512] float4.
+// wsm: per-warp shared memory = scr[kWarpScr] float2 | park[512] float4.
 template <int MODE>
-DEVFN void pitch_frame_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws,
-                            const float2* w32s, const int32_t* ds_idx) {
+DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
     const int lane = simt::tid() & 31;
     float2* scr = reinterpret_cast<float2*>(wsm);
-    float2* xs = scr + kWarpScr;
-    float4* park = reinterpret_cast<float4*>(xs + 512);
+    float4* park = reinterpret_cast<float4*>(scr + kWarpScr);
+    float2* xs = p.clip + (g0 >> 1) * 512;      // the clipped frame pair (global memory; the autocorrelation path reuses it for |y|)
     const float2* modA = p.tab + kTabMod;   // W1024^n, n = 32 t + lane
     const float2* HeB = p.tab + kTabHe;     // H1024[2k], k = 32 t + lane
     const float2* HoB = p.tab + kTabHo;     // H1024[2k+1]
     const bool hasB = g0 + 1 < total;
     const int L = p.frame_len;
-    {
-        // ---- gather both frames into xs from their staged source spans (a rolled loop: the fully unrolled form
-        // streamed 50 KB of straight-line code through the instruction cache per pair); sum |x| of the raw frames
-        // (sub_endpoint_detect, pitch.py:65) in float64 across the warp
-        const int ua = find_utt(p.frame_off, p.n_utt, g0, lane);
-        const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
-        unsigned char* stage = reinterpret_cast<unsigned char*>(park);     // park is free until the first transform is done
-        FrameCursor ca = frame_cursor(p, g0, ua, lane, true, stage);
-        FrameCursor cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB, stage + kStageBytes);
-        float fa = 0.f, fb = 0.f;
-        if (p.in_f32) gather_pair<true>(p, ca, cb, ds_idx, xs, lane, fa, fb);
-        else gather_pair<false>(p, ca, cb, ds_idx, xs, lane, fa, fb);
-        float xa[16], xb[16];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) { const float2 v = xs[32 * t + lane]; xa[t] = v.x; xb[t] = v.y; }
-        double sa = (double)fa, sb = (double)fb;
-        if (p.frame_amp) {
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
-            if (lane == 0) { p.frame_amp[g0] = sa; if (hasB) p.frame_amp[g0 + 1] = sb; }
-        }
-        // ---- centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
-        float2 med = make_float2(0.f, 0.f);
-        if (p.do_clip) med = warp_median_nonneg2(xa, xb, L, lane);
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const bool in = lane + 32 * t < L;
-            const float ca = p.do_clip ? clip_value(xa[t], med.x) : xa[t];
-            const float cb = p.do_clip ? clip_value(xb[t], med.y) : xb[t];
-            xs[32 * t + lane] = make_float2(in ? ca : 0.f, in ? cb : 0.f);
-        }
-    }
     // (every lane only ever touches its own xs / park entries: no barrier needed around them)
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);

@@ -21,8 +21,15 @@ void frame_body(void* a) {
     if (g0 >= A->total_frames) return;
     // the device kernel stages the twiddles and the decimator pattern in shared memory; the emulator reads them in place
     unsigned char* wsm = A->smem->data() + w * kWarpSmemBytes;
-    if (A->p.mode == 0) pitch_frame_pair<0>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32, A->p.ds_idx);
-    else pitch_frame_pair<1>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32, A->p.ds_idx);
+    if (A->p.mode == 0) pitch_fft_pair<0>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
+    else pitch_fft_pair<1>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
+}
+void clip_body(void* a) {
+    Args* A = (Args*)a;
+    const int w = simt::tid() >> 5;
+    const int64_t g0 = 2 * ((int64_t)simt::bid() * kPitchWarps + w);
+    if (g0 >= A->total_frames) return;
+    pitch_clip_pair(A->p, g0, A->total_frames, A->smem->data() + w * kClipWarpSmemBytes, A->p.ds_idx);
 }
 void track_body(void* a) {
     Args* A = (Args*)a;
@@ -70,6 +77,14 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
     p.ds_len = ds_len.data(); p.rows = rows; p.rows_out = rows_smoothed; p.score = score; p.frame_amp = amp.data();
     p.pitch = pitch ? pitch : pitch_own.data(); p.lag = lag ? lag : lag_own.data(); p.feat = feat; p.scratch = scratch.data();
     p.max_frames = fo;
+    std::vector<float2> clip((size_t)((fo + 1) / 2) * 512);
+    p.clip = clip.data();
+    std::vector<unsigned char> smem0(kPitchWarps * kClipWarpSmemBytes + 64);
+    Args A0{p, &smem0, fo};
+    for (int64_t b = 0; b * 2 * kPitchWarps < fo + 2 * kPitchWarps; ++b) {
+        std::memset(smem0.data(), 0xCD, smem0.size());
+        if (!emu::run_cta((int)b, 32 * kPitchWarps, clip_body, &A0)) { std::snprintf(errbuf, errcap, "deadlock in clip CTA %lld", (long long)b); return -3; }
+    }
     std::vector<unsigned char> smem(kPitchWarps * kWarpSmemBytes + 64);
     Args A{p, &smem, fo};
     for (int64_t b = 0; b * 2 * kPitchWarps < fo + 2 * kPitchWarps; ++b) {
