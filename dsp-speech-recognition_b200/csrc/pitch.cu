@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
 }
 
 // K4a-1: gather + exact median + centre clip, a frame pair per warp
-__global__ void __launch_bounds__(32 * kPitchWarps, 4) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
+__global__ void __launch_bounds__(32 * kPitchWarps, 6) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t* ds_idx = reinterpret_cast<int32_t*>(smem);
     const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
