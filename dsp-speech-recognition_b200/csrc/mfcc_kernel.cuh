@@ -344,7 +344,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                     if (vA <= v_hi) p.out[(row0 + vA) * (p.nfilt + 1) + j] = f.x;
                     if (vA + 2 <= v_hi) p.out[(row0 + vA + 2) * (p.nfilt + 1) + j] = f.y;
                 } else {
-                    lmel[j] = make_float2(dsp_logf(f.x), dsp_logf(f.y));
+                    lmel[j] = make_float2(dsp_fast_logf(f.x), dsp_fast_logf(f.y));
                 }
             }
             simt::group_sync();
