@@ -145,9 +145,14 @@ DSP_HD void zcr_rule(Zcr zcr, int F, const EpRule& r, double l_sil, int left, in
 }
 
 // basic_endpoint_detection (endpoint.py:34-66): frame-level decision + conversion to sample indices.
+template <class Amp>
+DSP_HD void endpoint_decide_amp(Amp amp, const int32_t* zcr, int F, const EpRule& r, int32_t* out_lr);
 DSP_HD void endpoint_decide(const int32_t* asum, const int32_t* zcr, int F, int frame_len, const EpRule& r, int32_t* out_lr) {
+    endpoint_decide_amp(AmpFromSum{asum, (double)frame_len}, zcr, F, r, out_lr);
+}
+template <class Amp>
+DSP_HD void endpoint_decide_amp(Amp amp, const int32_t* zcr, int F, const EpRule& r, int32_t* out_lr) {
     int left, right;
-    const AmpFromSum amp{asum, (double)frame_len};
     amplitude_rule(amp, F, r, r.mh1, &left, &right);
     if (right - left < r.min_span) amplitude_rule(amp, F, r, r.mh2, &left, &right);
     int l2, r2;
@@ -181,10 +186,10 @@ DSP_HD bool acr_gate_frame(const int16_t* x, long long avail, int len, int n0, i
 }
 
 // robust_endpoint_detection (endpoint.py:68-92): amplitude_rule(mh = 0.5) with the gate, zcr_rule, whole-signal fallback
-template <class Gate>
-DSP_HD void endpoint_decide_robust(const int32_t* asum, const int32_t* zcr, int F, int frame_len, const EpRule& r, Gate gate, int32_t* out_lr) {
+template <class Amp, class Gate>
+DSP_HD void endpoint_decide_robust(Amp amp, const int32_t* zcr, int F, const EpRule& r, Gate gate, int32_t* out_lr) {
     int left, right;
-    amplitude_rule(AmpFromSum{asum, (double)frame_len}, F, r, 0.5, &left, &right, nullptr, 0, gate);
+    amplitude_rule(amp, F, r, 0.5, &left, &right, nullptr, 0, gate);
     int l2, r2;
     zcr_rule(ZcrFromI32{zcr}, F, r, 0.0, left, right, &l2, &r2);
     if (r2 - l2 < r.min_span) { l2 = 0; r2 = F; }
@@ -332,23 +337,30 @@ __global__ void __launch_bounds__(256) ep_frame_kernel(EpParams p) {
 // warp first stages them in shared memory with coalesced loads (a thread walking global memory on its own pays a full
 // DRAM latency per frame), then lane 0 replays the rule.  Utterances longer than kEpStageFrames run from global memory.
 constexpr int kEpStageFrames = 1024;
-constexpr int kEpDecideWarps = 4;
+constexpr int kEpDecideWarps = 2;
+// amp[i] = sum|x| / frame_len as the reference's float64 mean, computed once per frame by the whole warp: the rule
+// compares every frame against its thresholds several times and a float64 division per comparison on one lane was the
+// kernel's critical path
+__device__ __forceinline__ void ep_stage(const int32_t* asum, const int32_t* zcr, int F, double len, double* s_amp, int32_t* s_zcr, int lane) {
+    for (int i = lane; i < F; i += 32) { s_amp[i] = (double)asum[i] / len; s_zcr[i] = zcr[i]; }
+    __syncwarp();
+}
 __global__ void __launch_bounds__(32 * kEpDecideWarps) ep_decide_kernel(EpParams p) {
-    __shared__ int32_t s_stat[kEpDecideWarps][2][kEpStageFrames];
+    __shared__ double s_amp[kEpDecideWarps][kEpStageFrames];
+    __shared__ int32_t s_zcr[kEpDecideWarps][kEpStageFrames];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * kEpDecideWarps + w;
     if (u >= p.n_utt) return;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
-    const int32_t* asum = p.asum + f0;
-    const int32_t* zcr = p.zcr + f0;
     if (F <= kEpStageFrames) {
-        for (int i = lane; i < F; i += 32) { s_stat[w][0][i] = asum[i]; s_stat[w][1][i] = zcr[i]; }
-        __syncwarp();
-        asum = s_stat[w][0]; zcr = s_stat[w][1];
+        ep_stage(p.asum + f0, p.zcr + f0, F, (double)p.frame_len, s_amp[w], s_zcr[w], lane);
+        if (lane == 0) endpoint_decide_amp(AmpFromF64{s_amp[w]}, s_zcr[w], F, p.rule, p.lr + 2 * u);
+    } else if (lane == 0) {
+        endpoint_decide(p.asum + f0, p.zcr + f0, F, p.frame_len, p.rule, p.lr + 2 * u);
     }
-    if (lane == 0) endpoint_decide(asum, zcr, F, p.frame_len, p.rule, p.lr + 2 * u);
 }
+
 // Warp-cooperative gate: the frame is staged as int32 in shared memory, every lane takes the lags n0 + lane + 32 m.
 // All lanes of the warp execute the rule in lock step on identical data, so the gate is called convergently.
 constexpr int kEpGateMaxLen = 1536;
@@ -382,24 +394,24 @@ struct GateWarp {
 
 constexpr int kEpRobustWarps = 2;
 __global__ void __launch_bounds__(32 * kEpRobustWarps) ep_decide_robust_kernel(EpParams p) {
-    __shared__ int32_t s_stat[kEpRobustWarps][2][kEpStageFrames];
+    __shared__ double s_amp[kEpRobustWarps][kEpStageFrames];
+    __shared__ int32_t s_zcr[kEpRobustWarps][kEpStageFrames];
     __shared__ int s_x[kEpRobustWarps][kEpGateMaxLen];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * kEpRobustWarps + w;
     if (u >= p.n_utt) return;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
-    const int32_t* asum = p.asum + f0;
-    const int32_t* zcr = p.zcr + f0;
-    if (F <= kEpStageFrames) {
-        for (int i = lane; i < F; i += 32) { s_stat[w][0][i] = asum[i]; s_stat[w][1][i] = zcr[i]; }
-        __syncwarp();
-        asum = s_stat[w][0]; zcr = s_stat[w][1];
-    }
     const GateWarp gate{p.pcm + p.offsets[u], (long long)(p.offsets[u + 1] - p.offsets[u]), p.frame_step, p.frame_len,
                         p.rule.rate / 500, p.rule.rate / 50, s_x[w]};
     int32_t lr[2];
-    endpoint_decide_robust(asum, zcr, F, p.frame_len, p.rule, gate, lr);   // every lane, identical data
+    // every lane replays the rule on identical data (the gate is warp-cooperative)
+    if (F <= kEpStageFrames) {
+        ep_stage(p.asum + f0, p.zcr + f0, F, (double)p.frame_len, s_amp[w], s_zcr[w], lane);
+        endpoint_decide_robust(AmpFromF64{s_amp[w]}, s_zcr[w], F, p.rule, gate, lr);
+    } else {
+        endpoint_decide_robust(AmpFromSum{p.asum + f0, (double)p.frame_len}, p.zcr + f0, F, p.rule, gate, lr);
+    }
     if (lane == 0) { p.lr[2 * u] = lr[0]; p.lr[2 * u + 1] = lr[1]; }
 }
 
