@@ -47,10 +47,13 @@ int parse_wav(const unsigned char* b, int64_t size, WavInfo& w, std::string& err
     return DSPFE_ERR_INVALID_ARG;
 }
 
-// channel 0 of interleaved int16 frames -> packed destination
-__global__ void channel0_kernel(const int16_t* src, int64_t n_frames, int channels, int16_t* dst) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_frames) dst[i] = src[i * channels];
+// channel 0 of interleaved int16 frames -> packed destination, a whole slab of files per launch
+struct FileDesc { int64_t src_off; int64_t dst_off; int64_t n_frames; int32_t channels; int32_t pad; };   // offsets in samples
+__global__ void channel0_kernel(const int16_t* slab, const FileDesc* desc, int16_t* dst) {
+    const FileDesc d = desc[blockIdx.y];
+    const int16_t* src = slab + d.src_off;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n_frames; i += (int64_t)gridDim.x * blockDim.x)
+        dst[d.dst_off + i] = src[i * d.channels];
 }
 
 }  // namespace
@@ -86,29 +89,55 @@ int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32
     if (total > capacity) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm capacity is below the total sample count");
     if (n_files == 0 || total == 0) return DSPFE_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    // two pinned staging buffers + two device buffers, ping-ponged: file f+1 is copied while file f's H2D is in flight
+    // Files are packed into slabs of up to kSlabBytes of raw sample bytes; two pinned staging buffers and two device
+    // buffers are ping-ponged, so the host fills slab s+1 while slab s crosses PCIe; one kernel launch per slab.
+    const int64_t kSlabBytes = 32ll << 20;
+    const int64_t slab_cap = max_bytes > kSlabBytes ? max_bytes : kSlabBytes;
+    const int kMaxFilesPerSlab = 4096;
     void* h_stage[2] = {nullptr, nullptr}; int16_t* d_stage[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
-    auto cleanup = [&]() { for (int i = 0; i < 2; ++i) { if (h_stage[i]) cudaFreeHost(h_stage[i]); if (d_stage[i]) cudaFree(d_stage[i]); if (ev[i]) cudaEventDestroy(ev[i]); } };
+    FileDesc* h_desc[2] = {nullptr, nullptr}; FileDesc* d_desc[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) {
+            if (h_stage[i]) cudaFreeHost(h_stage[i]); if (d_stage[i]) cudaFree(d_stage[i]); if (ev[i]) cudaEventDestroy(ev[i]);
+            if (h_desc[i]) cudaFreeHost(h_desc[i]); if (d_desc[i]) cudaFree(d_desc[i]);
+        }
+    };
     for (int i = 0; i < 2; ++i) {
-        if (cudaHostAlloc(&h_stage[i], (size_t)max_bytes + 16, cudaHostAllocDefault) != cudaSuccess ||
-            cudaMalloc(&d_stage[i], (size_t)max_bytes + 16) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        if (cudaHostAlloc(&h_stage[i], (size_t)slab_cap + 16, cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc(&d_stage[i], (size_t)slab_cap + 16) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaHostAlloc((void**)&h_desc[i], kMaxFilesPerSlab * sizeof(FileDesc), cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc(&d_desc[i], kMaxFilesPerSlab * sizeof(FileDesc)) != cudaSuccess) {
             cleanup(); return fail(DSPFE_ERR_NOMEM, "staging allocation failed");
         }
     }
-    for (int f = 0; f < n_files; ++f) {
-        const int s = f & 1;
-        const WavInfo& w = info[f];
-        if (w.n_frames == 0) continue;
-        const int64_t nb = w.n_frames * 2 * w.channels;
-        if (f >= 2) cudaEventSynchronize(ev[s]);                         // the slot's previous file has left the pinned buffer
-        std::memcpy(h_stage[s], (const unsigned char*)file_bytes[f] + w.data_offset, (size_t)nb);
-        cudaError_t e = cudaMemcpyAsync(d_stage[s], h_stage[s], (size_t)nb, cudaMemcpyHostToDevice, st);
+    int f = 0, slab = 0;
+    while (f < n_files) {
+        const int s = slab & 1;
+        if (slab >= 2) cudaEventSynchronize(ev[s]);                      // the slot's previous slab has left the pinned buffers
+        int64_t used = 0, longest = 0; int nd = 0;
+        while (f < n_files && nd < kMaxFilesPerSlab) {
+            const WavInfo& w = info[f];
+            const int64_t nb = w.n_frames * 2 * w.channels;
+            if (nd > 0 && used + nb > slab_cap) break;
+            if (nb > 0) {
+                std::memcpy((unsigned char*)h_stage[s] + used, (const unsigned char*)file_bytes[f] + w.data_offset, (size_t)nb);
+                h_desc[s][nd++] = FileDesc{used / 2, h_offsets[f], w.n_frames, w.channels, 0};
+                longest = w.n_frames > longest ? w.n_frames : longest;
+                used += nb;
+            }
+            ++f;
+        }
+        if (nd == 0) { ++slab; continue; }
+        cudaError_t e = cudaMemcpyAsync(d_stage[s], h_stage[s], (size_t)used, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc[s], h_desc[s], nd * sizeof(FileDesc), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) {
-            channel0_kernel<<<(unsigned)((w.n_frames + 255) / 256), 256, 0, st>>>(d_stage[s], w.n_frames, w.channels, d_pcm + h_offsets[f]);
+            unsigned gx = (unsigned)((longest + 255) / 256); if (gx > 1024) gx = 1024; if (gx < 1) gx = 1;
+            channel0_kernel<<<dim3(gx, (unsigned)nd), 256, 0, st>>>(d_stage[s], d_desc[s], d_pcm);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaEventRecord(ev[s], st);
         if (e != cudaSuccess) { cudaStreamSynchronize(st); cleanup(); return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
+        ++slab;
     }
     cudaStreamSynchronize(st);     // the staging buffers are released here; ingest is not on the kernels' hot path
     cleanup();

@@ -772,3 +772,18 @@ def ingest_wavs(paths):
     rates = np.zeros(max(n, 1), dtype=np.int32)
     _check(L.dspfe_ingest_wavs(ptrs, _np_ptr(sizes), n, pcm.data_ptr(), pcm.numel(), _np_ptr(off), _np_ptr(rates), _stream(torch, dev)))
     return pcm[:total], off, rates[:n]
+
+
+def pitch_num_frames_host(n_samples, samplerate=16000, dst_rate=10000, frame_len=512, frame_step=100, method=0):
+    """(pitch frames, decimated length) of an n_samples utterance; host only, no device needed."""
+    L = lib(); _bind_pitch(L)
+    L.dspfe_pitch_num_frames_host.argtypes = [ctypes.POINTER(_PitchParams), ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    L.dspfe_pitch_num_frames_host.restype = ctypes.c_int64
+    p = _PitchParams()
+    L.dspfe_pitch_params_default(ctypes.byref(p), int(method))
+    p.samplerate, p.dst_rate, p.frame_len, p.frame_step = int(samplerate), int(dst_rate), int(frame_len), int(frame_step)
+    ld = ctypes.c_int64(0)
+    nf = L.dspfe_pitch_num_frames_host(ctypes.byref(p), int(n_samples), ctypes.byref(ld))
+    if nf < 0:
+        raise DspfeError(-1, L.dspfe_last_error().decode())
+    return int(nf), int(ld.value)

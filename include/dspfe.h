@@ -218,6 +218,8 @@ int32_t dspfe_pitch_row_len(const dspfe_pitch_plan* plan);
 /* pitch frames of one utterance of n_samples (after decimation and framing) / upper bound for a whole batch */
 int64_t dspfe_pitch_num_frames(const dspfe_pitch_plan* plan, int64_t n_samples);
 int64_t dspfe_pitch_frames_bound(const dspfe_pitch_plan* plan, int64_t total_samples, int64_t n_utt);
+/* the same count without a plan or a device (host only); *n_decimated (optional) = len(downsampling(sig, samplerate, dst_rate)) */
+int64_t dspfe_pitch_num_frames_host(const dspfe_pitch_params* p, int64_t n_samples, int64_t* n_decimated);
 
 /* Device path, asynchronous on `stream`.  sample_dtype: 0 = int16, 1 = float32 samples.  d_trim as for
  * dspfe_mfcc_delta (pitch runs on sig[left:right], pitch_model.py:41).  Outputs (each may be NULL):
