@@ -219,7 +219,8 @@ int64_t dspfe_pitch_frames_bound(const dspfe_pitch_plan* pl, int64_t total_sampl
 int64_t dspfe_pitch_num_frames_host(const dspfe_pitch_params* q, int64_t n_samples, int64_t* n_decimated) {
     if (!q) return -1;
     PitchParams b; std::vector<float2> tab; std::string err;
-    if (build_pitch_tables(*q, b, tab, err)) { fail(DSPFE_ERR_INVALID_ARG, err); return -1; }
+    const int trc = build_pitch_tables(*q, b, tab, err);
+    if (trc) { fail(trc, err); return trc; }
     const int64_t ld = ds_length(n_samples, b.ds_idx, b.ds_in, b.ds_out);
     if (n_decimated) *n_decimated = ld;
     return num_frames(ld, b.frame_len, b.frame_step);

@@ -785,5 +785,5 @@ def pitch_num_frames_host(n_samples, samplerate=16000, dst_rate=10000, frame_len
     ld = ctypes.c_int64(0)
     nf = L.dspfe_pitch_num_frames_host(ctypes.byref(p), int(n_samples), ctypes.byref(ld))
     if nf < 0:
-        raise DspfeError(-1, L.dspfe_last_error().decode())
+        raise DspfeError(int(nf), L.dspfe_last_error().decode())
     return int(nf), int(ld.value)
