@@ -9,7 +9,10 @@
 
 #include "abi_common.h"
 #include "mfcc_kernel.cuh"
+#include "mfcc_long_kernel.cuh"
+#include "mfcc_long_tables.h"
 #include "mfcc_tables.h"
+#include "pitch_tables.h"
 #include "prep_kernel.cuh"
 
 using namespace dspfe;
@@ -20,6 +23,25 @@ template <bool HAS_WIN, int NFULL, bool F32IN, int MODE = 0>
 __global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __grid_constant__ MfccParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     mfcc_cta<HAS_WIN, NFULL, F32IN, MODE>(p, smem);
+}
+
+// K1L: long frames under nfft = 1536, a frame pair per warp; then delta / delta-delta over the cepstra
+__global__ void __launch_bounds__(32 * kLongWarps, 3) mfcc_long_kernel(const __grid_constant__ MfccLongParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* tws = reinterpret_cast<float2*>(smem);
+    const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
+    if (2 * (int64_t)blockIdx.x * kLongWarps >= total) return;
+    for (int i = threadIdx.x; i < kLtW1536 / 2; i += blockDim.x) tws[i] = reinterpret_cast<const float2*>(p.tab)[i];
+    __syncthreads();
+    const int w = threadIdx.x >> 5;
+    const int64_t g0 = 2 * ((int64_t)blockIdx.x * kLongWarps + w);
+    if (g0 >= total) return;
+    mfcc_long_pair(p, g0, total, smem + kLtW1536 * 4 + w * kLongWarpSmem, tws, tws + kLtW32 / 2);
+}
+__global__ void delta_batch_kernel(const float* mf, const int64_t* frame_off, int n_utt, int C, int N, float scale, int64_t max_frames, float* out) {
+    const int64_t total = frame_off[n_utt] < max_frames ? frame_off[n_utt] : max_frames;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total * C) delta_batch_thread(mf, frame_off, n_utt, C, N, scale, i, out);
 }
 
 typedef void (*mfcc_kernel_t)(const MfccParams);
@@ -51,7 +73,12 @@ MfccConfig to_config(const dspfe_mfcc_params& q) {
 
 // Per-stream scratch for one in-flight batch.
 struct Workspace {
-    int64_t cap_utt = 0, cap_tiles = 0;
+    int64_t cap_utt = 0, cap_tiles = 0, cap_cep = 0;
+    float* cep = nullptr;       // K1L: static cepstra [rows, numcep] between the two kernels
+    int ensure_cep(int64_t floats) {
+        if (floats > cap_cep) { cudaFree(cep); cep = nullptr; cap_cep = 0; CUDA_TRY(cudaMalloc(&cep, floats * sizeof(float))); cap_cep = floats; }
+        return DSPFE_OK;
+    }
     int64_t* seg_start = nullptr; int32_t* seg_len = nullptr; int64_t* frame_off = nullptr;
     int32_t* tile_off = nullptr; Tile* tiles = nullptr; int32_t* ntiles = nullptr;
     int ensure(int64_t n_utt, int64_t n_tiles) {
@@ -73,7 +100,7 @@ struct Workspace {
         return DSPFE_OK;
     }
     void release() {
-        cudaFree(seg_start); cudaFree(seg_len); cudaFree(frame_off); cudaFree(tile_off); cudaFree(tiles); cudaFree(ntiles);
+        cudaFree(seg_start); cudaFree(seg_len); cudaFree(frame_off); cudaFree(tile_off); cudaFree(tiles); cudaFree(ntiles); cudaFree(cep);
         *this = Workspace();
     }
 };
@@ -100,6 +127,8 @@ struct dspfe_plan {
     Workspace ws;
     HostSlot slots[kSlots];
     int width = 0;              // 3 * numcep
+    bool is_long = false;       // nfft = 1536: K1L
+    float* d_long_tab = nullptr;
 };
 
 namespace {
@@ -118,6 +147,23 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
     prep_kernel<<<1, kPrepThreads, 0, st>>>(pp);
     LAUNCH_CHECK("prep_kernel", st);
 
+    if (pl->is_long) {
+        if (mode != 0) return fail(DSPFE_ERR_UNSUPPORTED, "the filterbank / spectrum taps are built for nfft = 512");
+        const int64_t rows = total_samples / pl->cfg.frame_step + n_utt;
+        rc = ws.ensure_cep(rows * pl->cfg.numcep);
+        if (rc) return rc;
+        MfccLongParams lp;
+        lp.pcm = d_pcm; lp.in_f32 = f32 ? 1 : 0; lp.seg_start = ws.seg_start; lp.seg_len = ws.seg_len; lp.frame_off = pp.frame_off; lp.n_utt = n_utt;
+        lp.frame_len = pl->cfg.frame_len; lp.frame_step = pl->cfg.frame_step; lp.nfilt = pl->cfg.nfilt; lp.numcep = pl->cfg.numcep;
+        lp.append_energy = pl->cfg.append_energy; lp.preemph = (float)pl->cfg.preemph; lp.tab = pl->d_long_tab; lp.mfcc = ws.cep; lp.max_frames = rows;
+        mfcc_long_kernel<<<(unsigned)((rows + 2 * kLongWarps - 1) / (2 * kLongWarps)), 32 * kLongWarps, kLongCtaSmem, st>>>(lp);
+        LAUNCH_CHECK("mfcc_long_kernel", st);
+        int den = 0; for (int i = 1; i <= pl->cfg.delta_n; ++i) den += i * i;
+        delta_batch_kernel<<<(unsigned)((rows * pl->cfg.numcep + 255) / 256), 256, 0, st>>>(ws.cep, pp.frame_off, n_utt, pl->cfg.numcep, pl->cfg.delta_n,
+                                                                                          (float)(1.0 / (2.0 * den)), rows, d_out);
+        LAUNCH_CHECK("delta_batch_kernel", st);
+        return DSPFE_OK;
+    }
     MfccParams mp = f32 ? pl->layout_f32 : pl->layout;
     mp.pcm = d_pcm; mp.total_samples = total_samples; mp.seg_start = ws.seg_start; mp.seg_len = ws.seg_len;
     mp.frame_off = pp.frame_off; mp.tiles = ws.tiles; mp.ntiles = ws.ntiles; mp.tables = pl->d_tables; mp.out = d_out;
@@ -178,6 +224,18 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     pl->cfg = to_config(*p);
     std::memset(&pl->layout, 0, sizeof(pl->layout));
     std::string err;
+    if (pl->cfg.nfft == kLongNfft) {
+        err = mfcc_long_config_check(pl->cfg);
+        if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
+        pl->is_long = true; pl->has_win = !pl->cfg.window.empty(); pl->width = 3 * pl->cfg.numcep;
+        const std::vector<float> t = build_long_tables(pl->cfg);
+        cudaError_t e = cudaMalloc(&pl->d_long_tab, t.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_long_tab, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongCtaSmem);
+        if (e != cudaSuccess) { cudaFree(pl->d_long_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
+        *plan = pl;
+        return DSPFE_OK;
+    }
     std::vector<float> blob = build_mfcc_tables(pl->cfg, pl->layout, err);
     if (err.empty()) { std::memset(&pl->layout_f32, 0, sizeof(pl->layout_f32)); build_mfcc_tables(pl->cfg, pl->layout_f32, err, true); }
     if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
@@ -212,7 +270,7 @@ void dspfe_plan_destroy(dspfe_plan* pl) {
         if (s.h_off) cudaFreeHost(s.h_off);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    cudaFree(pl->d_tables);
+    cudaFree(pl->d_tables); cudaFree(pl->d_long_tab);
     delete pl;
 }
 
@@ -220,6 +278,14 @@ int dspfe_plan_info(const dspfe_plan* pl, int32_t* smem_bytes, int32_t* ctas_per
     if (!pl) return fail(DSPFE_ERR_INVALID_ARG, "null plan");
     cudaFuncAttributes fa;
     int nb = 0;
+    if (pl->is_long) {
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_long_kernel));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_long_kernel, 32 * kLongWarps, kLongCtaSmem));
+        if (smem_bytes) *smem_bytes = kLongCtaSmem;
+        if (ctas_per_sm) *ctas_per_sm = nb;
+        if (regs_per_thread) *regs_per_thread = fa.numRegs;
+        return DSPFE_OK;
+    }
     CUDA_TRY(cudaFuncGetAttributes(&fa, pl->kernel));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pl->kernel, kMfccThreads, pl->layout.sm_total));
     if (smem_bytes) *smem_bytes = pl->layout.sm_total;

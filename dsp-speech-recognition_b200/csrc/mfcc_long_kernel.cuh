@@ -1,0 +1,177 @@
+// K1L: MFCC for long frames under nfft = 1536 (sm_100a) -- the configuration the reference trainer really uses:
+// mfcc(sound.reshape(1,-1), rate, winlen=cfg.frame, winstep=cfg.step, nfft=1536, winfunc=np.hamming) (model.py:74), i.e.
+// 30 ms Hamming frames of 480 (16 kHz), 1323 (44.1 kHz) or 1440 (48 kHz) samples with hops of 160 / 441 / 480 (the odd hop
+// rules out K1's even/odd sample planes), zero padded to 1536 points.  Same arithmetic chain as K1 (sigproc.py:178-185
+// pre-emphasis, :66-98 framing, :151-158 power spectrum, base.py:18-32 filterbank, :8-16 log / DCT / lifter / energy).
+//
+// One warp per pair of consecutive frames (packed FP32: frame A in the .x halves, B in .y).  The 1536-point transform
+// of the real frame is a radix-3 decimation in time around the 512-point routine of fft_regs.h:
+//     X[k] = sum_{r<3} W1536^{rk} Z_r[k mod 512],   Z_r = FFT512(x[3m + r]),   k = 0..768,
+// accumulated per bin in shared memory (a lane only ever touches bins congruent to its lane index, so no barrier is
+// needed), then |X|^2 / 1536, triangular mel sums (one filter at a time across the lanes), log, DCT * lifter.
+// Delta and delta-delta run in a second kernel over the cepstra (delta_batch_kernel).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "fft_regs.h"
+#include "simt.h"
+
+namespace dspfe {
+
+constexpr int kLongNfft = 1536;
+constexpr int kLongBins = kLongNfft / 2 + 1;     // 769
+constexpr int kLongWarps = 4;
+constexpr int kLongScr = 2 * 16 * 17;            // fft512's transpose tiles (float2)
+// float blob offsets (in floats): fft twiddles | W1536^k | window | mel tables | dct
+constexpr int kLtTw = 0, kLtW32 = kLtTw + 1024, kLtW1536 = kLtW32 + 64, kLtWin = kLtW1536 + 2 * kLongNfft,
+              kLtEdge = kLtWin + kLongNfft, kLtInvUp = kLtEdge + 48, kLtInvDn = kLtInvUp + 48, kLtDct = kLtInvDn + 48,
+              kLtTotal = kLtDct + 16 * 48;
+constexpr int kLongWarpSmem = kLongScr * 8 + (kLongBins + 7) * 16 + 64 * 8;     // transpose tiles | X / power per bin | log-mel pair
+constexpr int kLongCtaSmem = (kLtW1536 * 4) + kLongWarps * kLongWarpSmem;          // shared twiddles | per-warp areas
+
+struct MfccLongParams {
+    const void* pcm; int in_f32;
+    const int64_t* seg_start;   // [U] first sample of each (trimmed) utterance inside pcm
+    const int32_t* seg_len;     // [U]
+    const int64_t* frame_off;   // [U+1]
+    int n_utt;
+    int frame_len, frame_step, nfilt, numcep, append_energy;
+    float preemph;
+    const float* tab;           // blob (kLt* offsets)
+    float* mfcc;                // [F_total, numcep] static cepstra
+    int64_t max_frames;
+};
+
+DEVFN int long_find_utt(const int64_t* frame_off, int n_utt, int64_t g) {
+    int lo = 0, hi = n_utt;   // frame_off[lo] <= g < frame_off[hi]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frame_off[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+
+struct LongFrame { const unsigned char* src; int64_t s0; int S; };   // samples of the utterance, first sample of the frame, length
+DEVFN float long_sample(const MfccLongParams& p, const LongFrame& f, int n, float w) {
+    const int64_t s = f.s0 + n;
+    if (n >= p.frame_len || s >= f.S) return 0.f;
+    float cur, prev = 0.f;
+    if (p.in_f32) { const float* q = reinterpret_cast<const float*>(f.src); cur = q[s]; if (s > 0) prev = q[s - 1]; }
+    else { const int16_t* q = reinterpret_cast<const int16_t*>(f.src); cur = cvt_i16(q[s]); if (s > 0) prev = cvt_i16(q[s - 1]); }
+    return dsp_fmaf(-p.preemph, prev, cur) * w;      // y[0] = x[0], y[n] = x[n] - c x[n-1] (sigproc.py:185), times the window
+}
+
+// wsm: per-warp shared memory = scr[kLongScr] float2 | acc[kLongBins] float4 | lmel[64] float2
+DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
+    const int lane = simt::tid() & 31;
+    float2* scr = reinterpret_cast<float2*>(wsm);
+    float4* acc = reinterpret_cast<float4*>(scr + kLongScr);
+    float2* lmel = reinterpret_cast<float2*>(acc + kLongBins + 7);
+    const float2* w1536 = reinterpret_cast<const float2*>(p.tab + kLtW1536);
+    const float* win = p.tab + kLtWin;
+    const int32_t* edge = reinterpret_cast<const int32_t*>(p.tab + kLtEdge);
+    const bool hasB = g0 + 1 < total;
+    const int esz = p.in_f32 ? 4 : 2;
+    LongFrame fa, fb;
+    {
+        const int ua = long_find_utt(p.frame_off, p.n_utt, g0);
+        const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
+        fa.src = reinterpret_cast<const unsigned char*>(p.pcm) + p.seg_start[ua] * esz;
+        fa.s0 = (g0 - p.frame_off[ua]) * p.frame_step; fa.S = p.seg_len[ua];
+        fb.src = reinterpret_cast<const unsigned char*>(p.pcm) + p.seg_start[ub] * esz;
+        fb.s0 = hasB ? (g0 + 1 - p.frame_off[ub]) * p.frame_step : 0; fb.S = hasB ? p.seg_len[ub] : 0;
+    }
+    cpx2 x[16];
+    const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+        // sub-sequence r: element m = 32 t + lane is sample n = 3 m + r of the frame
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int n = 96 * t + 3 * lane + r;
+            const float w = ldg(win + n);
+            x[t].re = make_float2(long_sample(p, fa, n, w), long_sample(p, fb, n, w));
+            x[t].im = zero2;
+        }
+        fft512(x, scr, tws, w32s, lane);
+        // X[k] += W1536^{r k} Z_r[k mod 512] for k = j and (j <= 256) k = j + 512, j = 32 t + lane
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int j = 32 * t + lane;
+            cpx2 v = x[t];
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r > 0) { const float2 w = ldg(w1536 + (r * j) % kLongNfft); v = cmuls(x[t], w.x, w.y); a = acc[j]; }
+            acc[j] = make_float4(a.x + v.re.x, a.y + v.re.y, a.z + v.im.x, a.w + v.im.y);
+            if (j <= 256) {
+                const int k = j + 512;
+                cpx2 u = x[t];
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r > 0) { const float2 w = ldg(w1536 + (r * k) % kLongNfft); u = cmuls(x[t], w.x, w.y); b = acc[k]; }
+                acc[k] = make_float4(b.x + u.re.x, b.y + u.re.y, b.z + u.im.x, b.w + u.im.y);
+            }
+        }
+    }
+    // power spectrum |X|^2 / NFFT (sigproc.py:158) into the .x / .y of the bin's own slot; frame energy = sum over all bins
+    float2 esum = zero2;
+    const float sc = 1.0f / (float)kLongNfft;
+    for (int k = lane; k < kLongBins; k += 32) {
+        const float4 a = acc[k];
+        const float2 pw = make_float2((a.x * a.x + a.z * a.z) * sc, (a.y * a.y + a.w * a.w) * sc);
+        acc[k].x = pw.x; acc[k].y = pw.y;
+        esum.x += pw.x; esum.y += pw.y;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { esum.x += simt::shfl32_xor(esum.x, m); esum.y += simt::shfl32_xor(esum.y, m); }
+    simt::warp_sync();
+    // mel filterbank (base.py:40-58): filter j rises over [e_j, e_{j+1}) and falls over [e_{j+1}, e_{j+2}); one filter at a
+    // time, its bins spread over the lanes
+    const float eps64 = 2.220446049250313e-16f;   // numpy.finfo(float64).eps floor (base.py:26,30)
+    const float* inv_up = p.tab + kLtInvUp;
+    const float* inv_dn = p.tab + kLtInvDn;
+    for (int j = 0; j < p.nfilt; ++j) {
+        const int lo = edge[j], mid = edge[j + 1], hi = edge[j + 2];
+        const float iu = inv_up[j], id = inv_dn[j];
+        float2 f = zero2;
+        for (int k = lo + lane; k < hi; k += 32) {
+            const float w = k < mid ? (float)(k - lo) * iu : (float)(hi - k) * id;
+            f.x = dsp_fmaf(w, acc[k].x, f.x); f.y = dsp_fmaf(w, acc[k].y, f.y);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) { f.x += simt::shfl32_xor(f.x, m); f.y += simt::shfl32_xor(f.y, m); }
+        if (lane == 0) lmel[j] = make_float2(dsp_logf(f.x == 0.f ? eps64 : f.x), dsp_logf(f.y == 0.f ? eps64 : f.y));
+    }
+    if (lane == 0) lmel[p.nfilt] = make_float2(dsp_logf(esum.x == 0.f ? eps64 : esum.x), dsp_logf(esum.y == 0.f ? eps64 : esum.y));
+    simt::warp_sync();
+    // DCT-II (ortho) * lifter (base.py:12-14), c0 := log(energy) (base.py:15)
+    if (lane < p.numcep) {
+        const float* d = p.tab + kLtDct + lane * 48;
+        float2 c = zero2;
+        for (int j = 0; j < p.nfilt; ++j) { const float2 l = lmel[j]; c.x = dsp_fmaf(d[j], l.x, c.x); c.y = dsp_fmaf(d[j], l.y, c.y); }
+        if (lane == 0 && p.append_energy) c = lmel[p.nfilt];
+        p.mfcc[g0 * p.numcep + lane] = c.x;
+        if (hasB) p.mfcc[(g0 + 1) * p.numcep + lane] = c.y;
+    }
+    simt::warp_sync();
+}
+
+// delta + delta-delta (base.py:70-79 twice, model.py:76-77) over per-utterance cepstra: one thread per (frame, column).
+// The second pass pads the DELTA array at the utterance edges, so it is evaluated as the weighted
+// sum of clamped deltas, each a weighted sum of clamped cepstra.
+DEVFN void delta_batch_thread(const float* mf, const int64_t* frame_off, int n_utt, int C, int N, float scale, int64_t i, float* out) {
+    const int64_t g = i / C;
+    const int c = (int)(i - g * C);
+    const int u = long_find_utt(frame_off, n_utt, g);
+    const int64_t r0 = frame_off[u];
+    const int F = (int)(frame_off[u + 1] - r0);
+    const int t = (int)(g - r0);
+    auto clampf = [&](int a) { return a < 0 ? 0 : (a > F - 1 ? F - 1 : a); };
+    auto d1 = [&](int a) {   // delta at the (clamped) frame a
+        float acc = 0.f;
+        for (int n = 1; n <= N; ++n) acc = dsp_fmaf((float)n, mf[(r0 + clampf(a + n)) * C + c] - mf[(r0 + clampf(a - n)) * C + c], acc);
+        return acc * scale;
+    };
+    float dd = 0.f;
+    for (int n = 1; n <= N; ++n) dd = dsp_fmaf((float)n, d1(clampf(t + n)) - d1(clampf(t - n)), dd);
+    float* o = out + g * 3 * C;
+    o[c] = mf[g * C + c]; o[C + c] = d1(t); o[2 * C + c] = dd * scale;
+}
+
+}  // namespace dspfe

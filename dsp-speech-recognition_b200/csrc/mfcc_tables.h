@@ -47,6 +47,21 @@ inline std::vector<double> mel_bin_edges(const MfccConfig& c) {
     return b;
 }
 
+// nfft = 1536 (the long-frame kernel K1L, mfcc_long_kernel.cuh)
+inline std::string mfcc_long_config_check(const MfccConfig& c) {
+    if (c.nfft != 1536) return "nfft must be 512 or 1536 in this build";
+    if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
+    if (c.frame_step < 1) return "frame_step must be >= 1";
+    if (c.nfilt < 1 || c.nfilt > kMaxNfilt) return "nfilt must be in [1, 40]";
+    if (c.numcep < 1 || c.numcep > kMaxNumcep || c.numcep > c.nfilt) return "numcep must be in [1, min(16, nfilt)]";
+    if (c.delta_n < 1 || c.delta_n > kMaxDeltaN) return "delta N must be in [1, 4]";
+    const double high = c.highfreq > 0 ? c.highfreq : c.samplerate / 2.0;
+    if (high > c.samplerate / 2.0) return "highfreq is greater than samplerate/2";
+    if (c.lowfreq < 0 || c.lowfreq >= high) return "lowfreq must be in [0, highfreq)";
+    if (!c.window.empty() && (int)c.window.size() != c.frame_len) return "window length must equal frame_len";
+    return "";
+}
+
 inline std::string mfcc_config_check(const MfccConfig& c) {
     if (c.nfft != kNfft) return "nfft must be 512 in this build (other sizes: SURVEY f-2)";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";

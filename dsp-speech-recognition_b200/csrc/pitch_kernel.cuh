@@ -192,50 +192,6 @@ DSP_HD bool pitch_feature_tail(const double* pitch, const double* amp, int F, do
 // ---------------------------------------------------------------------------------------------------------
 // warp-cooperative pieces (device + emulator)
 // ---------------------------------------------------------------------------------------------------------
-// 512-point complex FFT of a packed frame pair, one warp, 16 complex values per lane, 512 = 16 x 2 x 16:
-//   element n = 32*n1 + 16*q + n2'  ->  lane 16*q + n2', register n1   (natural order: n = 32*register + lane)
-// radix-16 in registers over n1, radix-2 across the two half-warps (one shuffle), twiddle, a 16x16 transpose inside each
-// half-warp through shared memory, radix-16 in registers over n2'.  With the radix-2 stage in the middle the output
-// lands in the SAME layout (k = k1 + 16*kq + 32*k2' -> lane 16*kq + k1, register k2'), so one routine serves every
-// transform of the chain and all pointwise tables are in natural order.  Forward DFT sum x[n] W512^{nk}; the
-// unnormalised inverse is the same routine between two conjugations.
-DEVFN cpx2 shfl_xor_c(cpx2 a, int m) {
-    cpx2 r;
-    r.re.x = simt::shfl32_xor(a.re.x, m); r.re.y = simt::shfl32_xor(a.re.y, m);
-    r.im.x = simt::shfl32_xor(a.im.x, m); r.im.y = simt::shfl32_xor(a.im.y, m);
-    return r;
-}
-
-// tws: W512^{n2' (k1 + 16 kq)} at [k1*32 + lane]; w32s: [2*k1 + q] = W32^{q k1}; scr: kWarpScr float2 owned by the warp
-DEVFN void fft512(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
-    dft16(x);                                                   // over n1 -> k1
-    const int q = lane >> 4, ll = lane & 15;
-    const float sg = q ? -1.f : 1.f;
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {                           // b[kq] = a[q=0] + (-1)^kq W32^k1 a[q=1]
-        const float2 w = w32s[2 * k1 + q];
-        const cpx2 u = cmuls(x[k1], w.x, w.y);
-        const cpx2 v = shfl_xor_c(u, 16);
-        cpx2 d; d.re = f2fmas(u.re, sg, v.re); d.im = f2fmas(u.im, sg, v.im);
-        const float2 t = tws[k1 * 32 + lane];
-        x[k1] = cmuls(d, t.x, t.y);
-    }
-    float2* tile = scr + q * (16 * 17);                         // (k1, n2') -> (n2', k1) inside the half-warp
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) tile[k1 * 17 + ll] = x[k1].re;
-    simt::warp_sync();
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) x[n2].re = tile[ll * 17 + n2];
-    simt::warp_sync();
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) tile[k1 * 17 + ll] = x[k1].im;
-    simt::warp_sync();
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) x[n2].im = tile[ll * 17 + n2];
-    simt::warp_sync();
-    dft16(x);                                                   // over n2' -> k2'
-}
-
 // medians of the non-negative entries of two frames at once (np.median(frame[frame >= 0]), pitch.py:146): exact k-th
 // order statistics by bitwise selection on the float bit patterns; NaN when a frame has no non-negative sample.
 DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], int L, int lane) {

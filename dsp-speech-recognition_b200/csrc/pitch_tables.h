@@ -26,6 +26,20 @@ inline void fir_taps(int N, double rate, double lo, double hi, bool hamming, std
     }
 }
 
+// twiddles of fft512 (fft_regs.h): tws[k1*32 + lane] = W512^{n2' (k1 + 16 kq)} with lane = 16 kq + n2', w32[2*k1 + q] = W32^{q k1}
+inline void fill_fft512_twiddles(float2* tws, float2* w32) {
+    const double kPi = 3.14159265358979323846;
+    for (int k1 = 0; k1 < 16; ++k1) {
+        for (int lane = 0; lane < 32; ++lane) {
+            const int kq = lane >> 4, n2 = lane & 15;
+            const double a = -2 * kPi * (double)(n2 * (k1 + 16 * kq)) / 512.0;
+            tws[k1 * 32 + lane] = make_float2((float)cos(a), (float)sin(a));
+        }
+        w32[2 * k1] = make_float2(1.f, 0.f);
+        w32[2 * k1 + 1] = make_float2((float)cos(-2 * kPi * k1 / 32.0), (float)sin(-2 * kPi * k1 / 32.0));
+    }
+}
+
 // Fills the scalar part of PitchParams and the two tables.  Returns 0 or a dspfe_status with `err` set.
 inline int build_pitch_tables(const dspfe_pitch_params& q, PitchParams& b, std::vector<float2>& tab, std::string& err) {
     std::memset(&b, 0, sizeof(b));
@@ -52,15 +66,7 @@ inline int build_pitch_tables(const dspfe_pitch_params& q, PitchParams& b, std::
     // spectrum of the FIR taps, all in natural order
     const double kPi = 3.14159265358979323846;
     tab.assign(kTabTotal, make_float2(0.f, 0.f));
-    for (int k1 = 0; k1 < 16; ++k1) {
-        for (int lane = 0; lane < 32; ++lane) {                   // W512^{n2' (k1 + 16 kq)}, lane = 16 kq + n2'
-            const int kq = lane >> 4, n2 = lane & 15;
-            const double a = -2 * kPi * (double)(n2 * (k1 + 16 * kq)) / 512.0;
-            tab[kTabTw + k1 * 32 + lane] = make_float2((float)cos(a), (float)sin(a));
-        }
-        tab[kTabW32 + 2 * k1] = make_float2(1.f, 0.f);            // W32^{q k1}
-        tab[kTabW32 + 2 * k1 + 1] = make_float2((float)cos(-2 * kPi * k1 / 32.0), (float)sin(-2 * kPi * k1 / 32.0));
-    }
+    fill_fft512_twiddles(tab.data() + kTabTw, tab.data() + kTabW32);
     for (int n = 0; n < 512; ++n) tab[kTabMod + n] = make_float2((float)cos(-2 * kPi * n / 1024.0), (float)sin(-2 * kPi * n / 1024.0));
     std::vector<double> hr, hi;
     fir_taps(q.frame_len, (double)q.dst_rate, q.band_lo, q.band_hi, true, hr, hi);

@@ -11,21 +11,21 @@ except Exception:  # pragma: no cover
     dct = None
 
 
-def _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc):
+def _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc, long_ok=False):
     signal = numpy.asarray(signal)
     if signal.ndim == 2:
         if signal.shape[0] != 1:
             raise NotImplementedError("2-D signals other than (1,S) are not supported")
         # reference sigproc.py:185 on a (1,S) array: signal[1:] is empty, so the row comes back unfiltered
         signal, preemph = signal[0], 0.0
-    if nfft != 512:
-        raise NotImplementedError("only nfft=512 is built (SURVEY f-2 lists the other sizes)")
+    if nfft != 512 and not (long_ok and nfft == 1536):
+        raise NotImplementedError("nfft=512 (and, for mfcc, nfft=1536 as model.py:74 uses) are built")
     frame_len = sigproc.round_half_up(winlen * samplerate)
     frame_step = sigproc.round_half_up(winstep * samplerate)
     if frame_len > nfft:
         raise NotImplementedError("frame longer than nfft (the reference truncates with a warning)")
-    if frame_step % 2 or frame_step < 2:
-        raise NotImplementedError("odd frame steps are not built")
+    if nfft == 512 and (frame_step % 2 or frame_step < 2):
+        raise NotImplementedError("odd frame steps are built for nfft=1536 only")
     win = numpy.asarray(winfunc(frame_len), dtype=numpy.float64)
     x, f32 = _gpu.pack_one(signal)
     return x, f32, frame_len, frame_step, float(preemph), win
@@ -37,7 +37,7 @@ def mfcc(signal, samplerate=16000, winlen=0.025, winstep=0.01, numcep=13,
     """reference base.py:8-16.  Returns float64 [NUMFRAMES, numcep]."""
     highfreq = highfreq or samplerate / 2
     assert highfreq <= samplerate / 2, "highfreq is greater than samplerate/2"
-    x, f32, flen, fstep, pre, win = _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc)
+    x, f32, flen, fstep, pre, win = _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc, long_ok=True)
     plan = _gpu.mfcc_plan(samplerate=samplerate, frame_len=flen, frame_step=fstep, nfft=nfft, nfilt=nfilt, numcep=numcep,
                           ceplifter=int(ceplifter), append_energy=bool(appendEnergy), delta_n=1, preemph=pre,
                           lowfreq=float(lowfreq), highfreq=float(highfreq), window=win)

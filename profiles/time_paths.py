@@ -51,6 +51,10 @@ feat, ffo = mf.mfcc_delta(pcm, off_d, trim=lr, out=out, frame_off=fo)
 inp = torch.empty((200, U, 39), dtype=torch.float32, device=dev)
 timed("cmvn_pad_batch (f-1: CMVN + pad to [200,U,39])", lambda: dspfe.cmvn_pad_batch(feat, ffo, out=inp))
 timed("robust_endpoint_detection (f-3: autocorrelation-gated rule)", lambda: ep.detect_robust(pcm, off_d))
+# f-2: model.py:74's configuration (30 ms Hamming frames, nfft 1536) on the trimmed batch
+mfl = dspfe.MfccPlan(frame_len=480, frame_step=160, nfft=1536, window=np.hamming(480), preemph=0.0, delta_n=3)
+outl = torch.empty((mfl.rows_bound(pcm.numel(), U), 39), dtype=torch.float32, device=dev)
+timed("mfcc_delta nfft=1536 (f-2: 480-sample Hamming frames, trimmed)", lambda: mfl.mfcc_delta(pcm, off_d, trim=lr, out=outl, frame_off=fo))
 if "--ingest" in sys.argv:
     import tempfile, time
     from scipy.io import wavfile

@@ -37,6 +37,7 @@ def lib():
         _lib = ctypes.CDLL(build())
         _lib.emu_mfcc_delta.restype = ctypes.c_longlong
         _lib.emu_pitch.restype = ctypes.c_longlong
+        _lib.emu_mfcc_long.restype = ctypes.c_longlong
     return _lib
 
 
@@ -68,6 +69,25 @@ def mfcc_delta(pcm, offsets, trim=None, **kw):
     r = lib().emu_mfcc_delta(ctypes.byref(p), pcm.ctypes.data_as(ctypes.c_void_p), int(f32), ctypes.c_longlong(len(pcm)),
                              offsets.ctypes.data_as(ctypes.c_void_p), tp, n, out.ctypes.data_as(ctypes.c_void_p),
                              ctypes.c_longlong(rows), fo.ctypes.data_as(ctypes.c_void_p), err, 256)
+    if r < 0:
+        raise RuntimeError(f"emulator: {err.value.decode()} ({r})")
+    return out[:r], fo
+
+
+def mfcc_long(pcm, offsets, **kw):
+    """K1L (nfft = 1536) bodies on the emulator: (out [F, 3*numcep], frame_off)."""
+    kw.setdefault("nfft", 1536)
+    p, keep = make_params(**kw)
+    f32 = np.asarray(pcm).dtype.kind == "f"
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32 if f32 else np.int16)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    rows = int(len(pcm) // p.frame_step + n)
+    out = np.full((rows, 3 * p.numcep), np.nan, dtype=np.float32)
+    fo = np.zeros(n + 1, dtype=np.int64)
+    err = ctypes.create_string_buffer(256)
+    r = lib().emu_mfcc_long(ctypes.byref(p), pcm.ctypes.data_as(ctypes.c_void_p), int(f32), offsets.ctypes.data_as(ctypes.c_void_p), n,
+                            out.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(rows), fo.ctypes.data_as(ctypes.c_void_p), err, 256)
     if r < 0:
         raise RuntimeError(f"emulator: {err.value.decode()} ({r})")
     return out[:r], fo

@@ -6,6 +6,7 @@
 
 #include "../../dsp-speech-recognition_b200/csrc/mfcc_kernel.cuh"
 #include "../../dsp-speech-recognition_b200/csrc/mfcc_tables.h"
+#include "../../dsp-speech-recognition_b200/csrc/mfcc_long_tables.h"
 #include "../../include/dspfe.h"
 
 namespace emu { bool run_cta(int bid, int nthreads, void (*body)(void*), void* arg); }
@@ -68,5 +69,55 @@ extern "C" long long emu_mfcc_delta(const dspfe_mfcc_params* q, const void* pcm,
         std::memset(smem.data(), 0xCD, smem.size());   // poison: uninitialised shared memory shows up as garbage
         if (!emu::run_cta(b, kMfccThreads, body, &A)) { std::snprintf(errbuf, errcap, "deadlock in CTA %d", b); return -3; }
     }
+    return fo;
+}
+
+
+// ---- K1L (nfft = 1536) on the emulator
+namespace {
+struct LArgs { MfccLongParams p; std::vector<unsigned char>* smem; int64_t total; };
+void long_body(void* a) {
+    LArgs* A = (LArgs*)a;
+    const int w = simt::tid() >> 5;
+    const int64_t g0 = 2 * ((int64_t)simt::bid() * kLongWarps + w);
+    if (g0 >= A->total) return;
+    const float2* tws = reinterpret_cast<const float2*>(A->p.tab);
+    mfcc_long_pair(A->p, g0, A->total, A->smem->data() + w * kLongWarpSmem, tws, tws + kLtW32 / 2);
+}
+}  // namespace
+
+extern "C" long long emu_mfcc_long(const dspfe_mfcc_params* q, const void* pcm, int in_f32, const long long* offsets, int n_utt,
+                                   float* out, long long max_rows, long long* frame_off_out, char* errbuf, int errcap) {
+    MfccConfig c;
+    c.samplerate = q->samplerate; c.frame_len = q->frame_len; c.frame_step = q->frame_step; c.nfft = q->nfft;
+    c.nfilt = q->nfilt; c.numcep = q->numcep; c.ceplifter = q->ceplifter; c.append_energy = q->append_energy;
+    c.delta_n = q->delta_n; c.preemph = q->preemph; c.lowfreq = q->lowfreq; c.highfreq = q->highfreq;
+    if (q->window) c.window.assign(q->window, q->window + q->frame_len);
+    const std::string err = mfcc_long_config_check(c);
+    if (!err.empty()) { std::snprintf(errbuf, errcap, "%s", err.c_str()); return -2; }
+    const std::vector<float> tab = build_long_tables(c);
+    std::vector<int64_t> seg_start(n_utt + 1), frame_off(n_utt + 1);
+    std::vector<int32_t> seg_len(n_utt + 1);
+    int64_t fo = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        seg_start[u] = offsets[u]; seg_len[u] = (int32_t)(offsets[u + 1] - offsets[u]);
+        frame_off[u] = fo; fo += num_frames(seg_len[u], c.frame_len, c.frame_step);
+    }
+    frame_off[n_utt] = fo;
+    if (fo > max_rows) { std::snprintf(errbuf, errcap, "out too small"); return -1; }
+    if (frame_off_out) std::memcpy(frame_off_out, frame_off.data(), (n_utt + 1) * sizeof(int64_t));
+    std::vector<float> cep((size_t)fo * c.numcep);
+    MfccLongParams p;
+    p.pcm = pcm; p.in_f32 = in_f32; p.seg_start = seg_start.data(); p.seg_len = seg_len.data(); p.frame_off = frame_off.data(); p.n_utt = n_utt;
+    p.frame_len = c.frame_len; p.frame_step = c.frame_step; p.nfilt = c.nfilt; p.numcep = c.numcep; p.append_energy = c.append_energy;
+    p.preemph = (float)c.preemph; p.tab = tab.data(); p.mfcc = cep.data(); p.max_frames = fo;
+    std::vector<unsigned char> smem(kLongWarps * kLongWarpSmem + 64);
+    LArgs A{p, &smem, fo};
+    for (int64_t b = 0; b * 2 * kLongWarps < fo + 2 * kLongWarps; ++b) {
+        std::memset(smem.data(), 0xCD, smem.size());
+        if (!emu::run_cta((int)b, 32 * kLongWarps, long_body, &A)) { std::snprintf(errbuf, errcap, "deadlock in CTA %lld", (long long)b); return -3; }
+    }
+    int den = 0; for (int i = 1; i <= c.delta_n; ++i) den += i * i;
+    for (int64_t i = 0; i < fo * c.numcep; ++i) delta_batch_thread(cep.data(), frame_off.data(), n_utt, c.numcep, c.delta_n, (float)(1.0 / (2.0 * den)), i, out);
     return fo;
 }

@@ -81,3 +81,22 @@ def test_unsupported_configs_are_rejected():
                dict(delta_n=0), dict(highfreq=9000.0)):
         with pytest.raises(RuntimeError):
             emu.mfcc_delta(x, [0, 1000], **kw)
+
+
+def test_long_frame_kernel_nfft1536():
+    """K1L: the configuration model.py:74 trains with -- 30 ms Hamming frames under nfft = 1536, at 16 kHz
+    (480 / 160) and at 44.1 kHz (1323 samples, odd hop of 441), pre-emphasis on and off, ragged batch."""
+    def ref39(x, rate, N, **kw):
+        m = O.mfcc(x, rate, winlen=0.03, winstep=0.01, nfft=1536, winfunc=np.hamming, **kw)
+        d1 = O.delta(m, N)
+        return np.concatenate([m, d1, O.delta(d1, N)], axis=1)
+    pcm, off = synth.synth_batch([9000, 479, 481, 4000], seed0=300)
+    out, fo = emu.mfcc_long(pcm, off, frame_len=480, frame_step=160, window=np.hamming(480), preemph=0.0, delta_n=3)
+    for u in range(4):
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(pcm[off[u]:off[u + 1]], 16000, 3, preemph=0), what=f"16k utt {u}")
+    x = synth.synth_utterance(301, 20000, sr=44100)
+    out, fo = emu.mfcc_long(x, [0, len(x)], frame_len=1323, frame_step=441, window=np.hamming(1323), samplerate=44100, delta_n=2)
+    assert_mfcc_close(out, ref39(x, 44100, 2), what="44.1k")
+    xf = (x / np.std(x)).astype(np.float32)          # model.py:62-63 feeds scaled float audio
+    out, fo = emu.mfcc_long(xf, [0, len(xf)], frame_len=1323, frame_step=441, window=np.hamming(1323), samplerate=44100, preemph=0.0)
+    assert_mfcc_close(out, ref39(xf.astype(np.float64), 44100, 2, preemph=0), what="44.1k float")

@@ -164,3 +164,34 @@ def test_model_batch_epilogue_cmvn_pad():
     assert np.max(np.abs(got - want) / (1 + np.abs(want))) <= 2e-4      # standardisation divides by a column std < 1 for some columns
     for u, n in enumerate(wl):
         assert not got[n:, u].any()                                      # zero padding beyond the utterance
+
+
+def test_nfft1536_long_frames_dropin_and_batch():
+    """model.py:74's call, through the drop-in API and through the batched plan."""
+    import torch
+    import dspfe
+    import features
+    from dspfe import synth
+    from oracle import ref_features as O
+    from tol import assert_mfcc_close
+    # the reference trainer's exact call: 2-D signal (pre-emphasis off by the quirk), Hamming, nfft 1536, float audio
+    x = synth.synth_utterance(410, 30000).astype(np.float64)
+    sound = x / np.std(x)
+    got = features.mfcc(sound.reshape(1, -1), 16000, winlen=0.03, winstep=0.01, nfft=1536, winfunc=np.hamming)
+    want = O.mfcc(sound, 16000, winlen=0.03, winstep=0.01, nfft=1536, preemph=0, winfunc=np.hamming)
+    assert_mfcc_close(got, want, what="model.py:74 call")
+    # 44.1 kHz, odd hop, int16 batch with delta N = 3
+    lengths = [44100, 20000, 1323, 60000, 500]
+    pcm, off = synth.synth_batch(lengths, seed0=420, sr=44100)
+    plan = dspfe.MfccPlan(samplerate=44100, frame_len=1323, frame_step=441, nfft=1536, window=np.hamming(1323), delta_n=3)
+    dev = torch.device("cuda:0")
+    out, fo = plan.mfcc_delta(torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev))
+    torch.cuda.synchronize()
+    out, fo = out.cpu().numpy(), fo.cpu().numpy()
+    for u in range(len(lengths)):
+        xs = pcm[off[u]:off[u + 1]]
+        m = O.mfcc(xs, 44100, winlen=0.03, winstep=0.01, nfft=1536, winfunc=np.hamming)
+        d1 = O.delta(m, 3)
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], np.concatenate([m, d1, O.delta(d1, 3)], axis=1), what=f"44.1k utt {u}")
+    host, _ = plan.mfcc_delta_host(pcm, off)
+    np.testing.assert_array_equal(host, out[: fo[-1]])
