@@ -56,9 +56,46 @@ __global__ void channel0_kernel(const int16_t* slab, const FileDesc* desc, int16
         dst[d.dst_off + i] = src[i * d.channels];
 }
 
+// Staging buffers of the ingest path, allocated on first use and kept (pinned allocations cost tens of milliseconds).
+struct IngestCtx {
+    void* h_stage[2] = {nullptr, nullptr}; int16_t* d_stage[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+    FileDesc* h_desc[2] = {nullptr, nullptr}; FileDesc* d_desc[2] = {nullptr, nullptr};
+    int64_t cap = 0; int device = -1;
+    void release() {
+        for (int i = 0; i < 2; ++i) {
+            if (h_stage[i]) cudaFreeHost(h_stage[i]); if (d_stage[i]) cudaFree(d_stage[i]); if (ev[i]) cudaEventDestroy(ev[i]);
+            if (h_desc[i]) cudaFreeHost(h_desc[i]); if (d_desc[i]) cudaFree(d_desc[i]);
+            h_stage[i] = nullptr; d_stage[i] = nullptr; ev[i] = nullptr; h_desc[i] = nullptr; d_desc[i] = nullptr;
+        }
+        cap = 0; device = -1;
+    }
+};
+IngestCtx g_ingest;
+constexpr int kMaxFilesPerSlab = 4096;
+
+int ingest_ensure(int64_t slab_cap) {
+    int dev = 0; cudaGetDevice(&dev);
+    if (g_ingest.cap >= slab_cap && g_ingest.device == dev) return DSPFE_OK;
+    g_ingest.release();
+    for (int i = 0; i < 2; ++i) {
+        if (cudaHostAlloc(&g_ingest.h_stage[i], (size_t)slab_cap + 16, cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc(&g_ingest.d_stage[i], (size_t)slab_cap + 16) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_ingest.ev[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaHostAlloc((void**)&g_ingest.h_desc[i], kMaxFilesPerSlab * sizeof(FileDesc), cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc(&g_ingest.d_desc[i], kMaxFilesPerSlab * sizeof(FileDesc)) != cudaSuccess) {
+            g_ingest.release(); return fail(DSPFE_ERR_NOMEM, "staging allocation failed");
+        }
+    }
+    g_ingest.cap = slab_cap; g_ingest.device = dev;
+    return DSPFE_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+void dspfe_ingest_release(void) { g_ingest.release(); }
+
 
 int dspfe_wav_info(const void* bytes, int64_t size, int32_t* rate, int32_t* channels, int32_t* bits, int64_t* n_frames, int64_t* data_offset) {
     if (!bytes || size < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
@@ -93,23 +130,10 @@ int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32
     // buffers are ping-ponged, so the host fills slab s+1 while slab s crosses PCIe; one kernel launch per slab.
     const int64_t kSlabBytes = 32ll << 20;
     const int64_t slab_cap = max_bytes > kSlabBytes ? max_bytes : kSlabBytes;
-    const int kMaxFilesPerSlab = 4096;
-    void* h_stage[2] = {nullptr, nullptr}; int16_t* d_stage[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
-    FileDesc* h_desc[2] = {nullptr, nullptr}; FileDesc* d_desc[2] = {nullptr, nullptr};
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) {
-            if (h_stage[i]) cudaFreeHost(h_stage[i]); if (d_stage[i]) cudaFree(d_stage[i]); if (ev[i]) cudaEventDestroy(ev[i]);
-            if (h_desc[i]) cudaFreeHost(h_desc[i]); if (d_desc[i]) cudaFree(d_desc[i]);
-        }
-    };
-    for (int i = 0; i < 2; ++i) {
-        if (cudaHostAlloc(&h_stage[i], (size_t)slab_cap + 16, cudaHostAllocDefault) != cudaSuccess ||
-            cudaMalloc(&d_stage[i], (size_t)slab_cap + 16) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaHostAlloc((void**)&h_desc[i], kMaxFilesPerSlab * sizeof(FileDesc), cudaHostAllocDefault) != cudaSuccess ||
-            cudaMalloc(&d_desc[i], kMaxFilesPerSlab * sizeof(FileDesc)) != cudaSuccess) {
-            cleanup(); return fail(DSPFE_ERR_NOMEM, "staging allocation failed");
-        }
-    }
+    { const int rc = ingest_ensure(slab_cap); if (rc) return rc; }
+    void** h_stage = g_ingest.h_stage; int16_t** d_stage = g_ingest.d_stage; cudaEvent_t* ev = g_ingest.ev;
+    FileDesc** h_desc = g_ingest.h_desc; FileDesc** d_desc = g_ingest.d_desc;
+    auto cleanup = [&]() {};
     int f = 0, slab = 0;
     while (f < n_files) {
         const int s = slab & 1;
@@ -139,8 +163,7 @@ int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32
         if (e != cudaSuccess) { cudaStreamSynchronize(st); cleanup(); return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
         ++slab;
     }
-    cudaStreamSynchronize(st);     // the staging buffers are released here; ingest is not on the kernels' hot path
-    cleanup();
+    cudaStreamSynchronize(st);     // the batch is resident when the call returns; the staging buffers stay for the next call
     return DSPFE_OK;
 }
 

@@ -296,6 +296,7 @@ int dspfe_delta_f32(const float* d_in, int64_t n_frames, int32_t n_cols, int32_t
  * and de-interleaves channel 0 on the device into d_pcm (capacity in samples); returns when the batch is resident.
  * ---------------------------------------------------------------------------------------------- */
 int dspfe_wav_info(const void* bytes, int64_t size, int32_t* rate, int32_t* channels, int32_t* bits, int64_t* n_frames, int64_t* data_offset);
+void dspfe_ingest_release(void);   /* frees the staging buffers the ingest path keeps between calls */
 int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32_t n_files, int16_t* d_pcm, int64_t capacity,
                       int64_t* h_offsets, int32_t* h_rates, void* stream);
 

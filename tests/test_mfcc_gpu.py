@@ -132,7 +132,9 @@ def test_errors(torch_dev):
     torch, dev = torch_dev
     import dspfe
     with pytest.raises(dspfe.DspfeError):
-        dspfe.MfccPlan(nfft=1536)
+        dspfe.MfccPlan(nfft=1024)
+    with pytest.raises(dspfe.DspfeError):
+        dspfe.MfccPlan(nfft=1536, frame_len=1600)
     with pytest.raises(dspfe.DspfeError):
         dspfe.MfccPlan(highfreq=9000.0)
     plan = dspfe.MfccPlan()
