@@ -2,6 +2,7 @@
 // Replaces the per-file Python loop of reference reader.py:67-85 (scipy.io.wavfile.read + sig[:,0]).  The host only
 // parses headers; sample bytes go to the device as they are, in slabs through two pinned staging buffers, and a
 // kernel picks channel 0 out of the interleaved frames straight into its place in the packed buffer.
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -164,6 +165,98 @@ int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32
         ++slab;
     }
     cudaStreamSynchronize(st);     // the batch is resident when the call returns; the staging buffers stay for the next call
+    return DSPFE_OK;
+}
+
+/* ---- path-based ingest: the library reads the files itself, sample bytes go straight into the pinned slabs ---- */
+static int scan_one(const char* path, WavInfo& w, std::string& err) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return DSPFE_ERR_INVALID_ARG; }
+    unsigned char head[4096];
+    const size_t got = std::fread(head, 1, sizeof(head), f);
+    std::fseek(f, 0, SEEK_END);
+    const long long fsize = std::ftell(f);
+    std::fclose(f);
+    // parse what was read; a data chunk that starts inside the first 4 KB is enough (its payload is measured against the file size)
+    int rc = parse_wav(head, (int64_t)got, w, err);
+    if (rc == DSPFE_OK && w.data_offset + w.n_frames * 2 * w.channels >= (int64_t)got && fsize > (long long)got) {
+        // the payload runs past the probe: recompute the frame count from the chunk length and the real file size
+        const int64_t len = rd32(head + w.data_offset - 4);
+        int64_t n = len;
+        if (w.data_offset + n > fsize) n = fsize - w.data_offset;
+        w.n_frames = n / (2 * w.channels);
+    }
+    return rc;
+}
+
+int dspfe_wav_scan_paths(const char* const* paths, int32_t n_files, int64_t* h_offsets, int32_t* h_rates) {
+    if (!paths || !h_offsets || n_files < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    int64_t total = 0;
+    for (int f = 0; f < n_files; ++f) {
+        WavInfo w{}; std::string err;
+        const int rc = scan_one(paths[f], w, err);
+        if (rc) return fail(rc, "file " + std::to_string(f) + ": " + err);
+        h_offsets[f] = total; total += w.n_frames;
+        if (h_rates) h_rates[f] = w.rate;
+    }
+    h_offsets[n_files] = total;
+    return DSPFE_OK;
+}
+
+int dspfe_ingest_wav_paths(const char* const* paths, int32_t n_files, int16_t* d_pcm, int64_t capacity, int64_t* h_offsets,
+                           int32_t* h_rates, void* stream) {
+    if (!paths || !h_offsets || n_files < 0 || (n_files > 0 && !d_pcm)) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    std::vector<WavInfo> info(n_files);
+    int64_t total = 0, max_bytes = 0;
+    for (int f = 0; f < n_files; ++f) {
+        std::string err;
+        const int rc = scan_one(paths[f], info[f], err);
+        if (rc) return fail(rc, "file " + std::to_string(f) + ": " + err);
+        h_offsets[f] = total; total += info[f].n_frames;
+        if (h_rates) h_rates[f] = info[f].rate;
+        const int64_t nb = info[f].n_frames * 2 * info[f].channels;
+        max_bytes = nb > max_bytes ? nb : max_bytes;
+    }
+    h_offsets[n_files] = total;
+    if (total > capacity) return fail(DSPFE_ERR_INVALID_ARG, "d_pcm capacity is below the total sample count");
+    if (n_files == 0 || total == 0) return DSPFE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t kSlabBytes = 32ll << 20;
+    const int64_t slab_cap = max_bytes > kSlabBytes ? max_bytes : kSlabBytes;
+    { const int rc = ingest_ensure(slab_cap); if (rc) return rc; }
+    int f = 0, slab = 0;
+    while (f < n_files) {
+        const int s = slab & 1;
+        if (slab >= 2) cudaEventSynchronize(g_ingest.ev[s]);
+        int64_t used = 0, longest = 0; int nd = 0;
+        while (f < n_files && nd < kMaxFilesPerSlab) {
+            const WavInfo& w = info[f];
+            const int64_t nb = w.n_frames * 2 * w.channels;
+            if (nd > 0 && used + nb > slab_cap) break;
+            if (nb > 0) {
+                FILE* fp = std::fopen(paths[f], "rb");
+                bool ok = fp != nullptr;
+                if (ok) { std::fseek(fp, (long)w.data_offset, SEEK_SET); ok = std::fread((unsigned char*)g_ingest.h_stage[s] + used, 1, (size_t)nb, fp) == (size_t)nb; std::fclose(fp); }
+                if (!ok) { cudaStreamSynchronize(st); return fail(DSPFE_ERR_INVALID_ARG, std::string("short read: ") + paths[f]); }
+                g_ingest.h_desc[s][nd++] = FileDesc{used / 2, h_offsets[f], w.n_frames, w.channels, 0};
+                longest = w.n_frames > longest ? w.n_frames : longest;
+                used += nb;
+            }
+            ++f;
+        }
+        if (nd == 0) { ++slab; continue; }
+        cudaError_t e = cudaMemcpyAsync(g_ingest.d_stage[s], g_ingest.h_stage[s], (size_t)used, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(g_ingest.d_desc[s], g_ingest.h_desc[s], nd * sizeof(FileDesc), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            unsigned gx = (unsigned)((longest + 255) / 256); if (gx > 1024) gx = 1024; if (gx < 1) gx = 1;
+            channel0_kernel<<<dim3(gx, (unsigned)nd), 256, 0, st>>>(g_ingest.d_stage[s], g_ingest.d_desc[s], d_pcm);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(g_ingest.ev[s], st);
+        if (e != cudaSuccess) { cudaStreamSynchronize(st); return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
+        ++slab;
+    }
+    cudaStreamSynchronize(st);
     return DSPFE_OK;
 }
 

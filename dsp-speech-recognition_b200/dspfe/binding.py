@@ -757,20 +757,20 @@ def wav_info(data):
 
 def ingest_wavs(paths):
     """reader.py:67-85 for a list of files: (pcm int16 CUDA tensor [total], offsets int64 NumPy [n+1], rates int32 [n]).
-    Channel 0 of every 16-bit PCM WAV file, packed back to back on the current device."""
+    Channel 0 of every 16-bit PCM WAV file, packed back to back on the current device; the library reads the files."""
     torch, dev = _cuda()
     L = lib()
-    L.dspfe_ingest_wavs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
-                                    ctypes.c_void_p, ctypes.c_void_p]
-    images = [np.fromfile(p, dtype=np.uint8) for p in paths]
-    n = len(images)
-    total = sum(wav_info(im)["n_frames"] for im in images)
-    ptrs = (ctypes.c_void_p * max(n, 1))(*[im.ctypes.data for im in images])
-    sizes = np.array([len(im) for im in images], dtype=np.int64)
-    pcm = torch.empty(max(total, 1), dtype=torch.int16, device=dev)
+    L.dspfe_wav_scan_paths.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    L.dspfe_ingest_wav_paths.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]
+    n = len(paths)
+    arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
     off = np.zeros(n + 1, dtype=np.int64)
     rates = np.zeros(max(n, 1), dtype=np.int32)
-    _check(L.dspfe_ingest_wavs(ptrs, _np_ptr(sizes), n, pcm.data_ptr(), pcm.numel(), _np_ptr(off), _np_ptr(rates), _stream(torch, dev)))
+    _check(L.dspfe_wav_scan_paths(arr, n, _np_ptr(off), _np_ptr(rates)))
+    total = int(off[-1])
+    pcm = torch.empty(max(total, 1), dtype=torch.int16, device=dev)
+    _check(L.dspfe_ingest_wav_paths(arr, n, pcm.data_ptr(), pcm.numel(), _np_ptr(off), _np_ptr(rates), _stream(torch, dev)))
     return pcm[:total], off, rates[:n]
 
 

@@ -300,6 +300,12 @@ void dspfe_ingest_release(void);   /* frees the staging buffers the ingest path 
 int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32_t n_files, int16_t* d_pcm, int64_t capacity,
                       int64_t* h_offsets, int32_t* h_rates, void* stream);
 
+/* The same from file paths: the library reads the files itself and the sample bytes go straight into the pinned slabs.
+ * dspfe_wav_scan_paths only reads the headers (h_offsets[n_files] = total samples, to size d_pcm). */
+int dspfe_wav_scan_paths(const char* const* paths, int32_t n_files, int64_t* h_offsets, int32_t* h_rates);
+int dspfe_ingest_wav_paths(const char* const* paths, int32_t n_files, int16_t* d_pcm, int64_t capacity, int64_t* h_offsets,
+                           int32_t* h_rates, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
