@@ -179,8 +179,8 @@ static int scan_one(const char* path, WavInfo& w, std::string& err) {
     std::fclose(f);
     // parse what was read; a data chunk that starts inside the first 4 KB is enough (its payload is measured against the file size)
     int rc = parse_wav(head, (int64_t)got, w, err);
-    if (rc == DSPFE_OK && w.data_offset + w.n_frames * 2 * w.channels >= (int64_t)got && fsize > (long long)got) {
-        // the payload runs past the probe: recompute the frame count from the chunk length and the real file size
+    if (rc == DSPFE_OK && fsize > (long long)got) {
+        // the file is longer than the probe: take the frame count from the chunk length and the real file size
         const int64_t len = rd32(head + w.data_offset - 4);
         int64_t n = len;
         if (w.data_offset + n > fsize) n = fsize - w.data_offset;

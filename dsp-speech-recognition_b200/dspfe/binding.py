@@ -755,6 +755,18 @@ def wav_info(data):
     return dict(rate=r.value, channels=c.value, bits=b.value, n_frames=n.value, data_offset=o.value)
 
 
+def wav_scan_paths(paths):
+    """Headers only (host): (offsets int64 [n+1] in samples of channel 0, rates int32 [n])."""
+    L = lib()
+    L.dspfe_wav_scan_paths.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    n = len(paths)
+    arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    off = np.zeros(n + 1, dtype=np.int64)
+    rates = np.zeros(max(n, 1), dtype=np.int32)
+    _check(L.dspfe_wav_scan_paths(arr, n, _np_ptr(off), _np_ptr(rates)))
+    return off, rates[:n]
+
+
 def ingest_wavs(paths):
     """reader.py:67-85 for a list of files: (pcm int16 CUDA tensor [total], offsets int64 NumPy [n+1], rates int32 [n]).
     Channel 0 of every 16-bit PCM WAV file, packed back to back on the current device; the library reads the files."""

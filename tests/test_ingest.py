@@ -40,6 +40,20 @@ def test_wav_header_parser_against_scipy():
     assert e.value.code == -2
 
 
+def test_scan_paths_counts_frames_beyond_the_header_probe(tmp_path):
+    rng = np.random.default_rng(2)
+    paths, want = [], []
+    for i, (rate, ch, n) in enumerate(((16000, 2, 20000), (16000, 1, 333), (44100, 2, 1), (16000, 2, 0), (48000, 3, 4097), (8000, 1, 2026))):
+        data = rng.integers(-32768, 32767, size=(n, ch) if ch > 1 else (n,), dtype=np.int16)
+        p = os.path.join(tmp_path, f"s{i}.wav")
+        wavfile.write(p, rate, data)
+        paths.append(p); want.append((rate, n))
+    off, rates = dspfe.wav_scan_paths(paths)
+    assert list(np.diff(off)) == [w[1] for w in want] and list(rates) == [w[0] for w in want]
+    with pytest.raises(dspfe.DspfeError):
+        dspfe.wav_scan_paths([os.path.join(tmp_path, "missing.wav")])
+
+
 @pytest.mark.gpu
 def test_ingest_matches_reader_semantics(tmp_path):
     rng = np.random.default_rng(1)
