@@ -147,6 +147,12 @@ void dspfe_endpoint_destroy(dspfe_endpoint_plan* pl) {
     delete pl;
 }
 
+int dspfe_endpoint_reserve(dspfe_endpoint_plan* pl, int64_t max_utt, int64_t max_total_samples) {
+    if (!pl || max_utt < 0 || max_total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    const int64_t frames = max_total_samples / pl->frame_step + max_utt;
+    return ensure(pl, max_utt, frames + max_utt * (pl->q + 1), frames);
+}
+
 int32_t dspfe_endpoint_frame_len(const dspfe_endpoint_plan* pl) { return pl ? pl->frame_len : -1; }
 int32_t dspfe_endpoint_frame_step(const dspfe_endpoint_plan* pl) { return pl ? pl->frame_step : -1; }
 

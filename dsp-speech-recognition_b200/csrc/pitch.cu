@@ -208,6 +208,11 @@ void dspfe_pitch_destroy(dspfe_pitch_plan* pl) {
     delete pl;
 }
 
+int dspfe_pitch_reserve(dspfe_pitch_plan* pl, int64_t max_utt, int64_t max_total_samples) {
+    if (!pl || max_utt < 0 || max_total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
+    return ensure(pl, max_utt, dspfe_pitch_frames_bound(pl, max_total_samples, max_utt));
+}
+
 int32_t dspfe_pitch_row_len(const dspfe_pitch_plan* pl) { return pl ? pl->base.row_len : -1; }
 
 int64_t dspfe_pitch_frames_bound(const dspfe_pitch_plan* pl, int64_t total_samples, int64_t n_utt) {

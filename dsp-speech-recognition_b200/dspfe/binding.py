@@ -273,6 +273,11 @@ class EndpointPlan:
     def frames_bound(self, total_samples, n_utt):
         return int(lib().dspfe_endpoint_frames_bound(self._h, int(total_samples), int(n_utt)))
 
+    def reserve(self, max_utt, max_total_samples):
+        L = lib()
+        L.dspfe_endpoint_reserve.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+        _check(L.dspfe_endpoint_reserve(self._h, int(max_utt), int(max_total_samples)))
+
     def detect(self, pcm, offsets, want_features=False, stream=None):
         """Device path: pcm int16 CUDA tensor, offsets int64 CUDA tensor [U+1].  Returns lr int32 [U,2]
         (and asum, zcr int32 [frames_bound], frame_off int64 [U+1] when want_features)."""
@@ -539,6 +544,11 @@ class PitchPlan:
 
     def frames_bound(self, total_samples, n_utt):
         return int(lib().dspfe_pitch_frames_bound(self._h, int(total_samples), int(n_utt)))
+
+    def reserve(self, max_utt, max_total_samples):
+        L = lib()
+        L.dspfe_pitch_reserve.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+        _check(L.dspfe_pitch_reserve(self._h, int(max_utt), int(max_total_samples)))
 
     def num_frames(self, n_samples):
         return int(lib().dspfe_pitch_num_frames(self._h, int(n_samples)))

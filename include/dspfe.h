@@ -146,6 +146,8 @@ typedef struct {
 void dspfe_endpoint_params_default(dspfe_endpoint_params* p, int32_t samplerate);
 int dspfe_endpoint_create(const dspfe_endpoint_params* p, dspfe_endpoint_plan** plan);
 void dspfe_endpoint_destroy(dspfe_endpoint_plan* plan);
+/* pre-sizes the plan's workspaces so that later calls up to these totals allocate nothing */
+int dspfe_endpoint_reserve(dspfe_endpoint_plan* plan, int64_t max_utt, int64_t max_total_samples);
 int32_t dspfe_endpoint_frame_len(const dspfe_endpoint_plan* plan);
 int32_t dspfe_endpoint_frame_step(const dspfe_endpoint_plan* plan);
 int64_t dspfe_endpoint_frames_bound(const dspfe_endpoint_plan* plan, int64_t total_samples, int64_t n_utt);
@@ -214,6 +216,7 @@ typedef struct {
 void dspfe_pitch_params_default(dspfe_pitch_params* p, int32_t method);
 int dspfe_pitch_create(const dspfe_pitch_params* p, dspfe_pitch_plan** plan);
 void dspfe_pitch_destroy(dspfe_pitch_plan* plan);
+int dspfe_pitch_reserve(dspfe_pitch_plan* plan, int64_t max_utt, int64_t max_total_samples);   /* pre-sizes the workspaces */
 int32_t dspfe_pitch_row_len(const dspfe_pitch_plan* plan);
 /* pitch frames of one utterance of n_samples (after decimation and framing) / upper bound for a whole batch */
 int64_t dspfe_pitch_num_frames(const dspfe_pitch_plan* plan, int64_t n_samples);

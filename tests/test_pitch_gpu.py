@@ -199,3 +199,25 @@ def test_config3_full_size_properties():
         if np.array_equal(got, want) and len(want) > 40:
             np.testing.assert_allclose(feat[u], O.pitch_feature(sig, 16000), rtol=1e-6, atol=1e-9)
     assert bad <= LAG_MISMATCH_BUDGET * tot, f"{bad} of {tot}"
+
+
+@pytest.mark.parametrize("rate", [8000, 44100, 48000])
+def test_other_sample_rates(rate):
+    """The sample-picking decimator for other source rates (44.1 kHz needs a 441 -> 100 pattern; at 48 kHz the frame's
+    source span does not fit the staging buffer and is read in place); 8 kHz is below 10 kHz: every sample is kept."""
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    lengths = [int(rate * t) for t in (0.6, 1.3, 0.2)]
+    pcm, off = synth.synth_batch(lengths, seed0=9100, sr=rate)
+    for method, fn in ((0, O.pitch_detect), (1, O.pitch_detect_sr)):
+        plan = dspfe.PitchPlan(method=method, samplerate=rate)
+        plan.reserve(len(lengths), len(pcm))
+        pitch, lag, fo = plan.detect_host(pcm, off)
+        bad = tot = 0
+        for u in range(len(lengths)):
+            want, _ = fn(pcm[off[u]:off[u + 1]], rate)
+            got = pitch[fo[u]:fo[u + 1]]
+            assert len(got) == len(want)
+            bad += int(np.sum(got != np.asarray(want))); tot += len(want)
+        assert bad <= max(1, LAG_MISMATCH_BUDGET * tot), (rate, method, bad, tot)
