@@ -10,9 +10,8 @@ constexpr int kGroupLanes = 16;       // lanes that cooperate on one frame pair
 constexpr int kMaxNfilt = 40;
 constexpr int kMaxNumcep = 16;
 constexpr int kMaxDeltaN = 4;
-constexpr int kMaxRanges = kMaxNfilt + 3;
-constexpr int kMaxTasks = 4;          // mel sub-ranges per lane
-constexpr int kMaxSubs = 64;          // mel sub-ranges (ranges longer than 16 bins are split)
+constexpr int kMelSlots = 3;          // mel filter pieces per lane (one per slot)
+constexpr int kMelMaxPieces = 4;      // pieces a single mel filter may be cut into
 constexpr int kScratchUnits = 272;    // 8-byte units per group: 16x17 transpose tile, >= 257 power bins
 constexpr int kMfccThreads = 128;     // 8 groups -> 16 frames per pass of the chunk loop
 constexpr int kMfccGroups = kMfccThreads / kGroupLanes;
@@ -32,11 +31,12 @@ struct MfccParams {
     const float* tables;        // constant tables blob (see MfccTables)
     float* out;                 // [F_total, 3*numcep]
     // dims
-    int frame_len, frame_step, nfilt, numcep, delta_n, seg_frames, nrange, append_energy;
+    int frame_len, frame_step, nfilt, numcep, delta_n, seg_frames, append_energy;
     int spec_kind;              // MODE 2 only: 0 power, 1 magnitude, 2 10*log10(power)
     float preemph, delta_scale, pow_scale;
     // table blob offsets, in floats
-    int o_twa, o_twp, o_sub, o_rsub, o_task, o_dct, o_win, dct_stride, tbl_floats;
+    int o_twa, o_twp, o_melw, o_melb, o_melc, o_dct, o_win, dct_stride, tbl_floats;
+    int mel_T[kMelSlots];       // iterations per mel slot (uniform over the lanes)
     // shared-memory carve-up, in bytes
     int sm_mbar, sm_scratch, sm_mfcc, sm_fbuf, sm_raw, sm_total;
     int fbuf_floats;            // (kFramesPerPass-1)*step + frame_len: samples one chunk needs

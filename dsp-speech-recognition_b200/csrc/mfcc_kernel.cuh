@@ -35,33 +35,32 @@ struct MfccSmem {
     unsigned char* raw;  // raw PCM chunk (bulk-copy destination): int16 or float32 samples
 };
 
+// Chunk geometry in 32-bit sample units relative to the utterance's aligned-down start (start & ~AL): the only
+// 64-bit quantity is the base pointer.  Utterances are limited to 2^31 - 2^16 samples.
 struct ChunkGeom {
-    int64_t a0s;        // packed-buffer sample index that lands at raw[0] (16-byte aligned)
-    int64_t bulk_src;   // == a0s
+    int a0;             // staging index 0 <-> relative sample a0 (16-byte aligned in the packed buffer)
     int bulk_bytes;     // multiple of 16, may be 0
-    int64_t tail_lo, tail_hi;  // packed sample range loaded with plain loads
-    int64_t s0;         // utterance sample index of fbuf[0]
+    int tail_lo, tail_hi;  // relative sample range loaded with plain loads
+    int s0;             // utterance sample index of the chunk's first frame
 };
 
 template <bool F32>
-DEVFN ChunkGeom chunk_geom(const MfccParams& p, int64_t start, int S, int frame0) {
-    const int64_t AL = F32 ? 3 : 7;   // samples per 16 bytes, minus one
+DEVFN ChunkGeom chunk_geom(const MfccParams& p, int sh, int lim, int S, int frame0) {
+    const int AL = F32 ? 3 : 7;   // samples per 16 bytes, minus one
     ChunkGeom g;
-    g.s0 = (int64_t)frame0 * p.frame_step;
-    int64_t s_first = g.s0 > 0 ? g.s0 - 1 : 0;
-    int64_t s_last = g.s0 + p.fbuf_floats;
+    g.s0 = frame0 * p.frame_step;
+    const int s_first = g.s0 > 0 ? g.s0 - 1 : 0;
+    int s_last = g.s0 + p.fbuf_floats;
     if (s_last > S) s_last = S;
     if (s_last < s_first) s_last = s_first;
-    int64_t p_first = start + s_first, p_last = start + s_last;
-    g.a0s = p_first & ~AL;
-    int64_t a1s = (p_last + AL) & ~AL;
-    int64_t lim = p.total_samples & ~AL;
-    if (a1s > lim) a1s = lim;
-    if (a1s < g.a0s) a1s = g.a0s;
-    g.bulk_src = g.a0s;
-    g.bulk_bytes = (int)(a1s - g.a0s) * (F32 ? 4 : 2);
-    g.tail_lo = a1s > p_first ? a1s : p_first;
-    g.tail_hi = p_last;
+    const int q_first = sh + s_first, q_last = sh + s_last;
+    g.a0 = q_first & ~AL;
+    int a1 = (q_last + AL) & ~AL;
+    if (a1 > lim) a1 = lim;
+    if (a1 < g.a0) a1 = g.a0;
+    g.bulk_bytes = (a1 - g.a0) * (F32 ? 4 : 2);
+    g.tail_lo = a1 > q_first ? a1 : q_first;
+    g.tail_hi = q_last;
     return g;
 }
 
@@ -104,42 +103,47 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
 
     const float2* twa = reinterpret_cast<const float2*>(sm.tables + p.o_twa);
     const float2* twp = reinterpret_cast<const float2*>(sm.tables + p.o_twp);
-    const int* subi = reinterpret_cast<const int*>(sm.tables + p.o_sub);   // per sub-range: lo, len | fi0, gi0, inv
-    const float* subf = sm.tables + p.o_sub;
-    const int* rsub = reinterpret_cast<const int*>(sm.tables + p.o_rsub);  // per range: first sub-range, count
-    const int* task = reinterpret_cast<const int*>(sm.tables + p.o_task);
+    const float2* melw = reinterpret_cast<const float2*>(sm.tables + p.o_melw) + lane;   // [iteration pair][lane] filter weights
+    const int* melb = reinterpret_cast<const int*>(sm.tables + p.o_melb) + lane;   // [slot][lane] first bin of the lane's piece
+    const int4* melc = reinterpret_cast<const int4*>(sm.tables + p.o_melc);  // [filter] -> the partial sums that make it up
     const float* dct = sm.tables + p.o_dct;
     const float* win = sm.tables + p.o_win;
     float2* scr = sm.scratch + grp * kScratchUnits;
 
-    auto issue_chunk = [&](int c) {
-        ChunkGeom g = chunk_geom<F32IN>(p, start, S, v_lo + c * kFramesPerPass);
-        const int esz = F32IN ? 4 : 2;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.pcm);
+    // everything below addresses the packed buffer relative to the utterance's aligned-down start
+    const int esz = F32IN ? 4 : 2;
+    const int sh = (int)(start & (F32IN ? 3 : 7));
+    const unsigned char* src8 = reinterpret_cast<const unsigned char*>(p.pcm) + (start - sh) * esz;
+    int lim;   // relative end of the last whole 16-byte unit of the packed buffer
+    {
+        const int64_t l64 = (p.total_samples & ~(int64_t)(F32IN ? 3 : 7)) - (start - sh);
+        lim = l64 > 0x7fff0000 ? 0x7fff0000 : (int)l64;
+    }
+    auto issue_chunk = [&](const ChunkGeom& g) {
         if (tid == 0 && g.bulk_bytes > 0) {
             simt::fence_proxy_async();
             simt::mbar_expect_tx(sm.mbar, (uint32_t)g.bulk_bytes);
-            simt::bulk_g2s(sm.raw, src + g.bulk_src * esz, (uint32_t)g.bulk_bytes, sm.mbar);
+            simt::bulk_g2s(sm.raw, src8 + (int64_t)g.a0 * esz, (uint32_t)g.bulk_bytes, sm.mbar);
         }
-        for (int64_t i = g.tail_lo + tid; i < g.tail_hi; i += kMfccThreads) {
-            if (F32IN) reinterpret_cast<float*>(sm.raw)[i - g.a0s] = reinterpret_cast<const float*>(src)[i];
-            else reinterpret_cast<int16_t*>(sm.raw)[i - g.a0s] = reinterpret_cast<const int16_t*>(src)[i];
+        for (int i = g.tail_lo + tid; i < g.tail_hi; i += kMfccThreads) {
+            if (F32IN) reinterpret_cast<float*>(sm.raw)[i - g.a0] = reinterpret_cast<const float*>(src8)[i];
+            else reinterpret_cast<int16_t*>(sm.raw)[i - g.a0] = reinterpret_cast<const int16_t*>(src8)[i];
         }
     };
-    issue_chunk(0);
+    ChunkGeom g = chunk_geom<F32IN>(p, sh, lim, S, v_lo);
+    issue_chunk(g);
 
     const int nfull = NFULL >= 0 ? NFULL : (p.frame_len >> 5);
     uint32_t parity = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int frame0 = v_lo + c * kFramesPerPass;
-        const ChunkGeom g = chunk_geom<F32IN>(p, start, S, frame0);
         if (g.bulk_bytes > 0) { simt::mbar_wait(sm.mbar, parity); parity ^= 1; }
         if (c == 0) simt::cta_sync();  // chunk-0 tail stores -> visible (later chunks: the loop-end barrier)
 
         // ---- raw int16 -> pre-emphasised fp32, 8 samples per thread.  Sample q of the staging area (packed sample
         // a0s + q) lands in plane q&1 at index q>>1.  Reference: y[0] = x[0], y[n] = x[n] - c*x[n-1] (sigproc.py:185), zeros past the end (:84-87).
         {
-            const int rel = (int)(g.a0s - start);  // utterance sample index of raw[0] (may be negative)
+            const int rel = g.a0 - sh;  // utterance sample index of raw[0] (may be negative)
             const float cpre = p.preemph;
             for (int j0 = 0; j0 < p.fbuf_vecs; j0 += kMfccThreads) {
                 const int j = j0 + tid;
@@ -181,7 +185,11 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             }
         }
         simt::cta_sync();
-        if (c + 1 < nchunks) issue_chunk(c + 1);  // raw is free again: overlap the next load with the FFTs
+        const int fb_base = sh - g.a0 + g.s0;     // staging index of sample 0 of the chunk's first frame
+        if (c + 1 < nchunks) {   // raw is free again: overlap the next load with the FFTs
+            g = chunk_geom<F32IN>(p, sh, lim, S, frame0 + kFramesPerPass);
+            issue_chunk(g);
+        }
 
         // ---- one frame pair per 16-lane group; a warp (two groups) is active or idle as a whole.  Within a warp
         // group 0 packs frames (f, f+2) and group 1 packs (f+1, f+3): the two groups' loads then fall into
@@ -191,7 +199,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
         if (frame0 + 4 * (tid >> 5) <= v_hi) {
             cpx2 x[16];
             {
-                const int fb0 = (int)(start - g.a0s + g.s0) + fl * p.frame_step;   // staging index of the frame's sample 0
+                const int fb0 = fb_base + fl * p.frame_step;   // staging index of the frame's sample 0
                 const float* plane_e = sm.fbuf;
                 const float* plane_o = sm.fbuf + 4 * p.fbuf_vecs;
                 const bool odd = (fb0 & 1) != 0;                                   // uniform over the CTA (even frame step)
@@ -242,6 +250,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             // partner Z[(256-k) mod 256] lives in lane (16-lane)&15, register 15-r (lane 0: register (16-r)&15).
             const int src = (16 - lane) & 15;
             const float sc = p.pow_scale;  // 1 / (4 * NFFT)
+            float2 esum = make_float2(0.f, 0.f);   // this lane's share of sum_k P[k] (frame energy, reference base.py:25)
 #pragma unroll
             for (int r = 0; r < 9; ++r) {
                 if (r == 8 && lane != 0) break;  // lane 0 also owns the self-paired bin 128
@@ -271,9 +280,12 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 if (r < 8) {
                     scr[k] = pa;                     // lane 0, r 0: Z[0] pairs with itself -> X[0] and X[256]
                     scr[256 - k] = pb;
+                    esum = f2add(esum, f2add(pa, pb));
                 } else {
                     scr[128] = pa;
+                    esum = f2add(esum, pa);
                 }
+                if (r == 0 && lane != 0) scr[256 + lane] = make_float2(0.f, 0.f);   // the mel pieces may read (with zero weights) past bin 256
             }
             simt::group_sync();
             if (MODE == 2) {   // spectrum tap: rows straight to global memory
@@ -287,30 +299,26 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 }
             } else {
 
-            // ---- mel filterbank as sums over sub-ranges of the triangle edges (see mfcc_tables.h): the weights
-            // are generated arithmetically, each power bin is read exactly once.
-            float2 upv[kMaxTasks], dnv[kMaxTasks];
-            float2 esum = make_float2(0.f, 0.f);
+            // ---- mel filterbank (reference base.py:28-29): every lane accumulates one piece of a filter per slot; the
+            // trip counts are uniform over the lanes and the weights come from a [iteration][lane] table (mfcc_tables.h)
+            float2 macc[kMelSlots];
+            {
+                int tb = 0;
 #pragma unroll
-            for (int t = 0; t < kMaxTasks; ++t) {
-                const int si = task[lane * kMaxTasks + t];
-                float2 up = make_float2(0.f, 0.f), dn = up;
-                if (si >= 0) {
-                    const int len = subi[5 * si + 1];
-                    const float2* pp = scr + subi[5 * si];
-                    float fi = subf[5 * si + 2], gi = subf[5 * si + 3];
-                    const float inv = subf[5 * si + 4];
-#pragma unroll 4
-                    for (int k = 0; k < len; ++k) {
-                        const float2 pw = pp[k];
-                        up = f2fmas(pw, fi, up);
-                        dn = f2fmas(pw, gi, dn);
-                        fi += 1.f; gi -= 1.f;
+                for (int s = 0; s < kMelSlots; ++s) {
+                    const int T = p.mel_T[s];
+                    const float2* pp = scr + melb[s * kGroupLanes];
+                    const float2* wp = melw + (tb >> 1) * kGroupLanes;
+                    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll 2
+                    for (int t = 0; t < T; t += 2) {   // T is even
+                        const float2 w = wp[(t >> 1) * kGroupLanes];
+                        a0 = f2fmas(pp[t], w.x, a0);
+                        a1 = f2fmas(pp[t + 1], w.y, a1);
                     }
-                    up = f2muls(up, inv); dn = f2muls(dn, inv);
-                    esum = f2add(esum, f2add(up, dn));   // rising + falling weights sum to 1: this is sum(P) of the sub-range
+                    macc[s] = f2add(a0, a1);
+                    tb += T;
                 }
-                upv[t] = up; dnv[t] = dn;
             }
             // total frame energy (reference base.py:25): reduce over the group
 #pragma unroll
@@ -319,24 +327,18 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 esum.y += simt::shfl16(esum.y, lane ^ m);
             }
             simt::group_sync();  // all lanes are done reading P before the staging area overwrites it
-            float2* segu = scr;                   // [kMaxSubs]
-            float2* segd = scr + kMaxSubs;        // [kMaxSubs]
-            float2* lmel = scr + 2 * kMaxSubs;    // [nfilt + 1]; the last entry is log(energy)
+            float2* part = scr;                                   // [kMelSlots * 16 + 1]; the last entry stays zero
+            float2* lmel = scr + kMelSlots * kGroupLanes + 2;     // [nfilt + 1]; the last entry is log(energy); 16-byte aligned
 #pragma unroll
-            for (int t = 0; t < kMaxTasks; ++t) {
-                const int si = task[lane * kMaxTasks + t];
-                if (si >= 0) { segu[si] = upv[t]; segd[si] = dnv[t]; }
-            }
+            for (int s = 0; s < kMelSlots; ++s) part[s * kGroupLanes + lane] = macc[s];
+            if (lane == 0) part[kMelSlots * kGroupLanes] = make_float2(0.f, 0.f);
             simt::group_sync();
             const float eps64 = 2.220446049250313e-16f;  // numpy.finfo(float64).eps, reference base.py:26,30
             for (int j = lane; j <= p.nfilt; j += 16) {
                 float2 f = esum;
-                if (j < p.nfilt) {   // filter j = rising part over range j+1 + falling part over range j+2
-                    f = make_float2(0.f, 0.f);
-                    const int a0 = rsub[2 * (j + 1)], an = rsub[2 * (j + 1) + 1];
-                    for (int q = 0; q < an; ++q) f = f2add(f, segu[a0 + q]);
-                    const int b0 = rsub[2 * (j + 2)], bn = rsub[2 * (j + 2) + 1];
-                    for (int q = 0; q < bn; ++q) f = f2add(f, segd[b0 + q]);
+                if (j < p.nfilt) {
+                    const int4 ci = melc[j];
+                    f = f2add(f2add(part[ci.x], part[ci.y]), f2add(part[ci.z], part[ci.w]));
                 }
                 if (f.x == 0.f) f.x = eps64;
                 if (f.y == 0.f) f.y = eps64;
@@ -371,62 +373,45 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     }
 
     if (MODE != 0) return;
-    // ---- epilogue: delta (clamped on the utterance), delta-delta (clamped on the delta array), stores.
-    // Three uniform passes (no divergent per-column work); flat indices advance by the CTA size without any
-    // division: (row, col) += (128 / w, 128 % w).
+    // ---- epilogue: delta (clamped on the utterance, reference base.py:70-79), delta-delta (= delta of the already
+    // clamped delta array, model.py:76-77 / Appendix A-5) and the [F, 3*numcep] row stores.  Thread = (row r of a
+    // block of 8 rows, column c): a thread keeps its column, rows advance by 8, so there is no index arithmetic in
+    // the loops; rows away from the utterance ends take the clamp-free path.
     float* dbuf = sm.fbuf;                                   // aliases fbuf+raw: no copy is in flight any more
-    float* ddbuf = reinterpret_cast<float*>(sm.scratch);     // aliases the FFT scratch
     const int u_lo = tile.f0 - N > 0 ? tile.f0 - N : 0;
     const int u_hi = tile.f0 + tile.nf - 1 + N < F - 1 ? tile.f0 + tile.nf - 1 + N : F - 1;
-    const int qstep = kMfccThreads / numcep, rstep = kMfccThreads % numcep;
-    {
-        const int nd = (u_hi - u_lo + 1) * numcep;
-        int uu = u_lo + tid / numcep, cc = tid % numcep;
-        for (int i = tid; i < nd; i += kMfccThreads) {
-            float acc = 0.f;
+    const int width = 3 * numcep;
+    const float dscale = p.delta_scale;
+    auto taps = [&](const float* q, int row) {   // sum_n n * (q[row + n] - q[row - n]), rows clamped to [0, F-1]
+        float acc = 0.f;
+        if (row >= N && row + N <= F - 1) {
+#pragma unroll
+            for (int n = 1; n <= kMaxDeltaN; ++n)
+                if (n <= N) acc = dsp_fmaf((float)n, q[n * numcep] - q[-n * numcep], acc);
+        } else {
             for (int n = 1; n <= N; ++n) {
-                int hi = uu + n; if (hi > F - 1) hi = F - 1;
-                int lo = uu - n; if (lo < 0) lo = 0;
-                acc = dsp_fmaf((float)n, sm.mfcc[(hi - v_lo) * numcep + cc] - sm.mfcc[(lo - v_lo) * numcep + cc], acc);
+                const int hi = row + n > F - 1 ? F - 1 - row : n, lo = row - n < 0 ? row : n;
+                acc = dsp_fmaf((float)n, q[hi * numcep] - q[-lo * numcep], acc);
             }
-            dbuf[i] = acc * p.delta_scale;
-            uu += qstep; cc += rstep;
-            if (cc >= numcep) { cc -= numcep; ++uu; }
+        }
+        return acc * dscale;
+    };
+    if (lane < numcep) {
+        for (int uu = u_lo + grp; uu <= u_hi; uu += kMfccGroups) {
+            const float* m0 = sm.mfcc + (uu - v_lo) * numcep + lane;
+            const float d = taps(m0, uu);
+            dbuf[(uu - u_lo) * numcep + lane] = d;
+            if (uu >= tile.f0 && uu < tile.f0 + tile.nf) {
+                float* o = p.out + (row0 + uu) * width + lane;
+                o[0] = m0[0];
+                o[numcep] = d;
+            }
         }
     }
     simt::cta_sync();
-    {
-        const int ndd = tile.nf * numcep;
-        int tt = tile.f0 + tid / numcep, cc = tid % numcep;
-        for (int i = tid; i < ndd; i += kMfccThreads) {
-            float acc = 0.f;
-            for (int n = 1; n <= N; ++n) {
-                int hi = tt + n; if (hi > F - 1) hi = F - 1;
-                int lo = tt - n; if (lo < 0) lo = 0;
-                acc = dsp_fmaf((float)n, dbuf[(hi - u_lo) * numcep + cc] - dbuf[(lo - u_lo) * numcep + cc], acc);
-            }
-            ddbuf[i] = acc * p.delta_scale;
-            tt += qstep; cc += rstep;
-            if (cc >= numcep) { cc -= numcep; ++tt; }
-        }
-    }
-    simt::cta_sync();
-    {
-        const int width = 3 * numcep;
-        const int nout = tile.nf * width;
-        float* outp = p.out + (row0 + tile.f0) * width;
-        const float* src0 = sm.mfcc + (tile.f0 - v_lo) * numcep;
-        const float* src1 = dbuf + (tile.f0 - u_lo) * numcep;
-        const int qs = kMfccThreads / width, rs = kMfccThreads % width;
-        int row = tid / width, col = tid % width;
-        for (int i = tid; i < nout; i += kMfccThreads) {
-            const float* s = src0; int cc = col;
-            if (col >= numcep) { s = src1; cc = col - numcep; }
-            if (col >= 2 * numcep) { s = ddbuf; cc = col - 2 * numcep; }
-            outp[i] = s[row * numcep + cc];
-            row += qs; col += rs;
-            if (col >= width) { col -= width; ++row; }
-        }
+    if (lane < numcep) {
+        for (int tt = tile.f0 + grp; tt < tile.f0 + tile.nf; tt += kMfccGroups)
+            p.out[(row0 + tt) * width + 2 * numcep + lane] = taps(dbuf + (tt - u_lo) * numcep + lane, tt);
     }
 }
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -91,7 +92,6 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     int den = 0; for (int i = 1; i <= c.delta_n; ++i) den += i * i;
     p.delta_scale = (float)(1.0 / (2.0 * den));
     p.pow_scale = (float)(1.0 / (4.0 * c.nfft));
-    p.nrange = c.nfilt + 3;
 
     auto align4 = [&]() { while (blob.size() & 3) blob.push_back(0.f); };
     // W256^{n2*k1} at [k1*16 + n2]
@@ -107,60 +107,140 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
         const double a = -2.0 * kPi * (double)k / 512.0;
         blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
     }
+    // Mel filterbank (reference base.py:40-58) as balanced *pieces*: filter j has non-zero weights on one contiguous
+    // run of bins; the runs are cut into pieces and every (slot, lane) of a 16-lane group owns at most one piece.
+    // All lanes run the same mel_T[slot] iterations per slot (zero weights pad short pieces), so the kernel's loop
+    // has a uniform trip count, no per-lane branching and reads its weights from a [iteration][lane] table.
     const std::vector<double> bins = mel_bin_edges(c);
-    std::vector<int> edge(p.nrange + 1);
-    edge[0] = 0;
-    for (int i = 0; i < c.nfilt + 2; ++i) edge[i + 1] = std::min(std::max((int)bins[i], 0), kBins);
-    edge[p.nrange] = kBins;
-    for (int i = 1; i <= p.nrange; ++i) edge[i] = std::max(edge[i], edge[i - 1]);
-    // Mel ranges = the intervals between consecutive filter centres (plus the two unfiltered ends).  Inside
-    // range [lo, hi): rising weight of filter j = (k-lo)/(hi-lo), falling weight of filter j-1 = (hi-k)/(hi-lo)
-    // (reference base.py:52-57).  Ranges longer than 16 bins are split into sub-ranges so that the 16 lanes of
-    // a group get balanced work; each sub-range starts its weight counters at (sub_lo - lo, hi - sub_lo).
-    struct Sub { int lo, len; float fi0, gi0, inv; int range; };
-    std::vector<Sub> subs;
-    std::vector<int> rsub(2 * kMaxRanges, 0);
-    for (int i = 0; i < p.nrange; ++i) {
-        const int lo = edge[i], hi = edge[i + 1];
-        rsub[2 * i] = (int)subs.size();
-        if (hi > lo) {
-            if (i >= 1 && i <= c.nfilt + 1 && (bins[i - 1] != (double)lo || bins[i] != (double)hi)) {
-                err = "mel bin edges fall outside [0, nfft/2]"; return {};
-            }
-            const int parts = (hi - lo + 15) / 16;
-            for (int q = 0; q < parts; ++q) {
-                const int a = lo + (int)((int64_t)(hi - lo) * q / parts), b = lo + (int)((int64_t)(hi - lo) * (q + 1) / parts);
-                subs.push_back({a, b - a, (float)(a - lo), (float)(hi - a), (float)(1.0 / (hi - lo)), i});
-            }
-        }
-        rsub[2 * i + 1] = (int)subs.size() - rsub[2 * i];
+    for (int i = 0; i < c.nfilt + 2; ++i)
+        if (bins[i] < 0 || bins[i] > kNfft / 2) { err = "mel bin edges fall outside [0, nfft/2]"; return {}; }
+    struct Run { int k0; std::vector<float> w; };
+    std::vector<Run> runs(c.nfilt);
+    for (int j = 0; j < c.nfilt; ++j) {
+        const int lo = (int)bins[j], ce = (int)bins[j + 1], hi = (int)bins[j + 2];
+        std::vector<double> w(kBins, 0.0);
+        for (int k = lo; k < ce; ++k) w[k] = (k - bins[j]) / (bins[j + 1] - bins[j]);
+        for (int k = ce; k < hi; ++k) w[k] = (bins[j + 2] - k) / (bins[j + 2] - bins[j + 1]);
+        int a = 0, b = kBins;
+        while (a < kBins && w[a] == 0.0) ++a;
+        while (b > a && w[b - 1] == 0.0) --b;
+        runs[j].k0 = a < kBins ? a : 0;
+        for (int k = a; k < b; ++k) runs[j].w.push_back((float)w[k]);
     }
-    if ((int)subs.size() > kMaxSubs) { err = "too many mel sub-ranges"; return {}; }
-    p.o_sub = (int)blob.size();
-    for (int i = 0; i < kMaxSubs; ++i) {
-        Sub s = i < (int)subs.size() ? subs[i] : Sub{0, 0, 0.f, 0.f, 0.f, 0};
-        float f; std::memcpy(&f, &s.lo, 4); blob.push_back(f);
-        std::memcpy(&f, &s.len, 4); blob.push_back(f);
-        blob.push_back(s.fi0); blob.push_back(s.gi0); blob.push_back(s.inv);
-    }
-    p.o_rsub = (int)blob.size();
-    for (int v : rsub) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
-    // longest-first assignment of the sub-ranges to the 16 lanes of a group
-    p.o_task = (int)blob.size();
+    struct Piece { int filt, off, len, slot, lane, k0; };
+    std::vector<Piece> pieces;
+    int mel_T[kMelSlots] = {0, 0, 0};
     {
-        std::vector<int> order;
-        for (int i = 0; i < (int)subs.size(); ++i) order.push_back(i);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subs[a].len > subs[b].len; });
-        std::vector<int> t(kGroupLanes * kMaxTasks, -1), load(kGroupLanes, 0), cnt(kGroupLanes, 0);
-        for (int si : order) {
-            int best = -1;
-            for (int l = 0; l < kGroupLanes; ++l)
-                if (cnt[l] < kMaxTasks && (best < 0 || load[l] < load[best])) best = l;
-            if (best < 0) { err = "mel sub-range assignment overflow"; return {}; }
-            t[best * kMaxTasks + cnt[best]++] = si;
-            load[best] += subs[si].len;
+        int nnz = 0, lmax = 0;
+        for (auto& r : runs) { nnz += (int)r.w.size(); lmax = std::max(lmax, (int)r.w.size()); }
+        // Lanes of a slot: lane l may take a piece whose first bin is k0 if it starts d = (k0 - l) mod 16 bins early
+        // (zero weights in front) -- then the 16 lanes of a group read 16 different 8-byte bank pairs in every iteration
+        // (no shared-memory bank conflicts).  Bipartite matching, augmenting paths.
+        bool allow_conflicts = false;
+        auto assign_lanes = [&](std::vector<Piece>& out, int s, int T) {
+            std::vector<int> idx;
+            for (int i = 0; i < (int)out.size(); ++i) if (out[i].slot == s) idx.push_back(i);
+            int owner[kGroupLanes]; for (int l = 0; l < kGroupLanes; ++l) owner[l] = -1;
+            auto ok = [&](int i, int l) {
+                const int k0 = runs[out[i].filt].k0 + out[i].off, d = ((k0 - l) % kGroupLanes + kGroupLanes) % kGroupLanes;
+                return k0 - d >= 0 && d + out[i].len <= T && k0 - d + T <= kScratchUnits;
+            };
+            bool seen[kGroupLanes];
+            std::function<bool(int)> aug = [&](int i) {
+                for (int l = 0; l < kGroupLanes; ++l) {
+                    if (seen[l] || !ok(i, l)) continue;
+                    seen[l] = true;
+                    if (owner[l] < 0 || aug(owner[l])) { owner[l] = i; return true; }
+                }
+                return false;
+            };
+            bool matched = true;
+            for (int i : idx) { for (bool& b : seen) b = false; if (!aug(i)) { matched = false; break; } }
+            if (!matched) {
+                if (!allow_conflicts) return false;
+                int l = 0;   // last resort (degenerate filterbanks): natural starts, bank conflicts accepted
+                for (int i : idx) {
+                    const int k0 = runs[out[i].filt].k0 + out[i].off;
+                    out[i].lane = l++; out[i].k0 = std::max(0, std::min(k0, kScratchUnits - T));
+                    if (k0 - out[i].k0 + out[i].len > T) return false;
+                }
+                return true;
+            }
+            for (int l = 0; l < kGroupLanes; ++l) if (owner[l] >= 0) {
+                Piece& pc = out[owner[l]];
+                const int k0 = runs[pc.filt].k0 + pc.off;
+                pc.lane = l; pc.k0 = k0 - ((k0 - l) % kGroupLanes + kGroupLanes) % kGroupLanes;
+            }
+            return true;
+        };
+        auto try_pack = [&](const int* T, int slack, std::vector<Piece>& out) {
+            int freec[kMelSlots];
+            for (int s = 0; s < kMelSlots; ++s) freec[s] = T[s] - slack > 0 ? kGroupLanes : 0;
+            std::vector<int> order(c.nfilt);
+            for (int j = 0; j < c.nfilt; ++j) order[j] = j;
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return runs[x].w.size() > runs[y].w.size(); });
+            out.clear();
+            for (int j : order) {
+                int rem = (int)runs[j].w.size(), off = 0, np = 0;
+                while (rem > 0) {
+                    if (np == kMelMaxPieces) return false;
+                    int pick = -1;   // tightest free slot that holds the rest, else the largest free slot (T is sorted descending)
+                    for (int s = 0; s < kMelSlots; ++s) if (freec[s] > 0 && T[s] - slack >= rem) pick = s;
+                    if (pick < 0) for (int s = 0; s < kMelSlots; ++s) if (freec[s] > 0) { pick = s; break; }
+                    if (pick < 0) return false;
+                    const int take = std::min(rem, T[pick] - slack);
+                    out.push_back({j, off, take, pick, 0, 0});
+                    --freec[pick]; off += take; rem -= take; ++np;
+                }
+            }
+            for (int s = 0; s < kMelSlots; ++s) if (!assign_lanes(out, s, T[s])) return false;
+            return true;
+        };
+        // iteration counts are even (the kernel consumes weight pairs); smallest total first
+        bool ok = nnz == 0;
+        const int bmax = kMelSlots * (lmax + kGroupLanes + 1);
+        for (int B = ((nnz + kGroupLanes - 1) / kGroupLanes + 1) & ~1; !ok && B <= bmax; B += 2)
+            for (int slack = 0; !ok && slack <= 3; ++slack)
+                for (int t0 = B & ~1; !ok && 3 * t0 >= B; t0 -= 2)
+                    for (int t1 = std::min(t0, B - t0); !ok && t1 >= 0 && 2 * t1 >= B - t0; t1 -= 2) {
+                        const int T[kMelSlots] = {t0, t1, B - t0 - t1};
+                        if (try_pack(T, slack, pieces)) { ok = true; for (int s = 0; s < kMelSlots; ++s) mel_T[s] = T[s]; }
+                    }
+        allow_conflicts = true;
+        for (int B = ((nnz + kGroupLanes - 1) / kGroupLanes + 1) & ~1; !ok && B <= bmax; B += 2)
+            for (int t0 = B & ~1; !ok && 3 * t0 >= B; t0 -= 2)
+                for (int t1 = std::min(t0, B - t0); !ok && t1 >= 0 && 2 * t1 >= B - t0; t1 -= 2) {
+                    const int T[kMelSlots] = {t0, t1, B - t0 - t1};
+                    if (try_pack(T, 0, pieces)) { ok = true; for (int s = 0; s < kMelSlots; ++s) mel_T[s] = T[s]; }
+                }
+        if (!ok) { err = "mel filterbank does not fit the piece table"; return {}; }
+    }
+    int mel_iters = 0;
+    for (int s = 0; s < kMelSlots; ++s) { p.mel_T[s] = mel_T[s]; mel_iters += mel_T[s]; }
+    {
+        // weights as pairs: [iteration / 2][lane][iteration & 1]
+        std::vector<float> wt((size_t)std::max(mel_iters, 2) * kGroupLanes, 0.f);
+        std::vector<int> base(kMelSlots * kGroupLanes, 0), comb(kMaxNfilt * kMelMaxPieces, kMelSlots * kGroupLanes);
+        for (int i = 0; i < kMelSlots * kGroupLanes; ++i) base[i] = i % kGroupLanes;   // idle lanes keep to their own banks
+        int npc[kMaxNfilt] = {0}, tb[kMelSlots];
+        tb[0] = 0; for (int s = 1; s < kMelSlots; ++s) tb[s] = tb[s - 1] + mel_T[s - 1];
+        for (const Piece& pc : pieces) {
+            const int shift = runs[pc.filt].k0 + pc.off - pc.k0;
+            base[pc.slot * kGroupLanes + pc.lane] = pc.k0;
+            for (int t = 0; t < pc.len; ++t) {
+                const int it = tb[pc.slot] + shift + t;
+                wt[((size_t)(it >> 1) * kGroupLanes + pc.lane) * 2 + (it & 1)] = runs[pc.filt].w[pc.off + t];
+            }
+            comb[pc.filt * kMelMaxPieces + npc[pc.filt]++] = pc.slot * kGroupLanes + pc.lane;
         }
-        for (int v : t) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
+        align4();
+        p.o_melw = (int)blob.size();
+        blob.insert(blob.end(), wt.begin(), wt.end());
+        p.o_melb = (int)blob.size();
+        for (int v : base) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
+        align4();
+        p.o_melc = (int)blob.size();
+        for (int v : comb) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
     }
     align4();
     // DCT-II (ortho) rows premultiplied by the lifter

@@ -53,6 +53,7 @@ template <class T> DEVFN T ldg(const T* p) { return *p; }
 DEVFN float cvt_lo16(uint32_t w) { return (float)(int16_t)(w & 0xffffu); }
 DEVFN float cvt_hi16(uint32_t w) { return (float)(int16_t)(w >> 16); }
 struct uint4 { uint32_t x, y, z, w; };
+struct int4 { int x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #else
 // ---------------------------------------------------------------- sm_100a device build
