@@ -310,7 +310,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                     const float2* pp = scr + melb[s * kGroupLanes];
                     const float2* wp = melw + (tb >> 1) * kGroupLanes;
                     float2 a0 = make_float2(0.f, 0.f), a1 = a0;
-#pragma unroll 2
+#pragma unroll 4
                     for (int t = 0; t < T; t += 2) {   // T is even
                         const float2 w = wp[(t >> 1) * kGroupLanes];
                         a0 = f2fmas(pp[t], w.x, a0);
@@ -382,12 +382,15 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     const int u_hi = tile.f0 + tile.nf - 1 + N < F - 1 ? tile.f0 + tile.nf - 1 + N : F - 1;
     const int width = 3 * numcep;
     const float dscale = p.delta_scale;
+    const int nc2 = 2 * numcep;
     auto taps = [&](const float* q, int row) {   // sum_n n * (q[row + n] - q[row - n]), rows clamped to [0, F-1]
         float acc = 0.f;
         if (row >= N && row + N <= F - 1) {
-#pragma unroll
-            for (int n = 1; n <= kMaxDeltaN; ++n)
-                if (n <= N) acc = dsp_fmaf((float)n, q[n * numcep] - q[-n * numcep], acc);
+            if (N == 2) {   // the reference call sites' N (model.py:76-77 uses 3; python_speech_features' default is 2)
+                acc = dsp_fmaf(2.f, q[nc2] - q[-nc2], q[numcep] - q[-numcep]);
+            } else {
+                for (int n = 1; n <= N; ++n) acc = dsp_fmaf((float)n, q[n * numcep] - q[-n * numcep], acc);
+            }
         } else {
             for (int n = 1; n <= N; ++n) {
                 const int hi = row + n > F - 1 ? F - 1 - row : n, lo = row - n < 0 ? row : n;
@@ -396,22 +399,25 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
         }
         return acc * dscale;
     };
+    const int rstep = kMfccGroups * numcep, ostep = kMfccGroups * width;
     if (lane < numcep) {
-        for (int uu = u_lo + grp; uu <= u_hi; uu += kMfccGroups) {
-            const float* m0 = sm.mfcc + (uu - v_lo) * numcep + lane;
+        int uu = u_lo + grp;
+        const float* m0 = sm.mfcc + (uu - v_lo) * numcep + lane;
+        float* db = dbuf + grp * numcep + lane;
+        float* o = p.out + (row0 + uu) * width + lane;
+        const int t_lo = tile.f0, t_hi = tile.f0 + tile.nf;
+        for (; uu <= u_hi; uu += kMfccGroups, m0 += rstep, db += rstep, o += ostep) {
             const float d = taps(m0, uu);
-            dbuf[(uu - u_lo) * numcep + lane] = d;
-            if (uu >= tile.f0 && uu < tile.f0 + tile.nf) {
-                float* o = p.out + (row0 + uu) * width + lane;
-                o[0] = m0[0];
-                o[numcep] = d;
-            }
+            *db = d;
+            if (uu >= t_lo && uu < t_hi) { o[0] = *m0; o[numcep] = d; }
         }
     }
     simt::cta_sync();
     if (lane < numcep) {
-        for (int tt = tile.f0 + grp; tt < tile.f0 + tile.nf; tt += kMfccGroups)
-            p.out[(row0 + tt) * width + 2 * numcep + lane] = taps(dbuf + (tt - u_lo) * numcep + lane, tt);
+        int tt = tile.f0 + grp;
+        const float* d0 = dbuf + (tt - u_lo) * numcep + lane;
+        float* o = p.out + (row0 + tt) * width + nc2 + lane;
+        for (; tt < tile.f0 + tile.nf; tt += kMfccGroups, d0 += rstep, o += ostep) *o = taps(d0, tt);
     }
 }
 
