@@ -345,17 +345,165 @@ __device__ __forceinline__ void ep_stage(const int32_t* asum, const int32_t* zcr
     for (int i = lane; i < F; i += 32) { s_amp[i] = (double)asum[i] / len; s_zcr[i] = zcr[i]; }
     __syncwarp();
 }
+// ---- warp-parallel form of basic_endpoint_detection's decision (endpoint.py:34-66, 133-179, 201-220).
+// The thresholds are the reference's float64 expressions evaluated in numpy's order; everything that is order-free runs
+// across the lanes: the amplitude maximum (warp max), the sort of the <= 32 silence samples (rank sort), and the
+// comparisons of every frame against the thresholds (ballots -> bit masks in shared memory).  The state machine then
+// walks bit masks with find-first-set jumps instead of touching every frame.  All lanes execute it redundantly on the same
+// shared data (warp-uniform control flow, no broadcasts).
+constexpr int kEpMaskWords = kEpStageFrames / 32;
+struct EpWarpSmem {
+    double amp[kEpStageFrames];
+    int32_t zcr[kEpStageFrames];
+    double sil[64], sq[64];
+    unsigned ge[kEpMaskWords], gt[kEpMaskWords], lo[kEpMaskWords], zt[kEpMaskWords];
+};
+// smallest index >= i whose bit equals `one` (bits at and beyond F read as "not found"), or F
+__device__ __forceinline__ int mask_next(const unsigned* m, int i, int F, bool one) {
+    while (i < F) {
+        unsigned w = one ? m[i >> 5] : ~m[i >> 5];
+        w &= 0xffffffffu << (i & 31);
+        if (w) { const int r = (i & ~31) + __ffs((int)w) - 1; return r < F ? r : F; }
+        i = (i & ~31) + 32;
+    }
+    return F;
+}
+// largest index <= i whose bit is zero, or -1
+__device__ __forceinline__ int mask_prev_zero(const unsigned* m, int i) {
+    while (i >= 0) {
+        unsigned w = ~m[i >> 5];
+        w &= 0xffffffffu >> (31 - (i & 31));
+        if (w) return (i & ~31) + 31 - __clz((int)w);
+        i = (i & ~31) - 1;
+    }
+    return -1;
+}
+__device__ __forceinline__ double warp_max_f64(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const double o = __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), m), __shfl_xor_sync(0xffffffffu, __double2loint(v), m));
+        v = o > v ? o : v;
+    }
+    return v;
+}
+// np.mean / np.std of a[0..n) (n <= 64) held in shared memory; sq is shared scratch.  Same operation order as np_mean_std.
+__device__ __forceinline__ void warp_mean_std(const double* a, int n, double* sq, int lane, double* mean, double* std) {
+    if (n <= 0) { *mean = NAN; *std = NAN; return; }
+    const double m = np_pairwise_sum(a, n) / (double)n;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) { const double d = a[i] - m; sq[i] = d * d; }
+    __syncwarp();
+    *mean = m;
+    *std = sqrt(np_pairwise_sum(sq, n) / (double)n);
+}
+// amplitude_rule's scan (endpoint.py:156-179) over the masks ge: amp >= M_H, gt: amp > M_H, lo: amp > M_L
+__device__ __forceinline__ void amp_scan_masks(const EpWarpSmem& s, int F, double T_H, int* left, int* right) {
+    int first = -1, last = -1, i = 0;
+    while (i < F) {
+        i = mask_next(s.ge, i, F, true);
+        if (i >= F) break;
+        int j = i, k = mask_next(s.gt, i, F, false);
+        if ((double)(k - j) < T_H) {
+            i = k;
+        } else {
+            if (j > 0) { const int z = mask_prev_zero(s.lo, j); j = z > 0 ? z : 0; }   // while j > 0 and amp[j] > M_L: j -= 1
+            k = mask_next(s.lo, k, F, false);                                           // while k < F and amp[k] > M_L: k += 1
+            if (first < 0) first = j;
+            last = k;
+            i = k;
+        }
+        ++i;
+    }
+    if (first < 0) { *left = 0; *right = F; } else { *left = first; *right = last; }
+}
+__device__ __forceinline__ void ep_decide_warp(EpWarpSmem& s, int F, const EpRule& r, int lane, int32_t* out_lr) {
+    const int nwords = (F + 31) >> 5;
+    // ---- silence model: sorted(amp[:nl] + amp[-nr:])[:-2] (endpoint.py:151-153), n <= 32 here
+    const int nl = (int)(r.l_sil / r.cfg_step), nr = (int)(r.r_sil / r.cfg_step);
+    const int n_l = nl < F ? nl : F, r0 = (nr > 0 && F - nr > 0) ? F - nr : 0;
+    const int n = n_l + (F - r0);
+    const double v = lane < n ? s.amp[lane < n_l ? lane : r0 + lane - n_l] : 0.0;
+    if (lane < n) s.sq[lane] = v;
+    __syncwarp();
+    int rank = 0;
+    for (int t = 0; t < n; ++t) { const double o = s.sq[t]; rank += (o < v || (o == v && t < lane)) ? 1 : 0; }
+    __syncwarp();
+    if (lane < n) s.sil[rank] = v;
+    double mx = -1.0e300;
+    for (int i = lane; i < F; i += 32) { const double a = s.amp[i]; mx = a > mx ? a : mx; }
+    const double amax = warp_max_f64(mx);
+    __syncwarp();
+    double s_mean, s_sigma;
+    warp_mean_std(s.sil, n - 2 > 0 ? n - 2 : 0, s.sq, lane, &s_mean, &s_sigma);
+    const double T_H = r.th / r.cfg_frame;
+    const double M_L = s_mean + r.sigma * s_sigma;
+    int left = 0, right = F;
+    for (int pass = 0; pass < 2; ++pass) {
+        const double a_hi = amax * (pass == 0 ? r.mh1 : r.mh2);
+        const double M_H = (M_L > a_hi) ? M_L : a_hi;
+        __syncwarp();
+        for (int c = 0; c < nwords; ++c) {
+            const int i = 32 * c + lane;
+            const double a = i < F ? s.amp[i] : 0.0;
+            const unsigned ge = __ballot_sync(0xffffffffu, i < F && a >= M_H), gt = __ballot_sync(0xffffffffu, i < F && a > M_H);
+            const unsigned lo = __ballot_sync(0xffffffffu, i < F && a > M_L);
+            if (lane == 0) { s.ge[c] = ge; s.gt[c] = gt; s.lo[c] = lo; }
+        }
+        __syncwarp();
+        amp_scan_masks(s, F, T_H, &left, &right);
+        if (right - left >= r.min_span) break;
+    }
+    // ---- zcr_rule (endpoint.py:201-220) with l_sil = 0: threshold from the last nr frames
+    const int zr = (int)(r.zcr_r_sil / r.cfg_step);
+    const int z0 = (zr > 0 && F - zr > 0) ? F - zr : 0;
+    const int zn = F - z0;   // <= 32 here
+    __syncwarp();
+    if (lane < zn) s.sil[lane] = (double)s.zcr[z0 + lane];
+    __syncwarp();
+    double mu, sg;
+    warp_mean_std(s.sil, zn, s.sq, lane, &mu, &sg);
+    const double thres = mu + 3 * sg;
+    for (int c = 0; c < nwords; ++c) {
+        const int i = 32 * c + lane;
+        const unsigned zt = __ballot_sync(0xffffffffu, i < F && (double)s.zcr[i < F ? i : 0] > thres);
+        if (lane == 0) s.zt[c] = zt;
+    }
+    __syncwarp();
+    // while j > 0 and left - j <= max_shift and zcr[j] > thres: j -= 1   (left - j <= max_shift <=> j >= left - floor(max_shift))
+    const double max_shift = r.zcr_max_shift / r.cfg_frame;
+    const int ms = (int)floor(max_shift);
+    int j = left, k = right;
+    if (j > 0 && j < F) {
+        int stop = mask_prev_zero(s.zt, j);
+        if (stop < left - ms - 1) stop = left - ms - 1;
+        j = stop > 0 ? stop : 0;
+    }   // (left < F always: it is a frame the scan stood on, or 0)
+    if (k < F) {
+        int stop = mask_next(s.zt, k, F, false);
+        if (stop > right + ms + 1) stop = right + ms + 1;
+        k = stop < F ? stop : F;
+    }
+    int l2 = j, r2 = k;
+    if (r2 - l2 < r.min_span) { l2 = 0; r2 = F; }
+    if (lane == 0) {
+        out_lr[0] = (int32_t)((double)l2 * r.cfg_step * (double)r.rate);
+        out_lr[1] = (int32_t)((double)r2 * r.cfg_step * (double)r.rate);
+    }
+}
+
 __global__ void __launch_bounds__(32 * kEpDecideWarps) ep_decide_kernel(EpParams p) {
-    __shared__ double s_amp[kEpDecideWarps][kEpStageFrames];
-    __shared__ int32_t s_zcr[kEpDecideWarps][kEpStageFrames];
+    __shared__ EpWarpSmem s_all[kEpDecideWarps];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * kEpDecideWarps + w;
     if (u >= p.n_utt) return;
+    EpWarpSmem& s = s_all[w];
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
-    if (F <= kEpStageFrames) {
-        ep_stage(p.asum + f0, p.zcr + f0, F, (double)p.frame_len, s_amp[w], s_zcr[w], lane);
-        if (lane == 0) endpoint_decide_amp(AmpFromF64{s_amp[w]}, s_zcr[w], F, p.rule, p.lr + 2 * u);
+    const EpRule& r = p.rule;
+    const int nl = (int)(r.l_sil / r.cfg_step), nr = (int)(r.r_sil / r.cfg_step), zr = (int)(r.zcr_r_sil / r.cfg_step);
+    if (F <= kEpStageFrames && nl >= 0 && nr >= 1 && nl + nr <= 32 && zr >= 1 && zr <= 32 && r.zcr_max_shift >= 0.0 && r.cfg_frame > 0.0) {
+        ep_stage(p.asum + f0, p.zcr + f0, F, (double)p.frame_len, s.amp, s.zcr, lane);
+        ep_decide_warp(s, F, r, lane, p.lr + 2 * u);
     } else if (lane == 0) {
         endpoint_decide(p.asum + f0, p.zcr + f0, F, p.frame_len, p.rule, p.lr + 2 * u);
     }

@@ -147,3 +147,45 @@ def test_get_amplitude_variants_and_noise():
     sep = O.amplitude_rule(amp)
     assert features.get_noise(amp, sep) == O.get_noise(amp, sep)
     assert features.get_noise(amp, [(0, len(amp))]) == 1e30
+
+
+def test_warp_parallel_decision_equals_serial_rule():
+    """The device decision (rank-sorted silence model, ballot masks, find-first-set walk) against the serial replay of the
+    reference rule (dspfe_endpoint_decide_host, the same code the oracle tests pin) on adversarial frame statistics:
+    plateaus exactly at the thresholds, all-equal amplitudes, digital silence, one-frame utterances, bursts."""
+    import torch
+    import dspfe
+    from dspfe import synth
+    rng = np.random.default_rng(77)
+    xs = []
+    for u in range(600):
+        n = int(rng.integers(1, 60000))
+        kind = u % 6
+        if kind == 0:
+            x = synth.synth_utterance(7000 + u, n)
+        elif kind == 1:
+            x = (rng.standard_normal(n) * rng.uniform(1, 3000)).astype(np.int16)
+        elif kind == 2:
+            x = np.full(n, int(rng.integers(-5, 6)), dtype=np.int16)                     # every frame identical (ties everywhere)
+        elif kind == 3:
+            x = ((rng.integers(0, 2, n) * 2 - 1) * int(rng.integers(1, 20000))).astype(np.int16)   # constant |x|, random signs
+        elif kind == 4:
+            x = np.zeros(n, dtype=np.int16)
+            for _ in range(int(rng.integers(1, 6))):                                      # bursts of equal level
+                a = int(rng.integers(0, n)); b = min(n, a + int(rng.integers(1, 9000)))
+                x[a:b] = ((rng.integers(0, 2, b - a) * 2 - 1) * 4000).astype(np.int16)
+        else:
+            x = (np.sin(np.arange(n) * rng.uniform(0.01, 1.5)) * rng.uniform(10, 30000) * (np.arange(n) % 3200 < 1600)).astype(np.int16)
+        xs.append(x)
+    pcm, off = pack(xs)
+    dev = torch.device("cuda:0")
+    plan = dspfe.EndpointPlan()
+    lr, asum, zcr, fo = plan.detect(torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev), want_features=True)
+    torch.cuda.synchronize()
+    lr, asum, zcr, fo = lr.cpu().numpy(), asum.cpu().numpy(), zcr.cpu().numpy(), fo.cpu().numpy()
+    bad = []
+    for u in range(len(xs)):
+        want = dspfe.endpoint_decide_host(asum[fo[u]:fo[u + 1]], zcr[fo[u]:fo[u + 1]])
+        if tuple(int(v) for v in lr[u]) != tuple(int(v) for v in want):
+            bad.append((u, tuple(lr[u]), tuple(want)))
+    assert not bad, f"{len(bad)} of {len(xs)} decisions differ, first: {bad[:3]}"
