@@ -39,7 +39,7 @@ UTT_SAMPLES = 2 * SR
 FRAME_LEN, FRAME_STEP, NUMCEP, DELTA_N = 400, 160, 13, 2
 METRIC = "audio-sec/sec of MFCC+delta+delta-delta (fused kernel), 4096 x 2 s utterances per B200"
 UNIT = "audio-s/s"
-K1_DRAM_TRAFFIC_BYTES = 357.4e6   # ncu --set full capture of this very workload (profiles/r1_k1_mfcc_ncu.md)
+K1_DRAM_TRAFFIC_BYTES = 355.4e6   # ncu --set full capture of this very workload (profiles/r1_k1_mfcc_ncu.md)
 
 
 def peaks():
@@ -284,9 +284,9 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": K1_DRAM_TRAFFIC_BYTES, "peak_source": peak_src,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_k1_mfcc_ncu.md "
-                                       "(262.5 MB read + 95.0 MB written; the rest of the 127 MB output is still in L2 when the kernel ends)",
+                                       "(262.4 MB read + 93.1 MB written; the rest of the 127 MB output is still in L2 when the kernel ends)",
                      "note": "one step = prep kernel (2-3 % of the step) + fused kernel; algorithmic bytes = 2*S + 156*F per "
-                             "utterance; the kernel is FP32-pipe/shared-memory bound, see DESIGN.md",
+                             "utterance; the kernel is bound by shared-memory bandwidth (L1/shared 77 % busy, the FFT transposes) and the FP32 pipe, not by HBM: see DESIGN.md",
                      "alg_bytes_per_launch": alg_bytes, "launch_ms": step_ms},
         "e2e": {"value": world * audio_s / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(pcm.numel() * 2 + (U + 1) * 8),
                 "d2h_bytes_per_step": int(rows * 3 * NUMCEP * 4), "ms_per_step": e2e_s * 1e3, "timer": "host wall clock around the blocking host-buffer call, max over ranks",
