@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(32 * kPitchWarps, 6) pitch_clip_kernel(const _
     const int w = threadIdx.x >> 5;
     const int64_t g0 = 2 * ((int64_t)blockIdx.x * kPitchWarps + w);
     if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
-    pitch_clip_pair(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
+    if (p.frame_len <= 320) pitch_clip_pair<10>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);   // e.g. the 300-sample frames of model.py:92
+    else pitch_clip_pair<16>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
 }
 
 // K4a-2 / K5a-2: the transforms, a frame pair per warp
@@ -191,6 +192,7 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, track_smem(kCepLen));
     if (e != cudaSuccess) { cudaFree(pl->d_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
     b.tab = pl->d_tab;
@@ -262,6 +264,7 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     pitch_clip_kernel<<<fgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_clip_kernel", st);
     if (p.mode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
+    else if (acr_short_frames(p.frame_len, p.row_len)) pitch_frame_kernel<2><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     else pitch_frame_kernel<1><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_frame_kernel", st);
     if (d_pitch || d_lag || d_feat) {

@@ -55,6 +55,8 @@ constexpr int kClipCtaSmem = kMaxDsOut * 4 + kPitchWarps * kClipWarpSmemBytes;
 constexpr int kTrackThreads = 256;
 constexpr int kTrackMaxFrames = 1024;   // utterances up to this many frames keep their lag / Hz track in shared memory
 constexpr int kTrackChunk = 32;     // frames smoothed per pass of K4b/K5b (16 for rows wider than 256 columns)
+// autocorrelation rows of lags kMinLag .. kMinLag + row_len - 1: no wrap-around in a 512-point circular correlation
+DSP_HD bool acr_short_frames(int frame_len, int row_len) { return frame_len + kMinLag + row_len - 1 <= 512; }
 DSP_HD int track_chunk(int row_len) { return row_len <= 256 ? kTrackChunk : kTrackChunk / 2; }
 
 struct PitchParams {
@@ -194,11 +196,13 @@ DSP_HD bool pitch_feature_tail(const double* pitch, const double* amp, int F, do
 // ---------------------------------------------------------------------------------------------------------
 // medians of the non-negative entries of two frames at once (np.median(frame[frame >= 0]), pitch.py:146): exact k-th
 // order statistics by bitwise selection on the float bit patterns; NaN when a frame has no non-negative sample.
-DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], int L, int lane) {
-    unsigned ka[16], kb[16];
+// NT = samples per lane (32 * NT >= L): 16 for 512-sample frames, 10 for frames of up to 320 samples.
+template <int NT>
+DEVFN float2 warp_median_nonneg2(const float (&xa)[NT], const float (&xb)[NT], int L, int lane) {
+    unsigned ka[NT], kb[NT];
     int cnt = 0;
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
+    for (int t = 0; t < NT; ++t) {
         const bool in = (lane + 32 * t) < L;
         const bool na = in && xa[t] >= 0.f, nb = in && xb[t] >= 0.f;
         ka[t] = na ? ((unsigned)__float_as_int_compat(xa[t]) & 0x7fffffffu) : 0xffffffffu;   // -0.0 counts as 0
@@ -217,12 +221,13 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], i
         // and never count).  Valid while every real key is below the half inf/NaN patterns (|x| < 2^121).
         int mx = -1;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) { mx = max(mx, (int)ka[t]); mx = max(mx, (int)kb[t]); }   // excluded keys are -1 as signed
+        for (int t = 0; t < NT; ++t) { mx = max(mx, (int)ka[t]); mx = max(mx, (int)kb[t]); }   // excluded keys are -1 as signed
         mx = __reduce_max_sync(0xffffffffu, mx);
         if (mx < 0x7C000000) {
-            __half2 pa[8], pb[8];
+            static_assert(NT % 2 == 0, "keys are packed in pairs");
+            __half2 pa[NT / 2], pb[NT / 2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NT / 2; ++j) {
                 const unsigned wa = __byte_perm(ka[2 * j], ka[2 * j + 1], 0x7632), wb = __byte_perm(kb[2 * j], kb[2 * j + 1], 0x7632);
                 pa[j] = *reinterpret_cast<const __half2*>(&wa); pb[j] = *reinterpret_cast<const __half2*>(&wb);
             }
@@ -231,10 +236,11 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], i
                 const __half2 ha = *reinterpret_cast<const __half2*>(&wa), hb = *reinterpret_cast<const __half2*>(&wb);
                 __half2 a0 = __hle2(pa[0], ha), a1 = __hle2(pa[1], ha), b0 = __hle2(pb[0], hb), b1 = __hle2(pb[1], hb);
 #pragma unroll
-                for (int j = 2; j < 8; j += 2) {
+                for (int j = 2; j + 1 < NT / 2; j += 2) {
                     a0 = __hadd2(a0, __hle2(pa[j], ha)); a1 = __hadd2(a1, __hle2(pa[j + 1], ha));
                     b0 = __hadd2(b0, __hle2(pb[j], hb)); b1 = __hadd2(b1, __hle2(pb[j + 1], hb));
                 }
+                if ((NT / 2) & 1) { a0 = __hadd2(a0, __hle2(pa[NT / 2 - 1], ha)); b0 = __hadd2(b0, __hle2(pb[NT / 2 - 1], hb)); }
                 a0 = __hadd2(a0, a1); b0 = __hadd2(b0, b1);
                 const int ca = __half2int_rn(__hadd(__low2half(a0), __high2half(a0)));
                 const int cb = __half2int_rn(__hadd(__low2half(b0), __high2half(b0)));
@@ -250,22 +256,22 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], i
             const int below = count_le(Ha ? Ha - 1 : 0, Hb ? Hb - 1 : 0);
             int qa = ra - (Ha ? (below & 0xffff) : 0), qb = rb - (Hb ? (below >> 16) : 0);
             // the bucket rarely holds more than a few distinct values: peel them off in increasing order
-            unsigned ma_[16], mb_[16];
+            unsigned ma_[NT], mb_[NT];
 #pragma unroll
-            for (int t = 0; t < 16; ++t) { ma_[t] = (ka[t] >> 16) == Ha ? ka[t] : 0xffffffffu; mb_[t] = (kb[t] >> 16) == Hb ? kb[t] : 0xffffffffu; }
+            for (int t = 0; t < NT; ++t) { ma_[t] = (ka[t] >> 16) == Ha ? ka[t] : 0xffffffffu; mb_[t] = (kb[t] >> 16) == Hb ? kb[t] : 0xffffffffu; }
             bool fa = ma == 0, fb = mb == 0;                    // nothing to find in an empty frame
             long long pva = -1, pvb = -1;
             while (!(fa && fb)) {
                 unsigned ca_ = 0xffffffffu, cb_ = 0xffffffffu;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
+                for (int t = 0; t < NT; ++t) {
                     if ((long long)ma_[t] > pva && ma_[t] < ca_) ca_ = ma_[t];
                     if ((long long)mb_[t] > pvb && mb_[t] < cb_) cb_ = mb_[t];
                 }
                 ca_ = __reduce_min_sync(0xffffffffu, ca_); cb_ = __reduce_min_sync(0xffffffffu, cb_);
                 int n = 0;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) n += (ma_[t] == ca_ ? 1 : 0) + (mb_[t] == cb_ ? 0x10000 : 0);
+                for (int t = 0; t < NT; ++t) n += (ma_[t] == ca_ ? 1 : 0) + (mb_[t] == cb_ ? 0x10000 : 0);
                 n = __reduce_add_sync(0xffffffffu, n);
                 if (!fa) { if (qa < (n & 0xffff) || ca_ == 0xffffffffu) { Ka = ca_; fa = true; } else { qa -= n & 0xffff; pva = ca_; } }
                 if (!fb) { if (qb < (n >> 16) || cb_ == 0xffffffffu) { Kb = cb_; fb = true; } else { qb -= n >> 16; pvb = cb_; } }
@@ -276,22 +282,20 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], i
 #endif
     for (int b = done ? -1 : 30; b >= 0; --b) {
         const unsigned ta = Ka | ((1u << b) - 1u), tb = Kb | ((1u << b) - 1u);
-        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;                   // independent partial counts: no 32-deep add chain
+        int c0 = 0, c1 = 0;                                   // independent partial counts: no 32-deep add chain
 #pragma unroll
-        for (int t = 0; t < 16; t += 4) {
+        for (int t = 0; t < NT; t += 2) {
             c0 += (ka[t] <= ta ? 1 : 0) + (kb[t] <= tb ? 0x10000 : 0);
             c1 += (ka[t + 1] <= ta ? 1 : 0) + (kb[t + 1] <= tb ? 0x10000 : 0);
-            c2 += (ka[t + 2] <= ta ? 1 : 0) + (kb[t + 2] <= tb ? 0x10000 : 0);
-            c3 += (ka[t + 3] <= ta ? 1 : 0) + (kb[t + 3] <= tb ? 0x10000 : 0);
         }
-        const int c = warp_redux_add((c0 + c1) + (c2 + c3));
+        const int c = warp_redux_add(c0 + c1);
         if ((c & 0xffff) < ra + 1) Ka |= 1u << b;
         if ((c >> 16) < rb + 1) Kb |= 1u << b;
     }
     // even count: the upper middle element is the same key when enough keys are <= K, else the next larger key
     int c = 0; unsigned na = 0xffffffffu, nb = 0xffffffffu;
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
+    for (int t = 0; t < NT; ++t) {
         c += (ka[t] <= Ka ? 1 : 0) + (kb[t] <= Kb ? 0x10000 : 0);
         if (ka[t] > Ka && ka[t] < na) na = ka[t];
         if (kb[t] > Kb && kb[t] < nb) nb = kb[t];
@@ -305,7 +309,7 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[16], const float (&xb)[16], i
     return med;
 }
 // single-frame form (center_clip tap)
-DEVFN float warp_median_nonneg(const float (&x)[16], int L, int lane) { return warp_median_nonneg2(x, x, L, lane).x; }
+DEVFN float warp_median_nonneg(const float (&x)[16], int L, int lane) { return warp_median_nonneg2<16>(x, x, L, lane).x; }
 
 // center_clip(frame, False) (pitch.py:145-155) on one value
 DEVFN float clip_value(float v, float med) {
@@ -398,9 +402,9 @@ DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds
     return v;
 }
 template <bool F32>
-DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb) {
+DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb, int nt) {
 #pragma unroll 1
-    for (int t0 = 0; t0 < 16; t0 += 4) {
+    for (int t0 = 0; t0 < nt; t0 += 4) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float va = frame_sample<F32>(p, ca, ds_idx, t0 + j), vb = frame_sample<F32>(p, cb, ds_idx, t0 + j);
@@ -414,6 +418,7 @@ DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, c
 // p.frame_amp.  Its own kernel: it needs few registers and little shared memory, so three times as many warps as the
 // transform kernel can hide its load and bisection latencies.
 // wsm: per-warp shared memory = stage[2][kStageBytes] | xs[512] float2.
+template <int NT>
 DEVFN void pitch_clip_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const int32_t* ds_idx) {
     const int lane = simt::tid() & 31;
     unsigned char* stage = wsm;
@@ -427,11 +432,12 @@ DEVFN void pitch_clip_pair(const PitchParams& p, int64_t g0, int64_t total, unsi
     FrameCursor ca = frame_cursor(p, g0, ua, lane, true, stage);
     FrameCursor cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB, stage + kStageBytes);
     float fa = 0.f, fb = 0.f;
-    if (p.in_f32) gather_pair<true>(p, ca, cb, ds_idx, xs, lane, fa, fb);
-    else gather_pair<false>(p, ca, cb, ds_idx, xs, lane, fa, fb);
-    float xa[16], xb[16];
+    constexpr int kGatherRows = (NT + 3) & ~3;   // rows t >= NT lie past the frame: the cursor returns zeros there
+    if (p.in_f32) gather_pair<true>(p, ca, cb, ds_idx, xs, lane, fa, fb, kGatherRows);
+    else gather_pair<false>(p, ca, cb, ds_idx, xs, lane, fa, fb, kGatherRows);
+    float xa[NT], xb[NT];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) { const float2 v = xs[32 * t + lane]; xa[t] = v.x; xb[t] = v.y; }
+    for (int t = 0; t < NT; ++t) { const float2 v = xs[32 * t + lane]; xa[t] = v.x; xb[t] = v.y; }
     double sa = (double)fa, sb = (double)fb;
     if (p.frame_amp) {
 #pragma unroll
@@ -440,14 +446,16 @@ DEVFN void pitch_clip_pair(const PitchParams& p, int64_t g0, int64_t total, unsi
     }
     // ---- centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
     float2 med = make_float2(0.f, 0.f);
-    if (p.do_clip) med = warp_median_nonneg2(xa, xb, L, lane);
+    if (p.do_clip) med = warp_median_nonneg2<NT>(xa, xb, L, lane);
     float2* dst = p.clip + (g0 >> 1) * 512;
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-        const bool in = lane + 32 * t < L;
-        const float va = p.do_clip ? clip_value(xa[t], med.x) : xa[t];
-        const float vb = p.do_clip ? clip_value(xb[t], med.y) : xb[t];
-        dst[32 * t + lane] = make_float2(in ? va : 0.f, in ? vb : 0.f);
+        float2 o = make_float2(0.f, 0.f);
+        if (t < NT && lane + 32 * t < L) {
+            o.x = p.do_clip ? clip_value(xa[t < NT ? t : 0], med.x) : xa[t < NT ? t : 0];
+            o.y = p.do_clip ? clip_value(xb[t < NT ? t : 0], med.y) : xb[t < NT ? t : 0];
+        }
+        dst[32 * t + lane] = o;
     }
 }
 
@@ -458,7 +466,9 @@ DEVFN void pitch_clip_pair(const PitchParams& p, int64_t g0, int64_t total, unsi
 // and for the cepstrum (pitch.py:135-143) the first inverse transform folds away:
 //     FFT512(y) = (Xe He + FFT512(W1024^-n IFFT512(Xo Ho))) / 2.
 // The transforms run as a rolled loop over stages (one copy of the routine in the instruction stream: the fully
-// inlined chain thrashed the instruction cache).  MODE 0 = cepstrum (5 transforms), 1 = autocorrelation (8).
+// inlined chain thrashed the instruction cache).  MODE 0 = cepstrum (5 transforms), 1 = autocorrelation (8), 2 = autocorrelation
+// of frames short enough (frame_len + 199 <= 512, e.g. the 300-sample frames of model.py:92) that the 512-point circular
+// correlation has no wrap-around on the lags 20..199: one transform pair instead of the even / odd split (6 transforms).
 // wsm: per-warp shared memory = scr[kWarpScr] float2 | park[512] float4.
 template <int MODE>
 DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
@@ -475,7 +485,7 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);
     const float inv1024 = 1.0f / 1024.0f;
-    constexpr int kStages = MODE == 0 ? 5 : 8;
+    constexpr int kStages = MODE == 0 ? 5 : (MODE == 1 ? 8 : 6);
     // cepstrum:         0 F(x)        -> park Xe He / 2        autocorrelation: 0 F(x)       -> Xe He
     //                   1 F(x W^n)    -> Xo Ho                                  1 inverse    -> park
     //                   2 inverse     -> W^-n d / 1024                          2 F(x W^n)   -> Xo Ho
@@ -486,7 +496,7 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
     for (int st = 0; st < kStages; ++st) {
         const bool inv = MODE == 0 ? (st == 2 || st == 4) : (st & 1);
         const bool load = MODE == 0 ? st <= 1 : !(st & 1);
-        const bool loadmod = MODE == 0 ? st == 1 : (st == 2 || st == 6);
+        const bool loadmod = MODE == 0 ? st == 1 : (st == 2 || (MODE == 1 && st == 6));
         if (load) {                                          // a real sequence from xs, optionally times W1024^n
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
@@ -554,10 +564,23 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
                     const bool in = 32 * t + lane < L;
                     xs[32 * t + lane] = make_float2(in ? dsp_fast_sqrtf(s2.x) * inv1024 : 0.f, in ? dsp_fast_sqrtf(s2.y) * inv1024 : 0.f);
                 }
+            } else if (MODE == 2 && st == 5) {               // short frames: r[n] = IFFT512(|V|^2)[n] / 512, unbiased normalisation, rows
+                const float inv512 = 1.0f / 512.0f;
+                float* rowa = p.rows + g0 * p.row_len;
+                float* rowb = rowa + p.row_len;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    const int n = 32 * t + lane, j = n - kMinLag;
+                    if (j >= 0 && j < p.row_len) {
+                        const float inv_n = (n < L) ? 1.0f / (float)(L - n) : NAN;
+                        rowa[j] = x[t].re.x * inv512 * inv_n;
+                        if (hasB) rowb[j] = x[t].re.y * inv512 * inv_n;
+                    }
+                }
             } else if (st == 4 || st == 6) {                 // power spectrum
 #pragma unroll
                 for (int t = 0; t < 16; ++t) { x[t].re = f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re)); x[t].im = zero2; }
-            } else if (st == 5) {                            // real parts of the even-bin half, lags < 224
+            } else if (MODE == 1 && st == 5) {               // real parts of the even-bin half, lags < 224
                 float2* ge = reinterpret_cast<float2*>(park);
 #pragma unroll
                 for (int t = 0; t < 7; ++t) ge[32 * t + lane] = x[t].re;

@@ -22,6 +22,7 @@ void frame_body(void* a) {
     // the device kernel stages the twiddles and the decimator pattern in shared memory; the emulator reads them in place
     unsigned char* wsm = A->smem->data() + w * kWarpSmemBytes;
     if (A->p.mode == 0) pitch_fft_pair<0>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
+    else if (acr_short_frames(A->p.frame_len, A->p.row_len)) pitch_fft_pair<2>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
     else pitch_fft_pair<1>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
 }
 void clip_body(void* a) {
@@ -29,7 +30,8 @@ void clip_body(void* a) {
     const int w = simt::tid() >> 5;
     const int64_t g0 = 2 * ((int64_t)simt::bid() * kPitchWarps + w);
     if (g0 >= A->total_frames) return;
-    pitch_clip_pair(A->p, g0, A->total_frames, A->smem->data() + w * kClipWarpSmemBytes, A->p.ds_idx);
+    if (A->p.frame_len <= 320) pitch_clip_pair<10>(A->p, g0, A->total_frames, A->smem->data() + w * kClipWarpSmemBytes, A->p.ds_idx);   // e.g. the 300-sample frames of model.py:92
+    else pitch_clip_pair<16>(A->p, g0, A->total_frames, A->smem->data() + w * kClipWarpSmemBytes, A->p.ds_idx);
 }
 void track_body(void* a) {
     Args* A = (Args*)a;
