@@ -509,42 +509,69 @@ __global__ void __launch_bounds__(32 * kEpDecideWarps) ep_decide_kernel(EpParams
     }
 }
 
-// Warp-cooperative gate: the frame is staged as int32 in shared memory, every lane takes the lags n0 + lane + 32 m.
+// Warp-cooperative gate (acr_rule, endpoint.py:142-144): the frame is staged in shared memory as float64 (int16 samples,
+// their products and the lag sums are exact in float64, as in the reference) with a zero tail.  A lane owns chunks of
+// kGateChunk CONSECUTIVE lags: for a block of eight sample positions it loads eight shared values x[i..i+7] (the same for all
+// lanes) and slides a register window over x[i+n..], so every shared-memory load feeds kGateChunk fused multiply-adds
+// (the first version did two loads per product and was bound by the load pipe).  Chunk c goes to lane c mod 32.
 // All lanes of the warp execute the rule in lock step on identical data, so the gate is called convergently.
 constexpr int kEpGateMaxLen = 1536;
+constexpr int kGateChunk = 9;
+constexpr int kGatePad = 32;
 struct GateWarp {
-    const int16_t* x; long long S; int step, len, n0, n1; int* sx;   // utterance samples, its length, framing, lag range, staging
+    const int16_t* x; long long S; int step, len, n0, n1; double* sx;   // utterance samples, its length, framing, lag range, staging
     __device__ bool operator()(int j) const {
         const int lane = threadIdx.x & 31;
         const long long b = (long long)j * step;
         __syncwarp();
-        for (int i = lane; i < len; i += 32) sx[i] = (b + i < S) ? (int)x[b + i] : 0;
+        for (int i = lane; i < len + kGatePad; i += 32) sx[i] = (i < len && b + i < S) ? (double)x[b + i] : 0.0;
         __syncwarp();
-        long long s0 = 0;
-        for (int i = lane; i < len; i += 32) s0 += (long long)sx[i] * sx[i];
-        double best = -1.0e300; 
-        for (int n = n0 + lane; n < n1 && n < len; n += 32) {
-            long long sn = 0;
-            for (int i = 0; i + n < len; ++i) sn += (long long)sx[i] * sx[i + n];
-            const double a = (double)sn / (double)(len - n);
-            best = a > best ? a : best;
+        double s0 = 0.0;
+        for (int i = lane; i < len; i += 32) s0 = fma(sx[i], sx[i], s0);
+        double best = -1.0e300;
+        const int nl = (n1 < len ? n1 : len) - n0;           // lags n0 .. n0 + nl - 1
+        for (int c = lane; c * kGateChunk < nl; c += 32) {
+            const int nb = n0 + c * kGateChunk;              // first lag of the chunk: it has the most terms
+            double acc[kGateChunk], w[kGateChunk + 7];
+#pragma unroll
+            for (int m = 0; m < kGateChunk; ++m) acc[m] = 0.0;
+#pragma unroll
+            for (int m = 0; m < kGateChunk - 1; ++m) w[m] = sx[nb + m];
+            for (int i = 0; i < len - nb; i += 8) {
+                // window w[u + m] = x[i + u + nb + m]; terms past the frame multiply the zero tail
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[kGateChunk - 1 + u] = sx[i + nb + kGateChunk - 1 + u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double a = sx[i + u];
+#pragma unroll
+                    for (int m = 0; m < kGateChunk; ++m) acc[m] = fma(a, w[u + m], acc[m]);
+                }
+#pragma unroll
+                for (int m = 0; m < kGateChunk - 1; ++m) w[m] = w[m + 8];
+            }
+#pragma unroll
+            for (int m = 0; m < kGateChunk; ++m) {
+                const int n = nb + m;
+                if (n < n0 + nl) { const double a = acc[m] / (double)(len - n); best = a > best ? a : best; }
+            }
         }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+            s0 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(s0), m), __shfl_xor_sync(0xffffffffu, __double2loint(s0), m));
             const double o = __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(best), m), __shfl_xor_sync(0xffffffffu, __double2loint(best), m));
             best = o > best ? o : best;
         }
-        if (n0 >= n1 || n0 >= len) return false;
-        return acr_gate_decide(best, s0, len);
+        if (nl <= 0) return false;
+        return best / (s0 / (double)len) > 0.55;   // acr_gate_decide on float64 sums (0 / 0 = NaN compares false, as in the reference)
     }
 };
 
-constexpr int kEpRobustWarps = 2;
+constexpr int kEpRobustWarps = 1;
 __global__ void __launch_bounds__(32 * kEpRobustWarps) ep_decide_robust_kernel(EpParams p) {
     __shared__ double s_amp[kEpRobustWarps][kEpStageFrames];
     __shared__ int32_t s_zcr[kEpRobustWarps][kEpStageFrames];
-    __shared__ int s_x[kEpRobustWarps][kEpGateMaxLen];
+    __shared__ double s_x[kEpRobustWarps][kEpGateMaxLen + kGatePad];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * kEpRobustWarps + w;
     if (u >= p.n_utt) return;
