@@ -100,3 +100,24 @@ def test_long_frame_kernel_nfft1536():
     xf = (x / np.std(x)).astype(np.float32)          # model.py:62-63 feeds scaled float audio
     out, fo = emu.mfcc_long(xf, [0, len(xf)], frame_len=1323, frame_step=441, window=np.hamming(1323), samplerate=44100, preemph=0.0)
     assert_mfcc_close(out, ref39(xf.astype(np.float64), 44100, 2, preemph=0), what="44.1k float")
+
+
+def test_mel_piece_tables_random_filterbanks():
+    """The mel filterbank runs as balanced, bank-conflict-free pieces built on the host (csrc/mfcc_tables.h: greedy cut
+    + bipartite lane matching).  Random bank shapes -- few / many filters, narrow bands, bands ending below Nyquist, other
+    sample rates -- against the oracle's dense filterbank product (base.py:18-32)."""
+    rng = np.random.default_rng(2024)
+    x = synth.synth_utterance(1234, 4000)
+    cases = [dict(nfilt=1, numcep=1), dict(nfilt=2, numcep=2), dict(nfilt=40, numcep=13, highfreq=1000.0),
+             dict(nfilt=40, numcep=16, lowfreq=20.0), dict(nfilt=7, numcep=5, lowfreq=3000.0, highfreq=3300.0)]
+    for _ in range(5):
+        nf = int(rng.integers(3, 41))
+        lo = float(rng.uniform(0, 3000)); hi = float(rng.uniform(lo + 200, 8000))
+        cases.append(dict(nfilt=nf, numcep=int(rng.integers(1, min(nf, 16) + 1)), lowfreq=lo, highfreq=hi))
+    for kw in cases:
+        try:
+            ref = O.mfcc(x, 16000, nfilt=kw["nfilt"], numcep=kw["numcep"], lowfreq=kw.get("lowfreq", 0), highfreq=kw.get("highfreq"))
+        except Exception:
+            continue      # the reference itself rejects the bank
+        out, _ = emu.mfcc_delta(x, [0, len(x)], **kw)
+        assert_mfcc_close(out[:, :kw["numcep"]], ref, what=str(kw))
