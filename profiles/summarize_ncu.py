@@ -1,5 +1,5 @@
 """Markdown summary of an `ncu --set full` report: per captured launch, the metrics DESIGN.md / bench.py quote.
-usage: python profiles/summarize_ncu.py gpurun_out/X.ncu-rep > profiles/rN_name.md"""
+usage: python profiles/summarize_ncu.py gpurun_out/X.ncu-rep|X_raw.csv > profiles/rN_name.md"""
 import csv
 import io
 import subprocess
@@ -35,7 +35,10 @@ KEYS = [
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # a raw page exported on the GPU box (`ncu -i X.ncu-rep --page raw --csv`)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
