@@ -30,6 +30,7 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only (NCCL prints its version banner there otherwise)
 
 import numpy as np  # noqa: E402
 
