@@ -52,21 +52,25 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------- CPU legs (oracle port)
-def _oracle_batch(xs):
+_CPU_XS = None      # the CPU legs' utterances: set before the pool forks, so the workers inherit them (no pickling in the timed region)
+
+
+def _oracle_batch(idx):
     from oracle import ref_features as O
-    for x in xs:
-        O.mfcc_delta39(x, DELTA_N)
-    return len(xs)
+    for i in idx:
+        O.mfcc_delta39(_CPU_XS[i % len(_CPU_XS)], DELTA_N)
+    return len(idx)
 
 
 def cpu_throughput(n_utt, cores):
     """Times the oracle's mfcc+delta+delta on n_utt synthetic 2 s utterances with `cores` worker processes.
-    Synthesis happens before the clock starts."""
+    Synthesis happens before the clock starts and the samples are already in every worker's memory (fork)."""
+    global _CPU_XS
     import multiprocessing as mp
     from dspfe import synth
-    xs = [synth.synth_utterance(7000 + i, UTT_SAMPLES) for i in range(min(n_utt, 64))]
-    xs = [xs[i % len(xs)] for i in range(n_utt)]
-    chunks = [xs[i::cores] for i in range(cores)]
+    if _CPU_XS is None:
+        _CPU_XS = [synth.synth_utterance(7000 + i, UTT_SAMPLES) for i in range(64)]
+    chunks = [list(range(i, n_utt, cores)) for i in range(cores)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         pool.map(_oracle_batch, [c[:2] for c in chunks])          # warm-up: imports, caches
@@ -81,8 +85,8 @@ def run_reference(args, rank):
         return
     cores = len(os.sched_getaffinity(0))
     # calibrate a bounded sample: about 2 s of wall time per step on this host
-    v1, _ = cpu_throughput(4 * cores, cores)
-    n = int(max(4 * cores, min(4096, (v1 * 2.0) / (UTT_SAMPLES / SR))))
+    v1, _ = cpu_throughput(16 * cores, cores)
+    n = int(max(16 * cores, min(4096, (v1 * 2.0) / (UTT_SAMPLES / SR))))
     n -= n % cores
     vals = []
     for i in range(args.warmup + args.steps):
