@@ -30,7 +30,17 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 os.environ.setdefault("OMP_NUM_THREADS", "1")
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only (NCCL prints its version banner there otherwise)
+
+# stdout carries the one JSON line and nothing else: everything that writes to file descriptor 1 from here on (NCCL prints its
+# version banner there) lands on stderr; emit() writes the line to the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
 
 import numpy as np  # noqa: E402
 
@@ -96,7 +106,7 @@ def run_reference(args, rank):
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3
     sample = f"{n} of the 4096 synthetic 2 s utterances per step, oracle.mfcc_delta39 in {cores} processes"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -301,7 +311,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -367,7 +377,7 @@ def run_frontend(args, rank, world, local_rank):
         rows = int(fo[-1]); pf = int(bufs["cep"]["frame_off"][-1]) + int(bufs["acr"]["frame_off"][-1])
         alg = 2.0 * float(lengths.sum()) + 156.0 * rows + 8.0 * pf + 48.0 * n_utt     # this rank's bytes
         peak, peak_src = peaks()
-        print(json.dumps({
+        emit(({
             "metric": "audio-sec/sec of MFCC+delta+pitch+endpoint (full front-end), ragged 0.5-5 s utterances", "value": audio_s / (ms * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
