@@ -203,11 +203,13 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[NT], const float (&xb)[NT], i
     int cnt = 0;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-        const bool in = (lane + 32 * t) < L;
-        const bool na = in && xa[t] >= 0.f, nb = in && xb[t] >= 0.f;
-        ka[t] = na ? ((unsigned)__float_as_int_compat(xa[t]) & 0x7fffffffu) : 0xffffffffu;   // -0.0 counts as 0
-        kb[t] = nb ? ((unsigned)__float_as_int_compat(xb[t]) & 0x7fffffffu) : 0xffffffffu;
-        cnt += (na ? 1 : 0) + (nb ? 0x10000 : 0);
+        // branch-free: a sample counts when it lies inside the frame and is >= 0 (-0.0 counts as 0, a NaN does not)
+        const float va = xa[t], vb = xb[t];
+        const int in = (lane + 32 * t) < L ? 1 : 0;
+        const int na = in & (va >= 0.f ? 1 : 0), nb = in & (vb >= 0.f ? 1 : 0);
+        ka[t] = na ? ((unsigned)__float_as_int_compat(va) & 0x7fffffffu) : 0xffffffffu;
+        kb[t] = nb ? ((unsigned)__float_as_int_compat(vb) & 0x7fffffffu) : 0xffffffffu;
+        cnt += na + (nb << 16);
     }
     cnt = warp_redux_add(cnt);
     const int ma = cnt & 0xffff, mb = cnt >> 16;
