@@ -200,18 +200,19 @@ DSP_HD bool pitch_feature_tail(const double* pitch, const double* amp, int F, do
 template <int NT>
 DEVFN float2 warp_median_nonneg2(const float (&xa)[NT], const float (&xb)[NT], int L, int lane) {
     unsigned ka[NT], kb[NT];
-    int cnt = 0;
+    int cnt = 0, cntb = 0;
+    const bool full = L >= 32 * NT;   // uniform: every lane's samples lie inside the frame
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
         // branch-free: a sample counts when it lies inside the frame and is >= 0 (-0.0 counts as 0, a NaN does not)
         const float va = xa[t], vb = xb[t];
-        const int in = (lane + 32 * t) < L ? 1 : 0;
-        const int na = in & (va >= 0.f ? 1 : 0), nb = in & (vb >= 0.f ? 1 : 0);
+        const bool in = full || (lane + 32 * t) < L;
+        const bool na = in & (va >= 0.f), nb = in & (vb >= 0.f);
         ka[t] = na ? ((unsigned)__float_as_int_compat(va) & 0x7fffffffu) : 0xffffffffu;
         kb[t] = nb ? ((unsigned)__float_as_int_compat(vb) & 0x7fffffffu) : 0xffffffffu;
-        cnt += na + (nb << 16);
+        cnt += na; cntb += nb;
     }
-    cnt = warp_redux_add(cnt);
+    cnt = warp_redux_add(cnt + (cntb << 16));
     const int ma = cnt & 0xffff, mb = cnt >> 16;
     const int ra = (ma - 1) >> 1, rb = (mb - 1) >> 1;          // rank of the lower middle element
     unsigned Ka = 0, Kb = 0;
@@ -315,9 +316,15 @@ DEVFN float warp_median_nonneg(const float (&x)[16], int L, int lane) { return w
 
 // center_clip(frame, False) (pitch.py:145-155) on one value
 DEVFN float clip_value(float v, float med) {
+    // v > med -> v - med;  v < -med -> v + med;  else 0  ==  v - clamp(v, -med, med) for finite v (v - v = +0; a NaN median --
+    // a frame without non-negative samples -- leaves the clamp at v, i.e. 0, as both reference comparisons are false)
+#ifdef DSPFE_EMU
     if (v > med) return v - med;
     if (v < -med) return v + med;
     return 0.f;
+#else
+    return v - fmaxf(-med, fminf(v, med));
+#endif
 }
 
 // frame g -> utterance index: last u with frame_off[u] <= g.  Warp-cooperative 32-ary search: three dependent loads
