@@ -388,7 +388,7 @@ DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane,
 }
 // one sample: pre-emphasised over the whole utterance (preprocess.py:11-19), zero past the decimated length
 // (sigproc.py:84-87); then the cursor moves on by 32 decimated samples
-template <bool F32>
+template <bool F32, bool PRE>
 DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds_idx, int t) {
     float v = 0.f;
     if (t < c.nvalid) {
@@ -397,30 +397,35 @@ DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds
         float cur, prev = 0.f;
         if (F32) {
             const float* q = reinterpret_cast<const float*>(c.src) + s;
-            cur = q[0]; if (s > c.lim) prev = q[-1];
+            cur = q[0]; if (PRE && s > c.lim) prev = q[-1];
         } else {
             const int16_t* q = reinterpret_cast<const int16_t*>(c.src) + s;
-            cur = cvt_i16(q[0]); if (s > c.lim) prev = cvt_i16(q[-1]);
+            cur = cvt_i16(q[0]); if (PRE && s > c.lim) prev = cvt_i16(q[-1]);
         }
         // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one;
-        // pre_hi = pre_lo = 0 leaves the sample as it is
-        v = dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur));
+        // PRE = false (pre_hi = pre_lo = 0) leaves the sample as it is and skips the load of its predecessor
+        v = PRE ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
     }
     c.a += p.ds_q32; c.b += p.ds_r32;
     if (c.b >= p.ds_out) { c.b -= p.ds_out; ++c.a; }
     return v;
 }
-template <bool F32>
-DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb, int nt) {
+template <bool F32, bool PRE>
+DEVFN void gather_pair_impl(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb, int nt) {
 #pragma unroll 1
     for (int t0 = 0; t0 < nt; t0 += 4) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float va = frame_sample<F32>(p, ca, ds_idx, t0 + j), vb = frame_sample<F32>(p, cb, ds_idx, t0 + j);
+            const float va = frame_sample<F32, PRE>(p, ca, ds_idx, t0 + j), vb = frame_sample<F32, PRE>(p, cb, ds_idx, t0 + j);
             xs[32 * (t0 + j) + lane] = make_float2(va, vb);
             fa += fabsf(va); fb += fabsf(vb);
         }
     }
+}
+template <bool F32>
+DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb, int nt) {
+    if (p.pre_hi != 0.f || p.pre_lo != 0.f) gather_pair_impl<F32, true>(p, ca, cb, ds_idx, xs, lane, fa, fb, nt);
+    else gather_pair_impl<F32, false>(p, ca, cb, ds_idx, xs, lane, fa, fb, nt);
 }
 
 // K4a-1: gather + median + centre clip of a frame pair -> p.clip[pair] (512 float2, frame A in .x, frame B in .y) and
