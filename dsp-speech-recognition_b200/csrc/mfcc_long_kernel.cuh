@@ -81,6 +81,36 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     }
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);
+    float2 esum = zero2;
+    const float sc = 1.0f / (float)kLongNfft;
+    if (p.frame_len <= 512) {
+        // Frames that fit 512 samples (30 ms at 16 kHz = 480): decimation in FREQUENCY.  X[3q + r] = FFT512(x[n] W1536^{n r})[q],
+        // and for real x the bins 3q + 2 mirror the bins 3q' + 1 (X[1536 - k] = conj X[k], k = 3q'+1 -> 3(511 - q') + 2), so
+        // two transforms in natural order give every power bin straight from the registers: r = 0 -> bins 3q (q <= 256),
+        // r = 1 -> bins 3q + 1 (q <= 255) and 3(511 - q) + 2 (q >= 256).  No per-bin accumulation pass, coalesced sample loads.
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int n = 32 * t + lane;
+                const float w = ldg(win + n);
+                const float2 v = make_float2(long_sample(p, fa, n, w), long_sample(p, fb, n, w));
+                float2 m = make_float2(1.f, 0.f);
+                if (r == 1) m = ldg(w1536 + n);
+                x[t].re = f2muls(v, m.x); x[t].im = f2muls(v, m.y);
+            }
+            fft512(x, scr, tws, w32s, lane);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int q = 32 * t + lane;
+                const float2 pw = f2muls(f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re)), sc);
+                int k = -1;
+                if (r == 0) { if (q <= 256) k = 3 * q; }
+                else k = q <= 255 ? 3 * q + 1 : 3 * (511 - q) + 2;
+                if (k >= 0) { acc[k].x = pw.x; acc[k].y = pw.y; esum = f2add(esum, pw); }
+            }
+        }
+    } else {
 #pragma unroll 1
     for (int r = 0; r < 3; ++r) {
         // sub-sequence r: element m = 32 t + lane is sample n = 3 m + r of the frame
@@ -110,13 +140,12 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
         }
     }
     // power spectrum |X|^2 / NFFT (sigproc.py:158) into the .x / .y of the bin's own slot; frame energy = sum over all bins
-    float2 esum = zero2;
-    const float sc = 1.0f / (float)kLongNfft;
     for (int k = lane; k < kLongBins; k += 32) {
         const float4 a = acc[k];
         const float2 pw = make_float2((a.x * a.x + a.z * a.z) * sc, (a.y * a.y + a.w * a.w) * sc);
         acc[k].x = pw.x; acc[k].y = pw.y;
         esum.x += pw.x; esum.y += pw.y;
+    }
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) { esum.x += simt::shfl32_xor(esum.x, m); esum.y += simt::shfl32_xor(esum.y, m); }
