@@ -93,10 +93,15 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
                 const int n = 32 * t + lane;
-                const float w = ldg(win + n);
-                const float2 v = make_float2(long_sample(p, fa, n, w), long_sample(p, fb, n, w));
-                float2 m = make_float2(1.f, 0.f);
-                if (r == 1) m = ldg(w1536 + n);
+                float2 v, m = make_float2(1.f, 0.f);
+                if (r == 0) {   // windowed, pre-emphasised samples; parked in the unused half of the lane's own bin slots for r = 1
+                    const float w = ldg(win + n);
+                    v = make_float2(long_sample(p, fa, n, w), long_sample(p, fb, n, w));
+                    acc[n].z = v.x; acc[n].w = v.y;
+                } else {
+                    v = make_float2(acc[n].z, acc[n].w);
+                    m = ldg(w1536 + n);
+                }
                 x[t].re = f2muls(v, m.x); x[t].im = f2muls(v, m.y);
             }
             fft512(x, scr, tws, w32s, lane);
