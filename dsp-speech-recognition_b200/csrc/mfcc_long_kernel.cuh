@@ -49,13 +49,15 @@ DEVFN int long_find_utt(const int64_t* frame_off, int n_utt, int64_t g) {
     return lo;
 }
 
-struct LongFrame { const unsigned char* src; int64_t s0; int S; };   // samples of the utterance, first sample of the frame, length
+// a frame's samples: base points at the frame's first sample, sample n is valid for n < lim (= min(frame_len, S - s0)), and
+// n = 0 of the utterance's first frame has no predecessor (first = 1)
+struct LongFrame { const unsigned char* base; int lim; int first; };
 DEVFN float long_sample(const MfccLongParams& p, const LongFrame& f, int n, float w) {
-    const int64_t s = f.s0 + n;
-    if (n >= p.frame_len || s >= f.S) return 0.f;
+    if (n >= f.lim) return 0.f;
     float cur, prev = 0.f;
-    if (p.in_f32) { const float* q = reinterpret_cast<const float*>(f.src); cur = q[s]; if (s > 0) prev = q[s - 1]; }
-    else { const int16_t* q = reinterpret_cast<const int16_t*>(f.src); cur = cvt_i16(q[s]); if (s > 0) prev = cvt_i16(q[s - 1]); }
+    const bool has_prev = n > 0 || !f.first;
+    if (p.in_f32) { const float* q = reinterpret_cast<const float*>(f.base); cur = q[n]; if (has_prev) prev = q[n - 1]; }
+    else { const int16_t* q = reinterpret_cast<const int16_t*>(f.base); cur = cvt_i16(q[n]); if (has_prev) prev = cvt_i16(q[n - 1]); }
     return dsp_fmaf(-p.preemph, prev, cur) * w;      // y[0] = x[0], y[n] = x[n] - c x[n-1] (sigproc.py:185), times the window
 }
 
@@ -74,10 +76,13 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     {
         const int ua = long_find_utt(p.frame_off, p.n_utt, g0);
         const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
-        fa.src = reinterpret_cast<const unsigned char*>(p.pcm) + p.seg_start[ua] * esz;
-        fa.s0 = (g0 - p.frame_off[ua]) * p.frame_step; fa.S = p.seg_len[ua];
-        fb.src = reinterpret_cast<const unsigned char*>(p.pcm) + p.seg_start[ub] * esz;
-        fb.s0 = hasB ? (g0 + 1 - p.frame_off[ub]) * p.frame_step : 0; fb.S = hasB ? p.seg_len[ub] : 0;
+        const int64_t sa = (g0 - p.frame_off[ua]) * p.frame_step;                 // first sample of the frame inside the utterance
+        const int64_t sb = hasB ? (g0 + 1 - p.frame_off[ub]) * p.frame_step : 0;
+        const int64_t ra = (int64_t)p.seg_len[ua] - sa, rb = hasB ? (int64_t)p.seg_len[ub] - sb : 0;   // samples left from the frame start
+        fa.base = reinterpret_cast<const unsigned char*>(p.pcm) + (p.seg_start[ua] + sa) * esz;
+        fb.base = reinterpret_cast<const unsigned char*>(p.pcm) + (p.seg_start[ub] + sb) * esz;
+        fa.lim = (int)(ra < p.frame_len ? (ra > 0 ? ra : 0) : p.frame_len); fa.first = sa == 0;
+        fb.lim = (int)(rb < p.frame_len ? (rb > 0 ? rb : 0) : p.frame_len); fb.first = sb == 0;
     }
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);
