@@ -165,19 +165,39 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     const float eps64 = 2.220446049250313e-16f;   // numpy.finfo(float64).eps floor (base.py:26,30)
     const float* inv_up = p.tab + kLtInvUp;
     const float* inv_dn = p.tab + kLtInvDn;
-    for (int j = 0; j < p.nfilt; ++j) {
-        const int lo = edge[j], mid = edge[j + 1], hi = edge[j + 2];
-        const float iu = inv_up[j], id = inv_dn[j];
-        float2 f = zero2;
-        for (int k = lo + lane; k < hi; k += 32) {
-            const float w = k < mid ? (float)(k - lo) * iu : (float)(hi - k) * id;
-            f.x = dsp_fmaf(w, acc[k].x, f.x); f.y = dsp_fmaf(w, acc[k].y, f.y);
-        }
+    // four filters at a time: each lane gathers its share of the four sums, then a transposing reduction (the lanes split
+    // the four sums among themselves while they halve the lane distance) brings a filter's total to eight lanes with 12 shuffles
+    // per group instead of 10 per filter, and every lane takes the logarithm of one filter only
+    for (int j0 = 0; j0 < p.nfilt; j0 += 4) {
+        float2 f[4];
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) { f.x += simt::shfl32_xor(f.x, m); f.y += simt::shfl32_xor(f.y, m); }
-        if (lane == 0) lmel[j] = make_float2(dsp_logf(f.x == 0.f ? eps64 : f.x), dsp_logf(f.y == 0.f ? eps64 : f.y));
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
+            f[u] = zero2;
+            if (j < p.nfilt) {
+                const int lo = edge[j], mid = edge[j + 1], hi = edge[j + 2];
+                const float iu = inv_up[j], id = inv_dn[j];
+                for (int k = lo + lane; k < hi; k += 32) {
+                    const float w = k < mid ? (float)(k - lo) * iu : (float)(hi - k) * id;
+                    f[u].x = dsp_fmaf(w, acc[k].x, f[u].x); f[u].y = dsp_fmaf(w, acc[k].y, f[u].y);
+                }
+            }
+        }
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        float2 k0 = up16 ? f[2] : f[0], k1 = up16 ? f[3] : f[1];
+        const float2 s0 = up16 ? f[0] : f[2], s1 = up16 ? f[1] : f[3];
+        k0.x += simt::shfl32_xor(s0.x, 16); k0.y += simt::shfl32_xor(s0.y, 16);
+        k1.x += simt::shfl32_xor(s1.x, 16); k1.y += simt::shfl32_xor(s1.y, 16);
+        float2 kk = up8 ? k1 : k0;
+        const float2 ss = up8 ? k0 : k1;
+        kk.x += simt::shfl32_xor(ss.x, 8); kk.y += simt::shfl32_xor(ss.y, 8);
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1) { kk.x += simt::shfl32_xor(kk.x, m); kk.y += simt::shfl32_xor(kk.y, m); }
+        const int jm = j0 + (up16 ? 2 : 0) + (up8 ? 1 : 0);
+        if ((lane & 7) == 0 && jm < p.nfilt)
+            lmel[jm] = make_float2(dsp_fast_logf(kk.x == 0.f ? eps64 : kk.x), dsp_fast_logf(kk.y == 0.f ? eps64 : kk.y));
     }
-    if (lane == 0) lmel[p.nfilt] = make_float2(dsp_logf(esum.x == 0.f ? eps64 : esum.x), dsp_logf(esum.y == 0.f ? eps64 : esum.y));
+    if (lane == 0) lmel[p.nfilt] = make_float2(dsp_fast_logf(esum.x == 0.f ? eps64 : esum.x), dsp_fast_logf(esum.y == 0.f ? eps64 : esum.y));
     simt::warp_sync();
     // DCT-II (ortho) * lifter (base.py:12-14), c0 := log(energy) (base.py:15)
     if (lane < p.numcep) {
