@@ -38,10 +38,36 @@ __global__ void __launch_bounds__(32 * kLongWarps, 3) mfcc_long_kernel(const __g
     if (g0 >= total) return;
     mfcc_long_pair(p, g0, total, smem + kLtW1536 * 4 + w * kLongWarpSmem, tws, tws + kLtW32 / 2);
 }
-__global__ void delta_batch_kernel(const float* mf, const int64_t* frame_off, int n_utt, int C, int N, float scale, int64_t max_frames, float* out) {
-    const int64_t total = frame_off[n_utt] < max_frames ? frame_off[n_utt] : max_frames;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total * C) delta_batch_thread(mf, frame_off, n_utt, C, N, scale, i, out);
+// delta + delta-delta over per-utterance cepstra (base.py:70-79 twice, model.py:76-77), one CTA per utterance: thread = (row of a
+// block of 8, column).  Pass 1 writes the static and delta columns, pass 2 reads the deltas back (edge-clamped on the DELTA
+// array) for the delta-deltas: 4N + 1 loads per output row instead of the 4N^2 + 2N of the one-pass form
+// (delta_batch_thread, kept for the CPU emulator), and no per-thread utterance search.  Same arithmetic, same order.
+__global__ void __launch_bounds__(128) delta_batch_kernel(const float* mf, const int64_t* frame_off, int n_utt, int C, int N, float scale, int64_t max_frames, float* out) {
+    const int u = blockIdx.x;
+    const int64_t r0 = frame_off[u];
+    const int F = (int)(frame_off[u + 1] - r0);                                   // clamps use the utterance's own frame count
+    const int Fw = (int)(r0 + F <= max_frames ? F : (max_frames > r0 ? max_frames - r0 : 0));   // rows that fit the output
+    const int c = threadIdx.x & 15, r = threadIdx.x >> 4;
+    if (Fw <= 0) return;
+    const int W = 3 * C;
+    auto clampf = [&](int a) { return a < 0 ? 0 : (a > F - 1 ? F - 1 : a); };
+    if (c < C) {
+        for (int t = r; t < Fw; t += 8) {
+            float acc = 0.f;
+            for (int n = 1; n <= N; ++n) acc = dsp_fmaf((float)n, mf[(r0 + clampf(t + n)) * C + c] - mf[(r0 + clampf(t - n)) * C + c], acc);
+            float* o = out + (r0 + t) * W;
+            o[c] = mf[(r0 + t) * C + c];
+            o[C + c] = acc * scale;
+        }
+    }
+    __syncthreads();
+    if (c < C) {
+        for (int t = r; t < Fw; t += 8) {
+            float acc = 0.f;
+            for (int n = 1; n <= N; ++n) acc = dsp_fmaf((float)n, out[(r0 + clampf(t + n)) * W + C + c] - out[(r0 + clampf(t - n)) * W + C + c], acc);
+            out[(r0 + t) * W + 2 * C + c] = acc * scale;
+        }
+    }
 }
 
 typedef void (*mfcc_kernel_t)(const MfccParams);
@@ -159,7 +185,7 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
         mfcc_long_kernel<<<(unsigned)((rows + 2 * kLongWarps - 1) / (2 * kLongWarps)), 32 * kLongWarps, kLongCtaSmem, st>>>(lp);
         LAUNCH_CHECK("mfcc_long_kernel", st);
         int den = 0; for (int i = 1; i <= pl->cfg.delta_n; ++i) den += i * i;
-        delta_batch_kernel<<<(unsigned)((rows * pl->cfg.numcep + 255) / 256), 256, 0, st>>>(ws.cep, pp.frame_off, n_utt, pl->cfg.numcep, pl->cfg.delta_n,
+        delta_batch_kernel<<<(unsigned)n_utt, 128, 0, st>>>(ws.cep, pp.frame_off, n_utt, pl->cfg.numcep, pl->cfg.delta_n,
                                                                                           (float)(1.0 / (2.0 * den)), rows, d_out);
         LAUNCH_CHECK("delta_batch_kernel", st);
         return DSPFE_OK;
