@@ -155,6 +155,7 @@ struct dspfe_plan {
     int width = 0;              // 3 * numcep
     bool is_long = false;       // nfft = 1536: K1L
     float* d_long_tab = nullptr;
+    std::vector<float> h_long_tab;   // host copy: the mel edges travel as kernel parameters
 };
 
 namespace {
@@ -182,6 +183,7 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
         lp.pcm = d_pcm; lp.in_f32 = f32 ? 1 : 0; lp.seg_start = ws.seg_start; lp.seg_len = ws.seg_len; lp.frame_off = pp.frame_off; lp.n_utt = n_utt;
         lp.frame_len = pl->cfg.frame_len; lp.frame_step = pl->cfg.frame_step; lp.nfilt = pl->cfg.nfilt; lp.numcep = pl->cfg.numcep;
         lp.append_energy = pl->cfg.append_energy; lp.preemph = (float)pl->cfg.preemph; lp.tab = pl->d_long_tab; lp.mfcc = ws.cep; lp.max_frames = rows;
+        long_fill_mel_params(lp, pl->h_long_tab.data());
         mfcc_long_kernel<<<(unsigned)((rows + 2 * kLongWarps - 1) / (2 * kLongWarps)), 32 * kLongWarps, kLongCtaSmem, st>>>(lp);
         LAUNCH_CHECK("mfcc_long_kernel", st);
         int den = 0; for (int i = 1; i <= pl->cfg.delta_n; ++i) den += i * i;
@@ -255,6 +257,7 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
         if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
         pl->is_long = true; pl->has_win = !pl->cfg.window.empty(); pl->width = 3 * pl->cfg.numcep;
         const std::vector<float> t = build_long_tables(pl->cfg);
+        pl->h_long_tab = t;
         cudaError_t e = cudaMalloc(&pl->d_long_tab, t.size() * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_long_tab, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongCtaSmem);

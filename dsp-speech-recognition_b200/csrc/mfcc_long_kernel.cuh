@@ -41,8 +41,31 @@ struct MfccLongParams {
     const float* tab;           // blob (kLt* offsets)
     float* mfcc;                // [F_total, numcep] static cepstra
     int64_t max_frames;
+    // the mel filter edges and slope reciprocals, copied out of the blob: kernel parameters are read through the constant
+    // bank with uniform loads, which takes five dependent global loads per filter out of the mel loop
+    int32_t mel_edge[48];
+    float mel_iu[48], mel_id[48];
 };
+inline void long_fill_mel_params(MfccLongParams& p, const float* host_tab) {
+    for (int i = 0; i < 48; ++i) {
+        p.mel_edge[i] = reinterpret_cast<const int32_t*>(host_tab + kLtEdge)[i];
+        p.mel_iu[i] = host_tab[kLtInvUp + i]; p.mel_id[i] = host_tab[kLtInvDn + i];
+    }
+}
 
+// warp-cooperative 32-ary form: three dependent loads for up to 32768 utterances instead of log2(U)
+DEVFN int long_find_utt_warp(const int64_t* frame_off, int n_utt, int64_t g, int lane) {
+    int lo = 0, hi = n_utt;   // invariant: frame_off[lo] <= g < frame_off[hi]
+    while (hi - lo > 1) {
+        const int stride = (hi - lo + 31) >> 5;
+        const int i = lo + lane * stride;
+        const bool le = i < hi && frame_off[i] <= g;            // true on a prefix of the lanes (lane 0 always)
+        const int c = warp_redux_add(le ? 1 : 0);
+        lo += (c - 1) * stride;
+        hi = lo + stride < hi ? lo + stride : hi;
+    }
+    return lo;
+}
 DEVFN int long_find_utt(const int64_t* frame_off, int n_utt, int64_t g) {
     int lo = 0, hi = n_utt;   // frame_off[lo] <= g < frame_off[hi]
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frame_off[mid] <= g) lo = mid; else hi = mid; }
@@ -69,12 +92,12 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     float2* lmel = reinterpret_cast<float2*>(acc + kLongBins + 7);
     const float2* w1536 = reinterpret_cast<const float2*>(p.tab + kLtW1536);
     const float* win = p.tab + kLtWin;
-    const int32_t* edge = reinterpret_cast<const int32_t*>(p.tab + kLtEdge);
+    const int32_t* edge = p.mel_edge;
     const bool hasB = g0 + 1 < total;
     const int esz = p.in_f32 ? 4 : 2;
     LongFrame fa, fb;
     {
-        const int ua = long_find_utt(p.frame_off, p.n_utt, g0);
+        const int ua = long_find_utt_warp(p.frame_off, p.n_utt, g0, lane);
         const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
         const int64_t sa = (g0 - p.frame_off[ua]) * p.frame_step;                 // first sample of the frame inside the utterance
         const int64_t sb = hasB ? (g0 + 1 - p.frame_off[ub]) * p.frame_step : 0;
@@ -163,8 +186,8 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     // mel filterbank (base.py:40-58): filter j rises over [e_j, e_{j+1}) and falls over [e_{j+1}, e_{j+2}); one filter at a
     // time, its bins spread over the lanes
     const float eps64 = 2.220446049250313e-16f;   // numpy.finfo(float64).eps floor (base.py:26,30)
-    const float* inv_up = p.tab + kLtInvUp;
-    const float* inv_dn = p.tab + kLtInvDn;
+    const float* inv_up = p.mel_iu;
+    const float* inv_dn = p.mel_id;
     // four filters at a time: each lane gathers its share of the four sums, then a transposing reduction (the lanes split
     // the four sums among themselves while they halve the lane distance) brings a filter's total to eight lanes with 12 shuffles
     // per group instead of 10 per filter, and every lane takes the logarithm of one filter only
