@@ -55,6 +55,10 @@ timed("robust_endpoint_detection (f-3: autocorrelation-gated rule)", lambda: ep.
 mfl = dspfe.MfccPlan(frame_len=480, frame_step=160, nfft=1536, window=np.hamming(480), preemph=0.0, delta_n=3)
 outl = torch.empty((mfl.rows_bound(pcm.numel(), U), 39), dtype=torch.float32, device=dev)
 timed("mfcc_delta nfft=1536 (f-2: 480-sample Hamming frames, trimmed)", lambda: mfl.mfcc_delta(pcm, off_d, trim=lr, out=outl, frame_off=fo))
+# the same call at the data set's own rate (report p.9: 44.1 kHz -> 1323-sample frames, hop 441); the batch is read as 44.1 kHz audio
+mfh = dspfe.MfccPlan(frame_len=1323, frame_step=441, nfft=1536, window=np.hamming(1323), preemph=0.0, delta_n=3, samplerate=44100)
+outh = torch.empty((mfh.rows_bound(pcm.numel(), U), 39), dtype=torch.float32, device=dev)
+timed("mfcc_delta nfft=1536 (f-2: 1323-sample Hamming frames, hop 441, untrimmed)", lambda: mfh.mfcc_delta(pcm, off_d, out=outh, frame_off=fo))
 if "--ingest" in sys.argv:
     import tempfile, time
     from scipy.io import wavfile

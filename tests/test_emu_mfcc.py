@@ -97,6 +97,10 @@ def test_long_frame_kernel_nfft1536():
     x = synth.synth_utterance(301, 20000, sr=44100)
     out, fo = emu.mfcc_long(x, [0, len(x)], frame_len=1323, frame_step=441, window=np.hamming(1323), samplerate=44100, delta_n=2)
     assert_mfcc_close(out, ref39(x, 44100, 2), what="44.1k")
+    # two folds of the 512-point transforms (frames of 513..1024 samples): 30 ms at 22.05 kHz = 662 samples, hop 221
+    x2 = synth.synth_utterance(302, 9000, sr=22050)
+    out, fo = emu.mfcc_long(x2, [0, len(x2)], frame_len=662, frame_step=221, window=np.hamming(662), samplerate=22050, delta_n=2)
+    assert_mfcc_close(out, ref39(x2, 22050, 2), what="22.05k")
     xf = (x / np.std(x)).astype(np.float32)          # model.py:62-63 feeds scaled float audio
     out, fo = emu.mfcc_long(xf, [0, len(xf)], frame_len=1323, frame_step=441, window=np.hamming(1323), samplerate=44100, preemph=0.0)
     assert_mfcc_close(out, ref39(xf.astype(np.float64), 44100, 2, preemph=0), what="44.1k float")
