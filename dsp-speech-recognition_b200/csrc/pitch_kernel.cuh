@@ -195,8 +195,27 @@ DSP_HD bool pitch_feature_tail(const double* pitch, const double* amp, int F, do
 // warp-cooperative pieces (device + emulator)
 // ---------------------------------------------------------------------------------------------------------
 // medians of the non-negative entries of two frames at once (np.median(frame[frame >= 0]), pitch.py:146): exact k-th
-// order statistics by bitwise selection on the float bit patterns; NaN when a frame has no non-negative sample.
+// order statistics by a bit-sliced radix selection on the float bit patterns; NaN when a frame has no non-negative sample.
 // NT = samples per lane (32 * NT >= L): 16 for 512-sample frames, 10 for frames of up to 320 samples.
+// Transposes two independent 16 x 16 bit matrices at once: A[r] holds row r of one matrix in its low 16 bits and row r of the
+// other in its high 16 bits (Hacker's Delight's masked-swap transpose, masks replicated in both halves; the shifts never
+// carry a bit across the halves because every mask clears the top j bits of each half).  Afterwards A[i] holds, per half,
+// the plane of bit 15 - i: its bit 15 - r is bit 15 - i of the original row r.
+DEVFN void transpose16_dual(unsigned (&A)[16]) {
+    unsigned m = 0x00ff00ffu;
+#pragma unroll
+    for (int j = 8; j != 0; j >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if ((k & j) == 0) {
+                const unsigned t = (A[k] ^ (A[k + j] >> j)) & m;
+                A[k] ^= t;
+                A[k + j] ^= t << j;
+            }
+        }
+        m ^= m << (j >> 1);
+    }
+}
 template <int NT>
 DEVFN float2 warp_median_nonneg2(const float (&xa)[NT], const float (&xb)[NT], int L, int lane) {
     unsigned ka[NT], kb[NT];
@@ -216,84 +235,35 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[NT], const float (&xb)[NT], i
     const int ma = cnt & 0xffff, mb = cnt >> 16;
     const int ra = (ma - 1) >> 1, rb = (mb - 1) >> 1;          // rank of the lower middle element
     unsigned Ka = 0, Kb = 0;
-    bool done = false;
-#ifndef DSPFE_EMU
     {
-        // Fast path: the high 16 bits of a non-negative float are the bit pattern of a non-negative half with the same
-        // ordering, so HSET2 compares two keys per instruction and HADD2 counts them (excluded keys 0xFFFF.. are NaNs
-        // and never count).  Valid while every real key is below the half inf/NaN patterns (|x| < 2^121).
-        int mx = -1;
+        // Bit-sliced radix select.  The lane's 16 keys of both frames are transposed into bit planes (a 16 x 16 bit-matrix
+        // transpose per half-word, frame A in the low halves of the registers and frame B in the high halves, so one
+        // sequence of masked swaps serves both): plane[b] has bit t set when key t has bit b set.  One selection step per
+        // key bit, most significant first, is then a handful of logic operations per lane: candidates with a zero bit =
+        // cand & ~plane, one population count per frame, a warp sum, and the candidate mask keeps the zeros or the ones.
+        unsigned H[16], Lo[16];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { mx = max(mx, (int)ka[t]); mx = max(mx, (int)kb[t]); }   // excluded keys are -1 as signed
-        mx = __reduce_max_sync(0xffffffffu, mx);
-        if (mx < 0x7C000000) {
-            static_assert(NT % 2 == 0, "keys are packed in pairs");
-            __half2 pa[NT / 2], pb[NT / 2];
-#pragma unroll
-            for (int j = 0; j < NT / 2; ++j) {
-                const unsigned wa = __byte_perm(ka[2 * j], ka[2 * j + 1], 0x7632), wb = __byte_perm(kb[2 * j], kb[2 * j + 1], 0x7632);
-                pa[j] = *reinterpret_cast<const __half2*>(&wa); pb[j] = *reinterpret_cast<const __half2*>(&wb);
-            }
-            auto count_le = [&](unsigned ta, unsigned tb) {    // #(hi16 <= t) per frame, packed (A | B << 16)
-                const unsigned wa = ta * 0x10001u, wb = tb * 0x10001u;
-                const __half2 ha = *reinterpret_cast<const __half2*>(&wa), hb = *reinterpret_cast<const __half2*>(&wb);
-                __half2 a0 = __hle2(pa[0], ha), a1 = __hle2(pa[1], ha), b0 = __hle2(pb[0], hb), b1 = __hle2(pb[1], hb);
-#pragma unroll
-                for (int j = 2; j + 1 < NT / 2; j += 2) {
-                    a0 = __hadd2(a0, __hle2(pa[j], ha)); a1 = __hadd2(a1, __hle2(pa[j + 1], ha));
-                    b0 = __hadd2(b0, __hle2(pb[j], hb)); b1 = __hadd2(b1, __hle2(pb[j + 1], hb));
-                }
-                if ((NT / 2) & 1) { a0 = __hadd2(a0, __hle2(pa[NT / 2 - 1], ha)); b0 = __hadd2(b0, __hle2(pb[NT / 2 - 1], hb)); }
-                a0 = __hadd2(a0, a1); b0 = __hadd2(b0, b1);
-                const int ca = __half2int_rn(__hadd(__low2half(a0), __high2half(a0)));
-                const int cb = __half2int_rn(__hadd(__low2half(b0), __high2half(b0)));
-                return __reduce_add_sync(0xffffffffu, ca + (cb << 16));
-            };
-            unsigned Ha = 0, Hb = 0;
-            for (int b = 14; b >= 0; --b) {
-                const int c = count_le(Ha | ((1u << b) - 1u), Hb | ((1u << b) - 1u));
-                if ((c & 0xffff) < ra + 1) Ha |= 1u << b;
-                if ((c >> 16) < rb + 1) Hb |= 1u << b;
-            }
-            // rank inside the bucket of keys that share the high half
-            const int below = count_le(Ha ? Ha - 1 : 0, Hb ? Hb - 1 : 0);
-            int qa = ra - (Ha ? (below & 0xffff) : 0), qb = rb - (Hb ? (below >> 16) : 0);
-            // the bucket rarely holds more than a few distinct values: peel them off in increasing order
-            unsigned ma_[NT], mb_[NT];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) { ma_[t] = (ka[t] >> 16) == Ha ? ka[t] : 0xffffffffu; mb_[t] = (kb[t] >> 16) == Hb ? kb[t] : 0xffffffffu; }
-            bool fa = ma == 0, fb = mb == 0;                    // nothing to find in an empty frame
-            long long pva = -1, pvb = -1;
-            while (!(fa && fb)) {
-                unsigned ca_ = 0xffffffffu, cb_ = 0xffffffffu;
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    if ((long long)ma_[t] > pva && ma_[t] < ca_) ca_ = ma_[t];
-                    if ((long long)mb_[t] > pvb && mb_[t] < cb_) cb_ = mb_[t];
-                }
-                ca_ = __reduce_min_sync(0xffffffffu, ca_); cb_ = __reduce_min_sync(0xffffffffu, cb_);
-                int n = 0;
-#pragma unroll
-                for (int t = 0; t < NT; ++t) n += (ma_[t] == ca_ ? 1 : 0) + (mb_[t] == cb_ ? 0x10000 : 0);
-                n = __reduce_add_sync(0xffffffffu, n);
-                if (!fa) { if (qa < (n & 0xffff) || ca_ == 0xffffffffu) { Ka = ca_; fa = true; } else { qa -= n & 0xffff; pva = ca_; } }
-                if (!fb) { if (qb < (n >> 16) || cb_ == 0xffffffffu) { Kb = cb_; fb = true; } else { qb -= n >> 16; pvb = cb_; } }
-            }
-            done = true;
+        for (int t = 0; t < 16; ++t) {
+            const unsigned a = t < NT ? ka[t < NT ? t : 0] : 0xffffffffu, b = t < NT ? kb[t < NT ? t : 0] : 0xffffffffu;
+            H[t] = (a >> 16) | (b & 0xffff0000u);
+            Lo[t] = (a & 0xffffu) | (b << 16);
         }
-    }
-#endif
-    for (int b = done ? -1 : 30; b >= 0; --b) {
-        const unsigned ta = Ka | ((1u << b) - 1u), tb = Kb | ((1u << b) - 1u);
-        int c0 = 0, c1 = 0;                                   // independent partial counts: no 32-deep add chain
+        transpose16_dual(H);
+        transpose16_dual(Lo);
+        unsigned cand = 0xffffffffu;
+        int rA = ra, rB = rb;
 #pragma unroll
-        for (int t = 0; t < NT; t += 2) {
-            c0 += (ka[t] <= ta ? 1 : 0) + (kb[t] <= tb ? 0x10000 : 0);
-            c1 += (ka[t + 1] <= ta ? 1 : 0) + (kb[t + 1] <= tb ? 0x10000 : 0);
+        for (int i = 0; i < 32; ++i) {
+            const unsigned P = i < 16 ? H[i & 15] : Lo[i & 15];           // plane of key bit 31 - i
+            const unsigned z = cand & ~P;
+            const int c = warp_redux_add(dsp_popc(z & 0xffffu) + (dsp_popc(z >> 16) << 16));
+            const int cA = c & 0xffff, cB = c >> 16;
+            const bool zA = rA < cA, zB = rB < cB;                        // the rank lies among the candidates with a zero bit
+            const unsigned sel = (zA ? 0x0000ffffu : 0u) | (zB ? 0xffff0000u : 0u);
+            cand = (z & sel) | (cand & P & ~sel);
+            if (!zA) { rA -= cA; Ka |= 1u << (31 - i); }
+            if (!zB) { rB -= cB; Kb |= 1u << (31 - i); }
         }
-        const int c = warp_redux_add(c0 + c1);
-        if ((c & 0xffff) < ra + 1) Ka |= 1u << b;
-        if ((c >> 16) < rb + 1) Kb |= 1u << b;
     }
     // even count: the upper middle element is the same key when enough keys are <= K, else the next larger key
     int c = 0; unsigned na = 0xffffffffu, nb = 0xffffffffu;

@@ -125,6 +125,15 @@ DEVFN int __float_as_int_compat(float f) { return __float_as_int(f); }
 DEVFN float __int_as_float_compat(int i) { return __int_as_float(i); }
 #endif
 
+// population count
+DEVFN int dsp_popc(unsigned v) {
+#ifdef DSPFE_EMU
+    return __builtin_popcount(v);
+#else
+    return __popc(v);
+#endif
+}
+
 // warp-wide integer sum (REDUX on sm_100a)
 DEVFN int warp_redux_add(int v) {
 #ifdef DSPFE_EMU
