@@ -66,13 +66,18 @@ DEVFN cpx2 shfl_xor_c(cpx2 a, int m) {
 }
 
 // tws: W512^{n2' (k1 + 16 kq)} at [k1*32 + lane]; w32s: [2*k1 + q] = W32^{q k1}; scr: kWarpScr float2 owned by the warp
+// W32IMM: take W32^k1 from immediates selected by the half-warp instead of the w32s table (one shared-memory load less per
+// k1; worth it only where registers are not the constraint)
+template <bool W32IMM = false>
 DEVFN void fft512(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
     dft16(x);                                                   // over n1 -> k1
     const int q = lane >> 4, ll = lane & 15;
     const float sg = q ? -1.f : 1.f;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {                           // b[kq] = a[q=0] + (-1)^kq W32^k1 a[q=1]
-        const float2 w = w32s[2 * k1 + q];
+        const float kC[16] = {1.0f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f, 0.382683432f, 0.195090322f, 6.123234e-17f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f};
+        const float kS[16] = {-0.0f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f, -1.0f, -0.98078528f, -0.923879533f, -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f};
+        const float2 w = W32IMM ? make_float2(q ? kC[k1] : 1.f, q ? kS[k1] : 0.f) : w32s[2 * k1 + q];
         const cpx2 u = cmuls(x[k1], w.x, w.y);
         const cpx2 v = shfl_xor_c(u, 16);
         cpx2 d; d.re = f2fmas(u.re, sg, v.re); d.im = f2fmas(u.im, sg, v.im);

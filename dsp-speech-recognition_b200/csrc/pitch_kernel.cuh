@@ -250,10 +250,11 @@ DEVFN float2 warp_median_nonneg2(const float (&xa)[NT], const float (&xb)[NT], i
         }
         transpose16_dual(H);
         transpose16_dual(Lo);
-        unsigned cand = 0xffffffffu;
+        // key bit 31 separates the excluded keys (all ones) from the real ones: its step needs no count
+        unsigned cand = ~H[0];
         int rA = ra, rB = rb;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 1; i < 32; ++i) {
             const unsigned P = i < 16 ? H[i & 15] : Lo[i & 15];           // plane of key bit 31 - i
             const unsigned z = cand & ~P;
             const int c = warp_redux_add(dsp_popc(z & 0xffffu) + (dsp_popc(z >> 16) << 16));
@@ -493,7 +494,7 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
         const float cj = inv ? -1.f : 1.f;                   // inverse = conj . forward . conj
 #pragma unroll
         for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
-        fft512(x, scr, tws, w32s, lane);
+        fft512<MODE != 0>(x, scr, tws, w32s, lane);
 #pragma unroll
         for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
         // ---- pointwise table products: He / Ho after a forward transform, conj(W1024^n) after the FIR's inverse
