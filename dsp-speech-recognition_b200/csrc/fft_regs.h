@@ -67,7 +67,7 @@ DEVFN cpx2 shfl_xor_c(cpx2 a, int m) {
 
 // tws: W512^{n2' (k1 + 16 kq)} at [k1*32 + lane]; w32s: [2*k1 + q] = W32^{q k1}; scr: kWarpScr float2 owned by the warp
 // W32IMM: take W32^k1 from immediates selected by the half-warp instead of the w32s table (one shared-memory load less per
-// k1; worth it only where registers are not the constraint)
+// k1; worth it only where registers are not the constraint: the pitch frame kernels at 3 CTAs/SM)
 template <bool W32IMM = false>
 DEVFN void fft512(cpx2 (&x)[16], float2* scr, const float2* tws, const float2* w32s, int lane) {
     dft16(x);                                                   // over n1 -> k1

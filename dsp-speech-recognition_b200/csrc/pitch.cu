@@ -67,10 +67,11 @@ __global__ void __launch_bounds__(32 * kPitchWarps, 6) pitch_clip_kernel(const _
     else pitch_clip_pair<16>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
 }
 
-// K4a-2 / K5a-2: the transforms, a frame pair per warp.  The autocorrelation chains keep more values alive: at 128 registers
-// (4 CTAs/SM) they spilled ~200 bytes per thread; 3 CTAs/SM without spills measured 3 % faster (the cepstrum chain was neutral).
+// K4a-2 / K5a-2: the transforms, a frame pair per warp.  At 128 registers (4 CTAs/SM) the chains spilled 130-230 bytes per
+// thread; 3 CTAs/SM without spills measured 3 % faster for the autocorrelation chains and 1 % for the cepstrum (the kernels sit
+// on the shared-memory pipe, so the fourth CTA bought nothing).
 template <int MODE>
-__global__ void __launch_bounds__(32 * kPitchWarps, MODE == 0 ? 4 : 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
+__global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
     const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;

@@ -494,7 +494,7 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
         const float cj = inv ? -1.f : 1.f;                   // inverse = conj . forward . conj
 #pragma unroll
         for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
-        fft512<MODE != 0>(x, scr, tws, w32s, lane);
+        fft512<true>(x, scr, tws, w32s, lane);
 #pragma unroll
         for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
         // ---- pointwise table products: He / Ho after a forward transform, conj(W1024^n) after the FIR's inverse
