@@ -133,6 +133,8 @@ int dspfe_endpoint_create(const dspfe_endpoint_params* p, dspfe_endpoint_plan** 
     if (!pl) return fail(DSPFE_ERR_NOMEM, "out of host memory");
     pl->prm = *p;
     int rc = fill_rule(*p, pl->rule, pl->frame_len, pl->frame_step);
+    if (!rc && pl->frame_step > pl->frame_len)
+        rc = fail(DSPFE_ERR_UNSUPPORTED, "cfg.step greater than cfg.frame (gaps between frames) is not built: the frame bounds assume overlapping or abutting frames");
     if (rc) { delete pl; return rc; }
     pl->q = pl->frame_len / pl->frame_step; pl->rem = pl->frame_len % pl->frame_step;
     *plan = pl;

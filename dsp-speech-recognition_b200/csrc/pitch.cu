@@ -265,10 +265,11 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     const unsigned fgrid = (unsigned)((bound + 2 * kPitchWarps - 1) / (2 * kPitchWarps));
     pitch_clip_kernel<<<fgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_clip_kernel", st);
-    if (p.mode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
-    else if (acr_short_frames(p.frame_len, p.row_len)) pitch_frame_kernel<2><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
+    const int fmode = p.mode == 0 ? 0 : (acr_short_frames(p.frame_len, p.row_len) ? 2 : 1);
+    if (fmode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
+    else if (fmode == 2) pitch_frame_kernel<2><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     else pitch_frame_kernel<1><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
-    LAUNCH_CHECK("pitch_frame_kernel", st);
+    LAUNCH_CHECK(fmode == 0 ? "pitch_frame_kernel<0>" : fmode == 2 ? "pitch_frame_kernel<2>" : "pitch_frame_kernel<1>", st);
     if (d_pitch || d_lag || d_feat) {
         pitch_track_kernel<<<(unsigned)n_utt, kTrackThreads, track_smem(p.row_len), st>>>(p);
         LAUNCH_CHECK("pitch_track_kernel", st);

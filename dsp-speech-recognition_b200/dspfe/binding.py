@@ -58,9 +58,13 @@ def lib():
     return _lib
 
 
+class DspfeUnsupported(DspfeError, NotImplementedError):
+    """DSPFE_ERR_UNSUPPORTED: a parameter combination outside the built set (there is no CPU fallback to hand it to)."""
+
+
 def _check(rc):
     if rc != 0:
-        raise DspfeError(rc, lib().dspfe_last_error().decode())
+        raise (DspfeUnsupported if rc == -2 else DspfeError)(rc, lib().dspfe_last_error().decode())
 
 
 def mfcc_params(samplerate=16000, frame_len=400, frame_step=160, nfft=512, nfilt=26, numcep=13, ceplifter=22,
@@ -809,3 +813,142 @@ def pitch_num_frames_host(n_samples, samplerate=16000, dst_rate=10000, frame_len
     if nf < 0:
         raise DspfeError(int(nf), L.dspfe_last_error().decode())
     return int(nf), int(ld.value)
+
+
+# ---------------------------------------------------------------------------------------------- whole front-end
+class _FrontendParams(ctypes.Structure):
+    _fields_ = [("samplerate", ctypes.c_int32), ("delta_n", ctypes.c_int32), ("acr_frame_len", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("slab_samples", ctypes.c_int64), ("host_slab_samples", ctypes.c_int64),
+                ("cep_preemph", ctypes.c_double)]
+
+
+class _FrontendOut(ctypes.Structure):
+    _fields_ = [("lr", ctypes.c_void_p), ("mfcc", ctypes.c_void_p), ("mfcc_cap", ctypes.c_int64), ("mfcc_frame_off", ctypes.c_void_p),
+                ("cep_pitch", ctypes.c_void_p), ("cep_cap", ctypes.c_int64), ("cep_frame_off", ctypes.c_void_p),
+                ("cep_feat", ctypes.c_void_p), ("acr_pitch", ctypes.c_void_p), ("acr_cap", ctypes.c_int64),
+                ("acr_frame_off", ctypes.c_void_p), ("cep_lag", ctypes.c_void_p), ("acr_lag", ctypes.c_void_p)]
+
+
+def _bind_frontend(L):
+    if getattr(L, "_fe_bound", False):
+        return
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.dspfe_frontend_params_default.argtypes = [ctypes.POINTER(_FrontendParams)]
+    L.dspfe_frontend_params_default.restype = None
+    L.dspfe_frontend_create.argtypes = [ctypes.POINTER(_FrontendParams), ctypes.POINTER(vp)]
+    L.dspfe_frontend_destroy.argtypes = [vp]
+    L.dspfe_frontend_destroy.restype = None
+    L.dspfe_frontend_bounds.argtypes = [vp, i64, i64, vp]
+    L.dspfe_frontend.argtypes = [vp, vp, vp, vp, i32, ctypes.POINTER(_FrontendOut), vp, vp]
+    L.dspfe_frontend_host.argtypes = [vp, vp, vp, i32, ctypes.POINTER(_FrontendOut), vp]
+    L.dspfe_timing_begin.argtypes = [vp]
+    L.dspfe_timing_end.argtypes = [vp, vp, i32, ctypes.POINTER(i32)]
+    L.dspfe_launch_count.restype = i64
+    L._fe_bound = True
+
+
+class FrontendPlan:
+    """dspfe_frontend_plan: endpoints -> MFCC+delta+delta on sig[l:r] -> cepstrum pitch + pitch_feature on
+    preemphasis(sig)[l:r] -> autocorrelation pitch on sig[l:r] for every utterance of a packed ragged batch
+    (reference model.py:52-95, pitch_model.py:38-41), walked in slabs with bounded workspaces."""
+    KEYS = ("lr", "mfcc", "mfcc_frame_off", "cep_pitch", "cep_frame_off", "cep_feat", "acr_pitch", "acr_frame_off", "cep_lag", "acr_lag")
+
+    def __init__(self, samplerate=16000, delta_n=2, acr_frame_len=300, slab_samples=0, host_slab_samples=0, cep_preemph=0.97):
+        L = lib(); _bind_endpoint(L); _bind_pitch(L); _bind_frontend(L)
+        p = _FrontendParams()
+        L.dspfe_frontend_params_default(ctypes.byref(p))
+        p.samplerate, p.delta_n, p.acr_frame_len = int(samplerate), int(delta_n), int(acr_frame_len)
+        p.slab_samples, p.host_slab_samples, p.cep_preemph = int(slab_samples), int(host_slab_samples), float(cep_preemph)
+        h = ctypes.c_void_p()
+        _check(L.dspfe_frontend_create(ctypes.byref(p), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dspfe_frontend_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def bounds(self, total_samples, n_utt):
+        """(MFCC rows, cepstrum frames, autocorrelation frames) capacities that hold any batch with these totals."""
+        caps = (ctypes.c_int64 * 3)()
+        _check(lib().dspfe_frontend_bounds(self._h, int(total_samples), int(n_utt), caps))
+        return tuple(int(c) for c in caps)
+
+    def alloc(self, total_samples, n_utt, device=None, pinned=False):
+        """Output arrays for a batch: CUDA tensors on `device`, or NumPy arrays (over pinned torch storage if `pinned`)."""
+        import torch
+        c0, c1, c2 = self.bounds(total_samples, n_utt)
+        shapes = dict(lr=((n_utt, 2), torch.int32), mfcc=((c0, 39), torch.float32), mfcc_frame_off=((n_utt + 1,), torch.int64),
+                      cep_pitch=((c1,), torch.float64), cep_frame_off=((n_utt + 1,), torch.int64), cep_feat=((n_utt, 5), torch.float64),
+                      acr_pitch=((c2,), torch.float64), acr_frame_off=((n_utt + 1,), torch.int64),
+                      cep_lag=((c1,), torch.int32), acr_lag=((c2,), torch.int32))
+        out = {}
+        for k, (shape, dt) in shapes.items():
+            if device is not None:
+                out[k] = torch.empty(shape, dtype=dt, device=device)
+            else:
+                t = torch.empty(shape, dtype=dt)
+                out[k] = t.pin_memory() if pinned else t
+        return out
+
+    @staticmethod
+    def _out_struct(o, ptr):
+        s = _FrontendOut()
+        for k in FrontendPlan.KEYS:
+            setattr(s, k, ptr(o[k]) if o.get(k) is not None else None)
+        s.mfcc_cap = int(o["mfcc"].shape[0]) if o.get("mfcc") is not None else 0
+        s.cep_cap = int(o["cep_pitch"].shape[0]) if o.get("cep_pitch") is not None else 0
+        s.acr_cap = int(o["acr_pitch"].shape[0]) if o.get("acr_pitch") is not None else 0
+        return s
+
+    def run(self, pcm, offsets, h_offsets, out, stream=None):
+        """Device path: pcm int16 CUDA tensor, offsets int64 CUDA tensor [U+1], h_offsets its NumPy copy, `out` from
+        alloc(device=...).  Returns (MFCC rows, cepstrum frames, autocorrelation frames) written."""
+        import torch
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+        assert offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()
+        h_offsets = np.ascontiguousarray(h_offsets, dtype=np.int64)
+        n_utt = len(h_offsets) - 1
+        s = self._out_struct(out, lambda t: t.data_ptr())
+        tot = (ctypes.c_int64 * 3)()
+        st = stream if stream is not None else torch.cuda.current_stream(pcm.device).cuda_stream
+        _check(lib().dspfe_frontend(self._h, pcm.data_ptr(), offsets.data_ptr(), _np_ptr(h_offsets), n_utt, ctypes.byref(s), tot,
+                                    ctypes.c_void_p(st)))
+        return tuple(int(t) for t in tot)
+
+    def run_host(self, pcm, offsets, out):
+        """Host path: pcm int16 NumPy array (pinned memory makes the copies asynchronous), offsets int64 NumPy [U+1],
+        `out` a dict of NumPy arrays / CPU tensors from alloc(device=None)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_utt = len(offsets) - 1
+        s = self._out_struct(out, lambda t: t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data)
+        tot = (ctypes.c_int64 * 3)()
+        _check(lib().dspfe_frontend_host(self._h, _np_ptr(pcm), _np_ptr(offsets), n_utt, ctypes.byref(s), tot))
+        return tuple(int(t) for t in tot)
+
+
+def timing_begin(stream=None):
+    """Start bracketing every kernel the library launches on `stream` (default: torch's current stream) with CUDA events."""
+    import torch
+    L = lib(); _bind_frontend(L)
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    _check(L.dspfe_timing_begin(ctypes.c_void_p(st)))
+
+
+def timing_end(cap=4096):
+    """Waits for the stream and returns [(kernel name, ms), ...] in launch order."""
+    L = lib(); _bind_frontend(L)
+    names = ctypes.create_string_buffer(48 * cap)
+    ms = (ctypes.c_float * cap)()
+    n = ctypes.c_int32(0)
+    _check(L.dspfe_timing_end(names, ms, cap, ctypes.byref(n)))
+    k = min(n.value, cap)
+    return [(names.raw[48 * i:48 * i + 48].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(k)]
+
+
+def launch_count():
+    L = lib(); _bind_frontend(L)
+    return int(L.dspfe_launch_count())

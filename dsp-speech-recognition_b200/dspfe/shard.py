@@ -70,17 +70,16 @@ def gather_rows(rows, counts, idx, n_total, group=None):
     g_r = [torch.empty_like(pad_r) for _ in range(world)]
     dist.all_gather(g_i, pad_i, group=group); dist.all_gather(g_c, pad_c, group=group); dist.all_gather(g_r, pad_r, group=group)
     cnt = torch.zeros(n_total, dtype=torch.int64, device=dev)
+    n_u = [int(s[0]) for s in all_sizes]; n_r = [int(s[1]) for s in all_sizes]
     for r in range(world):
-        n = int(all_sizes[r][0])
-        cnt[g_i[r][:n]] = g_c[r][:n]
+        cnt[g_i[r][:n_u[r]]] = g_c[r][:n_u[r]]
     off = torch.zeros(n_total + 1, dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(cnt, 0)
     out = torch.empty((int(off[-1]), rows.shape[1]), dtype=rows.dtype, device=dev)
     for r in range(world):
-        n = int(all_sizes[r][0])
-        src = 0
-        for k in range(n):
-            u, c = int(g_i[r][k]), int(g_c[r][k])
-            out[int(off[u]): int(off[u]) + c] = g_r[r][src: src + c]
-            src += c
+        # destination of every source row of rank r: its utterance's first global row + its position inside the block
+        c, u = g_c[r][:n_u[r]], g_i[r][:n_u[r]]
+        src_start = torch.cumsum(c, 0) - c
+        dst = torch.repeat_interleave(off[u] - src_start, c) + torch.arange(n_r[r], device=dev)
+        out.index_copy_(0, dst, g_r[r][:n_r[r]])
     return out, off

@@ -44,7 +44,7 @@ def basic_endpoint_detection(sig, rate, return_feature=False):
     cfg_frame, cfg_step = _gpu.cfg_frame_step()
     x, f32 = _gpu.pack_one(sig)
     if f32:
-        raise NotImplementedError("endpoint detection is built for int16-valued PCM (what reader.py delivers)")
+        return _float_endpoint_detection(np.asarray(sig, dtype=np.float64), rate, cfg_frame, cfg_step, return_feature, False)
     plan = _gpu.endpoint_plan(int(rate), cfg_frame, cfg_step)
     off = np.array([0, len(x)], dtype=np.int64)
     if not return_feature:
@@ -61,10 +61,32 @@ def robust_endpoint_detection(sig, rate):
     cfg_frame, cfg_step = _gpu.cfg_frame_step()
     x, f32 = _gpu.pack_one(sig)
     if f32:
-        raise NotImplementedError("endpoint detection is built for int16-valued PCM (what reader.py delivers)")
+        return _float_endpoint_detection(np.asarray(sig, dtype=np.float64), rate, cfg_frame, cfg_step, False, True)
     plan = _gpu.endpoint_plan(int(rate), cfg_frame, cfg_step)
     lr = plan.detect_robust_host(x, np.array([0, len(x)], dtype=np.int64))
     return int(lr[0, 0]), int(lr[0, 1])
+
+
+def _float_endpoint_detection(sig, rate, cfg_frame, cfg_step, return_feature, robust):
+    """Signals that are not int16-valued (reference endpoint.py:34 takes any real dtype): the reference's own sequence of
+    calls (endpoint.py:40-66 / :71-92) over this module's device-backed pieces -- framing, per-frame amplitude and
+    zero-crossing kernels in float64, then the shared C++ rules.  The fused int16 kernels K2/K3 are the batch path."""
+    frames = to_frames(sig, rate, t=cfg_frame, step=cfg_step)  # noqa: F405
+    amp = get_amplitude(frames)
+    if robust:
+        sep_point = amplitude_rule(amp, 0.5, frames=frames, use_acr=True, rate=rate)
+    else:
+        sep_point = amplitude_rule(amp)
+        left, right = sep_point[0][0], sep_point[-1][1]
+        if right - left < 50:
+            sep_point = amplitude_rule(amp, 0.125)
+    left, right = sep_point[0][0], sep_point[-1][1]
+    zcr = get_zcr(frames)
+    left2, right2 = zcr_rule(zcr, left, right)
+    if right2 - left2 < 50:
+        left2, right2 = 0, len(frames)
+    lr = int(left2 * cfg_step * rate), int(right2 * cfg_step * rate)
+    return lr + (amp, zcr) if return_feature else lr
 
 
 def get_noise(amp, sep_point):

@@ -309,6 +309,72 @@ int dspfe_wav_scan_paths(const char* const* paths, int32_t n_files, int64_t* h_o
 int dspfe_ingest_wav_paths(const char* const* paths, int32_t n_files, int16_t* d_pcm, int64_t capacity, int64_t* h_offsets,
                            int32_t* h_rates, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole front-end over one packed ragged batch, as the reference's two callers chain it per utterance:
+ *   (l, r) = basic_endpoint_detection(sig, rate)                                   model.py:52-53, pitch_model.py:38
+ *   mfcc(sig[l:r]) + delta + delta (N = delta_n)                                   model.py:74-77
+ *   pitch_feature(preemphasis(sig, 0.97)[l:r], rate)  (cepstrum pitch + 5 floats)  pitch_model.py:39-41
+ *   pitch_detect_sr(sig[l:r], rate, winlen=cfg.frame, step=cfg.step)               model.py:92
+ * The batch is walked in slabs of consecutive utterances so that the pitch workspaces (about 3 KB per 10 ms of audio)
+ * stay bounded by the slab, whatever the batch size (BASELINE config 5).  Row / frame offsets in the outputs are global.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dspfe_frontend_plan dspfe_frontend_plan;
+
+typedef struct {
+    int32_t samplerate;        /* 16000 */
+    int32_t delta_n;           /* 2 */
+    int32_t acr_frame_len;     /* 300 = int(10000 * cfg.frame), model.py:92 */
+    int32_t reserved;
+    int64_t slab_samples;      /* device path: samples per slab, 0 = 256 Mi */
+    int64_t host_slab_samples; /* host path: samples per pipelined slab, 0 = 16 Mi */
+    double cep_preemph;        /* 0.97 (pitch_model.py:39) */
+} dspfe_frontend_params;
+
+/* Output arrays (device pointers for dspfe_frontend, host pointers for dspfe_frontend_host); any pointer may be NULL
+ * to skip that output's copy (the path still runs).  Capacities are in rows / frames and must cover the untrimmed
+ * bounds: dspfe_rows_bound / dspfe_pitch_frames_bound of the whole batch. */
+typedef struct {
+    int32_t* lr;               /* [n_utt,2] endpoints (left, right) */
+    float* mfcc;               /* [mfcc_cap, 39] */
+    int64_t mfcc_cap;
+    int64_t* mfcc_frame_off;   /* [n_utt+1] */
+    double* cep_pitch;         /* [cep_cap] Hz, cepstrum method */
+    int64_t cep_cap;
+    int64_t* cep_frame_off;    /* [n_utt+1] */
+    double* cep_feat;          /* [n_utt,5] pitch_feature */
+    double* acr_pitch;         /* [acr_cap] Hz, autocorrelation method */
+    int64_t acr_cap;
+    int64_t* acr_frame_off;    /* [n_utt+1] */
+    int32_t* cep_lag;          /* [cep_cap] 20 + argmax before the octave repair (optional) */
+    int32_t* acr_lag;          /* [acr_cap] (optional) */
+} dspfe_frontend_out;
+
+void dspfe_frontend_params_default(dspfe_frontend_params* p);
+int dspfe_frontend_create(const dspfe_frontend_params* p, dspfe_frontend_plan** plan);
+void dspfe_frontend_destroy(dspfe_frontend_plan* plan);
+/* capacities that hold any batch with these totals: caps[0] MFCC rows, caps[1] cepstrum frames, caps[2] autocorrelation frames */
+int dspfe_frontend_bounds(const dspfe_frontend_plan* plan, int64_t total_samples, int64_t n_utt, int64_t* caps);
+/* Device path: PCM and outputs resident.  h_offsets is the host copy of d_offsets (the slab boundaries are cut on the
+ * host).  totals[3] (host, optional) receives the MFCC rows / cepstrum frames / autocorrelation frames written.  The call
+ * waits for each slab's frame counts (one 24-byte read back per slab) and returns when the last slab has been queued on
+ * `stream` and counted, i.e. the outputs are complete when it returns. */
+int dspfe_frontend(dspfe_frontend_plan* plan, const int16_t* d_pcm, const int64_t* d_offsets, const int64_t* h_offsets,
+                   int32_t n_utt, const dspfe_frontend_out* d_out, int64_t* totals, void* stream);
+/* Host-buffer path: slabs are copied H2D, processed and copied back D2H on three internal streams, overlapped. */
+int dspfe_frontend_host(dspfe_frontend_plan* plan, const int16_t* h_pcm, const int64_t* h_offsets, int32_t n_utt,
+                        const dspfe_frontend_out* h_out, int64_t* totals);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-kernel timing for reports (bench.py): between dspfe_timing_begin(stream) and dspfe_timing_end every kernel the
+ * library launches on `stream` is bracketed by CUDA events.  dspfe_timing_end waits for the stream and writes up to
+ * `cap` records: names[i*48 .. ] = kernel name (NUL terminated, 48 bytes each), ms[i] = its duration; *n = records
+ * available.  dspfe_launch_count = kernels launched by the library since it was loaded.
+ * ---------------------------------------------------------------------------------------------- */
+int dspfe_timing_begin(void* stream);
+int dspfe_timing_end(char* names, float* ms, int32_t cap, int32_t* n);
+int64_t dspfe_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

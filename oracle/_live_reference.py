@@ -3,7 +3,7 @@
 Test infrastructure (see oracle/ref_features.py header).  Recipe from SURVEY.md §8c:
 stub matplotlib (plotter.py:8-10 imports it), run from a scratch cwd because
 config.py:42-47 creates ./log/<time>.txt at import, put the reference on sys.path.
-Never used on the GPU box: /root/reference does not exist there.
+On the GPU box /root/reference does not exist; bench.py's CPU legs find the copy under baseline/_ref/ instead.
 """
 import contextlib
 import io
@@ -13,7 +13,17 @@ import tempfile
 import types
 import warnings
 
-REF_DIR = os.environ.get("DSP_REF_DIR", "/root/reference")
+def _find():
+    """$DSP_REF_DIR, else /root/reference (CPU container), else baseline/_ref/ (oracle/install_reference.py's copy: the
+    only one that exists on the GPU box, used by bench.py's CPU legs alone)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in (os.environ.get("DSP_REF_DIR"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if d and os.path.isdir(os.path.join(d, "features")):
+            return d
+    return "/root/reference"
+
+
+REF_DIR = _find()
 
 
 def available():

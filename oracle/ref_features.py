@@ -127,11 +127,9 @@ def window(sig, rate, low_freq=0, high_freq=500, wintype="square"):
     h = fir_taps(N, rate, low_freq, high_freq, wintype)
     if sig.ndim == 1:
         return np.convolve(sig, h)[:N]
-    # batched: y[f, n] = sum_{m<=n} sig[f, m] * h[n-m]  (lower-triangular Toeplitz)
-    n = np.arange(N)
-    d = n[None, :] - n[:, None]  # [m, n] -> n - m
-    T = np.where(d >= 0, h[np.clip(d, 0, N - 1)], 0)
-    return sig.astype(np.complex128) @ T
+    # batched: y[f, n] = sum_{m<=n} sig[f, m] * h[n-m], the first N samples of the linear convolution, evaluated through a
+    # zero-padded 2N-point transform (equal to np.convolve to ~1e-16 relative; validated against the live reference)
+    return np.fft.ifft(np.fft.fft(sig, 2 * N, axis=-1) * np.fft.fft(h, 2 * N), axis=-1)[..., :N]
 
 
 def acr(frame, n):
@@ -512,6 +510,18 @@ def robust_max_pitch(g, bias=20):
     return pitch
 
 
+def robust_pitch_from_lags(lags):
+    """robust_max_pitch (pitch.py:191-206) restarted from integer lags (= bias + argmax): Hz per frame."""
+    pitch = [1 / (0.0001 * int(l)) for l in lags]
+    for i in range(1, len(pitch)):
+        if abs(2 * pitch[i] - pitch[i - 1]) < 50 and pitch[i] < 170:
+            pitch[i] = 2 * pitch[i]
+    for i in range(len(pitch) - 2, 0, -1):
+        if abs(2 * pitch[i] - pitch[i + 1]) < 50 and pitch[i] < 170:
+            pitch[i] = 2 * pitch[i]
+    return pitch
+
+
 def dp_max_pitch(g):
     """pitch.py:208-225 (Viterbi over lags; never called on the path)."""
     g = np.array(g)
@@ -565,6 +575,54 @@ def pitch_detect_sr(sig, rate, winlen=0.0512, step=0.01):
     """pitch.py:96-110: autocorrelation pitch."""
     scores, frames = pitch_scores_sr(sig, rate, winlen, step)
     return robust_max_pitch(scores, bias=20), frames
+
+
+def pitch_rows_cep(sig, rate, winlen=0.0512, step=0.01):
+    """The smoothed cepstrum rows peak_score sees inside pitch_detect (pitch.py:83-91): float64 [F, N]."""
+    sig = downsampling(sig, rate, 10000)
+    frames = to_frames(sig, 10000, winlen, step)
+    return np.asarray(smooth(pitch_detect_frame(center_clip(frames, False), 10000)))
+
+
+def peak_score_bounds(row, tol, min_f=20, max_f=100):
+    """peak_score (pitch.py:227-242) with every comparison `row[j] <= v` moved by -tol / +tol: (lo, hi) integer score bounds
+    that any evaluation of the row perturbed by less than tol / 2 per sample must respect.  Checker for float32 near-ties."""
+    row = np.asarray(row, dtype=np.float64)
+    n = len(row)
+    lo, hi = [], []
+    for i in range(min_f, max_f):
+        v = row[i]
+        out = []
+        for t in (-tol, tol):
+            with np.errstate(invalid="ignore"):
+                stop = ~(row <= v + t)
+            stop[i] = False
+            left = np.nonzero(stop[1:i + 1])[0]
+            p = (left[-1] + 1) if len(left) else 0
+            right = np.nonzero(stop[i:])[0]
+            q = (right[0] + i) if len(right) else n
+            out.append(int(min(i - p, q - i)))
+        lo.append(out[0]); hi.append(out[1])
+    return np.array(lo), np.array(hi)
+
+
+def lag_is_near_tie_cep(row, lag, rel_tol=1e-5, bias=20):
+    """True when `lag` (= bias + argmax of some float32 evaluation of peak_score(row)) is explained by a near-tie of the
+    float64 row: its upper score bound reaches the largest lower bound (north_star: mismatches are allowed only where the
+    reference statistic lies within tolerance of the decision threshold)."""
+    row = np.asarray(row, dtype=np.float64)
+    if not np.all(np.isfinite(row)):
+        return False
+    lo, hi = peak_score_bounds(row, rel_tol * float(np.max(np.abs(row))))
+    return bool(hi[int(lag) - bias] >= lo.max())
+
+
+def lag_is_near_tie_sr(row, lag, rel_tol=1e-5, bias=20):
+    """Autocorrelation rows (pitch.py:96-110): the chosen lag's smoothed score lies within rel_tol * max|row| of the maximum."""
+    row = np.asarray(row, dtype=np.float64)
+    if not np.all(np.isfinite(row)):
+        return False
+    return bool(row[int(lag) - bias] >= row.max() - rel_tol * float(np.max(np.abs(row))))
 
 
 def sub_endpoint_detect(frames):

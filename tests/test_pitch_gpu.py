@@ -1,14 +1,14 @@
 """GPU parity tests of the pitch kernels (K4a/K4b/K5/K6) through the C ABI.
 
-Contract (BASELINE.json north_star): pitch-peak lags are exact except where a float32 near-tie moves
-an integer peak score; such frames are counted and bounded.  pitch_feature floats: 1e-6 relative on utterances whose
-lags are all exact."""
+Contract (BASELINE.json north_star): pitch-peak lags are exact except where the reference statistic lies
+within tolerance of the decision threshold; such frames are counted (tests/pitchcheck.py) and every other difference
+fails.  pitch_feature floats: 1e-6 relative on utterances whose lags are all exact."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+import pitchcheck
 
-LAG_MISMATCH_BUDGET = 0.01   # fraction of frames whose Hz value may differ from the float64 reference
+pytestmark = pytest.mark.gpu
 
 
 def pack(xs):
@@ -56,15 +56,12 @@ def test_ragged_batch_vs_oracle(method):
     lengths[:6] = [1, 700, 1000, 819, 8001, 110000]   # the last one exceeds the feature kernel's staged frame count
     pcm, off = synth.synth_batch(lengths, seed0=4200)
     pitch, lag, fo = dspfe.PitchPlan(method=method).detect_host(pcm, off)
-    ref_fn = O.pitch_detect if method == 0 else O.pitch_detect_sr
-    bad = tot = 0
+    tot = np.zeros(3, dtype=np.int64)
     for u in range(len(lengths)):
-        want, _ = ref_fn(pcm[off[u]:off[u + 1]], 16000)
-        got = pitch[fo[u]:fo[u + 1]]
-        assert len(got) == len(want), u
-        bad += int(np.sum(got != np.asarray(want))); tot += len(want)
-    print(f"method {method}: {bad} of {tot} frames differ")
-    assert bad <= LAG_MISMATCH_BUDGET * tot
+        tot += pitchcheck.check_lags(method, pcm[off[u]:off[u + 1]], 16000, lag[fo[u]:fo[u + 1]], pitch[fo[u]:fo[u + 1]],
+                                     what=f"method {method} utterance {u}")
+    pitchcheck.record(f"ragged_batch_vs_oracle[{method}]", *tot)
+    assert tot[1] <= 0.02 * tot[0], f"{tot[1]} of {tot[0]} frames are near-ties: the kernel's float32 error is larger than designed"
 
 
 def test_rows_tap_matches_reference_cepstrum_and_acr():
@@ -188,17 +185,18 @@ def test_config3_full_size_properties():
     assert torch.equal(sub["pitch"][: fo[b] - fo[a]], o["pitch"][fo[a]:fo[b]])
     # sampled oracle parity
     feat = o["feat"].cpu().numpy()
-    bad = tot = 0
+    tot = np.zeros(3, dtype=np.int64)
     for u in (0, 1, 777, 2048, 4095):
         x = pcm[off_h[u]:off_h[u + 1]].cpu().numpy()
         l, r = int(lr_h[u, 0]), int(lr_h[u, 1])
         sig = O.preemphasis(x, 0.97)[l:r]
-        want, _ = O.pitch_detect(sig, 16000)
-        got = pitch[fo[u]:fo[u + 1]]
-        bad += int(np.sum(got != np.asarray(want))); tot += len(want)
-        if np.array_equal(got, want) and len(want) > 40:
+        c = pitchcheck.check_lags(0, sig, 16000, lag[fo[u]:fo[u + 1]], pitch[fo[u]:fo[u + 1]], what=f"config 3 utterance {u}")
+        tot += c
+        if c[1] == 0 and c[0] > 40:
             np.testing.assert_allclose(feat[u], O.pitch_feature(sig, 16000), rtol=1e-6, atol=1e-9)
-    assert bad <= LAG_MISMATCH_BUDGET * tot, f"{bad} of {tot}"
+        tot += pitchcheck.check_lags(1, x, 16000, lag2[fo2[u]:fo2[u + 1]], acr["pitch"][fo2[u]:fo2[u + 1]].cpu().numpy(),
+                                     what=f"config 3 autocorrelation utterance {u}")
+    pitchcheck.record("config3_full_size", *tot)
 
 
 @pytest.mark.parametrize("rate", [8000, 44100, 48000])
@@ -214,10 +212,8 @@ def test_other_sample_rates(rate):
         plan = dspfe.PitchPlan(method=method, samplerate=rate)
         plan.reserve(len(lengths), len(pcm))
         pitch, lag, fo = plan.detect_host(pcm, off)
-        bad = tot = 0
+        tot = np.zeros(3, dtype=np.int64)
         for u in range(len(lengths)):
-            want, _ = fn(pcm[off[u]:off[u + 1]], rate)
-            got = pitch[fo[u]:fo[u + 1]]
-            assert len(got) == len(want)
-            bad += int(np.sum(got != np.asarray(want))); tot += len(want)
-        assert bad <= max(1, LAG_MISMATCH_BUDGET * tot), (rate, method, bad, tot)
+            tot += pitchcheck.check_lags(method, pcm[off[u]:off[u + 1]], rate, lag[fo[u]:fo[u + 1]], pitch[fo[u]:fo[u + 1]],
+                                         what=f"rate {rate} method {method} utterance {u}")
+        pitchcheck.record(f"other_sample_rates[{rate},{method}]", *tot)
