@@ -133,8 +133,6 @@ int dspfe_endpoint_create(const dspfe_endpoint_params* p, dspfe_endpoint_plan** 
     if (!pl) return fail(DSPFE_ERR_NOMEM, "out of host memory");
     pl->prm = *p;
     int rc = fill_rule(*p, pl->rule, pl->frame_len, pl->frame_step);
-    if (!rc && pl->frame_step > pl->frame_len)
-        rc = fail(DSPFE_ERR_UNSUPPORTED, "cfg.step greater than cfg.frame (gaps between frames) is not built: the frame bounds assume overlapping or abutting frames");
     if (rc) { delete pl; return rc; }
     pl->q = pl->frame_len / pl->frame_step; pl->rem = pl->frame_len % pl->frame_step;
     *plan = pl;
@@ -151,7 +149,7 @@ void dspfe_endpoint_destroy(dspfe_endpoint_plan* pl) {
 
 int dspfe_endpoint_reserve(dspfe_endpoint_plan* pl, int64_t max_utt, int64_t max_total_samples) {
     if (!pl || max_utt < 0 || max_total_samples < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
-    const int64_t frames = max_total_samples / pl->frame_step + max_utt;
+    const int64_t frames = dspfe_endpoint_frames_bound(pl, max_total_samples, max_utt);
     return ensure(pl, max_utt, frames + max_utt * (pl->q + 1), frames);
 }
 
@@ -160,7 +158,9 @@ int32_t dspfe_endpoint_frame_step(const dspfe_endpoint_plan* pl) { return pl ? p
 
 int64_t dspfe_endpoint_frames_bound(const dspfe_endpoint_plan* pl, int64_t total_samples, int64_t n_utt) {
     if (!pl) return -1;
-    return total_samples / pl->frame_step + n_utt;
+    // framesig's count is 1 + ceil((len - frame_len) / step) <= len / step + 1 per utterance when frame_len >= step, and
+    // <= len / step + 2 when cfg.step exceeds cfg.frame (gaps between frames)
+    return total_samples / pl->frame_step + (pl->frame_len >= pl->frame_step ? 1 : 2) * n_utt;
 }
 
 int dspfe_endpoint(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets, int32_t n_utt,

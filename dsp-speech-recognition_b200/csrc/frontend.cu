@@ -27,13 +27,15 @@ __global__ void fe_rel_offsets_kernel(const int64_t* off, int n, int64_t a0, int
 // slab's totals
 struct FeFinish {
     const int64_t* loc[3]; int64_t* glob[3]; int64_t base[3]; int64_t* tot; int n;   // n = utterances + 1
+    const int64_t* dbase_in; int64_t* dbase_out;   // host path: the bases live on the device (no host round trip per slab)
 };
 __global__ void fe_finish_kernel(const FeFinish f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        if (i < f.n && f.glob[k]) f.glob[k][i] = f.base[k] + f.loc[k][i];
-        if (i == 0) f.tot[k] = f.loc[k][f.n - 1];
+        const int64_t base = f.dbase_in ? f.dbase_in[k] : f.base[k];
+        if (i < f.n && f.glob[k]) f.glob[k][i] = base + f.loc[k][i];
+        if (i == 0) { f.tot[k] = f.loc[k][f.n - 1]; if (f.dbase_out) f.dbase_out[k] = base + f.loc[k][f.n - 1]; }
     }
 }
 
@@ -55,7 +57,7 @@ struct dspfe_frontend_plan {
     dspfe_frontend_params prm;
     dspfe_endpoint_plan* ep = nullptr; dspfe_plan* mf = nullptr; dspfe_pitch_plan* cep = nullptr; dspfe_pitch_plan* acr = nullptr;
     int64_t* rel_off = nullptr; int64_t* loc_off[3] = {nullptr, nullptr, nullptr}; int64_t cap_utt = 0;
-    int64_t* d_tot = nullptr; int64_t* h_tot = nullptr;
+    int64_t* d_tot = nullptr; int64_t* h_tot = nullptr;     // d_tot [3] slab totals | [2][3] device-side bases; h_tot pinned [kFeSlots][3]
     // scratch for outputs the caller does not want
     int32_t* s_lr = nullptr; int64_t cap_slr = 0;
     float* s_mfcc = nullptr; int64_t cap_smfcc = 0;
@@ -91,7 +93,8 @@ int ensure_utt(dspfe_frontend_plan* pl, int64_t n) {
 // the slab's kernels on `st`: endpoints -> MFCC -> cepstrum pitch + pitch_feature -> autocorrelation pitch -> offsets
 int run_slab(dspfe_frontend_plan* pl, const int16_t* pcm, int64_t total, const int64_t* rel_off, int32_t nu, int32_t* lr,
              float* mfcc, int64_t mfcc_cap, double* cep, int32_t* cep_lag, int64_t cep_cap, double* feat, double* acr, int32_t* acr_lag,
-             int64_t acr_cap, int64_t* const glob[3], const int64_t base[3], cudaStream_t st) {
+             int64_t acr_cap, int64_t* const glob[3], const int64_t base[3], cudaStream_t st, const int64_t* dbase_in = nullptr,
+             int64_t* dbase_out = nullptr, int64_t* h_tot = nullptr) {
     int rc = dspfe_endpoint(pl->ep, pcm, total, rel_off, nu, lr, nullptr, nullptr, nullptr, 0, st);
     if (rc) return rc;
     rc = dspfe_mfcc_delta(pl->mf, pcm, total, rel_off, lr, nu, mfcc, mfcc_cap, pl->loc_off[0], st);
@@ -102,10 +105,10 @@ int run_slab(dspfe_frontend_plan* pl, const int16_t* pcm, int64_t total, const i
     if (rc) return rc;
     FeFinish f;
     for (int k = 0; k < 3; ++k) { f.loc[k] = pl->loc_off[k]; f.glob[k] = glob[k]; f.base[k] = base[k]; }
-    f.tot = pl->d_tot; f.n = nu + 1;
+    f.tot = pl->d_tot; f.n = nu + 1; f.dbase_in = dbase_in; f.dbase_out = dbase_out;
     fe_finish_kernel<<<(unsigned)((nu + 1 + 255) / 256), 256, 0, st>>>(f);
     LAUNCH_CHECK("fe_finish_kernel", st);
-    CUDA_TRY(cudaMemcpyAsync(pl->h_tot, pl->d_tot, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_tot ? h_tot : pl->h_tot, pl->d_tot, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     return DSPFE_OK;
 }
 
@@ -155,7 +158,7 @@ int dspfe_frontend_create(const dspfe_frontend_params* q, dspfe_frontend_plan** 
     if (!pl) return fail(DSPFE_ERR_NOMEM, "out of host memory");
     pl->prm = *q;
     if (pl->prm.slab_samples == 0) pl->prm.slab_samples = 256ll << 20;
-    if (pl->prm.host_slab_samples == 0) pl->prm.host_slab_samples = 16ll << 20;
+    if (pl->prm.host_slab_samples == 0) pl->prm.host_slab_samples = 32ll << 20;
     dspfe_endpoint_params eq; dspfe_endpoint_params_default(&eq, q->samplerate);
     dspfe_mfcc_params mq; dspfe_mfcc_params_default(&mq);
     mq.samplerate = q->samplerate; mq.delta_n = q->delta_n;
@@ -168,8 +171,8 @@ int dspfe_frontend_create(const dspfe_frontend_params* q, dspfe_frontend_plan** 
     if (!rc) rc = dspfe_plan_create(&mq, &pl->mf);
     if (!rc) rc = dspfe_pitch_create(&cq, &pl->cep);
     if (!rc) rc = dspfe_pitch_create(&aq, &pl->acr);
-    if (!rc && cudaMalloc(&pl->d_tot, 3 * sizeof(int64_t)) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaMalloc failed");
-    if (!rc && cudaHostAlloc(&pl->h_tot, 3 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaHostAlloc failed");
+    if (!rc && cudaMalloc(&pl->d_tot, 9 * sizeof(int64_t)) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaMalloc failed");
+    if (!rc && cudaHostAlloc(&pl->h_tot, kFeSlots * 3 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaHostAlloc failed");
     if (rc) { const std::string keep = g_err; dspfe_frontend_destroy(pl); g_err = keep; return rc; }
     *plan = pl;
     return DSPFE_OK;
@@ -266,6 +269,7 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
             CUDA_TRY(cudaHostAlloc(&sl.h_rel, cap * sizeof(int64_t), cudaHostAllocDefault));
             sl.cap_utt = cap;
         }
+        CUDA_TRY(cudaEventSynchronize(sl.h2d_done));                               // the slot's previous offsets have left h_rel
         for (int32_t i = 0; i <= nu; ++i) sl.h_rel[i] = h_off[u0 + i] - a0;
         // (a0 - base0 .. ) may start before h_off[u0]: those samples belong to the previous utterance and exist in h_pcm
         if (total > 0) CUDA_TRY(cudaMemcpyAsync(sl.d_pcm, h_pcm + a0, total * sizeof(int16_t), cudaMemcpyHostToDevice, pl->s_copy));
@@ -273,7 +277,39 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
         CUDA_TRY(cudaEventRecord(sl.h2d_done, pl->s_copy));
         return DSPFE_OK;
     };
+    // The kernels of slab s are queued without waiting for slab s - 1: the running row / frame bases live on the device
+    // (d_tot[3 + 3 * (s & 1)], written by the previous slab's last kernel).  The host only needs a slab's totals to size its
+    // D2H copies, and drains slab s - 1 after queuing slab s, so the GPU never waits for the host.
     int64_t base[3] = {0, 0, 0};
+    const int64_t zero3[3] = {0, 0, 0};
+    CUDA_TRY(cudaMemsetAsync(pl->d_tot + 3, 0, 3 * sizeof(int64_t), pl->s_compute));
+    auto drain = [&](int s) -> int {
+        FeSlot& sl = pl->slots[s % kFeSlots];
+        const int32_t u0 = cut[s], nu = cut[s + 1] - u0;
+        CUDA_TRY(cudaEventSynchronize(sl.compute_done));                           // the slab's frame counts are in its h_tot
+        const int64_t* ht = pl->h_tot + 3 * (s % kFeSlots);
+        const int64_t t0 = ht[0], t1 = ht[1], t2 = ht[2];
+        cudaStream_t so = pl->s_out;
+        CUDA_TRY(cudaStreamWaitEvent(so, sl.compute_done, 0));
+        if (o->lr) CUDA_TRY(cudaMemcpyAsync(o->lr + 2 * (int64_t)u0, sl.d_lr, (int64_t)nu * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+        if (o->mfcc) {
+            if (base[0] + t0 > o->mfcc_cap) return fail(DSPFE_ERR_INVALID_ARG, "h_out->mfcc capacity too small");
+            CUDA_TRY(cudaMemcpyAsync(o->mfcc + base[0] * kFeWidth, sl.d_mfcc, t0 * kFeWidth * sizeof(float), cudaMemcpyDeviceToHost, so));
+        }
+        if ((o->cep_pitch || o->cep_lag) && base[1] + t1 > o->cep_cap) return fail(DSPFE_ERR_INVALID_ARG, "h_out cepstrum capacity too small");
+        if ((o->acr_pitch || o->acr_lag) && base[2] + t2 > o->acr_cap) return fail(DSPFE_ERR_INVALID_ARG, "h_out autocorrelation capacity too small");
+        if (o->cep_pitch) CUDA_TRY(cudaMemcpyAsync(o->cep_pitch + base[1], sl.d_cep, t1 * sizeof(double), cudaMemcpyDeviceToHost, so));
+        if (o->acr_pitch) CUDA_TRY(cudaMemcpyAsync(o->acr_pitch + base[2], sl.d_acr, t2 * sizeof(double), cudaMemcpyDeviceToHost, so));
+        if (o->cep_lag) CUDA_TRY(cudaMemcpyAsync(o->cep_lag + base[1], sl.d_cep_lag, t1 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+        if (o->acr_lag) CUDA_TRY(cudaMemcpyAsync(o->acr_lag + base[2], sl.d_acr_lag, t2 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+        if (o->cep_feat) CUDA_TRY(cudaMemcpyAsync(o->cep_feat + 5 * (int64_t)u0, sl.d_feat, (int64_t)nu * 5 * sizeof(double), cudaMemcpyDeviceToHost, so));
+        int64_t* hg[3] = {o->mfcc_frame_off, o->cep_frame_off, o->acr_frame_off};
+        for (int k = 0; k < 3; ++k)
+            if (hg[k]) CUDA_TRY(cudaMemcpyAsync(hg[k] + u0, sl.d_goff[k], (int64_t)(nu + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, so));
+        CUDA_TRY(cudaEventRecord(sl.d2h_done, so));
+        base[0] += t0; base[1] += t1; base[2] += t2;
+        return DSPFE_OK;
+    };
     int rc = issue_h2d(0);
     if (rc) return rc;
     for (int s = 0; s < n_slab; ++s) {
@@ -291,35 +327,15 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
         rc = ensure_utt(pl, nu + 1); if (rc) return rc;
         CUDA_TRY(cudaStreamWaitEvent(pl->s_compute, sl.h2d_done, 0));
         rc = run_slab(pl, sl.d_pcm, total, sl.d_rel, nu, sl.d_lr, sl.d_mfcc, need0, sl.d_cep, o->cep_lag ? sl.d_cep_lag : nullptr, need1, sl.d_feat, sl.d_acr,
-                      o->acr_lag ? sl.d_acr_lag : nullptr, need2, sl.d_goff, base, pl->s_compute);
+                      o->acr_lag ? sl.d_acr_lag : nullptr, need2, sl.d_goff, zero3, pl->s_compute, pl->d_tot + 3 + 3 * (s & 1), pl->d_tot + 3 + 3 * ((s + 1) & 1),
+                      pl->h_tot + 3 * (s % kFeSlots));
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(sl.compute_done, pl->s_compute));
         if (s + 1 < n_slab) { rc = issue_h2d(s + 1); if (rc) return rc; }          // overlaps this slab's kernels
-        CUDA_TRY(cudaStreamSynchronize(pl->s_compute));                            // the slab's frame counts are in h_tot
-        const int64_t t0 = pl->h_tot[0], t1 = pl->h_tot[1], t2 = pl->h_tot[2];
-        cudaStream_t so = pl->s_out;                                               // (ordered after the kernels by the wait above)
-        if (o->lr) CUDA_TRY(cudaMemcpyAsync(o->lr + 2 * (int64_t)u0, sl.d_lr, (int64_t)nu * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
-        if (o->mfcc) {
-            if (base[0] + t0 > o->mfcc_cap) return fail(DSPFE_ERR_INVALID_ARG, "h_out->mfcc capacity too small");
-            CUDA_TRY(cudaMemcpyAsync(o->mfcc + base[0] * kFeWidth, sl.d_mfcc, t0 * kFeWidth * sizeof(float), cudaMemcpyDeviceToHost, so));
-        }
-        if (o->cep_pitch) {
-            if (base[1] + t1 > o->cep_cap) return fail(DSPFE_ERR_INVALID_ARG, "h_out->cep_pitch capacity too small");
-            CUDA_TRY(cudaMemcpyAsync(o->cep_pitch + base[1], sl.d_cep, t1 * sizeof(double), cudaMemcpyDeviceToHost, so));
-        }
-        if (o->acr_pitch) {
-            if (base[2] + t2 > o->acr_cap) return fail(DSPFE_ERR_INVALID_ARG, "h_out->acr_pitch capacity too small");
-            CUDA_TRY(cudaMemcpyAsync(o->acr_pitch + base[2], sl.d_acr, t2 * sizeof(double), cudaMemcpyDeviceToHost, so));
-        }
-        if (o->cep_lag) CUDA_TRY(cudaMemcpyAsync(o->cep_lag + base[1], sl.d_cep_lag, t1 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
-        if (o->acr_lag) CUDA_TRY(cudaMemcpyAsync(o->acr_lag + base[2], sl.d_acr_lag, t2 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
-        if (o->cep_feat) CUDA_TRY(cudaMemcpyAsync(o->cep_feat + 5 * (int64_t)u0, sl.d_feat, (int64_t)nu * 5 * sizeof(double), cudaMemcpyDeviceToHost, so));
-        int64_t* hg[3] = {o->mfcc_frame_off, o->cep_frame_off, o->acr_frame_off};
-        for (int k = 0; k < 3; ++k)
-            if (hg[k]) CUDA_TRY(cudaMemcpyAsync(hg[k] + u0, sl.d_goff[k], (int64_t)(nu + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, so));
-        CUDA_TRY(cudaEventRecord(sl.d2h_done, so));
-        base[0] += t0; base[1] += t1; base[2] += t2;
+        if (s >= 1) { rc = drain(s - 1); if (rc) return rc; }                      // (that slab finished while this one was being queued)
     }
+    rc = drain(n_slab - 1);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(pl->s_out));
     if (totals) for (int k = 0; k < 3; ++k) totals[k] = base[k];
     return DSPFE_OK;

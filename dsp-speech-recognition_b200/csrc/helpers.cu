@@ -27,7 +27,7 @@ __global__ void frames_kernel(const double* sig, int64_t n, int frame_len, int f
 __global__ void preemph_kernel(const double* x, int64_t n, double coeff, double* y) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    y[i] = i == 0 ? x[0] : x[i] - coeff * x[i - 1];
+    y[i] = i == 0 ? x[0] : __dsub_rn(x[i], __dmul_rn(coeff, x[i - 1]));   // product rounded first, as NumPy does (no FMA contraction): bit-exact
 }
 
 // numpy's pairwise sum for any n, evaluated without recursion (explicit stack of pending right halves)

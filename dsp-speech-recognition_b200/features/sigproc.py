@@ -76,7 +76,7 @@ def _spectrum(frames, NFFT, kind):
     if NFFT != 512:
         raise NotImplementedError("only NFFT=512 is built (SURVEY f-2 lists the other sizes)")
     if numpy.shape(frames)[1] > NFFT:
-        logging.warn('frame length (%d) is greater than FFT size (%d), frame will be truncated. Increase NFFT to avoid.',
+        logging.warning('frame length (%d) is greater than FFT size (%d), frame will be truncated. Increase NFFT to avoid.',
                      numpy.shape(frames)[1], NFFT)
         frames = frames[:, :NFFT]
     nf, L = frames.shape

@@ -327,7 +327,7 @@ typedef struct {
     int32_t acr_frame_len;     /* 300 = int(10000 * cfg.frame), model.py:92 */
     int32_t reserved;
     int64_t slab_samples;      /* device path: samples per slab, 0 = 256 Mi */
-    int64_t host_slab_samples; /* host path: samples per pipelined slab, 0 = 16 Mi */
+    int64_t host_slab_samples; /* host path: samples per pipelined slab, 0 = 32 Mi */
     double cep_preemph;        /* 0.97 (pitch_model.py:39) */
 } dspfe_frontend_params;
 

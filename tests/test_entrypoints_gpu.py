@@ -170,5 +170,15 @@ def test_step_longer_than_frame_is_rejected():
         features.mfcc(x, winlen=0.01, winstep=0.025)
     with pytest.raises(NotImplementedError):
         features.mfcc(x, winlen=0.01, winstep=0.025, nfft=1536)
-    with pytest.raises(NotImplementedError):
-        dspfe.EndpointPlan(cfg_frame=0.01, cfg_step=0.03)
+    # the endpoint path does take cfg.step > cfg.frame (its frame bound counts two frames per utterance then)
+    from dspfe import synth
+    from oracle import ref_features as O
+    lengths = [16300, 8000, 16001, 159, 161]
+    pcm, off = synth.synth_batch(lengths, seed0=77)
+    lr, asum, zcr, fo = dspfe.EndpointPlan(cfg_frame=0.01, cfg_step=0.025).detect_host(pcm, off, want_features=True)
+    for u in range(len(lengths)):
+        xs = pcm[off[u]:off[u + 1]]
+        l, r, amp, z = O.basic_endpoint_detection(xs, 16000, return_feature=True, cfg_frame=0.01, cfg_step=0.025)
+        assert (int(lr[u, 0]), int(lr[u, 1])) == (l, r)
+        np.testing.assert_array_equal(zcr[fo[u]:fo[u + 1]], np.array(z))
+        np.testing.assert_array_equal(asum[fo[u]:fo[u + 1]] / 160.0, np.array(amp))
