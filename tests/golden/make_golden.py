@@ -162,7 +162,39 @@ def gold_pitch():
     save("pitch", **a)
 
 
+def gold_model():
+    """SURVEY row f-1 pinned on the live caller: model.py's own _ModelBase.endpoint_detect (:52-64), feature_extract_mfcc
+    (:66-88) and pad_batch (:35-50) run on synthetic utterances; the batch is assembled as get_batch_full (:114-135) does
+    (its last two lines only move the arrays into a float32 torch tensor [T, B, 39])."""
+    import os as _os
+    cwd = _os.getcwd()
+    _os.chdir(_os.environ.get("TMPDIR", "/tmp"))          # config.py writes ./log at import
+    try:
+        with live.quiet():
+            import model as ref_model                      # the reference's model.py (torch imports included)
+    finally:
+        _os.chdir(cwd)
+    mb = object.__new__(ref_model._ModelBase)              # __init__ wants the data directory; the methods do not
+    a = {}
+    lengths = [16000, 52000, 9000, 33333, 70000, 24000, 120000]      # the last one keeps more than 200 frames: truncation
+    sounds, feats, len0 = [], [], []
+    for i, n in enumerate(lengths):
+        x = synth.synth_utterance(640 + i, n)
+        a[f"u{i}/x"] = x
+        with live.quiet():
+            sound = mb.endpoint_detect(x, 16000)
+            (m0, m1, m2), l = mb.feature_extract_mfcc(sound, 16000)
+        feats.append((m0, m1, m2)); len0.append(l)
+    with live.quiet():
+        cols = [mb.pad_batch(list(c)).transpose(1, 0, 2) for c in zip(*feats)]      # [T, B, 13] each
+    a["inp"] = np.concatenate(cols, axis=2).astype(np.float64)
+    a["len0"] = np.array(len0)
+    a["n"] = np.array(len(lengths))
+    save("model", **a)
+
+
 if __name__ == "__main__":
+    gold_model()
     gold_mfcc()
     gold_helpers()
     gold_endpoint()

@@ -168,6 +168,38 @@ def test_model_batch_epilogue_cmvn_pad():
         assert not got[n:, u].any()                                      # zero padding beyond the utterance
 
 
+def test_model_batch_golden_on_the_trainer_config(golden):
+    """SURVEY row f-1 on top of f-2, the only combination model.py uses: the golden is the live model.py's own
+    endpoint_detect (:52-64) -> feature_extract_mfcc (:66-88: mfcc(sound.reshape(1,-1), winlen=cfg.frame, winstep=cfg.step,
+    nfft=1536, winfunc=np.hamming), delta(., 3) twice, scale) -> pad_batch (:35-50) -> [T, B, 39] (tests/golden/make_golden.py).
+    Device chain: K2/K3 endpoints -> K1L on sig[l:r] (pre-emphasis off: the 2-D quirk) -> cmvn_pad_kernel.  The reference
+    scales the signal by its standard deviation first (model.py:62-63); that moves every log filterbank energy by one
+    constant, which the mean subtraction, the deltas and the per-column standardisation remove."""
+    import torch
+    import dspfe
+    g = golden("model")
+    n = int(g["n"])
+    xs = [g[f"u{i}/x"] for i in range(n)]
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in xs], out=off[1:])
+    pcm = np.concatenate(xs)
+    dev = torch.device("cuda:0")
+    pcm_d, off_d = torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev)
+    lr = dspfe.EndpointPlan().detect(pcm_d, off_d)
+    plan = dspfe.MfccPlan(frame_len=480, frame_step=160, nfft=1536, window=np.hamming(480), preemph=0.0, delta_n=3)
+    feat, fo = plan.mfcc_delta(pcm_d, off_d, trim=lr)
+    inp, len0 = dspfe.cmvn_pad_batch(feat, fo)
+    torch.cuda.synchronize()
+    want = g["inp"]
+    assert inp.shape == want.shape == (200, n, 39)
+    np.testing.assert_array_equal(len0.cpu().numpy(), g["len0"])
+    assert g["len0"].max() == 200 and (np.diff(fo.cpu().numpy()) > 200).any()        # the truncation branch of model.py:38-39 is exercised
+    got = inp.cpu().numpy()
+    assert np.max(np.abs(got - want) / (1 + np.abs(want))) <= 2e-4
+    for u, k in enumerate(g["len0"]):
+        assert not got[k:, u].any()
+
+
 def test_nfft1536_long_frames_dropin_and_batch():
     """model.py:74's call, through the drop-in API and through the batched plan."""
     import torch

@@ -125,3 +125,12 @@ def test_pitch_end_to_end(golden):
         assert (l, r) == tuple(g[f"u{i}/lr"])
         y = O.preemphasis(x, 0.97)
         np.testing.assert_allclose(O.pitch_feature(y[l:r], 16000), g["pitch_feature"][i], rtol=1e-7, atol=1e-9)
+
+
+def test_model_batch_pinned_on_live_model_py(golden):
+    """oracle.model_batch (restated model.py:35-88,114-135 glue) against the live model.py's output."""
+    g = golden("model")
+    utts = [g[f"u{i}/x"] for i in range(int(g["n"]))]
+    inp, len0 = O.model_batch(utts, N=3, winlen=0.03, winstep=0.01, nfft=1536, preemph=0, winfunc=np.hamming)
+    np.testing.assert_array_equal(len0, g["len0"])
+    np.testing.assert_allclose(inp, g["inp"], rtol=0, atol=1e-11)
