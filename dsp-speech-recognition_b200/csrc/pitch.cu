@@ -74,14 +74,16 @@ template <int MODE>
 __global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
+    constexpr int kPer = MODE == 2 ? 4 : 2;                              // frames per warp: a quad (pitch_acr_quad) or a pair
     const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
-    if (2 * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // surplus CTAs leave before touching the tables
+    if (kPer * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // surplus CTAs leave before touching the tables
     for (int i = threadIdx.x; i < kTabMod; i += blockDim.x) tws[i] = p.tab[i];
     __syncthreads();
     const int w = threadIdx.x >> 5;
-    const int64_t g0 = 2 * ((int64_t)blockIdx.x * kPitchWarps + w);
+    const int64_t g0 = kPer * ((int64_t)blockIdx.x * kPitchWarps + w);
     if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
-    pitch_fft_pair<MODE>(p, g0, total, smem + kTabMod * 8 + w * kWarpSmemBytes, tws, tws + kTabW32);
+    if (MODE == 2) pitch_acr_quad(p, g0, total, smem + kTabMod * 8 + w * kQuadWarpSmemBytes, tws, tws + kTabW32);
+    else pitch_fft_pair<(MODE == 2 ? 1 : MODE)>(p, g0, total, smem + kTabMod * 8 + w * kWarpSmemBytes, tws, tws + kTabW32);
 }
 
 __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid_constant__ PitchParams p) {
@@ -194,7 +196,7 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, track_smem(kCepLen));
     if (e != cudaSuccess) { cudaFree(pl->d_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
     b.tab = pl->d_tab;
@@ -267,7 +269,7 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     LAUNCH_CHECK("pitch_clip_kernel", st);
     const int fmode = p.mode == 0 ? 0 : (acr_short_frames(p.frame_len, p.row_len) ? 2 : 1);
     if (fmode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
-    else if (fmode == 2) pitch_frame_kernel<2><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
+    else if (fmode == 2) pitch_frame_kernel<2><<<(fgrid + 1) / 2, 32 * kPitchWarps, kQuadCtaSmem, st>>>(p);
     else pitch_frame_kernel<1><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     LAUNCH_CHECK(fmode == 0 ? "pitch_frame_kernel<0>" : fmode == 2 ? "pitch_frame_kernel<2>" : "pitch_frame_kernel<1>", st);
     if (d_pitch || d_lag || d_feat) {

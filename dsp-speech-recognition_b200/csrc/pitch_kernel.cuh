@@ -451,9 +451,9 @@ DEVFN void pitch_clip_pair(const PitchParams& p, int64_t g0, int64_t total, unsi
 // and for the cepstrum (pitch.py:135-143) the first inverse transform folds away:
 //     FFT512(y) = (Xe He + FFT512(W1024^-n IFFT512(Xo Ho))) / 2.
 // The transforms run as a rolled loop over stages (one copy of the routine in the instruction stream: the fully
-// inlined chain thrashed the instruction cache).  MODE 0 = cepstrum (5 transforms), 1 = autocorrelation (8), 2 = autocorrelation
-// of frames short enough (frame_len + 199 <= 512, e.g. the 300-sample frames of model.py:92) that the 512-point circular
-// correlation has no wrap-around on the lags 20..199: one transform pair instead of the even / odd split (6 transforms).
+// inlined chain thrashed the instruction cache).  MODE 0 = cepstrum (5 transforms), 1 = autocorrelation (8).  Autocorrelation
+// frames short enough (frame_len + 199 <= 512, e.g. the 300-sample frames of model.py:92) that nothing wraps in 512 points
+// take pitch_acr_quad below instead (3 transforms per pair).
 // wsm: per-warp shared memory = scr[kWarpScr] float2 | park[512] float4.
 template <int MODE>
 DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
@@ -470,7 +470,7 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);
     const float inv1024 = 1.0f / 1024.0f;
-    constexpr int kStages = MODE == 0 ? 5 : (MODE == 1 ? 8 : 6);
+    constexpr int kStages = MODE == 0 ? 5 : 8;
     // cepstrum:         0 F(x)        -> park Xe He / 2        autocorrelation: 0 F(x)       -> Xe He
     //                   1 F(x W^n)    -> Xo Ho                                  1 inverse    -> park
     //                   2 inverse     -> W^-n d / 1024                          2 F(x W^n)   -> Xo Ho
@@ -481,7 +481,7 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
     for (int st = 0; st < kStages; ++st) {
         const bool inv = MODE == 0 ? (st == 2 || st == 4) : (st & 1);
         const bool load = MODE == 0 ? st <= 1 : !(st & 1);
-        const bool loadmod = MODE == 0 ? st == 1 : (st == 2 || (MODE == 1 && st == 6));
+        const bool loadmod = MODE == 0 ? st == 1 : (st == 2 || st == 6);
         if (load) {                                          // a real sequence from xs, optionally times W1024^n
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
@@ -549,23 +549,10 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
                     const bool in = 32 * t + lane < L;
                     xs[32 * t + lane] = make_float2(in ? dsp_fast_sqrtf(s2.x) * inv1024 : 0.f, in ? dsp_fast_sqrtf(s2.y) * inv1024 : 0.f);
                 }
-            } else if (MODE == 2 && st == 5) {               // short frames: r[n] = IFFT512(|V|^2)[n] / 512, unbiased normalisation, rows
-                const float inv512 = 1.0f / 512.0f;
-                float* rowa = p.rows + g0 * p.row_len;
-                float* rowb = rowa + p.row_len;
-#pragma unroll
-                for (int t = 0; t < 7; ++t) {
-                    const int n = 32 * t + lane, j = n - kMinLag;
-                    if (j >= 0 && j < p.row_len) {
-                        const float inv_n = (n < L) ? 1.0f / (float)(L - n) : NAN;
-                        rowa[j] = x[t].re.x * inv512 * inv_n;
-                        if (hasB) rowb[j] = x[t].re.y * inv512 * inv_n;
-                    }
-                }
             } else if (st == 4 || st == 6) {                 // power spectrum
 #pragma unroll
                 for (int t = 0; t < 16; ++t) { x[t].re = f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re)); x[t].im = zero2; }
-            } else if (MODE == 1 && st == 5) {               // real parts of the even-bin half, lags < 224
+            } else if (st == 5) {                            // real parts of the even-bin half, lags < 224
                 float2* ge = reinterpret_cast<float2*>(park);
 #pragma unroll
                 for (int t = 0; t < 7; ++t) ge[32 * t + lane] = x[t].re;
@@ -584,6 +571,135 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
                         rowa[j] = r.x * inv_n;
                         if (hasB) rowb[j] = r.y * inv_n;
                     }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5a-2 for frames short enough that nothing wraps in 512 points (acr_short_frames: e.g. the 300-sample frames of
+// model.py:92): FOUR consecutive frames (two clipped pairs) per warp, 6 transforms per quad instead of the 12 the
+// pair-at-a-time chain (MODE 2 of pitch_fft_pair) takes.  Two uses of "two real sequences in one complex transform":
+//   * the FIR.  With T = 512 - L, h = h_lo (taps 0..T) + h_hi (taps T+1..L-1) and x_lo = x[0 .. L-T-2], the first L
+//     samples of conv(x, h) are those of conv(x, h_lo) + conv(x_lo, h_hi), and both of these fit 512 points without
+//     wrapping (supports end at 511 and at 2L - T - 3 <= 511).  x and x_lo are real, so one forward transform of
+//     z = x + i x_lo carries both spectra: X = (Z + Zr*)/2, X_lo = (Z - Zr*)/(2i) with Zr[k] = Z[-k], and
+//         FFT512(y) = X H_lo + X_lo H_hi = Z A + Zr* B,   A = (H_lo - i H_hi)/2,  B = (H_lo + i H_hi)/2
+//     (tables at kTabHe / kTabHo, the inverse transform's 1/512 folded in).  One forward + one inverse per pair.
+//   * the autocorrelation.  v1 = |y| of the first pair and v2 = |y| of the second are real: Z = FFT512(v1 + i v2) gives
+//     |V1|^2 = |Z + Zr*|^2 / 4 and |V2|^2 = |Z - Zr*|^2 / 4; both power spectra are real and even, so the inverse transform
+//     of |V1|^2 + i |V2|^2 has r1 in its real part and r2 in its imaginary part: one forward + one inverse per quad.
+// The partner bins Zr come from the lane 32 - lane (register 15 - t) by shuffles; lane 0 holds the bins 32 t, whose partners
+// 32 (16 - t) are its own registers, fetched with a one-register look-behind so that the update can run in place.
+// wsm: per-warp shared memory = scr[kWarpScr] float2 | vpark[32 * kQuadT] float2.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kQuadT = 10;                                            // registers that hold samples of a frame of <= 320 samples
+constexpr int kQuadWarpSmemBytes = kWarpScr * 8 + 32 * kQuadT * 8;
+constexpr int kQuadCtaSmem = (kTabMod * 8) + kPitchWarps * kQuadWarpSmemBytes;
+DEVFN cpx2 shfl_c(cpx2 a, int src) {
+    cpx2 r;
+    r.re.x = __int_as_float_compat(simt::shfl32_i(__float_as_int_compat(a.re.x), src)); r.re.y = __int_as_float_compat(simt::shfl32_i(__float_as_int_compat(a.re.y), src));
+    r.im.x = __int_as_float_compat(simt::shfl32_i(__float_as_int_compat(a.im.x), src)); r.im.y = __int_as_float_compat(simt::shfl32_i(__float_as_int_compat(a.im.y), src));
+    return r;
+}
+// KIND 0: x[k] <- x[k] A[k] + conj(x[-k]) B[k];  KIND 1: x[k] <- (|x[k] + conj(x[-k])|^2 + i |x[k] - conj(x[-k])|^2) / 4
+template <int KIND>
+DEVFN void split_pairs(cpx2 (&x)[16], const float2* A, const float2* B, int lane) {
+    const int src = (32 - lane) & 31;
+    const bool l0 = lane == 0;
+    cpx2 saved = x[0];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int a = t, b = 15 - t;
+        cpx2 sa = shfl_c(x[b], src), sb = shfl_c(x[a], src);
+        if (l0) { sa = saved; sb = x[a + 1]; }
+        saved = x[b];
+        const cpx2 za = x[a], zb = x[b];
+        if (KIND == 0) {
+            const float2 Aa = ldg(A + 32 * a + lane), Ba = ldg(B + 32 * a + lane), Ab = ldg(A + 32 * b + lane), Bb = ldg(B + 32 * b + lane);
+            // z A + conj(s) B:  re = z.re A.x - z.im A.y + s.re B.x + s.im B.y;  im = z.re A.y + z.im A.x + s.re B.y - s.im B.x
+            x[a].re = f2fmas(sa.im, Ba.y, f2fmas(sa.re, Ba.x, f2fmas(za.im, -Aa.y, f2muls(za.re, Aa.x))));
+            x[a].im = f2fmas(sa.im, -Ba.x, f2fmas(sa.re, Ba.y, f2fmas(za.im, Aa.x, f2muls(za.re, Aa.y))));
+            x[b].re = f2fmas(sb.im, Bb.y, f2fmas(sb.re, Bb.x, f2fmas(zb.im, -Ab.y, f2muls(zb.re, Ab.x))));
+            x[b].im = f2fmas(sb.im, -Bb.x, f2fmas(sb.re, Bb.y, f2fmas(zb.im, Ab.x, f2muls(zb.re, Ab.y))));
+        } else {
+            const float2 pa_r = f2add(za.re, sa.re), pa_i = f2sub(za.im, sa.im), ma_r = f2sub(za.re, sa.re), ma_i = f2add(za.im, sa.im);
+            const float2 pb_r = f2add(zb.re, sb.re), pb_i = f2sub(zb.im, sb.im), mb_r = f2sub(zb.re, sb.re), mb_i = f2add(zb.im, sb.im);
+            x[a].re = f2muls(f2fma(pa_i, pa_i, f2mul(pa_r, pa_r)), 0.25f); x[a].im = f2muls(f2fma(ma_i, ma_i, f2mul(ma_r, ma_r)), 0.25f);
+            x[b].re = f2muls(f2fma(pb_i, pb_i, f2mul(pb_r, pb_r)), 0.25f); x[b].im = f2muls(f2fma(mb_i, mb_i, f2mul(mb_r, mb_r)), 0.25f);
+        }
+    }
+}
+DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
+    const int lane = simt::tid() & 31;
+    float2* scr = reinterpret_cast<float2*>(wsm);
+    float2* vpark = scr + kWarpScr;
+    const float2* tabA = p.tab + kTabHe;
+    const float2* tabB = p.tab + kTabHo;
+    const int L = p.frame_len;
+    const int nlo = 2 * L - 514;                      // x_lo = x[0 .. L - T - 2], T = 512 - L
+    const bool has2 = g0 + 2 < total;                 // the second pair exists (its slot was written by the clip kernel)
+    const float2 zero2 = make_float2(0.f, 0.f);
+    cpx2 x[16];
+    // stage 0 F(x + i x_lo) of pair 1 -> Z A + Zr* B      1 inverse -> v1 = |y|, parked
+    //       2 the same for pair 2                            3 inverse -> v2;  z = v1 + i v2
+    //       4 F(z) -> |V1|^2 + i |V2|^2                    5 inverse -> r1 + i r2 -> rows
+#pragma unroll 1
+    for (int st = 0; st < 6; ++st) {
+        const bool inv = st & 1;
+        if (st == 0 || st == 2) {
+            const float2* xs = p.clip + ((g0 >> 1) + (st >> 1)) * 512;
+            const bool live = st == 0 || has2;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int n = 32 * t + lane;
+                float2 v = zero2;
+                if (t < kQuadT && live) v = xs[n];
+                x[t].re = v; x[t].im = n <= nlo ? v : zero2;
+            }
+        }
+        if (inv) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) x[t].im = f2neg(x[t].im);
+        }
+        fft512<true>(x, scr, tws, w32s, lane);
+        if (st == 0 || st == 2) {
+            split_pairs<0>(x, tabA, tabB, lane);
+        } else if (st == 1 || st == 3) {                     // v = |y| on the frame, zero beyond it (the conjugation does not change |.|)
+            float2 v[kQuadT];
+#pragma unroll
+            for (int t = 0; t < kQuadT; ++t) {
+                const float2 s2 = f2fma(x[t].im, x[t].im, f2mul(x[t].re, x[t].re));
+                const bool in = 32 * t + lane < L;
+                v[t] = make_float2(in ? dsp_fast_sqrtf(s2.x) : 0.f, in ? dsp_fast_sqrtf(s2.y) : 0.f);
+            }
+            if (st == 1) {
+#pragma unroll
+                for (int t = 0; t < kQuadT; ++t) vpark[32 * t + lane] = v[t];      // (a lane only ever touches its own entries)
+            } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    x[t].re = t < kQuadT ? vpark[32 * (t < kQuadT ? t : 0) + lane] : zero2;
+                    x[t].im = t < kQuadT ? v[t < kQuadT ? t : 0] : zero2;
+                }
+            }
+        } else if (st == 4) {
+            split_pairs<1>(x, tabA, tabB, lane);
+        } else {                                             // st == 5: r[n] / 512, unbiased normalisation (sigproc.py:48-53), rows
+            const float inv512 = 1.0f / 512.0f;
+            float* row = p.rows + g0 * p.row_len;
+            const int RL = p.row_len;
+            const bool f1 = g0 + 1 < total, f2 = g0 + 2 < total, f3 = g0 + 3 < total;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                const int n = 32 * t + lane, j = n - kMinLag;
+                if (j >= 0 && j < RL) {
+                    const float sc = (n < L) ? inv512 / (float)(L - n) : NAN;
+                    row[j] = x[t].re.x * sc;
+                    if (f1) row[RL + j] = x[t].re.y * sc;
+                    if (f2) row[2 * RL + j] = -x[t].im.x * sc;       // the inverse is conj . forward . conj: its imaginary part is
+                    if (f3) row[3 * RL + j] = -x[t].im.y * sc;       // minus the imaginary part left in the registers
                 }
             }
         }

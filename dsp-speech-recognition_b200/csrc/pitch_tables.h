@@ -80,6 +80,21 @@ inline int build_pitch_tables(const dspfe_pitch_params& q, PitchParams& b, std::
             }
             tab[(odd ? kTabHo : kTabHe) + k] = make_float2((float)sr, (float)si);
         }
+    if (q.method == 1 && acr_short_frames(q.frame_len, b.row_len)) {
+        // pitch_acr_quad's split FIR: H_lo = FFT512(taps 0..T), H_hi = FFT512(taps T+1..L-1 left in place), T = 512 - L;
+        // kTabHe <- A = (H_lo - i H_hi) / 2, kTabHo <- B = (H_lo + i H_hi) / 2, both with the inverse transform's 1/512
+        const int L = q.frame_len, T = 512 - L;
+        for (int k = 0; k < 512; ++k) {
+            double lr = 0, li = 0, gr = 0, gi = 0;
+            for (int n = 0; n < L; ++n) {
+                const double a = -2 * kPi * (double)((long long)k * n % 512) / 512.0, c = cos(a), s_ = sin(a);
+                const double tr = hr[n] * c - hi[n] * s_, ti = hr[n] * s_ + hi[n] * c;
+                if (n <= T) { lr += tr; li += ti; } else { gr += tr; gi += ti; }
+            }
+            tab[kTabHe + k] = make_float2((float)((lr + gi) / 1024.0), (float)((li - gr) / 1024.0));
+            tab[kTabHo + k] = make_float2((float)((lr - gi) / 1024.0), (float)((li + gr) / 1024.0));
+        }
+    }
     return 0;
 }
 

@@ -17,12 +17,13 @@ struct Args { PitchParams p; std::vector<unsigned char>* smem; int64_t total_fra
 void frame_body(void* a) {
     Args* A = (Args*)a;
     const int w = simt::tid() >> 5;
-    const int64_t g0 = 2 * ((int64_t)simt::bid() * kPitchWarps + w);
+    const bool quad = A->p.mode != 0 && acr_short_frames(A->p.frame_len, A->p.row_len);
+    const int64_t g0 = (quad ? 4 : 2) * ((int64_t)simt::bid() * kPitchWarps + w);
     if (g0 >= A->total_frames) return;
     // the device kernel stages the twiddles and the decimator pattern in shared memory; the emulator reads them in place
     unsigned char* wsm = A->smem->data() + w * kWarpSmemBytes;
     if (A->p.mode == 0) pitch_fft_pair<0>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
-    else if (acr_short_frames(A->p.frame_len, A->p.row_len)) pitch_fft_pair<2>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
+    else if (quad) pitch_acr_quad(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
     else pitch_fft_pair<1>(A->p, g0, A->total_frames, wsm, A->p.tab, A->p.tab + kTabW32);
 }
 void clip_body(void* a) {

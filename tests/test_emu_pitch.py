@@ -92,3 +92,24 @@ def test_decimator_pattern_matches_reference(rate):
     assert len(r["pitch"]) == len(fr)
     want = O.pitch_detect_frame_sr(fr, 10000)          # the gathered samples are the kept indices themselves
     assert np.max(np.abs(r["rows"] - want)) <= 2e-5 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("frame_len", [300, 313, 256, 200])
+def test_short_frame_autocorrelation_quads(frame_len):
+    """pitch_acr_quad (four frames per warp, the split FIR and the packed autocorrelation): the rows of every frame count
+    modulo 4 against pitch_detect_frame_sr of the oracle, for frame lengths on both sides of the tap split (T = 512 - L)."""
+    lengths = [9000, 4961, 5121, 5281, 700]          # 54, 29, 30, 31 frames of 300 samples (+ a one-frame utterance)
+    pcm, off = synth.synth_batch(lengths, seed0=31)
+    r = emu.pitch(pcm, off, method=1, frame_len=frame_len, want_rows=True)
+    for u in range(len(lengths)):
+        x = pcm[off[u]:off[u + 1]]
+        fr = O.to_frames(O.downsampling(x, 16000, 10000), 10000, frame_len / 10000.0, 0.01)
+        want = np.asarray(O.pitch_detect_frame_sr(O.center_clip(fr, False), 10000))
+        got = r["rows"][r["frame_off"][u]:r["frame_off"][u + 1]]
+        assert got.shape == want.shape, (u, got.shape, want.shape)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin)
+        # float32 transforms: absolute error ~1e-7 of sum v^2, and the last lags divide it by L - n -> 1
+        assert np.max(np.abs(got[fin] - want[fin])) <= 5e-5 * np.max(np.abs(want[fin])), u
+        p_want, _ = O.pitch_detect_sr(x, 16000, winlen=frame_len / 10000.0, step=0.01)
+        assert np.mean(r["pitch"][r["frame_off"][u]:r["frame_off"][u + 1]] != np.asarray(p_want)) <= 0.02
