@@ -53,18 +53,19 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
 }
 
 // K4a-1: gather + exact median + centre clip, a frame pair per warp
-__global__ void __launch_bounds__(32 * kPitchWarps, 6) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
+template <bool I16>
+__global__ void __launch_bounds__(32 * kPitchWarps, 5) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t* ds_idx = reinterpret_cast<int32_t*>(smem);
     const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
-    if (2 * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // the grid is sized for the untrimmed batch
+    if (kClipRun * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // the grid is sized for the untrimmed batch
     for (int i = threadIdx.x; i < p.ds_out; i += blockDim.x) ds_idx[i] = p.ds_idx[i];
     __syncthreads();
     const int w = threadIdx.x >> 5;
-    const int64_t g0 = 2 * ((int64_t)blockIdx.x * kPitchWarps + w);
+    const int64_t g0 = kClipRun * ((int64_t)blockIdx.x * kPitchWarps + w);
     if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
-    if (p.frame_len <= 320) pitch_clip_pair<10>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);   // e.g. the 300-sample frames of model.py:92
-    else pitch_clip_pair<16>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
+    if (p.frame_len <= 320) pitch_clip_run<10, I16>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);   // e.g. the 300-sample frames of model.py:92
+    else pitch_clip_run<16, I16>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
 }
 
 // K4a-2 / K5a-2: the transforms, a frame pair per warp.  At 128 registers (4 CTAs/SM) the chains spilled 130-230 bytes per
@@ -165,7 +166,7 @@ int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
     return DSPFE_OK;
 }
 
-int track_smem(int row_len) { return (track_chunk(row_len) + 1) * row_len * (int)sizeof(float) + track_chunk(row_len) * kPeakLags * (int)sizeof(int) + kTrackMaxFrames * 12; }
+int track_smem(int row_len) { return (track_chunk(row_len) + 1) * row_len * (int)sizeof(float) + track_chunk(row_len) * kPeakLags * (int)sizeof(int) + kTrackMaxFrames * 12 + (kTrackThreads / 32) * kTrackListPerWarp * 2 + 8; }
 
 }  // namespace
 
@@ -193,7 +194,8 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
     if (trc) { delete pl; return fail(trc, err); }
     cudaError_t e = cudaMalloc(&pl->d_tab, kTabTotal * sizeof(float2));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_tab, tab.data(), kTabTotal * sizeof(float2), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipCtaSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipCtaSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameCtaSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pitch_frame_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadCtaSmem);
@@ -265,7 +267,9 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     pitch_prep_kernel<<<1, kPitchPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("pitch_prep_kernel", st);
     const unsigned fgrid = (unsigned)((bound + 2 * kPitchWarps - 1) / (2 * kPitchWarps));
-    pitch_clip_kernel<<<fgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
+    const unsigned cgrid = (unsigned)((bound + kClipRun * kPitchWarps - 1) / (kClipRun * kPitchWarps));
+    if (clip_i16_keys(p)) pitch_clip_kernel<true><<<cgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
+    else pitch_clip_kernel<false><<<cgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_clip_kernel", st);
     const int fmode = p.mode == 0 ? 0 : (acr_short_frames(p.frame_len, p.row_len) ? 2 : 1);
     if (fmode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);

@@ -49,9 +49,6 @@ constexpr int kWarpSmemBytes = kWarpScr * 8 + 512 * 16;              // transfor
 constexpr int kTabTw = 0, kTabW32 = kTabTw + 512, kTabMod = kTabW32 + 32, kTabHe = kTabMod + 512, kTabHo = kTabHe + 512,
               kTabTotal = kTabHo + 512;
 constexpr int kFrameCtaSmem = (kTabMod * 8) + kPitchWarps * kWarpSmemBytes;                      // shared tables | per-warp areas
-constexpr int kStageBytes = 2048;   // per frame; the span of a 512-sample frame at 16 kHz -> 10 kHz is 1.7 KB of int16
-constexpr int kClipWarpSmemBytes = 2 * kStageBytes + 512 * 8;       // clip kernel: two staged source spans | gathered frame pair
-constexpr int kClipCtaSmem = kMaxDsOut * 4 + kPitchWarps * kClipWarpSmemBytes;
 constexpr int kTrackThreads = 256;
 constexpr int kTrackMaxFrames = 1024;   // utterances up to this many frames keep their lag / Hz track in shared memory
 constexpr int kTrackChunk = 32;     // frames smoothed per pass of K4b/K5b (16 for rows wider than 256 columns)
@@ -216,6 +213,60 @@ DEVFN void transpose16_dual(unsigned (&A)[16]) {
         m ^= m << (j >> 1);
     }
 }
+// Integer-valued samples in [0, 32767] (int16 PCM that was neither pre-emphasised nor scaled): 15-bit keys -- one bit-matrix
+// transpose and 15 selection steps instead of two and 31.
+template <int NT>
+DEVFN float2 warp_median_nonneg2_i16(const float (&xa)[NT], const float (&xb)[NT], int L, int lane) {
+    unsigned ka[NT], kb[NT];
+    int cnt = 0, cntb = 0;
+    const bool full = L >= 32 * NT;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const float va = xa[t], vb = xb[t];
+        const bool in = full || (lane + 32 * t) < L;
+        const bool na = in & (va >= 0.f), nb = in & (vb >= 0.f);
+        // value + 2^23 has the integer in its low mantissa bits (exact for 0 <= value < 2^23)
+        ka[t] = na ? ((unsigned)__float_as_int_compat(va + 8388608.0f) & 0x7fffu) : 0xffffu;
+        kb[t] = nb ? ((unsigned)__float_as_int_compat(vb + 8388608.0f) & 0x7fffu) : 0xffffu;
+        cnt += na; cntb += nb;
+    }
+    cnt = warp_redux_add(cnt + (cntb << 16));
+    const int ma = cnt & 0xffff, mb = cnt >> 16;
+    int rA = (ma - 1) >> 1, rB = (mb - 1) >> 1;
+    unsigned Ka = 0, Kb = 0;
+    {
+        unsigned P[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) P[t] = t < NT ? (ka[t < NT ? t : 0] | (kb[t < NT ? t : 0] << 16)) : 0xffffffffu;
+        transpose16_dual(P);                                    // P[i] = plane of key bit 15 - i; bit 15 marks the excluded keys
+        unsigned cand = ~P[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            const unsigned z = cand & ~P[i];
+            const int c = warp_redux_add(dsp_popc(z & 0xffffu) + (dsp_popc(z >> 16) << 16));
+            const int cA = c & 0xffff, cB = c >> 16;
+            const bool zA = rA < cA, zB = rB < cB;
+            const unsigned sel = (zA ? 0x0000ffffu : 0u) | (zB ? 0xffff0000u : 0u);
+            cand = (z & sel) | (cand & P[i] & ~sel);
+            if (!zA) { rA -= cA; Ka |= 1u << (15 - i); }
+            if (!zB) { rB -= cB; Kb |= 1u << (15 - i); }
+        }
+    }
+    int c = 0; unsigned na = 0xffffu, nb = 0xffffu;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        c += (ka[t] <= Ka ? 1 : 0) + (kb[t] <= Kb ? 0x10000 : 0);
+        if (ka[t] > Ka && ka[t] < na) na = ka[t];
+        if (kb[t] > Kb && kb[t] < nb) nb = kb[t];
+    }
+    c = warp_redux_add(c); na = warp_redux_min(na); nb = warp_redux_min(nb);
+    const unsigned Ka2 = ((ma & 1) || (c & 0xffff) >= (ma >> 1) + 1) ? Ka : na;
+    const unsigned Kb2 = ((mb & 1) || (c >> 16) >= (mb >> 1) + 1) ? Kb : nb;
+    float2 med;
+    med.x = ma ? ((float)(int)Ka + (float)(int)Ka2) * 0.5f : NAN;
+    med.y = mb ? ((float)(int)Kb + (float)(int)Kb2) * 0.5f : NAN;
+    return med;
+}
 template <int NT>
 DEVFN float2 warp_median_nonneg2(const float (&xa)[NT], const float (&xb)[NT], int L, int lane) {
     unsigned ka[NT], kb[NT];
@@ -324,7 +375,8 @@ struct FrameCursor {
 };
 // Stages the source span of one frame in shared memory with 16-byte loads (one DRAM latency for the whole frame
 // instead of one per group of samples) and returns the cursor; spans that do not fit are read in place.
-DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane, bool valid, unsigned char* stage) {
+// span = decimated samples wanted from the frame's first one on (one frame: frame_len; a run of frames: (R-1)*step + frame_len)
+DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane, bool valid, unsigned char* stage, int span, int stage_cap) {
     FrameCursor c;
     const int esz = p.in_f32 ? 4 : 2;
     const int64_t start = p.seg_start[u];
@@ -336,8 +388,8 @@ DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane,
     const int k = kf + lane;
     c.a = k >= 1 ? (k - 1) / p.ds_out : -1;                    // k = 0 starts from -1 = (-1, ds_out - 1): its index
     c.b = k >= 1 ? (k - 1) - c.a * p.ds_out : p.ds_out - 1;    // a*ds_in + ds_idx[b] is negative and clamps to sample 0
-    const int kl = kf + p.frame_len - 1 < Ld - 1 ? kf + p.frame_len - 1 : Ld - 1;
-    const int nlim = (p.frame_len < Ld - kf ? p.frame_len : Ld - kf) - lane;   // samples n = lane + 32 t with n < min(L, Ld - kf)
+    const int kl = kf + span - 1 < Ld - 1 ? kf + span - 1 : Ld - 1;
+    const int nlim = (span < Ld - kf ? span : Ld - kf) - lane;   // samples n = lane + 32 t with n < min(span, Ld - kf)
     c.nvalid = nlim > 0 ? (nlim + 31) >> 5 : 0;
     if (kf <= kl) {
         int s_lo = (int)ds_index(kf, p.ds_idx, p.ds_in, p.ds_out) - 1;
@@ -345,7 +397,7 @@ DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane,
         const int s_hi = (int)ds_index(kl, p.ds_idx, p.ds_in, p.ds_out);
         const int64_t b_lo = (start + s_lo) * esz, b_hi = (start + s_hi + 1) * esz, a0 = b_lo & ~(int64_t)15;
         const int nbytes = (int)(b_hi - a0);
-        if (nbytes <= kStageBytes) {
+        if (nbytes <= stage_cap) {
             const int64_t total_bytes = p.total_samples * esz;
             for (int off = lane * 16; off < nbytes; off += 512) {
                 if (a0 + off + 16 <= total_bytes) *reinterpret_cast<uint4*>(stage + off) = ldg(reinterpret_cast<const uint4*>(pcm + a0 + off));
@@ -381,66 +433,110 @@ DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds
     if (c.b >= p.ds_out) { c.b -= p.ds_out; ++c.a; }
     return v;
 }
+// K4a-1: gather + median + centre clip -> p.clip[pair] (512 float2, frame A in .x, frame B in .y) and p.frame_amp.  Its own
+// kernel: it needs few registers and little shared memory, so twice as many warps as the transform kernels hide its load
+// and selection latencies.  A warp takes a RUN of kClipRun consecutive frames: consecutive frames of an utterance overlap
+// (512 samples every 100), so the run's source span is staged once (16-byte loads), walked once through the sample-picking
+// decimator (and the pre-emphasis) into a float buffer of decimated samples, and every frame of the run then reads its
+// samples from that buffer with plain contiguous loads -- the index arithmetic is paid per decimated sample, not per
+// sample per frame.  A run that crosses an utterance boundary restages at the boundary.
+// wsm: per-warp shared memory = stage[kClipStageBytes] | dec[kClipDecCap] float.
+constexpr int kClipRun = 8;                  // frames per warp (even: pairs never straddle two warps)
+constexpr int kClipStageBytes = 4096;        // source span of a run: 1212 decimated samples are 3.9 KB of int16 at 16 -> 10 kHz
+constexpr int kClipDecCap = 1280;               // floats: 7 * 100 + 512 decimated samples of a run, rounded up to the unrolled row count
+constexpr int kClipWarpSmemBytes = kClipStageBytes + kClipDecCap * 4;
+constexpr int kClipCtaSmem = kMaxDsOut * 4 + kPitchWarps * kClipWarpSmemBytes;
+struct ClipRun {                             // the staged part of one utterance
+    int u;                                   // utterance (-1: nothing staged)
+    int64_t f_lo, f_hi;                      // global frames whose samples are in dec
+    int kf_lo;                               // decimated index of dec[0] inside the utterance
+    int Ld;                                  // decimated length of the utterance
+};
 template <bool F32, bool PRE>
-DEVFN void gather_pair_impl(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb, int nt) {
+DEVFN void decimate_span(const PitchParams& p, FrameCursor& c, const int32_t* ds_idx, float* dec, int lane, int rows) {
 #pragma unroll 1
-    for (int t0 = 0; t0 < nt; t0 += 4) {
+    for (int t0 = 0; t0 < rows; t0 += 4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float va = frame_sample<F32, PRE>(p, ca, ds_idx, t0 + j), vb = frame_sample<F32, PRE>(p, cb, ds_idx, t0 + j);
-            xs[32 * (t0 + j) + lane] = make_float2(va, vb);
-            fa += fabsf(va); fb += fabsf(vb);
-        }
+        for (int j = 0; j < 4; ++j) dec[32 * (t0 + j) + lane] = frame_sample<F32, PRE>(p, c, ds_idx, t0 + j);
     }
 }
-template <bool F32>
-DEVFN void gather_pair(const PitchParams& p, FrameCursor& ca, FrameCursor& cb, const int32_t* ds_idx, float2* xs, int lane, float& fa, float& fb, int nt) {
-    if (p.pre_hi != 0.f || p.pre_lo != 0.f) gather_pair_impl<F32, true>(p, ca, cb, ds_idx, xs, lane, fa, fb, nt);
-    else gather_pair_impl<F32, false>(p, ca, cb, ds_idx, xs, lane, fa, fb, nt);
+// stages frames [g, g_hi) of utterance u (as many as the buffers hold) and fills dec
+DEVFN void clip_stage_run(const PitchParams& p, ClipRun& r, int u, int64_t g, int64_t g_hi, int lane, unsigned char* stage, float* dec,
+                          const int32_t* ds_idx) {
+    const int L = p.frame_len, step = p.frame_step;
+    int nf = (int)(g_hi - g);
+    const int fit = (kClipDecCap - L) / step + 1;                     // frames whose samples fit dec
+    nf = nf < fit ? nf : fit;
+    const int span = (nf - 1) * step + L;
+    simt::warp_sync();                                                // every lane has finished reading the previous run
+    FrameCursor c = frame_cursor(p, g, u, lane, true, stage, span, kClipStageBytes);
+    const int rows = (((span + 31) >> 5) + 3) & ~3;                   // rows of 32 decimated samples, rounded to the unroll (rows past the span give zeros)
+    const bool pre = p.pre_hi != 0.f || p.pre_lo != 0.f;
+    if (p.in_f32) { if (pre) decimate_span<true, true>(p, c, ds_idx, dec, lane, rows); else decimate_span<true, false>(p, c, ds_idx, dec, lane, rows); }
+    else { if (pre) decimate_span<false, true>(p, c, ds_idx, dec, lane, rows); else decimate_span<false, false>(p, c, ds_idx, dec, lane, rows); }
+    simt::warp_sync();
+    r.u = u; r.f_lo = g; r.f_hi = g + nf; r.kf_lo = (int)(g - p.frame_off[u]) * step; r.Ld = p.ds_len[u];
 }
-
-// K4a-1: gather + median + centre clip of a frame pair -> p.clip[pair] (512 float2, frame A in .x, frame B in .y) and
-// p.frame_amp.  Its own kernel: it needs few registers and little shared memory, so three times as many warps as the
-// transform kernel can hide its load and bisection latencies.
-// wsm: per-warp shared memory = stage[2][kStageBytes] | xs[512] float2.
 template <int NT>
-DEVFN void pitch_clip_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const int32_t* ds_idx) {
+DEVFN void clip_fetch_frame(const PitchParams& p, ClipRun& r, int64_t g, int64_t g_end, int lane, unsigned char* stage, float* dec,
+                            const int32_t* ds_idx, float (&x)[NT], float& amp) {
+    if (r.u < 0 || g < r.f_lo || g >= r.f_hi) {
+        int u = r.u;
+        if (u < 0 || g < p.frame_off[u] || g >= p.frame_off[u + 1]) u = find_utt(p.frame_off, p.n_utt, g, lane);
+        const int64_t u_end = p.frame_off[u + 1];
+        clip_stage_run(p, r, u, g, g_end < u_end ? g_end : u_end, lane, stage, dec, ds_idx);
+    }
+    const int base = (int)(g - r.f_lo) * p.frame_step;
+    const int kf = r.kf_lo + base;
+    const int cnt = p.frame_len < r.Ld - kf ? p.frame_len : r.Ld - kf;    // samples of the frame inside the decimated signal; zeros after
+    amp = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int n = 32 * t + lane;
+        const float v = n < cnt ? dec[base + n] : 0.f;
+        x[t] = v; amp += fabsf(v);
+    }
+}
+// I16: raw int16 samples (no pre-emphasis, no float input): integer keys for the median
+DSP_HD bool clip_i16_keys(const PitchParams& p) { return !p.in_f32 && p.pre_hi == 0.f && p.pre_lo == 0.f; }
+template <int NT, bool I16>
+DEVFN void pitch_clip_run(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const int32_t* ds_idx) {
     const int lane = simt::tid() & 31;
     unsigned char* stage = wsm;
-    float2* xs = reinterpret_cast<float2*>(wsm + 2 * kStageBytes);
-    const bool hasB = g0 + 1 < total;
+    float* dec = reinterpret_cast<float*>(wsm + kClipStageBytes);
     const int L = p.frame_len;
-    // ---- gather both frames into xs from their staged source spans; sum |x| of the raw frames (sub_endpoint_detect,
-    // pitch.py:65) in float64 across the warp
-    const int ua = find_utt(p.frame_off, p.n_utt, g0, lane);
-    const int ub = (hasB && g0 + 1 >= p.frame_off[ua + 1]) ? ua + 1 : ua;
-    FrameCursor ca = frame_cursor(p, g0, ua, lane, true, stage);
-    FrameCursor cb = frame_cursor(p, hasB ? g0 + 1 : g0, ub, lane, hasB, stage + kStageBytes);
-    float fa = 0.f, fb = 0.f;
-    constexpr int kGatherRows = (NT + 3) & ~3;   // rows t >= NT lie past the frame: the cursor returns zeros there
-    if (p.in_f32) gather_pair<true>(p, ca, cb, ds_idx, xs, lane, fa, fb, kGatherRows);
-    else gather_pair<false>(p, ca, cb, ds_idx, xs, lane, fa, fb, kGatherRows);
-    float xa[NT], xb[NT];
+    const int64_t g_end = g0 + kClipRun < total ? g0 + kClipRun : total;
+    ClipRun run; run.u = -1; run.f_lo = run.f_hi = 0; run.kf_lo = 0; run.Ld = 0;
+#pragma unroll 1
+    for (int64_t g = g0; g < g_end; g += 2) {
+        const bool hasB = g + 1 < total;
+        float xa[NT], xb[NT], fa, fb = 0.f;
+        clip_fetch_frame<NT>(p, run, g, g_end, lane, stage, dec, ds_idx, xa, fa);
+        if (hasB) clip_fetch_frame<NT>(p, run, g + 1, g_end, lane, stage, dec, ds_idx, xb, fb);
+        else {
 #pragma unroll
-    for (int t = 0; t < NT; ++t) { const float2 v = xs[32 * t + lane]; xa[t] = v.x; xb[t] = v.y; }
-    double sa = (double)fa, sb = (double)fb;
-    if (p.frame_amp) {
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
-        if (lane == 0) { p.frame_amp[g0] = sa; if (hasB) p.frame_amp[g0 + 1] = sb; }
-    }
-    // ---- centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
-    float2 med = make_float2(0.f, 0.f);
-    if (p.do_clip) med = warp_median_nonneg2<NT>(xa, xb, L, lane);
-    float2* dst = p.clip + (g0 >> 1) * 512;
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        float2 o = make_float2(0.f, 0.f);
-        if (t < NT && lane + 32 * t < L) {
-            o.x = p.do_clip ? clip_value(xa[t < NT ? t : 0], med.x) : xa[t < NT ? t : 0];
-            o.y = p.do_clip ? clip_value(xb[t < NT ? t : 0], med.y) : xb[t < NT ? t : 0];
+            for (int t = 0; t < NT; ++t) xb[t] = 0.f;
         }
-        dst[32 * t + lane] = o;
+        // sum |x| of the raw frames (sub_endpoint_detect, pitch.py:65) in float64 across the warp
+        if (p.frame_amp) {
+            double sa = (double)fa, sb = (double)fb;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
+            if (lane == 0) { p.frame_amp[g] = sa; if (hasB) p.frame_amp[g + 1] = sb; }
+        }
+        // centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
+        float2 med = make_float2(0.f, 0.f);
+        if (p.do_clip) med = I16 ? warp_median_nonneg2_i16<NT>(xa, xb, L, lane) : warp_median_nonneg2<NT>(xa, xb, L, lane);
+        float2* dst = p.clip + (g >> 1) * 512;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            float2 o = make_float2(0.f, 0.f);
+            if (t < NT && lane + 32 * t < L) {
+                o.x = p.do_clip ? clip_value(xa[t < NT ? t : 0], med.x) : xa[t < NT ? t : 0];
+                o.y = p.do_clip ? clip_value(xb[t < NT ? t : 0], med.y) : xb[t < NT ? t : 0];
+            }
+            dst[32 * t + lane] = o;
+        }
     }
 }
 
@@ -706,12 +802,15 @@ DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsig
     }
 }
 
-// K4b / K5b: one CTA (256 threads) per utterance, frames in order, kTrackChunk at a time.  Each pass first stages the
-// raw rows of the chunk (plus one row of look-ahead) in shared memory with coalesced vector loads, then runs the
-// reference's in-place running mean on them (one column per thread; rows < i are already smoothed, exactly the
-// reference's recurrence), scores the rows in parallel and takes the arg-max with one warp per row.
+// K4b / K5b: one CTA (256 threads) per utterance, frames in order, kTrackChunk at a time.  Each pass stages the raw rows of
+// the chunk (plus one row of look-ahead) in shared memory with coalesced vector loads, runs the reference's in-place running
+// mean on them (one column per thread; rows < i are already smoothed, exactly the reference's recurrence), then one warp per
+// row scores the row (peak_score) and takes the arg-max.
 // smem (CH = track_chunk(row_len)): float buf[(CH + 1) * row_len] + int sc[CH * 80] + double spitch[kTrackMaxFrames]
-//       + int slag[kTrackMaxFrames].
+//       + int slag[kTrackMaxFrames] + ushort olist[8 * kTrackListPerWarp] (+ 8 bytes of alignment slack).
+constexpr int kTrackListPerWarp = kTrackChunk * kPeakLags / (kTrackThreads / 32);     // tasks a warp sees per chunk (all of them may stay open)
+DEVFN bool stops(float x, float v) { return !(x <= v); }          // pitch.py:236,239: the scan goes on while sig[j] <= v (a NaN stops it)
+
 DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* spitch) {
     const int u = simt::bid();
     const int tid = simt::tid();
@@ -723,7 +822,9 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
     const float* rows = p.rows + f0 * RL;
     // the lag track stays in shared memory for the octave-repair sweeps (a thread walking global memory on its own
     // pays a DRAM latency per frame); longer utterances use the global arrays directly
+    spitch = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(spitch) + 7) & ~(uintptr_t)7);   // rows of odd length leave it 4-byte aligned
     int32_t* slag = reinterpret_cast<int32_t*>(spitch + kTrackMaxFrames);
+    unsigned short* olist = reinterpret_cast<unsigned short*>(slag + kTrackMaxFrames);                 // per warp: its open (row, lag) tasks
     const bool staged = F <= kTrackMaxFrames;
     int32_t* lagv = staged ? slag : p.lag + f0;
     float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};    // smoothed rows i-1 and i-2 of this thread's (up to two) columns
@@ -737,109 +838,153 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
             for (int i = tid; i < nload; i += kTrackThreads) buf[i] = src[i];
         }
         simt::cta_sync();
+        if (!p.no_smooth) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int col = tid + cc * kTrackThreads;
-            if (col < RL) {
-                for (int k = 0; k < nrows; ++k) {
-                    const int i = c0 + k;
-                    const float r0 = buf[k * RL + col];
-                    // smooth (pitch.py:157-164): g[i] = mean(g[left:right]) in place; np.mean over axis 0 adds the rows
-                    // in order, then divides by the count
-                    const int right = (i + 2 < F) ? i + 2 : F - 1;
-                    const int left = i - 2 > 0 ? i - 2 : 0;
-                    float acc = 0.f; bool any = false;
-                    if (i - 2 >= 0 && i - 2 < right) { acc = s2[cc]; any = true; }
-                    if (i - 1 >= 0 && i - 1 < right) { acc = any ? acc + s1[cc] : s1[cc]; any = true; }
-                    if (i < right) { acc = any ? acc + r0 : r0; any = true; }
-                    if (i + 1 < right) { const float r1 = buf[(k + 1) * RL + col]; acc = any ? acc + r1 : r1; any = true; }
-                    float gsm = any ? acc / (float)(right - left) : NAN;   // empty window: np.mean([]) = NaN
-                    if (p.no_smooth) gsm = r0;
-                    buf[k * RL + col] = gsm;
-                    if (p.rows_out) p.rows_out[(f0 + i) * RL + col] = gsm;
-                    s2[cc] = s1[cc]; s1[cc] = gsm;
+            for (int cc = 0; cc < 2; ++cc) {
+                const int col = tid + cc * kTrackThreads;
+                if (col < RL) {
+                    float a2 = s2[cc], a1 = s1[cc];
+                    float r0 = buf[col];
+                    for (int k = 0; k < nrows; ++k) {
+                        const int i = c0 + k;
+                        // smooth (pitch.py:157-164): g[i] = mean(g[left:right]) in place, left = max(i-2, 0), right = i+2 if i+2 < F
+                        // else F-1; np.mean over axis 0 adds the rows in order (rows < i already smoothed), then divides by the count
+                        float gsm, r1 = 0.f;
+                        if (i >= 2 && i + 2 < F) {                    // interior: rows i-2, i-1 (smoothed), i, i+1 (raw); /4 is exact as *0.25
+                            r1 = buf[(k + 1) * RL + col];
+                            gsm = (((a2 + a1) + r0) + r1) * 0.25f;
+                        } else {
+                            const int right = (i + 2 < F) ? i + 2 : F - 1;
+                            const int left = i - 2 > 0 ? i - 2 : 0;
+                            float acc = 0.f; bool any = false;
+                            if (i - 2 >= 0 && i - 2 < right) { acc = a2; any = true; }
+                            if (i - 1 >= 0 && i - 1 < right) { acc = any ? acc + a1 : a1; any = true; }
+                            if (i < right) { acc = any ? acc + r0 : r0; any = true; }
+                            if (i + 1 < F) r1 = buf[(k + 1) * RL + col];   // raw row i + 1 (inside the chunk or its look-ahead row): the next row's r0
+                            if (i + 1 < right) { acc = any ? acc + r1 : r1; any = true; }
+                            gsm = any ? acc / (float)(right - left) : NAN;   // empty window: np.mean([]) = NaN
+                        }
+                        buf[k * RL + col] = gsm;
+                        if (p.rows_out) p.rows_out[(f0 + i) * RL + col] = gsm;
+                        a2 = a1; a1 = gsm; r0 = r1;
+                    }
+                    s2[cc] = a2; s1[cc] = a1;
                 }
             }
+        } else if (p.rows_out) {
+            for (int i = tid; i < nrows * RL; i += kTrackThreads) p.rows_out[(f0 + c0) * RL + i] = buf[i];
         }
         simt::cta_sync();
         if (p.mode == 0) {
-            // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk: min over both sides of the
-            // distance to the nearest sample that is not <= the lag's value (the left scan ends at index 0, the right
-            // one at the row end).  Only the smaller distance matters, so both sides expand together.  Most lags stop
-            // within a few samples; the few real peaks would keep a whole warp spinning, so after four steps the
-            // unfinished lags are finished one at a time with the 32 lanes spread over the distances.
+            // peak_score (pitch.py:227-242) for lags 20..99 of every row of the chunk: min over both sides of the distance to
+            // the nearest sample that stops the scan (the left scan ends at index 0, the right one at the row end); only the
+            // smaller distance matters, so both sides expand together.
+            //   A  one (row, lag) task per thread, distances 1..4 as straight-line code (no loop, no divergence): most lags
+            //      stop there.  The others -- the row's peaks at that scale -- go to the warp's own list.
+            //   B  the listed tasks, one per lane, eight distances at a time (straight-line) for up to four rounds;
+            //   C  what is still open (scores above 36) one task at a time with the 32 lanes spread over the distances.
             const int ntask = nrows * kPeakLags;
+            unsigned short* wlist = olist + warp * kTrackListPerWarp;
+            int n_open = 0;
+            const bool wide = RL >= kMinLag + kPeakLags + 4;              // lags + 4 stay inside the row: no bound checks in A
             for (int t0 = warp * 32; t0 < ntask; t0 += kTrackThreads) {
                 const int t = t0 + lane;
                 const bool live = t < ntask;
                 const int k = live ? t / kPeakLags : 0, c = kMinLag + (live ? t % kPeakLags : 0);
                 const float* row = buf + k * RL;
                 const float v = row[c];
-                const int rmax = c < RL - c ? c : RL - c;         // index 0 / the row end stop the scans
-                int sv = 0;                                       // a NaN value stops both scans at once
-                bool open = false;
-                if (live && v == v) {
+                const int rmax = c < RL - c ? c : RL - c;             // index 0 / the row end stop the scans
+                int sv;
+                if (wide) {
+                    const bool s1 = stops(row[c - 1], v) || stops(row[c + 1], v), s2 = stops(row[c - 2], v) || stops(row[c + 2], v);
+                    const bool s3 = stops(row[c - 3], v) || stops(row[c + 3], v), s4 = stops(row[c - 4], v) || stops(row[c + 4], v);
+                    sv = s1 ? 1 : (s2 ? 2 : (s3 ? 3 : (s4 ? 4 : 5)));
+                    sv = sv < rmax ? sv : rmax;
+                } else {
                     int r = 1;
-                    while (r < rmax && r <= 4 && row[c - r] <= v && row[c + r] <= v) ++r;
+                    while (r < rmax && r <= 4 && !stops(row[c - r], v) && !stops(row[c + r], v)) ++r;
                     sv = r;
-                    open = r > 4 && r < rmax;                      // all of r = 1..4 passed: keep going from r = 5
                 }
-                unsigned todo = simt::ballot32(open);
+                if (!(v == v)) sv = 0;                                 // a NaN value stops both scans at once
+                const bool is_open = live && sv > 4 && sv < rmax;      // all of r = 1..4 passed: go on from r = 5
+                if (live) sc[t] = sv;
+                const unsigned m = simt::ballot32(is_open);
+                if (is_open) wlist[n_open + dsp_popc(m & ((1u << lane) - 1u))] = (unsigned short)t;
+                n_open += dsp_popc(m);
+            }
+            simt::warp_sync();
+            for (int i0 = 0; i0 < n_open; i0 += 32) {
+                const bool has = i0 + lane < n_open;
+                const int t = has ? wlist[i0 + lane] : 0;
+                const int k = t / kPeakLags, c = kMinLag + t % kPeakLags;
+                const float* row = buf + k * RL;
+                const float v = row[c];
+                const int rmax = c < RL - c ? c : RL - c;
+                int found = -1, r = 5;
+                bool pending = has;
+#pragma unroll 1
+                for (int round = 0; round < 4 && simt::ballot32(pending) != 0; ++round, r += 8) {
+                    int first = 8;
+#pragma unroll
+                    for (int d = 7; d >= 0; --d) {
+                        const int rr = r + d < rmax ? r + d : rmax - 1;    // (an index inside the row; past rmax the result is not used)
+                        const bool st = r + d < rmax && (stops(row[c - rr], v) || stops(row[c + rr], v));
+                        first = st ? d : first;
+                    }
+                    if (pending) {
+                        if (first < 8) { found = r + first; pending = false; }
+                        else if (r + 8 >= rmax) { found = rmax; pending = false; }
+                    }
+                }
+                unsigned todo = simt::ballot32(pending);               // r = 37 onwards
                 while (todo) {
                     const int src = __builtin_ffs((int)todo) - 1;
                     todo &= todo - 1;
                     const int ck = simt::shfl32_i(k, src), cc = simt::shfl32_i(c, src), cm = simt::shfl32_i(rmax, src);
                     const float cv = __int_as_float_compat(simt::shfl32_i(__float_as_int_compat(v), src));
                     const float* crow = buf + ck * RL;
-                    int found = cm;
-                    for (int r0 = 5; r0 < cm; r0 += 32) {
-                        const int r = r0 + lane;
-                        const bool stop = r < cm && !(crow[cc - r] <= cv && crow[cc + r] <= cv);
-                        const unsigned m = simt::ballot32(stop);
-                        if (m) { found = r0 + __builtin_ffs((int)m) - 1; break; }
+                    int f = cm;
+                    for (int r0 = 37; r0 < cm; r0 += 32) {
+                        const int rr = r0 + lane;
+                        const bool st = rr < cm && (stops(crow[cc - rr], cv) || stops(crow[cc + rr], cv));
+                        const unsigned hit = simt::ballot32(st);
+                        if (hit) { f = r0 + __builtin_ffs((int)hit) - 1; break; }
                     }
-                    if (lane == src) sv = found;
+                    if (lane == src) found = f;
                 }
-                if (live) {
-                    sc[t] = sv;
-                    if (p.score) p.score[(f0 + c0 + k) * kPeakLags + (c - kMinLag)] = sv;
-                }
+                if (has) sc[t] = found;
             }
             simt::cta_sync();
             for (int k = warp; k < nrows; k += kTrackThreads / 32) {   // first argmax (pitch.py:169), one warp per row
                 const int* srow = sc + k * kPeakLags;
-                int bv = -1, bi = 0;
-                for (int t = lane; t < kPeakLags; t += 32) if (srow[t] > bv) { bv = srow[t]; bi = t; }
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) {
-                    const int ov = simt::shfl32_i(bv, lane ^ m), oi = simt::shfl32_i(bi, lane ^ m);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                }
-                if (lane == 0) lagv[c0 + k] = kMinLag + bi;
+                if (p.score) for (int t = lane; t < kPeakLags; t += 32) p.score[(f0 + c0 + k) * kPeakLags + t] = srow[t];
+                unsigned key = 0;                                      // (score, first index wins): score * 128 + (127 - index)
+                for (int t = lane; t < kPeakLags; t += 32) { const unsigned q = ((unsigned)srow[t] << 7) | (unsigned)(127 - t); key = q > key ? q : key; }
+                key = warp_redux_max(key);
+                if (lane == 0) lagv[c0 + k] = kMinLag + 127 - (int)(key & 127u);
             }
         } else {
-            // np.argmax over the smoothed scores, one warp per row: first maximum, a NaN counts as the maximum
+            // np.argmax over the smoothed scores, one warp per row: first maximum, a NaN counts as the maximum.  Values map to
+            // unsigned keys in float order (a NaN above +inf); one warp maximum, then the smallest index that attains it.
             for (int k = warp; k < nrows; k += kTrackThreads / 32) {
                 const float* row = buf + k * RL;
-                float bv = 0.f; int bi = -1;
+                unsigned best = 0;
                 for (int j = lane; j < RL; j += 32) {
                     const float v = row[j];
-                    const bool better = bi < 0 || (v != v && bv == bv) || (bv == bv && v > bv);
-                    if (better) { bv = v; bi = j; }
+                    const unsigned b = (unsigned)__float_as_int_compat(v);
+                    const unsigned q = v != v ? 0xffffffffu : (b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u));
+                    best = q > best ? q : best;
                 }
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) {
-                    const float ov = simt::shfl32_xor(bv, m);
-                    const int oi = simt::shfl32_i(bi, lane ^ m);
-                    const bool an = bv != bv, on = ov != ov;
-                    bool take;
-                    if (oi < 0) take = false;
-                    else if (bi < 0) take = true;
-                    else if (an || on) take = on && (!an || oi < bi);
-                    else take = ov > bv || (ov == bv && oi < bi);
-                    if (take) { bv = ov; bi = oi; }
+                const unsigned top = warp_redux_max(best);
+                unsigned idx = 0xffffffffu;
+                for (int j = lane; j < RL; j += 32) {
+                    const float v = row[j];
+                    const unsigned b = (unsigned)__float_as_int_compat(v);
+                    const unsigned q = v != v ? 0xffffffffu : (b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u));
+                    if (q == top && (unsigned)j < idx) idx = (unsigned)j;
                 }
-                if (lane == 0) lagv[c0 + k] = kMinLag + (bi < 0 ? 0 : bi);
+                idx = warp_redux_min(idx);
+                if (lane == 0) lagv[c0 + k] = kMinLag + (int)idx;
             }
         }
         simt::cta_sync();

@@ -152,6 +152,15 @@ DEVFN unsigned warp_redux_min(unsigned v) {
 #endif
 }
 
+DEVFN unsigned warp_redux_max(unsigned v) {
+#ifdef DSPFE_EMU
+    for (int m = 16; m >= 1; m >>= 1) { const unsigned o = (unsigned)simt::shfl32_i((int)v, (simt::tid() & 31) ^ m); v = o > v ? o : v; }
+    return v;
+#else
+    return __reduce_max_sync(0xffffffffu, v);
+#endif
+}
+
 // float64 xor-shuffle over the full warp (two 32-bit shuffles)
 DEVFN double shfl32_xor_f64(double v, int m) {
     const int src = (simt::tid() & 31) ^ m;

@@ -29,10 +29,15 @@ void frame_body(void* a) {
 void clip_body(void* a) {
     Args* A = (Args*)a;
     const int w = simt::tid() >> 5;
-    const int64_t g0 = 2 * ((int64_t)simt::bid() * kPitchWarps + w);
+    const int64_t g0 = kClipRun * ((int64_t)simt::bid() * kPitchWarps + w);
     if (g0 >= A->total_frames) return;
-    if (A->p.frame_len <= 320) pitch_clip_pair<10>(A->p, g0, A->total_frames, A->smem->data() + w * kClipWarpSmemBytes, A->p.ds_idx);   // e.g. the 300-sample frames of model.py:92
-    else pitch_clip_pair<16>(A->p, g0, A->total_frames, A->smem->data() + w * kClipWarpSmemBytes, A->p.ds_idx);
+    unsigned char* wsm = A->smem->data() + w * kClipWarpSmemBytes;
+    const bool i16 = clip_i16_keys(A->p);
+    if (A->p.frame_len <= 320) {   // e.g. the 300-sample frames of model.py:92
+        if (i16) pitch_clip_run<10, true>(A->p, g0, A->total_frames, wsm, A->p.ds_idx); else pitch_clip_run<10, false>(A->p, g0, A->total_frames, wsm, A->p.ds_idx);
+    } else {
+        if (i16) pitch_clip_run<16, true>(A->p, g0, A->total_frames, wsm, A->p.ds_idx); else pitch_clip_run<16, false>(A->p, g0, A->total_frames, wsm, A->p.ds_idx);
+    }
 }
 void track_body(void* a) {
     Args* A = (Args*)a;
@@ -84,7 +89,7 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
     p.clip = clip.data();
     std::vector<unsigned char> smem0(kPitchWarps * kClipWarpSmemBytes + 64);
     Args A0{p, &smem0, fo};
-    for (int64_t b = 0; b * 2 * kPitchWarps < fo + 2 * kPitchWarps; ++b) {
+    for (int64_t b = 0; b * kClipRun * kPitchWarps < fo + kClipRun * kPitchWarps; ++b) {
         std::memset(smem0.data(), 0xCD, smem0.size());
         if (!emu::run_cta((int)b, 32 * kPitchWarps, clip_body, &A0)) { std::snprintf(errbuf, errcap, "deadlock in clip CTA %lld", (long long)b); return -3; }
     }
@@ -94,7 +99,7 @@ extern "C" long long emu_pitch(const dspfe_pitch_params* q, const void* pcm, int
         std::memset(smem.data(), 0xCD, smem.size());
         if (!emu::run_cta((int)b, 32 * kPitchWarps, frame_body, &A)) { std::snprintf(errbuf, errcap, "deadlock in frame CTA %lld", (long long)b); return -3; }
     }
-    std::vector<unsigned char> smem2((track_chunk(p.row_len) + 1) * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + kTrackMaxFrames * 12 + 64);
+    std::vector<unsigned char> smem2((track_chunk(p.row_len) + 1) * p.row_len * sizeof(float) + kTrackChunk * kPeakLags * sizeof(int) + kTrackMaxFrames * 12 + (kTrackThreads / 32) * kTrackListPerWarp * 2 + 8 + 64);
     Args B{p, &smem2, fo};
     for (int u = 0; u < n_utt; ++u) {
         std::memset(smem2.data(), 0xCD, smem2.size());

@@ -217,3 +217,27 @@ def test_other_sample_rates(rate):
             tot += pitchcheck.check_lags(method, pcm[off[u]:off[u + 1]], rate, lag[fo[u]:fo[u + 1]], pitch[fo[u]:fo[u + 1]],
                                          what=f"rate {rate} method {method} utterance {u}")
         pitchcheck.record(f"other_sample_rates[{rate},{method}]", *tot)
+
+
+@pytest.mark.parametrize("row_len", [100, 200, 203, 512])
+def test_peak_score_adversarial_rows(row_len):
+    """peak_score (pitch.py:227-242) through the rows tap (dspfe_track_rows_f32, the same warp routine K4b runs): plateaus,
+    constant rows, ramps, isolated spikes, NaN samples and NaN lags, for row lengths with and without a partial last block."""
+    import dspfe
+    from oracle import ref_features as O
+    rng = np.random.default_rng(row_len)
+    n = np.arange(row_len, dtype=np.float64)
+    rows = [np.ones(row_len), n.copy(), -n, np.cos(n / 7.0), np.floor(np.cos(n / 5.0) * 3) / 3, rng.standard_normal(row_len),
+            np.round(rng.standard_normal(row_len) * 2) / 2, np.where(n == 0, 100.0, 0.0), np.where(n == 60, 5.0, np.cos(n / 9.0))]
+    r = rng.standard_normal(row_len); r[[3, 41, 77]] = np.nan; rows.append(r)
+    r = np.cos(n / 11.0); r[50] = np.nan; rows.append(r)
+    r = np.zeros(row_len); r[1] = 1.0; rows.append(r)
+    r = np.zeros(row_len); r[row_len - 1] = 1.0; rows.append(r)
+    for k in range(40):                                   # smooth random rows of mixed scales: long scans on both sides
+        w = int(rng.integers(1, 40))
+        rows.append(np.convolve(rng.standard_normal(row_len + w), np.ones(w) / w, mode="valid")[:row_len])
+    rows = np.stack(rows).astype(np.float32)
+    _, score, lag = dspfe.smooth_rows_f32(rows, mode=0, want_score=True, want_lag=True, do_smooth=False)
+    want = np.array([O.peak_score(x) for x in rows])
+    np.testing.assert_array_equal(score, want)
+    np.testing.assert_array_equal(lag, 20 + np.argmax(want, axis=1))
