@@ -18,11 +18,11 @@ constexpr int kPitchPrepThreads = 1024;
 
 // per-utterance ranges, decimated lengths and the frame prefix sums (single CTA, no host round trip)
 __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchParams p) {
-    __shared__ long long s_fr[kPitchPrepThreads];
+    __shared__ long long s_fr[kPitchPrepThreads], s_sl[kPitchPrepThreads];
     const int tid = threadIdx.x;
     const int per = (p.n_utt + kPitchPrepThreads - 1) / kPitchPrepThreads;
     const int u0 = min(tid * per, p.n_utt), u1 = min(u0 + per, p.n_utt);
-    long long fr = 0;
+    long long fr = 0, sl = 0;
     for (int u = u0; u < u1; ++u) {
         long long a = p.offsets[u], len = p.offsets[u + 1] - a;
         if (p.trim) {  // Python slice sig[l:r] with l, r >= 0
@@ -34,22 +34,24 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
         p.seg_start[u] = a; p.seg_len[u] = (int)len;
         const long long ld = ds_length(len, p.ds_idx, p.ds_in, p.ds_out);
         p.ds_len[u] = (int)ld;
-        fr += num_frames(ld, p.frame_len, p.frame_step);
+        const long long nf = num_frames(ld, p.frame_len, p.frame_step);
+        fr += nf; sl += (nf + kClipRun - 1) / kClipRun * kClipRun;
     }
-    s_fr[tid] = fr;
+    s_fr[tid] = fr; s_sl[tid] = sl;
     __syncthreads();
     for (int d = 1; d < kPitchPrepThreads; d <<= 1) {
-        long long f = tid >= d ? s_fr[tid - d] : 0;
+        long long f = tid >= d ? s_fr[tid - d] : 0, g = tid >= d ? s_sl[tid - d] : 0;
         __syncthreads();
-        s_fr[tid] += f;
+        s_fr[tid] += f; s_sl[tid] += g;
         __syncthreads();
     }
-    long long fo = s_fr[tid] - fr;
+    long long fo = s_fr[tid] - fr, so = s_sl[tid] - sl;
     for (int u = u0; u < u1; ++u) {
-        p.frame_off[u] = fo;
-        fo += num_frames(p.ds_len[u], p.frame_len, p.frame_step);
+        p.frame_off[u] = fo; p.slot_off[u] = so;
+        const long long nf = num_frames(p.ds_len[u], p.frame_len, p.frame_step);
+        fo += nf; so += (nf + kClipRun - 1) / kClipRun * kClipRun;
     }
-    if (tid == kPitchPrepThreads - 1) p.frame_off[p.n_utt] = s_fr[tid];
+    if (tid == kPitchPrepThreads - 1) { p.frame_off[p.n_utt] = s_fr[tid]; p.slot_off[p.n_utt] = s_sl[tid]; }
 }
 
 // K4a-1: gather + exact median + centre clip, a frame pair per warp
@@ -57,15 +59,15 @@ template <bool I16>
 __global__ void __launch_bounds__(32 * kPitchWarps, 5) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t* ds_idx = reinterpret_cast<int32_t*>(smem);
-    const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
+    const int64_t total = p.slot_off[p.n_utt];
     if (kClipRun * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // the grid is sized for the untrimmed batch
     for (int i = threadIdx.x; i < p.ds_out; i += blockDim.x) ds_idx[i] = p.ds_idx[i];
     __syncthreads();
     const int w = threadIdx.x >> 5;
-    const int64_t g0 = kClipRun * ((int64_t)blockIdx.x * kPitchWarps + w);
-    if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
-    if (p.frame_len <= 320) pitch_clip_run<10, I16>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);   // e.g. the 300-sample frames of model.py:92
-    else pitch_clip_run<16, I16>(p, g0, total, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
+    const int64_t h0 = kClipRun * ((int64_t)blockIdx.x * kPitchWarps + w);
+    if (h0 >= total) return;   // whole warp leaves; only warp-level syncs below
+    if (p.frame_len <= 320) pitch_clip_run<10, I16>(p, h0, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);   // e.g. the 300-sample frames of model.py:92
+    else pitch_clip_run<16, I16>(p, h0, smem + kMaxDsOut * 4 + w * kClipWarpSmemBytes, ds_idx);
 }
 
 // K4a-2 / K5a-2: the transforms, a frame pair per warp.  At 128 registers (4 CTAs/SM) the chains spilled 130-230 bytes per
@@ -75,16 +77,19 @@ template <int MODE>
 __global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
-    constexpr int kPer = MODE == 2 ? 4 : 2;                              // frames per warp: a quad (pitch_acr_quad) or a pair
-    const int64_t total = p.frame_off[p.n_utt] < p.max_frames ? p.frame_off[p.n_utt] : p.max_frames;
+    constexpr int kPer = MODE == 2 ? 4 : 2;                              // slots per warp: a quad (pitch_acr_quad) or a pair
+    const int64_t total = p.slot_off[p.n_utt];
     if (kPer * (int64_t)blockIdx.x * kPitchWarps >= total) return;   // surplus CTAs leave before touching the tables
     for (int i = threadIdx.x; i < kTabMod; i += blockDim.x) tws[i] = p.tab[i];
     __syncthreads();
     const int w = threadIdx.x >> 5;
-    const int64_t g0 = kPer * ((int64_t)blockIdx.x * kPitchWarps + w);
-    if (g0 >= total) return;   // whole warp leaves; only warp-level syncs below
-    if (MODE == 2) pitch_acr_quad(p, g0, total, smem + kTabMod * 8 + w * kQuadWarpSmemBytes, tws, tws + kTabW32);
-    else pitch_fft_pair<(MODE == 2 ? 1 : MODE)>(p, g0, total, smem + kTabMod * 8 + w * kWarpSmemBytes, tws, tws + kTabW32);
+    const int64_t h0 = kPer * ((int64_t)blockIdx.x * kPitchWarps + w);
+    if (h0 >= total) return;   // whole warp leaves; only warp-level syncs below
+    int nvalid; int64_t g0;
+    slot_unit_from_desc(p, h0, kPer, g0, nvalid);
+    if (nvalid == 0) return;   // padding slots at the end of an utterance
+    if (MODE == 2) pitch_acr_quad(p, h0, g0, nvalid, smem + kTabMod * 8 + w * kQuadWarpSmemBytes, tws, tws + kTabW32);
+    else pitch_fft_pair<(MODE == 2 ? 1 : MODE)>(p, h0, g0, nvalid > 1, smem + kTabMod * 8 + w * kWarpSmemBytes, tws, tws + kTabW32);
 }
 
 __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid_constant__ PitchParams p) {
@@ -131,9 +136,9 @@ struct dspfe_pitch_plan {
     PitchParams base;          // scalars + table pointers; per-call pointers filled in launch
     float2* d_tab = nullptr;
     // workspaces
-    int64_t cap_utt = 0, cap_frames = 0;
-    int64_t* seg_start = nullptr; int32_t* seg_len = nullptr; int32_t* ds_len = nullptr; int64_t* frame_off = nullptr;
-    float2* clip = nullptr; float* rows = nullptr; double* frame_amp = nullptr; double* pitch = nullptr; int32_t* lag = nullptr; double* scratch = nullptr;
+    int64_t cap_utt = 0, cap_frames = 0, cap_slots = 0;
+    int64_t* seg_start = nullptr; int32_t* seg_len = nullptr; int32_t* ds_len = nullptr; int64_t* frame_off = nullptr; int64_t* slot_off = nullptr;
+    float2* clip = nullptr; int4* run_desc = nullptr; float* rows = nullptr; double* frame_amp = nullptr; double* pitch = nullptr; int32_t* lag = nullptr; double* scratch = nullptr;
     // host-path staging
     cudaStream_t stream = nullptr;
     void* d_pcm = nullptr; int64_t cap_bytes = 0;
@@ -144,24 +149,31 @@ namespace {
 
 int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
     if (n_utt + 1 > pl->cap_utt) {
-        cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off);
-        pl->seg_start = nullptr; pl->seg_len = nullptr; pl->ds_len = nullptr; pl->frame_off = nullptr; pl->cap_utt = 0;
+        cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off); cudaFree(pl->slot_off);
+        pl->seg_start = nullptr; pl->seg_len = nullptr; pl->ds_len = nullptr; pl->frame_off = nullptr; pl->slot_off = nullptr; pl->cap_utt = 0;
         CUDA_TRY(cudaMalloc(&pl->seg_start, (n_utt + 1) * sizeof(int64_t)));
         CUDA_TRY(cudaMalloc(&pl->seg_len, (n_utt + 1) * sizeof(int32_t)));
         CUDA_TRY(cudaMalloc(&pl->ds_len, (n_utt + 1) * sizeof(int32_t)));
         CUDA_TRY(cudaMalloc(&pl->frame_off, (n_utt + 1) * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&pl->slot_off, (n_utt + 1) * sizeof(int64_t)));
         pl->cap_utt = n_utt + 1;
     }
     if (frames > pl->cap_frames) {
-        cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch); cudaFree(pl->clip);
-        pl->clip = nullptr; pl->rows = nullptr; pl->frame_amp = nullptr; pl->pitch = nullptr; pl->lag = nullptr; pl->scratch = nullptr; pl->cap_frames = 0;
-        CUDA_TRY(cudaMalloc(&pl->clip, ((frames + 1) / 2) * 512 * sizeof(float2)));
+        cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
+        pl->rows = nullptr; pl->frame_amp = nullptr; pl->pitch = nullptr; pl->lag = nullptr; pl->scratch = nullptr; pl->cap_frames = 0;
         CUDA_TRY(cudaMalloc(&pl->rows, frames * pl->base.row_len * sizeof(float)));
         CUDA_TRY(cudaMalloc(&pl->frame_amp, frames * sizeof(double)));
         CUDA_TRY(cudaMalloc(&pl->pitch, frames * sizeof(double)));
         CUDA_TRY(cudaMalloc(&pl->lag, frames * sizeof(int32_t)));
         CUDA_TRY(cudaMalloc(&pl->scratch, 3 * frames * sizeof(double)));
         pl->cap_frames = frames;
+    }
+    const int64_t slots = frames + (kClipRun - 1) * n_utt;       // every utterance's frame count rounded up to a run
+    if (slots > pl->cap_slots) {
+        cudaFree(pl->clip); cudaFree(pl->run_desc); pl->clip = nullptr; pl->run_desc = nullptr; pl->cap_slots = 0;
+        CUDA_TRY(cudaMalloc(&pl->clip, ((slots + 1) / 2) * 512 * sizeof(float2)));
+        CUDA_TRY(cudaMalloc(&pl->run_desc, (slots / kClipRun + 1) * sizeof(int4)));
+        pl->cap_slots = slots;
     }
     return DSPFE_OK;
 }
@@ -209,8 +221,8 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
 void dspfe_pitch_destroy(dspfe_pitch_plan* pl) {
     if (!pl) return;
     cudaFree(pl->d_tab);
-    cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off);
-    cudaFree(pl->clip); cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
+    cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off); cudaFree(pl->slot_off);
+    cudaFree(pl->clip); cudaFree(pl->run_desc); cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
     cudaFree(pl->d_pcm); cudaFree(pl->d_off); cudaFree(pl->d_trim); cudaFree(pl->d_feat);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     delete pl;
@@ -260,20 +272,22 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     cudaStream_t st = (cudaStream_t)stream;
     PitchParams p = pl->base;
     p.pcm = d_pcm; p.in_f32 = sample_dtype; p.total_samples = total_samples; p.offsets = d_offsets; p.trim = d_trim; p.n_utt = n_utt;
-    p.frame_off = d_frame_off ? d_frame_off : pl->frame_off; p.seg_start = pl->seg_start; p.seg_len = pl->seg_len; p.ds_len = pl->ds_len;
-    p.clip = pl->clip; p.rows = d_rows ? d_rows : pl->rows; p.rows_out = nullptr; p.score = nullptr; p.frame_amp = pl->frame_amp;
+    p.frame_off = d_frame_off ? d_frame_off : pl->frame_off; p.slot_off = pl->slot_off; p.seg_start = pl->seg_start; p.seg_len = pl->seg_len; p.ds_len = pl->ds_len;
+    p.clip = pl->clip; p.run_desc = pl->run_desc; p.rows = d_rows ? d_rows : pl->rows; p.rows_out = nullptr; p.score = nullptr; p.frame_amp = pl->frame_amp;
     p.pitch = d_pitch ? d_pitch : pl->pitch; p.lag = d_lag ? d_lag : pl->lag; p.feat = d_feat; p.scratch = pl->scratch;
     p.max_frames = bound;
     pitch_prep_kernel<<<1, kPitchPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("pitch_prep_kernel", st);
-    const unsigned fgrid = (unsigned)((bound + 2 * kPitchWarps - 1) / (2 * kPitchWarps));
-    const unsigned cgrid = (unsigned)((bound + kClipRun * kPitchWarps - 1) / (kClipRun * kPitchWarps));
+    const int64_t slots = bound + (int64_t)(kClipRun - 1) * n_utt;
+    const unsigned cgrid = (unsigned)((slots + kClipRun * kPitchWarps - 1) / (kClipRun * kPitchWarps));
     if (clip_i16_keys(p)) pitch_clip_kernel<true><<<cgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
     else pitch_clip_kernel<false><<<cgrid, 32 * kPitchWarps, kClipCtaSmem, st>>>(p);
     LAUNCH_CHECK("pitch_clip_kernel", st);
     const int fmode = p.mode == 0 ? 0 : (acr_short_frames(p.frame_len, p.row_len) ? 2 : 1);
+    const int per = (fmode == 2 ? 4 : 2) * kPitchWarps;
+    const unsigned fgrid = (unsigned)((slots + per - 1) / per);
     if (fmode == 0) pitch_frame_kernel<0><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
-    else if (fmode == 2) pitch_frame_kernel<2><<<(fgrid + 1) / 2, 32 * kPitchWarps, kQuadCtaSmem, st>>>(p);
+    else if (fmode == 2) pitch_frame_kernel<2><<<fgrid, 32 * kPitchWarps, kQuadCtaSmem, st>>>(p);
     else pitch_frame_kernel<1><<<fgrid, 32 * kPitchWarps, kFrameCtaSmem, st>>>(p);
     LAUNCH_CHECK(fmode == 0 ? "pitch_frame_kernel<0>" : fmode == 2 ? "pitch_frame_kernel<2>" : "pitch_frame_kernel<1>", st);
     if (d_pitch || d_lag || d_feat) {

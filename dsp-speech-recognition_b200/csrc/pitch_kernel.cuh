@@ -49,6 +49,7 @@ constexpr int kWarpSmemBytes = kWarpScr * 8 + 512 * 16;              // transfor
 constexpr int kTabTw = 0, kTabW32 = kTabTw + 512, kTabMod = kTabW32 + 32, kTabHe = kTabMod + 512, kTabHo = kTabHe + 512,
               kTabTotal = kTabHo + 512;
 constexpr int kFrameCtaSmem = (kTabMod * 8) + kPitchWarps * kWarpSmemBytes;                      // shared tables | per-warp areas
+constexpr int kClipRun = 8;         // frames per warp of K4a-1, and the padding unit of the slot space (even: pairs never straddle two runs)
 constexpr int kTrackThreads = 256;
 constexpr int kTrackMaxFrames = 1024;   // utterances up to this many frames keep their lag / Hz track in shared memory
 constexpr int kTrackChunk = 32;     // frames smoothed per pass of K4b/K5b (16 for rows wider than 256 columns)
@@ -74,8 +75,12 @@ struct PitchParams {
     int mode;                            // 0 cepstrum, 1 autocorrelation
     int row_len;                         // columns per row: cepstrum 200 (fused) or 512 (tap); autocorrelation 180
     int64_t* frame_off;                  // [U+1] prefix sums of pitch frames
+    int64_t* slot_off;                   // [U+1] prefix sums of the frame counts rounded up to kClipRun: the work units of K4a/K5a (runs of 8,
+                                         //       quads, pairs) are cut in this padded index space, so none of them straddles two utterances and a
+                                         //       frame's result does not depend on what else is in the batch
     int64_t* seg_start; int32_t* seg_len; int32_t* ds_len;   // per utterance: trimmed range and decimated length
-    float2* clip;                        // [ceil(F_total/2), 512] clipped frame pairs (K4a-1 -> K4a-2)
+    float2* clip;                        // [slots/2, 512] clipped frame pairs in slot order (K4a-1 -> K4a-2)
+    int4* run_desc;                      // [slots/kClipRun] per run of slots: (first global frame lo, hi, frames that exist, utterance), written by K4a-1
     float* rows;                         // [F_total, row_len] raw rows (K4a/K5a output)
     float* rows_out;                     // optional: smoothed rows (tap of smooth, pitch.py:157)
     int32_t* score;                      // optional [F_total, 80]: peak_score of every smoothed row (tap)
@@ -364,6 +369,27 @@ DEVFN int find_utt(const int64_t* frame_off, int n_utt, int64_t g, int lane) {
     return lo;
 }
 
+// Work unit of `per` consecutive slots starting at slot h0 (a multiple of per, per | kClipRun): its utterance, the global index
+// of its first frame and how many of its frames exist (0: the unit is padding).
+DEVFN void slot_unit(const PitchParams& p, int64_t h0, int per, int lane, int& u, int64_t& g0, int& nvalid) {
+    u = find_utt(p.slot_off, p.n_utt, h0, lane);
+    const int64_t f0 = p.frame_off[u];
+    const int64_t local = h0 - p.slot_off[u], F = p.frame_off[u + 1] - f0;
+    const int64_t left = F - local;
+    nvalid = left <= 0 ? 0 : (left < per ? (int)left : per);
+    g0 = f0 + local;
+    if (g0 + nvalid > p.max_frames) nvalid = g0 < p.max_frames ? (int)(p.max_frames - g0) : 0;   // (outputs are sized by the bound: never taken)
+}
+
+// The same from the run descriptor K4a-1 left behind (one 16-byte load instead of a three-level search)
+DEVFN void slot_unit_from_desc(const PitchParams& p, int64_t h0, int per, int64_t& g0, int& nvalid) {
+    const int4 d = ldg(p.run_desc + h0 / kClipRun);
+    const int in_run = (int)(h0 % kClipRun);
+    const int left = d.z - in_run;
+    nvalid = left <= 0 ? 0 : (left < per ? left : per);
+    g0 = (((int64_t)d.y << 32) | (int64_t)(unsigned)d.x) + in_run;
+}
+
 // Source cursor of one frame for the gather through the sample-picking decimator (preprocess.py:21-28): the lane's
 // sample t sits at decimated index k = f*step + lane + 32 t, and k - 1 = a * ds_out + b is advanced by 32 per step
 // without a division (k = 0 starts from -1 = (-1, ds_out - 1)).
@@ -425,9 +451,10 @@ DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds
             const int16_t* q = reinterpret_cast<const int16_t*>(c.src) + s;
             cur = cvt_i16(q[0]); if (PRE && s > c.lim) prev = cvt_i16(q[-1]);
         }
-        // x[n] - c*x[n-1] with c = c_hi + c_lo split so that the float32 result is within an ulp of the float64 one;
-        // PRE = false (pre_hi = pre_lo = 0) leaves the sample as it is and skips the load of its predecessor
-        v = PRE ? dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur)) : cur;
+        // x[n] - c*x[n-1] in float64 with NumPy's two roundings (preprocess.py:18), then rounded to float32: exact zeros and
+        // signs as in the reference (they decide the membership of the median's sample set, pitch.py:146);
+        // PRE = false leaves the sample as it is and skips the load of its predecessor
+        v = PRE ? dsp_preemph_f64(p.preemph, cur, prev) : cur;
     }
     c.a += p.ds_q32; c.b += p.ds_r32;
     if (c.b >= p.ds_out) { c.b -= p.ds_out; ++c.a; }
@@ -439,19 +466,12 @@ DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds
 // (512 samples every 100), so the run's source span is staged once (16-byte loads), walked once through the sample-picking
 // decimator (and the pre-emphasis) into a float buffer of decimated samples, and every frame of the run then reads its
 // samples from that buffer with plain contiguous loads -- the index arithmetic is paid per decimated sample, not per
-// sample per frame.  A run that crosses an utterance boundary restages at the boundary.
+// sample per frame.  Runs are cut in the padded slot space (PitchParams::slot_off): a run belongs to one utterance.
 // wsm: per-warp shared memory = stage[kClipStageBytes] | dec[kClipDecCap] float.
-constexpr int kClipRun = 8;                  // frames per warp (even: pairs never straddle two warps)
 constexpr int kClipStageBytes = 4096;        // source span of a run: 1212 decimated samples are 3.9 KB of int16 at 16 -> 10 kHz
 constexpr int kClipDecCap = 1280;               // floats: 7 * 100 + 512 decimated samples of a run, rounded up to the unrolled row count
 constexpr int kClipWarpSmemBytes = kClipStageBytes + kClipDecCap * 4;
 constexpr int kClipCtaSmem = kMaxDsOut * 4 + kPitchWarps * kClipWarpSmemBytes;
-struct ClipRun {                             // the staged part of one utterance
-    int u;                                   // utterance (-1: nothing staged)
-    int64_t f_lo, f_hi;                      // global frames whose samples are in dec
-    int kf_lo;                               // decimated index of dec[0] inside the utterance
-    int Ld;                                  // decimated length of the utterance
-};
 template <bool F32, bool PRE>
 DEVFN void decimate_span(const PitchParams& p, FrameCursor& c, const int32_t* ds_idx, float* dec, int lane, int rows) {
 #pragma unroll 1
@@ -460,82 +480,66 @@ DEVFN void decimate_span(const PitchParams& p, FrameCursor& c, const int32_t* ds
         for (int j = 0; j < 4; ++j) dec[32 * (t0 + j) + lane] = frame_sample<F32, PRE>(p, c, ds_idx, t0 + j);
     }
 }
-// stages frames [g, g_hi) of utterance u (as many as the buffers hold) and fills dec
-DEVFN void clip_stage_run(const PitchParams& p, ClipRun& r, int u, int64_t g, int64_t g_hi, int lane, unsigned char* stage, float* dec,
-                          const int32_t* ds_idx) {
-    const int L = p.frame_len, step = p.frame_step;
-    int nf = (int)(g_hi - g);
-    const int fit = (kClipDecCap - L) / step + 1;                     // frames whose samples fit dec
-    nf = nf < fit ? nf : fit;
-    const int span = (nf - 1) * step + L;
-    simt::warp_sync();                                                // every lane has finished reading the previous run
-    FrameCursor c = frame_cursor(p, g, u, lane, true, stage, span, kClipStageBytes);
-    const int rows = (((span + 31) >> 5) + 3) & ~3;                   // rows of 32 decimated samples, rounded to the unroll (rows past the span give zeros)
-    const bool pre = p.pre_hi != 0.f || p.pre_lo != 0.f;
-    if (p.in_f32) { if (pre) decimate_span<true, true>(p, c, ds_idx, dec, lane, rows); else decimate_span<true, false>(p, c, ds_idx, dec, lane, rows); }
-    else { if (pre) decimate_span<false, true>(p, c, ds_idx, dec, lane, rows); else decimate_span<false, false>(p, c, ds_idx, dec, lane, rows); }
-    simt::warp_sync();
-    r.u = u; r.f_lo = g; r.f_hi = g + nf; r.kf_lo = (int)(g - p.frame_off[u]) * step; r.Ld = p.ds_len[u];
-}
-template <int NT>
-DEVFN void clip_fetch_frame(const PitchParams& p, ClipRun& r, int64_t g, int64_t g_end, int lane, unsigned char* stage, float* dec,
-                            const int32_t* ds_idx, float (&x)[NT], float& amp) {
-    if (r.u < 0 || g < r.f_lo || g >= r.f_hi) {
-        int u = r.u;
-        if (u < 0 || g < p.frame_off[u] || g >= p.frame_off[u + 1]) u = find_utt(p.frame_off, p.n_utt, g, lane);
-        const int64_t u_end = p.frame_off[u + 1];
-        clip_stage_run(p, r, u, g, g_end < u_end ? g_end : u_end, lane, stage, dec, ds_idx);
-    }
-    const int base = (int)(g - r.f_lo) * p.frame_step;
-    const int kf = r.kf_lo + base;
-    const int cnt = p.frame_len < r.Ld - kf ? p.frame_len : r.Ld - kf;    // samples of the frame inside the decimated signal; zeros after
-    amp = 0.f;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        const int n = 32 * t + lane;
-        const float v = n < cnt ? dec[base + n] : 0.f;
-        x[t] = v; amp += fabsf(v);
-    }
-}
 // I16: raw int16 samples (no pre-emphasis, no float input): integer keys for the median
 DSP_HD bool clip_i16_keys(const PitchParams& p) { return !p.in_f32 && p.pre_hi == 0.f && p.pre_lo == 0.f; }
+// h0: first slot of the run (a multiple of kClipRun)
 template <int NT, bool I16>
-DEVFN void pitch_clip_run(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const int32_t* ds_idx) {
+DEVFN void pitch_clip_run(const PitchParams& p, int64_t h0, unsigned char* wsm, const int32_t* ds_idx) {
     const int lane = simt::tid() & 31;
     unsigned char* stage = wsm;
     float* dec = reinterpret_cast<float*>(wsm + kClipStageBytes);
-    const int L = p.frame_len;
-    const int64_t g_end = g0 + kClipRun < total ? g0 + kClipRun : total;
-    ClipRun run; run.u = -1; run.f_lo = run.f_hi = 0; run.kf_lo = 0; run.Ld = 0;
+    const int L = p.frame_len, step = p.frame_step;
+    int u, nf; int64_t g0;
+    slot_unit(p, h0, kClipRun, lane, u, g0, nf);
+    if (lane == 0) p.run_desc[h0 / kClipRun] = make_int4((int)(g0 & 0xffffffffll), (int)(g0 >> 32), nf, u);   // spares K4a-2 / K5a-2 the search
+    if (nf == 0) return;
+    const int Ld = p.ds_len[u];
+    const int kf0 = (int)(g0 - p.frame_off[u]) * step;              // decimated index of the run's first sample inside the utterance
+    const int fit = ((kClipDecCap - L) / step + 1) & ~1;              // frames whose samples fit dec at once (8 for 512 / 100); even: pairs stay together
 #pragma unroll 1
-    for (int64_t g = g0; g < g_end; g += 2) {
-        const bool hasB = g + 1 < total;
-        float xa[NT], xb[NT], fa, fb = 0.f;
-        clip_fetch_frame<NT>(p, run, g, g_end, lane, stage, dec, ds_idx, xa, fa);
-        if (hasB) clip_fetch_frame<NT>(p, run, g + 1, g_end, lane, stage, dec, ds_idx, xb, fb);
-        else {
+    for (int j0 = 0; j0 < nf; j0 += fit) {                            // (one pass unless the framing is unusual)
+        const int nj = nf - j0 < fit ? nf - j0 : fit;
+        const int span = (nj - 1) * step + L;
+        simt::warp_sync();
+        FrameCursor c = frame_cursor(p, g0 + j0, u, lane, true, stage, span, kClipStageBytes);
+        const int rows = (((span + 31) >> 5) + 3) & ~3;               // rows of 32 decimated samples, rounded to the unroll (rows past the span give zeros)
+        const bool pre = p.pre_hi != 0.f || p.pre_lo != 0.f;
+        if (p.in_f32) { if (pre) decimate_span<true, true>(p, c, ds_idx, dec, lane, rows); else decimate_span<true, false>(p, c, ds_idx, dec, lane, rows); }
+        else { if (pre) decimate_span<false, true>(p, c, ds_idx, dec, lane, rows); else decimate_span<false, false>(p, c, ds_idx, dec, lane, rows); }
+        simt::warp_sync();
+#pragma unroll 1
+        for (int j = j0; j < j0 + nj; j += 2) {
+            const bool hasB = j + 1 < nf && j + 1 < j0 + nj;
+            float xa[NT], xb[NT], fa = 0.f, fb = 0.f;
+            const int base = (j - j0) * step;
+            const int cnta = L < Ld - (kf0 + j * step) ? L : Ld - (kf0 + j * step);          // samples inside the decimated signal; zeros after
+            const int cntb = hasB ? (L < Ld - (kf0 + (j + 1) * step) ? L : Ld - (kf0 + (j + 1) * step)) : 0;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) xb[t] = 0.f;
-        }
-        // sum |x| of the raw frames (sub_endpoint_detect, pitch.py:65) in float64 across the warp
-        if (p.frame_amp) {
-            double sa = (double)fa, sb = (double)fb;
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
-            if (lane == 0) { p.frame_amp[g] = sa; if (hasB) p.frame_amp[g + 1] = sb; }
-        }
-        // centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
-        float2 med = make_float2(0.f, 0.f);
-        if (p.do_clip) med = I16 ? warp_median_nonneg2_i16<NT>(xa, xb, L, lane) : warp_median_nonneg2<NT>(xa, xb, L, lane);
-        float2* dst = p.clip + (g >> 1) * 512;
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            float2 o = make_float2(0.f, 0.f);
-            if (t < NT && lane + 32 * t < L) {
-                o.x = p.do_clip ? clip_value(xa[t < NT ? t : 0], med.x) : xa[t < NT ? t : 0];
-                o.y = p.do_clip ? clip_value(xb[t < NT ? t : 0], med.y) : xb[t < NT ? t : 0];
+            for (int t = 0; t < NT; ++t) {
+                const int n = 32 * t + lane;
+                const float va = n < cnta ? dec[base + n] : 0.f, vb = n < cntb ? dec[base + step + n] : 0.f;
+                xa[t] = va; xb[t] = vb; fa += fabsf(va); fb += fabsf(vb);
             }
-            dst[32 * t + lane] = o;
+            // sum |x| of the raw frames (sub_endpoint_detect, pitch.py:65) in float64 across the warp
+            if (p.frame_amp) {
+                double sa = (double)fa, sb = (double)fb;
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) { sa += shfl32_xor_f64(sa, m); sb += shfl32_xor_f64(sb, m); }
+                if (lane == 0) { p.frame_amp[g0 + j] = sa; if (hasB) p.frame_amp[g0 + j + 1] = sb; }
+            }
+            // centre clip at the median of the non-negative samples (pitch.py:145-155); padding zeros are samples too
+            float2 med = make_float2(0.f, 0.f);
+            if (p.do_clip) med = I16 ? warp_median_nonneg2_i16<NT>(xa, xb, L, lane) : warp_median_nonneg2<NT>(xa, xb, L, lane);
+            float2* dst = p.clip + ((h0 + j) >> 1) * 512;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                float2 o = make_float2(0.f, 0.f);
+                if (t < NT && lane + 32 * t < L) {
+                    o.x = p.do_clip ? clip_value(xa[t < NT ? t : 0], med.x) : xa[t < NT ? t : 0];
+                    o.y = p.do_clip ? clip_value(xb[t < NT ? t : 0], med.y) : xb[t < NT ? t : 0];
+                }
+                dst[32 * t + lane] = o;
+            }
         }
     }
 }
@@ -552,15 +556,15 @@ DEVFN void pitch_clip_run(const PitchParams& p, int64_t g0, int64_t total, unsig
 // take pitch_acr_quad below instead (3 transforms per pair).
 // wsm: per-warp shared memory = scr[kWarpScr] float2 | park[512] float4.
 template <int MODE>
-DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
+// h0: the pair's first slot (even); g0: global index of its first frame; hasB: the second frame exists
+DEVFN void pitch_fft_pair(const PitchParams& p, int64_t h0, int64_t g0, bool hasB, unsigned char* wsm, const float2* tws, const float2* w32s) {
     const int lane = simt::tid() & 31;
     float2* scr = reinterpret_cast<float2*>(wsm);
     float4* park = reinterpret_cast<float4*>(scr + kWarpScr);
-    float2* xs = p.clip + (g0 >> 1) * 512;      // the clipped frame pair (global memory; the autocorrelation path reuses it for |y|)
+    float2* xs = p.clip + (h0 >> 1) * 512;      // the clipped frame pair (global memory; the autocorrelation path reuses it for |y|)
     const float2* modA = p.tab + kTabMod;   // W1024^n, n = 32 t + lane
     const float2* HeB = p.tab + kTabHe;     // H1024[2k], k = 32 t + lane
     const float2* HoB = p.tab + kTabHo;     // H1024[2k+1]
-    const bool hasB = g0 + 1 < total;
     const int L = p.frame_len;
     // (every lane only ever touches its own xs / park entries: no barrier needed around them)
     cpx2 x[16];
@@ -587,12 +591,15 @@ DEVFN void pitch_fft_pair(const PitchParams& p, int64_t g0, int64_t total, unsig
                 x[t].re = f2muls(xv, m.x); x[t].im = f2muls(xv, m.y);
             }
         }
-        const float cj = inv ? -1.f : 1.f;                   // inverse = conj . forward . conj
+        if (inv) {                                           // inverse = conj . forward . conj
 #pragma unroll
-        for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
+            for (int t = 0; t < 16; ++t) x[t].im = f2neg(x[t].im);
+        }
         fft512<true>(x, scr, tws, w32s, lane);
+        if (inv) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) x[t].im = f2muls(x[t].im, cj);
+            for (int t = 0; t < 16; ++t) x[t].im = f2neg(x[t].im);
+        }
         // ---- pointwise table products: He / Ho after a forward transform, conj(W1024^n) after the FIR's inverse
         const bool mulH = MODE == 0 ? st <= 1 : (st == 0 || st == 2);
         const bool mulM = MODE == 0 ? st == 2 : st == 3;
@@ -727,7 +734,8 @@ DEVFN void split_pairs(cpx2 (&x)[16], const float2* A, const float2* B, int lane
         }
     }
 }
-DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
+// h0: the quad's first slot (a multiple of 4); g0: global index of its first frame; nvalid: how many of its frames exist (1..4)
+DEVFN void pitch_acr_quad(const PitchParams& p, int64_t h0, int64_t g0, int nvalid, unsigned char* wsm, const float2* tws, const float2* w32s) {
     const int lane = simt::tid() & 31;
     float2* scr = reinterpret_cast<float2*>(wsm);
     float2* vpark = scr + kWarpScr;
@@ -735,8 +743,9 @@ DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsig
     const float2* tabB = p.tab + kTabHo;
     const int L = p.frame_len;
     const int nlo = 2 * L - 514;                      // x_lo = x[0 .. L - T - 2], T = 512 - L
-    const bool has2 = g0 + 2 < total;                 // the second pair exists (its slot was written by the clip kernel)
+    const bool has2 = nvalid > 2;                     // the second pair exists (its slot was written by the clip kernel)
     const float2 zero2 = make_float2(0.f, 0.f);
+    float2 unscale = make_float2(1.f, 1.f);
     cpx2 x[16];
     // stage 0 F(x + i x_lo) of pair 1 -> Z A + Zr* B      1 inverse -> v1 = |y|, parked
     //       2 the same for pair 2                            3 inverse -> v2;  z = v1 + i v2
@@ -745,7 +754,7 @@ DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsig
     for (int st = 0; st < 6; ++st) {
         const bool inv = st & 1;
         if (st == 0 || st == 2) {
-            const float2* xs = p.clip + ((g0 >> 1) + (st >> 1)) * 512;
+            const float2* xs = p.clip + ((h0 >> 1) + (st >> 1)) * 512;
             const bool live = st == 0 || has2;
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
@@ -774,10 +783,27 @@ DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsig
 #pragma unroll
                 for (int t = 0; t < kQuadT; ++t) vpark[32 * t + lane] = v[t];      // (a lane only ever touches its own entries)
             } else {
+                // Rounding errors of a complex transform leak between its real and imaginary parts at ~1e-7 of the LARGER one:
+                // bring the second pair to the first pair's level with a power of two (exact) before packing, undo it after.
+                float2 e1 = zero2, e2 = zero2;
+#pragma unroll
+                for (int t = 0; t < kQuadT; ++t) { const float2 a = vpark[32 * t + lane]; x[t].re = a; e1 = f2fma(a, a, e1); e2 = f2fma(v[t], v[t], e2); }
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    e1.x += simt::shfl32_xor(e1.x, m); e1.y += simt::shfl32_xor(e1.y, m);
+                    e2.x += simt::shfl32_xor(e2.x, m); e2.y += simt::shfl32_xor(e2.y, m);
+                }
+                int kx = ((__float_as_int_compat(e1.x) >> 23) - (__float_as_int_compat(e2.x) >> 23)) / 2;    // half the exponent gap of the energies
+                int ky = ((__float_as_int_compat(e1.y) >> 23) - (__float_as_int_compat(e2.y) >> 23)) / 2;
+                if (!(e1.x > 0.f && e2.x > 0.f && e1.x < 3e38f && e2.x < 3e38f)) kx = 0;
+                if (!(e1.y > 0.f && e2.y > 0.f && e1.y < 3e38f && e2.y < 3e38f)) ky = 0;
+                kx = kx < -40 ? -40 : (kx > 40 ? 40 : kx); ky = ky < -40 ? -40 : (ky > 40 ? 40 : ky);
+                const float2 sc2 = make_float2(__int_as_float_compat((127 + kx) << 23), __int_as_float_compat((127 + ky) << 23));
+                unscale = make_float2(__int_as_float_compat((127 - 2 * kx) << 23), __int_as_float_compat((127 - 2 * ky) << 23));
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    x[t].re = t < kQuadT ? vpark[32 * (t < kQuadT ? t : 0) + lane] : zero2;
-                    x[t].im = t < kQuadT ? v[t < kQuadT ? t : 0] : zero2;
+                    if (t >= kQuadT) x[t].re = zero2;
+                    x[t].im = t < kQuadT ? f2mul(v[t < kQuadT ? t : 0], sc2) : zero2;
                 }
             }
         } else if (st == 4) {
@@ -786,7 +812,7 @@ DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsig
             const float inv512 = 1.0f / 512.0f;
             float* row = p.rows + g0 * p.row_len;
             const int RL = p.row_len;
-            const bool f1 = g0 + 1 < total, f2 = g0 + 2 < total, f3 = g0 + 3 < total;
+            const bool f1 = nvalid > 1, f2 = nvalid > 2, f3 = nvalid > 3;
 #pragma unroll
             for (int t = 0; t < 7; ++t) {
                 const int n = 32 * t + lane, j = n - kMinLag;
@@ -794,8 +820,8 @@ DEVFN void pitch_acr_quad(const PitchParams& p, int64_t g0, int64_t total, unsig
                     const float sc = (n < L) ? inv512 / (float)(L - n) : NAN;
                     row[j] = x[t].re.x * sc;
                     if (f1) row[RL + j] = x[t].re.y * sc;
-                    if (f2) row[2 * RL + j] = -x[t].im.x * sc;       // the inverse is conj . forward . conj: its imaginary part is
-                    if (f3) row[3 * RL + j] = -x[t].im.y * sc;       // minus the imaginary part left in the registers
+                    if (f2) row[2 * RL + j] = -x[t].im.x * unscale.x * sc;   // the inverse is conj . forward . conj: its imaginary part is
+                    if (f3) row[3 * RL + j] = -x[t].im.y * unscale.y * sc;   // minus the imaginary part left in the registers
                 }
             }
         }

@@ -47,6 +47,7 @@ inline int build_pitch_tables(const dspfe_pitch_params& q, PitchParams& b, std::
     if (q.method != 0 && q.method != 1) { err = "method must be 0 (cepstrum) or 1 (autocorrelation)"; return DSPFE_ERR_INVALID_ARG; }
     if (q.method == 0 && q.frame_len != kCepLen) { err = "the cepstrum kernel is built for 512-sample frames"; return DSPFE_ERR_UNSUPPORTED; }
     if (q.method == 1 && (q.frame_len <= kMinLag || q.frame_len > 512)) { err = "autocorrelation frames must have 21..512 samples"; return DSPFE_ERR_UNSUPPORTED; }
+    if (q.frame_len + q.frame_step > kClipDecCap) { err = "frame_step too large: two frames must fit the clip kernel's sample buffer"; return DSPFE_ERR_UNSUPPORTED; }
     // decimator pattern (preprocess.py:21-28): the k-th kept sample (k >= 1) is floor((k-1)*src/dst) + 1
     if (q.dst_rate >= q.samplerate) { b.ds_in = 1; b.ds_out = 1; b.ds_idx[0] = 1; }
     else {

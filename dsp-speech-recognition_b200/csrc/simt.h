@@ -55,6 +55,7 @@ DEVFN float cvt_hi16(uint32_t w) { return (float)(int16_t)(w >> 16); }
 struct uint4 { uint32_t x, y, z, w; };
 struct int4 { int x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #else
 // ---------------------------------------------------------------- sm_100a device build
 #include <cuda_runtime.h>
@@ -181,6 +182,19 @@ DEVFN double shfl32_f64(double v, int src) {
     double r; std::memcpy(&r, w, 8); return r;
 #else
     return __hiloint2double(simt::shfl32_i(__double2hiint(v), src), simt::shfl32_i(__double2loint(v), src));
+#endif
+}
+
+// pre-emphasis cur - c * prev exactly as NumPy evaluates it in float64 (product rounded, then the difference rounded; no
+// contraction), rounded once more to float32: the sign and the exact zeros of the result decide which samples enter the
+// median of center_clip, so they must not depend on a float32 evaluation order
+DEVFN float dsp_preemph_f64(double c, float cur, float prev) {
+#ifdef DSPFE_EMU
+    volatile double prod = c * (double)prev;
+    volatile double diff = (double)cur - prod;
+    return (float)diff;
+#else
+    return (float)__dsub_rn((double)cur, __dmul_rn(c, (double)prev));
 #endif
 }
 

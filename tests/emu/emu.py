@@ -131,3 +131,13 @@ def pitch(pcm, offsets, trim=None, method=0, samplerate=16000, dst_rate=10000, f
         if sc is not None:
             out["score"] = sc[:r]
     return out
+
+
+def median2(a, b, i16=False):
+    """The warp's dual exact median (np.median(frame[frame >= 0]) of two frames at once)."""
+    a = np.ascontiguousarray(a, dtype=np.float32); b = np.ascontiguousarray(b, dtype=np.float32)
+    assert a.shape == b.shape and a.ndim == 1 and len(a) <= 512
+    out = np.zeros(2, dtype=np.float32)
+    rc = lib().emu_median2(a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), len(a), int(i16), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return out

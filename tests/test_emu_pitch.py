@@ -113,3 +113,50 @@ def test_short_frame_autocorrelation_quads(frame_len):
         assert np.max(np.abs(got[fin] - want[fin])) <= 5e-5 * np.max(np.abs(want[fin])), u
         p_want, _ = O.pitch_detect_sr(x, 16000, winlen=frame_len / 10000.0, step=0.01)
         assert np.mean(r["pitch"][r["frame_off"][u]:r["frame_off"][u + 1]] != np.asarray(p_want)) <= 0.02
+
+
+def test_preemphasis_zeros_keep_the_median_sample_set():
+    """x[n] = 97 j after x[n-1] = 100 j gives x[n] - 0.97 x[n-1] == 0.0 exactly in the reference's float64 (a member of
+    center_clip's `frame >= 0` set, pitch.py:146); a float32 evaluation leaves +-1e-13 there, flips the parity of the set and
+    moves the median by a whole order statistic (found on the 8192-utterance bench batch: cepstrum rows off by 1e-3).  The kernel
+    evaluates the pre-emphasis in float64 with NumPy's two roundings."""
+    rng = np.random.default_rng(3)
+    x = synth.synth_utterance(77, 16000).astype(np.int64)
+    for k in rng.integers(200, 15800, size=400):                # plant exact zeros of the pre-emphasised signal
+        j = int(rng.integers(-80, 80))
+        x[k - 1], x[k] = 100 * j, 97 * j
+    x = x.astype(np.int16)
+    pre = O.preemphasis(x, 0.97)
+    assert np.sum(pre == 0.0) >= 300
+    r = emu.pitch(x, [0, len(x)], method=0, preemph=0.97, want_rows=True, row_len=512)
+    fr = O.to_frames(O.downsampling(pre, 16000, 10000), 10000, 0.0512, 0.01)
+    ce = O.pitch_detect_frame(O.center_clip(fr, False), 10000)
+    assert np.max(np.abs(r["rows"] - ce)) <= 1e-5 * np.max(np.abs(ce))
+    np.testing.assert_array_equal(r["pitch"], O.pitch_detect(pre, 16000)[0])
+
+
+@pytest.mark.parametrize("i16", [False, True])
+def test_dual_median_adversarial(i16):
+    """The warp's exact dual median (bit-sliced radix select) against np.median(frame[frame >= 0]): ties, duplicates around the
+    middle, zeros and negative zeros, even / odd counts, no non-negative sample, short frames."""
+    rng = np.random.default_rng(11 + i16)
+    def ref(v):
+        nn = v[v >= 0]
+        return np.float32(np.median(nn.astype(np.float64))) if len(nn) else np.float32(np.nan)
+    cases = []
+    for L in (512, 511, 300, 33, 1):
+        for _ in range(6):
+            if i16:
+                a = rng.integers(-32768, 32768, size=L).astype(np.float32)
+                b = (rng.integers(-50, 50, size=L) * rng.integers(0, 3, size=L)).astype(np.float32)      # many duplicates and zeros
+            else:
+                a = (rng.standard_normal(L) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+                b = np.round(rng.standard_normal(L) * 3).astype(np.float32) / 4
+                b[rng.integers(0, L, size=max(L // 8, 1))] = -0.0
+            cases.append((a, b))
+        cases.append((-np.ones(L, dtype=np.float32), np.zeros(L, dtype=np.float32)))                      # empty set / all zeros
+        cases.append((np.full(L, 7, dtype=np.float32), np.arange(L, dtype=np.float32) - L // 2))
+    for a, b in cases:
+        got = emu.median2(a, b, i16=i16)
+        for g, w in zip(got, (ref(a), ref(b))):
+            assert (np.isnan(g) and np.isnan(w)) or g == w, (len(a), g, w)
