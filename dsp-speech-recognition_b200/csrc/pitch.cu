@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
 }
 
 // K4a-1: gather + exact median + centre clip, a frame pair per warp
+// (4 CTAs/SM at 128 registers without spills beat 5 CTAs/SM at 96 with 100-180 bytes of them)
 template <bool I16>
-__global__ void __launch_bounds__(32 * kPitchWarps, 5) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
+__global__ void __launch_bounds__(32 * kPitchWarps, 4) pitch_clip_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t* ds_idx = reinterpret_cast<int32_t*>(smem);
     const int64_t total = p.slot_off[p.n_utt];
@@ -102,6 +103,40 @@ __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid
 __global__ void __launch_bounds__(32) pitch_feature_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     pitch_feature_warp(p, blockIdx.x, reinterpret_cast<double*>(smem));
+}
+
+// dp_max_pitch (pitch.py:208-225) on the device: Viterbi over the columns of g [n_rows, n_cols] with a jump penalty of 5 per
+// column, one CTA, thread j owns column j.  Per row every thread maximises dp[k] - 5 |k - j| + g[i][j] over k in float64 with the
+// reference's evaluation order and first-maximum tie rule; the back-trace starts, as in the reference, from the predecessor
+// chosen for the LAST column of the last row (`step` as the Python loops leave it), not from the best end state.
+constexpr int kDpMaxCols = 1024;
+__global__ void __launch_bounds__(kDpMaxCols) dp_max_pitch_kernel(const double* g, int n_rows, int n_cols, int32_t* prev, double* path) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* dp = reinterpret_cast<double*>(smem);            // [2][n_cols]
+    const int j = threadIdx.x;
+    if (j < n_cols) dp[j] = 0.0;                                // dp[0] = zeros (np.zeros, row 0 is never scored)
+    __syncthreads();
+    for (int i = 1; i < n_rows; ++i) {
+        const double* cur = dp + ((i - 1) & 1) * n_cols;
+        double* nxt = dp + (i & 1) * n_cols;
+        if (j < n_cols) {
+            const double gij = g[(size_t)i * n_cols + j];
+            double best = 0.0; int arg = -1;
+            for (int k = 0; k < n_cols; ++k) {
+                const double r = (cur[k] - 5.0 * (double)(k > j ? k - j : j - k)) + gij;
+                if (arg < 0 || r > best) { best = r; arg = k; }
+            }
+            nxt[j] = best; prev[(size_t)i * n_cols + j] = arg;
+        }
+        __syncthreads();
+    }
+    if (j == 0) {
+        int step = n_rows > 1 ? prev[(size_t)(n_rows - 1) * n_cols + (n_cols - 1)] : 0;
+        for (int i = n_rows - 1; i >= 0; --i) {
+            path[i] = 10000.0 / (double)step;
+            step = i >= 1 ? prev[(size_t)i * n_cols + step] : 0;    // prev[0] is all zeros in the reference
+        }
+    }
 }
 
 // smooth + peak_score on caller-supplied rows (taps of pitch.py:157 / :227): one "utterance" of n_rows frames
@@ -418,6 +453,20 @@ int dspfe_pitch_feature_tail_host(const double* pitch, const double* amp, int32_
     if (!pitch || !amp || !out5 || n_frames < 1) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
     std::vector<double> work(3 * (size_t)n_frames);
     pitch_feature_tail(pitch, amp, n_frames, work.data(), out5);
+    return DSPFE_OK;
+}
+
+int dspfe_dp_max_pitch(const double* d_g, int32_t n_rows, int32_t n_cols, double* d_path, void* stream) {
+    if (!d_g || !d_path || n_rows < 2 || n_cols < 1) return fail(DSPFE_ERR_INVALID_ARG, "dp_max_pitch needs at least two rows");
+    if (n_cols > kDpMaxCols) return fail(DSPFE_ERR_UNSUPPORTED, "dp_max_pitch is built for up to 1024 columns");
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* d_prev = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_prev, (size_t)n_rows * n_cols * sizeof(int32_t), st));
+    const int threads = (n_cols + 31) & ~31;
+    dp_max_pitch_kernel<<<1, threads, 2 * n_cols * sizeof(double), st>>>(d_g, n_rows, n_cols, d_prev, d_path);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_prev, st);
+    if (e != cudaSuccess) return fail(DSPFE_ERR_CUDA, std::string("dp_max_pitch_kernel: ") + cudaGetErrorString(e));
     return DSPFE_OK;
 }
 

@@ -425,9 +425,22 @@ DEVFN FrameCursor frame_cursor(const PitchParams& p, int64_t g, int u, int lane,
         const int nbytes = (int)(b_hi - a0);
         if (nbytes <= stage_cap) {
             const int64_t total_bytes = p.total_samples * esz;
-            for (int off = lane * 16; off < nbytes; off += 512) {
-                if (a0 + off + 16 <= total_bytes) *reinterpret_cast<uint4*>(stage + off) = ldg(reinterpret_cast<const uint4*>(pcm + a0 + off));
-                else for (int e = 0; e < 16 && a0 + off + e < total_bytes; ++e) stage[off + e] = pcm[a0 + off + e];
+            // four 16-byte loads in flight per lane (a load -> store loop pays one DRAM latency per iteration)
+            for (int off0 = lane * 16; off0 < nbytes; off0 += 4 * 512) {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int off = off0 + k * 512;
+                    if (off < nbytes && a0 + off + 16 <= total_bytes) v[k] = ldg(reinterpret_cast<const uint4*>(pcm + a0 + off));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int off = off0 + k * 512;
+                    if (off < nbytes) {
+                        if (a0 + off + 16 <= total_bytes) *reinterpret_cast<uint4*>(stage + off) = v[k];
+                        else for (int e = 0; e < 16 && a0 + off + e < total_bytes; ++e) stage[off + e] = pcm[a0 + off + e];
+                    }
+                }
             }
             c.src = stage + (start * esz - a0);
         }
@@ -454,7 +467,14 @@ DEVFN float frame_sample(const PitchParams& p, FrameCursor& c, const int32_t* ds
         // x[n] - c*x[n-1] in float64 with NumPy's two roundings (preprocess.py:18), then rounded to float32: exact zeros and
         // signs as in the reference (they decide the membership of the median's sample set, pitch.py:146);
         // PRE = false leaves the sample as it is and skips the load of its predecessor
-        v = PRE ? dsp_preemph_f64(p.preemph, cur, prev) : cur;
+        if (PRE) {
+            // float32 first (c = c_hi + c_lo split: within an ulp of the float64 result); where the two terms cancel -- the only place
+            // where the sign or an exact zero can come out differently -- the float64 evaluation decides
+            v = dsp_fmaf(-p.pre_lo, prev, dsp_fmaf(-p.pre_hi, prev, cur));
+            if (fabsf(v) <= 1e-3f * fabsf(cur)) v = dsp_preemph_f64(p.preemph, cur, prev);
+        } else {
+            v = cur;
+        }
     }
     c.a += p.ds_q32; c.b += p.ds_r32;
     if (c.b >= p.ds_out) { c.b -= p.ds_out; ++c.a; }
@@ -859,7 +879,15 @@ DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* sp
         const int nload = (c0 + nrows < F ? nrows + 1 : nrows) * RL;          // floats to stage (rows are contiguous)
         const float* src = rows + (int64_t)c0 * RL;
         if ((RL & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-            for (int i = tid; i < (nload >> 2); i += kTrackThreads) reinterpret_cast<float4*>(buf)[i] = reinterpret_cast<const float4*>(src)[i];
+            // eight 16-byte loads in flight per thread (a load -> store loop pays one DRAM latency per iteration)
+            const int n4 = nload >> 2;
+            for (int i0 = tid; i0 < n4; i0 += 8 * kTrackThreads) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const int i = i0 + k * kTrackThreads; if (i < n4) v[k] = ldg(reinterpret_cast<const float4*>(src) + i); }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const int i = i0 + k * kTrackThreads; if (i < n4) reinterpret_cast<float4*>(buf)[i] = v[k]; }
+            }
         } else {
             for (int i = tid; i < nload; i += kTrackThreads) buf[i] = src[i];
         }

@@ -10,4 +10,4 @@ from .binding import (DspfeError, EndpointPlan, MfccPlan, endpoint_decide_host, 
                       center_clip_f32, smooth_rows_f32, robust_max_pitch_host, smooth_subsequence_host,
                       sub_endpoint_host, pitch_feature_tail_host, poly_lead_host, dp_max_pitch_host, fir_window_f64, acr_f64, cmvn_pad_batch,
                       amplitude_rule_gated_host, acr_gate_rows_f64, wav_info, wav_scan_paths, ingest_wavs, row_windowed_amplitude_f64, pitch_num_frames_host,
-                      FrontendPlan, timing_begin, timing_end, launch_count)
+                      FrontendPlan, timing_begin, timing_end, launch_count, dp_max_pitch_f64)

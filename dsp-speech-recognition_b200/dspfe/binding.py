@@ -697,6 +697,17 @@ def dp_max_pitch_host(g):
     return out
 
 
+def dp_max_pitch_f64(g):
+    """dp_max_pitch (reference pitch.py:208-225) on the device (dspfe_dp_max_pitch): [n_rows] float64."""
+    torch, dev = _cuda()
+    L = lib(); _bind_pitch(L)
+    L.dspfe_dp_max_pitch.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    x = torch.from_numpy(np.ascontiguousarray(g, dtype=np.float64)).to(dev)
+    out = torch.empty(x.shape[0], dtype=torch.float64, device=dev)
+    _check(L.dspfe_dp_max_pitch(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _stream(torch, dev)))
+    return out.cpu().numpy()
+
+
 def fir_window_f64(sig, rate, low_freq, high_freq, hamming):
     """window (reference sigproc.py:22-46) on the device: complex128 [n]."""
     torch, dev = _cuda()

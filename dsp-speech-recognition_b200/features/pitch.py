@@ -192,7 +192,7 @@ def dp_max_pitch(g):
     a = np.asarray(g, dtype=np.float64)
     if a.ndim != 2 or a.shape[0] < 2:
         raise NotImplementedError("dp_max_pitch needs a 2-D score array with at least two rows")
-    return dspfe.dp_max_pitch_host(a).tolist()
+    return dspfe.dp_max_pitch_f64(a).tolist()       # device kernel (dspfe_dp_max_pitch)
 
 
 def peak_score(sig, gender='male'):

@@ -257,7 +257,10 @@ int dspfe_smooth_subsequence_host(const double* pitch, int32_t n, int32_t tor, d
 int dspfe_sub_endpoint_host(const double* amp, int32_t n_frames, int32_t* p);
 int dspfe_pitch_feature_tail_host(const double* pitch, const double* amp, int32_t n_frames, double* out5);
 int dspfe_poly_lead_host(const double* seq, int32_t n, int32_t deg, double* coef);
-/* dp_max_pitch (pitch.py:208-225): Viterbi over the columns of g [n_rows,n_cols]; path [n_rows] = 10000 / lag index */
+/* dp_max_pitch (pitch.py:208-225): Viterbi over the columns of g [n_rows,n_cols]; path [n_rows] = 10000 / lag index.
+ * dspfe_dp_max_pitch is the device kernel (d_g, d_path device memory, n_cols <= 1024, asynchronous on `stream`);
+ * dspfe_dp_max_pitch_host the same recurrence on host arrays (no CUDA), kept for CPU-only checks. */
+int dspfe_dp_max_pitch(const double* d_g, int32_t n_rows, int32_t n_cols, double* d_path, void* stream);
 int dspfe_dp_max_pitch_host(const double* g, int32_t n_rows, int32_t n_cols, double* path);
 
 /* ------------------------------------------------------------------------------------------------

@@ -241,3 +241,19 @@ def test_peak_score_adversarial_rows(row_len):
     want = np.array([O.peak_score(x) for x in rows])
     np.testing.assert_array_equal(score, want)
     np.testing.assert_array_equal(lag, 20 + np.argmax(want, axis=1))
+
+
+def test_dp_max_pitch_on_device():
+    """dp_max_pitch (pitch.py:208-225) as a device kernel: bit-exact float64 path against the oracle and the
+    host replay, including the reference's back-trace start and first-maximum ties."""
+    import dspfe
+    import features
+    from oracle import ref_features as O
+    rng = np.random.default_rng(8)
+    for rows, cols in ((2, 5), (40, 80), (97, 180), (30, 200)):
+        g = rng.standard_normal((rows, cols)) * 20
+        g[rows // 2] = np.round(g[rows // 2])            # exact ties
+        want = np.array(O.dp_max_pitch(g))
+        np.testing.assert_array_equal(dspfe.dp_max_pitch_f64(g), want)
+        np.testing.assert_array_equal(dspfe.dp_max_pitch_host(g), want)
+        assert features.dp_max_pitch(g.tolist()) == want.tolist()
