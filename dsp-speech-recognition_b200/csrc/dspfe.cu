@@ -90,10 +90,12 @@ mfcc_kernel_t pick_kernel(bool has_win, int frame_len, bool f32, int mode = 0) {
 MfccConfig to_config(const dspfe_mfcc_params& q) {
     MfccConfig c;
     c.samplerate = q.samplerate; c.frame_len = q.frame_len; c.frame_step = q.frame_step; c.nfft = q.nfft;
+    c.count_len = q.frame_len;
+    if (q.nfft > 0 && q.frame_len > q.nfft) c.frame_len = q.nfft;   // frames longer than nfft: truncated for the transform, as the reference does
     c.nfilt = q.nfilt; c.numcep = q.numcep; c.ceplifter = q.ceplifter; c.append_energy = q.append_energy;
     c.delta_n = q.delta_n; c.seg_frames = q.seg_frames > 0 ? q.seg_frames : 256;
     c.preemph = q.preemph; c.lowfreq = q.lowfreq; c.highfreq = q.highfreq;
-    if (q.window) c.window.assign(q.window, q.window + (q.frame_len > 0 ? q.frame_len : 0));
+    if (q.window) c.window.assign(q.window, q.window + (c.frame_len > 0 ? c.frame_len : 0));   // (the first nfft entries of a longer window)
     return c;
 }
 
@@ -168,7 +170,7 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
     if (rc) return rc;
     PrepParams pp;
     pp.offsets = d_offsets; pp.trim = d_trim; pp.n_utt = n_utt;
-    pp.frame_len = pl->cfg.frame_len; pp.frame_step = pl->cfg.frame_step; pp.seg_frames = pl->cfg.seg_frames;
+    pp.frame_len = pl->cfg.count_len; pp.frame_step = pl->cfg.frame_step; pp.seg_frames = pl->cfg.seg_frames;
     pp.seg_start = ws.seg_start; pp.seg_len = ws.seg_len; pp.frame_off = d_frame_off ? d_frame_off : ws.frame_off;
     pp.tile_off = ws.tile_off; pp.tiles = ws.tiles; pp.ntiles = ws.ntiles; pp.max_tiles = (int)max_tiles;
     prep_kernel<<<1, kPrepThreads, 0, st>>>(pp);
@@ -374,7 +376,7 @@ int dspfe_mfcc_delta_host(dspfe_plan* pl, const int16_t* h_pcm, const int64_t* h
                           int64_t* h_frame_off) {
     if (!pl || !h_offsets || !h_out || n_utt < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
     if (n_utt == 0) return DSPFE_OK;
-    const int flen = pl->cfg.frame_len, fstep = pl->cfg.frame_step, width = pl->width;
+    const int flen = pl->cfg.count_len, fstep = pl->cfg.frame_step, width = pl->width;
     // slabs of consecutive utterances: <= kSlabSamples samples each (one oversized utterance = its own slab)
     const int64_t kSlabSamples = 8ll << 20;
     int64_t row = 0;

@@ -15,7 +15,9 @@ using namespace dspfe;
 namespace {
 
 constexpr int kFeWidth = 39;          // 3 * numcep of the default MFCC configuration
-constexpr int kFeSlots = 2;
+constexpr int kFeSlots = 3;           // host path: PCM / output staging sets (H2D runs up to two slabs ahead)
+constexpr int kFeLanes = 2;           // host path: slabs in flight on the GPU (own plans + stream each), so a slab's tail and its single-CTA
+                                      // prefix-sum kernels overlap the next slab's transforms
 
 // rel[i] = off[i] - a0 for i < n: the slab's offsets relative to its 16-byte aligned first sample
 __global__ void fe_rel_offsets_kernel(const int64_t* off, int n, int64_t a0, int64_t* rel) {
@@ -53,18 +55,27 @@ struct FeSlot {
 
 }  // namespace
 
+struct FeLane {                       // one slab in flight: the four sub-plans own the workspaces of their kernels
+    dspfe_endpoint_plan* ep = nullptr; dspfe_plan* mf = nullptr; dspfe_pitch_plan* cep = nullptr; dspfe_pitch_plan* acr = nullptr;
+    int64_t* loc_off[3] = {nullptr, nullptr, nullptr}; int64_t cap_utt = 0;      // slab-local row / frame prefix sums
+    int64_t* d_tot = nullptr;                                                    // [3] the slab's totals
+    cudaStream_t stream = nullptr;                                               // host path only
+    cudaEvent_t finish_done = nullptr;
+};
+
 struct dspfe_frontend_plan {
     dspfe_frontend_params prm;
-    dspfe_endpoint_plan* ep = nullptr; dspfe_plan* mf = nullptr; dspfe_pitch_plan* cep = nullptr; dspfe_pitch_plan* acr = nullptr;
-    int64_t* rel_off = nullptr; int64_t* loc_off[3] = {nullptr, nullptr, nullptr}; int64_t cap_utt = 0;
-    int64_t* d_tot = nullptr; int64_t* h_tot = nullptr;     // d_tot [3] slab totals | [2][3] device-side bases; h_tot pinned [kFeSlots][3]
+    FeLane lanes[kFeLanes];               // the device path uses lane 0 on the caller's stream
+    int64_t* rel_off = nullptr; int64_t cap_rel = 0;
+    int64_t* d_base = nullptr;            // [2][3] device-side running bases of the host path (ping-pong between consecutive slabs)
+    int64_t* h_tot = nullptr;             // pinned [kFeSlots][3]
     // scratch for outputs the caller does not want
     int32_t* s_lr = nullptr; int64_t cap_slr = 0;
     float* s_mfcc = nullptr; int64_t cap_smfcc = 0;
     double* s_cep = nullptr; int64_t cap_scep = 0;
     double* s_acr = nullptr; int64_t cap_sacr = 0;
     FeSlot slots[kFeSlots];
-    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_out = nullptr;
+    cudaStream_t s_copy = nullptr, s_out = nullptr;
 };
 
 namespace {
@@ -79,36 +90,53 @@ int grow(T*& p, int64_t& cap, int64_t need, int64_t floor_elems = 0) {
     return DSPFE_OK;
 }
 
-int ensure_utt(dspfe_frontend_plan* pl, int64_t n) {
-    if (n <= pl->cap_utt) return DSPFE_OK;
-    cudaFree(pl->rel_off); pl->rel_off = nullptr;
-    for (auto& q : pl->loc_off) { cudaFree(q); q = nullptr; }
-    pl->cap_utt = 0;
-    CUDA_TRY(cudaMalloc(&pl->rel_off, n * sizeof(int64_t)));
-    for (auto& q : pl->loc_off) CUDA_TRY(cudaMalloc(&q, n * sizeof(int64_t)));
-    pl->cap_utt = n;
+int ensure_utt(FeLane& ln, int64_t n) {
+    if (n <= ln.cap_utt) return DSPFE_OK;
+    for (auto& q : ln.loc_off) { cudaFree(q); q = nullptr; }
+    ln.cap_utt = 0;
+    for (auto& q : ln.loc_off) CUDA_TRY(cudaMalloc(&q, n * sizeof(int64_t)));
+    ln.cap_utt = n;
     return DSPFE_OK;
 }
 
-// the slab's kernels on `st`: endpoints -> MFCC -> cepstrum pitch + pitch_feature -> autocorrelation pitch -> offsets
-int run_slab(dspfe_frontend_plan* pl, const int16_t* pcm, int64_t total, const int64_t* rel_off, int32_t nu, int32_t* lr,
+int create_lane(FeLane& ln, const dspfe_frontend_params& q) {
+    dspfe_endpoint_params eq; dspfe_endpoint_params_default(&eq, q.samplerate);
+    dspfe_mfcc_params mq; dspfe_mfcc_params_default(&mq);
+    mq.samplerate = q.samplerate; mq.delta_n = q.delta_n;
+    mq.frame_len = (int32_t)(0.025 * q.samplerate + 0.5); mq.frame_step = (int32_t)(0.01 * q.samplerate + 0.5);
+    dspfe_pitch_params cq; dspfe_pitch_params_default(&cq, 0);
+    cq.samplerate = q.samplerate; cq.preemph = q.cep_preemph;
+    dspfe_pitch_params aq; dspfe_pitch_params_default(&aq, 1);
+    aq.samplerate = q.samplerate; aq.frame_len = q.acr_frame_len;
+    int rc = dspfe_endpoint_create(&eq, &ln.ep);
+    if (!rc) rc = dspfe_plan_create(&mq, &ln.mf);
+    if (!rc) rc = dspfe_pitch_create(&cq, &ln.cep);
+    if (!rc) rc = dspfe_pitch_create(&aq, &ln.acr);
+    if (!rc && cudaMalloc(&ln.d_tot, 3 * sizeof(int64_t)) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaMalloc failed");
+    return rc;
+}
+
+// the slab's kernels on `st`: endpoints -> MFCC -> cepstrum pitch + pitch_feature -> autocorrelation pitch -> offsets.
+// `wait_prev` (host path): the previous slab's finish kernel, which wrote the running bases this slab's finish kernel reads.
+int run_slab(dspfe_frontend_plan* pl, FeLane& ln, const int16_t* pcm, int64_t total, const int64_t* rel_off, int32_t nu, int32_t* lr,
              float* mfcc, int64_t mfcc_cap, double* cep, int32_t* cep_lag, int64_t cep_cap, double* feat, double* acr, int32_t* acr_lag,
              int64_t acr_cap, int64_t* const glob[3], const int64_t base[3], cudaStream_t st, const int64_t* dbase_in = nullptr,
-             int64_t* dbase_out = nullptr, int64_t* h_tot = nullptr) {
-    int rc = dspfe_endpoint(pl->ep, pcm, total, rel_off, nu, lr, nullptr, nullptr, nullptr, 0, st);
+             int64_t* dbase_out = nullptr, int64_t* h_tot = nullptr, cudaEvent_t wait_prev = nullptr) {
+    int rc = dspfe_endpoint(ln.ep, pcm, total, rel_off, nu, lr, nullptr, nullptr, nullptr, 0, st);
     if (rc) return rc;
-    rc = dspfe_mfcc_delta(pl->mf, pcm, total, rel_off, lr, nu, mfcc, mfcc_cap, pl->loc_off[0], st);
+    rc = dspfe_mfcc_delta(ln.mf, pcm, total, rel_off, lr, nu, mfcc, mfcc_cap, ln.loc_off[0], st);
     if (rc) return rc;
-    rc = dspfe_pitch(pl->cep, pcm, 0, total, rel_off, lr, nu, cep, cep_lag, feat, nullptr, pl->loc_off[1], cep_cap, st);
+    rc = dspfe_pitch(ln.cep, pcm, 0, total, rel_off, lr, nu, cep, cep_lag, feat, nullptr, ln.loc_off[1], cep_cap, st);
     if (rc) return rc;
-    rc = dspfe_pitch(pl->acr, pcm, 0, total, rel_off, lr, nu, acr, acr_lag, nullptr, nullptr, pl->loc_off[2], acr_cap, st);
+    rc = dspfe_pitch(ln.acr, pcm, 0, total, rel_off, lr, nu, acr, acr_lag, nullptr, nullptr, ln.loc_off[2], acr_cap, st);
     if (rc) return rc;
+    if (wait_prev) CUDA_TRY(cudaStreamWaitEvent(st, wait_prev, 0));
     FeFinish f;
-    for (int k = 0; k < 3; ++k) { f.loc[k] = pl->loc_off[k]; f.glob[k] = glob[k]; f.base[k] = base[k]; }
-    f.tot = pl->d_tot; f.n = nu + 1; f.dbase_in = dbase_in; f.dbase_out = dbase_out;
+    for (int k = 0; k < 3; ++k) { f.loc[k] = ln.loc_off[k]; f.glob[k] = glob[k]; f.base[k] = base[k]; }
+    f.tot = ln.d_tot; f.n = nu + 1; f.dbase_in = dbase_in; f.dbase_out = dbase_out;
     fe_finish_kernel<<<(unsigned)((nu + 1 + 255) / 256), 256, 0, st>>>(f);
     LAUNCH_CHECK("fe_finish_kernel", st);
-    CUDA_TRY(cudaMemcpyAsync(h_tot ? h_tot : pl->h_tot, pl->d_tot, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_tot ? h_tot : pl->h_tot, ln.d_tot, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     return DSPFE_OK;
 }
 
@@ -131,9 +159,14 @@ void dspfe_frontend_params_default(dspfe_frontend_params* p) {
 
 void dspfe_frontend_destroy(dspfe_frontend_plan* pl) {
     if (!pl) return;
-    dspfe_endpoint_destroy(pl->ep); dspfe_plan_destroy(pl->mf); dspfe_pitch_destroy(pl->cep); dspfe_pitch_destroy(pl->acr);
-    cudaFree(pl->rel_off); for (auto q : pl->loc_off) cudaFree(q);
-    cudaFree(pl->d_tot); if (pl->h_tot) cudaFreeHost(pl->h_tot);
+    for (auto& ln : pl->lanes) {
+        dspfe_endpoint_destroy(ln.ep); dspfe_plan_destroy(ln.mf); dspfe_pitch_destroy(ln.cep); dspfe_pitch_destroy(ln.acr);
+        for (auto q : ln.loc_off) cudaFree(q);
+        cudaFree(ln.d_tot);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.finish_done) cudaEventDestroy(ln.finish_done);
+    }
+    cudaFree(pl->rel_off); cudaFree(pl->d_base); if (pl->h_tot) cudaFreeHost(pl->h_tot);
     cudaFree(pl->s_lr); cudaFree(pl->s_mfcc); cudaFree(pl->s_cep); cudaFree(pl->s_acr);
     for (auto& s : pl->slots) {
         cudaFree(s.d_pcm); cudaFree(s.d_rel); if (s.h_rel) cudaFreeHost(s.h_rel);
@@ -144,7 +177,6 @@ void dspfe_frontend_destroy(dspfe_frontend_plan* pl) {
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
     }
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
-    if (pl->s_compute) cudaStreamDestroy(pl->s_compute);
     if (pl->s_out) cudaStreamDestroy(pl->s_out);
     delete pl;
 }
@@ -159,19 +191,8 @@ int dspfe_frontend_create(const dspfe_frontend_params* q, dspfe_frontend_plan** 
     pl->prm = *q;
     if (pl->prm.slab_samples == 0) pl->prm.slab_samples = 256ll << 20;
     if (pl->prm.host_slab_samples == 0) pl->prm.host_slab_samples = 32ll << 20;
-    dspfe_endpoint_params eq; dspfe_endpoint_params_default(&eq, q->samplerate);
-    dspfe_mfcc_params mq; dspfe_mfcc_params_default(&mq);
-    mq.samplerate = q->samplerate; mq.delta_n = q->delta_n;
-    mq.frame_len = (int32_t)(0.025 * q->samplerate + 0.5); mq.frame_step = (int32_t)(0.01 * q->samplerate + 0.5);
-    dspfe_pitch_params cq; dspfe_pitch_params_default(&cq, 0);
-    cq.samplerate = q->samplerate; cq.preemph = q->cep_preemph;
-    dspfe_pitch_params aq; dspfe_pitch_params_default(&aq, 1);
-    aq.samplerate = q->samplerate; aq.frame_len = q->acr_frame_len;
-    int rc = dspfe_endpoint_create(&eq, &pl->ep);
-    if (!rc) rc = dspfe_plan_create(&mq, &pl->mf);
-    if (!rc) rc = dspfe_pitch_create(&cq, &pl->cep);
-    if (!rc) rc = dspfe_pitch_create(&aq, &pl->acr);
-    if (!rc && cudaMalloc(&pl->d_tot, 9 * sizeof(int64_t)) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaMalloc failed");
+    int rc = create_lane(pl->lanes[0], pl->prm);       // the second lane (host path only) is created on first use
+    if (!rc && cudaMalloc(&pl->d_base, 6 * sizeof(int64_t)) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaMalloc failed");
     if (!rc && cudaHostAlloc(&pl->h_tot, kFeSlots * 3 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) rc = fail(DSPFE_ERR_CUDA, "cudaHostAlloc failed");
     if (rc) { const std::string keep = g_err; dspfe_frontend_destroy(pl); g_err = keep; return rc; }
     *plan = pl;
@@ -181,11 +202,12 @@ int dspfe_frontend_create(const dspfe_frontend_params* q, dspfe_frontend_plan** 
 int dspfe_frontend_bounds(const dspfe_frontend_plan* pl, int64_t total_samples, int64_t n_utt, int64_t* caps) {
     if (!pl || !caps || total_samples < 0 || n_utt < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
     // a slab starts at the 16-byte aligned sample at or before its first utterance: up to 7 extra samples per slab
-    const int64_t slabs = total_samples / std::min(pl->prm.slab_samples, pl->prm.host_slab_samples) + 2;
+    const int64_t slabs = total_samples / std::min(pl->prm.slab_samples, pl->prm.host_slab_samples) + 4;   // (+ the host path's two short ramp-up slabs)
     const int64_t padded = total_samples + 8 * slabs;
-    caps[0] = dspfe_rows_bound(pl->mf, padded, n_utt);
-    caps[1] = dspfe_pitch_frames_bound(pl->cep, padded, n_utt) + 3 * slabs;
-    caps[2] = dspfe_pitch_frames_bound(pl->acr, padded, n_utt) + 3 * slabs;
+    const FeLane& l0 = pl->lanes[0];
+    caps[0] = dspfe_rows_bound(l0.mf, padded, n_utt);
+    caps[1] = dspfe_pitch_frames_bound(l0.cep, padded, n_utt) + 3 * slabs;
+    caps[2] = dspfe_pitch_frames_bound(l0.acr, padded, n_utt) + 3 * slabs;
     return DSPFE_OK;
 }
 
@@ -202,12 +224,15 @@ int dspfe_frontend(dspfe_frontend_plan* pl, const int16_t* d_pcm, const int64_t*
     for (int32_t u0 = 0; u0 < n_utt;) {
         const int32_t u1 = slab_end(h_off, u0, n_utt, pl->prm.slab_samples), nu = u1 - u0;
         const int64_t a0 = h_off[u0] & ~(int64_t)7, total = h_off[u1] - a0;
-        int rc = ensure_utt(pl, nu + 1);
+        FeLane& ln = pl->lanes[0];
+        int rc = ensure_utt(ln, nu + 1);
+        if (rc) return rc;
+        rc = grow(pl->rel_off, pl->cap_rel, nu + 1);
         if (rc) return rc;
         fe_rel_offsets_kernel<<<(unsigned)((nu + 1 + 255) / 256), 256, 0, st>>>(d_offsets + u0, nu + 1, a0, pl->rel_off);
         LAUNCH_CHECK("fe_rel_offsets_kernel", st);
-        const int64_t need0 = dspfe_rows_bound(pl->mf, total, nu), need1 = dspfe_pitch_frames_bound(pl->cep, total, nu),
-                      need2 = dspfe_pitch_frames_bound(pl->acr, total, nu);
+        const int64_t need0 = dspfe_rows_bound(ln.mf, total, nu), need1 = dspfe_pitch_frames_bound(ln.cep, total, nu),
+                      need2 = dspfe_pitch_frames_bound(ln.acr, total, nu);
         int32_t* lr = o->lr ? o->lr + 2 * (int64_t)u0 : nullptr;
         float* mfcc = o->mfcc ? o->mfcc + base[0] * kFeWidth : nullptr; int64_t cap0 = o->mfcc_cap - base[0];
         double* cep = o->cep_pitch ? o->cep_pitch + base[1] : nullptr; int64_t cap1 = o->cep_cap - base[1];
@@ -219,7 +244,7 @@ int dspfe_frontend(dspfe_frontend_plan* pl, const int16_t* d_pcm, const int64_t*
         if (cap0 < need0 || cap1 < need1 || cap2 < need2) return fail(DSPFE_ERR_INVALID_ARG, "output capacity is below dspfe_frontend_bounds()");
         int64_t* glob[3] = {o->mfcc_frame_off ? o->mfcc_frame_off + u0 : nullptr, o->cep_frame_off ? o->cep_frame_off + u0 : nullptr,
                             o->acr_frame_off ? o->acr_frame_off + u0 : nullptr};
-        rc = run_slab(pl, d_pcm + a0, total, pl->rel_off, nu, lr, mfcc, cap0, cep, o->cep_lag ? o->cep_lag + base[1] : nullptr, cap1,
+        rc = run_slab(pl, ln, d_pcm + a0, total, pl->rel_off, nu, lr, mfcc, cap0, cep, o->cep_lag ? o->cep_lag + base[1] : nullptr, cap1,
                       o->cep_feat ? o->cep_feat + 5 * (int64_t)u0 : nullptr, acr, o->acr_lag ? o->acr_lag + base[2] : nullptr, cap2, glob, base, st);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -238,7 +263,11 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
     if (!h_pcm && h_off[n_utt] > h_off[0]) return fail(DSPFE_ERR_INVALID_ARG, "h_pcm is null");
     for (int32_t u = 0; u < n_utt; ++u) if (h_off[u + 1] < h_off[u]) return fail(DSPFE_ERR_INVALID_ARG, "offsets must be non-decreasing");
     if (!pl->s_copy) CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
-    if (!pl->s_compute) CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_compute, cudaStreamNonBlocking));
+    for (auto& ln : pl->lanes) {
+        if (!ln.ep) { int rc = create_lane(ln, pl->prm); if (rc) return rc; }
+        if (!ln.stream) CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        if (!ln.finish_done) CUDA_TRY(cudaEventCreateWithFlags(&ln.finish_done, cudaEventDisableTiming));
+    }
     if (!pl->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
     for (auto& s : pl->slots) {
         if (!s.h2d_done) CUDA_TRY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
@@ -246,8 +275,11 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
         if (!s.d2h_done) CUDA_TRY(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
     }
     // the slabs
-    std::vector<int32_t> cut{0};
-    while (cut.back() < n_utt) cut.push_back(slab_end(h_off, cut.back(), n_utt, pl->prm.host_slab_samples));
+    std::vector<int32_t> cut{0};                         // short slabs first: the kernels start after a quarter-slab's copy
+    while (cut.back() < n_utt) {
+        const size_t k = cut.size();
+        cut.push_back(slab_end(h_off, cut.back(), n_utt, k == 1 ? pl->prm.host_slab_samples / 4 : (k == 2 ? pl->prm.host_slab_samples / 2 : pl->prm.host_slab_samples)));
+    }
     const int n_slab = (int)cut.size() - 1;
     const int64_t base0 = h_off[0] & ~(int64_t)7;     // h_pcm is addressed from this sample on (its predecessors are never read)
     auto issue_h2d = [&](int s) -> int {
@@ -277,12 +309,13 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
         CUDA_TRY(cudaEventRecord(sl.h2d_done, pl->s_copy));
         return DSPFE_OK;
     };
-    // The kernels of slab s are queued without waiting for slab s - 1: the running row / frame bases live on the device
-    // (d_tot[3 + 3 * (s & 1)], written by the previous slab's last kernel).  The host only needs a slab's totals to size its
+    // The kernels of slab s are queued without waiting for slab s - 1, on the other lane (its own plans and stream: two slabs
+    // are in flight on the GPU); the running row / frame bases live on the device (d_base[s & 1], written by the previous
+    // slab's last kernel, the only cross-lane dependency).  The host only needs a slab's totals to size its
     // D2H copies, and drains slab s - 1 after queuing slab s, so the GPU never waits for the host.
     int64_t base[3] = {0, 0, 0};
     const int64_t zero3[3] = {0, 0, 0};
-    CUDA_TRY(cudaMemsetAsync(pl->d_tot + 3, 0, 3 * sizeof(int64_t), pl->s_compute));
+    CUDA_TRY(cudaMemsetAsync(pl->d_base, 0, 3 * sizeof(int64_t), pl->lanes[0].stream));    // slab 0 runs on lane 0 and reads d_base[0]
     auto drain = [&](int s) -> int {
         FeSlot& sl = pl->slots[s % kFeSlots];
         const int32_t u0 = cut[s], nu = cut[s + 1] - u0;
@@ -316,21 +349,24 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
         FeSlot& sl = pl->slots[s % kFeSlots];
         const int32_t u0 = cut[s], u1 = cut[s + 1], nu = u1 - u0;
         const int64_t a0 = std::max(h_off[u0] & ~(int64_t)7, base0), total = h_off[u1] - a0;
-        const int64_t need0 = dspfe_rows_bound(pl->mf, total, nu), need1 = dspfe_pitch_frames_bound(pl->cep, total, nu),
-                      need2 = dspfe_pitch_frames_bound(pl->acr, total, nu);
-        CUDA_TRY(cudaStreamWaitEvent(pl->s_compute, sl.d2h_done, 0));             // the slot's previous outputs have left
+        FeLane& ln = pl->lanes[s % kFeLanes];
+        cudaStream_t sc = ln.stream;
+        const int64_t need0 = dspfe_rows_bound(ln.mf, total, nu), need1 = dspfe_pitch_frames_bound(ln.cep, total, nu),
+                      need2 = dspfe_pitch_frames_bound(ln.acr, total, nu);
+        CUDA_TRY(cudaStreamWaitEvent(sc, sl.d2h_done, 0));                        // the slot's previous outputs have left
         rc = grow(sl.d_mfcc, sl.cap_rows, need0 * kFeWidth); if (rc) return rc;
         rc = grow(sl.d_cep, sl.cap_cep, need1); if (rc) return rc;
         rc = grow(sl.d_acr, sl.cap_acr, need2); if (rc) return rc;
         if (o->cep_lag) { rc = grow(sl.d_cep_lag, sl.cap_cep_lag, need1); if (rc) return rc; }
         if (o->acr_lag) { rc = grow(sl.d_acr_lag, sl.cap_acr_lag, need2); if (rc) return rc; }
-        rc = ensure_utt(pl, nu + 1); if (rc) return rc;
-        CUDA_TRY(cudaStreamWaitEvent(pl->s_compute, sl.h2d_done, 0));
-        rc = run_slab(pl, sl.d_pcm, total, sl.d_rel, nu, sl.d_lr, sl.d_mfcc, need0, sl.d_cep, o->cep_lag ? sl.d_cep_lag : nullptr, need1, sl.d_feat, sl.d_acr,
-                      o->acr_lag ? sl.d_acr_lag : nullptr, need2, sl.d_goff, zero3, pl->s_compute, pl->d_tot + 3 + 3 * (s & 1), pl->d_tot + 3 + 3 * ((s + 1) & 1),
-                      pl->h_tot + 3 * (s % kFeSlots));
+        rc = ensure_utt(ln, nu + 1); if (rc) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(sc, sl.h2d_done, 0));
+        rc = run_slab(pl, ln, sl.d_pcm, total, sl.d_rel, nu, sl.d_lr, sl.d_mfcc, need0, sl.d_cep, o->cep_lag ? sl.d_cep_lag : nullptr, need1, sl.d_feat, sl.d_acr,
+                      o->acr_lag ? sl.d_acr_lag : nullptr, need2, sl.d_goff, zero3, sc, pl->d_base + 3 * (s & 1), pl->d_base + 3 * ((s + 1) & 1),
+                      pl->h_tot + 3 * (s % kFeSlots), s > 0 ? pl->lanes[(s - 1) % kFeLanes].finish_done : nullptr);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(sl.compute_done, pl->s_compute));
+        CUDA_TRY(cudaEventRecord(ln.finish_done, sc));
+        CUDA_TRY(cudaEventRecord(sl.compute_done, sc));
         if (s + 1 < n_slab) { rc = issue_h2d(s + 1); if (rc) return rc; }          // overlaps this slab's kernels
         if (s >= 1) { rc = drain(s - 1); if (rc) return rc; }                      // (that slab finished while this one was being queued)
     }

@@ -169,24 +169,44 @@ int dspfe_ingest_wavs(const void* const* file_bytes, const int64_t* sizes, int32
 }
 
 /* ---- path-based ingest: the library reads the files itself, sample bytes go straight into the pinned slabs ---- */
+// Walks the RIFF chunks of the file itself (8-byte chunk headers, seeks over the payloads): a `data` chunk behind a large
+// LIST / bext / id3 chunk is found wherever it sits, as scipy.io.wavfile.read does (reader.py:76).
 static int scan_one(const char* path, WavInfo& w, std::string& err) {
     FILE* f = std::fopen(path, "rb");
     if (!f) { err = std::string("cannot open ") + path; return DSPFE_ERR_INVALID_ARG; }
-    unsigned char head[4096];
-    const size_t got = std::fread(head, 1, sizeof(head), f);
-    std::fseek(f, 0, SEEK_END);
+    struct Closer { FILE* f; ~Closer() { std::fclose(f); } } closer{f};
+    if (std::fseek(f, 0, SEEK_END) != 0) { err = "cannot seek"; return DSPFE_ERR_INVALID_ARG; }
     const long long fsize = std::ftell(f);
-    std::fclose(f);
-    // parse what was read; a data chunk that starts inside the first 4 KB is enough (its payload is measured against the file size)
-    int rc = parse_wav(head, (int64_t)got, w, err);
-    if (rc == DSPFE_OK && fsize > (long long)got) {
-        // the file is longer than the probe: take the frame count from the chunk length and the real file size
-        const int64_t len = rd32(head + w.data_offset - 4);
-        int64_t n = len;
-        if (w.data_offset + n > fsize) n = fsize - w.data_offset;
-        w.n_frames = n / (2 * w.channels);
+    if (fsize < 0 || std::fseek(f, 0, SEEK_SET) != 0) { err = "cannot seek"; return DSPFE_ERR_INVALID_ARG; }
+    unsigned char h[48];
+    if (std::fread(h, 1, 12, f) != 12 || std::memcmp(h, "RIFF", 4) != 0 || std::memcmp(h + 8, "WAVE", 4) != 0) { err = "not a RIFF/WAVE file"; return DSPFE_ERR_INVALID_ARG; }
+    long long pos = 12;
+    bool have_fmt = false;
+    while (pos + 8 <= fsize) {
+        if (std::fseek(f, (long)pos, SEEK_SET) != 0 || std::fread(h, 1, 8, f) != 8) break;
+        const long long len = rd32(h + 4);
+        if (std::memcmp(h, "fmt ", 4) == 0) {
+            const size_t want = (size_t)(len < 40 ? len : 40);
+            if (len < 16 || std::fread(h + 8, 1, want, f) != want) { err = "truncated fmt chunk"; return DSPFE_ERR_INVALID_ARG; }
+            uint16_t tag = rd16(h + 8);
+            w.channels = rd16(h + 10); w.rate = (int32_t)rd32(h + 12); w.bits = rd16(h + 22);
+            if (tag == 0xFFFE && len >= 40) tag = rd16(h + 8 + 24);   // sub-format GUID starts with the tag
+            if (tag != 1) { err = "only integer PCM WAV files are built"; return DSPFE_ERR_UNSUPPORTED; }
+            if (w.bits != 16) { err = "only 16-bit WAV files are built (what the reference's data set holds)"; return DSPFE_ERR_UNSUPPORTED; }
+            if (w.channels < 1) { err = "WAV file without channels"; return DSPFE_ERR_INVALID_ARG; }
+            have_fmt = true;
+        } else if (std::memcmp(h, "data", 4) == 0) {
+            if (!have_fmt) { err = "data chunk before fmt chunk"; return DSPFE_ERR_INVALID_ARG; }
+            long long n = len;
+            if (pos + 8 + n > fsize) n = fsize - pos - 8;      // scipy also reads what is there
+            w.data_offset = pos + 8;
+            w.n_frames = n / (2 * w.channels);
+            return DSPFE_OK;
+        }
+        pos += 8 + len + (len & 1);
     }
-    return rc;
+    err = "no data chunk";
+    return DSPFE_ERR_INVALID_ARG;
 }
 
 int dspfe_wav_scan_paths(const char* const* paths, int32_t n_files, int64_t* h_offsets, int32_t* h_rates) {

@@ -111,6 +111,10 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     const float2 zero2 = make_float2(0.f, 0.f);
     float2 esum = zero2;
     const float sc = 1.0f / (float)kLongNfft;
+    // power spectrum of the pair as compact float2 [kLongBins] (8-byte stride: the mel loop's loads are conflict-free; the
+    // float4 slots of the accumulation path put consecutive bins 16 bytes apart, a 4-way conflict on every scalar access)
+    float2* pw2 = reinterpret_cast<float2*>(acc);
+    float2* parked = pw2 + kLongBins + 7;            // [512] the windowed samples between the two passes (inside acc's area)
     if (p.frame_len <= 512) {
         // Frames that fit 512 samples (30 ms at 16 kHz = 480): decimation in FREQUENCY.  X[3q + r] = FFT512(x[n] W1536^{n r})[q],
         // and for real x the bins 3q + 2 mirror the bins 3q' + 1 (X[1536 - k] = conj X[k], k = 3q'+1 -> 3(511 - q') + 2), so
@@ -125,9 +129,9 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
                 if (r == 0) {   // windowed, pre-emphasised samples; parked in the unused half of the lane's own bin slots for r = 1
                     const float w = ldg(win + n);
                     v = make_float2(long_sample(p, fa, n, w), long_sample(p, fb, n, w));
-                    acc[n].z = v.x; acc[n].w = v.y;
+                    parked[n] = v;
                 } else {
-                    v = make_float2(acc[n].z, acc[n].w);
+                    v = parked[n];
                     m = ldg(w1536 + n);
                 }
                 x[t].re = f2muls(v, m.x); x[t].im = f2muls(v, m.y);
@@ -140,7 +144,7 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
                 int k = -1;
                 if (r == 0) { if (q <= 256) k = 3 * q; }
                 else k = q <= 255 ? 3 * q + 1 : 3 * (511 - q) + 2;
-                if (k >= 0) { acc[k].x = pw.x; acc[k].y = pw.y; esum = f2add(esum, pw); }
+                if (k >= 0) { pw2[k] = pw; esum = f2add(esum, pw); }
             }
         }
     } else {
@@ -173,11 +177,15 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
         }
     }
     // power spectrum |X|^2 / NFFT (sigproc.py:158) into the .x / .y of the bin's own slot; frame energy = sum over all bins
-    for (int k = lane; k < kLongBins; k += 32) {
-        const float4 a = acc[k];
-        const float2 pw = make_float2((a.x * a.x + a.z * a.z) * sc, (a.y * a.y + a.w * a.w) * sc);
-        acc[k].x = pw.x; acc[k].y = pw.y;
-        esum.x += pw.x; esum.y += pw.y;
+    // (bin k's float2 slot pw2[k] lies below its float4 accumulator acc[k] and is only written after acc[k] was read by the
+    // same lane; other lanes' accumulators at or below byte 8k + 8 belong to bins <= k/2, read by the same loop iteration or earlier)
+    for (int k0 = 0; k0 < kLongBins; k0 += 32) {
+        const int k = k0 + lane;
+        float2 pw = zero2;
+        if (k < kLongBins) { const float4 a = acc[k]; pw = make_float2((a.x * a.x + a.z * a.z) * sc, (a.y * a.y + a.w * a.w) * sc); }
+        simt::warp_sync();
+        if (k < kLongBins) { pw2[k] = pw; esum.x += pw.x; esum.y += pw.y; }
+        simt::warp_sync();
     }
     }
 #pragma unroll
@@ -202,7 +210,8 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
                 const float iu = inv_up[j], id = inv_dn[j];
                 for (int k = lo + lane; k < hi; k += 32) {
                     const float w = k < mid ? (float)(k - lo) * iu : (float)(hi - k) * id;
-                    f[u].x = dsp_fmaf(w, acc[k].x, f[u].x); f[u].y = dsp_fmaf(w, acc[k].y, f[u].y);
+                    const float2 pk = pw2[k];
+                    f[u].x = dsp_fmaf(w, pk.x, f[u].x); f[u].y = dsp_fmaf(w, pk.y, f[u].y);
                 }
             }
         }

@@ -18,6 +18,8 @@ struct MfccConfig {
     int samplerate = 16000;
     int frame_len = 400;     // samples (caller applies round_half_up(winlen*samplerate), sigproc.py:77)
     int frame_step = 160;
+    int count_len = 0;       // frame length framesig counts and pads with (sigproc.py:79-87); > frame_len when the caller's frames are longer
+                             // than nfft: the reference then transforms the first nfft samples of each frame (sigproc.py:143-147)
     int nfft = 512;
     int nfilt = 26;
     int numcep = 13;
@@ -53,7 +55,7 @@ inline std::string mfcc_long_config_check(const MfccConfig& c) {
     if (c.nfft != 1536) return "nfft must be 512 or 1536 in this build";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
     if (c.frame_step < 1) return "frame_step must be >= 1";
-    if (c.frame_step > c.frame_len) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
+    if (c.frame_step > (c.count_len > 0 ? c.count_len : c.frame_len)) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
     if (c.nfilt < 1 || c.nfilt > kMaxNfilt) return "nfilt must be in [1, 40]";
     if (c.numcep < 1 || c.numcep > kMaxNumcep || c.numcep > c.nfilt) return "numcep must be in [1, min(16, nfilt)]";
     if (c.delta_n < 1 || c.delta_n > kMaxDeltaN) return "delta N must be in [1, 4]";
@@ -68,7 +70,7 @@ inline std::string mfcc_config_check(const MfccConfig& c) {
     if (c.nfft != kNfft) return "nfft must be 512 in this build (other sizes: SURVEY f-2)";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
     if (c.frame_step < 2 || (c.frame_step & 1)) return "frame_step must be even and >= 2";
-    if (c.frame_step > c.frame_len) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
+    if (c.frame_step > (c.count_len > 0 ? c.count_len : c.frame_len)) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
     if (c.nfilt < 1 || c.nfilt > kMaxNfilt) return "nfilt must be in [1, 40]";
     if (c.numcep < 1 || c.numcep > kMaxNumcep || c.numcep > c.nfilt) return "numcep must be in [1, min(16, nfilt)]";
     if (c.delta_n < 1 || c.delta_n > kMaxDeltaN) return "delta N must be in [1, 4]";

@@ -1,4 +1,6 @@
 """Drop-in for reference features/base.py: MFCC, filterbank energies, deltas."""
+import logging
+
 import numpy
 
 import dspfe
@@ -22,8 +24,8 @@ def _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc, long_o
         raise NotImplementedError("nfft=512 (and, for mfcc, nfft=1536 as model.py:74 uses) are built")
     frame_len = sigproc.round_half_up(winlen * samplerate)
     frame_step = sigproc.round_half_up(winstep * samplerate)
-    if frame_len > nfft:
-        raise NotImplementedError("frame longer than nfft (the reference truncates with a warning)")
+    if frame_len > nfft:   # reference sigproc.py:143-146: frames are counted and windowed at full length, the transform takes their first nfft samples
+        logging.warning('frame length (%d) is greater than FFT size (%d), frame will be truncated. Increase NFFT to avoid.', frame_len, nfft)
     if nfft == 512 and (frame_step % 2 or frame_step < 2):
         raise NotImplementedError("odd frame steps are built for nfft=1536 only")
     win = numpy.asarray(winfunc(frame_len), dtype=numpy.float64)

@@ -10,9 +10,12 @@
  *   - every function returns 0 (DSPFE_OK) or a negative dspfe_status; dspfe_last_error() gives
  *     the message of the calling thread's last failure;
  *   - `d_` pointers are device memory, `h_` pointers host memory; the caller owns all of them;
- *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*), never
- *     synchronise, and keep their workspaces inside the plan (grown only when a larger batch
- *     than ever before arrives; dspfe_plan_reserve() pre-sizes them);
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*) and keep
+ *     their workspaces inside the plan: ONE call per plan may be in flight at a time (calls on the
+ *     same plan must be ordered on one stream or by events; use one plan per concurrent stream --
+ *     dspfe_frontend_host does exactly that with two lanes).  A workspace grows only when a larger
+ *     batch than ever before arrives, with cudaFree / cudaMalloc, which synchronises the device
+ *     once; dspfe_*_reserve() pre-sizes them so that later calls never allocate;
  *   - a packed ragged batch is int16 PCM `pcm[total_samples]` plus `offsets[n_utt+1]` (int64,
  *     samples); utterance u is pcm[offsets[u] .. offsets[u+1]).  No padding between utterances
  *     is required; `d_pcm` itself must be 16-byte aligned.

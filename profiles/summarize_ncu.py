@@ -55,6 +55,23 @@ def main():
             if k in col and r[col[k]] != "":
                 print(f"| {name} (`{k}`) | {r[col[k]]} {units[col[k]]} |")
         print()
+    if "--traffic" in sys.argv:      # profiles/r2_traffic.json: dram bytes per launch and kernel, read by bench.py's roofline.traffic
+        import json
+        import re
+        out_path = sys.argv[sys.argv.index("--traffic") + 1]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tr, order = {}, {}
+        for r in rows[2:]:
+            name = r[col['Kernel Name']]
+            short = re.sub(r"\(.*$", "", name).replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("dspfe::", "").replace("void ", "").strip()
+            short = re.sub(r"^mfcc_delta_kernel<.*", "mfcc_delta_kernel", short)
+            tot = sum(float(r[col[k]]) * unit[units[col[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            order[short] = order.get(short, 0) + 1
+            key = short if order[short] == 1 else f"{short}#{order[short]}"      # a second launch of the same kernel in the step (the autocorrelation chain)
+            tr[key] = tot
+        tr["_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of profiles/run_frontend_once.py (the bench step), {rep.split('/')[-1]}"
+        with open(out_path, "w") as f:
+            json.dump(tr, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -182,3 +182,19 @@ def test_step_longer_than_frame_is_rejected():
         assert (int(lr[u, 0]), int(lr[u, 1])) == (l, r)
         np.testing.assert_array_equal(zcr[fo[u]:fo[u + 1]], np.array(z))
         np.testing.assert_array_equal(asum[fo[u]:fo[u + 1]] / 160.0, np.array(amp))
+
+
+def test_frames_longer_than_nfft_are_truncated(caplog):
+    """reference sigproc.py:143-146: with winlen * samplerate > nfft the frames are counted, padded and windowed at full length
+    and the transform takes their first nfft samples (a warning is logged)."""
+    import features
+    from dspfe import synth
+    from oracle import ref_features as O
+    x = synth.synth_utterance(88, 20000)
+    for kw in (dict(winlen=0.04, winstep=0.01), dict(winlen=0.04, winstep=0.01, winfunc=np.hamming), dict(winlen=0.1, winstep=0.02, nfft=1536)):
+        with caplog.at_level(logging.WARNING):
+            got = features.mfcc(x, **kw)
+        want = O.mfcc(x, **kw)
+        assert got.shape == want.shape, (kw, got.shape, want.shape)
+        assert_mfcc_close(got, want, what=f"truncated frames {kw}")
+    assert any("truncated" in r.message for r in caplog.records)

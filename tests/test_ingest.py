@@ -74,3 +74,22 @@ def test_ingest_matches_reader_semantics(tmp_path):
     import torch
     lr = dspfe.EndpointPlan().detect(torch.from_numpy(pcm).cuda(), torch.from_numpy(off).cuda())
     assert lr.shape == (5, 2)
+
+
+def test_scan_paths_finds_a_data_chunk_behind_a_large_list_chunk(tmp_path):
+    """A valid WAV whose `data` chunk sits beyond the first 4 KB (a large LIST chunk first): scipy.io.wavfile.read reads it
+    (reader.py:76), so does the scanner (it walks the chunk headers of the file instead of probing a fixed prefix)."""
+    import struct
+    from scipy.io import wavfile
+    import dspfe
+    x = (np.arange(6000).reshape(-1, 2) % 977 - 400).astype(np.int16)
+    fmt = struct.pack("<4sIHHIIHH", b"fmt ", 16, 1, 2, 16000, 16000 * 4, 4, 16)
+    junk = struct.pack("<4sI", b"LIST", 10001) + b"\0" * 10001 + b"\0"        # odd length: one pad byte
+    data = struct.pack("<4sI", b"data", x.nbytes) + x.tobytes()
+    body = b"WAVE" + fmt + junk + data
+    p = tmp_path / "late_data.wav"
+    p.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    rate, ref = wavfile.read(str(p))
+    assert rate == 16000 and np.array_equal(ref, x)
+    off, rates = dspfe.wav_scan_paths([str(p)])
+    assert list(off) == [0, len(x)] and list(rates) == [16000]
