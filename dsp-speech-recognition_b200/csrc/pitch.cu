@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32 * kPitchWarps, 4) pitch_clip_kernel(const _
 // thread; 3 CTAs/SM without spills measured 3 % faster for the autocorrelation chains and 1 % for the cepstrum (the kernels sit
 // on the shared-memory pipe, so the fourth CTA bought nothing).
 template <int MODE>
-__global__ void __launch_bounds__(32 * kPitchWarps, 3) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
+__global__ void __launch_bounds__(32 * kPitchWarps, MODE == 1 ? 3 : 4) pitch_frame_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tws = reinterpret_cast<float2*>(smem);                       // W512 twiddles + W32 (kTabMod float2)
     constexpr int kPer = MODE == 2 ? 4 : 2;                              // slots per warp: a quad (pitch_acr_quad) or a pair
