@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(32 * kLongWarps, 3) mfcc_long_kernel(const __g
     const int w = threadIdx.x >> 5;
     const int64_t g0 = 2 * ((int64_t)blockIdx.x * kLongWarps + w);
     if (g0 >= total) return;
-    mfcc_long_pair(p, g0, total, smem + kLtW1536 * 4 + w * kLongWarpSmem, tws, tws + kLtW32 / 2);
+    mfcc_long_pair(p, g0, total, smem + kLtW1536 * 4 + w * p.warp_smem, tws, tws + kLtW32 / 2);
 }
 // delta + delta-delta over per-utterance cepstra (base.py:70-79 twice, model.py:76-77), one CTA per utterance: thread = (row of a
 // block of 8, column).  Pass 1 writes the static and delta columns, pass 2 reads the deltas back (edge-clamped on the DELTA
@@ -155,7 +155,7 @@ struct dspfe_plan {
     Workspace ws;
     HostSlot slots[kSlots];
     int width = 0;              // 3 * numcep
-    bool is_long = false;       // nfft = 1536: K1L
+    bool is_long = false;       // K1L: nfft other than 512, or nfft = 512 with an odd hop
     float* d_long_tab = nullptr;
     std::vector<float> h_long_tab;   // host copy: the mel edges travel as kernel parameters
 };
@@ -177,17 +177,17 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
     LAUNCH_CHECK("prep_kernel", st);
 
     if (pl->is_long) {
-        if (mode != 0) return fail(DSPFE_ERR_UNSUPPORTED, "the filterbank / spectrum taps are built for nfft = 512");
         const int64_t rows = total_samples / pl->cfg.frame_step + n_utt;
-        rc = ws.ensure_cep(rows * pl->cfg.numcep);
-        if (rc) return rc;
+        if (mode == 0) { rc = ws.ensure_cep(rows * pl->cfg.numcep); if (rc) return rc; }
         MfccLongParams lp;
         lp.pcm = d_pcm; lp.in_f32 = f32 ? 1 : 0; lp.seg_start = ws.seg_start; lp.seg_len = ws.seg_len; lp.frame_off = pp.frame_off; lp.n_utt = n_utt;
         lp.frame_len = pl->cfg.frame_len; lp.frame_step = pl->cfg.frame_step; lp.nfilt = pl->cfg.nfilt; lp.numcep = pl->cfg.numcep;
-        lp.append_energy = pl->cfg.append_energy; lp.preemph = (float)pl->cfg.preemph; lp.tab = pl->d_long_tab; lp.mfcc = ws.cep; lp.max_frames = rows;
+        lp.append_energy = pl->cfg.append_energy; lp.preemph = (float)pl->cfg.preemph; lp.tab = pl->d_long_tab; lp.mfcc = mode == 0 ? ws.cep : d_out; lp.max_frames = rows;
+        long_fill_size_params(lp, pl->cfg.nfft, mode, spec_kind);
         long_fill_mel_params(lp, pl->h_long_tab.data());
-        mfcc_long_kernel<<<(unsigned)((rows + 2 * kLongWarps - 1) / (2 * kLongWarps)), 32 * kLongWarps, kLongCtaSmem, st>>>(lp);
+        mfcc_long_kernel<<<(unsigned)((rows + 2 * kLongWarps - 1) / (2 * kLongWarps)), 32 * kLongWarps, long_cta_smem(pl->cfg.nfft), st>>>(lp);
         LAUNCH_CHECK("mfcc_long_kernel", st);
+        if (mode != 0) return DSPFE_OK;
         int den = 0; for (int i = 1; i <= pl->cfg.delta_n; ++i) den += i * i;
         delta_batch_kernel<<<(unsigned)n_utt, 128, 0, st>>>(ws.cep, pp.frame_off, n_utt, pl->cfg.numcep, pl->cfg.delta_n,
                                                                                           (float)(1.0 / (2.0 * den)), rows, d_out);
@@ -254,7 +254,8 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     pl->cfg = to_config(*p);
     std::memset(&pl->layout, 0, sizeof(pl->layout));
     std::string err;
-    if (pl->cfg.nfft == kLongNfft) {
+    // K1 takes nfft = 512 with an even hop (its sample planes); every other size / hop goes to the general kernel K1L
+    if (pl->cfg.nfft != kNfft || (pl->cfg.frame_step & 1) || pl->cfg.frame_step < 2) {
         err = mfcc_long_config_check(pl->cfg);
         if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
         pl->is_long = true; pl->has_win = !pl->cfg.window.empty(); pl->width = 3 * pl->cfg.numcep;
@@ -262,7 +263,7 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
         pl->h_long_tab = t;
         cudaError_t e = cudaMalloc(&pl->d_long_tab, t.size() * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_long_tab, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongCtaSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, long_cta_smem(kLongMaxNfft));
         if (e != cudaSuccess) { cudaFree(pl->d_long_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
         *plan = pl;
         return DSPFE_OK;
@@ -311,8 +312,8 @@ int dspfe_plan_info(const dspfe_plan* pl, int32_t* smem_bytes, int32_t* ctas_per
     int nb = 0;
     if (pl->is_long) {
         CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_long_kernel));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_long_kernel, 32 * kLongWarps, kLongCtaSmem));
-        if (smem_bytes) *smem_bytes = kLongCtaSmem;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_long_kernel, 32 * kLongWarps, long_cta_smem(pl->cfg.nfft)));
+        if (smem_bytes) *smem_bytes = long_cta_smem(pl->cfg.nfft);
         if (ctas_per_sm) *ctas_per_sm = nb;
         if (regs_per_thread) *regs_per_thread = fa.numRegs;
         return DSPFE_OK;

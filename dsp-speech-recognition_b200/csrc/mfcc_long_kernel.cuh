@@ -1,4 +1,5 @@
-// K1L: MFCC for long frames under nfft = 1536 (sm_100a) -- the configuration the reference trainer really uses:
+// K1L: MFCC for every transform size other than K1's even-hop nfft = 512 (sm_100a) -- first of all the configuration the
+// reference trainer really uses:
 // mfcc(sound.reshape(1,-1), rate, winlen=cfg.frame, winstep=cfg.step, nfft=1536, winfunc=np.hamming) (model.py:74), i.e.
 // 30 ms Hamming frames of 480 (16 kHz), 1323 (44.1 kHz) or 1440 (48 kHz) samples with hops of 160 / 441 / 480 (the odd hop
 // rules out K1's even/odd sample planes), zero padded to 1536 points.  Same arithmetic chain as K1 (sigproc.py:178-185
@@ -10,6 +11,12 @@
 // accumulated per bin in shared memory (a lane only ever touches bins congruent to its lane index, so no barrier is
 // needed), then |X|^2 / 1536, triangular mel sums (one filter at a time across the lanes), log, DCT * lifter.
 // Delta and delta-delta run in a second kernel over the cepstra (delta_batch_kernel).
+//
+// Other sizes (round 2; python_speech_features lets the caller choose NFFT, base.py:8 / sigproc.py:136-175): the same
+// decimation in time with R = nfft / 512 sub-sequences for nfft = 512 (odd hops, which K1's sample planes rule out), 1024,
+// 1536, 2048; for nfft = 512 / D < 512 the frame (at most nfft samples) is zero padded to 512 points and bin k of the short
+// transform is bin D k of the long one.  The filterbank (base.py:18) and spectrum (sigproc.py:136-175) taps of these sizes
+// leave the same code early (mode 1 / 2).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -19,16 +26,26 @@
 
 namespace dspfe {
 
-constexpr int kLongNfft = 1536;
+constexpr int kLongNfft = 1536;                  // the size with the decimation-in-frequency fast path
 constexpr int kLongBins = kLongNfft / 2 + 1;     // 769
+constexpr int kLongMaxNfft = 2048;
 constexpr int kLongWarps = 4;
 constexpr int kLongScr = 2 * 16 * 17;            // fft512's transpose tiles (float2)
 // float blob offsets (in floats): fft twiddles | W1536^k | window | mel tables | dct
-constexpr int kLtTw = 0, kLtW32 = kLtTw + 1024, kLtW1536 = kLtW32 + 64, kLtWin = kLtW1536 + 2 * kLongNfft,
-              kLtEdge = kLtWin + kLongNfft, kLtInvUp = kLtEdge + 48, kLtInvDn = kLtInvUp + 48, kLtDct = kLtInvDn + 48,
+constexpr int kLtTw = 0, kLtW32 = kLtTw + 1024, kLtW1536 = kLtW32 + 64, kLtWin = kLtW1536 + 2 * kLongMaxNfft,
+              kLtEdge = kLtWin + kLongMaxNfft, kLtInvUp = kLtEdge + 48, kLtInvDn = kLtInvUp + 48, kLtDct = kLtInvDn + 48,
               kLtTotal = kLtDct + 16 * 48;
-constexpr int kLongWarpSmem = kLongScr * 8 + (kLongBins + 7) * 16 + 64 * 8;     // transpose tiles | X / power per bin | log-mel pair
-constexpr int kLongCtaSmem = (kLtW1536 * 4) + kLongWarps * kLongWarpSmem;          // shared twiddles | per-warp areas
+// per-warp shared memory: transpose tiles | X / power per bin | log-mel pair.  The accumulators need nfft/2 + 1 float4 slots; the
+// decimation-in-frequency path of nfft = 1536 parks 512 float2 behind 769 + 7 float2 power values, which fits the same area.
+#ifdef __CUDACC__
+#define LONG_HD __host__ __device__
+#else
+#define LONG_HD
+#endif
+LONG_HD constexpr int long_warp_smem(int nfft) { return kLongScr * 8 + ((nfft < kLongNfft ? kLongNfft : nfft) / 2 + 1 + 7) * 16 + 64 * 8; }
+LONG_HD constexpr int long_cta_smem(int nfft) { return (kLtW1536 * 4) + kLongWarps * long_warp_smem(nfft); }   // shared twiddles | per-warp areas
+constexpr int kLongWarpSmem = long_warp_smem(kLongNfft);
+constexpr int kLongCtaSmem = long_cta_smem(kLongNfft);
 
 struct MfccLongParams {
     const void* pcm; int in_f32;
@@ -39,13 +56,24 @@ struct MfccLongParams {
     int frame_len, frame_step, nfilt, numcep, append_energy;
     float preemph;
     const float* tab;           // blob (kLt* offsets)
-    float* mfcc;                // [F_total, numcep] static cepstra
+    float* mfcc;                // [F_total, numcep] static cepstra (mode 0), [F_total, nfilt + 1] (mode 1), [F_total, nfft/2 + 1] (mode 2)
     int64_t max_frames;
+    int nfft, nbins;            // transform size, nfft / 2 + 1
+    int nsub, bin_stride;       // R = max(nfft / 512, 1) sub-sequences; D = max(512 / nfft, 1): bin k = bin D k of the 512-point transform
+    int warp_smem;              // long_warp_smem(nfft)
+    int mode, spec_kind;        // 0 cepstra | 1 filterbank energies + frame energy | 2 spectrum (0 power, 1 magnitude, 2 10 log10 power)
     // the mel filter edges and slope reciprocals, copied out of the blob: kernel parameters are read through the constant
     // bank with uniform loads, which takes five dependent global loads per filter out of the mel loop
     int32_t mel_edge[48];
     float mel_iu[48], mel_id[48];
 };
+inline bool long_nfft_ok(int nfft) {
+    return nfft == 32 || nfft == 64 || nfft == 128 || nfft == 256 || nfft == 512 || nfft == 1024 || nfft == 1536 || nfft == 2048;
+}
+inline void long_fill_size_params(MfccLongParams& p, int nfft, int mode, int spec_kind) {
+    p.nfft = nfft; p.nbins = nfft / 2 + 1; p.nsub = nfft >= 512 ? nfft / 512 : 1; p.bin_stride = nfft >= 512 ? 1 : 512 / nfft;
+    p.warp_smem = long_warp_smem(nfft); p.mode = mode; p.spec_kind = spec_kind;
+}
 inline void long_fill_mel_params(MfccLongParams& p, const float* host_tab) {
     for (int i = 0; i < 48; ++i) {
         p.mel_edge[i] = reinterpret_cast<const int32_t*>(host_tab + kLtEdge)[i];
@@ -89,7 +117,8 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     const int lane = simt::tid() & 31;
     float2* scr = reinterpret_cast<float2*>(wsm);
     float4* acc = reinterpret_cast<float4*>(scr + kLongScr);
-    float2* lmel = reinterpret_cast<float2*>(acc + kLongBins + 7);
+    const int nbins = p.nbins;
+    float2* lmel = reinterpret_cast<float2*>(wsm + p.warp_smem) - 64;
     const float2* w1536 = reinterpret_cast<const float2*>(p.tab + kLtW1536);
     const float* win = p.tab + kLtWin;
     const int32_t* edge = p.mel_edge;
@@ -110,12 +139,12 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);
     float2 esum = zero2;
-    const float sc = 1.0f / (float)kLongNfft;
+    const float sc = 1.0f / (float)p.nfft;
     // power spectrum of the pair as compact float2 [kLongBins] (8-byte stride: the mel loop's loads are conflict-free; the
     // float4 slots of the accumulation path put consecutive bins 16 bytes apart, a 4-way conflict on every scalar access)
     float2* pw2 = reinterpret_cast<float2*>(acc);
     float2* parked = pw2 + kLongBins + 7;            // [512] the windowed samples between the two passes (inside acc's area)
-    if (p.frame_len <= 512) {
+    if (p.nfft == kLongNfft && p.frame_len <= 512) {
         // Frames that fit 512 samples (30 ms at 16 kHz = 480): decimation in FREQUENCY.  X[3q + r] = FFT512(x[n] W1536^{n r})[q],
         // and for real x the bins 3q + 2 mirror the bins 3q' + 1 (X[1536 - k] = conj X[k], k = 3q'+1 -> 3(511 - q') + 2), so
         // two transforms in natural order give every power bin straight from the registers: r = 0 -> bins 3q (q <= 256),
@@ -148,49 +177,65 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
             }
         }
     } else {
+    const int R = p.nsub, D = p.bin_stride, half = p.nfft >> 1;
 #pragma unroll 1
-    for (int r = 0; r < 3; ++r) {
-        // sub-sequence r: element m = 32 t + lane is sample n = 3 m + r of the frame
+    for (int r = 0; r < R; ++r) {
+        // sub-sequence r: element m = 32 t + lane is sample n = R m + r of the frame
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-            const int n = 96 * t + 3 * lane + r;
-            const float w = ldg(win + n);
+            const int n = R * (32 * t + lane) + r;
+            const float w = ldg(win + n);                   // zero past the frame
             x[t].re = make_float2(long_sample(p, fa, n, w), long_sample(p, fb, n, w));
             x[t].im = zero2;
         }
         fft512(x, scr, tws, w32s, lane);
-        // X[k] += W1536^{r k} Z_r[k mod 512] for k = j and (j <= 256) k = j + 512, j = 32 t + lane
+        // X[k] += W_nfft^{r k} Z_r[k mod 512] for every bin k = j + 512 c <= nfft / 2, j = 32 t + lane (nfft >= 512);
+        // X[k] = Z_0[D k] for the short transforms
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int j = 32 * t + lane;
-            cpx2 v = x[t];
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r > 0) { const float2 w = ldg(w1536 + (r * j) % kLongNfft); v = cmuls(x[t], w.x, w.y); a = acc[j]; }
-            acc[j] = make_float4(a.x + v.re.x, a.y + v.re.y, a.z + v.im.x, a.w + v.im.y);
-            if (j <= 256) {
-                const int k = j + 512;
-                cpx2 u = x[t];
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r > 0) { const float2 w = ldg(w1536 + (r * k) % kLongNfft); u = cmuls(x[t], w.x, w.y); b = acc[k]; }
-                acc[k] = make_float4(b.x + u.re.x, b.y + u.re.y, b.z + u.im.x, b.w + u.im.y);
+            if (D > 1) {
+                if ((j & (D - 1)) == 0 && j / D <= half) acc[j / D] = make_float4(x[t].re.x, x[t].re.y, x[t].im.x, x[t].im.y);
+                continue;
+            }
+            for (int k = j; k <= half; k += 512) {
+                cpx2 v = x[t];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r > 0) {
+                    int i = r * k; if (i >= p.nfft) i -= p.nfft;     // r k < 2 nfft for R <= 4
+                    const float2 w = ldg(w1536 + i); v = cmuls(x[t], w.x, w.y); a = acc[k];
+                }
+                acc[k] = make_float4(a.x + v.re.x, a.y + v.re.y, a.z + v.im.x, a.w + v.im.y);
             }
         }
     }
+    simt::warp_sync();   // the short transforms' bins were written by other lanes
     // power spectrum |X|^2 / NFFT (sigproc.py:158) into the .x / .y of the bin's own slot; frame energy = sum over all bins
     // (bin k's float2 slot pw2[k] lies below its float4 accumulator acc[k] and is only written after acc[k] was read by the
     // same lane; other lanes' accumulators at or below byte 8k + 8 belong to bins <= k/2, read by the same loop iteration or earlier)
-    for (int k0 = 0; k0 < kLongBins; k0 += 32) {
+    for (int k0 = 0; k0 < nbins; k0 += 32) {
         const int k = k0 + lane;
         float2 pw = zero2;
-        if (k < kLongBins) { const float4 a = acc[k]; pw = make_float2((a.x * a.x + a.z * a.z) * sc, (a.y * a.y + a.w * a.w) * sc); }
+        if (k < nbins) { const float4 a = acc[k]; pw = make_float2((a.x * a.x + a.z * a.z) * sc, (a.y * a.y + a.w * a.w) * sc); }
         simt::warp_sync();
-        if (k < kLongBins) { pw2[k] = pw; esum.x += pw.x; esum.y += pw.y; }
+        if (k < nbins) { pw2[k] = pw; esum.x += pw.x; esum.y += pw.y; }
         simt::warp_sync();
     }
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) { esum.x += simt::shfl32_xor(esum.x, m); esum.y += simt::shfl32_xor(esum.y, m); }
     simt::warp_sync();
+    if (p.mode == 2) {   // spectrum tap (sigproc.py:136-175): rows straight to global memory
+        const float nf = (float)p.nfft;
+        for (int k = lane; k < nbins; k += 32) {
+            float2 v = pw2[k];
+            if (p.spec_kind == 1) { v.x = sqrtf(v.x * nf); v.y = sqrtf(v.y * nf); }
+            else if (p.spec_kind == 2) { v.x = 10.f * log10f(fmaxf(v.x, 1e-30f)); v.y = 10.f * log10f(fmaxf(v.y, 1e-30f)); }
+            p.mfcc[g0 * nbins + k] = v.x;
+            if (hasB) p.mfcc[(g0 + 1) * nbins + k] = v.y;
+        }
+        return;
+    }
     // mel filterbank (base.py:40-58): filter j rises over [e_j, e_{j+1}) and falls over [e_{j+1}, e_{j+2}); one filter at a
     // time, its bins spread over the lanes
     const float eps64 = 2.220446049250313e-16f;   // numpy.finfo(float64).eps floor (base.py:26,30)
@@ -226,10 +271,24 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
 #pragma unroll
         for (int m = 4; m >= 1; m >>= 1) { kk.x += simt::shfl32_xor(kk.x, m); kk.y += simt::shfl32_xor(kk.y, m); }
         const int jm = j0 + (up16 ? 2 : 0) + (up8 ? 1 : 0);
-        if ((lane & 7) == 0 && jm < p.nfilt)
-            lmel[jm] = make_float2(dsp_fast_logf(kk.x == 0.f ? eps64 : kk.x), dsp_fast_logf(kk.y == 0.f ? eps64 : kk.y));
+        if ((lane & 7) == 0 && jm < p.nfilt) {
+            if (kk.x == 0.f) kk.x = eps64;
+            if (kk.y == 0.f) kk.y = eps64;
+            if (p.mode == 1) {   // filterbank tap (base.py:18-32): energies, column nfilt = frame energy
+                p.mfcc[g0 * (p.nfilt + 1) + jm] = kk.x;
+                if (hasB) p.mfcc[(g0 + 1) * (p.nfilt + 1) + jm] = kk.y;
+            } else {
+                lmel[jm] = make_float2(dsp_fast_logf(kk.x), dsp_fast_logf(kk.y));
+            }
+        }
     }
-    if (lane == 0) lmel[p.nfilt] = make_float2(dsp_fast_logf(esum.x == 0.f ? eps64 : esum.x), dsp_fast_logf(esum.y == 0.f ? eps64 : esum.y));
+    if (esum.x == 0.f) esum.x = eps64;
+    if (esum.y == 0.f) esum.y = eps64;
+    if (p.mode == 1) {
+        if (lane == 0) { p.mfcc[g0 * (p.nfilt + 1) + p.nfilt] = esum.x; if (hasB) p.mfcc[(g0 + 1) * (p.nfilt + 1) + p.nfilt] = esum.y; }
+        return;
+    }
+    if (lane == 0) lmel[p.nfilt] = make_float2(dsp_fast_logf(esum.x), dsp_fast_logf(esum.y));
     simt::warp_sync();
     // DCT-II (ortho) * lifter (base.py:12-14), c0 := log(energy) (base.py:15)
     if (lane < p.numcep) {

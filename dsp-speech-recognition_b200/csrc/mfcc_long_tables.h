@@ -15,11 +15,11 @@ inline std::vector<float> build_long_tables(const MfccConfig& c) {
     const double kPi = 3.14159265358979323846;
     std::vector<float> t(kLtTotal, 0.f);
     fill_fft512_twiddles(reinterpret_cast<float2*>(t.data() + kLtTw), reinterpret_cast<float2*>(t.data() + kLtW32));
-    for (int k = 0; k < kLongNfft; ++k) { t[kLtW1536 + 2 * k] = (float)cos(-2 * kPi * k / kLongNfft); t[kLtW1536 + 2 * k + 1] = (float)sin(-2 * kPi * k / kLongNfft); }
+    for (int k = 0; k < c.nfft; ++k) { t[kLtW1536 + 2 * k] = (float)cos(-2 * kPi * k / c.nfft); t[kLtW1536 + 2 * k + 1] = (float)sin(-2 * kPi * k / c.nfft); }
     for (int n = 0; n < c.frame_len; ++n) t[kLtWin + n] = c.window.empty() ? 1.f : (float)c.window[n];
     const std::vector<double> bins = mel_bin_edges(c);            // floor((nfft+1) * mel2hz(.) / samplerate), base.py:49
     int32_t* edge = reinterpret_cast<int32_t*>(t.data() + kLtEdge);
-    for (int i = 0; i < c.nfilt + 2; ++i) edge[i] = std::min(std::max((int)bins[i], 0), kLongBins);
+    for (int i = 0; i < c.nfilt + 2; ++i) edge[i] = std::min(std::max((int)bins[i], 0), c.nfft / 2 + 1);
     for (int j = 0; j < c.nfilt; ++j) {
         t[kLtInvUp + j] = edge[j + 1] > edge[j] ? (float)(1.0 / (bins[j + 1] - bins[j])) : 0.f;
         t[kLtInvDn + j] = edge[j + 2] > edge[j + 1] ? (float)(1.0 / (bins[j + 2] - bins[j + 1])) : 0.f;

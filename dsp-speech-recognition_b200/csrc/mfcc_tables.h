@@ -50,9 +50,10 @@ inline std::vector<double> mel_bin_edges(const MfccConfig& c) {
     return b;
 }
 
-// nfft = 1536 (the long-frame kernel K1L, mfcc_long_kernel.cuh)
+// every transform size but K1's (the long-frame / general kernel K1L, mfcc_long_kernel.cuh)
 inline std::string mfcc_long_config_check(const MfccConfig& c) {
-    if (c.nfft != 1536) return "nfft must be 512 or 1536 in this build";
+    if (!(c.nfft == 32 || c.nfft == 64 || c.nfft == 128 || c.nfft == 256 || c.nfft == 512 || c.nfft == 1024 || c.nfft == 1536 || c.nfft == 2048))
+        return "nfft must be a power of two in [32, 2048] or 1536 in this build";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
     if (c.frame_step < 1) return "frame_step must be >= 1";
     if (c.frame_step > (c.count_len > 0 ? c.count_len : c.frame_len)) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";

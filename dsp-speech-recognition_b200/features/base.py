@@ -13,21 +13,22 @@ except Exception:  # pragma: no cover
     dct = None
 
 
-def _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc, long_ok=False):
+_NFFT_BUILT = (32, 64, 128, 256, 512, 1024, 1536, 2048)
+
+
+def _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc):
     signal = numpy.asarray(signal)
     if signal.ndim == 2:
         if signal.shape[0] != 1:
             raise NotImplementedError("2-D signals other than (1,S) are not supported")
         # reference sigproc.py:185 on a (1,S) array: signal[1:] is empty, so the row comes back unfiltered
         signal, preemph = signal[0], 0.0
-    if nfft != 512 and not (long_ok and nfft == 1536):
-        raise NotImplementedError("nfft=512 (and, for mfcc, nfft=1536 as model.py:74 uses) are built")
+    if nfft not in _NFFT_BUILT:
+        raise NotImplementedError("nfft must be a power of two in [32, 2048] or 1536 (model.py:74)")
     frame_len = sigproc.round_half_up(winlen * samplerate)
     frame_step = sigproc.round_half_up(winstep * samplerate)
     if frame_len > nfft:   # reference sigproc.py:143-146: frames are counted and windowed at full length, the transform takes their first nfft samples
         logging.warning('frame length (%d) is greater than FFT size (%d), frame will be truncated. Increase NFFT to avoid.', frame_len, nfft)
-    if nfft == 512 and (frame_step % 2 or frame_step < 2):
-        raise NotImplementedError("odd frame steps are built for nfft=1536 only")
     win = numpy.asarray(winfunc(frame_len), dtype=numpy.float64)
     x, f32 = _gpu.pack_one(signal)
     return x, f32, frame_len, frame_step, float(preemph), win
@@ -39,7 +40,7 @@ def mfcc(signal, samplerate=16000, winlen=0.025, winstep=0.01, numcep=13,
     """reference base.py:8-16.  Returns float64 [NUMFRAMES, numcep]."""
     highfreq = highfreq or samplerate / 2
     assert highfreq <= samplerate / 2, "highfreq is greater than samplerate/2"
-    x, f32, flen, fstep, pre, win = _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc, long_ok=True)
+    x, f32, flen, fstep, pre, win = _prepare(signal, samplerate, winlen, winstep, nfft, preemph, winfunc)
     plan = _gpu.mfcc_plan(samplerate=samplerate, frame_len=flen, frame_step=fstep, nfft=nfft, nfilt=nfilt, numcep=numcep,
                           ceplifter=int(ceplifter), append_energy=bool(appendEnergy), delta_n=1, preemph=pre,
                           lowfreq=float(lowfreq), highfreq=float(highfreq), window=win)

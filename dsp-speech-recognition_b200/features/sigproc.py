@@ -73,8 +73,8 @@ def _spectrum(frames, NFFT, kind):
     frames = numpy.asarray(frames, dtype=numpy.float64)
     if frames.ndim != 2:
         raise NotImplementedError("frames must be a 2-D array")
-    if NFFT != 512:
-        raise NotImplementedError("only NFFT=512 is built (SURVEY f-2 lists the other sizes)")
+    if NFFT not in (32, 64, 128, 256, 512, 1024, 1536, 2048):
+        raise NotImplementedError("NFFT must be a power of two in [32, 2048] or 1536")
     if numpy.shape(frames)[1] > NFFT:
         logging.warning('frame length (%d) is greater than FFT size (%d), frame will be truncated. Increase NFFT to avoid.',
                      numpy.shape(frames)[1], NFFT)

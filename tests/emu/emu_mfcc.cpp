@@ -82,7 +82,7 @@ void long_body(void* a) {
     const int64_t g0 = 2 * ((int64_t)simt::bid() * kLongWarps + w);
     if (g0 >= A->total) return;
     const float2* tws = reinterpret_cast<const float2*>(A->p.tab);
-    mfcc_long_pair(A->p, g0, A->total, A->smem->data() + w * kLongWarpSmem, tws, tws + kLtW32 / 2);
+    mfcc_long_pair(A->p, g0, A->total, A->smem->data() + w * A->p.warp_smem, tws, tws + kLtW32 / 2);
 }
 }  // namespace
 
@@ -111,8 +111,9 @@ extern "C" long long emu_mfcc_long(const dspfe_mfcc_params* q, const void* pcm, 
     p.pcm = pcm; p.in_f32 = in_f32; p.seg_start = seg_start.data(); p.seg_len = seg_len.data(); p.frame_off = frame_off.data(); p.n_utt = n_utt;
     p.frame_len = c.frame_len; p.frame_step = c.frame_step; p.nfilt = c.nfilt; p.numcep = c.numcep; p.append_energy = c.append_energy;
     p.preemph = (float)c.preemph; p.tab = tab.data(); p.mfcc = cep.data(); p.max_frames = fo;
+    long_fill_size_params(p, c.nfft, 0, 0);
     long_fill_mel_params(p, tab.data());
-    std::vector<unsigned char> smem(kLongWarps * kLongWarpSmem + 64);
+    std::vector<unsigned char> smem(kLongWarps * p.warp_smem + 64);
     LArgs A{p, &smem, fo};
     for (int64_t b = 0; b * 2 * kLongWarps < fo + 2 * kLongWarps; ++b) {
         std::memset(smem.data(), 0xCD, smem.size());
