@@ -206,7 +206,9 @@ int dspfe_endpoint_robust(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t
     p.pcm = d_pcm; p.offsets = d_offsets; p.n_utt = n_utt; p.frame_len = pl->frame_len; p.frame_step = pl->frame_step;
     p.q = pl->q; p.rem = pl->rem; p.frame_off = pl->frame_off; p.block_off = pl->block_off; p.blk = pl->blk; p.asum = pl->asum; p.zcr = pl->zcr;
     p.lr = d_lr; p.max_blocks = 0; p.max_frames = frames_bound; p.rule = pl->rule;
-    ep_decide_robust_kernel<<<(unsigned)((n_utt + kEpRobustWarps - 1) / kEpRobustWarps), 32 * kEpRobustWarps, 0, st>>>(p);
+    CUDA_TRY(cudaFuncSetAttribute(ep_decide_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpRobustSmem));
+    CUDA_TRY(cudaFuncSetAttribute(ep_decide_robust_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    ep_decide_robust_kernel<<<(unsigned)n_utt, 32 * kEpRobustWarps, kEpRobustSmem, st>>>(p);
     LAUNCH_CHECK("ep_decide_robust_kernel", st);
     return DSPFE_OK;
 }

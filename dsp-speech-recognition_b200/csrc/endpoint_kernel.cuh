@@ -78,8 +78,10 @@ struct ZcrFromI32 { const int32_t* z; DSP_HD double operator()(int i) const { re
 // number of segments found; *left/*right = first segment start / last segment end, or (0, F) when none qualifies.
 // Gate of the expansion loops: always open for the basic rule; robust_endpoint_detection closes it on frames whose
 // normalised autocorrelation peak is below 0.55 (acr_rule, endpoint.py:142-144).
-struct GateOpen { DSP_HD bool operator()(int) const { return true; } };
-struct GateFromFlags { const int32_t* g; DSP_HD bool operator()(int i) const { return g[i] != 0; } };
+// hint(dir, M_L): the walk about to start moves by dir (-1 / +1) per frame and continues while amp > M_L and the gate holds; a
+// gate that is expensive may evaluate the frames ahead speculatively (K3r).
+struct GateOpen { DSP_HD bool operator()(int) const { return true; } DSP_HD void hint(int, double) {} };
+struct GateFromFlags { const int32_t* g; DSP_HD bool operator()(int i) const { return g[i] != 0; } DSP_HD void hint(int, double) {} };
 
 template <class Amp, class Gate = GateOpen>
 DSP_HD int amplitude_rule(Amp amp, int F, const EpRule& r, double mh, int* left, int* right, int32_t* segs = nullptr, int seg_cap = 0,
@@ -110,7 +112,9 @@ DSP_HD int amplitude_rule(Amp amp, int F, const EpRule& r, double mh, int* left,
             if ((double)(k - j) < T_H) {
                 i = k;
             } else {
+                gate.hint(-1, M_L);
                 while (j > 0 && amp(j) > M_L && gate(j)) --j;
+                gate.hint(+1, M_L);
                 while (k < F && amp(k) > M_L && gate(k)) ++k;
                 if (first < 0) first = j;
                 last = k;
@@ -509,86 +513,134 @@ __global__ void __launch_bounds__(32 * kEpDecideWarps) ep_decide_kernel(EpParams
     }
 }
 
-// Warp-cooperative gate (acr_rule, endpoint.py:142-144): the frame is staged in shared memory as float64 (int16 samples,
-// their products and the lag sums are exact in float64, as in the reference) with a zero tail.  A lane owns chunks of
-// kGateChunk CONSECUTIVE lags: for a block of eight sample positions it loads eight shared values x[i..i+7] (the same for all
-// lanes) and slides a register window over x[i+n..], so every shared-memory load feeds kGateChunk fused multiply-adds
-// (the first version did two loads per product and was bound by the load pipe).  Chunk c goes to lane c mod 32.
-// All lanes of the warp execute the rule in lock step on identical data, so the gate is called convergently.
+// K3r gate (acr_rule, endpoint.py:142-144), one warp per frame.  The frame is staged in shared memory as float32 (int16
+// samples are exact) with a zero tail.  A lane owns chunks of kGateChunk CONSECUTIVE lags: for a block of eight sample positions
+// it loads eight shared values x[i..i+7] (the same for all lanes) and slides a register window over x[i+n..], so every
+// shared-memory load feeds kGateChunk fused multiply-adds.  Chunk c goes to lane c mod 32.
+//   * screening pass in float32: the lag sums carry a relative error of at most k 2^-24 sum|x_i x_{i+n}| <= k 2^-24 s0 (k terms,
+//     Cauchy-Schwarz), i.e. at most delta = 1.5 len 2^-24 len / (len - n_max) on the ratio the rule thresholds at 0.55;
+//   * only when the float32 ratio lies within delta of 0.55 the sums are recomputed exactly (float64: products of int16
+//     samples and their sums are exact, as in the reference's float64), so the decision is the reference's bit for bit.
 constexpr int kEpGateMaxLen = 1536;
 constexpr int kGateChunk = 9;
 constexpr int kGatePad = 32;
-struct GateWarp {
-    const int16_t* x; long long S; int step, len, n0, n1; double* sx;   // utterance samples, its length, framing, lag range, staging
-    __device__ bool operator()(int j) const {
-        const int lane = threadIdx.x & 31;
-        const long long b = (long long)j * step;
-        __syncwarp();
-        for (int i = lane; i < len + kGatePad; i += 32) sx[i] = (i < len && b + i < S) ? (double)x[b + i] : 0.0;
-        __syncwarp();
-        double s0 = 0.0;
-        for (int i = lane; i < len; i += 32) s0 = fma(sx[i], sx[i], s0);
-        double best = -1.0e300;
-        const int nl = (n1 < len ? n1 : len) - n0;           // lags n0 .. n0 + nl - 1
-        for (int c = lane; c * kGateChunk < nl; c += 32) {
-            const int nb = n0 + c * kGateChunk;              // first lag of the chunk: it has the most terms
-            double acc[kGateChunk], w[kGateChunk + 7];
+// max over the lags n0 .. n0 + nl - 1 of acr(n) = S_n / (len - n), this lane's share (reduce with warp_max_f64).  sx is 16-byte
+// aligned: the eight x[i..i+7] every lane needs come from two broadcast 16-byte loads.
+// (A split that pairs chunk c with chunk 31 - c on two lanes, so that every lane walks the same number of positions, was
+// measured slower -- 3.37 against 2.99 ms: the lanes then read x[i..] at different i, all multiples of eight apart, and the
+// loads that were broadcasts turn into 4-way bank conflicts.)
+template <typename T>
+__device__ __forceinline__ T gate_best(const float* sx, int len, int n0, int nl, int lane) {
+    T best = (T)-3.0e38f;
+    for (int c = lane; c * kGateChunk < nl; c += 32) {
+        const int nb = n0 + c * kGateChunk;              // first lag of the chunk: it has the most terms
+        T acc[kGateChunk], w[kGateChunk + 7];
 #pragma unroll
-            for (int m = 0; m < kGateChunk; ++m) acc[m] = 0.0;
+        for (int m = 0; m < kGateChunk; ++m) acc[m] = (T)0;
 #pragma unroll
-            for (int m = 0; m < kGateChunk - 1; ++m) w[m] = sx[nb + m];
-            for (int i = 0; i < len - nb; i += 8) {
-                // window w[u + m] = x[i + u + nb + m]; terms past the frame multiply the zero tail
+        for (int m = 0; m < kGateChunk - 1; ++m) w[m] = (T)sx[nb + m];
+        for (int i = 0; i < len - nb; i += 8) {
+            // window w[u + m] = x[i + u + nb + m]; terms past the frame multiply the zero tail
 #pragma unroll
-                for (int u = 0; u < 8; ++u) w[kGateChunk - 1 + u] = sx[i + nb + kGateChunk - 1 + u];
+            for (int u = 0; u < 8; ++u) w[kGateChunk - 1 + u] = (T)sx[i + nb + kGateChunk - 1 + u];
+            const float4 a0 = *reinterpret_cast<const float4*>(sx + i), a1 = *reinterpret_cast<const float4*>(sx + i + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const double a = sx[i + u];
+            for (int u = 0; u < 8; ++u) {
+                const T a = (T)av[u];
 #pragma unroll
-                    for (int m = 0; m < kGateChunk; ++m) acc[m] = fma(a, w[u + m], acc[m]);
-                }
-#pragma unroll
-                for (int m = 0; m < kGateChunk - 1; ++m) w[m] = w[m + 8];
+                for (int m = 0; m < kGateChunk; ++m) acc[m] = fma(a, w[u + m], acc[m]);
             }
 #pragma unroll
-            for (int m = 0; m < kGateChunk; ++m) {
-                const int n = nb + m;
-                if (n < n0 + nl) { const double a = acc[m] / (double)(len - n); best = a > best ? a : best; }
-            }
+            for (int m = 0; m < kGateChunk - 1; ++m) w[m] = w[m + 8];
         }
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            s0 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(s0), m), __shfl_xor_sync(0xffffffffu, __double2loint(s0), m));
-            const double o = __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(best), m), __shfl_xor_sync(0xffffffffu, __double2loint(best), m));
-            best = o > best ? o : best;
+        for (int m = 0; m < kGateChunk; ++m) {
+            const int n = nb + m;
+            if (n < n0 + nl) { const T a = acc[m] / (T)(len - n); best = a > best ? a : best; }
         }
-        if (nl <= 0) return false;
-        return best / (s0 / (double)len) > 0.55;   // acr_gate_decide on float64 sums (0 / 0 = NaN compares false, as in the reference)
+    }
+    return best;
+}
+// the gate of the frame starting at sample b of the utterance x[0..S); warp-uniform result
+__device__ bool gate_frame_warp(const int16_t* x, long long S, long long b, int len, int n0, int n1, float* sx, int lane) {
+    __syncwarp();
+    for (int i = lane; i < len + kGatePad; i += 32) sx[i] = (i < len && b + i < S) ? (float)x[b + i] : 0.f;
+    __syncwarp();
+    const int nl = (n1 < len ? n1 : len) - n0;           // lags n0 .. n0 + nl - 1
+    if (nl <= 0) return false;
+    long long s0i = 0;
+    for (int i = lane; i < len; i += 32) { const long long v = (long long)sx[i]; s0i += v * v; }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s0i += __shfl_xor_sync(0xffffffffu, s0i, m);
+    if (s0i == 0) return false;                          // 0 / 0 = NaN compares false, as in the reference
+    const double a0 = (double)s0i / (double)len;
+    const double delta = 1.5 * (double)len * 5.9604644775390625e-08 * (double)len / (double)(len - (n0 + nl - 1));
+    if (delta < 0.01) {
+        const float bf = gate_best<float>(sx, len, n0, nl, lane);
+        const double ratio = warp_max_f64((double)bf) / a0;
+        if (ratio > 0.55 + delta) return true;
+        if (ratio < 0.55 - delta) return false;
+    }
+    return warp_max_f64(gate_best<double>(sx, len, n0, nl, lane)) / a0 > 0.55;   // acr_gate_decide on exact sums
+}
+
+// CTA-cooperative gate of K3r: every thread of the CTA replays the rule in lock step on identical data.  A request for a frame
+// that is not in the current window makes the CTA's warps evaluate that frame and the next kEpRobustWarps - 1 frames of the
+// walk (those the walk can reach: amp > M_L all the way) at once, one frame per warp; the walk's following requests hit the window.
+constexpr int kEpRobustWarps = 8;
+template <class Amp>
+struct GateCta {
+    const int16_t* x; long long S; int step, len, n0, n1, F;
+    Amp amp; float* sx; int* s_res;       // per-warp staging areas [kEpRobustWarps][kEpGateMaxLen + kGatePad], window results
+    int dir; double m_l; int win_base, win_dir, win_known, win_val;
+    __device__ void hint(int d, double ml) { dir = d; m_l = ml; }
+    __device__ bool operator()(int j) {
+        const int wi = (j - win_base) * win_dir;
+        if (wi >= 0 && wi < kEpRobustWarps && ((win_known >> wi) & 1)) return (win_val >> wi) & 1;
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int fj = j + dir * w;
+        bool want = dir < 0 ? fj >= 1 : fj < F;
+        for (int t = 1; t <= w && want; ++t) want = amp(j + dir * t) > m_l;
+        int res = 0;
+        if (want) res = 2 | (gate_frame_warp(x, S, (long long)fj * step, len, n0, n1, sx + w * (kEpGateMaxLen + kGatePad), lane) ? 1 : 0);
+        __syncthreads();                 // the previous window's results have been read by every thread
+        if (lane == 0) s_res[w] = res;
+        __syncthreads();
+        win_base = j; win_dir = dir; win_known = 0; win_val = 0;
+#pragma unroll
+        for (int t = 0; t < kEpRobustWarps; ++t) { const int r = s_res[t]; win_known |= (r >> 1) << t; win_val |= (r & 1) << t; }
+        return win_val & 1;
     }
 };
 
-constexpr int kEpRobustWarps = 1;
-__global__ void __launch_bounds__(32 * kEpRobustWarps) ep_decide_robust_kernel(EpParams p) {
-    __shared__ double s_amp[kEpRobustWarps][kEpStageFrames];
-    __shared__ int32_t s_zcr[kEpRobustWarps][kEpStageFrames];
-    __shared__ double s_x[kEpRobustWarps][kEpGateMaxLen + kGatePad];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int u = blockIdx.x * kEpRobustWarps + w;
-    if (u >= p.n_utt) return;
+__global__ void __launch_bounds__(32 * kEpRobustWarps, 3) ep_decide_robust_kernel(EpParams p) {
+    extern __shared__ __align__(16) unsigned char ep_rsm[];
+    double* s_amp = reinterpret_cast<double*>(ep_rsm);                                   // [kEpStageFrames]
+    int32_t* s_zcr = reinterpret_cast<int32_t*>(s_amp + kEpStageFrames);                 // [kEpStageFrames]
+    int* s_res = s_zcr + kEpStageFrames;                                                 // [kEpRobustWarps]
+    float* s_x = reinterpret_cast<float*>(s_res + kEpRobustWarps);                       // [kEpRobustWarps][kEpGateMaxLen + kGatePad]
+    const int u = blockIdx.x;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
-    const GateWarp gate{p.pcm + p.offsets[u], (long long)(p.offsets[u + 1] - p.offsets[u]), p.frame_step, p.frame_len,
-                        p.rule.rate / 500, p.rule.rate / 50, s_x[w]};
+    const int16_t* x = p.pcm + p.offsets[u];
+    const long long S = (long long)(p.offsets[u + 1] - p.offsets[u]);
     int32_t lr[2];
-    // every lane replays the rule on identical data (the gate is warp-cooperative)
+    // every thread replays the rule on identical data (the gate is CTA-cooperative)
     if (F <= kEpStageFrames) {
-        ep_stage(p.asum + f0, p.zcr + f0, F, (double)p.frame_len, s_amp[w], s_zcr[w], lane);
-        endpoint_decide_robust(AmpFromF64{s_amp[w]}, s_zcr[w], F, p.rule, gate, lr);
+        for (int i = threadIdx.x; i < F; i += blockDim.x) { s_amp[i] = (double)p.asum[f0 + i] / (double)p.frame_len; s_zcr[i] = p.zcr[f0 + i]; }
+        __syncthreads();
+        GateCta<AmpFromF64> gate{x, S, p.frame_step, p.frame_len, p.rule.rate / 500, p.rule.rate / 50, F, AmpFromF64{s_amp}, s_x, s_res,
+                                 -1, 0.0, 0, 1, 0, 0};
+        endpoint_decide_robust(AmpFromF64{s_amp}, s_zcr, F, p.rule, gate, lr);
     } else {
-        endpoint_decide_robust(AmpFromSum{p.asum + f0, (double)p.frame_len}, p.zcr + f0, F, p.rule, gate, lr);
+        const AmpFromSum amp{p.asum + f0, (double)p.frame_len};
+        GateCta<AmpFromSum> gate{x, S, p.frame_step, p.frame_len, p.rule.rate / 500, p.rule.rate / 50, F, amp, s_x, s_res, -1, 0.0, 0, 1, 0, 0};
+        endpoint_decide_robust(amp, p.zcr + f0, F, p.rule, gate, lr);
     }
-    if (lane == 0) { p.lr[2 * u] = lr[0]; p.lr[2 * u + 1] = lr[1]; }
+    if (threadIdx.x == 0) { p.lr[2 * u] = lr[0]; p.lr[2 * u + 1] = lr[1]; }
 }
+constexpr int kEpRobustSmem = kEpStageFrames * 12 + kEpRobustWarps * 4 + kEpRobustWarps * (kEpGateMaxLen + kGatePad) * 4;
 
 // the gate of every row of a float64 frame matrix (the list-typed amplitude_rule(use_acr=True, frames=...) API): one warp per row
 __global__ void acr_gate_rows_kernel(const double* frames, int64_t n_rows, int len, int n0, int n1, int32_t* gate) {
