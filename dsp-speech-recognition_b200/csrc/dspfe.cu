@@ -25,6 +25,13 @@ __global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __gri
     mfcc_cta<HAS_WIN, NFULL, F32IN, MODE>(p, smem);
 }
 
+// K1T: nfft = 1536 for frames of at most 512 samples (model.py:74 at 16 kHz) on K1's tile structure
+template <bool HAS_WIN, int NFULL, bool F32IN>
+__global__ void __launch_bounds__(kMfccThreads, 2) mfcc_tri_kernel(const __grid_constant__ MfccParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    mfcc_cta<HAS_WIN, NFULL, F32IN, 0, true>(p, smem);
+}
+
 // K1L: long frames under nfft = 1536, a frame pair per warp; then delta / delta-delta over the cepstra
 __global__ void __launch_bounds__(32 * kLongWarps, 3) mfcc_long_kernel(const __grid_constant__ MfccLongParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -85,6 +92,12 @@ mfcc_kernel_t pick_kernel(bool has_win, int frame_len, bool f32, int mode = 0) {
     if (nfull == 12) return mfcc_delta_kernel<false, 12, false>;
     if (nfull == 15) return mfcc_delta_kernel<false, 15, false>;
     return mfcc_delta_kernel<false, -1, false>;
+}
+
+mfcc_kernel_t pick_tri_kernel(bool has_win, int frame_len, bool f32) {
+    if (f32) return has_win ? mfcc_tri_kernel<true, -1, true> : mfcc_tri_kernel<false, -1, true>;
+    if (has_win) return (frame_len >> 5) == 15 ? mfcc_tri_kernel<true, 15, false> : mfcc_tri_kernel<true, -1, false>;
+    return mfcc_tri_kernel<false, -1, false>;
 }
 
 MfccConfig to_config(const dspfe_mfcc_params& q) {
@@ -176,7 +189,7 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
     prep_kernel<<<1, kPrepThreads, 0, st>>>(pp);
     LAUNCH_CHECK("prep_kernel", st);
 
-    if (pl->is_long) {
+    if (pl->is_long || (mode != 0 && pl->d_long_tab)) {
         const int64_t rows = total_samples / pl->cfg.frame_step + n_utt;
         if (mode == 0) { rc = ws.ensure_cep(rows * pl->cfg.numcep); if (rc) return rc; }
         MfccLongParams lp;
@@ -255,18 +268,18 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     std::memset(&pl->layout, 0, sizeof(pl->layout));
     std::string err;
     // K1 takes nfft = 512 with an even hop (its sample planes); every other size / hop goes to the general kernel K1L
-    if (pl->cfg.nfft != kNfft || (pl->cfg.frame_step & 1) || pl->cfg.frame_step < 2) {
+    const bool tiled = (pl->cfg.nfft == kNfft || (pl->cfg.nfft == kTriNfft && pl->cfg.frame_len <= 512)) && !(pl->cfg.frame_step & 1) && pl->cfg.frame_step >= 2;
+    if (!tiled || pl->cfg.nfft != kNfft) {   // (a K1T plan keeps the general kernel for its filterbank / spectrum taps)
         err = mfcc_long_config_check(pl->cfg);
         if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
-        pl->is_long = true; pl->has_win = !pl->cfg.window.empty(); pl->width = 3 * pl->cfg.numcep;
+        pl->is_long = !tiled; pl->has_win = !pl->cfg.window.empty(); pl->width = 3 * pl->cfg.numcep;
         const std::vector<float> t = build_long_tables(pl->cfg);
         pl->h_long_tab = t;
         cudaError_t e = cudaMalloc(&pl->d_long_tab, t.size() * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_long_tab, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, long_cta_smem(kLongMaxNfft));
         if (e != cudaSuccess) { cudaFree(pl->d_long_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
-        *plan = pl;
-        return DSPFE_OK;
+        if (!tiled) { *plan = pl; return DSPFE_OK; }
     }
     std::vector<float> blob = build_mfcc_tables(pl->cfg, pl->layout, err);
     if (err.empty()) { std::memset(&pl->layout_f32, 0, sizeof(pl->layout_f32)); build_mfcc_tables(pl->cfg, pl->layout_f32, err, true); }
@@ -275,14 +288,17 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     pl->width = 3 * pl->cfg.numcep;
     cudaError_t e = cudaMalloc(&pl->d_tables, blob.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice);
-    pl->kernel = pick_kernel(pl->has_win, pl->cfg.frame_len, false);
-    pl->kernel_f32 = pick_kernel(pl->has_win, pl->cfg.frame_len, true);
+    const bool tri = pl->cfg.nfft == kTriNfft;
+    pl->kernel = tri ? pick_tri_kernel(pl->has_win, pl->cfg.frame_len, false) : pick_kernel(pl->has_win, pl->cfg.frame_len, false);
+    pl->kernel_f32 = tri ? pick_tri_kernel(pl->has_win, pl->cfg.frame_len, true) : pick_kernel(pl->has_win, pl->cfg.frame_len, true);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout.sm_total);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
-    pl->kernel_fbank = pick_kernel(pl->has_win, pl->cfg.frame_len, true, 1);
-    pl->kernel_spec = pick_kernel(pl->has_win, pl->cfg.frame_len, true, 2);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_fbank, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
+    if (!tri) {
+        pl->kernel_fbank = pick_kernel(pl->has_win, pl->cfg.frame_len, true, 1);
+        pl->kernel_spec = pick_kernel(pl->has_win, pl->cfg.frame_len, true, 2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_fbank, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pl->kernel_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->layout_f32.sm_total);
+    }
     if (e != cudaSuccess) { cudaFree(pl->d_tables); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
     *plan = pl;
     return DSPFE_OK;

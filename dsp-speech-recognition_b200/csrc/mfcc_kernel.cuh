@@ -68,7 +68,13 @@ DEVFN ChunkGeom chunk_geom(const MfccParams& p, int sh, int lim, int S, int fram
 // F32IN: the packed batch holds float32 samples instead of int16 (e.g. a signal the caller already scaled).
 // MODE: 0 = MFCC + delta + delta-delta rows [F, 3*numcep]; 1 = filterbank energies + frame energy [F, nfilt+1]
 // (reference fbank, base.py:18); 2 = spectrum [F, 257]: power (sigproc.py:151), magnitude (:136) or 10*log10 power (:161).
-template <bool HAS_WIN, int NFULL, bool F32IN, int MODE>
+// TRI: K1T -- nfft = 1536 for frames of at most 512 samples (model.py:74 at 16 kHz), same tile / chunk / epilogue structure.
+// The 1536-point real transform is a 768-point complex one on z[m] = x[2m] + i x[2m+1]; only z[0..255] is non-zero, so the
+// decimation in frequency by three needs no butterflies: Z[3q + r] = FFT256(z[m] W768^{m r})[q], three of K1's register
+// transforms per frame pair.  The real split pairs Z[k] with Z[768 - k]: class 0 (k = 3q) with itself -- K1's split verbatim,
+// W1536^{3q} = W512^q -- and class 2 (k = 3q + 2) with class 1 (768 - k = 3 (255 - q) + 1), which waits in shared memory.
+// Power bins stay in three arrays indexed by q (class c = bins 3q + c); the mel pieces are built per class (mfcc_tables.h).
+template <bool HAS_WIN, int NFULL, bool F32IN, int MODE, bool TRI = false>
 DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     const int tid = simt::tid();
     const int lane = tid & 15;
@@ -103,12 +109,10 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
 
     const float2* twa = reinterpret_cast<const float2*>(sm.tables + p.o_twa);
     const float2* twp = reinterpret_cast<const float2*>(sm.tables + p.o_twp);
-    const float2* melw = reinterpret_cast<const float2*>(sm.tables + p.o_melw) + lane;   // [iteration pair][lane] filter weights
-    const int* melb = reinterpret_cast<const int*>(sm.tables + p.o_melb) + lane;   // [slot][lane] first bin of the lane's piece
     const int4* melc = reinterpret_cast<const int4*>(sm.tables + p.o_melc);  // [filter] -> the partial sums that make it up
     const float* dct = sm.tables + p.o_dct;
     const float* win = sm.tables + p.o_win;
-    float2* scr = sm.scratch + grp * kScratchUnits;
+    float2* scr = sm.scratch + grp * (TRI ? kTriUnits : kScratchUnits);
 
     // everything below addresses the packed buffer relative to the utterance's aligned-down start
     const int esz = F32IN ? 4 : 2;
@@ -198,7 +202,8 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
         const int vA = frame0 + fl;
         if (frame0 + 4 * (tid >> 5) <= v_hi) {
             cpx2 x[16];
-            {
+            // windowed samples of the pair as z[m] = x[2m] + i x[2m+1], m = 16 n1 + lane
+            auto load_pair = [&](cpx2 (&x)[16]) {
                 const int fb0 = fb_base + fl * p.frame_step;   // staging index of the frame's sample 0
                 const float* plane_e = sm.fbuf;
                 const float* plane_o = sm.fbuf + 4 * p.fbuf_vecs;
@@ -224,30 +229,36 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                     x[n1].re = make_float2(ar, br);
                     x[n1].im = make_float2(ai, bi);
                 }
-            }
-            // stage 1: DFT over n1 (registers); lane = n2
-            dft16(x);
-            // twiddle W256^{n2*k1}
+            };
+            // 256-point complex transform of the pair: lane = n2 in, lane = k1 out, register k2 holds Z[k1 + 16*k2]
+            auto fft256 = [&](cpx2 (&x)[16]) {
+                // stage 1: DFT over n1 (registers); lane = n2
+                dft16(x);
+                // twiddle W256^{n2*k1}
 #pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) { const float2 w = twa[k1 * 16 + lane]; x[k1] = cmuls(x[k1], w.x, w.y); }
-            // transpose through shared: (k1, n2) -> lane k1, register n2; real parts then imaginary parts
+                for (int k1 = 1; k1 < 16; ++k1) { const float2 w = twa[k1 * 16 + lane]; x[k1] = cmuls(x[k1], w.x, w.y); }
+                // transpose through shared: (k1, n2) -> lane k1, register n2; real parts then imaginary parts
 #pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) scr[k1 * 17 + lane] = x[k1].re;
-            simt::group_sync();
+                for (int k1 = 0; k1 < 16; ++k1) scr[k1 * 17 + lane] = x[k1].re;
+                simt::group_sync();
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) x[n2].re = scr[lane * 17 + n2];
-            simt::group_sync();
+                for (int n2 = 0; n2 < 16; ++n2) x[n2].re = scr[lane * 17 + n2];
+                simt::group_sync();
 #pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) scr[k1 * 17 + lane] = x[k1].im;
-            simt::group_sync();
+                for (int k1 = 0; k1 < 16; ++k1) scr[k1 * 17 + lane] = x[k1].im;
+                simt::group_sync();
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) x[n2].im = scr[lane * 17 + n2];
-            simt::group_sync();
-            // stage 2: DFT over n2; lane = k1, register k2 holds Z[k1 + 16*k2]
-            dft16(x);
+                for (int n2 = 0; n2 < 16; ++n2) x[n2].im = scr[lane * 17 + n2];
+                simt::group_sync();
+                // stage 2: DFT over n2; lane = k1, register k2 holds Z[k1 + 16*k2]
+                dft16(x);
+            };
+            load_pair(x);
+            fft256(x);
 
             // ---- real-FFT split, pairwise: bins k = lane + 16 r (r < 8) and 256 - k share one butterfly.
             // partner Z[(256-k) mod 256] lives in lane (16-lane)&15, register 15-r (lane 0: register (16-r)&15).
+            // (K1T: the same butterflies give the class-0 bins X[3k] and X[3 (256 - k)] of the 1536-point transform.)
             const int src = (16 - lane) & 15;
             const float sc = p.pow_scale;  // 1 / (4 * NFFT)
             float2 esum = make_float2(0.f, 0.f);   // this lane's share of sum_k P[k] (frame energy, reference base.py:25)
@@ -301,13 +312,16 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
 
             // ---- mel filterbank (reference base.py:28-29): every lane accumulates one piece of a filter per slot; the
             // trip counts are uniform over the lanes and the weights come from a [iteration][lane] table (mfcc_tables.h)
-            float2 macc[kMelSlots];
-            {
+            constexpr int NCLS = TRI ? 3 : 1;
+            float2 macc[NCLS][kMelSlots];
+            auto mel_round = [&](int cls, const float2* P, float2 (&acc)[kMelSlots]) {
+                const float2* melw = reinterpret_cast<const float2*>(sm.tables + p.o_melw_c[cls]) + lane;   // [iteration pair][lane] filter weights
+                const int* melb = reinterpret_cast<const int*>(sm.tables + p.o_melb_c[cls]) + lane;         // [slot][lane] first bin of the lane's piece
                 int tb = 0;
 #pragma unroll
                 for (int s = 0; s < kMelSlots; ++s) {
-                    const int T = p.mel_T[s];
-                    const float2* pp = scr + melb[s * kGroupLanes];
+                    const int T = p.mel_Tc[cls][s];
+                    const float2* pp = P + melb[s * kGroupLanes];
                     const float2* wp = melw + (tb >> 1) * kGroupLanes;
                     float2 a0 = make_float2(0.f, 0.f), a1 = a0;
 #pragma unroll 4
@@ -316,9 +330,60 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                         a0 = f2fmas(pp[t], w.x, a0);
                         a1 = f2fmas(pp[t + 1], w.y, a1);
                     }
-                    macc[s] = f2add(a0, a1);
+                    acc[s] = f2add(a0, a1);
                     tb += T;
                 }
+            };
+            mel_round(0, scr, macc[0]);
+            if constexpr (TRI) {
+                float4* zb = reinterpret_cast<float4*>(scr + kScratchUnits);   // [256] Z_1 of the pair: (re.x, re.y, im.x, im.y)
+                float2* p1 = scr + kScratchUnits + 256;                        // [256] class-1 power bins, in zb's upper half once it is consumed
+                const float2* tw3 = reinterpret_cast<const float2*>(sm.tables + p.o_tw3) + lane;
+                const float2* tws2 = reinterpret_cast<const float2*>(sm.tables + p.o_tws2) + lane;
+                simt::group_sync();          // the class-0 bins have been consumed: the tile is free again
+                // class 1: Z[3q + 1] = FFT256(z[m] W768^m)[q], parked
+                load_pair(x);
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) { const float2 w = tw3[16 * n1]; x[n1] = cmuls(x[n1], w.x, w.y); }
+                fft256(x);
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) zb[lane + 16 * k2] = make_float4(x[k2].re.x, x[k2].re.y, x[k2].im.x, x[k2].im.y);
+                // class 2: Z[3q + 2] = FFT256(z[m] W768^{2m})[q] in registers; Z[3q' + 2] pairs with Z[768 - (3q' + 2)] = Z_1[255 - q']
+                load_pair(x);
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) { const float2 w = tw3[256 + 16 * n1]; x[n1] = cmuls(x[n1], w.x, w.y); }
+                fft256(x);
+                // four butterflies at a time: the partners are read before the batch's class-1 results overwrite the upper
+                // half of zb (entries the later batches still read lie below everything written so far)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float4 zq[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) zq[t] = zb[255 - (lane + 16 * (4 * g + t))];
+                    simt::group_sync();
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int k2 = 4 * g + t, q = lane + 16 * k2;
+                        const cpx2 a = x[k2];
+                        cpx2 b; b.re = make_float2(zq[t].x, zq[t].y); b.im = make_float2(zq[t].z, zq[t].w);
+                        const float2 sre = f2add(a.re, b.re), sim = f2sub(a.im, b.im);
+                        const float2 dre = f2sub(a.re, b.re), dim = f2add(a.im, b.im);
+                        const float2 w = tws2[16 * k2];  // W1536^{3q + 2}
+                        const float2 tre = f2fmas(dim, w.x, f2muls(dre, w.y));
+                        const float2 tim = f2fmas(dim, w.y, f2muls(dre, -w.x));
+                        const float2 are = f2add(sre, tre), aim = f2add(sim, tim);
+                        const float2 bre = f2sub(sre, tre), bim = f2sub(sim, tim);
+                        const float2 pa = f2muls(f2fma(aim, aim, f2mul(are, are)), sc);   // bin 3q + 2
+                        const float2 pb = f2muls(f2fma(bim, bim, f2mul(bre, bre)), sc);   // bin 3 (255 - q) + 1
+                        scr[q] = pa;
+                        p1[255 - q] = pb;
+                        esum = f2add(esum, f2add(pa, pb));
+                    }
+                }
+                scr[256 + lane] = make_float2(0.f, 0.f);     // class 2 has 256 bins; the pieces may read (with zero weights) past them
+                simt::group_sync();
+                mel_round(1, p1, macc[1]);
+                mel_round(2, scr, macc[2]);
             }
             // total frame energy (reference base.py:25): reduce over the group
 #pragma unroll
@@ -327,18 +392,25 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 esum.y += simt::shfl16(esum.y, lane ^ m);
             }
             simt::group_sync();  // all lanes are done reading P before the staging area overwrites it
-            float2* part = scr;                                   // [kMelSlots * 16 + 1]; the last entry stays zero
-            float2* lmel = scr + kMelSlots * kGroupLanes + 2;     // [nfilt + 1]; the last entry is log(energy); 16-byte aligned
+            float2* part = scr;                                   // [NCLS * kMelSlots * 16 + 1]; the last entry stays zero
+            float2* lmel = scr + NCLS * kMelSlots * kGroupLanes + 2;     // [nfilt + 1]; the last entry is log(energy); 16-byte aligned
 #pragma unroll
-            for (int s = 0; s < kMelSlots; ++s) part[s * kGroupLanes + lane] = macc[s];
-            if (lane == 0) part[kMelSlots * kGroupLanes] = make_float2(0.f, 0.f);
+            for (int c = 0; c < NCLS; ++c)
+#pragma unroll
+                for (int s = 0; s < kMelSlots; ++s) part[(c * kMelSlots + s) * kGroupLanes + lane] = macc[c][s];
+            if (lane == 0) part[NCLS * kMelSlots * kGroupLanes] = make_float2(0.f, 0.f);
             simt::group_sync();
             const float eps64 = 2.220446049250313e-16f;  // numpy.finfo(float64).eps, reference base.py:26,30
             for (int j = lane; j <= p.nfilt; j += 16) {
                 float2 f = esum;
                 if (j < p.nfilt) {
-                    const int4 ci = melc[j];
+                    const int4 ci = melc[j * NCLS];
                     f = f2add(f2add(part[ci.x], part[ci.y]), f2add(part[ci.z], part[ci.w]));
+#pragma unroll
+                    for (int c = 1; c < NCLS; ++c) {
+                        const int4 cj = melc[j * NCLS + c];
+                        f = f2add(f, f2add(f2add(part[cj.x], part[cj.y]), f2add(part[cj.z], part[cj.w])));
+                    }
                 }
                 if (f.x == 0.f) f.x = eps64;
                 if (f.y == 0.f) f.y = eps64;

@@ -68,7 +68,8 @@ inline std::string mfcc_long_config_check(const MfccConfig& c) {
 }
 
 inline std::string mfcc_config_check(const MfccConfig& c) {
-    if (c.nfft != kNfft) return "nfft must be 512 in this build (other sizes: SURVEY f-2)";
+    if (c.nfft != kNfft && c.nfft != kTriNfft) return "the tiled kernel is built for nfft 512 and 1536 (other sizes: the general kernel)";
+    if (c.nfft == kTriNfft && c.frame_len > 512) return "the tiled nfft-1536 kernel takes frames of at most 512 samples (longer frames: the general kernel)";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
     if (c.frame_step < 2 || (c.frame_step & 1)) return "frame_step must be even and >= 2";
     if (c.frame_step > (c.count_len > 0 ? c.count_len : c.frame_len)) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
@@ -112,27 +113,56 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
         const double a = -2.0 * kPi * (double)k / 512.0;
         blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
     }
+    // K1T input twiddles W768^{m r} (decimation in frequency by three) and the split twiddles of the class-2 bins
+    const bool tri = c.nfft == kTriNfft;
+    p.tri = tri ? 1 : 0;
+    p.grp_units = tri ? kTriUnits : kScratchUnits;
+    if (tri) {
+        align4();
+        p.o_tw3 = (int)blob.size();
+        for (int r = 1; r <= 2; ++r)
+            for (int m = 0; m < 256; ++m) {
+                const double a = -2.0 * kPi * (double)(m * r) / 768.0;
+                blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
+            }
+        p.o_tws2 = (int)blob.size();
+        for (int q = 0; q < 256; ++q) {
+            const double a = -2.0 * kPi * (double)(3 * q + 2) / 1536.0;
+            blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
+        }
+    }
     // Mel filterbank (reference base.py:40-58) as balanced *pieces*: filter j has non-zero weights on one contiguous
     // run of bins; the runs are cut into pieces and every (slot, lane) of a 16-lane group owns at most one piece.
     // All lanes run the same mel_T[slot] iterations per slot (zero weights pad short pieces), so the kernel's loop
     // has a uniform trip count, no per-lane branching and reads its weights from a [iteration][lane] table.
+    // K1T keeps the power bins in three arrays, class c = bins 3q + c indexed by q: a filter's weights on one class are again a
+    // contiguous run, so every class gets its own piece table and the partial sums of the three meet in the combine step.
+    const int nbins = c.nfft / 2 + 1, ncls = tri ? 3 : 1;
     const std::vector<double> bins = mel_bin_edges(c);
     for (int i = 0; i < c.nfilt + 2; ++i)
-        if (bins[i] < 0 || bins[i] > kNfft / 2) { err = "mel bin edges fall outside [0, nfft/2]"; return {}; }
-    struct Run { int k0; std::vector<float> w; };
-    std::vector<Run> runs(c.nfilt);
+        if (bins[i] < 0 || bins[i] > c.nfft / 2) { err = "mel bin edges fall outside [0, nfft/2]"; return {}; }
+    std::vector<std::vector<double>> dense(c.nfilt, std::vector<double>(nbins, 0.0));
     for (int j = 0; j < c.nfilt; ++j) {
         const int lo = (int)bins[j], ce = (int)bins[j + 1], hi = (int)bins[j + 2];
-        std::vector<double> w(kBins, 0.0);
-        for (int k = lo; k < ce; ++k) w[k] = (k - bins[j]) / (bins[j + 1] - bins[j]);
-        for (int k = ce; k < hi; ++k) w[k] = (bins[j + 2] - k) / (bins[j + 2] - bins[j + 1]);
-        int a = 0, b = kBins;
-        while (a < kBins && w[a] == 0.0) ++a;
-        while (b > a && w[b - 1] == 0.0) --b;
-        runs[j].k0 = a < kBins ? a : 0;
-        for (int k = a; k < b; ++k) runs[j].w.push_back((float)w[k]);
+        for (int k = lo; k < ce; ++k) dense[j][k] = (k - bins[j]) / (bins[j + 1] - bins[j]);
+        for (int k = ce; k < hi; ++k) dense[j][k] = (bins[j + 2] - k) / (bins[j + 2] - bins[j + 1]);
     }
+    struct Run { int k0; std::vector<float> w; };
     struct Piece { int filt, off, len, slot, lane, k0; };
+    const int zero_part = ncls * kMelSlots * kGroupLanes;      // index of the always-zero partial sum
+    std::vector<int> comb((size_t)kMaxNfilt * kMelMaxPieces * ncls, zero_part);
+    int npc[kMaxNfilt] = {0};
+    for (int cls = 0; cls < ncls; ++cls) {
+    const int nq = (nbins - cls + ncls - 1) / ncls;            // entries of the class array
+    const int units = tri && cls == 1 ? 256 : kScratchUnits;   // 8-byte units a piece may read (zero padded past nq)
+    std::vector<Run> runs(c.nfilt);
+    for (int j = 0; j < c.nfilt; ++j) {
+        int a = 0, b = nq;
+        while (a < nq && dense[j][ncls * a + cls] == 0.0) ++a;
+        while (b > a && dense[j][ncls * (b - 1) + cls] == 0.0) --b;
+        runs[j].k0 = a < nq ? a : 0;
+        for (int k = a; k < b; ++k) runs[j].w.push_back((float)dense[j][ncls * k + cls]);
+    }
     std::vector<Piece> pieces;
     int mel_T[kMelSlots] = {0, 0, 0};
     {
@@ -148,7 +178,7 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
             int owner[kGroupLanes]; for (int l = 0; l < kGroupLanes; ++l) owner[l] = -1;
             auto ok = [&](int i, int l) {
                 const int k0 = runs[out[i].filt].k0 + out[i].off, d = ((k0 - l) % kGroupLanes + kGroupLanes) % kGroupLanes;
-                return k0 - d >= 0 && d + out[i].len <= T && k0 - d + T <= kScratchUnits;
+                return k0 - d >= 0 && d + out[i].len <= T && k0 - d + T <= units;
             };
             bool seen[kGroupLanes];
             std::function<bool(int)> aug = [&](int i) {
@@ -166,7 +196,7 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
                 int l = 0;   // last resort (degenerate filterbanks): natural starts, bank conflicts accepted
                 for (int i : idx) {
                     const int k0 = runs[out[i].filt].k0 + out[i].off;
-                    out[i].lane = l++; out[i].k0 = std::max(0, std::min(k0, kScratchUnits - T));
+                    out[i].lane = l++; out[i].k0 = std::max(0, std::min(k0, units - T));
                     if (k0 - out[i].k0 + out[i].len > T) return false;
                 }
                 return true;
@@ -221,13 +251,13 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
         if (!ok) { err = "mel filterbank does not fit the piece table"; return {}; }
     }
     int mel_iters = 0;
-    for (int s = 0; s < kMelSlots; ++s) { p.mel_T[s] = mel_T[s]; mel_iters += mel_T[s]; }
+    for (int s = 0; s < kMelSlots; ++s) { p.mel_Tc[cls][s] = mel_T[s]; if (cls == 0) p.mel_T[s] = mel_T[s]; mel_iters += mel_T[s]; }
     {
         // weights as pairs: [iteration / 2][lane][iteration & 1]
         std::vector<float> wt((size_t)std::max(mel_iters, 2) * kGroupLanes, 0.f);
-        std::vector<int> base(kMelSlots * kGroupLanes, 0), comb(kMaxNfilt * kMelMaxPieces, kMelSlots * kGroupLanes);
+        std::vector<int> base(kMelSlots * kGroupLanes, 0);
         for (int i = 0; i < kMelSlots * kGroupLanes; ++i) base[i] = i % kGroupLanes;   // idle lanes keep to their own banks
-        int npc[kMaxNfilt] = {0}, tb[kMelSlots];
+        int tb[kMelSlots];
         tb[0] = 0; for (int s = 1; s < kMelSlots; ++s) tb[s] = tb[s - 1] + mel_T[s - 1];
         for (const Piece& pc : pieces) {
             const int shift = runs[pc.filt].k0 + pc.off - pc.k0;
@@ -236,17 +266,20 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
                 const int it = tb[pc.slot] + shift + t;
                 wt[((size_t)(it >> 1) * kGroupLanes + pc.lane) * 2 + (it & 1)] = runs[pc.filt].w[pc.off + t];
             }
-            comb[pc.filt * kMelMaxPieces + npc[pc.filt]++] = pc.slot * kGroupLanes + pc.lane;
+            comb[((size_t)pc.filt * ncls + cls) * kMelMaxPieces + npc[pc.filt]++ % kMelMaxPieces] = cls * kMelSlots * kGroupLanes + pc.slot * kGroupLanes + pc.lane;
         }
+        for (int j = 0; j < c.nfilt; ++j) npc[j] = 0;
         align4();
-        p.o_melw = (int)blob.size();
+        p.o_melw_c[cls] = (int)blob.size();
         blob.insert(blob.end(), wt.begin(), wt.end());
-        p.o_melb = (int)blob.size();
+        p.o_melb_c[cls] = (int)blob.size();
         for (int v : base) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
-        align4();
-        p.o_melc = (int)blob.size();
-        for (int v : comb) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
     }
+    }   // classes
+    p.o_melw = p.o_melw_c[0]; p.o_melb = p.o_melb_c[0];
+    align4();
+    p.o_melc = (int)blob.size();      // [filter][class] int4: the partial sums that make the filter up
+    for (int v : comb) { float f; std::memcpy(&f, &v, 4); blob.push_back(f); }
     align4();
     // DCT-II (ortho) rows premultiplied by the lifter
     p.o_dct = (int)blob.size();
@@ -271,7 +304,7 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     int off = up16(p.tbl_floats * 4);
     p.sm_mbar = off; off += 16;
     // FFT scratch; the epilogue reuses it for the delta-delta rows of the tile
-    p.sm_scratch = off; off += std::max(kMfccGroups * kScratchUnits * 8, up16(c.seg_frames * c.numcep * 4));
+    p.sm_scratch = off; off += std::max(kMfccGroups * p.grp_units * 8, up16(c.seg_frames * c.numcep * 4));
     p.sm_mfcc = off; off += up16((c.seg_frames + 4 * c.delta_n) * c.numcep * 4);
     p.fbuf_floats = (kFramesPerPass - 1) * c.frame_step + c.frame_len;
     // raw staging: the chunk's samples + one history sample + up to 7 samples of 16-byte alignment slack either side;

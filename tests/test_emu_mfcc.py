@@ -77,7 +77,7 @@ def test_float32_input_path():
 
 def test_unsupported_configs_are_rejected():
     x = np.zeros(1000, dtype=np.int16)
-    for kw in (dict(nfft=1536), dict(frame_len=600), dict(frame_step=161), dict(nfilt=41), dict(numcep=17),
+    for kw in (dict(nfft=1024), dict(nfft=1536, frame_len=600), dict(frame_len=600), dict(frame_step=161), dict(nfilt=41), dict(numcep=17),
                dict(delta_n=0), dict(highfreq=9000.0)):
         with pytest.raises(RuntimeError):
             emu.mfcc_delta(x, [0, 1000], **kw)
@@ -104,6 +104,37 @@ def test_long_frame_kernel_nfft1536():
     xf = (x / np.std(x)).astype(np.float32)          # model.py:62-63 feeds scaled float audio
     out, fo = emu.mfcc_long(xf, [0, len(xf)], frame_len=1323, frame_step=441, window=np.hamming(1323), samplerate=44100, preemph=0.0)
     assert_mfcc_close(out, ref39(xf.astype(np.float64), 44100, 2, preemph=0), what="44.1k float")
+
+
+def test_tiled_nfft1536_kernel():
+    """K1T: model.py:74's configuration at 16 kHz -- 30 ms Hamming frames of 480 samples under nfft = 1536 --
+    on K1's tile structure: three 256-point complex transforms per frame pair, per-class mel pieces.  Ragged batch incl.
+    one-frame and multi-tile utterances, delta N = 2 / 3, float input, rectangular window, other frame lengths, trims."""
+    def ref39(x, N, **kw):
+        kw.setdefault("winlen", 0.03)
+        m = O.mfcc(x, 16000, winstep=0.01, nfft=1536, **kw)
+        d1 = O.delta(m, N)
+        return np.concatenate([m, d1, O.delta(d1, N)], axis=1)
+    pcm, off = synth.synth_batch([9000, 479, 481, 4000, 1, 50000], seed0=300)
+    for N in (2, 3):
+        out, fo = emu.mfcc_delta(pcm, off, nfft=1536, frame_len=480, frame_step=160, window=np.hamming(480), preemph=0.0, delta_n=N)
+        for u in range(6):
+            assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(pcm[off[u]:off[u + 1]], N, preemph=0, winfunc=np.hamming), what=f"N={N} utt {u}")
+    out, fo = emu.mfcc_delta(pcm, off, nfft=1536, frame_len=480, frame_step=160, seg_frames=32)       # rectangular window, pre-emphasis, small tiles
+    for u in range(6):
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(pcm[off[u]:off[u + 1]], 2), what=f"rect utt {u}")
+    for flen in (400, 512, 161):
+        out, fo = emu.mfcc_delta(pcm[:9000], [0, 9000], nfft=1536, frame_len=flen, frame_step=160, window=np.hamming(flen))
+        assert_mfcc_close(out, ref39(pcm[:9000], 2, winlen=flen / 16000, winfunc=np.hamming), what=f"frame_len {flen}")
+    x = pcm[off[3]:off[4]]
+    xf = (x / np.std(x)).astype(np.float32)          # model.py:62-63 feeds scaled float audio
+    out, fo = emu.mfcc_delta(xf, [0, len(xf)], nfft=1536, frame_len=480, frame_step=160, window=np.hamming(480), preemph=0.0, delta_n=3)
+    assert_mfcc_close(out, ref39(xf.astype(np.float64), 3, preemph=0, winfunc=np.hamming), what="float input")
+    trim = np.array([[100, 8000], [0, 479], [5, 400], [1000, 1500], [0, 1], [777, 40001]], dtype=np.int32)
+    out, fo = emu.mfcc_delta(pcm, off, trim=trim, nfft=1536, frame_len=480, frame_step=160, window=np.hamming(480), preemph=0.0)
+    for u in range(6):
+        xs = pcm[off[u]:off[u + 1]][trim[u, 0]:trim[u, 1]]
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(xs, 2, preemph=0, winfunc=np.hamming), what=f"trim utt {u}")
 
 
 def test_general_kernel_other_transform_sizes():

@@ -299,3 +299,44 @@ def test_other_transform_sizes_and_odd_hops():
             assert_mfcc_close(out[fo[u]:fo[u + 1]], ref, what=f"nfft {nfft} utt {u}")
     with pytest.raises(NotImplementedError):
         features.mfcc(x, nfft=768)
+
+
+def test_tiled_nfft1536_kernel_batch():
+    """K1T: the 16 kHz form of model.py:74's call (480-sample Hamming frames, nfft 1536) on the tile kernel:
+    ragged int16 batch with endpoint-style trims and delta N = 3, float32 samples, the host-buffer path."""
+    import torch
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    from tol import assert_mfcc_close
+    dev = torch.device("cuda:0")
+    lengths = [30000, 479, 481, 16000, 1, 90000, 52345]
+    pcm, off = synth.synth_batch(lengths, seed0=1536)
+    trim = np.array([[0, 30000], [0, 479], [3, 480], [500, 15000], [0, 1], [1234, 88888], [0, 52345]], dtype=np.int32)
+    plan = dspfe.MfccPlan(frame_len=480, frame_step=160, nfft=1536, window=np.hamming(480), preemph=0.0, delta_n=3)
+    assert plan.info()["ctas_per_sm"] >= 2
+    out, fo = plan.mfcc_delta(torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev), trim=torch.from_numpy(trim).to(dev))
+    torch.cuda.synchronize()
+    out, fo = out.cpu().numpy(), fo.cpu().numpy()
+
+    def ref39(x, N):
+        m = O.mfcc(x, 16000, winlen=0.03, winstep=0.01, nfft=1536, preemph=0, winfunc=np.hamming)
+        d1 = O.delta(m, N)
+        return np.concatenate([m, d1, O.delta(d1, N)], axis=1)
+    for u in range(len(lengths)):
+        xs = pcm[off[u]:off[u + 1]][trim[u, 0]:trim[u, 1]]
+        assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(xs, 3), what=f"K1T utt {u}")
+    host, hfo = plan.mfcc_delta_host(pcm, off)
+    for u in (0, 3, 5):
+        assert_mfcc_close(host[hfo[u]:hfo[u + 1]], ref39(pcm[off[u]:off[u + 1]], 3), what=f"K1T host utt {u}")
+    xf = (pcm[off[5]:off[6]] / 3000.0).astype(np.float32)
+    of, ff = plan.mfcc_delta_f32(torch.from_numpy(xf).to(dev), torch.tensor([0, len(xf)], device=dev))
+    torch.cuda.synchronize()
+    assert_mfcc_close(of.cpu().numpy()[: int(ff[-1])], ref39(xf.astype(np.float64), 3), what="K1T float32 samples")
+    # the filterbank / spectrum taps of such a plan go through the general kernel
+    import features
+    x = pcm[off[0]:off[1]]
+    feat, energy = features.fbank(x, winlen=0.03, nfft=1536, winfunc=np.hamming)
+    wf, we = O.fbank(x, winlen=0.03, nfft=1536, winfunc=np.hamming)
+    assert np.max(np.abs(feat - wf) / np.maximum(np.abs(wf), 1e-3 * wf.max())) <= 1e-4
+    assert np.max(np.abs(energy - we) / np.abs(we)) <= 1e-4
