@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kMfccThreads, 2) mfcc_tri_kernel(const __grid_
 }
 
 // K1L: long frames under nfft = 1536, a frame pair per warp; then delta / delta-delta over the cepstra
+template <int NFFT>
 __global__ void __launch_bounds__(32 * kLongWarps, 3) mfcc_long_kernel(const __grid_constant__ MfccLongParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* tws = reinterpret_cast<float2*>(smem);
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(32 * kLongWarps, 3) mfcc_long_kernel(const __g
     const int w = threadIdx.x >> 5;
     const int64_t g0 = 2 * ((int64_t)blockIdx.x * kLongWarps + w);
     if (g0 >= total) return;
-    mfcc_long_pair(p, g0, total, smem + kLtW1536 * 4 + w * p.warp_smem, tws, tws + kLtW32 / 2);
+    mfcc_long_pair<NFFT>(p, g0, total, smem + kLtW1536 * 4 + w * p.warp_smem, tws, tws + kLtW32 / 2);
 }
 // delta + delta-delta over per-utterance cepstra (base.py:70-79 twice, model.py:76-77), one CTA per utterance: thread = (row of a
 // block of 8, column).  Pass 1 writes the static and delta columns, pass 2 reads the deltas back (edge-clamped on the DELTA
@@ -198,7 +199,9 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
         lp.append_energy = pl->cfg.append_energy; lp.preemph = (float)pl->cfg.preemph; lp.tab = pl->d_long_tab; lp.mfcc = mode == 0 ? ws.cep : d_out; lp.max_frames = rows;
         long_fill_size_params(lp, pl->cfg.nfft, mode, spec_kind);
         long_fill_mel_params(lp, pl->h_long_tab.data());
-        mfcc_long_kernel<<<(unsigned)((rows + 2 * kLongWarps - 1) / (2 * kLongWarps)), 32 * kLongWarps, long_cta_smem(pl->cfg.nfft), st>>>(lp);
+        const unsigned lgrid = (unsigned)((rows + 2 * kLongWarps - 1) / (2 * kLongWarps));
+        if (pl->cfg.nfft == kLongNfft) mfcc_long_kernel<kLongNfft><<<lgrid, 32 * kLongWarps, long_cta_smem(kLongNfft), st>>>(lp);
+        else mfcc_long_kernel<0><<<lgrid, 32 * kLongWarps, long_cta_smem(pl->cfg.nfft), st>>>(lp);
         LAUNCH_CHECK("mfcc_long_kernel", st);
         if (mode != 0) return DSPFE_OK;
         int den = 0; for (int i = 1; i <= pl->cfg.delta_n; ++i) den += i * i;
@@ -277,7 +280,8 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
         pl->h_long_tab = t;
         cudaError_t e = cudaMalloc(&pl->d_long_tab, t.size() * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_long_tab, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, long_cta_smem(kLongMaxNfft));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, long_cta_smem(kLongMaxNfft));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mfcc_long_kernel<kLongNfft>, cudaFuncAttributeMaxDynamicSharedMemorySize, long_cta_smem(kLongNfft));
         if (e != cudaSuccess) { cudaFree(pl->d_long_tab); delete pl; return fail(DSPFE_ERR_CUDA, cudaGetErrorString(e)); }
         if (!tiled) { *plan = pl; return DSPFE_OK; }
     }
@@ -327,8 +331,13 @@ int dspfe_plan_info(const dspfe_plan* pl, int32_t* smem_bytes, int32_t* ctas_per
     cudaFuncAttributes fa;
     int nb = 0;
     if (pl->is_long) {
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_long_kernel));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_long_kernel, 32 * kLongWarps, long_cta_smem(pl->cfg.nfft)));
+        if (pl->cfg.nfft == kLongNfft) {
+            CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_long_kernel<kLongNfft>));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_long_kernel<kLongNfft>, 32 * kLongWarps, long_cta_smem(pl->cfg.nfft)));
+        } else {
+            CUDA_TRY(cudaFuncGetAttributes(&fa, mfcc_long_kernel<0>));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mfcc_long_kernel<0>, 32 * kLongWarps, long_cta_smem(pl->cfg.nfft)));
+        }
         if (smem_bytes) *smem_bytes = long_cta_smem(pl->cfg.nfft);
         if (ctas_per_sm) *ctas_per_sm = nb;
         if (regs_per_thread) *regs_per_thread = fa.numRegs;

@@ -61,6 +61,9 @@ struct FeLane {                       // one slab in flight: the four sub-plans 
     int64_t* d_tot = nullptr;                                                    // [3] the slab's totals
     cudaStream_t stream = nullptr;                                               // host path only
     cudaEvent_t finish_done = nullptr;
+    // the two pitch chains of a slab run beside its MFCC kernels (they only share the endpoints): side streams, fork / join events
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 struct dspfe_frontend_plan {
@@ -124,12 +127,34 @@ int run_slab(dspfe_frontend_plan* pl, FeLane& ln, const int16_t* pcm, int64_t to
              int64_t* dbase_out = nullptr, int64_t* h_tot = nullptr, cudaEvent_t wait_prev = nullptr) {
     int rc = dspfe_endpoint(ln.ep, pcm, total, rel_off, nu, lr, nullptr, nullptr, nullptr, 0, st);
     if (rc) return rc;
+    // MFCC, cepstrum pitch and autocorrelation pitch depend on the endpoints only: three branches, so that the single-CTA
+    // prefix sums, the latency-bound pitch_feature kernel and the ragged tails of the track kernels of one branch are filled
+    // by the other branches' transforms.  While a per-kernel timing collection is open everything stays on `st`, serially.
+    const bool fork = !g_timer.on;
+    cudaStream_t sa = st, sb = st;
+    if (fork) {
+        for (int k = 0; k < 2; ++k) {
+            if (!ln.side[k]) CUDA_TRY(cudaStreamCreateWithFlags(&ln.side[k], cudaStreamNonBlocking));
+            if (!ln.ev_join[k]) CUDA_TRY(cudaEventCreateWithFlags(&ln.ev_join[k], cudaEventDisableTiming));
+        }
+        if (!ln.ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ln.ev_fork, st));
+        sa = ln.side[0]; sb = ln.side[1];
+        CUDA_TRY(cudaStreamWaitEvent(sa, ln.ev_fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(sb, ln.ev_fork, 0));
+    }
+    rc = dspfe_pitch(ln.cep, pcm, 0, total, rel_off, lr, nu, cep, cep_lag, feat, nullptr, ln.loc_off[1], cep_cap, sa);
+    if (rc) return rc;
+    rc = dspfe_pitch(ln.acr, pcm, 0, total, rel_off, lr, nu, acr, acr_lag, nullptr, nullptr, ln.loc_off[2], acr_cap, sb);
+    if (rc) return rc;
     rc = dspfe_mfcc_delta(ln.mf, pcm, total, rel_off, lr, nu, mfcc, mfcc_cap, ln.loc_off[0], st);
     if (rc) return rc;
-    rc = dspfe_pitch(ln.cep, pcm, 0, total, rel_off, lr, nu, cep, cep_lag, feat, nullptr, ln.loc_off[1], cep_cap, st);
-    if (rc) return rc;
-    rc = dspfe_pitch(ln.acr, pcm, 0, total, rel_off, lr, nu, acr, acr_lag, nullptr, nullptr, ln.loc_off[2], acr_cap, st);
-    if (rc) return rc;
+    if (fork) {
+        CUDA_TRY(cudaEventRecord(ln.ev_join[0], sa));
+        CUDA_TRY(cudaEventRecord(ln.ev_join[1], sb));
+        CUDA_TRY(cudaStreamWaitEvent(st, ln.ev_join[0], 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, ln.ev_join[1], 0));
+    }
     if (wait_prev) CUDA_TRY(cudaStreamWaitEvent(st, wait_prev, 0));
     FeFinish f;
     for (int k = 0; k < 3; ++k) { f.loc[k] = ln.loc_off[k]; f.glob[k] = glob[k]; f.base[k] = base[k]; }
@@ -165,6 +190,9 @@ void dspfe_frontend_destroy(dspfe_frontend_plan* pl) {
         cudaFree(ln.d_tot);
         if (ln.stream) cudaStreamDestroy(ln.stream);
         if (ln.finish_done) cudaEventDestroy(ln.finish_done);
+        for (auto q : ln.side) if (q) cudaStreamDestroy(q);
+        for (auto q : ln.ev_join) if (q) cudaEventDestroy(q);
+        if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
     }
     cudaFree(pl->rel_off); cudaFree(pl->d_base); if (pl->h_tot) cudaFreeHost(pl->h_tot);
     cudaFree(pl->s_lr); cudaFree(pl->s_mfcc); cudaFree(pl->s_cep); cudaFree(pl->s_acr);

@@ -113,11 +113,14 @@ DEVFN float long_sample(const MfccLongParams& p, const LongFrame& f, int n, floa
 }
 
 // wsm: per-warp shared memory = scr[kLongScr] float2 | acc[kLongBins] float4 | lmel[64] float2
+// NFFT: the transform size when known at compile time (1536: the trainer's), else 0
+template <int NFFT = 0>
 DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, unsigned char* wsm, const float2* tws, const float2* w32s) {
     const int lane = simt::tid() & 31;
     float2* scr = reinterpret_cast<float2*>(wsm);
     float4* acc = reinterpret_cast<float4*>(scr + kLongScr);
-    const int nbins = p.nbins;
+    const int nfft = NFFT ? NFFT : p.nfft;
+    const int nbins = NFFT ? NFFT / 2 + 1 : p.nbins;
     float2* lmel = reinterpret_cast<float2*>(wsm + p.warp_smem) - 64;
     const float2* w1536 = reinterpret_cast<const float2*>(p.tab + kLtW1536);
     const float* win = p.tab + kLtWin;
@@ -139,12 +142,12 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     cpx2 x[16];
     const float2 zero2 = make_float2(0.f, 0.f);
     float2 esum = zero2;
-    const float sc = 1.0f / (float)p.nfft;
+    const float sc = 1.0f / (float)nfft;
     // power spectrum of the pair as compact float2 [kLongBins] (8-byte stride: the mel loop's loads are conflict-free; the
     // float4 slots of the accumulation path put consecutive bins 16 bytes apart, a 4-way conflict on every scalar access)
     float2* pw2 = reinterpret_cast<float2*>(acc);
     float2* parked = pw2 + kLongBins + 7;            // [512] the windowed samples between the two passes (inside acc's area)
-    if (p.nfft == kLongNfft && p.frame_len <= 512) {
+    if (nfft == kLongNfft && p.frame_len <= 512) {
         // Frames that fit 512 samples (30 ms at 16 kHz = 480): decimation in FREQUENCY.  X[3q + r] = FFT512(x[n] W1536^{n r})[q],
         // and for real x the bins 3q + 2 mirror the bins 3q' + 1 (X[1536 - k] = conj X[k], k = 3q'+1 -> 3(511 - q') + 2), so
         // two transforms in natural order give every power bin straight from the registers: r = 0 -> bins 3q (q <= 256),
@@ -177,7 +180,7 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
             }
         }
     } else {
-    const int R = p.nsub, D = p.bin_stride, half = p.nfft >> 1;
+    const int R = NFFT ? (NFFT >= 512 ? NFFT / 512 : 1) : p.nsub, D = NFFT ? (NFFT >= 512 ? 1 : 512 / NFFT) : p.bin_stride, half = nfft >> 1;
 #pragma unroll 1
     for (int r = 0; r < R; ++r) {
         // sub-sequence r: element m = 32 t + lane is sample n = R m + r of the frame
@@ -202,7 +205,7 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
                 cpx2 v = x[t];
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r > 0) {
-                    int i = r * k; if (i >= p.nfft) i -= p.nfft;     // r k < 2 nfft for R <= 4
+                    int i = r * k; if (i >= nfft) i -= nfft;     // r k < 2 nfft for R <= 4
                     const float2 w = ldg(w1536 + i); v = cmuls(x[t], w.x, w.y); a = acc[k];
                 }
                 acc[k] = make_float4(a.x + v.re.x, a.y + v.re.y, a.z + v.im.x, a.w + v.im.y);
@@ -226,7 +229,7 @@ DEVFN void mfcc_long_pair(const MfccLongParams& p, int64_t g0, int64_t total, un
     for (int m = 16; m >= 1; m >>= 1) { esum.x += simt::shfl32_xor(esum.x, m); esum.y += simt::shfl32_xor(esum.y, m); }
     simt::warp_sync();
     if (p.mode == 2) {   // spectrum tap (sigproc.py:136-175): rows straight to global memory
-        const float nf = (float)p.nfft;
+        const float nf = (float)nfft;
         for (int k = lane; k < nbins; k += 32) {
             float2 v = pw2[k];
             if (p.spec_kind == 1) { v.x = sqrtf(v.x * nf); v.y = sqrtf(v.y * nf); }
