@@ -471,6 +471,10 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
         }
         return acc * dscale;
     };
+    // (Round 2 experiment, reverted: the delta-delta rows to shared memory as well and the tile's contiguous [nf, 3*numcep] block
+    // written with 16-byte vector stores -- every vector element located by a divide-by-width -- measured 4 % slower on the
+    // whole kernel (0.603 against 0.582 ms per 4096 x 2 s): the kernel is bound by the shared-memory pipe, not by its stores,
+    // and the extra pass adds wavefronts.  The 13-lane row stores below fill whole 32-byte sectors in L2 all the same.)
     const int rstep = kMfccGroups * numcep, ostep = kMfccGroups * width;
     if (lane < numcep) {
         int uu = u_lo + grp;
