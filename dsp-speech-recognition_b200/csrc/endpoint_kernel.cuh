@@ -263,6 +263,10 @@ __device__ inline int find_owner(const int64_t* off, int n, int64_t g) {
 // (the first version spent one warp and a five-step shuffle reduction on every hop).  Utterance starts are only
 // 2-byte aligned: the aligned middle of the hop goes through uint4 loads, the few samples either side through
 // scalar loads.  Samples past the end of the utterance are zeros (sigproc.py:84-87).
+// (Round 2 experiments, both reverted: four lanes per hop 0.149 ms and a PAIR of lanes per hop 0.137 ms against 0.111 ms for the lane
+// per hop below, all bit-exact.  Sharing a hop between lanes halves / quarters the 128-byte lines a load instruction touches, but
+// every extra lane repeats the owner search and the hop geometry -- about 150 instructions against 900 for the hop's samples -- and
+// the kernel is bound by instruction issue (45 per 16-byte vector: unpack, |x|, the products' sign bits), not by the line rate.)
 struct HopAcc {
     int A, Z, A2, Z2;   // sum |x|, sign changes between neighbours inside the hop; the same over the first `rem` samples
     int prev; int i;    // previous sample, index of the next sample inside the hop
