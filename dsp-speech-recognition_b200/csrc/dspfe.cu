@@ -26,10 +26,10 @@ __global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __gri
 }
 
 // K1T: nfft = 1536 for frames of at most 512 samples (model.py:74 at 16 kHz) on K1's tile structure
-template <bool HAS_WIN, int NFULL, bool F32IN>
-__global__ void __launch_bounds__(kMfccThreads, 2) mfcc_tri_kernel(const __grid_constant__ MfccParams p) {
+template <bool HAS_WIN, int NFULL, bool F32IN, bool LONG = false>
+__global__ void __launch_bounds__(kMfccThreads, LONG ? 1 : 2) mfcc_tri_kernel(const __grid_constant__ MfccParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    mfcc_cta<HAS_WIN, NFULL, F32IN, 0, true>(p, smem);
+    mfcc_cta<HAS_WIN, NFULL, F32IN, 0, true, LONG>(p, smem);
 }
 
 // K1L: long frames under nfft = 1536, a frame pair per warp; then delta / delta-delta over the cepstra
@@ -96,6 +96,10 @@ mfcc_kernel_t pick_kernel(bool has_win, int frame_len, bool f32, int mode = 0) {
 }
 
 mfcc_kernel_t pick_tri_kernel(bool has_win, int frame_len, bool f32) {
+    if (frame_len > 512) {   // K1T LONG: 30 ms frames at 22.05 / 44.1 / 48 kHz
+        if (f32) return has_win ? mfcc_tri_kernel<true, -1, true, true> : mfcc_tri_kernel<false, -1, true, true>;
+        return has_win ? mfcc_tri_kernel<true, -1, false, true> : mfcc_tri_kernel<false, -1, false, true>;
+    }
     if (f32) return has_win ? mfcc_tri_kernel<true, -1, true> : mfcc_tri_kernel<false, -1, true>;
     if (has_win) return (frame_len >> 5) == 15 ? mfcc_tri_kernel<true, 15, false> : mfcc_tri_kernel<true, -1, false>;
     return mfcc_tri_kernel<false, -1, false>;
@@ -271,7 +275,7 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     std::memset(&pl->layout, 0, sizeof(pl->layout));
     std::string err;
     // K1 takes nfft = 512 with an even hop (its sample planes); every other size / hop goes to the general kernel K1L
-    const bool tiled = (pl->cfg.nfft == kNfft || (pl->cfg.nfft == kTriNfft && pl->cfg.frame_len <= 512)) && !(pl->cfg.frame_step & 1) && pl->cfg.frame_step >= 2;
+    const bool tiled = (pl->cfg.nfft == kNfft && !(pl->cfg.frame_step & 1) && pl->cfg.frame_step >= 2) || pl->cfg.nfft == kTriNfft;
     if (!tiled || pl->cfg.nfft != kNfft) {   // (a K1T plan keeps the general kernel for its filterbank / spectrum taps)
         err = mfcc_long_config_check(pl->cfg);
         if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }

@@ -74,7 +74,9 @@ DEVFN ChunkGeom chunk_geom(const MfccParams& p, int sh, int lim, int S, int fram
 // transforms per frame pair.  The real split pairs Z[k] with Z[768 - k]: class 0 (k = 3q) with itself -- K1's split verbatim,
 // W1536^{3q} = W512^q -- and class 2 (k = 3q + 2) with class 1 (768 - k = 3 (255 - q) + 1), which waits in shared memory.
 // Power bins stay in three arrays indexed by q (class c = bins 3q + c); the mel pieces are built per class (mfcc_tables.h).
-template <bool HAS_WIN, int NFULL, bool F32IN, int MODE, bool TRI = false>
+// LONG (K1T only): frames of 513 .. 1536 samples (30 ms at 44.1 / 48 kHz: 1323 / 1440) -- all three thirds of z are populated and
+// the transform of class r starts from u_r[m] = (z[m] + w^r z[m+256] + w^2r z[m+512]) W768^{m r}, w = exp(-2 pi i / 3).
+template <bool HAS_WIN, int NFULL, bool F32IN, int MODE, bool TRI = false, bool LONG = false>
 DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     const int tid = simt::tid();
     const int lane = tid & 15;
@@ -230,6 +232,47 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                     x[n1].im = make_float2(ai, bi);
                 }
             };
+            // K1T LONG: the radix-3 input butterfly of class r over the three thirds of z (window planes of 768 entries)
+            auto load_pair_long = [&](cpx2 (&x)[16], int r) {
+                const int fb0 = fb_base + fl * p.frame_step;
+                const float* plane_e = sm.fbuf;
+                const float* plane_o = sm.fbuf + 4 * p.fbuf_vecs;
+                const bool odd = (fb0 & 1) != 0;
+                const float* fre = (odd ? plane_o : plane_e) + (fb0 >> 1) + lane;
+                const float* fim = (odd ? plane_e + 1 : plane_o) + (fb0 >> 1) + lane;
+                const int dB = p.frame_step;
+                const float hs = r == 1 ? 0.8660254037844386f : -0.8660254037844386f;     // -i sqrt(3)/2 (z1 - z2) for r = 1, + for r = 2
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    cpx2 z[3];
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const int m0 = 256 * t + 16 * n1;                  // z index of lane 0
+                        float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+                        if (2 * m0 + 31 < p.frame_len) {
+                            ar = fre[m0]; ai = fim[m0]; br = fre[m0 + dB]; bi = fim[m0 + dB];
+                        } else {
+                            const int i0 = 2 * (m0 + lane);
+                            if (i0 < p.frame_len) { ar = fre[m0]; br = fre[m0 + dB]; }
+                            if (i0 + 1 < p.frame_len) { ai = fim[m0]; bi = fim[m0 + dB]; }
+                        }
+                        if (HAS_WIN) {
+                            const float w0 = win[m0 + lane], w1 = win[768 + m0 + lane];
+                            ar *= w0; br *= w0; ai *= w1; bi *= w1;
+                        }
+                        z[t].re = make_float2(ar, br); z[t].im = make_float2(ai, bi);
+                    }
+                    if (r == 0) {
+                        x[n1] = cadd(z[0], cadd(z[1], z[2]));
+                    } else {
+                        const cpx2 sm2 = cadd(z[1], z[2]), d = csub(z[1], z[2]);
+                        cpx2 o;
+                        o.re = f2fmas(d.im, hs, f2fmas(sm2.re, -0.5f, z[0].re));      // z0 - s/2 + hs * (-i d): (-i d) = (d.im, -d.re)
+                        o.im = f2fmas(d.re, -hs, f2fmas(sm2.im, -0.5f, z[0].im));
+                        x[n1] = o;
+                    }
+                }
+            };
             // 256-point complex transform of the pair: lane = n2 in, lane = k1 out, register k2 holds Z[k1 + 16*k2]
             auto fft256 = [&](cpx2 (&x)[16]) {
                 // stage 1: DFT over n1 (registers); lane = n2
@@ -253,7 +296,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 // stage 2: DFT over n2; lane = k1, register k2 holds Z[k1 + 16*k2]
                 dft16(x);
             };
-            load_pair(x);
+            if constexpr (LONG) load_pair_long(x, 0); else load_pair(x);
             fft256(x);
 
             // ---- real-FFT split, pairwise: bins k = lane + 16 r (r < 8) and 256 - k share one butterfly.
@@ -342,14 +385,14 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 const float2* tws2 = reinterpret_cast<const float2*>(sm.tables + p.o_tws2) + lane;
                 simt::group_sync();          // the class-0 bins have been consumed: the tile is free again
                 // class 1: Z[3q + 1] = FFT256(z[m] W768^m)[q], parked
-                load_pair(x);
+                if constexpr (LONG) load_pair_long(x, 1); else load_pair(x);
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) { const float2 w = tw3[16 * n1]; x[n1] = cmuls(x[n1], w.x, w.y); }
                 fft256(x);
 #pragma unroll
                 for (int k2 = 0; k2 < 16; ++k2) zb[lane + 16 * k2] = make_float4(x[k2].re.x, x[k2].re.y, x[k2].im.x, x[k2].im.y);
                 // class 2: Z[3q + 2] = FFT256(z[m] W768^{2m})[q] in registers; Z[3q' + 2] pairs with Z[768 - (3q' + 2)] = Z_1[255 - q']
-                load_pair(x);
+                if constexpr (LONG) load_pair_long(x, 2); else load_pair(x);
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) { const float2 w = tw3[256 + 16 * n1]; x[n1] = cmuls(x[n1], w.x, w.y); }
                 fft256(x);

@@ -69,9 +69,9 @@ inline std::string mfcc_long_config_check(const MfccConfig& c) {
 
 inline std::string mfcc_config_check(const MfccConfig& c) {
     if (c.nfft != kNfft && c.nfft != kTriNfft) return "the tiled kernel is built for nfft 512 and 1536 (other sizes: the general kernel)";
-    if (c.nfft == kTriNfft && c.frame_len > 512) return "the tiled nfft-1536 kernel takes frames of at most 512 samples (longer frames: the general kernel)";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
-    if (c.frame_step < 2 || (c.frame_step & 1)) return "frame_step must be even and >= 2";
+    if (c.nfft == kNfft && (c.frame_step < 2 || (c.frame_step & 1))) return "frame_step must be even and >= 2 (odd hops: the general kernel)";
+    if (c.frame_step < 1) return "frame_step must be >= 1";
     if (c.frame_step > (c.count_len > 0 ? c.count_len : c.frame_len)) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
     if (c.nfilt < 1 || c.nfilt > kMaxNfilt) return "nfilt must be in [1, 40]";
     if (c.numcep < 1 || c.numcep > kMaxNumcep || c.numcep > c.nfilt) return "numcep must be in [1, min(16, nfilt)]";
@@ -293,8 +293,9 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     align4();
     p.o_win = (int)blob.size();
     if (!c.window.empty()) {   // two zero-padded planes: even-index and odd-index window samples
+        const int plane = c.frame_len > 512 ? 768 : 256;          // (K1T LONG: all three thirds)
         for (int q = 0; q < 2; ++q)
-            for (int n = 0; n < 256; ++n) { const int i = 2 * n + q; blob.push_back(i < c.frame_len ? (float)c.window[i] : 0.f); }
+            for (int n = 0; n < plane; ++n) { const int i = 2 * n + q; blob.push_back(i < c.frame_len ? (float)c.window[i] : 0.f); }
     }
     align4();
     p.tbl_floats = (int)blob.size();

@@ -17,6 +17,11 @@ struct Args { MfccParams p; bool has_win; bool f32; std::vector<unsigned char>* 
 void body(void* a) {
     Args* A = (Args*)a;
     const int nfull = A->p.frame_len >> 5;
+    if (A->p.tri && A->p.frame_len > 512) {   // K1T LONG
+        if (A->f32) { if (A->has_win) mfcc_cta<true, -1, true, 0, true, true>(A->p, A->smem->data()); else mfcc_cta<false, -1, true, 0, true, true>(A->p, A->smem->data()); return; }
+        if (A->has_win) mfcc_cta<true, -1, false, 0, true, true>(A->p, A->smem->data()); else mfcc_cta<false, -1, false, 0, true, true>(A->p, A->smem->data());
+        return;
+    }
     if (A->p.tri) {   // K1T (nfft = 1536, frames of at most 512 samples)
         if (A->f32) { if (A->has_win) mfcc_cta<true, -1, true, 0, true>(A->p, A->smem->data()); else mfcc_cta<false, -1, true, 0, true>(A->p, A->smem->data()); return; }
         if (A->has_win) { if (nfull == 15) mfcc_cta<true, 15, false, 0, true>(A->p, A->smem->data()); else mfcc_cta<true, -1, false, 0, true>(A->p, A->smem->data()); }

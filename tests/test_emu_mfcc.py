@@ -77,7 +77,7 @@ def test_float32_input_path():
 
 def test_unsupported_configs_are_rejected():
     x = np.zeros(1000, dtype=np.int16)
-    for kw in (dict(nfft=1024), dict(nfft=1536, frame_len=600), dict(frame_len=600), dict(frame_step=161), dict(nfilt=41), dict(numcep=17),
+    for kw in (dict(nfft=1024), dict(nfft=1536, frame_len=1600), dict(frame_len=600), dict(frame_step=161), dict(nfilt=41), dict(numcep=17),
                dict(delta_n=0), dict(highfreq=9000.0)):
         with pytest.raises(RuntimeError):
             emu.mfcc_delta(x, [0, 1000], **kw)
@@ -135,6 +135,29 @@ def test_tiled_nfft1536_kernel():
     for u in range(6):
         xs = pcm[off[u]:off[u + 1]][trim[u, 0]:trim[u, 1]]
         assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(xs, 2, preemph=0, winfunc=np.hamming), what=f"trim utt {u}")
+
+
+def test_tiled_nfft1536_kernel_long_frames():
+    """K1T LONG: 30 ms Hamming frames at 44.1 kHz (1323 samples, odd hop 441), 48 kHz (1440 / 480) and 22.05 kHz (662 / 221: two
+    thirds populated) under nfft 1536 on the tile kernel, int16 and scaled float input, delta N = 2 / 3."""
+    def ref39(x, rate, N, **kw):
+        m = O.mfcc(x, rate, winlen=0.03, winstep=0.01, nfft=1536, winfunc=np.hamming, **kw)
+        d1 = O.delta(m, N)
+        return np.concatenate([m, d1, O.delta(d1, N)], axis=1)
+    for rate, flen, step, lengths in ((44100, 1323, 441, [20000, 1322, 1324, 5000]), (48000, 1440, 480, [30000, 1440, 100]),
+                                      (22050, 662, 221, [9000, 663])):
+        pcm, off = synth.synth_batch(lengths, seed0=rate, sr=rate)
+        out, fo = emu.mfcc_delta(pcm, off, nfft=1536, frame_len=flen, frame_step=step, window=np.hamming(flen), samplerate=rate, delta_n=3, seg_frames=32)
+        for u in range(len(lengths)):
+            assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(pcm[off[u]:off[u + 1]], rate, 3), what=f"{rate} utt {u}")
+    x = synth.synth_utterance(301, 20000, sr=44100)
+    xf = (x / np.std(x)).astype(np.float32)          # model.py:62-63 feeds scaled float audio
+    out, fo = emu.mfcc_delta(xf, [0, len(xf)], nfft=1536, frame_len=1323, frame_step=441, window=np.hamming(1323), samplerate=44100, preemph=0.0)
+    assert_mfcc_close(out, ref39(xf.astype(np.float64), 44100, 2, preemph=0), what="44.1k float")
+    out, fo = emu.mfcc_delta(x, [0, len(x)], nfft=1536, frame_len=1536, frame_step=512)            # rectangular window, full-length frames
+    m = O.mfcc(x, 16000, winlen=0.096, winstep=0.032, nfft=1536)
+    d1 = O.delta(m, 2)
+    assert_mfcc_close(out, np.concatenate([m, d1, O.delta(d1, 2)], axis=1), what="1536-sample frames")
 
 
 def test_general_kernel_other_transform_sizes():
