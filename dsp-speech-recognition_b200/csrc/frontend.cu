@@ -230,7 +230,7 @@ int dspfe_frontend_create(const dspfe_frontend_params* q, dspfe_frontend_plan** 
 int dspfe_frontend_bounds(const dspfe_frontend_plan* pl, int64_t total_samples, int64_t n_utt, int64_t* caps) {
     if (!pl || !caps || total_samples < 0 || n_utt < 0) return fail(DSPFE_ERR_INVALID_ARG, "bad argument");
     // a slab starts at the 16-byte aligned sample at or before its first utterance: up to 7 extra samples per slab
-    const int64_t slabs = total_samples / std::min(pl->prm.slab_samples, pl->prm.host_slab_samples) + 4;   // (+ the host path's two short ramp-up slabs)
+    const int64_t slabs = total_samples / std::min(pl->prm.slab_samples, pl->prm.host_slab_samples) + 8;   // (+ the host path's short ramp-up / ramp-down slabs)
     const int64_t padded = total_samples + 8 * slabs;
     const FeLane& l0 = pl->lanes[0];
     caps[0] = dspfe_rows_bound(l0.mf, padded, n_utt);
@@ -303,10 +303,13 @@ int dspfe_frontend_host(dspfe_frontend_plan* pl, const int16_t* h_pcm, const int
         if (!s.d2h_done) CUDA_TRY(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
     }
     // the slabs
-    std::vector<int32_t> cut{0};                         // short slabs first: the kernels start after a quarter-slab's copy
-    while (cut.back() < n_utt) {
+    std::vector<int32_t> cut{0};                         // short slabs first: the kernels start after a quarter-slab's copy;
+    while (cut.back() < n_utt) {                         // short slabs last: nothing overlaps the last slab's kernels and its copy back
         const size_t k = cut.size();
-        cut.push_back(slab_end(h_off, cut.back(), n_utt, k == 1 ? pl->prm.host_slab_samples / 4 : (k == 2 ? pl->prm.host_slab_samples / 2 : pl->prm.host_slab_samples)));
+        const int64_t S = pl->prm.host_slab_samples, rem = h_off[n_utt] - h_off[cut.back()];
+        int64_t cap = k == 1 ? S / 4 : (k == 2 ? S / 2 : S);
+        if (rem > S / 4) cap = std::min(cap, std::max(S / 4, rem / 2));
+        cut.push_back(slab_end(h_off, cut.back(), n_utt, cap));
     }
     const int n_slab = (int)cut.size() - 1;
     const int64_t base0 = h_off[0] & ~(int64_t)7;     // h_pcm is addressed from this sample on (its predecessors are never read)
