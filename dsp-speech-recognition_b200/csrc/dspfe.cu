@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kMfccThreads, 4) mfcc_delta_kernel(const __gri
 
 // K1T: nfft = 1536 for frames of at most 512 samples (model.py:74 at 16 kHz) on K1's tile structure
 template <bool HAS_WIN, int NFULL, bool F32IN, bool LONG = false>
-__global__ void __launch_bounds__(kMfccThreads, LONG ? 1 : 2) mfcc_tri_kernel(const __grid_constant__ MfccParams p) {
+__global__ void __launch_bounds__(kMfccThreads, LONG ? 2 : 3) mfcc_tri_kernel(const __grid_constant__ MfccParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     mfcc_cta<HAS_WIN, NFULL, F32IN, 0, true, LONG>(p, smem);
 }

@@ -14,7 +14,6 @@ constexpr int kMelSlots = 3;          // mel filter pieces per lane (one per slo
 constexpr int kMelMaxPieces = 4;      // pieces a single mel filter may be cut into
 constexpr int kScratchUnits = 272;    // 8-byte units per group: 16x17 transpose tile, >= 257 power bins
 constexpr int kTriNfft = 1536;        // K1T: the transform size of model.py:74
-constexpr int kTriUnits = kScratchUnits + 512;   // K1T: transpose tile | 256 float4 of the class-1 transform (later 256 class-1 power bins)
 constexpr int kMfccThreads = 128;     // 8 groups -> 16 frames per pass of the chunk loop
 constexpr int kMfccGroups = kMfccThreads / kGroupLanes;
 constexpr int kFramesPerPass = 2 * kMfccGroups;
@@ -45,10 +44,10 @@ struct MfccParams {
     int fbuf_vecs;              // 8-sample vectors converted per chunk (covers the raw staging area)
     // K1T (nfft = 1536 as three 256-point complex transforms, mfcc_kernel.cuh TRI): bins 3q + c form class c
     int tri;                    // 0: K1 (nfft 512), 1: K1T
-    int grp_units;              // 8-byte scratch units per 16-lane group: kScratchUnits (K1) or kTriUnits (K1T)
-    int o_tw3, o_tws2;          // W768^{m r} at [(r-1)*256 + m], r = 1, 2; W1536^{3q + 2} at [q]
-    int o_melw_c[3], o_melb_c[3];   // per-class piece tables (class 0 = o_melw / o_melb)
-    int mel_Tc[3][kMelSlots];
+    int grp_units;              // 8-byte scratch units per 16-lane group (kScratchUnits)
+    int o_tw3, o_tws2;          // [m] float4 (cos a1, cos a2, sin a1, sin a2) of W768^m, W768^2m; W1536^{3q + 2} at [q]
+    int o_melw_c[2], o_melb_c[2];   // piece tables: class 0 (= o_melw / o_melb), the joint classes 1 + 2
+    int mel_Tc[2][kMelSlots];
 };
 
 struct PrepParams {

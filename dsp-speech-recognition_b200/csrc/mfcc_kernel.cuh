@@ -68,12 +68,17 @@ DEVFN ChunkGeom chunk_geom(const MfccParams& p, int sh, int lim, int S, int fram
 // F32IN: the packed batch holds float32 samples instead of int16 (e.g. a signal the caller already scaled).
 // MODE: 0 = MFCC + delta + delta-delta rows [F, 3*numcep]; 1 = filterbank energies + frame energy [F, nfilt+1]
 // (reference fbank, base.py:18); 2 = spectrum [F, 257]: power (sigproc.py:151), magnitude (:136) or 10*log10 power (:161).
-// TRI: K1T -- nfft = 1536 for frames of at most 512 samples (model.py:74 at 16 kHz), same tile / chunk / epilogue structure.
-// The 1536-point real transform is a 768-point complex one on z[m] = x[2m] + i x[2m+1]; only z[0..255] is non-zero, so the
-// decimation in frequency by three needs no butterflies: Z[3q + r] = FFT256(z[m] W768^{m r})[q], three of K1's register
-// transforms per frame pair.  The real split pairs Z[k] with Z[768 - k]: class 0 (k = 3q) with itself -- K1's split verbatim,
-// W1536^{3q} = W512^q -- and class 2 (k = 3q + 2) with class 1 (768 - k = 3 (255 - q) + 1), which waits in shared memory.
-// Power bins stay in three arrays indexed by q (class c = bins 3q + c); the mel pieces are built per class (mfcc_tables.h).
+// TRI: K1T -- nfft = 1536 (model.py:74), same tile / chunk / epilogue structure.
+// The 1536-point real transform is a 768-point complex one on z[m] = x[2m] + i x[2m+1]; for frames of at most 512 samples only
+// z[0..255] is non-zero, so the decimation in frequency by three needs no butterflies: Z[3q + r] = FFT256(z[m] W768^{m r})[q],
+// K1's register transform.  The real split pairs Z[k] with Z[768 - k]: class 0 (k = 3q) with itself -- K1's split verbatim,
+// W1536^{3q} = W512^q, both frames of the pair in the packed halves -- and class 2 (k = 3q + 2) with class 1
+// (768 - k = 3 (255 - q) + 1).  For those the packed halves carry the two CLASSES of one frame instead of two frames: the
+// transform of (z W768^m, z W768^2m) leaves Z_1 in the .x and Z_2 in the .y halves, the partner Z_1[255 - q] of Z_2[q] sits in
+// the mirrored lane and register (as in the class-0 split), and nothing is parked in shared memory (the first version parked
+// Z_1 of the pair: 4 KB per group, 2 CTAs/SM).  Three packed transforms per frame pair either way.
+// Power bins stay in arrays indexed by q: class 0 as (frame A, frame B), classes 1 / 2 of one frame as (class 1, class 2);
+// the mel pieces are built per class (mfcc_tables.h).
 // LONG (K1T only): frames of 513 .. 1536 samples (30 ms at 44.1 / 48 kHz: 1323 / 1440) -- all three thirds of z are populated and
 // the transform of class r starts from u_r[m] = (z[m] + w^r z[m+256] + w^2r z[m+512]) W768^{m r}, w = exp(-2 pi i / 3).
 template <bool HAS_WIN, int NFULL, bool F32IN, int MODE, bool TRI = false, bool LONG = false>
@@ -114,7 +119,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
     const int4* melc = reinterpret_cast<const int4*>(sm.tables + p.o_melc);  // [filter] -> the partial sums that make it up
     const float* dct = sm.tables + p.o_dct;
     const float* win = sm.tables + p.o_win;
-    float2* scr = sm.scratch + grp * (TRI ? kTriUnits : kScratchUnits);
+    float2* scr = sm.scratch + grp * kScratchUnits;
 
     // everything below addresses the packed buffer relative to the utterance's aligned-down start
     const int esz = F32IN ? 4 : 2;
@@ -232,8 +237,8 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                     x[n1].im = make_float2(ai, bi);
                 }
             };
-            // K1T LONG: the radix-3 input butterfly of class r over the three thirds of z (window planes of 768 entries)
-            auto load_pair_long = [&](cpx2 (&x)[16], int r) {
+            // K1T LONG, class 0: z[m] + z[m+256] + z[m+512] of the pair (window planes of 768 entries)
+            auto load_pair_long = [&](cpx2 (&x)[16]) {
                 const int fb0 = fb_base + fl * p.frame_step;
                 const float* plane_e = sm.fbuf;
                 const float* plane_o = sm.fbuf + 4 * p.fbuf_vecs;
@@ -241,10 +246,9 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 const float* fre = (odd ? plane_o : plane_e) + (fb0 >> 1) + lane;
                 const float* fim = (odd ? plane_e + 1 : plane_o) + (fb0 >> 1) + lane;
                 const int dB = p.frame_step;
-                const float hs = r == 1 ? 0.8660254037844386f : -0.8660254037844386f;     // -i sqrt(3)/2 (z1 - z2) for r = 1, + for r = 2
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) {
-                    cpx2 z[3];
+                    cpx2 acc; acc.re = make_float2(0.f, 0.f); acc.im = acc.re;
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         const int m0 = 256 * t + 16 * n1;                  // z index of lane 0
@@ -260,17 +264,53 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                             const float w0 = win[m0 + lane], w1 = win[768 + m0 + lane];
                             ar *= w0; br *= w0; ai *= w1; bi *= w1;
                         }
-                        z[t].re = make_float2(ar, br); z[t].im = make_float2(ai, bi);
+                        acc.re = f2add(acc.re, make_float2(ar, br)); acc.im = f2add(acc.im, make_float2(ai, bi));
                     }
-                    if (r == 0) {
-                        x[n1] = cadd(z[0], cadd(z[1], z[2]));
+                    x[n1] = acc;
+                }
+            };
+            // K1T, classes 1 and 2 of ONE frame (f = 0: frame A, 1: frame B) in the packed halves: x[n1] = (u_1[m], u_2[m]),
+            // u_r[m] = (z[m] + w^r z[m+256] + w^2r z[m+512]) W768^{m r}, w = exp(-2 pi i / 3); a short frame has z[m] only
+            auto load_classes = [&](cpx2 (&x)[16], int f) {
+                const int fb0 = fb_base + (fl + 2 * f) * p.frame_step;
+                const float* plane_e = sm.fbuf;
+                const float* plane_o = sm.fbuf + 4 * p.fbuf_vecs;
+                const bool odd = (fb0 & 1) != 0;
+                const float* fre = (odd ? plane_o : plane_e) + (fb0 >> 1) + lane;
+                const float* fim = (odd ? plane_e + 1 : plane_o) + (fb0 >> 1) + lane;
+                const float4* tw12 = reinterpret_cast<const float4*>(sm.tables + p.o_tw3) + lane;
+                constexpr int WP = LONG ? 768 : 256;
+                const float hs = 0.8660254037844386f;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    float zr[3] = {0.f, 0.f, 0.f}, zi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int t = 0; t < (LONG ? 3 : 1); ++t) {
+                        const int m0 = 256 * t + 16 * n1;
+                        float ar = 0.f, ai = 0.f;
+                        if (LONG ? (2 * m0 + 31 < p.frame_len) : (n1 < nfull)) {
+                            ar = fre[m0]; ai = fim[m0];
+                        } else if (LONG || n1 == nfull) {
+                            const int i0 = 2 * (m0 + lane);
+                            if (i0 < p.frame_len) ar = fre[m0];
+                            if (i0 + 1 < p.frame_len) ai = fim[m0];
+                        }
+                        if (HAS_WIN) { ar *= win[m0 + lane]; ai *= win[WP + m0 + lane]; }
+                        zr[t] = ar; zi[t] = ai;
+                    }
+                    float2 ure, uim;     // (class 1, class 2) before the twiddle
+                    if (LONG) {
+                        // z0 + w z1 + w^2 z2 = z0 - s/2 - i (sqrt 3 / 2) d and z0 + w^2 z1 + w z2 = z0 - s/2 + i (sqrt 3 / 2) d, s = z1 + z2, d = z1 - z2
+                        const float br = zr[0] - 0.5f * (zr[1] + zr[2]), bi = zi[0] - 0.5f * (zi[1] + zi[2]);
+                        const float er = hs * (zi[1] - zi[2]), ei = -hs * (zr[1] - zr[2]);       // -i (sqrt 3 / 2) d
+                        ure = make_float2(br + er, br - er); uim = make_float2(bi + ei, bi - ei);
                     } else {
-                        const cpx2 sm2 = cadd(z[1], z[2]), d = csub(z[1], z[2]);
-                        cpx2 o;
-                        o.re = f2fmas(d.im, hs, f2fmas(sm2.re, -0.5f, z[0].re));      // z0 - s/2 + hs * (-i d): (-i d) = (d.im, -d.re)
-                        o.im = f2fmas(d.re, -hs, f2fmas(sm2.im, -0.5f, z[0].im));
-                        x[n1] = o;
+                        ure = make_float2(zr[0], zr[0]); uim = make_float2(zi[0], zi[0]);
                     }
+                    const float4 tw = tw12[16 * n1];
+                    const float2 C = make_float2(tw.x, tw.y), S = make_float2(tw.z, tw.w);
+                    x[n1].re = f2fma(uim, f2neg(S), f2mul(ure, C));
+                    x[n1].im = f2fma(uim, C, f2mul(ure, S));
                 }
             };
             // 256-point complex transform of the pair: lane = n2 in, lane = k1 out, register k2 holds Z[k1 + 16*k2]
@@ -296,7 +336,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                 // stage 2: DFT over n2; lane = k1, register k2 holds Z[k1 + 16*k2]
                 dft16(x);
             };
-            if constexpr (LONG) load_pair_long(x, 0); else load_pair(x);
+            if constexpr (LONG) load_pair_long(x); else load_pair(x);
             fft256(x);
 
             // ---- real-FFT split, pairwise: bins k = lane + 16 r (r < 8) and 256 - k share one butterfly.
@@ -355,7 +395,7 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
 
             // ---- mel filterbank (reference base.py:28-29): every lane accumulates one piece of a filter per slot; the
             // trip counts are uniform over the lanes and the weights come from a [iteration][lane] table (mfcc_tables.h)
-            constexpr int NCLS = TRI ? 3 : 1;
+            constexpr int NCLS = TRI ? 2 : 1;
             float2 macc[NCLS][kMelSlots];
             auto mel_round = [&](int cls, const float2* P, float2 (&acc)[kMelSlots]) {
                 const float2* melw = reinterpret_cast<const float2*>(sm.tables + p.o_melw_c[cls]) + lane;   // [iteration pair][lane] filter weights
@@ -379,54 +419,57 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
             };
             mel_round(0, scr, macc[0]);
             if constexpr (TRI) {
-                float4* zb = reinterpret_cast<float4*>(scr + kScratchUnits);   // [256] Z_1 of the pair: (re.x, re.y, im.x, im.y)
-                float2* p1 = scr + kScratchUnits + 256;                        // [256] class-1 power bins, in zb's upper half once it is consumed
-                const float2* tw3 = reinterpret_cast<const float2*>(sm.tables + p.o_tw3) + lane;
                 const float2* tws2 = reinterpret_cast<const float2*>(sm.tables + p.o_tws2) + lane;
-                simt::group_sync();          // the class-0 bins have been consumed: the tile is free again
-                // class 1: Z[3q + 1] = FFT256(z[m] W768^m)[q], parked
-                if constexpr (LONG) load_pair_long(x, 1); else load_pair(x);
+                const float2* melw12 = reinterpret_cast<const float2*>(sm.tables + p.o_melw_c[1]) + lane;   // [iteration][lane] (class-1, class-2) weights
+                const int* melb12 = reinterpret_cast<const int*>(sm.tables + p.o_melb_c[1]) + lane;
+                float* qf = reinterpret_cast<float*>(scr);       // Q[q] = (class-1 bin 3q + 1, class-2 bin 3q + 2) of the frame
+                const int mir = 15 - lane;
 #pragma unroll
-                for (int n1 = 0; n1 < 16; ++n1) { const float2 w = tw3[16 * n1]; x[n1] = cmuls(x[n1], w.x, w.y); }
-                fft256(x);
+                for (int f = 0; f < 2; ++f) {
+                    simt::group_sync();          // the bins in the tile have been consumed: it is free again
+                    load_classes(x, f);
+                    fft256(x);                   // .x halves: Z_1[q], .y halves: Z_2[q], q = lane + 16 k2
+                    float es = 0.f;
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) zb[lane + 16 * k2] = make_float4(x[k2].re.x, x[k2].re.y, x[k2].im.x, x[k2].im.y);
-                // class 2: Z[3q + 2] = FFT256(z[m] W768^{2m})[q] in registers; Z[3q' + 2] pairs with Z[768 - (3q' + 2)] = Z_1[255 - q']
-                if constexpr (LONG) load_pair_long(x, 2); else load_pair(x);
-#pragma unroll
-                for (int n1 = 0; n1 < 16; ++n1) { const float2 w = tw3[256 + 16 * n1]; x[n1] = cmuls(x[n1], w.x, w.y); }
-                fft256(x);
-                // four butterflies at a time: the partners are read before the batch's class-1 results overwrite the upper
-                // half of zb (entries the later batches still read lie below everything written so far)
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float4 zq[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) zq[t] = zb[255 - (lane + 16 * (4 * g + t))];
-                    simt::group_sync();
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int k2 = 4 * g + t, q = lane + 16 * k2;
-                        const cpx2 a = x[k2];
-                        cpx2 b; b.re = make_float2(zq[t].x, zq[t].y); b.im = make_float2(zq[t].z, zq[t].w);
-                        const float2 sre = f2add(a.re, b.re), sim = f2sub(a.im, b.im);
-                        const float2 dre = f2sub(a.re, b.re), dim = f2add(a.im, b.im);
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        // Z[3q + 2] = Z_2[q] pairs with Z[768 - (3q + 2)] = Z_1[255 - q]: lane 15 - lane, register 15 - k2
+                        const int q = lane + 16 * k2;
+                        const float are_ = x[k2].re.y, aim_ = x[k2].im.y;
+                        const float bre_ = simt::shfl16(x[15 - k2].re.x, mir), bim_ = simt::shfl16(x[15 - k2].im.x, mir);
+                        const float sre = are_ + bre_, sim = aim_ - bim_, dre = are_ - bre_, dim = aim_ + bim_;
                         const float2 w = tws2[16 * k2];  // W1536^{3q + 2}
-                        const float2 tre = f2fmas(dim, w.x, f2muls(dre, w.y));
-                        const float2 tim = f2fmas(dim, w.y, f2muls(dre, -w.x));
-                        const float2 are = f2add(sre, tre), aim = f2add(sim, tim);
-                        const float2 bre = f2sub(sre, tre), bim = f2sub(sim, tim);
-                        const float2 pa = f2muls(f2fma(aim, aim, f2mul(are, are)), sc);   // bin 3q + 2
-                        const float2 pb = f2muls(f2fma(bim, bim, f2mul(bre, bre)), sc);   // bin 3 (255 - q) + 1
-                        scr[q] = pa;
-                        p1[255 - q] = pb;
-                        esum = f2add(esum, f2add(pa, pb));
+                        const float tre = dsp_fmaf(dim, w.x, dre * w.y), tim = dsp_fmaf(dim, w.y, -dre * w.x);
+                        const float2 xr = make_float2(sre + tre, sre - tre), xi = make_float2(sim + tim, sim - tim);
+                        const float2 pw = f2muls(f2fma(xi, xi, f2mul(xr, xr)), sc);   // (bin 3q + 2, bin 3 (255 - q) + 1)
+                        qf[2 * q + 1] = pw.x;
+                        qf[2 * (255 - q)] = pw.y;
+                        es += pw.x + pw.y;
+                    }
+                    if (f == 0) esum.x += es; else esum.y += es;
+                    scr[256 + lane] = make_float2(0.f, 0.f);     // 256 bins per class; the pieces may read (with zero weights) past them
+                    simt::group_sync();
+                    int tb = 0;
+                    float2 tot[kMelSlots];
+#pragma unroll
+                    for (int s2 = 0; s2 < kMelSlots; ++s2) {
+                        const int T = p.mel_Tc[1][s2];
+                        const float2* pp = scr + melb12[s2 * kGroupLanes];
+                        const float2* wp = melw12 + tb * kGroupLanes;
+                        float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll 4
+                        for (int t = 0; t < T; t += 2) {   // T is even
+                            a0 = f2fma(pp[t], wp[t * kGroupLanes], a0);
+                            a1 = f2fma(pp[t + 1], wp[(t + 1) * kGroupLanes], a1);
+                        }
+                        tot[s2] = f2add(a0, a1);
+                        tb += T;
+                    }
+#pragma unroll
+                    for (int s2 = 0; s2 < kMelSlots; ++s2) {
+                        const float v = tot[s2].x + tot[s2].y;       // the lane's piece over both classes
+                        if (f == 0) macc[1][s2].x = v; else macc[1][s2].y = v;
                     }
                 }
-                scr[256 + lane] = make_float2(0.f, 0.f);     // class 2 has 256 bins; the pieces may read (with zero weights) past them
-                simt::group_sync();
-                mel_round(1, p1, macc[1]);
-                mel_round(2, scr, macc[2]);
             }
             // total frame energy (reference base.py:25): reduce over the group
 #pragma unroll

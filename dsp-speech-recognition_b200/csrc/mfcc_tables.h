@@ -116,15 +116,15 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     // K1T input twiddles W768^{m r} (decimation in frequency by three) and the split twiddles of the class-2 bins
     const bool tri = c.nfft == kTriNfft;
     p.tri = tri ? 1 : 0;
-    p.grp_units = tri ? kTriUnits : kScratchUnits;
+    p.grp_units = kScratchUnits;
     if (tri) {
         align4();
-        p.o_tw3 = (int)blob.size();
-        for (int r = 1; r <= 2; ++r)
-            for (int m = 0; m < 256; ++m) {
-                const double a = -2.0 * kPi * (double)(m * r) / 768.0;
-                blob.push_back((float)std::cos(a)); blob.push_back((float)std::sin(a));
-            }
+        p.o_tw3 = (int)blob.size();      // [m] (cos a1, cos a2, sin a1, sin a2), a_r = -2 pi m r / 768: the classes 1 and 2 ride in one packed transform
+        for (int m = 0; m < 256; ++m) {
+            const double a1 = -2.0 * kPi * (double)m / 768.0, a2 = -2.0 * kPi * (double)(2 * m) / 768.0;
+            blob.push_back((float)std::cos(a1)); blob.push_back((float)std::cos(a2));
+            blob.push_back((float)std::sin(a1)); blob.push_back((float)std::sin(a2));
+        }
         p.o_tws2 = (int)blob.size();
         for (int q = 0; q < 256; ++q) {
             const double a = -2.0 * kPi * (double)(3 * q + 2) / 1536.0;
@@ -135,9 +135,11 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     // run of bins; the runs are cut into pieces and every (slot, lane) of a 16-lane group owns at most one piece.
     // All lanes run the same mel_T[slot] iterations per slot (zero weights pad short pieces), so the kernel's loop
     // has a uniform trip count, no per-lane branching and reads its weights from a [iteration][lane] table.
-    // K1T keeps the power bins in three arrays, class c = bins 3q + c indexed by q: a filter's weights on one class are again a
-    // contiguous run, so every class gets its own piece table and the partial sums of the three meet in the combine step.
-    const int nbins = c.nfft / 2 + 1, ncls = tri ? 3 : 1;
+    // K1T keeps the power bins by residue class, bins 3q + c indexed by q: class 0 as one array of (frame A, frame B) values, the
+    // classes 1 and 2 of ONE frame as an array of (class 1, class 2) values.  A filter's weights on a class are again a contiguous
+    // run in q, so class 0 gets a piece table like K1's and the classes 1 / 2 a joint one with a weight PAIR per entry; the partial
+    // sums meet in the combine step.
+    const int nbins = c.nfft / 2 + 1, ncls = tri ? 2 : 1, nres = tri ? 3 : 1;
     const std::vector<double> bins = mel_bin_edges(c);
     for (int i = 0; i < c.nfilt + 2; ++i)
         if (bins[i] < 0 || bins[i] > c.nfft / 2) { err = "mel bin edges fall outside [0, nfft/2]"; return {}; }
@@ -147,21 +149,24 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
         for (int k = lo; k < ce; ++k) dense[j][k] = (k - bins[j]) / (bins[j + 1] - bins[j]);
         for (int k = ce; k < hi; ++k) dense[j][k] = (bins[j + 2] - k) / (bins[j + 2] - bins[j + 1]);
     }
-    struct Run { int k0; std::vector<float> w; };
+    struct Run { int k0; std::vector<float> w, w2; };
     struct Piece { int filt, off, len, slot, lane, k0; };
     const int zero_part = ncls * kMelSlots * kGroupLanes;      // index of the always-zero partial sum
     std::vector<int> comb((size_t)kMaxNfilt * kMelMaxPieces * ncls, zero_part);
     int npc[kMaxNfilt] = {0};
     for (int cls = 0; cls < ncls; ++cls) {
-    const int nq = (nbins - cls + ncls - 1) / ncls;            // entries of the class array
-    const int units = tri && cls == 1 ? 256 : kScratchUnits;   // 8-byte units a piece may read (zero padded past nq)
+    const bool joint = cls == 1;                               // K1T: residues 1 and 2 together
+    const int nq = joint ? 256 : (nbins + nres - 1) / nres;    // entries of the class array
+    const int units = kScratchUnits;                           // 8-byte units a piece may read (zero padded past nq)
     std::vector<Run> runs(c.nfilt);
     for (int j = 0; j < c.nfilt; ++j) {
+        auto wgt = [&](int q, int res) { return dense[j][nres * q + res]; };
+        auto nz = [&](int q) { return joint ? (wgt(q, 1) != 0.0 || wgt(q, 2) != 0.0) : wgt(q, 0) != 0.0; };
         int a = 0, b = nq;
-        while (a < nq && dense[j][ncls * a + cls] == 0.0) ++a;
-        while (b > a && dense[j][ncls * (b - 1) + cls] == 0.0) --b;
+        while (a < nq && !nz(a)) ++a;
+        while (b > a && !nz(b - 1)) --b;
         runs[j].k0 = a < nq ? a : 0;
-        for (int k = a; k < b; ++k) runs[j].w.push_back((float)dense[j][ncls * k + cls]);
+        for (int k = a; k < b; ++k) { runs[j].w.push_back((float)wgt(k, joint ? 1 : 0)); if (joint) runs[j].w2.push_back((float)wgt(k, 2)); }
     }
     std::vector<Piece> pieces;
     int mel_T[kMelSlots] = {0, 0, 0};
@@ -253,8 +258,8 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
     int mel_iters = 0;
     for (int s = 0; s < kMelSlots; ++s) { p.mel_Tc[cls][s] = mel_T[s]; if (cls == 0) p.mel_T[s] = mel_T[s]; mel_iters += mel_T[s]; }
     {
-        // weights as pairs: [iteration / 2][lane][iteration & 1]
-        std::vector<float> wt((size_t)std::max(mel_iters, 2) * kGroupLanes, 0.f);
+        // weights as pairs: [iteration / 2][lane][iteration & 1]; the joint class: [iteration][lane] (class-1 weight, class-2 weight)
+        std::vector<float> wt((size_t)std::max(mel_iters, 2) * kGroupLanes * (joint ? 2 : 1), 0.f);
         std::vector<int> base(kMelSlots * kGroupLanes, 0);
         for (int i = 0; i < kMelSlots * kGroupLanes; ++i) base[i] = i % kGroupLanes;   // idle lanes keep to their own banks
         int tb[kMelSlots];
@@ -264,9 +269,14 @@ inline std::vector<float> build_mfcc_tables(const MfccConfig& c, MfccParams& p, 
             base[pc.slot * kGroupLanes + pc.lane] = pc.k0;
             for (int t = 0; t < pc.len; ++t) {
                 const int it = tb[pc.slot] + shift + t;
-                wt[((size_t)(it >> 1) * kGroupLanes + pc.lane) * 2 + (it & 1)] = runs[pc.filt].w[pc.off + t];
+                if (joint) {
+                    wt[((size_t)it * kGroupLanes + pc.lane) * 2] = runs[pc.filt].w[pc.off + t];
+                    wt[((size_t)it * kGroupLanes + pc.lane) * 2 + 1] = runs[pc.filt].w2[pc.off + t];
+                } else {
+                    wt[((size_t)(it >> 1) * kGroupLanes + pc.lane) * 2 + (it & 1)] = runs[pc.filt].w[pc.off + t];
+                }
             }
-            comb[((size_t)pc.filt * ncls + cls) * kMelMaxPieces + npc[pc.filt]++ % kMelMaxPieces] = cls * kMelSlots * kGroupLanes + pc.slot * kGroupLanes + pc.lane;
+            comb[((size_t)pc.filt * ncls + cls) * kMelMaxPieces + npc[pc.filt]++] = cls * kMelSlots * kGroupLanes + pc.slot * kGroupLanes + pc.lane;
         }
         for (int j = 0; j < c.nfilt; ++j) npc[j] = 0;
         align4();
