@@ -195,7 +195,7 @@ int launch_mfcc(dspfe_plan* pl, Workspace& ws, const void* d_pcm, bool f32, int6
     LAUNCH_CHECK("prep_kernel", st);
 
     if (pl->is_long || (mode != 0 && pl->d_long_tab)) {
-        const int64_t rows = total_samples / pl->cfg.frame_step + n_utt;
+        const int64_t rows = dspfe_rows_bound(pl, total_samples, n_utt);
         if (mode == 0) { rc = ws.ensure_cep(rows * pl->cfg.numcep); if (rc) return rc; }
         MfccLongParams lp;
         lp.pcm = d_pcm; lp.in_f32 = f32 ? 1 : 0; lp.seg_start = ws.seg_start; lp.seg_len = ws.seg_len; lp.frame_off = pp.frame_off; lp.n_utt = n_utt;
@@ -275,7 +275,8 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     std::memset(&pl->layout, 0, sizeof(pl->layout));
     std::string err;
     // K1 takes nfft = 512 with an even hop (its sample planes); every other size / hop goes to the general kernel K1L
-    const bool tiled = (pl->cfg.nfft == kNfft && !(pl->cfg.frame_step & 1) && pl->cfg.frame_step >= 2) || pl->cfg.nfft == kTriNfft;
+    const bool tiled = ((pl->cfg.nfft == kNfft && !(pl->cfg.frame_step & 1) && pl->cfg.frame_step >= 2) || pl->cfg.nfft == kTriNfft) &&
+                       pl->cfg.frame_step <= pl->cfg.count_len;     // (gaps between frames, winstep > winlen: the general kernel)
     if (!tiled || pl->cfg.nfft != kNfft) {   // (a K1T plan keeps the general kernel for its filterbank / spectrum taps)
         err = mfcc_long_config_check(pl->cfg);
         if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
@@ -357,7 +358,8 @@ int dspfe_plan_info(const dspfe_plan* pl, int32_t* smem_bytes, int32_t* ctas_per
 
 int64_t dspfe_rows_bound(const dspfe_plan* pl, int64_t total_samples, int64_t n_utt) {
     if (!pl) return -1;
-    return total_samples / pl->cfg.frame_step + n_utt;
+    // 1 + ceil((S - L) / step) <= S / step + 1 frames per utterance for abutting or overlapping frames, + 2 when step > L (gaps)
+    return total_samples / pl->cfg.frame_step + (pl->cfg.frame_step > pl->cfg.count_len ? 2 : 1) * n_utt;
 }
 
 int dspfe_mfcc_delta(dspfe_plan* pl, const int16_t* d_pcm, int64_t total_samples, const int64_t* d_offsets,
@@ -441,7 +443,7 @@ int dspfe_mfcc_delta_host(dspfe_plan* pl, const int16_t* h_pcm, const int64_t* h
             CUDA_TRY(cudaHostAlloc(&s.h_off, cap * sizeof(int64_t), cudaHostAllocDefault));
             s.cap_utt = cap;
         }
-        const int64_t rows_bound = samples / fstep + nu;
+        const int64_t rows_bound = dspfe_rows_bound(pl, samples, nu);
         if (rows_bound > s.cap_rows) {
             cudaFree(s.d_out); s.d_out = nullptr; s.cap_rows = 0;
             const int64_t cap = std::max<int64_t>(rows_bound, kSlabSamples / fstep + 4096);

@@ -56,7 +56,6 @@ inline std::string mfcc_long_config_check(const MfccConfig& c) {
         return "nfft must be a power of two in [32, 2048] or 1536 in this build";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
     if (c.frame_step < 1) return "frame_step must be >= 1";
-    if (c.frame_step > (c.count_len > 0 ? c.count_len : c.frame_len)) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
     if (c.nfilt < 1 || c.nfilt > kMaxNfilt) return "nfilt must be in [1, 40]";
     if (c.numcep < 1 || c.numcep > kMaxNumcep || c.numcep > c.nfilt) return "numcep must be in [1, min(16, nfilt)]";
     if (c.delta_n < 1 || c.delta_n > kMaxDeltaN) return "delta N must be in [1, 4]";

@@ -82,7 +82,7 @@ def mfcc_long(pcm, offsets, **kw):
     pcm = np.ascontiguousarray(pcm, dtype=np.float32 if f32 else np.int16)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = len(offsets) - 1
-    rows = int(len(pcm) // p.frame_step + n)
+    rows = int(len(pcm) // p.frame_step + 2 * n)
     out = np.full((rows, 3 * p.numcep), np.nan, dtype=np.float32)
     fo = np.zeros(n + 1, dtype=np.int64)
     err = ctypes.create_string_buffer(256)

@@ -175,9 +175,11 @@ def test_general_kernel_other_transform_sizes():
         (16000, dict(nfft=1024, frame_len=400, frame_step=160), dict(winlen=0.025, winstep=0.01)),
         (16000, dict(nfft=2048, frame_len=2048, frame_step=512), dict(winlen=0.128, winstep=0.032)),
         (16000, dict(nfft=128, frame_len=128, frame_step=64, nfilt=10, numcep=8), dict(winlen=0.008, winstep=0.004, nfilt=10, numcep=8)),
+        (16000, dict(nfft=512, frame_len=160, frame_step=400), dict(winlen=0.01, winstep=0.025)),       # gaps between frames
     ]
     for rate, kw, okw in cases:
         out, fo = emu.mfcc_long(pcm, off, samplerate=rate, window=np.hamming(kw["frame_len"]), delta_n=2, **kw)
+        assert fo[-1] == sum(1 + max(0, -(-(n - kw["frame_len"]) // kw["frame_step"])) for n in np.diff(off))
         for u in range(4):
             assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(pcm[off[u]:off[u + 1]], rate, 2, nfft=kw["nfft"], winfunc=np.hamming, **okw),
                               what=f"{kw} utt {u}")

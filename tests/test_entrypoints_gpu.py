@@ -160,19 +160,20 @@ def test_features_endpoint_float_input(golden):
     np.testing.assert_array_equal(np.array(zcr), np.array(wzcr))
 
 
-def test_step_longer_than_frame_is_rejected():
-    """Gaps between frames (winstep > winlen, cfg.step > cfg.frame) are outside the built set: the plan constructors fail
-    with DSPFE_ERR_UNSUPPORTED (NotImplementedError in the drop-in) instead of writing past their row bounds."""
+def test_step_longer_than_frame():
+    """Gaps between frames (winstep > winlen, cfg.step > cfg.frame): the MFCC plans route such framings to the general
+    kernel with a row bound of two frames per utterance (reference sigproc.py:79-87 pads the last frame with zeros)."""
     import dspfe
     import features
-    x = np.zeros(16300, dtype=np.int16)
-    with pytest.raises(NotImplementedError):
-        features.mfcc(x, winlen=0.01, winstep=0.025)
-    with pytest.raises(NotImplementedError):
-        features.mfcc(x, winlen=0.01, winstep=0.025, nfft=1536)
-    # the endpoint path does take cfg.step > cfg.frame (its frame bound counts two frames per utterance then)
     from dspfe import synth
     from oracle import ref_features as O
+    x = synth.synth_utterance(5, 16300)
+    for kw in (dict(winlen=0.01, winstep=0.025), dict(winlen=0.01, winstep=0.025, nfft=1536), dict(winlen=0.02, winstep=0.0500625, nfft=1024)):
+        assert_mfcc_close(features.mfcc(x, **kw), O.mfcc(x, **kw), what=f"gaps {kw}")
+    feat, energy = features.fbank(x, winlen=0.01, winstep=0.025)
+    wf, we = O.fbank(x, winlen=0.01, winstep=0.025)
+    assert feat.shape == wf.shape and np.max(np.abs(feat - wf) / np.maximum(np.abs(wf), 1e-3 * wf.max())) <= 1e-4
+    # the endpoint path does take cfg.step > cfg.frame (its frame bound counts two frames per utterance then)
     lengths = [16300, 8000, 16001, 159, 161]
     pcm, off = synth.synth_batch(lengths, seed0=77)
     lr, asum, zcr, fo = dspfe.EndpointPlan(cfg_frame=0.01, cfg_step=0.025).detect_host(pcm, off, want_features=True)

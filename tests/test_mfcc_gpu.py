@@ -134,7 +134,7 @@ def test_errors(torch_dev):
     with pytest.raises(dspfe.DspfeError):
         dspfe.MfccPlan(nfft=768)
     with pytest.raises(dspfe.DspfeError):
-        dspfe.MfccPlan(nfft=1536, frame_len=400, frame_step=500)      # gaps between frames
+        dspfe.MfccPlan(nfft=1536, frame_len=400, frame_step=0)
     with pytest.raises(dspfe.DspfeError):
         dspfe.MfccPlan(highfreq=9000.0)
     plan = dspfe.MfccPlan()
