@@ -199,3 +199,40 @@ def test_frames_longer_than_nfft_are_truncated(caplog):
         assert got.shape == want.shape, (kw, got.shape, want.shape)
         assert_mfcc_close(got, want, what=f"truncated frames {kw}")
     assert any("truncated" in r.message for r in caplog.records)
+
+
+def test_torch_custom_ops():
+    """the batched entry points as torch.library custom ops on CUDA tensors (torch.ops.dspfe.*): same results as
+    the plans, fake (shape-only) implementations for tracing, no CPU implementation."""
+    import torch
+    import dspfe
+    import dspfe.torch_ops  # noqa: F401  registers the ops
+    from dspfe import synth
+    dev = torch.device("cuda:0")
+    lengths = [16000, 8000, 30001, 12345]
+    pcm, off = synth.synth_batch(lengths, seed0=99)
+    pcm_d, off_d = torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev)
+    lr = torch.ops.dspfe.endpoint(pcm_d, off_d)
+    assert torch.equal(lr, dspfe.EndpointPlan().detect(pcm_d, off_d))
+    rows, fo = torch.ops.dspfe.mfcc_delta(pcm_d, off_d, lr)
+    want, wfo = dspfe.MfccPlan(delta_n=2).mfcc_delta(pcm_d, off_d, trim=lr)
+    n = int(fo[-1])
+    assert torch.equal(fo, wfo) and torch.equal(rows[:n], want[:n])
+    rows2, fo2 = torch.ops.dspfe.mfcc_delta(pcm_d, off_d, None, 16000, 480, 160, 1536, 3, 0.0, True)      # model.py:74 at 16 kHz
+    w2, _ = dspfe.MfccPlan(frame_len=480, frame_step=160, nfft=1536, delta_n=3, preemph=0.0, window=np.hamming(480)).mfcc_delta(pcm_d, off_d)
+    assert torch.equal(rows2[: int(fo2[-1])], w2[: int(fo2[-1])])
+    hz, lag, pfo = torch.ops.dspfe.pitch(pcm_d, off_d, lr, 1, 16000, 300, 0.0)
+    o = dspfe.PitchPlan(method=1, frame_len=300).detect(pcm_d, off_d, trim=lr)
+    m = int(pfo[-1])
+    assert torch.equal(pfo, o["frame_off"]) and torch.equal(lag[:m], o["lag"][:m]) and torch.equal(hz[:m], o["pitch"][:m])
+    # shape-only tracing
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        fp = torch.empty(pcm.shape[0], dtype=torch.int16, device="cuda")
+        fo_ = torch.empty(len(lengths) + 1, dtype=torch.int64, device="cuda")
+        r, f = torch.ops.dspfe.mfcc_delta(fp, fo_)
+        assert r.shape == rows.shape and f.shape == fo.shape
+        h, l, q = torch.ops.dspfe.pitch(fp, fo_, None, 1, 16000, 300, 0.0)
+        assert h.shape == hz.shape and l.shape == lag.shape
+    with pytest.raises(NotImplementedError):
+        torch.ops.dspfe.endpoint(torch.from_numpy(pcm), torch.from_numpy(off))

@@ -162,3 +162,21 @@ def test_pitch_frame_counts():
     constructor needs CUDA, so the same formulas are checked through the oracle's index list."""
     for S in (1, 2, 3, 8, 9, 100, 8000, 32000, 80000):
         assert len(O.downsample_indices(S, 16000, 10000)) == ((S - 1) * 5 - 1) // 8 + 2 if S > 1 else 1
+
+
+def test_torch_custom_ops_register_and_trace_without_a_device():
+    """torch.ops.dspfe.* (dspfe/torch_ops.py): registered, shape-only fake implementations agree with the C ABI's bounds, and
+    there is no CPU implementation to fall back to."""
+    import torch
+    import dspfe.torch_ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        pcm = torch.empty(100000, dtype=torch.int16, device="cuda")
+        off = torch.empty(5, dtype=torch.int64, device="cuda")
+        assert torch.ops.dspfe.endpoint(pcm, off).shape == (4, 2)
+        rows, fo = torch.ops.dspfe.mfcc_delta(pcm, off)
+        assert rows.shape == (100000 // 160 + 4, 39) and fo.shape == (5,)
+        hz, lag, pfo = torch.ops.dspfe.pitch(pcm, off, None, 1, 16000, 300, 0.0)
+        assert hz.shape == lag.shape == ((100000 // 8 + 1) * 5 // 100 + 12,) and hz.dtype == torch.float64
+    with pytest.raises(NotImplementedError):
+        torch.ops.dspfe.endpoint(torch.zeros(10, dtype=torch.int16), torch.zeros(2, dtype=torch.int64))
