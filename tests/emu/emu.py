@@ -24,7 +24,10 @@ def build():
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DDSPFE_EMU", "-shared", "-fPIC", "-o", LIB] + srcs)
+    # DSPFE_EMU_ASAN=1: the kernel bodies under AddressSanitizer (shared-memory carve-ups and workspaces are heap vectors here);
+    # run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 and delete _build/ afterwards
+    flags = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("DSPFE_EMU_ASAN") == "1" else ["-O2"]
+    subprocess.check_call(["g++"] + flags + ["-std=c++17", "-DDSPFE_EMU", "-shared", "-fPIC", "-o", LIB] + srcs)
     return LIB
 
 
