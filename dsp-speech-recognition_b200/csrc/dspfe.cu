@@ -292,6 +292,9 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     }
     std::vector<float> blob = build_mfcc_tables(pl->cfg, pl->layout, err);
     if (err.empty()) { std::memset(&pl->layout_f32, 0, sizeof(pl->layout_f32)); build_mfcc_tables(pl->cfg, pl->layout_f32, err, true); }
+    if (!err.empty() && pl->d_long_tab) {   // e.g. a chunk of 16 long frames with a long hop does not fit shared memory: the general kernel takes it
+        pl->is_long = true; *plan = pl; return DSPFE_OK;
+    }
     if (!err.empty()) { delete pl; return fail(DSPFE_ERR_UNSUPPORTED, err); }
     pl->has_win = !pl->cfg.window.empty();
     pl->width = 3 * pl->cfg.numcep;

@@ -340,3 +340,67 @@ def test_tiled_nfft1536_kernel_batch():
     wf, we = O.fbank(x, winlen=0.03, nfft=1536, winfunc=np.hamming)
     assert np.max(np.abs(feat - wf) / np.maximum(np.abs(wf), 1e-3 * wf.max())) <= 1e-4
     assert np.max(np.abs(energy - we) / np.abs(we)) <= 1e-4
+
+
+def test_tiled_nfft1536_random_configs():
+    """K1T over random framings and filterbanks (frame lengths 32 .. 1536 incl. odd ones, hops 1 .. frame_len incl. odd ones, sample
+    rates, nfilt / numcep / lifter / delta N, window on / off, pre-emphasis on / off) against the oracle on a small ragged batch."""
+    import torch
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    from tol import assert_mfcc_close
+    rng = np.random.default_rng(1536)
+    dev = torch.device("cuda:0")
+    for trial in range(24):
+        rate = int(rng.choice([8000, 16000, 22050, 44100, 48000]))
+        flen = int(rng.integers(32, 1537)) if trial % 3 else int(rng.choice([480, 512, 513, 1024, 1025, 1323, 1440, 1536]))
+        step = int(rng.integers(max(1, flen // 8), flen + 1))
+        nfilt = int(rng.integers(8, 41)); numcep = int(rng.integers(1, min(nfilt, 16) + 1))
+        N = int(rng.integers(1, 5)); lifter = int(rng.choice([0, 22])); pre = float(rng.choice([0.0, 0.97])); win = bool(rng.integers(0, 2))
+        lengths = [int(rng.integers(1, 6 * flen)), flen - 1, flen + 1, int(rng.integers(flen, 12 * flen))]
+        pcm, off = synth.synth_batch(lengths, seed0=1000 + trial, sr=rate)
+        plan = dspfe.MfccPlan(samplerate=rate, frame_len=flen, frame_step=step, nfft=1536, nfilt=nfilt, numcep=numcep, ceplifter=lifter,
+                              delta_n=N, preemph=pre, window=np.hamming(flen) if win else None, seg_frames=int(rng.choice([16, 64, 256])))
+        out, fo = plan.mfcc_delta(torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev))
+        torch.cuda.synchronize()
+        out, fo = out.cpu().numpy(), fo.cpu().numpy()
+        for u in range(len(lengths)):
+            m = O.mfcc(pcm[off[u]:off[u + 1]], rate, winlen=flen / rate, winstep=step / rate, numcep=numcep, nfilt=nfilt, nfft=1536, preemph=pre,
+                       ceplifter=lifter, winfunc=np.hamming if win else (lambda n: np.ones((n,))))
+            assert O.round_half_up(flen / rate * rate) == flen and O.round_half_up(step / rate * rate) == step
+            d1 = O.delta(m, N)
+            assert_mfcc_close(out[fo[u]:fo[u + 1]], np.concatenate([m, d1, O.delta(d1, N)], axis=1),
+                              what=f"trial {trial}: rate {rate} flen {flen} step {step} nfilt {nfilt} numcep {numcep} N {N} win {win} pre {pre} utt {u}")
+
+
+def test_general_kernel_random_configs():
+    """K1L over random transform sizes (64 .. 2048, 512 with odd hops), framings incl. frames longer than nfft and gaps between
+    frames, filterbanks and delta N against the oracle."""
+    import torch
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    from tol import assert_mfcc_close
+    rng = np.random.default_rng(2048)
+    dev = torch.device("cuda:0")
+    for trial in range(16):
+        nfft = int(rng.choice([64, 128, 256, 512, 1024, 2048]))
+        rate = int(rng.choice([8000, 16000, 44100]))
+        flen = int(rng.integers(16, nfft + nfft // 4))                 # now and then longer than nfft: truncated for the transform
+        step = int(rng.integers(max(1, flen // 6), flen + flen // 3)) | (1 if nfft == 512 else 0)      # odd hops at 512; now and then gaps
+        nfilt = int(rng.integers(4, 27)); numcep = int(rng.integers(1, min(nfilt, 13) + 1)); N = int(rng.integers(1, 4))
+        win = bool(rng.integers(0, 2)); pre = float(rng.choice([0.0, 0.95]))
+        lengths = [int(rng.integers(1, 5 * flen)), flen, int(rng.integers(flen, 20 * flen))]
+        pcm, off = synth.synth_batch(lengths, seed0=2000 + trial, sr=rate)
+        plan = dspfe.MfccPlan(samplerate=rate, frame_len=flen, frame_step=step, nfft=nfft, nfilt=nfilt, numcep=numcep, delta_n=N, preemph=pre,
+                              window=np.hamming(flen) if win else None)
+        out, fo = plan.mfcc_delta(torch.from_numpy(pcm).to(dev), torch.from_numpy(off).to(dev))
+        torch.cuda.synchronize()
+        out, fo = out.cpu().numpy(), fo.cpu().numpy()
+        for u in range(len(lengths)):
+            m = O.mfcc(pcm[off[u]:off[u + 1]], rate, winlen=flen / rate, winstep=step / rate, numcep=numcep, nfilt=nfilt, nfft=nfft, preemph=pre,
+                       winfunc=np.hamming if win else (lambda n: np.ones((n,))))
+            d1 = O.delta(m, N)
+            assert_mfcc_close(out[fo[u]:fo[u + 1]], np.concatenate([m, d1, O.delta(d1, N)], axis=1),
+                              what=f"trial {trial}: nfft {nfft} rate {rate} flen {flen} step {step} nfilt {nfilt} numcep {numcep} N {N} win {win} utt {u}")
