@@ -527,15 +527,16 @@ __global__ void __launch_bounds__(32 * kEpDecideWarps) ep_decide_kernel(EpParams
 //     samples and their sums are exact, as in the reference's float64), so the decision is the reference's bit for bit.
 constexpr int kEpGateMaxLen = 1536;
 constexpr int kGateChunk = 9;
-constexpr int kGatePad = 32;
+constexpr int kGatePad = 48;        // zero tail: the probe reads up to 38 samples past the frame, the chunked loops 15
 // max over the lags n0 .. n0 + nl - 1 of acr(n) = S_n / (len - n), this lane's share (reduce with warp_max_f64).  sx is 16-byte
 // aligned: the eight x[i..i+7] every lane needs come from two broadcast 16-byte loads.
 // (A split that pairs chunk c with chunk 31 - c on two lanes, so that every lane walks the same number of positions, was
 // measured slower -- 3.37 against 2.99 ms: the lanes then read x[i..] at different i, all multiples of eight apart, and the
 // loads that were broadcasts turn into 4-way bank conflicts.)
 template <typename T>
-__device__ __forceinline__ T gate_best(const float* sx, int len, int n0, int nl, int lane) {
+__device__ __forceinline__ T gate_best(const float* sx, int len, int n0, int nl, int lane, int& best_n) {
     T best = (T)-3.0e38f;
+    best_n = n0;
     for (int c = lane; c * kGateChunk < nl; c += 32) {
         const int nb = n0 + c * kGateChunk;              // first lag of the chunk: it has the most terms
         T acc[kGateChunk], w[kGateChunk + 7];
@@ -561,13 +562,23 @@ __device__ __forceinline__ T gate_best(const float* sx, int len, int n0, int nl,
 #pragma unroll
         for (int m = 0; m < kGateChunk; ++m) {
             const int n = nb + m;
-            if (n < n0 + nl) { const T a = acc[m] / (T)(len - n); best = a > best ? a : best; }
+            if (n < n0 + nl) { const T a = acc[m] / (T)(len - n); if (a > best) { best = a; best_n = n; } }
         }
     }
     return best;
 }
-// the gate of the frame starting at sample b of the utterance x[0..S); warp-uniform result
-__device__ bool gate_frame_warp(const int16_t* x, long long S, long long b, int len, int n0, int n1, float* sx, int lane) {
+// the lane whose value equals the warp maximum hands its lag to everybody (lowest such lane)
+__device__ __forceinline__ int warp_arg_of_max(double v, double vmax, int n, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, v == vmax);
+    return __shfl_sync(0xffffffffu, n, m ? __ffs((int)m) - 1 : 0);
+}
+// The gate of the frame starting at sample b of the utterance x[0..S); warp-uniform result.  `pred` (in): a lag at which the
+// neighbouring frame's autocorrelation peaked, or -1; (out) this frame's peak lag when the gate holds.
+// With a prediction the warp first PROBES the 32 lags around it, one lag per lane: the rule only asks whether SOME lag exceeds
+// 0.55 acr(0), most evaluated frames are voiced (a walk is a run of true gates ended by one false one) and the pitch moves
+// slowly, so the probe usually settles the frame for a ninth of the multiply-adds of the full evaluation.  A probe that does not
+// clear 0.55 + delta proves nothing and the full evaluation follows.
+__device__ bool gate_frame_warp(const int16_t* x, long long S, long long b, int len, int n0, int n1, float* sx, int lane, int& pred) {
     __syncwarp();
     for (int i = lane; i < len + kGatePad; i += 32) sx[i] = (i < len && b + i < S) ? (float)x[b + i] : 0.f;
     __syncwarp();
@@ -580,71 +591,129 @@ __device__ bool gate_frame_warp(const int16_t* x, long long S, long long b, int 
     if (s0i == 0) return false;                          // 0 / 0 = NaN compares false, as in the reference
     const double a0 = (double)s0i / (double)len;
     const double delta = 1.5 * (double)len * 5.9604644775390625e-08 * (double)len / (double)(len - (n0 + nl - 1));
+    int bn;
     if (delta < 0.01) {
-        const float bf = gate_best<float>(sx, len, n0, nl, lane);
-        const double ratio = warp_max_f64((double)bf) / a0;
-        if (ratio > 0.55 + delta) return true;
+        if (pred >= 0 && nl >= 32) {
+            int p0 = pred - 16;
+            p0 = p0 < n0 ? n0 : (p0 > n0 + nl - 32 ? n0 + nl - 32 : p0);
+            const int n = p0 + lane;
+            float acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+            for (int i = 0; i < len - p0; i += 8) {      // terms past the frame (i + n >= len) multiply the zero tail
+                const float4 a0v = *reinterpret_cast<const float4*>(sx + i), a1v = *reinterpret_cast<const float4*>(sx + i + 4);
+                const float av[8] = {a0v.x, a0v.y, a0v.z, a0v.w, a1v.x, a1v.y, a1v.z, a1v.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = fmaf(av[u], sx[i + n + u], acc[u]);
+            }
+            const float sn = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            const double r = (double)(sn / (float)(len - n));
+            const double rmax = warp_max_f64(r);
+            if (rmax / a0 > 0.55 + delta) { pred = warp_arg_of_max(r, rmax, n, lane); return true; }
+        }
+        const double bf = (double)gate_best<float>(sx, len, n0, nl, lane, bn);
+        const double bmax = warp_max_f64(bf);
+        const double ratio = bmax / a0;
+        if (ratio > 0.55 + delta) { pred = warp_arg_of_max(bf, bmax, bn, lane); return true; }
         if (ratio < 0.55 - delta) return false;
     }
-    return warp_max_f64(gate_best<double>(sx, len, n0, nl, lane)) / a0 > 0.55;   // acr_gate_decide on exact sums
+    const double bd = gate_best<double>(sx, len, n0, nl, lane, bn);
+    const double dmax = warp_max_f64(bd);
+    if (dmax / a0 > 0.55) { pred = warp_arg_of_max(bd, dmax, bn, lane); return true; }   // acr_gate_decide on exact sums
+    return false;
 }
 
 // CTA-cooperative gate of K3r: every thread of the CTA replays the rule in lock step on identical data.  A request for a frame
 // that is not in the current window makes the CTA's warps evaluate that frame and the next kEpRobustWarps - 1 frames of the
 // walk (those the walk can reach: amp > M_L all the way) at once, one frame per warp; the walk's following requests hit the window.
-constexpr int kEpRobustWarps = 8;
+constexpr int kEpRobustWarps = 4;     // (8 warps: 1.56 ms, 4 warps: 1.40 ms per 4096 utterances -- fewer idle warps at the window barriers)
+// Warp 0 alone replays the rule (the first version had all 256 threads do it in lock step: the silence sort, the thresholds and the
+// frame walk were a third of the kernel's issue slots); the other warps serve its gate requests.  Requests and results travel
+// through shared memory between two named barriers that every thread of the CTA passes once per window.
+struct GateRequest { int j, dir, pred, done; double m_l; double pad; };      // 32 bytes: the staging areas behind it stay 16-byte aligned
+__device__ __forceinline__ void robust_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * kEpRobustWarps) : "memory"); }
+// one window: warp w evaluates frame j + dir * w when the walk can reach it
 template <class Amp>
-struct GateCta {
+__device__ __forceinline__ int gate_window_warp(const GateRequest& q, const int16_t* x, long long S, int step, int len, int n0, int n1, int F,
+                                                Amp amp, float* sx, int w, int lane) {
+    const int fj = q.j + q.dir * w;
+    bool want = q.dir < 0 ? fj >= 1 : fj < F;
+    for (int t = 1; t <= w && want; ++t) want = amp(q.j + q.dir * t) > q.m_l;
+    if (q.pred < 0 && w > 0) want = false;     // no peak lag yet (the utterance's first gate): one full evaluation, not eight
+    int res = 0, lag = q.pred;
+    if (want) res = 2 | (gate_frame_warp(x, S, (long long)fj * step, len, n0, n1, sx + w * (kEpGateMaxLen + kGatePad), lane, lag) ? 1 : 0);
+    return res | ((lag < 0 ? 0 : lag) << 2);
+}
+template <class Amp>
+struct GateCta {           // lives in warp 0
     const int16_t* x; long long S; int step, len, n0, n1, F;
-    Amp amp; float* sx; int* s_res;       // per-warp staging areas [kEpRobustWarps][kEpGateMaxLen + kGatePad], window results
+    Amp amp; float* sx; int* s_res; GateRequest* req;
     int dir; double m_l; int win_base, win_dir, win_known, win_val;
+    int pred;                              // the peak lag of the last frame whose gate held (the probe's centre), -1: none yet
     __device__ void hint(int d, double ml) { dir = d; m_l = ml; }
     __device__ bool operator()(int j) {
         const int wi = (j - win_base) * win_dir;
         if (wi >= 0 && wi < kEpRobustWarps && ((win_known >> wi) & 1)) return (win_val >> wi) & 1;
-        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int fj = j + dir * w;
-        bool want = dir < 0 ? fj >= 1 : fj < F;
-        for (int t = 1; t <= w && want; ++t) want = amp(j + dir * t) > m_l;
-        int res = 0;
-        if (want) res = 2 | (gate_frame_warp(x, S, (long long)fj * step, len, n0, n1, sx + w * (kEpGateMaxLen + kGatePad), lane) ? 1 : 0);
-        __syncthreads();                 // the previous window's results have been read by every thread
-        if (lane == 0) s_res[w] = res;
-        __syncthreads();
+        const int lane = threadIdx.x & 31;
+        if (lane == 0) { req->j = j; req->dir = dir; req->pred = pred; req->done = 0; req->m_l = m_l; }
+        robust_bar(1);                   // the request is posted (and the previous window's results have been read)
+        const int res = gate_window_warp(*req, x, S, step, len, n0, n1, F, amp, sx, 0, lane);
+        if (lane == 0) s_res[0] = res;
+        robust_bar(2);                   // the results are in
         win_base = j; win_dir = dir; win_known = 0; win_val = 0;
 #pragma unroll
-        for (int t = 0; t < kEpRobustWarps; ++t) { const int r = s_res[t]; win_known |= (r >> 1) << t; win_val |= (r & 1) << t; }
+        for (int t = 0; t < kEpRobustWarps; ++t) {
+            const int r = s_res[t];
+            win_known |= ((r >> 1) & 1) << t; win_val |= (r & 1) << t;
+            if ((r & 3) == 3) pred = r >> 2;                     // the furthest frame of the window whose gate held
+        }
         return win_val & 1;
     }
 };
+template <class Amp>
+__device__ __forceinline__ void robust_cta(const EpParams& p, Amp amp, const int32_t* zcr, int F, const int16_t* x, long long S, float* s_x, int* s_res,
+                                           GateRequest* req, int u) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = p.rule.rate / 500, n1 = p.rule.rate / 50;
+    if (w == 0) {
+        GateCta<Amp> gate{x, S, p.frame_step, p.frame_len, n0, n1, F, amp, s_x, s_res, req, -1, 0.0, 0, 1, 0, 0, -1};
+        int32_t lr[2];
+        endpoint_decide_robust(amp, zcr, F, p.rule, gate, lr);
+        if (lane == 0) { req->done = 1; p.lr[2 * u] = lr[0]; p.lr[2 * u + 1] = lr[1]; }
+        robust_bar(1);                   // releases the serving warps
+    } else {
+        for (;;) {
+            robust_bar(1);
+            if (req->done) break;
+            const int res = gate_window_warp(*req, x, S, p.frame_step, p.frame_len, n0, n1, F, amp, s_x, w, lane);
+            if (lane == 0) s_res[w] = res;
+            robust_bar(2);
+        }
+    }
+}
 
-__global__ void __launch_bounds__(32 * kEpRobustWarps, 3) ep_decide_robust_kernel(EpParams p) {
+__global__ void __launch_bounds__(32 * kEpRobustWarps, 6) ep_decide_robust_kernel(EpParams p) {
     extern __shared__ __align__(16) unsigned char ep_rsm[];
     double* s_amp = reinterpret_cast<double*>(ep_rsm);                                   // [kEpStageFrames]
     int32_t* s_zcr = reinterpret_cast<int32_t*>(s_amp + kEpStageFrames);                 // [kEpStageFrames]
     int* s_res = s_zcr + kEpStageFrames;                                                 // [kEpRobustWarps]
-    float* s_x = reinterpret_cast<float*>(s_res + kEpRobustWarps);                       // [kEpRobustWarps][kEpGateMaxLen + kGatePad]
+    static_assert(kEpRobustWarps % 4 == 0, "the window results keep the request and the staging areas 16-byte aligned");
+    GateRequest* req = reinterpret_cast<GateRequest*>(s_res + kEpRobustWarps);
+    float* s_x = reinterpret_cast<float*>(req + 1);                                      // [kEpRobustWarps][kEpGateMaxLen + kGatePad], 16-byte aligned
     const int u = blockIdx.x;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
     const int16_t* x = p.pcm + p.offsets[u];
     const long long S = (long long)(p.offsets[u + 1] - p.offsets[u]);
-    int32_t lr[2];
-    // every thread replays the rule on identical data (the gate is CTA-cooperative)
     if (F <= kEpStageFrames) {
         for (int i = threadIdx.x; i < F; i += blockDim.x) { s_amp[i] = (double)p.asum[f0 + i] / (double)p.frame_len; s_zcr[i] = p.zcr[f0 + i]; }
         __syncthreads();
-        GateCta<AmpFromF64> gate{x, S, p.frame_step, p.frame_len, p.rule.rate / 500, p.rule.rate / 50, F, AmpFromF64{s_amp}, s_x, s_res,
-                                 -1, 0.0, 0, 1, 0, 0};
-        endpoint_decide_robust(AmpFromF64{s_amp}, s_zcr, F, p.rule, gate, lr);
+        robust_cta(p, AmpFromF64{s_amp}, s_zcr, F, x, S, s_x, s_res, req, u);
     } else {
-        const AmpFromSum amp{p.asum + f0, (double)p.frame_len};
-        GateCta<AmpFromSum> gate{x, S, p.frame_step, p.frame_len, p.rule.rate / 500, p.rule.rate / 50, F, amp, s_x, s_res, -1, 0.0, 0, 1, 0, 0};
-        endpoint_decide_robust(amp, p.zcr + f0, F, p.rule, gate, lr);
+        robust_cta(p, AmpFromSum{p.asum + f0, (double)p.frame_len}, p.zcr + f0, F, x, S, s_x, s_res, req, u);
     }
-    if (threadIdx.x == 0) { p.lr[2 * u] = lr[0]; p.lr[2 * u + 1] = lr[1]; }
 }
-constexpr int kEpRobustSmem = kEpStageFrames * 12 + kEpRobustWarps * 4 + kEpRobustWarps * (kEpGateMaxLen + kGatePad) * 4;
+constexpr int kEpRobustSmem = kEpStageFrames * 12 + kEpRobustWarps * 4 + (int)sizeof(GateRequest) + kEpRobustWarps * (kEpGateMaxLen + kGatePad) * 4;
 
 // the gate of every row of a float64 frame matrix (the list-typed amplitude_rule(use_acr=True, frames=...) API): one warp per row
 __global__ void acr_gate_rows_kernel(const double* frames, int64_t n_rows, int len, int n0, int n1, int32_t* gate) {
