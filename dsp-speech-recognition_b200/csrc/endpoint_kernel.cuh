@@ -578,17 +578,19 @@ __device__ __forceinline__ int warp_arg_of_max(double v, double vmax, int n, int
 // 0.55 acr(0), most evaluated frames are voiced (a walk is a run of true gates ended by one false one) and the pitch moves
 // slowly, so the probe usually settles the frame for a ninth of the multiply-adds of the full evaluation.  A probe that does not
 // clear 0.55 + delta proves nothing and the full evaluation follows.
-__device__ bool gate_frame_warp(const int16_t* x, long long S, long long b, int len, int n0, int n1, float* sx, int lane, int& pred) {
+// probe_only (the speculated frames of a window): 1 = the gate holds, -1 = not settled (the full evaluation is left to the window
+// in which the walk actually asks for the frame: speculated frames past the end of a walk are mostly unvoiced)
+__device__ int gate_frame_warp(const int16_t* x, long long S, long long b, int len, int n0, int n1, float* sx, int lane, int& pred, bool probe_only) {
     __syncwarp();
     for (int i = lane; i < len + kGatePad; i += 32) sx[i] = (i < len && b + i < S) ? (float)x[b + i] : 0.f;
     __syncwarp();
     const int nl = (n1 < len ? n1 : len) - n0;           // lags n0 .. n0 + nl - 1
-    if (nl <= 0) return false;
+    if (nl <= 0) return 0;
     long long s0i = 0;
     for (int i = lane; i < len; i += 32) { const long long v = (long long)sx[i]; s0i += v * v; }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) s0i += __shfl_xor_sync(0xffffffffu, s0i, m);
-    if (s0i == 0) return false;                          // 0 / 0 = NaN compares false, as in the reference
+    if (s0i == 0) return 0;                              // 0 / 0 = NaN compares false, as in the reference
     const double a0 = (double)s0i / (double)len;
     const double delta = 1.5 * (double)len * 5.9604644775390625e-08 * (double)len / (double)(len - (n0 + nl - 1));
     int bn;
@@ -609,24 +611,25 @@ __device__ bool gate_frame_warp(const int16_t* x, long long S, long long b, int 
             const float sn = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
             const double r = (double)(sn / (float)(len - n));
             const double rmax = warp_max_f64(r);
-            if (rmax / a0 > 0.55 + delta) { pred = warp_arg_of_max(r, rmax, n, lane); return true; }
+            if (rmax / a0 > 0.55 + delta) { pred = warp_arg_of_max(r, rmax, n, lane); return 1; }
         }
+        if (probe_only) return -1;
         const double bf = (double)gate_best<float>(sx, len, n0, nl, lane, bn);
         const double bmax = warp_max_f64(bf);
         const double ratio = bmax / a0;
-        if (ratio > 0.55 + delta) { pred = warp_arg_of_max(bf, bmax, bn, lane); return true; }
-        if (ratio < 0.55 - delta) return false;
-    }
+        if (ratio > 0.55 + delta) { pred = warp_arg_of_max(bf, bmax, bn, lane); return 1; }
+        if (ratio < 0.55 - delta) return 0;
+    } else if (probe_only) return -1;
     const double bd = gate_best<double>(sx, len, n0, nl, lane, bn);
     const double dmax = warp_max_f64(bd);
-    if (dmax / a0 > 0.55) { pred = warp_arg_of_max(bd, dmax, bn, lane); return true; }   // acr_gate_decide on exact sums
-    return false;
+    if (dmax / a0 > 0.55) { pred = warp_arg_of_max(bd, dmax, bn, lane); return 1; }   // acr_gate_decide on exact sums
+    return 0;
 }
 
 // CTA-cooperative gate of K3r: every thread of the CTA replays the rule in lock step on identical data.  A request for a frame
 // that is not in the current window makes the CTA's warps evaluate that frame and the next kEpRobustWarps - 1 frames of the
 // walk (those the walk can reach: amp > M_L all the way) at once, one frame per warp; the walk's following requests hit the window.
-constexpr int kEpRobustWarps = 4;     // (8 warps: 1.56 ms, 4 warps: 1.40 ms per 4096 utterances -- fewer idle warps at the window barriers)
+constexpr int kEpRobustWarps = 4;     // (8 warps: 1.56 -> 1.80 ms with probe-only speculation, 4 warps: 1.40 -> 1.33 ms per 4096 utterances: fewer idle warps at the window barriers)
 // Warp 0 alone replays the rule (the first version had all 256 threads do it in lock step: the silence sort, the thresholds and the
 // frame walk were a third of the kernel's issue slots); the other warps serve its gate requests.  Requests and results travel
 // through shared memory between two named barriers that every thread of the CTA passes once per window.
@@ -641,7 +644,10 @@ __device__ __forceinline__ int gate_window_warp(const GateRequest& q, const int1
     for (int t = 1; t <= w && want; ++t) want = amp(q.j + q.dir * t) > q.m_l;
     if (q.pred < 0 && w > 0) want = false;     // no peak lag yet (the utterance's first gate): one full evaluation, not eight
     int res = 0, lag = q.pred;
-    if (want) res = 2 | (gate_frame_warp(x, S, (long long)fj * step, len, n0, n1, sx + w * (kEpGateMaxLen + kGatePad), lane, lag) ? 1 : 0);
+    if (want) {
+        const int g = gate_frame_warp(x, S, (long long)fj * step, len, n0, n1, sx + w * (kEpGateMaxLen + kGatePad), lane, lag, w > 0);
+        if (g >= 0) res = 2 | g;
+    }
     return res | ((lag < 0 ? 0 : lag) << 2);
 }
 template <class Amp>
