@@ -430,6 +430,10 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                     load_classes(x, f);
                     fft256(x);                   // .x halves: Z_1[q], .y halves: Z_2[q], q = lane + 16 k2
                     float es = 0.f;
+                    const bool swp = (grp & 1) != 0;
+                    const int st1 = swp ? -32 : 32;                                   // words per k2 step of the first store
+                    float* d1 = qf + (swp ? 2 * (255 - lane) : 2 * lane + 1);
+                    float* d2 = qf + (swp ? 2 * lane + 1 : 2 * (255 - lane));
 #pragma unroll
                     for (int k2 = 0; k2 < 16; ++k2) {
                         // Z[3q + 2] = Z_2[q] pairs with Z[768 - (3q + 2)] = Z_1[255 - q]: lane 15 - lane, register 15 - k2
@@ -441,8 +445,11 @@ DEVFN void mfcc_cta(const MfccParams& p, unsigned char* smem_raw) {
                         const float tre = dsp_fmaf(dim, w.x, dre * w.y), tim = dsp_fmaf(dim, w.y, -dre * w.x);
                         const float2 xr = make_float2(sre + tre, sre - tre), xi = make_float2(sim + tim, sim - tim);
                         const float2 pw = f2muls(f2fma(xi, xi, f2mul(xr, xr)), sc);   // (bin 3q + 2, bin 3 (255 - q) + 1)
-                        qf[2 * q + 1] = pw.x;
-                        qf[2 * (255 - q)] = pw.y;
+                        // (the two groups of a warp issue these stores together and their tiles start on the same bank: the odd group
+                        // stores the pair in the opposite order -- d1 / d2 below -- so one instruction writes odd words in one group and
+                        // even words in the other)
+                        d1[st1 * k2] = swp ? pw.y : pw.x;
+                        d2[-st1 * k2] = swp ? pw.x : pw.y;
                         es += pw.x + pw.y;
                     }
                     if (f == 0) esum.x += es; else esum.y += es;
