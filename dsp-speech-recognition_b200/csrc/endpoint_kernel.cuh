@@ -582,12 +582,31 @@ __device__ __forceinline__ int warp_arg_of_max(double v, double vmax, int n, int
 // in which the walk actually asks for the frame: speculated frames past the end of a walk are mostly unvoiced)
 __device__ int gate_frame_warp(const int16_t* x, long long S, long long b, int len, int n0, int n1, float* sx, int lane, int& pred, bool probe_only) {
     __syncwarp();
-    for (int i = lane; i < len + kGatePad; i += 32) sx[i] = (i < len && b + i < S) ? (float)x[b + i] : 0.f;
+    // stage the frame as float32 (exact for int16; mantissa splicing instead of the slow I2F) with a zero tail, summing x^2 on the way;
+    // sample pairs through 32-bit loads where the frame starts on a 4-byte boundary
+    long long s0i = 0;
+    const int nv = (int)(S - b < (long long)len ? (S - b > 0 ? S - b : 0) : (long long)len);      // samples of the frame that exist
+    auto cvt = [](int v) { return __uint_as_float(0x4B000000u | (((unsigned)v & 0xffffu) ^ 0x8000u)) - 8421376.0f; };
+    if ((reinterpret_cast<uintptr_t>(x + b) & 3) == 0) {
+        const int* xw = reinterpret_cast<const int*>(x + b);
+        for (int i2 = lane; 2 * i2 < len + kGatePad; i2 += 32) {
+            const int i = 2 * i2;
+            int lo = 0, hi = 0;
+            if (i + 1 < nv) { const int w = __ldg(xw + i2); lo = (int)(short)(w & 0xffff); hi = w >> 16; }
+            else if (i < nv) lo = (int)x[b + i];
+            *reinterpret_cast<float2*>(sx + i) = make_float2(cvt(lo), cvt(hi));
+            s0i += (long long)(lo * lo) + (long long)(hi * hi);                   // each < 2^30: the 32-bit products are exact
+        }
+    } else {
+        for (int i = lane; i < len + kGatePad; i += 32) {
+            const int v = i < nv ? (int)x[b + i] : 0;
+            sx[i] = cvt(v);
+            s0i += (long long)(v * v);
+        }
+    }
     __syncwarp();
     const int nl = (n1 < len ? n1 : len) - n0;           // lags n0 .. n0 + nl - 1
     if (nl <= 0) return 0;
-    long long s0i = 0;
-    for (int i = lane; i < len; i += 32) { const long long v = (long long)sx[i]; s0i += v * v; }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) s0i += __shfl_xor_sync(0xffffffffu, s0i, m);
     if (s0i == 0) return 0;                              // 0 / 0 = NaN compares false, as in the reference
