@@ -274,8 +274,8 @@ int dspfe_plan_create(const dspfe_mfcc_params* p, dspfe_plan** plan) {
     pl->cfg = to_config(*p);
     std::memset(&pl->layout, 0, sizeof(pl->layout));
     std::string err;
-    // K1 takes nfft = 512 with an even hop (its sample planes); every other size / hop goes to the general kernel K1L
-    const bool tiled = ((pl->cfg.nfft == kNfft && !(pl->cfg.frame_step & 1) && pl->cfg.frame_step >= 2) || pl->cfg.nfft == kTriNfft) &&
+    // K1 / K1T take nfft = 512 / 1536 at any hop; every other size (and gaps between frames) goes to the general kernel K1L
+    const bool tiled = (pl->cfg.nfft == kNfft || pl->cfg.nfft == kTriNfft) &&
                        pl->cfg.frame_step <= pl->cfg.count_len;     // (gaps between frames, winstep > winlen: the general kernel)
     if (!tiled || pl->cfg.nfft != kNfft) {   // (a K1T plan keeps the general kernel for its filterbank / spectrum taps)
         err = mfcc_long_config_check(pl->cfg);

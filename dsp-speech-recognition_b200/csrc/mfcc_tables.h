@@ -69,7 +69,6 @@ inline std::string mfcc_long_config_check(const MfccConfig& c) {
 inline std::string mfcc_config_check(const MfccConfig& c) {
     if (c.nfft != kNfft && c.nfft != kTriNfft) return "the tiled kernel is built for nfft 512 and 1536 (other sizes: the general kernel)";
     if (c.frame_len < 1 || c.frame_len > c.nfft) return "frame_len must be in [1, nfft] (longer frames are truncated by the reference with a warning; not supported)";
-    if (c.nfft == kNfft && (c.frame_step < 2 || (c.frame_step & 1))) return "frame_step must be even and >= 2 (odd hops: the general kernel)";
     if (c.frame_step < 1) return "frame_step must be >= 1";
     if (c.frame_step > (c.count_len > 0 ? c.count_len : c.frame_len)) return "frame_step greater than frame_len (gaps between frames) is not built: the row bounds assume overlapping or abutting frames";
     if (c.nfilt < 1 || c.nfilt > kMaxNfilt) return "nfilt must be in [1, 40]";

@@ -48,8 +48,8 @@ typedef struct {
     int32_t samplerate;      /* 16000 */
     int32_t frame_len;       /* 400  (25 ms) */
     int32_t frame_step;      /* 160  (10 ms) */
-    int32_t nfft;            /* 512; built: 32..2048 powers of two and 1536 (model.py:74).  512 with an even hop: the tiled
-                              * kernel K1; 1536: the tiled kernel K1T; everything else: the general kernel K1L */
+    int32_t nfft;            /* 512; built: 32..2048 powers of two and 1536 (model.py:74).  512: the tiled kernel K1; 1536: the tiled
+                              * kernel K1T; everything else (and frame_step > frame_len): the general kernel K1L */
     int32_t nfilt;           /* 26 */
     int32_t numcep;          /* 13 */
     int32_t ceplifter;       /* 22 (<= 0 disables, base.py:66-68) */

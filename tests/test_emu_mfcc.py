@@ -77,7 +77,7 @@ def test_float32_input_path():
 
 def test_unsupported_configs_are_rejected():
     x = np.zeros(1000, dtype=np.int16)
-    for kw in (dict(nfft=1024), dict(nfft=1536, frame_len=1600), dict(frame_len=600), dict(frame_step=161), dict(nfilt=41), dict(numcep=17),
+    for kw in (dict(nfft=1024), dict(nfft=1536, frame_len=1600), dict(frame_len=600), dict(seg_frames=8), dict(nfilt=41), dict(numcep=17),
                dict(delta_n=0), dict(highfreq=9000.0)):
         with pytest.raises(RuntimeError):
             emu.mfcc_delta(x, [0, 1000], **kw)
@@ -183,6 +183,18 @@ def test_general_kernel_other_transform_sizes():
         for u in range(4):
             assert_mfcc_close(out[fo[u]:fo[u + 1]], ref39(pcm[off[u]:off[u + 1]], rate, 2, nfft=kw["nfft"], winfunc=np.hamming, **okw),
                               what=f"{kw} utt {u}")
+
+
+def test_odd_hops_on_the_tiled_kernel():
+    """K1 with odd hops (e.g. 10 ms at 22.05 kHz = 221 samples): the sample planes are addressed per frame, the frames of a pair are two
+    hops apart and therefore share their parity."""
+    for rate, flen, step, n in ((16000, 400, 161, 9000), (22050, 512, 221, 12000), (16000, 37, 1, 300), (8000, 200, 79, 5000)):
+        x = synth.synth_utterance(70 + step, n, sr=rate)
+        pcm = np.concatenate([x, x[: n // 3]]); off = [0, n, n + n // 3]
+        out, fo = emu.mfcc_delta(pcm, off, frame_len=flen, frame_step=step, samplerate=rate, window=np.hamming(flen), seg_frames=64)
+        for u in range(2):
+            ref = O.mfcc_delta39(pcm[off[u]:off[u + 1]], 2, samplerate=rate, winlen=flen / rate, winstep=step / rate, winfunc=np.hamming)
+            assert_mfcc_close(out[fo[u]:fo[u + 1]], ref, what=f"rate {rate} frame {flen} hop {step} utt {u}")
 
 
 def test_mel_piece_tables_random_filterbanks():

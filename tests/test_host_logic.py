@@ -63,7 +63,7 @@ def test_mel_edges_match_reference_filterbank(cfg):
 
 def test_unsupported_configs_raise():
     # (frame_len > nfft is no longer an error: such frames are truncated for the transform, as the reference does -- sigproc.py:143-146)
-    for kw in (dict(nfft=768), dict(nfft=1024), dict(frame_step=161), dict(nfilt=41), dict(numcep=17), dict(delta_n=0), dict(frame_len=100, frame_step=160)):
+    for kw in (dict(nfft=768), dict(nfft=1024), dict(seg_frames=8), dict(nfilt=41), dict(numcep=17), dict(delta_n=0), dict(frame_len=100, frame_step=160)):
         with pytest.raises(dspfe.DspfeError) as e:
             dspfe.mfcc_tables_host(**kw)
         assert e.value.code == -2
