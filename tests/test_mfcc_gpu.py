@@ -375,8 +375,8 @@ def test_tiled_nfft1536_random_configs():
 
 
 def test_general_kernel_random_configs():
-    """K1L over random transform sizes (64 .. 2048, 512 with odd hops), framings incl. frames longer than nfft and gaps between
-    frames, filterbanks and delta N against the oracle."""
+    """Random transform sizes (64 .. 2048 on the general kernel K1L; 512 with odd hops on K1, or on K1L when the hop leaves gaps),
+    framings incl. frames longer than nfft and gaps between frames, filterbanks and delta N against the oracle."""
     import torch
     import dspfe
     from dspfe import synth
