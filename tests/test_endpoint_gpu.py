@@ -189,3 +189,19 @@ def test_warp_parallel_decision_equals_serial_rule():
         if tuple(int(v) for v in lr[u]) != tuple(int(v) for v in want):
             bad.append((u, tuple(lr[u]), tuple(want)))
     assert not bad, f"{len(bad)} of {len(xs)} decisions differ, first: {bad[:3]}"
+
+
+def test_robust_endpoint_detection_other_rates():
+    """K3r at 8 kHz (240-sample frames, lags 16..159) and 44.1 kHz (1323-sample frames, lags 88..881: several lag chunks per lane,
+    odd frame length): the probe at the predicted lag, the float32 screening and the exact recompute against the oracle."""
+    import dspfe
+    from dspfe import synth
+    from oracle import ref_features as O
+    for rate, lo, hi in ((8000, 4000, 30000), (44100, 20000, 120000)):
+        lengths = synth.ragged_lengths(10, seed=rate, lo=lo, hi=hi)
+        lengths[0] = int(0.03 * rate) - 1
+        pcm, off = synth.synth_batch(lengths, seed0=rate + 7, sr=rate)
+        lr = dspfe.EndpointPlan(samplerate=rate).detect_robust_host(pcm, off)
+        for u in range(len(lengths)):
+            want = O.robust_endpoint_detection(pcm[off[u]:off[u + 1]], rate)
+            assert (int(lr[u, 0]), int(lr[u, 1])) == want, (rate, u)
