@@ -52,6 +52,38 @@ __global__ void __launch_bounds__(kPitchPrepThreads) pitch_prep_kernel(PitchPara
         fo += nf; so += (nf + kClipRun - 1) / kClipRun * kClipRun;
     }
     if (tid == kPitchPrepThreads - 1) { p.frame_off[p.n_utt] = s_fr[tid]; p.slot_off[p.n_utt] = s_sl[tid]; }
+    // the utterances by descending frame count (counting sort, bins of one frame, the longest share the last bin): the order in
+    // which the CTA-per-utterance kernels take them.  Positions inside a bin depend on the atomics' order; the results do not.
+    int* order = const_cast<int*>(p.order);
+    if (order) {
+        __syncthreads();
+        int* bins = reinterpret_cast<int*>(s_fr);          // [kPitchPrepThreads] (the scan arrays are done)
+        bins[tid] = 0;
+        __syncthreads();
+        for (int u = u0; u < u1; ++u) {
+            const long long nf = num_frames(p.ds_len[u], p.frame_len, p.frame_step);
+            atomicAdd(&bins[nf < kPitchPrepThreads - 1 ? (int)nf : kPitchPrepThreads - 1], 1);
+        }
+        __syncthreads();
+        // start[b] = utterances in the bins above b: inclusive suffix sums, then shift
+        int* start = reinterpret_cast<int*>(s_sl);
+        start[tid] = bins[tid];
+        __syncthreads();
+        for (int d = 1; d < kPitchPrepThreads; d <<= 1) {
+            const int v = tid + d < kPitchPrepThreads ? start[tid + d] : 0;
+            __syncthreads();
+            start[tid] += v;
+            __syncthreads();
+        }
+        const int mine = start[tid] - bins[tid];
+        __syncthreads();
+        start[tid] = mine;
+        __syncthreads();
+        for (int u = u0; u < u1; ++u) {
+            const long long nf = num_frames(p.ds_len[u], p.frame_len, p.frame_step);
+            order[atomicAdd(&start[nf < kPitchPrepThreads - 1 ? (int)nf : kPitchPrepThreads - 1], 1)] = u;
+        }
+    }
 }
 
 // K4a-1: gather + exact median + centre clip, a frame pair per warp
@@ -102,7 +134,7 @@ __global__ void __launch_bounds__(kTrackThreads) pitch_track_kernel(const __grid
 
 __global__ void __launch_bounds__(32) pitch_feature_kernel(const __grid_constant__ PitchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    pitch_feature_warp(p, blockIdx.x, reinterpret_cast<double*>(smem));
+    pitch_feature_warp(p, p.order ? p.order[blockIdx.x] : (int)blockIdx.x, reinterpret_cast<double*>(smem));
 }
 
 // dp_max_pitch (pitch.py:208-225) on the device: Viterbi over the columns of g [n_rows, n_cols] with a jump penalty of 5 per
@@ -173,6 +205,7 @@ struct dspfe_pitch_plan {
     // workspaces
     int64_t cap_utt = 0, cap_frames = 0, cap_slots = 0;
     int64_t* seg_start = nullptr; int32_t* seg_len = nullptr; int32_t* ds_len = nullptr; int64_t* frame_off = nullptr; int64_t* slot_off = nullptr;
+    int32_t* order = nullptr;
     float2* clip = nullptr; int4* run_desc = nullptr; float* rows = nullptr; double* frame_amp = nullptr; double* pitch = nullptr; int32_t* lag = nullptr; double* scratch = nullptr;
     // host-path staging
     cudaStream_t stream = nullptr;
@@ -184,13 +217,14 @@ namespace {
 
 int ensure(dspfe_pitch_plan* pl, int64_t n_utt, int64_t frames) {
     if (n_utt + 1 > pl->cap_utt) {
-        cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off); cudaFree(pl->slot_off);
-        pl->seg_start = nullptr; pl->seg_len = nullptr; pl->ds_len = nullptr; pl->frame_off = nullptr; pl->slot_off = nullptr; pl->cap_utt = 0;
+        cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off); cudaFree(pl->slot_off); cudaFree(pl->order);
+        pl->order = nullptr; pl->seg_start = nullptr; pl->seg_len = nullptr; pl->ds_len = nullptr; pl->frame_off = nullptr; pl->slot_off = nullptr; pl->cap_utt = 0;
         CUDA_TRY(cudaMalloc(&pl->seg_start, (n_utt + 1) * sizeof(int64_t)));
         CUDA_TRY(cudaMalloc(&pl->seg_len, (n_utt + 1) * sizeof(int32_t)));
         CUDA_TRY(cudaMalloc(&pl->ds_len, (n_utt + 1) * sizeof(int32_t)));
         CUDA_TRY(cudaMalloc(&pl->frame_off, (n_utt + 1) * sizeof(int64_t)));
         CUDA_TRY(cudaMalloc(&pl->slot_off, (n_utt + 1) * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&pl->order, (n_utt + 1) * sizeof(int32_t)));
         pl->cap_utt = n_utt + 1;
     }
     if (frames > pl->cap_frames) {
@@ -256,7 +290,7 @@ int dspfe_pitch_create(const dspfe_pitch_params* q, dspfe_pitch_plan** plan) {
 void dspfe_pitch_destroy(dspfe_pitch_plan* pl) {
     if (!pl) return;
     cudaFree(pl->d_tab);
-    cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off); cudaFree(pl->slot_off);
+    cudaFree(pl->seg_start); cudaFree(pl->seg_len); cudaFree(pl->ds_len); cudaFree(pl->frame_off); cudaFree(pl->slot_off); cudaFree(pl->order);
     cudaFree(pl->clip); cudaFree(pl->run_desc); cudaFree(pl->rows); cudaFree(pl->frame_amp); cudaFree(pl->pitch); cudaFree(pl->lag); cudaFree(pl->scratch);
     cudaFree(pl->d_pcm); cudaFree(pl->d_off); cudaFree(pl->d_trim); cudaFree(pl->d_feat);
     if (pl->stream) cudaStreamDestroy(pl->stream);
@@ -310,7 +344,7 @@ int dspfe_pitch(dspfe_pitch_plan* pl, const void* d_pcm, int32_t sample_dtype, i
     p.frame_off = d_frame_off ? d_frame_off : pl->frame_off; p.slot_off = pl->slot_off; p.seg_start = pl->seg_start; p.seg_len = pl->seg_len; p.ds_len = pl->ds_len;
     p.clip = pl->clip; p.run_desc = pl->run_desc; p.rows = d_rows ? d_rows : pl->rows; p.rows_out = nullptr; p.score = nullptr; p.frame_amp = pl->frame_amp;
     p.pitch = d_pitch ? d_pitch : pl->pitch; p.lag = d_lag ? d_lag : pl->lag; p.feat = d_feat; p.scratch = pl->scratch;
-    p.max_frames = bound;
+    p.max_frames = bound; p.order = pl->order;
     pitch_prep_kernel<<<1, kPitchPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("pitch_prep_kernel", st);
     const int64_t slots = bound + (int64_t)(kClipRun - 1) * n_utt;

@@ -91,6 +91,8 @@ struct PitchParams {
     double* feat;                        // [U,5] pitch_feature, or null
     double* scratch;                     // [3*F_total] K6 work area
     int64_t max_frames;
+    const int32_t* order;                // optional [U]: the utterances by descending frame count (the CTA-per-utterance kernels take
+                                         //   them in this order, longest first: no long utterance is left to run alone at the end); null = identity
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -859,7 +861,7 @@ constexpr int kTrackListPerWarp = kTrackChunk * kPeakLags / (kTrackThreads / 32)
 DEVFN bool stops(float x, float v) { return !(x <= v); }          // pitch.py:236,239: the scan goes on while sig[j] <= v (a NaN stops it)
 
 DEVFN void pitch_track_cta(const PitchParams& p, float* buf, int* sc, double* spitch) {
-    const int u = simt::bid();
+    const int u = p.order ? p.order[simt::bid()] : simt::bid();
     const int tid = simt::tid();
     const int lane = tid & 31, warp = tid >> 5;
     const int64_t f0 = p.frame_off[u];
