@@ -14,7 +14,7 @@ struct dspfe_endpoint_plan {
     int frame_len, frame_step, q, rem;
     // workspaces
     int64_t cap_utt = 0, cap_blocks = 0, cap_frames = 0;
-    int64_t *frame_off = nullptr, *block_off = nullptr;
+    int64_t *frame_off = nullptr, *block_off = nullptr; int32_t* order = nullptr;
     int32_t *blk = nullptr, *asum = nullptr, *zcr = nullptr;
     // host-path staging
     cudaStream_t stream = nullptr;
@@ -39,8 +39,9 @@ int fill_rule(const dspfe_endpoint_params& q, EpRule& r, int& frame_len, int& fr
 
 int ensure(dspfe_endpoint_plan* pl, int64_t n_utt, int64_t blocks, int64_t frames) {
     if (n_utt + 1 > pl->cap_utt) {
-        cudaFree(pl->frame_off); cudaFree(pl->block_off); pl->frame_off = pl->block_off = nullptr; pl->cap_utt = 0;
+        cudaFree(pl->frame_off); cudaFree(pl->block_off); cudaFree(pl->order); pl->frame_off = pl->block_off = nullptr; pl->order = nullptr; pl->cap_utt = 0;
         CUDA_TRY(cudaMalloc(&pl->frame_off, (n_utt + 1) * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&pl->order, (n_utt + 1) * sizeof(int32_t)));
         CUDA_TRY(cudaMalloc(&pl->block_off, (n_utt + 1) * sizeof(int64_t)));
         pl->cap_utt = n_utt + 1;
     }
@@ -141,7 +142,7 @@ int dspfe_endpoint_create(const dspfe_endpoint_params* p, dspfe_endpoint_plan** 
 
 void dspfe_endpoint_destroy(dspfe_endpoint_plan* pl) {
     if (!pl) return;
-    cudaFree(pl->frame_off); cudaFree(pl->block_off); cudaFree(pl->blk); cudaFree(pl->asum); cudaFree(pl->zcr);
+    cudaFree(pl->frame_off); cudaFree(pl->block_off); cudaFree(pl->order); cudaFree(pl->blk); cudaFree(pl->asum); cudaFree(pl->zcr);
     cudaFree(pl->d_pcm); cudaFree(pl->d_off); cudaFree(pl->d_lr);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     delete pl;
@@ -179,7 +180,7 @@ int dspfe_endpoint(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t total_
     p.pcm = d_pcm; p.offsets = d_offsets; p.n_utt = n_utt; p.frame_len = pl->frame_len; p.frame_step = pl->frame_step;
     p.q = pl->q; p.rem = pl->rem; p.frame_off = d_frame_off ? d_frame_off : pl->frame_off; p.block_off = pl->block_off;
     p.blk = pl->blk; p.asum = d_asum ? d_asum : pl->asum; p.zcr = d_zcr ? d_zcr : pl->zcr; p.lr = d_lr;
-    p.max_blocks = blocks_bound; p.max_frames = frames_bound; p.rule = pl->rule;
+    p.max_blocks = blocks_bound; p.max_frames = frames_bound; p.rule = pl->rule; p.order = pl->order;
     ep_prep_kernel<<<1, kEpPrepThreads, 0, st>>>(p);
     LAUNCH_CHECK("ep_prep_kernel", st);
     ep_block_kernel<<<(unsigned)((blocks_bound + 127) / 128), 128, 0, st>>>(p);
@@ -205,7 +206,7 @@ int dspfe_endpoint_robust(dspfe_endpoint_plan* pl, const int16_t* d_pcm, int64_t
     EpParams p;
     p.pcm = d_pcm; p.offsets = d_offsets; p.n_utt = n_utt; p.frame_len = pl->frame_len; p.frame_step = pl->frame_step;
     p.q = pl->q; p.rem = pl->rem; p.frame_off = pl->frame_off; p.block_off = pl->block_off; p.blk = pl->blk; p.asum = pl->asum; p.zcr = pl->zcr;
-    p.lr = d_lr; p.max_blocks = 0; p.max_frames = frames_bound; p.rule = pl->rule;
+    p.lr = d_lr; p.max_blocks = 0; p.max_frames = frames_bound; p.rule = pl->rule; p.order = pl->order;
     CUDA_TRY(cudaFuncSetAttribute(ep_decide_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpRobustSmem));
     CUDA_TRY(cudaFuncSetAttribute(ep_decide_robust_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ep_decide_robust_kernel<<<(unsigned)n_utt, 32 * kEpRobustWarps, kEpRobustSmem, st>>>(p);

@@ -216,6 +216,7 @@ struct EpParams {
     int32_t* lr;               // [U, 2]
     int64_t max_blocks, max_frames;
     EpRule rule;
+    int32_t* order;            // optional [U]: the utterances by descending frame count (K3r takes them longest first); null = identity
 };
 
 #ifdef __CUDACC__
@@ -249,6 +250,34 @@ __global__ void __launch_bounds__(kEpPrepThreads) ep_prep_kernel(EpParams p) {
         fo += F; bo += ep_blocks(F, p.q, p.rem);
     }
     if (tid == kEpPrepThreads - 1) { p.frame_off[p.n_utt] = s_f[tid]; p.block_off[p.n_utt] = s_b[tid]; }
+    if (p.order) {   // counting sort by frame count, descending (bins of one frame; the longest utterances share the last bin)
+        __syncthreads();
+        int* bins = reinterpret_cast<int*>(s_f);
+        int* start = reinterpret_cast<int*>(s_b);
+        bins[tid] = 0;
+        __syncthreads();
+        for (int u = u0; u < u1; ++u) {
+            const long long F = num_frames(p.offsets[u + 1] - p.offsets[u], p.frame_len, p.frame_step);
+            atomicAdd(&bins[F < kEpPrepThreads - 1 ? (int)F : kEpPrepThreads - 1], 1);
+        }
+        __syncthreads();
+        start[tid] = bins[tid];
+        __syncthreads();
+        for (int d = 1; d < kEpPrepThreads; d <<= 1) {
+            const int v = tid + d < kEpPrepThreads ? start[tid + d] : 0;
+            __syncthreads();
+            start[tid] += v;
+            __syncthreads();
+        }
+        const int mine = start[tid] - bins[tid];
+        __syncthreads();
+        start[tid] = mine;
+        __syncthreads();
+        for (int u = u0; u < u1; ++u) {
+            const long long F = num_frames(p.offsets[u + 1] - p.offsets[u], p.frame_len, p.frame_step);
+            p.order[atomicAdd(&start[F < kEpPrepThreads - 1 ? (int)F : kEpPrepThreads - 1], 1)] = u;
+        }
+    }
 }
 
 // largest u with off[u] <= g
@@ -725,7 +754,7 @@ __global__ void __launch_bounds__(32 * kEpRobustWarps, 6) ep_decide_robust_kerne
     static_assert(kEpRobustWarps % 4 == 0, "the window results keep the request and the staging areas 16-byte aligned");
     GateRequest* req = reinterpret_cast<GateRequest*>(s_res + kEpRobustWarps);
     float* s_x = reinterpret_cast<float*>(req + 1);                                      // [kEpRobustWarps][kEpGateMaxLen + kGatePad], 16-byte aligned
-    const int u = blockIdx.x;
+    const int u = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
     const int64_t f0 = p.frame_off[u];
     const int F = (int)(p.frame_off[u + 1] - f0);
     const int16_t* x = p.pcm + p.offsets[u];
